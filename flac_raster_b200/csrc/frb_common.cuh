@@ -1,0 +1,96 @@
+// frb_common.cuh -- shared helpers for the sm_100a FLAC engine.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include "../../include/flacraster_b200.h"
+
+namespace frb {
+
+// Unity build: this header is included exactly once by flacraster_b200.cu.
+static thread_local char g_last_cuda_error[256] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+inline int cuda_fail(cudaError_t e, const char *what) {
+    snprintf(g_last_cuda_error, sizeof g_last_cuda_error, "%s: %s", what, cudaGetErrorString(e));
+    return FRB_ERR_CUDA;
+}
+
+#define FRB_CUDA(call)                                                    \
+    do {                                                                  \
+        cudaError_t e__ = (call);                                         \
+        if (e__ != cudaSuccess) return frb::cuda_fail(e__, #call);        \
+    } while (0)
+
+#define FRB_LAUNCH_CHECK(name)                                            \
+    do {                                                                  \
+        frb::g_launches.fetch_add(1, std::memory_order_relaxed);          \
+        cudaError_t e__ = cudaGetLastError();                             \
+        if (e__ != cudaSuccess) return frb::cuda_fail(e__, name);         \
+    } while (0)
+
+constexpr int kNumSMs = 148;   // B200
+
+// ---- big-endian / bit helpers -------------------------------------------
+__device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+
+// CRC tables live in constant memory (CRC-8 poly 0x07, CRC-16 poly 0x8005; RFC 9639 9.1.8 / 9.3)
+__constant__ uint8_t  c_crc8[256];
+__constant__ uint16_t c_crc16[256];
+
+// GF(2) helpers for CRC-16 combination: multiply a(x)*b(x) mod P, P = x^16+x^15+x^2+1
+__host__ __device__ __forceinline__ uint32_t gf16_mul(uint32_t a, uint32_t b) {
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        r = (r << 1) ^ ((r & 0x8000u) ? 0x18005u : 0u);
+        if (b & (0x8000u >> i)) r ^= a;
+    }
+    return r & 0xFFFFu;
+}
+// x^(8*nbytes) mod P
+__host__ __device__ __forceinline__ uint32_t gf16_xpow8(uint64_t nbytes) {
+    uint32_t result = 1;          // x^0
+    uint32_t base = 0x0100u;      // x^8
+    while (nbytes) {
+        if (nbytes & 1) result = gf16_mul(result, base);
+        base = gf16_mul(base, base);
+        nbytes >>= 1;
+    }
+    return result;
+}
+
+// UTF-8-style coded number length (frame number field)
+__host__ __device__ __forceinline__ int utf8_len(uint64_t v) {
+    return v < 0x80 ? 1 : v < 0x800 ? 2 : v < 0x10000 ? 3 : v < 0x200000 ? 4 : v < 0x4000000 ? 5 : v < 0x80000000ull ? 6 : 7;
+}
+
+__host__ __device__ __forceinline__ uint32_t blocksize_code(uint32_t bs, int *hint_bytes) {
+    *hint_bytes = 0;
+    switch (bs) {
+        case 192: return 1; case 576: return 2; case 1152: return 3; case 2304: return 4; case 4608: return 5;
+        case 256: return 8; case 512: return 9; case 1024: return 10; case 2048: return 11; case 4096: return 12;
+        case 8192: return 13; case 16384: return 14; case 32768: return 15;
+    }
+    if (bs <= 256) { *hint_bytes = 1; return 6; }
+    *hint_bytes = 2; return 7;
+}
+__host__ __device__ __forceinline__ uint32_t samplerate_code(uint32_t sr, int *hint_kind) {
+    *hint_kind = 0;
+    switch (sr) {
+        case 88200: return 1; case 176400: return 2; case 192000: return 3; case 8000: return 4;
+        case 16000: return 5; case 22050: return 6; case 24000: return 7; case 32000: return 8;
+        case 44100: return 9; case 48000: return 10; case 96000: return 11;
+    }
+    if (sr <= 255000 && sr % 1000 == 0) { *hint_kind = 1; return 12; }
+    if (sr <= 655350 && sr % 10 == 0) { *hint_kind = 3; return 14; }
+    if (sr <= 0xFFFF) { *hint_kind = 2; return 13; }
+    return 0;
+}
+__host__ __device__ __forceinline__ uint32_t bps_code(uint32_t bps) {
+    switch (bps) { case 8: return 1; case 12: return 2; case 16: return 4; case 20: return 5; case 24: return 6; case 32: return 7; }
+    return 0;
+}
+
+}  // namespace frb

@@ -1,0 +1,546 @@
+// frb_decode.cuh -- FLAC frame discovery + Rice decode + predictor restore (sm_100a).
+//
+// Replaces pyflac.FileDecoder.process (reference converter.py:181-182), i.e.
+// libFLAC's frame_sync_/read_frame_/read_residual_partitioned_rice_/
+// FLAC__lpc_restore_signal, for batches of independent fixed-blocksize streams.
+//
+// Kernels
+//   k_sync_scan     every byte position tested for 0xFFF8 + valid header + CRC-8;
+//                   hits are scattered by their coded frame number (no sort needed)
+//   k_decode_frames one thread per frame, warp = 32 frames in lock-step over the
+//                   sample index; decoded samples staged in a 32x33 smem tile
+//                   (doubles as the LPC history) and flushed as 128-byte rows
+//   k_crc16_frames  one warp per frame, lane-parallel CRC-16 with GF(2) combine
+//   k_stereo_fix    undo left/side, side/right, mid/side (2-channel streams only)
+#pragma once
+#include "frb_common.cuh"
+
+namespace frb {
+
+constexpr unsigned long long kNoPos = 0xFFFFFFFFFFFFFFFFull;
+
+struct DecStreamDev {
+    uint64_t byte_offset, byte_length, n_samples;
+    int64_t audio_base;
+    uint32_t sample_rate, frame_base, n_frames, pad;
+};
+
+struct FrameHdr {
+    uint32_t blocksize, sample_rate, ch_assign, bps, header_bytes;
+    uint64_t number;
+};
+
+__device__ __forceinline__ uint32_t rate_from_code(uint32_t c) {
+    switch (c) {
+        case 1: return 88200; case 2: return 176400; case 3: return 192000; case 4: return 8000;
+        case 5: return 16000; case 6: return 22050; case 7: return 24000; case 8: return 32000;
+        case 9: return 44100; case 10: return 48000; case 11: return 96000;
+    }
+    return 0;
+}
+
+// Parse + CRC-8-check a candidate frame header at p (avail bytes readable). Fixed blocksize only.
+__device__ inline bool parse_frame_header(const uint8_t *p, uint64_t avail, uint32_t stream_rate,
+                                          uint32_t stream_bps, FrameHdr *h) {
+    if (avail < 6) return false;
+    if (p[0] != 0xFF || p[1] != 0xF8) return false;
+    uint32_t b2 = p[2], b3 = p[3];
+    uint32_t bsc = b2 >> 4, src = b2 & 15, chc = b3 >> 4, bpc = (b3 >> 1) & 7;
+    if ((b3 & 1) || bsc == 0 || src == 15 || bpc == 3 || chc > 10) return false;
+    uint32_t i = 4;
+    uint32_t b0 = p[i++];
+    uint64_t num; int extra;
+    if (b0 < 0x80) { num = b0; extra = 0; }
+    else if ((b0 & 0xE0) == 0xC0) { num = b0 & 0x1F; extra = 1; }
+    else if ((b0 & 0xF0) == 0xE0) { num = b0 & 0x0F; extra = 2; }
+    else if ((b0 & 0xF8) == 0xF0) { num = b0 & 0x07; extra = 3; }
+    else if ((b0 & 0xFC) == 0xF8) { num = b0 & 0x03; extra = 4; }
+    else if ((b0 & 0xFE) == 0xFC) { num = b0 & 0x01; extra = 5; }
+    else return false;
+    if (avail < (uint64_t)(i + extra + 5)) return false;
+    for (int k = 0; k < extra; k++) {
+        uint32_t b = p[i++];
+        if ((b & 0xC0) != 0x80) return false;
+        num = (num << 6) | (b & 0x3F);
+    }
+    h->number = num;
+    if (bsc == 1) h->blocksize = 192;
+    else if (bsc <= 5) h->blocksize = 576u << (bsc - 2);
+    else if (bsc == 6) h->blocksize = (uint32_t)p[i++] + 1;
+    else if (bsc == 7) { h->blocksize = (((uint32_t)p[i] << 8) | p[i + 1]) + 1; i += 2; }
+    else h->blocksize = 256u << (bsc - 8);
+    if (src == 0) h->sample_rate = stream_rate;
+    else if (src <= 11) h->sample_rate = rate_from_code(src);
+    else if (src == 12) h->sample_rate = (uint32_t)p[i++] * 1000u;
+    else if (src == 13) { h->sample_rate = ((uint32_t)p[i] << 8) | p[i + 1]; i += 2; }
+    else { h->sample_rate = (((uint32_t)p[i] << 8) | p[i + 1]) * 10u; i += 2; }
+    h->ch_assign = chc;
+    const uint32_t bt[8] = {0, 8, 12, 0, 16, 20, 24, 32};
+    h->bps = bpc == 0 ? stream_bps : bt[bpc];
+    uint8_t crc = 0;
+    for (uint32_t k = 0; k < i; k++) crc = c_crc8[crc ^ p[k]];
+    if (crc != p[i]) return false;
+    h->header_bytes = i + 1;
+    return true;
+}
+
+__global__ void k_fill_u64(unsigned long long *p, uint64_t n, unsigned long long v) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// grid (chunks, n_streams); every thread tests 4 byte positions per step.
+__global__ void __launch_bounds__(256)
+k_sync_scan(const uint8_t *__restrict__ bytes, const DecStreamDev *__restrict__ streams, uint32_t channels,
+            uint32_t bps, uint32_t blocksize, unsigned long long *__restrict__ frame_pos,
+            unsigned long long *__restrict__ probe /* optional: [0]=max key, [1]=count */) {
+    const DecStreamDev st = streams[blockIdx.y];
+    const uint64_t start = st.byte_offset, end = st.byte_offset + st.byte_length;
+    const uint64_t w0 = start >> 2, w1 = (end + 3) >> 2;
+    const uint32_t *words = (const uint32_t *)bytes;   // cudaMalloc'd base is 256B aligned
+    for (uint64_t w = w0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < w1;
+         w += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t a = __ldg(words + w), b = __ldg(words + w + 1);     // little-endian words: byte k = (a >> 8k)
+        // bytes b[0..4]
+        uint64_t v = (uint64_t)a | ((uint64_t)b << 32);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t two = (uint32_t)(v >> (8 * k)) & 0xFFFFu;       // byte k low, byte k+1 high
+            if (two != 0xF8FFu) continue;
+            uint64_t pos = w * 4 + k;
+            if (pos < start || pos + 8 > end) continue;
+            FrameHdr h;
+            if (!parse_frame_header(bytes + pos, end - pos, st.sample_rate, bps, &h)) continue;
+            if (h.bps != bps || h.sample_rate != st.sample_rate) continue;
+            uint32_t nch = h.ch_assign < 8 ? h.ch_assign + 1 : 2;
+            if (nch != channels || h.blocksize > blocksize) continue;
+            if (probe) {
+                atomicMax(&probe[0], (h.number << 20) | h.blocksize);
+                atomicAdd(&probe[1], 1ull);
+            }
+            if (!frame_pos) continue;
+            if (h.number >= st.n_frames) continue;
+            uint64_t expect = (h.number + 1 < st.n_frames) ? blocksize : (st.n_samples - h.number * blocksize);
+            if (h.blocksize != expect) continue;
+            atomicMin(&frame_pos[st.frame_base + h.number], (unsigned long long)pos);
+        }
+    }
+}
+
+// ---- per-thread MSB-first bit reader over global memory ----------------------
+struct BitReader {
+    const uint32_t *wp;     // next aligned word to load
+    const uint32_t *wend;   // first word that may not be read (reads past it yield all-ones, which ends any unary run)
+    uint64_t buf;           // MSB-aligned bit window
+    int avail;              // valid bits in buf
+    int64_t loaded_bits;    // bits loaded since byte0 (for position bookkeeping)
+    __device__ __forceinline__ void init(const uint8_t *base, uint64_t byte_pos, uint64_t byte_end) {
+        uint64_t addr = byte_pos;
+        wp = (const uint32_t *)base + (addr >> 2);
+        wend = (const uint32_t *)base + ((byte_end + 3) >> 2) + 1;
+        int skip = (int)(addr & 3) * 8;
+        uint32_t a = bswap32(__ldg(wp)), b = bswap32(__ldg(wp + 1));
+        wp += 2;
+        buf = (((uint64_t)a << 32) | b) << skip;
+        avail = 64 - skip;
+        loaded_bits = 64 - skip;
+    }
+    __device__ __forceinline__ void refill() {        // afterwards avail >= 33
+        if (avail <= 32) {
+            const uint32_t w = wp < wend ? bswap32(__ldg(wp)) : 0xFFFFFFFFu;
+            wp++;
+            buf |= (uint64_t)w << (32 - avail);
+            avail += 32;
+            loaded_bits += 32;
+        }
+    }
+    __device__ __forceinline__ uint32_t get(int n) {  // n in 0..32
+        refill();
+        uint32_t v = n ? (uint32_t)(buf >> (64 - n)) : 0u;
+        buf <<= n; avail -= n;
+        return v;
+    }
+    __device__ __forceinline__ int32_t get_signed(int n) {   // n in 0..33 (side channel of 32-bps)
+        if (n == 0) return 0;
+        if (n > 32) { (void)get(n - 32); n = 32; }            // value fits 32 bits for our data; top bits are sign copies
+        uint32_t v = get(n);
+        uint32_t m = 1u << (n - 1);
+        return (int32_t)((v ^ m) - m);
+    }
+    __device__ __forceinline__ uint32_t unary() {             // zeros before the next 1
+        uint32_t q = 0;
+        while (true) {
+            refill();
+            uint32_t hi = (uint32_t)(buf >> 32);
+            if (hi) { int z = __clz(hi); q += z; buf <<= (z + 1); avail -= (z + 1); return q; }
+            q += 32; buf <<= 32; avail -= 32;
+        }
+    }
+    __device__ __forceinline__ int64_t consumed_bits() const { return loaded_bits - avail; }
+};
+
+constexpr int kDecWarps = 4;
+constexpr int kTileStride = 33;
+
+// status words: 0 frames_missing, 1 crc16_errors, 2 parse_errors, 3 frames_decoded, 4 order_overflow
+template <int MAXORD>
+__global__ void __launch_bounds__(kDecWarps * 32)
+k_decode_frames(const uint8_t *__restrict__ bytes, const DecStreamDev *__restrict__ streams, uint32_t n_streams,
+                uint32_t channels, uint32_t bps, uint32_t blocksize, uint32_t total_frames,
+                const unsigned long long *__restrict__ frame_pos, int32_t *__restrict__ audio,
+                uint8_t *__restrict__ frame_chassign, uint32_t *__restrict__ status) {
+    __shared__ int32_t s_tile[kDecWarps][32 * kTileStride];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int32_t *tile = s_tile[warp];
+    int32_t *row = tile + lane * kTileStride;
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+
+    // locate stream by binary search over frame_base
+    bool alive = f < total_frames;
+    uint32_t n = 0, ch_assign = 0;
+    int64_t dst0 = 0, chan_stride = 0;
+    uint64_t fstart = 0, fend = 0;
+    if (alive) {
+        uint32_t lo = 0, hi = n_streams - 1;
+        while (lo < hi) {
+            uint32_t mid = (lo + hi + 1) >> 1;
+            if (streams[mid].frame_base <= f) lo = mid; else hi = mid - 1;
+        }
+        const DecStreamDev st = streams[lo];
+        uint32_t k = f - st.frame_base;
+        unsigned long long p0 = frame_pos[f];
+        unsigned long long p1 = (k + 1 < st.n_frames) ? frame_pos[f + 1] : (st.byte_offset + st.byte_length);
+        n = (k + 1 < st.n_frames) ? blocksize : (uint32_t)(st.n_samples - (uint64_t)k * blocksize);
+        dst0 = st.audio_base + (int64_t)k * blocksize;
+        chan_stride = (int64_t)st.n_samples;
+        if (p0 == kNoPos || p1 == kNoPos || p1 <= p0) { alive = false; atomicAdd(&status[0], 1u); }
+        fstart = p0; fend = p1;
+    }
+    BitReader br;
+    bool err = false;
+    uint32_t hdr_bytes = 0;
+    if (alive) {
+        FrameHdr h;
+        if (!parse_frame_header(bytes + fstart, fend - fstart, 0, bps, &h)) { err = true; }
+        else {
+            ch_assign = h.ch_assign;
+            br.init(bytes, fstart + h.header_bytes, fend);
+            hdr_bytes = h.header_bytes;
+            frame_chassign[f] = (uint8_t)h.ch_assign;
+        }
+    }
+    if (!alive || err) { br.wp = (const uint32_t *)bytes; br.wend = br.wp; br.buf = 0; br.avail = 64; br.loaded_bits = 64; }
+    const uint32_t n_eff = (alive && !err) ? n : 0;
+
+    int32_t cf[MAXORD];
+    for (uint32_t c = 0; c < channels; c++) {
+        // per-subframe state
+        uint32_t type = 0, order = 0, wasted = 0, sbps = bps, k = 0, part_left = 0, part_n = 0;
+        int shift = 0; bool escape = false; uint32_t raw_bits = 0; int plen = 4;
+        int32_t const_val = 0;
+#pragma unroll
+        for (int j = 0; j < MAXORD; j++) cf[j] = 0;
+        if ((ch_assign == 8 && c == 1) || (ch_assign == 9 && c == 0) || (ch_assign == 10 && c == 1)) sbps++;
+
+        for (uint32_t chunk = 0; chunk * 32 < blocksize; chunk++) {
+            for (uint32_t j = 0; j < 32; j++) {
+                const uint32_t i = chunk * 32 + j;
+                if (i < n_eff && !err) {
+                    if (i == 0) {
+                        uint32_t hd = br.get(8);
+                        if (hd & 0x80) err = true;
+                        uint32_t t = (hd >> 1) & 0x3F;
+                        if (hd & 1) wasted = br.unary() + 1;
+                        if (wasted >= sbps) { err = true; wasted = 0; }
+                        sbps -= wasted;
+                        if (t == 0) { type = 0; order = 0; const_val = br.get_signed((int)sbps); }
+                        else if (t == 1) { type = 1; order = n; }
+                        else if (t >= 8 && t <= 12) {
+                            type = 2; order = t - 8; shift = 0;
+                            if (order >= 1) { cf[0] = order == 1 ? 1 : order == 2 ? 2 : order == 3 ? 3 : 4; }
+                            if (MAXORD > 1 && order >= 2) cf[1] = order == 2 ? -1 : order == 3 ? -3 : -6;
+                            if (MAXORD > 2 && order >= 3) cf[2] = order == 3 ? 1 : 4;
+                            if (MAXORD > 3 && order >= 4) cf[3] = -1;
+                        }
+                        else if (t >= 32) { type = 3; order = t - 31; if (order > (uint32_t)MAXORD) { err = true; atomicAdd(&status[4], 1u); order = 0; type = 0; } }
+                        else err = true;
+                        if (order > n && type != 1) err = true;
+                    }
+                    int32_t val;
+                    if (type == 0) val = const_val;
+                    else if (i < order) val = br.get_signed((int)sbps);
+                    else {
+                        if (i == order) {
+                            if (type == 3) {
+                                uint32_t prec = br.get(4) + 1;
+                                if (prec == 16) err = true;
+                                shift = (int)br.get(5);
+                                if (shift & 16) err = true;     // negative shift is invalid
+#pragma unroll
+                                for (int q = 0; q < MAXORD; q++)
+                                    if ((uint32_t)q < order) cf[q] = br.get_signed((int)prec);
+                            }
+                            uint32_t m = br.get(2);
+                            if (m > 1) err = true;
+                            plen = m ? 5 : 4;
+                            uint32_t po = br.get(4);
+                            part_n = n >> po;
+                            if (po > 0 && ((n & ((1u << po) - 1)) || part_n < order)) err = true;
+                            part_left = part_n - order;
+                            if (part_n < order) part_left = 0;
+                            k = br.get(plen);
+                            escape = (k == (plen == 5 ? 31u : 15u));
+                            if (escape) raw_bits = br.get(5);
+                            // an empty first partition (n>>po == order) moves straight to the next
+                            while (part_left == 0 && !err) {
+                                k = br.get(plen);
+                                escape = (k == (plen == 5 ? 31u : 15u));
+                                if (escape) raw_bits = br.get(5);
+                                part_left = part_n;
+                                if (part_n == 0) err = true;
+                            }
+                        }
+                        int32_t r;
+                        if (escape) r = br.get_signed((int)raw_bits);
+                        else {
+                            uint32_t q = br.unary();
+                            uint32_t u = (q << k) | br.get((int)k);
+                            r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
+                        }
+                        if (--part_left == 0 && i + 1 < n) {
+                            k = br.get(plen);
+                            escape = (k == (plen == 5 ? 31u : 15u));
+                            if (escape) raw_bits = br.get(5);
+                            part_left = part_n;
+                        }
+                        int64_t acc = 0;
+#pragma unroll
+                        for (int q = 0; q < MAXORD; q++)
+                            acc += (int64_t)cf[q] * (int64_t)row[(i - 1 - q) & 31];
+                        val = r + (int32_t)(acc >> shift);
+                    }
+                    row[i & 31] = val;
+                }
+            }
+            __syncwarp();
+            // flush 32 rows x 32 samples, one 128-byte row per store
+            {
+                const int64_t my_dst = dst0 + (int64_t)c * chan_stride;
+                const uint32_t idx = chunk * 32 + lane;
+#pragma unroll 4
+                for (int r = 0; r < 32; r++) {
+                    int64_t d = __shfl_sync(0xFFFFFFFFu, my_dst, r);
+                    uint32_t nr = __shfl_sync(0xFFFFFFFFu, n_eff, r);
+                    uint32_t wr = __shfl_sync(0xFFFFFFFFu, wasted, r);
+                    if (idx < nr) audio[d + idx] = (int32_t)((uint32_t)tile[r * kTileStride + lane] << wr);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (alive) {
+        if (!err) {
+            // frame must end (after byte padding) exactly 2 bytes before the next frame
+            int64_t bits = br.consumed_bits();
+            // consumed_bits counts from the header end
+            const uint64_t end_byte = fstart + hdr_bytes + (uint64_t)((bits + 7) >> 3);
+            if (end_byte + 2 != fend) err = true;
+        }
+        if (err) atomicAdd(&status[2], 1u); else atomicAdd(&status[3], 1u);
+    }
+}
+
+// one warp per frame: CRC-16 over [pos, next_pos-2) must equal the trailing 2 bytes
+__global__ void __launch_bounds__(256)
+k_crc16_frames(const uint8_t *__restrict__ bytes, const DecStreamDev *__restrict__ streams, uint32_t n_streams,
+               uint32_t total_frames, const unsigned long long *__restrict__ frame_pos, uint32_t *__restrict__ status) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (f >= total_frames) return;
+    uint32_t lo = 0, hi = n_streams - 1;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (streams[mid].frame_base <= f) lo = mid; else hi = mid - 1;
+    }
+    const DecStreamDev st = streams[lo];
+    uint32_t k = f - st.frame_base;
+    unsigned long long p0 = frame_pos[f];
+    unsigned long long p1 = (k + 1 < st.n_frames) ? frame_pos[f + 1] : (st.byte_offset + st.byte_length);
+    if (p0 == kNoPos || p1 == kNoPos || p1 < p0 + 3) return;     // counted as missing by the decoder
+    const uint64_t len = p1 - p0 - 2;
+    const uint64_t seg = (len + 31) / 32;
+    uint64_t a = (uint64_t)lane * seg, b = a + seg;
+    if (a > len) a = len;
+    if (b > len) b = len;
+    uint32_t crc = 0;
+    for (uint64_t i = a; i < b; i++) crc = ((crc << 8) & 0xFFFFu) ^ c_crc16[(crc >> 8) ^ bytes[p0 + i]];
+    crc = gf16_mul(crc, gf16_xpow8(len - b));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) crc ^= __shfl_xor_sync(0xFFFFFFFFu, crc, o);
+    if (lane == 0) {
+        uint32_t want = ((uint32_t)bytes[p1 - 2] << 8) | bytes[p1 - 1];
+        if (crc != want) atomicAdd(&status[1], 1u);
+    }
+}
+
+// one CTA per frame; only frames with ch_assign 8/9/10 do work
+__global__ void __launch_bounds__(128)
+k_stereo_fix(const DecStreamDev *__restrict__ streams, uint32_t n_streams, uint32_t blocksize, uint32_t total_frames,
+             const uint8_t *__restrict__ frame_chassign, const unsigned long long *__restrict__ frame_pos,
+             int32_t *__restrict__ audio) {
+    const uint32_t f = blockIdx.x;
+    if (f >= total_frames || frame_pos[f] == kNoPos) return;
+    const uint32_t ca = frame_chassign[f];
+    if (ca < 8 || ca > 10) return;
+    uint32_t lo = 0, hi = n_streams - 1;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (streams[mid].frame_base <= f) lo = mid; else hi = mid - 1;
+    }
+    const DecStreamDev st = streams[lo];
+    uint32_t k = f - st.frame_base;
+    uint32_t n = (k + 1 < st.n_frames) ? blocksize : (uint32_t)(st.n_samples - (uint64_t)k * blocksize);
+    int32_t *c0 = audio + st.audio_base + (int64_t)k * blocksize;
+    int32_t *c1 = c0 + st.n_samples;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        int64_t a = c0[i], b = c1[i];
+        if (ca == 8) c1[i] = (int32_t)(a - b);
+        else if (ca == 9) c0[i] = (int32_t)(a + b);
+        else {
+            int64_t m = (a << 1) | (b & 1);
+            c0[i] = (int32_t)((m + b) >> 1);
+            c1[i] = (int32_t)((m - b) >> 1);
+        }
+    }
+}
+
+struct DecWorkspace {
+    DecStreamDev *streams;
+    unsigned long long *frame_pos;
+    uint8_t *chassign;
+};
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+static inline size_t dec_ws_layout(uint32_t n_streams, uint64_t total_frames, void *base, DecWorkspace *w) {
+    size_t off = 0;
+    uint8_t *b = (uint8_t *)base;
+    if (w) w->streams = (DecStreamDev *)(b + off);
+    off += align256(sizeof(DecStreamDev) * (size_t)n_streams);
+    if (w) w->frame_pos = (unsigned long long *)(b + off);
+    off += align256(8 * (size_t)(total_frames + 1));
+    if (w) w->chassign = b + off;
+    off += align256((size_t)total_frames + 1);
+    return off;
+}
+
+}  // namespace frb
+
+extern "C" int frb_decode_workspace_size(const frb_decode_params *p, uint64_t total_frames, size_t *bytes) {
+    if (!p || !bytes) return FRB_ERR_INVALID_ARG;
+    *bytes = frb::dec_ws_layout(p->n_streams, total_frames, nullptr, nullptr);
+    return FRB_OK;
+}
+
+extern "C" int frb_decode_batch(const frb_decode_params *p, const frb_decode_stream *h_streams,
+                                const uint8_t *d_bytes, uint64_t total_frames, int32_t *d_audio,
+                                void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream) {
+    using namespace frb;
+    if (!p || !h_streams || !d_bytes || !d_audio || !d_workspace || !d_status) return FRB_ERR_INVALID_ARG;
+    if (p->n_streams == 0 || p->channels < 1 || p->channels > FRB_MAX_CHANNELS || p->blocksize < 16 ||
+        p->blocksize > 65535 || p->bps < 4 || p->bps > 32) return FRB_ERR_INVALID_ARG;
+    if (total_frames == 0 || total_frames > 0x7FFFFFFFull) return FRB_ERR_INVALID_ARG;
+    int rc = ensure_tables_impl();
+    if (rc) return rc;
+    DecWorkspace w;
+    if (dec_ws_layout(p->n_streams, total_frames, d_workspace, &w) > workspace_bytes) return FRB_ERR_OVERFLOW;
+    cudaStream_t s = (cudaStream_t)stream;
+    // stream table (host -> device). Pageable source: staged by the runtime before return.
+    std::vector<DecStreamDev> hs(p->n_streams);
+    uint64_t max_len = 0, frames = 0;
+    for (uint32_t i = 0; i < p->n_streams; i++) {
+        const frb_decode_stream &a = h_streams[i];
+        DecStreamDev d;
+        d.byte_offset = a.byte_offset; d.byte_length = a.byte_length; d.n_samples = a.n_samples;
+        d.audio_base = a.audio_base; d.sample_rate = a.sample_rate; d.frame_base = a.frame_base;
+        d.n_frames = (uint32_t)((a.n_samples + p->blocksize - 1) / p->blocksize); d.pad = 0;
+        if (a.frame_base != frames) return FRB_ERR_INVALID_ARG;
+        frames += d.n_frames;
+        if (a.byte_length > max_len) max_len = a.byte_length;
+        hs[i] = d;
+    }
+    if (frames != total_frames) return FRB_ERR_INVALID_ARG;
+    FRB_CUDA(cudaMemcpyAsync(w.streams, hs.data(), sizeof(DecStreamDev) * hs.size(), cudaMemcpyHostToDevice, s));
+    FRB_CUDA(cudaStreamSynchronize(s));   // hs is a stack-local staging vector
+    FRB_CUDA(cudaMemsetAsync(d_status, 0, 8 * sizeof(uint32_t), s));
+    FRB_CUDA(cudaMemsetAsync(w.chassign, 0, (size_t)total_frames + 1, s));
+    k_fill_u64<<<grid_for(total_frames + 1, 256 * 4, kNumSMs * 4), 256, 0, s>>>(w.frame_pos, total_frames + 1, kNoPos);
+    FRB_LAUNCH_CHECK("k_fill_u64");
+    {
+        uint64_t words = max_len / 4 + 2;
+        uint32_t gx = (uint32_t)((words + 256 * 8 - 1) / (256 * 8));
+        uint32_t cap = (kNumSMs * 16 + p->n_streams - 1) / p->n_streams;
+        if (gx > cap) gx = cap;
+        if (gx < 1) gx = 1;
+        dim3 grid(gx, p->n_streams);
+        k_sync_scan<<<grid, 256, 0, s>>>(d_bytes, w.streams, p->channels, p->bps, p->blocksize, w.frame_pos, nullptr);
+        FRB_LAUNCH_CHECK("k_sync_scan");
+    }
+    {
+        uint32_t threads = kDecWarps * 32;
+        uint32_t grid = (uint32_t)((total_frames + threads - 1) / threads);
+        const bool wide = p->reserved > 12;
+        if (!wide)
+            k_decode_frames<12><<<grid, threads, 0, s>>>(d_bytes, w.streams, p->n_streams, p->channels, p->bps, p->blocksize,
+                                                        (uint32_t)total_frames, w.frame_pos, d_audio, w.chassign, d_status);
+        else
+            k_decode_frames<32><<<grid, threads, 0, s>>>(d_bytes, w.streams, p->n_streams, p->channels, p->bps, p->blocksize,
+                                                        (uint32_t)total_frames, w.frame_pos, d_audio, w.chassign, d_status);
+        FRB_LAUNCH_CHECK("k_decode_frames");
+    }
+    if (p->verify_crc16) {
+        uint64_t threads = total_frames * 32;
+        k_crc16_frames<<<(uint32_t)((threads + 255) / 256), 256, 0, s>>>(d_bytes, w.streams, p->n_streams,
+                                                                        (uint32_t)total_frames, w.frame_pos, d_status);
+        FRB_LAUNCH_CHECK("k_crc16_frames");
+    }
+    if (p->channels == 2) {
+        k_stereo_fix<<<(uint32_t)total_frames, 128, 0, s>>>(w.streams, p->n_streams, p->blocksize, (uint32_t)total_frames,
+                                                           w.chassign, w.frame_pos, d_audio);
+        FRB_LAUNCH_CHECK("k_stereo_fix");
+    }
+    return FRB_OK;
+}
+
+extern "C" int frb_probe_stream(const uint8_t *d_bytes, uint64_t byte_offset, uint64_t byte_length,
+                                uint32_t channels, uint32_t bps, uint32_t blocksize, uint32_t sample_rate,
+                                uint64_t *n_frames, uint64_t *n_samples, void *stream) {
+    using namespace frb;
+    if (!d_bytes || !n_frames || !n_samples || !byte_length) return FRB_ERR_INVALID_ARG;
+    int rc = ensure_tables_impl();
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    DecStreamDev hs;
+    hs.byte_offset = byte_offset; hs.byte_length = byte_length; hs.n_samples = 0; hs.audio_base = 0;
+    hs.sample_rate = sample_rate; hs.frame_base = 0; hs.n_frames = 0; hs.pad = 0;
+    uint8_t *d_tmp = nullptr;
+    FRB_CUDA(cudaMalloc(&d_tmp, 512));
+    DecStreamDev *d_st = (DecStreamDev *)d_tmp;
+    unsigned long long *d_probe = (unsigned long long *)(d_tmp + 256);
+    cudaError_t e = cudaMemcpyAsync(d_st, &hs, sizeof hs, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_probe, 0, 16, s);
+    if (e != cudaSuccess) { cudaFree(d_tmp); return cuda_fail(e, "probe setup"); }
+    uint64_t words = byte_length / 4 + 2;
+    uint32_t gx = (uint32_t)((words + 256 * 8 - 1) / (256 * 8));
+    if (gx > (uint32_t)kNumSMs * 16) gx = kNumSMs * 16;
+    k_sync_scan<<<dim3(gx, 1), 256, 0, s>>>(d_bytes, d_st, channels, bps, blocksize, nullptr, d_probe);
+    g_launches.fetch_add(1);
+    unsigned long long h_probe[2] = {0, 0};
+    e = cudaMemcpyAsync(h_probe, d_probe, 16, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d_tmp);
+    if (e != cudaSuccess) return cuda_fail(e, "probe");
+    if (h_probe[1] == 0) return FRB_ERR_BAD_STREAM;
+    uint64_t last_no = h_probe[0] >> 20, last_bs = h_probe[0] & 0xFFFFF;
+    if (h_probe[1] != last_no + 1) return FRB_ERR_BAD_STREAM;
+    *n_frames = last_no + 1;
+    *n_samples = last_no * blocksize + last_bs;
+    return FRB_OK;
+}

@@ -1,0 +1,1012 @@
+// frb_encode.cuh -- FLAC subframe analysis, Rice coding, bit packing and frame assembly (sm_100a).
+//
+// Replaces pyflac.StreamEncoder.process/finish (reference converter.py:139-154,
+// spatial_encoder.py:291-304), i.e. libFLAC 1.4.3's process_subframe_ pipeline,
+// for batches of independent streams.  The decision procedure follows libFLAC's
+// preset table (docs/sonos-pyflac.txt:6926-6934): wasted bits, CONSTANT/VERBATIM,
+// FIXED order by abs-error sums, windowed autocorrelation -> Levinson-Durbin ->
+// order estimate -> quantisation, Rice partition order/parameter by the abs-sum
+// estimate.  Bit lengths are exact; a subframe that would exceed VERBATIM falls
+// back to VERBATIM.
+//
+// Kernels
+//   k_encode_subframes  one 256-thread CTA per (frame, channel): 16 samples per
+//                       thread, samples/residuals in shared memory, warp-shuffle
+//                       reductions, CTA prefix scan for bit offsets, per-thread
+//                       bit assembly, 128-bit coalesced slot stores
+//   k_frame_sizes       header + subframe bits -> bytes per frame
+//   k_stream_scan       per-stream exclusive scan of frame sizes (CTA scan)
+//   k_emit_frames       one CTA per frame: header + CRC-8, funnel-shift
+//                       concatenation of subframe slots, padding, parallel CRC-16
+#pragma once
+#include "frb_common.cuh"
+
+namespace frb {
+
+constexpr int kEncThreads = 256;
+constexpr int kSPT = 16;                 // samples per thread at blocksize 4096
+constexpr int kMaxBlock = kEncThreads * kSPT;   // 4096
+constexpr int kMaxOrd = 12;              // libFLAC presets never exceed 12
+constexpr int kMaxPO = 8;
+
+struct EncStreamDev {
+    uint64_t n_samples;
+    int64_t audio_base;
+    uint64_t out_offset;
+    uint32_t sample_rate, frame_base, n_frames, pad;
+};
+
+struct LevelCfg { int max_lpc_order, max_po, windows; };
+__host__ __device__ __forceinline__ LevelCfg level_cfg(uint32_t level) {
+    // docs/sonos-pyflac.txt:6926-6934
+    switch (level) {
+        case 0: case 1: case 2: return {0, 3, 1};
+        case 3: return {6, 4, 1};
+        case 4: return {8, 4, 1};
+        case 5: return {8, 5, 1};
+        case 6: return {8, 6, 2};
+        case 7: return {12, 6, 2};
+        default: return {12, 6, 3};
+    }
+}
+__host__ __device__ __forceinline__ uint32_t qlp_precision_for(uint32_t bps, uint32_t blocksize) {
+    if (bps < 16) { uint32_t p = 2 + bps / 2; return p < 5 ? 5 : p; }
+    if (bps == 16) return blocksize <= 192 ? 7 : blocksize <= 384 ? 8 : blocksize <= 576 ? 9 : blocksize <= 1152 ? 10 : blocksize <= 2304 ? 11 : blocksize <= 4608 ? 12 : 13;
+    return blocksize <= 384 ? 13 : blocksize <= 1152 ? 14 : 15;
+}
+__host__ __device__ __forceinline__ uint32_t slot_words_for(uint32_t blocksize, uint32_t bps) {
+    // VERBATIM upper bound: 8 + 32 (wasted unary) + n*bps bits, rounded up to 16 bytes (+1 word for funnel reads)
+    uint32_t bits = 8 + 32 + blocksize * bps;
+    uint32_t words = (bits + 31) / 32 + 1;
+    return (words + 3) & ~3u;
+}
+
+struct Choice {
+    int type;            // 0 CONSTANT 1 VERBATIM 2 FIXED 3 LPC
+    int order, wasted, precision, shift, method, po;
+    uint32_t bits;       // estimated bits (decision metric)
+    int32_t coefs[kMaxOrd];
+    uint8_t params[1 << kMaxPO];
+};
+
+struct EncShared {
+    // [resA | x | resB]: the bit buffer aliases x plus the non-best residual buffer
+    int32_t buf[3][kMaxBlock];
+    unsigned long long psum[1 << (kMaxPO + 1)];
+    uint32_t pbits[1 << (kMaxPO + 1)];
+    uint8_t pk[1 << (kMaxPO + 1)];
+    unsigned long long red_u64[8][8];
+    double red_f64[8][kMaxOrd + 1];
+    double autoc[kMaxOrd + 1], autoc_root[kMaxOrd + 1];
+    double lp_err[kMaxOrd];
+    float lp[kMaxOrd][kMaxOrd];
+    uint32_t scan[kEncThreads / 32];
+    uint32_t order_bits[kMaxPO + 1];
+    Choice best, cand;
+    int best_buf;          // 0 -> resA holds best residual, 2 -> resB
+    int flag, flag2;
+    uint32_t misc[8];
+};
+
+// ---- block reductions -------------------------------------------------------
+__device__ __forceinline__ uint32_t block_or(uint32_t v, EncShared &S) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) S.scan[warp] = v;
+    __syncthreads();
+    uint32_t r = 0;
+#pragma unroll
+    for (int w = 0; w < kEncThreads / 32; w++) r |= S.scan[w];
+    return r;
+}
+
+template <int N>
+__device__ __forceinline__ void block_sum_u64(unsigned long long (&v)[N], EncShared &S) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < N; k++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xFFFFFFFFu, v[k], o);
+    __syncthreads();
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < N; k++) S.red_u64[warp][k] = v[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        unsigned long long s = 0;
+#pragma unroll
+        for (int w = 0; w < kEncThreads / 32; w++) s += S.red_u64[w][k];
+        v[k] = s;
+    }
+}
+
+// exclusive prefix sum over the CTA; returns this thread's offset, total in *total
+__device__ __forceinline__ uint32_t block_exscan(uint32_t v, uint32_t *total, EncShared &S) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();
+    if (lane == 31) S.scan[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kEncThreads / 32; w++) {
+        uint32_t s = S.scan[w];
+        if (w < warp) base += s;
+        tot += s;
+    }
+    *total = tot;
+    return base + inc - v;
+}
+
+// ---- thread-local bit writer into a zeroed shared word buffer (MSB first) ----
+struct SmemBitWriter {
+    uint32_t *buf;
+    uint32_t pos;      // absolute bit position
+    uint32_t cur;      // pending bits of word pos>>5
+    __device__ __forceinline__ void init(uint32_t *b, uint32_t bitpos) { buf = b; pos = bitpos; cur = 0; }
+    __device__ __forceinline__ void flush_word(uint32_t idx) { if (cur) atomicOr(&buf[idx], cur); cur = 0; }
+    __device__ __forceinline__ void put(uint32_t value, uint32_t nbits) {   // nbits 0..32, value < 2^nbits
+        if (nbits == 0) return;
+        const uint32_t room = 32 - (pos & 31);
+        const uint32_t idx = pos >> 5;
+        if (nbits < room) { cur |= value << (room - nbits); }
+        else {
+            cur |= value >> (nbits - room);
+            flush_word(idx);
+            const uint32_t rest = nbits - room;
+            if (rest) cur = value << (32 - rest);
+        }
+        pos += nbits;
+    }
+    __device__ __forceinline__ void zeros(uint32_t q) {
+        if (q == 0) return;
+        const uint32_t idx = pos >> 5;
+        pos += q;
+        if ((pos >> 5) != idx) flush_word(idx);
+    }
+    __device__ __forceinline__ void finish() { flush_word(pos >> 5); }
+};
+
+__device__ __forceinline__ uint32_t zigzag(int32_t v) { return ((uint32_t)v << 1) ^ (uint32_t)(v >> 31); }
+__device__ __forceinline__ int ilog2_u32(uint32_t v) { return 31 - __clz(v); }
+__device__ __forceinline__ int ilog2_u64(unsigned long long v) { return 63 - __clzll(v); }
+
+__device__ __forceinline__ uint32_t rice_bits_estimate(uint32_t k, uint32_t n, unsigned long long sum) {
+    unsigned long long v = 4ull + (unsigned long long)(1 + k) * n + (k ? (sum >> (k - 1)) : (sum << 1)) - (n >> 1);
+    return v > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)v;
+}
+
+__device__ __forceinline__ uint32_t max_po_for(uint32_t limit, uint32_t n, uint32_t order) {
+    uint32_t m = n ? (uint32_t)(__ffs((int)n) - 1) : 0;
+    if (m > limit) m = limit;
+    if (m > (uint32_t)kMaxPO) m = kMaxPO;
+    while (m > 0 && (n >> m) <= order) m--;
+    return m;
+}
+
+// Compute the residual of predictor (coefs, order, shift) into res[i] (indexed by sample), for this
+// thread's samples.  Returns false if any residual does not fit in int32 (or is INT32_MIN).
+__device__ __forceinline__ bool compute_residual(const int32_t *x, int32_t *res, uint32_t n, int order, int shift,
+                                                 const int32_t *coefs /*smem, kMaxOrd padded*/) {
+    const uint32_t i0 = threadIdx.x * kSPT;
+    int32_t xv[kSPT + kMaxOrd];
+#pragma unroll
+    for (int j = 0; j < kSPT + kMaxOrd; j++) {
+        int idx = (int)i0 - kMaxOrd + j;
+        xv[j] = (idx >= 0 && (uint32_t)idx < n) ? x[idx] : 0;
+    }
+    int32_t cf[kMaxOrd];
+#pragma unroll
+    for (int j = 0; j < kMaxOrd; j++) cf[j] = coefs[j];
+    bool ok = true;
+#pragma unroll
+    for (int s = 0; s < kSPT; s++) {
+        const uint32_t i = i0 + s;
+        long long acc = 0;
+#pragma unroll
+        for (int j = 0; j < kMaxOrd; j++) acc += (long long)cf[j] * (long long)xv[kMaxOrd + s - 1 - j];
+        long long r = (long long)xv[kMaxOrd + s] - (acc >> shift);
+        if (i < n) {
+            if (i >= (uint32_t)order) {
+                if (r > 2147483647ll || r <= -2147483648ll) ok = false;
+                res[i] = (int32_t)r;
+            } else res[i] = 0;
+        }
+    }
+    return ok;
+}
+
+// Partition sums + libFLAC estimate search.  On return S.cand.{po,method,params,bits(residual bits)} are set.
+__device__ __forceinline__ uint32_t search_partitions(const int32_t *res, uint32_t n, int order, uint32_t max_po_cfg,
+                                                      uint32_t k_limit, EncShared &S) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t P = max_po_for(max_po_cfg, n, (uint32_t)order);
+    const uint32_t parts = 1u << P, psize = n >> P;
+    // level 0 (finest) sums at psum[0..parts)
+    for (uint32_t p = warp; p < parts; p += kEncThreads / 32) {
+        unsigned long long s = 0;
+        const uint32_t a = p * psize, b = a + psize;
+        for (uint32_t i = a + lane; i < b; i += 32) {
+            if (i >= (uint32_t)order) { int32_t v = res[i]; s += (unsigned long long)(v < 0 ? -(long long)v : (long long)v); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+        if (lane == 0) S.psum[p] = s;
+    }
+    __syncthreads();
+    // merge upward: level l holds order P-l at offset off_l
+    {
+        uint32_t off = 0, cnt = parts;
+        for (uint32_t l = 0; l < P; l++) {
+            for (uint32_t p = threadIdx.x; p < cnt / 2; p += kEncThreads)
+                S.psum[off + cnt + p] = S.psum[off + 2 * p] + S.psum[off + 2 * p + 1];
+            off += cnt; cnt >>= 1;
+            __syncthreads();
+        }
+    }
+    // per (order, partition) parameter + estimated bits
+    const uint32_t total_entries = (parts << 1) - 1;
+    for (uint32_t e = threadIdx.x; e < total_entries; e += kEncThreads) {
+        // find level: entries [off_l, off_l + parts>>l)
+        uint32_t l = 0, off = 0, cnt = parts;
+        while (e >= off + cnt) { off += cnt; cnt >>= 1; l++; }
+        const uint32_t po = P - l, p = e - off;
+        uint32_t np = n >> po;
+        if (p == 0) np -= (uint32_t)order;
+        const uint32_t div = 0x40000u / np;
+        const unsigned long long mean = S.psum[e];
+        uint32_t k;
+        unsigned long long t = mean < 2 ? 0ull : (((mean - 1) * div) >> 18);
+        if (t == 0) k = 0; else k = (uint32_t)ilog2_u64(t) + 1;
+        if (k >= k_limit) k = k_limit - 1;
+        S.pk[e] = (uint8_t)k;
+        S.pbits[e] = rice_bits_estimate(k, np, mean);
+    }
+    __syncthreads();
+    // per-order totals: warp w sums order P-w, P-w-8...
+    for (uint32_t l = warp; l <= P; l += kEncThreads / 32) {
+        uint32_t off = 0, cnt = parts;
+        for (uint32_t q = 0; q < l; q++) { off += cnt; cnt >>= 1; }
+        unsigned long long s = 0;
+        for (uint32_t p = lane; p < cnt; p += 32) s += S.pbits[off + p];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+        s += 6;
+        if (lane == 0) S.order_bits[l] = s > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)s;
+    }
+    __syncthreads();
+    // choose: iterate partition order from max down to 0, strict improvement only
+    uint32_t best_l = 0, best_bits = S.order_bits[0];
+    for (uint32_t l = 1; l <= P; l++) { uint32_t b = S.order_bits[l]; if (b < best_bits) { best_bits = b; best_l = l; } }
+    {
+        uint32_t off = 0, cnt = parts;
+        for (uint32_t q = 0; q < best_l; q++) { off += cnt; cnt >>= 1; }
+        bool rice2 = false;
+        for (uint32_t p = threadIdx.x; p < cnt; p += kEncThreads) { uint8_t k = S.pk[off + p]; S.cand.params[p] = k; if (k >= 15) rice2 = true; }
+        int any = __syncthreads_or(rice2 ? 1 : 0);
+        if (threadIdx.x == 0) { S.cand.po = (int)(P - best_l); S.cand.method = any ? 1 : 0; }
+    }
+    __syncthreads();
+    return best_bits;
+}
+
+// If the candidate in S.cand (with residual in buffer cand_buf) beats S.best, adopt it.
+__device__ __forceinline__ void consider_candidate(uint32_t cand_bits, int cand_buf, EncShared &S) {
+    __syncthreads();
+    const bool better = cand_bits < S.best.bits;
+    __syncthreads();
+    if (better) {
+        if (threadIdx.x == 0) { S.cand.bits = cand_bits; S.best_buf = cand_buf; }
+        __syncthreads();
+        // struct copy by words
+        const uint32_t words = sizeof(Choice) / 4;
+        uint32_t *d = (uint32_t *)&S.best; const uint32_t *s = (const uint32_t *)&S.cand;
+        for (uint32_t i = threadIdx.x; i < words; i += kEncThreads) d[i] = s[i];
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kEncThreads)
+k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint32_t channels, uint32_t bps_stream,
+                   uint32_t blocksize, uint32_t level, const int32_t *__restrict__ audio,
+                   const float *__restrict__ window, uint32_t slot_words, uint32_t *__restrict__ slots,
+                   uint32_t *__restrict__ sub_bits) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EncShared &S = *reinterpret_cast<EncShared *>(smem_raw);
+    const uint32_t task = blockIdx.x;
+    const uint32_t f = task / channels, c = task - f * channels;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // locate stream
+    uint32_t lo = 0, hi = n_streams - 1;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (streams[mid].frame_base <= f) lo = mid; else hi = mid - 1;
+    }
+    const EncStreamDev st = streams[lo];
+    const uint32_t kf = f - st.frame_base;
+    const uint32_t n = (kf + 1 < st.n_frames) ? blocksize : (uint32_t)(st.n_samples - (uint64_t)kf * blocksize);
+    const int32_t *src = audio + st.audio_base + (int64_t)c * (int64_t)st.n_samples + (int64_t)kf * blocksize;
+    int32_t *X = S.buf[1];
+    const LevelCfg cfg = level_cfg(level);
+    const uint32_t k_limit = bps_stream > 16 ? 31u : 15u;
+    const uint32_t i0 = tid * kSPT;
+
+    // ---- load, wasted bits, constant check -----------------------------------
+    uint32_t orv = 0, diff = 0;
+    const int32_t x_first = n ? __ldg(src) : 0;
+#pragma unroll
+    for (int s = 0; s < kSPT; s++) {
+        const uint32_t i = i0 + s;
+        if (i < n) { int32_t v = __ldg(src + i); X[i] = v; orv |= (uint32_t)v; diff |= (uint32_t)(v ^ x_first); }
+    }
+    orv = block_or(orv, S);
+    diff = block_or(diff, S);
+    uint32_t wasted = orv ? (uint32_t)(__ffs((int)orv) - 1) : 0;
+    if (wasted > bps_stream) wasted = bps_stream;
+    const uint32_t bps = bps_stream - wasted;
+    if (wasted) {
+#pragma unroll
+        for (int s = 0; s < kSPT; s++) { const uint32_t i = i0 + s; if (i < n) X[i] >>= wasted; }
+    }
+    if (tid == 0) {
+        S.best.type = 1; S.best.order = 0; S.best.wasted = (int)wasted; S.best.precision = 0; S.best.shift = 0;
+        S.best.method = 0; S.best.po = 0; S.best.bits = 8 + wasted + n * bps;
+        S.best_buf = 0;
+    }
+    __syncthreads();
+    const uint32_t verbatim_bits = 8 + wasted + n * bps;
+
+    if (n > 4) {
+        if (diff == 0) {
+            if (tid == 0) { uint32_t b = 8 + wasted + bps; if (b < S.best.bits) { S.best.type = 0; S.best.bits = b; } }
+            __syncthreads();
+        } else {
+            // ---- fixed predictor abs-error sums over i in [4, n) --------------------
+            unsigned long long e[5] = {0, 0, 0, 0, 0};
+            {
+                int32_t xv[kSPT + 4];
+#pragma unroll
+                for (int j = 0; j < kSPT + 4; j++) { int idx = (int)i0 - 4 + j; xv[j] = (idx >= 0 && (uint32_t)idx < n) ? X[idx] : 0; }
+#pragma unroll
+                for (int s = 0; s < kSPT; s++) {
+                    const uint32_t i = i0 + s;
+                    if (i >= 4 && i < n) {
+                        long long a = xv[s + 4], b = xv[s + 3], cc = xv[s + 2], d = xv[s + 1], ee = xv[s];
+                        long long r0 = a, r1 = a - b, r2 = a - 2 * b + cc, r3 = a - 3 * b + 3 * cc - d, r4 = a - 4 * b + 6 * cc - 4 * d + ee;
+                        e[0] += (unsigned long long)(r0 < 0 ? -r0 : r0);
+                        e[1] += (unsigned long long)(r1 < 0 ? -r1 : r1);
+                        e[2] += (unsigned long long)(r2 < 0 ? -r2 : r2);
+                        e[3] += (unsigned long long)(r3 < 0 ? -r3 : r3);
+                        e[4] += (unsigned long long)(r4 < 0 ? -r4 : r4);
+                    }
+                }
+            }
+            block_sum_u64<5>(e, S);
+            uint32_t guess;
+            {
+                unsigned long long m1234 = min(min(e[1], e[2]), min(e[3], e[4]));
+                unsigned long long m234 = min(e[2], min(e[3], e[4]));
+                unsigned long long m34 = min(e[3], e[4]);
+                if (e[0] <= m1234) guess = 0; else if (e[1] <= m234) guess = 1; else if (e[2] <= m34) guess = 2; else if (e[3] <= e[4]) guess = 3; else guess = 4;
+            }
+            const float fbits_guess = (float)(e[guess] > 0 ? log(0.69314718055994530942 * (double)e[guess] / (double)(n - 4)) / 0.69314718055994530942 : 0.0);
+            int cand_buf = 0;      // first candidate residual goes to resA (buf[0]); next to the non-best one
+            if (!(fbits_guess >= (float)bps)) {
+                if (tid == 0) {
+                    Choice &C = S.cand;
+                    C.type = 2; C.order = (int)guess; C.wasted = (int)wasted; C.precision = 0; C.shift = 0;
+                    for (int j = 0; j < kMaxOrd; j++) C.coefs[j] = 0;
+                    if (guess == 1) { C.coefs[0] = 1; }
+                    else if (guess == 2) { C.coefs[0] = 2; C.coefs[1] = -1; }
+                    else if (guess == 3) { C.coefs[0] = 3; C.coefs[1] = -3; C.coefs[2] = 1; }
+                    else if (guess == 4) { C.coefs[0] = 4; C.coefs[1] = -6; C.coefs[2] = 4; C.coefs[3] = -1; }
+                }
+                __syncthreads();
+                int32_t *R = S.buf[cand_buf];
+                bool ok = compute_residual(X, R, n, (int)guess, 0, S.cand.coefs);
+                int bad = __syncthreads_or(ok ? 0 : 1);
+                if (!bad) {
+                    uint32_t rb = search_partitions(R, n, (int)guess, (uint32_t)cfg.max_po, k_limit, S);
+                    uint32_t total = 8 + wasted + guess * bps + rb;
+                    consider_candidate(total, cand_buf, S);
+                }
+            }
+            // ---- LPC ---------------------------------------------------------------
+            uint32_t max_lpc = (uint32_t)cfg.max_lpc_order;
+            if (max_lpc >= n) max_lpc = n - 1;
+            if (max_lpc > 0) {
+                const uint32_t qprec_cfg = qlp_precision_for(bps_stream, blocksize);
+                const int kinds = cfg.windows;
+                for (int b = 1; b <= kinds; b++) {
+                    const int ncs = (b == 1) ? 1 : (b == 2 ? 2 : 2 * b);
+                    for (int ci = 0; ci < ncs; ci++) {
+                        const int cidx = (b == 2) ? 2 * ci : ci;
+                        bool have_ac = true;
+                        if (b > 1 && n / (uint32_t)b <= 32) have_ac = false;
+                        if (have_ac && (b == 1 || !(cidx & 1))) {
+                            // windowed autocorrelation over [wshift, wshift + wlen)
+                            uint32_t wshift = 0, wlen = n, part = 0;
+                            if (b > 1) { part = n / (uint32_t)b / 2; wshift = ((uint32_t)(cidx / 2) * n) / (uint32_t)b; wlen = n / (uint32_t)b; }
+                            double dd[kSPT + kMaxOrd];
+#pragma unroll
+                            for (int j = 0; j < kSPT + kMaxOrd; j++) {
+                                int idx = (int)i0 - kMaxOrd + j;
+                                double v = 0.0;
+                                if (idx >= (int)wshift && (uint32_t)idx < wshift + wlen && (uint32_t)idx < n) {
+                                    uint32_t local = (uint32_t)idx - wshift;
+                                    float wv;
+                                    if (b == 1) wv = __ldg(window + idx);
+                                    else if (local < part) wv = __ldg(window + local);
+                                    else if (local < 2 * part) wv = __ldg(window + (n - 2 * part + local));
+                                    else wv = 0.0f;
+                                    v = (double)__fmul_rn((float)X[idx], wv);
+                                }
+                                dd[j] = v;
+                            }
+                            double ac[kMaxOrd + 1];
+#pragma unroll
+                            for (int l = 0; l <= kMaxOrd; l++) ac[l] = 0.0;
+#pragma unroll
+                            for (int s = 0; s < kSPT; s++)
+#pragma unroll
+                                for (int l = 0; l <= kMaxOrd; l++) ac[l] = fma(dd[kMaxOrd + s], dd[kMaxOrd + s - l], ac[l]);
+#pragma unroll
+                            for (int l = 0; l <= kMaxOrd; l++)
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) ac[l] += __shfl_xor_sync(0xFFFFFFFFu, ac[l], o);
+                            __syncthreads();
+                            if (lane == 0)
+#pragma unroll
+                                for (int l = 0; l <= kMaxOrd; l++) S.red_f64[warp][l] = ac[l];
+                            __syncthreads();
+                            if (tid <= kMaxOrd) {
+                                double s = 0.0;
+                                for (int w = 0; w < kEncThreads / 32; w++) s += S.red_f64[w][tid];
+                                S.autoc[tid] = s;
+                                if (b == 1) S.autoc_root[tid] = s;
+                            }
+                            __syncthreads();
+                        } else if (have_ac) {
+                            // punch-out window: root minus the previous partial window (lags < max_lpc as libFLAC does)
+                            if ((uint32_t)tid < max_lpc) S.autoc[tid] = S.autoc_root[tid] - S.autoc[tid];
+                            __syncthreads();
+                        }
+                        // ---- Levinson-Durbin, order estimate, quantisation (one thread) ----
+                        if (tid == 0) {
+                            S.flag = 0;
+                            if (have_ac && S.autoc[0] != 0.0) {
+                                double lpc[kMaxOrd];
+                                double err = S.autoc[0];
+                                uint32_t mo = max_lpc;
+                                for (uint32_t i = 0; i < max_lpc; i++) {
+                                    double r = -S.autoc[i + 1];
+                                    for (uint32_t j = 0; j < i; j++) r = __dsub_rn(r, __dmul_rn(lpc[j], S.autoc[i - j]));
+                                    r = __ddiv_rn(r, err);
+                                    lpc[i] = r;
+                                    uint32_t j;
+                                    for (j = 0; j < (i >> 1); j++) {
+                                        double tmp = lpc[j];
+                                        lpc[j] = __dadd_rn(lpc[j], __dmul_rn(r, lpc[i - 1 - j]));
+                                        lpc[i - 1 - j] = __dadd_rn(lpc[i - 1 - j], __dmul_rn(r, tmp));
+                                    }
+                                    if (i & 1) lpc[j] = __dadd_rn(lpc[j], __dmul_rn(lpc[j], r));
+                                    err = __dmul_rn(err, __dsub_rn(1.0, __dmul_rn(r, r)));
+                                    for (j = 0; j <= i; j++) S.lp[i][j] = (float)(-lpc[j]);
+                                    S.lp_err[i] = err;
+                                    if (err == 0.0) { mo = i + 1; break; }
+                                }
+                                // FLAC__lpc_compute_best_order
+                                const double scale = 0.5 / (double)n;
+                                uint32_t best_i = 0; double best_b = 4294967295.0;
+                                const uint32_t overhead = bps + qprec_cfg;
+                                for (uint32_t i = 0; i < mo; i++) {
+                                    double le = S.lp_err[i], eb;
+                                    if (le > 0.0) { eb = 0.5 * log(scale * le) / 0.69314718055994530942; if (eb < 0.0) eb = 0.0; }
+                                    else if (le < 0.0) eb = 1e32; else eb = 0.0;
+                                    double bits = eb * (double)(n - (i + 1)) + (double)((i + 1) * overhead);
+                                    if (bits < best_b) { best_b = bits; best_i = i; }
+                                }
+                                const uint32_t order = best_i + 1;
+                                double le = S.lp_err[order - 1], eb;
+                                const double scale2 = 0.5 / (double)(n - order);
+                                if (le > 0.0) { eb = 0.5 * log(scale2 * le) / 0.69314718055994530942; if (eb < 0.0) eb = 0.0; }
+                                else if (le < 0.0) eb = 1e32; else eb = 0.0;
+                                if (!(eb >= (double)bps)) {
+                                    uint32_t prec = qprec_cfg;
+                                    if (bps <= 17) { uint32_t lim = 32 - bps - (uint32_t)ilog2_u32(order); if (lim < prec) prec = lim; }
+                                    // FLAC__lpc_quantize_coefficients
+                                    const float *lpv = S.lp[order - 1];
+                                    int p1 = (int)prec - 1;
+                                    int qmax = (1 << p1) - 1, qmin = -(1 << p1);
+                                    double cmax = 0.0;
+                                    for (uint32_t i = 0; i < order; i++) { double d = fabs((double)lpv[i]); if (d > cmax) cmax = d; }
+                                    if (cmax > 0.0) {
+                                        int log2cmax; (void)frexp(cmax, &log2cmax); log2cmax--;
+                                        int sh = p1 - log2cmax - 1;
+                                        bool okq = true;
+                                        if (sh > 15) sh = 15; else if (sh < -16) okq = false;
+                                        if (okq) {
+                                            Choice &C = S.cand;
+                                            for (int j = 0; j < kMaxOrd; j++) C.coefs[j] = 0;
+                                            double er = 0.0;
+                                            if (sh >= 0) {
+                                                for (uint32_t i = 0; i < order; i++) {
+                                                    er = __dadd_rn(er, __dmul_rn((double)lpv[i], (double)(1 << sh)));
+                                                    long long q = llround(er);
+                                                    if (q > qmax) q = qmax; else if (q < qmin) q = qmin;
+                                                    er = __dsub_rn(er, (double)q); C.coefs[i] = (int32_t)q;
+                                                }
+                                            } else {
+                                                const int ns = -sh;
+                                                for (uint32_t i = 0; i < order; i++) {
+                                                    er = __dadd_rn(er, __ddiv_rn((double)lpv[i], (double)(1 << ns)));
+                                                    long long q = llround(er);
+                                                    if (q > qmax) q = qmax; else if (q < qmin) q = qmin;
+                                                    er = __dsub_rn(er, (double)q); C.coefs[i] = (int32_t)q;
+                                                }
+                                                sh = 0;
+                                            }
+                                            C.type = 3; C.order = (int)order; C.wasted = (int)wasted; C.precision = (int)prec; C.shift = sh;
+                                            S.flag = 1;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        __syncthreads();
+                        if (S.flag) {
+                            cand_buf = (S.best_buf == 0 && (S.best.type >= 2)) ? 2 : 0;
+                            const int order = S.cand.order, sh = S.cand.shift;
+                            int32_t *R = S.buf[cand_buf];
+                            bool ok = compute_residual(X, R, n, order, sh, S.cand.coefs);
+                            int bad = __syncthreads_or(ok ? 0 : 1);
+                            if (!bad) {
+                                uint32_t rb = search_partitions(R, n, order, (uint32_t)cfg.max_po, k_limit, S);
+                                uint32_t total = 8 + wasted + 4 + 5 + (uint32_t)order * ((uint32_t)S.cand.precision + bps) + rb;
+                                consider_candidate(total, cand_buf, S);
+                            }
+                        }
+                        __syncthreads();
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- exact bit lengths, fallback to VERBATIM, pack ----------------------------
+    int type = S.best.type;
+    const int order = S.best.order, po = S.best.po, method = S.best.method;
+    const int32_t *R = S.buf[S.best_buf];
+    const uint32_t plen = method ? 5u : 4u;
+    const uint32_t psize = n >> po;
+    uint32_t my_bits = 0;
+    if (type >= 2) {
+#pragma unroll
+        for (int s = 0; s < kSPT; s++) {
+            const uint32_t i = i0 + s;
+            if (i < n && i >= (uint32_t)order) {
+                const uint32_t p = i / psize;
+                const uint32_t k = S.best.params[p];
+                const uint32_t u = zigzag(R[i]);
+                my_bits += (u >> k) + 1 + k;
+                if (i == p * psize || i == (uint32_t)order) my_bits += plen;
+            }
+        }
+    }
+    uint32_t hdr_bits = 8 + wasted;
+    if (type == 0) hdr_bits += bps;
+    else if (type == 2) hdr_bits += (uint32_t)order * bps + 6;
+    else if (type == 3) hdr_bits += (uint32_t)order * bps + 9 + (uint32_t)(order * S.best.precision) + 6;
+    uint32_t total_res = 0;
+    uint32_t my_off = block_exscan(my_bits, &total_res, S);
+    __syncthreads();
+    if (type >= 2 && hdr_bits + total_res > verbatim_bits) type = 1;     // exactness guard
+    uint32_t total_bits;
+    if (type == 1) { hdr_bits = 8 + wasted; total_bits = verbatim_bits; }
+    else total_bits = hdr_bits + total_res;
+
+    // bit buffer: X + the non-best residual buffer (contiguous 32 KB); warm-up samples saved first
+    int32_t warm[kMaxOrd];
+    int32_t xfirst_shifted = 0;
+    if (tid == 0) {
+#pragma unroll
+        for (int j = 0; j < kMaxOrd; j++) warm[j] = (j < order && (uint32_t)j < n) ? X[j] : 0;
+        xfirst_shifted = n ? X[0] : 0;
+    }
+    uint32_t *bitbuf;
+    int32_t xv_verb[kSPT];
+    if (type == 1) {
+#pragma unroll
+        for (int s = 0; s < kSPT; s++) { const uint32_t i = i0 + s; xv_verb[s] = (i < n) ? X[i] : 0; }
+        bitbuf = (uint32_t *)S.buf[1];              // X + resB: nothing else is needed any more
+    } else {
+        bitbuf = (S.best_buf == 0) ? (uint32_t *)S.buf[1] : (uint32_t *)S.buf[0];
+    }
+    __syncthreads();
+    const uint32_t nwords = (total_bits + 31) / 32;
+    for (uint32_t wd = tid; wd < nwords + 1 && wd < 2 * kMaxBlock; wd += kEncThreads) bitbuf[wd] = 0;
+    __syncthreads();
+
+    const uint32_t mask_bps = bps >= 32 ? 0xFFFFFFFFu : ((1u << bps) - 1u);
+    SmemBitWriter bw;
+    if (tid == 0) {
+        bw.init(bitbuf, 0);
+        uint32_t typecode = type == 0 ? 0u : type == 1 ? 1u : type == 2 ? (8u | (uint32_t)order) : (32u | (uint32_t)(order - 1));
+        bw.put((typecode << 1) | (wasted ? 1u : 0u), 8);
+        if (wasted) { bw.zeros(wasted - 1); bw.put(1, 1); }
+        if (type == 0) bw.put((uint32_t)xfirst_shifted & mask_bps, bps);
+        else if (type >= 2) {
+#pragma unroll
+            for (int j = 0; j < kMaxOrd; j++) if (j < order) bw.put((uint32_t)warm[j] & mask_bps, bps);
+            if (type == 3) {
+                const uint32_t prec = (uint32_t)S.best.precision;
+                bw.put(prec - 1, 4);
+                bw.put((uint32_t)S.best.shift & 31u, 5);
+#pragma unroll
+                for (int j = 0; j < kMaxOrd; j++) if (j < order) bw.put((uint32_t)S.best.coefs[j] & ((1u << prec) - 1u), prec);
+            }
+            bw.put((uint32_t)method, 2);
+            bw.put((uint32_t)po, 4);
+        }
+        bw.finish();
+    }
+    if (type == 1) {
+        bw.init(bitbuf, hdr_bits + i0 * bps);
+#pragma unroll
+        for (int s = 0; s < kSPT; s++) { const uint32_t i = i0 + s; if (i < n) bw.put((uint32_t)xv_verb[s] & mask_bps, bps); }
+        bw.finish();
+    } else if (type >= 2) {
+        bw.init(bitbuf, hdr_bits + my_off);
+#pragma unroll
+        for (int s = 0; s < kSPT; s++) {
+            const uint32_t i = i0 + s;
+            if (i < n && i >= (uint32_t)order) {
+                const uint32_t p = i / psize;
+                const uint32_t k = S.best.params[p];
+                if (i == p * psize || i == (uint32_t)order) bw.put(k, plen);
+                const uint32_t u = zigzag(R[i]);
+                bw.zeros(u >> k);
+                bw.put((1u << k) | (u & ((1u << k) - 1u)), k + 1);
+            }
+        }
+        bw.finish();
+    }
+    __syncthreads();
+    // ---- slot store (128-bit, coalesced) -------------------------------------------
+    uint32_t *slot = slots + (size_t)task * slot_words;
+    const uint32_t nq = (nwords + 1 + 3) / 4;          // one extra word so the emitter can funnel-read past the end
+    const uint4 *b4 = reinterpret_cast<const uint4 *>(bitbuf);
+    uint4 *s4 = reinterpret_cast<uint4 *>(slot);
+    for (uint32_t q = tid; q < nq && q * 4 < slot_words; q += kEncThreads) s4[q] = b4[q];
+    if (tid == 0) sub_bits[task] = total_bits;
+}
+
+// ---- frame sizes / scans -------------------------------------------------------
+__device__ __forceinline__ uint32_t frame_header_bytes(uint32_t n, uint32_t sample_rate, uint64_t number) {
+    int bh, sh;
+    (void)blocksize_code(n, &bh);
+    (void)samplerate_code(sample_rate, &sh);
+    return 4 + (uint32_t)utf8_len(number) + (uint32_t)bh + (sh == 0 ? 0u : sh == 1 ? 1u : 2u) + 1;
+}
+
+__global__ void __launch_bounds__(256)
+k_frame_sizes(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint32_t channels, uint32_t blocksize,
+              uint32_t total_frames, const uint32_t *__restrict__ sub_bits, uint32_t *__restrict__ frame_bytes) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= total_frames) return;
+    uint32_t lo = 0, hi = n_streams - 1;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (streams[mid].frame_base <= f) lo = mid; else hi = mid - 1;
+    }
+    const EncStreamDev st = streams[lo];
+    const uint32_t k = f - st.frame_base;
+    const uint32_t n = (k + 1 < st.n_frames) ? blocksize : (uint32_t)(st.n_samples - (uint64_t)k * blocksize);
+    uint64_t bits = 0;
+    for (uint32_t c = 0; c < channels; c++) bits += sub_bits[(size_t)f * channels + c];
+    frame_bytes[f] = frame_header_bytes(n, st.sample_rate, k) + (uint32_t)((bits + 7) >> 3) + 2;
+}
+
+// one CTA per stream: exclusive scan of its frame sizes -> frame_off, total -> stream_bytes
+__global__ void __launch_bounds__(1024)
+k_stream_scan(const EncStreamDev *__restrict__ streams, const uint32_t *__restrict__ frame_bytes,
+              unsigned long long *__restrict__ frame_off, unsigned long long *__restrict__ stream_bytes) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    const EncStreamDev st = streams[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < st.n_frames; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        unsigned long long v = i < st.n_frames ? frame_bytes[st.frame_base + i] : 0ull;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        unsigned long long wbase = 0, tot = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { unsigned long long s = s_warp[w]; if (w < warp) wbase += s; tot += s; }
+        const unsigned long long carry = s_carry;
+        if (i < st.n_frames) frame_off[st.frame_base + i] = carry + wbase + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) stream_bytes[blockIdx.x] = s_carry;
+}
+
+__global__ void k_set_out_offsets(EncStreamDev *streams, const unsigned long long *offs, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) streams[i].out_offset = offs[i];
+}
+
+// ---- frame assembly ------------------------------------------------------------
+constexpr int kEmitThreads = 128;
+
+__global__ void __launch_bounds__(kEmitThreads)
+k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint32_t channels, uint32_t bps_stream,
+              uint32_t blocksize, uint32_t total_frames, const uint32_t *__restrict__ sub_bits,
+              const uint32_t *__restrict__ slots, uint32_t slot_words, const uint32_t *__restrict__ frame_bytes,
+              const unsigned long long *__restrict__ frame_off, uint8_t *__restrict__ out, uint64_t out_capacity,
+              uint32_t *__restrict__ err_flag) {
+    __shared__ uint32_t s_hdr[6];             // header bits, MSB-first words
+    __shared__ uint32_t s_seg_start[FRB_MAX_CHANNELS + 2];   // bit start of each segment within the frame
+    __shared__ uint16_t s_crc_tab[256];
+    __shared__ uint32_t s_crc_part[kEmitThreads];
+    const uint32_t f = blockIdx.x;
+    const int tid = threadIdx.x;
+    uint32_t lo = 0, hi = n_streams - 1;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (streams[mid].frame_base <= f) lo = mid; else hi = mid - 1;
+    }
+    const EncStreamDev st = streams[lo];
+    const uint32_t k = f - st.frame_base;
+    const uint32_t n = (k + 1 < st.n_frames) ? blocksize : (uint32_t)(st.n_samples - (uint64_t)k * blocksize);
+    const uint32_t total = frame_bytes[f];
+    const uint64_t dst_off = st.out_offset + frame_off[f];
+    for (int i = tid; i < 256; i += kEmitThreads) s_crc_tab[i] = c_crc16[i];
+    if (tid == 0) {
+        uint8_t hb[16];
+        int bh, sh;
+        const uint32_t bsc = blocksize_code(n, &bh), src = samplerate_code(st.sample_rate, &sh);
+        uint32_t i = 0;
+        hb[i++] = 0xFF; hb[i++] = 0xF8;
+        hb[i++] = (uint8_t)((bsc << 4) | src);
+        hb[i++] = (uint8_t)(((channels - 1) << 4) | (bps_code(bps_stream) << 1));
+        {
+            uint64_t v = k; int len = utf8_len(v);
+            if (len == 1) hb[i++] = (uint8_t)v;
+            else {
+                const uint8_t lead[8] = {0, 0, 0xC0, 0xE0, 0xF0, 0xF8, 0xFC, 0xFE};
+                for (int q = len - 1; q > 0; q--) { hb[i + q] = (uint8_t)(0x80 | (v & 0x3F)); v >>= 6; }
+                hb[i] = (uint8_t)(lead[len] | v);
+                i += len;
+            }
+        }
+        if (bh == 1) hb[i++] = (uint8_t)(n - 1);
+        else if (bh == 2) { hb[i++] = (uint8_t)((n - 1) >> 8); hb[i++] = (uint8_t)(n - 1); }
+        if (sh == 1) hb[i++] = (uint8_t)(st.sample_rate / 1000);
+        else if (sh == 2) { hb[i++] = (uint8_t)(st.sample_rate >> 8); hb[i++] = (uint8_t)st.sample_rate; }
+        else if (sh == 3) { hb[i++] = (uint8_t)((st.sample_rate / 10) >> 8); hb[i++] = (uint8_t)(st.sample_rate / 10); }
+        uint8_t crc = 0;
+        for (uint32_t q = 0; q < i; q++) crc = c_crc8[crc ^ hb[q]];
+        hb[i++] = crc;
+        for (uint32_t q = i; q < 16; q++) hb[q] = 0;
+        for (int w = 0; w < 4; w++) s_hdr[w] = ((uint32_t)hb[4 * w] << 24) | ((uint32_t)hb[4 * w + 1] << 16) | ((uint32_t)hb[4 * w + 2] << 8) | hb[4 * w + 3];
+        s_hdr[4] = 0; s_hdr[5] = 0;
+        uint32_t pos = i * 8;
+        s_seg_start[0] = pos;                       // segment c+... : subframe c starts here
+        for (uint32_t c = 0; c < channels; c++) { pos += sub_bits[(size_t)f * channels + c]; s_seg_start[c + 1] = pos; }
+        if (((pos + 7) >> 3) + 2 != total || dst_off + total > out_capacity) atomicExch(err_flag, 1u);
+    }
+    __syncthreads();
+    const uint32_t payload = total - 2;                    // bytes covered by the CRC
+    if (dst_off + total > out_capacity) return;
+    const uint32_t nwords = (payload + 3) / 4;
+    const uint32_t wpt = (nwords + kEmitThreads - 1) / kEmitThreads;
+    const uint32_t w_begin = tid * wpt, w_end = min(nwords, w_begin + wpt);
+    const uint32_t hdr_bits = s_seg_start[0], end_bits = s_seg_start[channels];
+    uint8_t *dst = out + dst_off;
+    uint32_t crc = 0;
+    for (uint32_t w = w_begin; w < w_end; w++) {
+        // gather 32 bits starting at frame bit position P
+        uint32_t P = w * 32, need = 32, val = 0;
+        while (need) {
+            uint32_t take, bits;
+            if (P < hdr_bits) {
+                take = min(need, hdr_bits - P);
+                uint32_t wi = P >> 5, sh = P & 31;
+                uint32_t v = __funnelshift_l(s_hdr[wi + 1], s_hdr[wi], sh);
+                bits = take == 32 ? v : (v >> (32 - take));
+            } else if (P < end_bits) {
+                uint32_t c = 0;
+                while (s_seg_start[c + 1] <= P) c++;
+                uint32_t o = P - s_seg_start[c];
+                take = min(need, s_seg_start[c + 1] - P);
+                const uint32_t *sl = slots + ((size_t)f * channels + c) * slot_words;
+                uint32_t wi = o >> 5, sh = o & 31;
+                uint32_t v = __funnelshift_l(__ldg(sl + wi + 1), __ldg(sl + wi), sh);
+                bits = take == 32 ? v : (v >> (32 - take));
+            } else { take = need; bits = 0; }
+            val = take == 32 ? bits : ((val << take) | bits);
+            need -= take; P += take;
+        }
+        const uint32_t nb = min(4u, payload - w * 4);
+#pragma unroll
+        for (uint32_t q = 0; q < 4; q++) {
+            if (q < nb) {
+                uint8_t byte = (uint8_t)(val >> (24 - 8 * q));
+                dst[w * 4 + q] = byte;
+                crc = ((crc << 8) & 0xFFFFu) ^ s_crc_tab[((crc >> 8) ^ byte) & 0xFF];
+            }
+        }
+    }
+    // combine partial CRCs
+    {
+        uint64_t my_end = min((uint64_t)w_end * 4, (uint64_t)payload);
+        if (w_begin >= w_end) { crc = 0; my_end = payload; }
+        s_crc_part[tid] = gf16_mul(crc, gf16_xpow8(payload - my_end));
+    }
+    __syncthreads();
+    if (tid < 32) {
+        uint32_t v = 0;
+        for (int i = tid; i < kEmitThreads; i += 32) v ^= s_crc_part[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if (tid == 0) { dst[payload] = (uint8_t)(v >> 8); dst[payload + 1] = (uint8_t)v; }
+    }
+}
+
+// ---- workspace -----------------------------------------------------------------
+struct EncWorkspace {
+    EncStreamDev *streams;
+    uint32_t *sub_bits;
+    uint32_t *frame_bytes;
+    unsigned long long *frame_off;
+    unsigned long long *stream_bytes;
+    unsigned long long *out_offs;
+    uint32_t *err_flag;
+    float *window;
+    uint32_t *slots;
+};
+static inline size_t enc_ws_layout(const frb_encode_params *p, uint64_t total_frames, void *base, EncWorkspace *w) {
+    size_t off = 0;
+    uint8_t *b = (uint8_t *)base;
+    const uint64_t subs = total_frames * p->channels;
+#define FRB_TAKE(field, type, count)                                         \
+    if (w) w->field = (type *)(b + off);                                      \
+    off += align256(sizeof(type) * (size_t)(count));
+    FRB_TAKE(streams, EncStreamDev, p->n_streams)
+    FRB_TAKE(sub_bits, uint32_t, subs)
+    FRB_TAKE(frame_bytes, uint32_t, total_frames)
+    FRB_TAKE(frame_off, unsigned long long, total_frames)
+    FRB_TAKE(stream_bytes, unsigned long long, p->n_streams)
+    FRB_TAKE(out_offs, unsigned long long, p->n_streams)
+    FRB_TAKE(err_flag, uint32_t, 64)
+    FRB_TAKE(window, float, FRB_MAX_BLOCKSIZE)
+    FRB_TAKE(slots, uint32_t, subs * slot_words_for(p->blocksize, p->bps))
+#undef FRB_TAKE
+    return off;
+}
+
+static inline void make_tukey(float *w, int L, float p) {
+    // FLAC__window_tukey
+    for (int n = 0; n < L; n++) w[n] = 1.0f;
+    if (p <= 0.0f) return;
+    const int Np = (int)(p / 2.0f * L) - 1;
+    if (Np > 0) {
+        for (int n = 0; n <= Np; n++) {
+            w[n] = (float)(0.5f - 0.5f * cosf((float)(M_PI * n / Np)));
+            w[L - Np - 1 + n] = (float)(0.5f - 0.5f * cosf((float)(M_PI * (n + Np) / Np)));
+        }
+    }
+}
+
+static inline bool enc_params_ok(const frb_encode_params *p) {
+    return p && p->n_streams >= 1 && p->channels >= 1 && p->channels <= FRB_MAX_CHANNELS &&
+           (p->bps == 16 || p->bps == 32) && p->blocksize >= 16 && p->blocksize <= FRB_MAX_BLOCKSIZE && p->level <= 8;
+}
+
+}  // namespace frb
+
+extern "C" int frb_encode_workspace_size(const frb_encode_params *p, uint64_t total_frames, size_t *bytes) {
+    if (!frb::enc_params_ok(p) || !bytes) return FRB_ERR_INVALID_ARG;
+    *bytes = frb::enc_ws_layout(p, total_frames, nullptr, nullptr);
+    return FRB_OK;
+}
+
+extern "C" int frb_encode_analyse(const frb_encode_params *p, const int32_t *d_audio,
+                                  const uint64_t *h_n_samples, const uint32_t *h_sample_rate,
+                                  const int64_t *h_audio_base, void *d_workspace, size_t workspace_bytes,
+                                  uint64_t *d_stream_bytes, uint64_t *h_stream_bytes, void *stream) {
+    using namespace frb;
+    if (!enc_params_ok(p) || !d_audio || !h_n_samples || !h_sample_rate || !h_audio_base || !d_workspace) return FRB_ERR_INVALID_ARG;
+    int rc = ensure_tables_impl();
+    if (rc) return rc;
+    std::vector<EncStreamDev> hs(p->n_streams);
+    uint64_t frames = 0;
+    for (uint32_t i = 0; i < p->n_streams; i++) {
+        if (h_n_samples[i] == 0) return FRB_ERR_INVALID_ARG;
+        EncStreamDev d;
+        d.n_samples = h_n_samples[i]; d.audio_base = h_audio_base[i]; d.out_offset = 0;
+        d.sample_rate = h_sample_rate[i]; d.frame_base = (uint32_t)frames;
+        d.n_frames = (uint32_t)((h_n_samples[i] + p->blocksize - 1) / p->blocksize); d.pad = 0;
+        frames += d.n_frames;
+        hs[i] = d;
+    }
+    if (frames == 0 || frames * p->channels > 0x7FFFFFFFull) return FRB_ERR_INVALID_ARG;
+    EncWorkspace w;
+    if (enc_ws_layout(p, frames, d_workspace, &w) > workspace_bytes) return FRB_ERR_OVERFLOW;
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<float> win(FRB_MAX_BLOCKSIZE, 1.0f);
+    make_tukey(win.data(), (int)p->blocksize, 0.5f / (float)level_cfg(p->level).windows);
+    FRB_CUDA(cudaMemcpyAsync(w.streams, hs.data(), sizeof(EncStreamDev) * hs.size(), cudaMemcpyHostToDevice, s));
+    FRB_CUDA(cudaMemcpyAsync(w.window, win.data(), sizeof(float) * FRB_MAX_BLOCKSIZE, cudaMemcpyHostToDevice, s));
+    FRB_CUDA(cudaMemsetAsync(w.err_flag, 0, 256, s));
+    FRB_CUDA(cudaStreamSynchronize(s));       // staging vectors are locals
+    const uint32_t slot_words = slot_words_for(p->blocksize, p->bps);
+    static bool attr_set = false;
+    if (!attr_set) {
+        FRB_CUDA(cudaFuncSetAttribute(k_encode_subframes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncShared)));
+        attr_set = true;
+    }
+    k_encode_subframes<<<(uint32_t)(frames * p->channels), kEncThreads, sizeof(EncShared), s>>>(
+        w.streams, p->n_streams, p->channels, p->bps, p->blocksize, p->level, d_audio, w.window, slot_words, w.slots, w.sub_bits);
+    FRB_LAUNCH_CHECK("k_encode_subframes");
+    k_frame_sizes<<<(uint32_t)((frames + 255) / 256), 256, 0, s>>>(w.streams, p->n_streams, p->channels, p->blocksize,
+                                                                 (uint32_t)frames, w.sub_bits, w.frame_bytes);
+    FRB_LAUNCH_CHECK("k_frame_sizes");
+    k_stream_scan<<<p->n_streams, 1024, 0, s>>>(w.streams, w.frame_bytes, w.frame_off, w.stream_bytes);
+    FRB_LAUNCH_CHECK("k_stream_scan");
+    if (d_stream_bytes)
+        FRB_CUDA(cudaMemcpyAsync(d_stream_bytes, w.stream_bytes, 8 * (size_t)p->n_streams, cudaMemcpyDeviceToDevice, s));
+    if (h_stream_bytes) {
+        FRB_CUDA(cudaMemcpyAsync(h_stream_bytes, w.stream_bytes, 8 * (size_t)p->n_streams, cudaMemcpyDeviceToHost, s));
+        FRB_CUDA(cudaStreamSynchronize(s));
+    }
+    return FRB_OK;
+}
+
+extern "C" int frb_encode_emit(const frb_encode_params *p, void *d_workspace, size_t workspace_bytes,
+                               const uint64_t *h_out_offset, uint8_t *d_out, size_t out_capacity,
+                               uint32_t *d_frame_bytes, void *stream) {
+    using namespace frb;
+    if (!enc_params_ok(p) || !d_workspace || !h_out_offset || !d_out) return FRB_ERR_INVALID_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    // recover the frame count from the stream table written by analyse
+    EncWorkspace w0;
+    (void)enc_ws_layout(p, 0, d_workspace, &w0);
+    EncStreamDev last;
+    FRB_CUDA(cudaMemcpyAsync(&last, w0.streams + (p->n_streams - 1), sizeof last, cudaMemcpyDeviceToHost, s));
+    FRB_CUDA(cudaStreamSynchronize(s));
+    const uint64_t frames = (uint64_t)last.frame_base + last.n_frames;
+    EncWorkspace w;
+    if (enc_ws_layout(p, frames, d_workspace, &w) > workspace_bytes) return FRB_ERR_OVERFLOW;
+    FRB_CUDA(cudaMemcpyAsync(w.out_offs, h_out_offset, 8 * (size_t)p->n_streams, cudaMemcpyHostToDevice, s));
+    k_set_out_offsets<<<(p->n_streams + 255) / 256, 256, 0, s>>>(w.streams, w.out_offs, p->n_streams);
+    FRB_LAUNCH_CHECK("k_set_out_offsets");
+    k_emit_frames<<<(uint32_t)frames, kEmitThreads, 0, s>>>(w.streams, p->n_streams, p->channels, p->bps, p->blocksize,
+                                                           (uint32_t)frames, w.sub_bits, w.slots, slot_words_for(p->blocksize, p->bps),
+                                                           w.frame_bytes, w.frame_off, d_out, (uint64_t)out_capacity, w.err_flag);
+    FRB_LAUNCH_CHECK("k_emit_frames");
+    if (d_frame_bytes)
+        FRB_CUDA(cudaMemcpyAsync(d_frame_bytes, w.frame_bytes, 4 * (size_t)frames, cudaMemcpyDeviceToDevice, s));
+    uint32_t h_err = 0;
+    FRB_CUDA(cudaMemcpyAsync(&h_err, w.err_flag, 4, cudaMemcpyDeviceToHost, s));
+    FRB_CUDA(cudaStreamSynchronize(s));
+    if (h_err) return FRB_ERR_OVERFLOW;
+    return FRB_OK;
+}
+static_assert(sizeof(frb::EncShared) <= 100 * 1024, "EncShared must allow >= 2 CTAs per SM");

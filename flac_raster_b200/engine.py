@@ -1,0 +1,220 @@
+"""Batch device API: tiles of a device-resident raster <-> FLAC frames on the GPU.
+
+This is the fast path behind SpatialFLACEncoder.encode(streaming=True) and
+SpatialFLACStreamer.get_tiles_by_bbox: the reference's serial per-tile loop
+(cli.py:553-622: window read -> temp TIFF -> tiff_to_flac -> bytes) becomes
+four batched launches over all tiles at once:
+  minmax_tiles -> normalize_tiles -> encode_analyse -> encode_emit
+and the reverse (extract, cli.py:297-315, looped) becomes
+  sync_scan -> decode_frames -> crc16 -> denormalize_tiles.
+PyTorch is used only for device buffers and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .normalization import audio_params_for
+
+TORCH_DTYPES = {
+    "uint8": torch.uint8, "int8": torch.int8, "uint16": torch.uint16, "int16": torch.int16,
+    "uint32": torch.uint32, "int32": torch.int32, "float32": torch.float32, "float64": torch.float64,
+}
+
+
+def tile_grid(height: int, width: int, tile_size: int) -> np.ndarray:
+    """Row-major tile windows exactly as cli.py:553-556 enumerates them (edge tiles are smaller)."""
+    rows = range(0, height, tile_size)
+    cols = range(0, width, tile_size)
+    t = np.zeros(len(rows) * len(cols), dtype=nat.TILE_DTYPE)
+    i = 0
+    for r in rows:
+        for c in cols:
+            t[i] = (r, c, min(tile_size, height - r), min(tile_size, width - c))
+            i += 1
+    return t
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev_bytes(n: int, device) -> torch.Tensor:
+    return torch.empty(max(int(n), 1), dtype=torch.uint8, device=device)
+
+
+@dataclass
+class EncodedTiles:
+    """Frames of a batch of tiles, still on the device."""
+    payload: torch.Tensor          # uint8, concatenated frame payloads (no metadata blocks)
+    offsets: np.ndarray            # int64 [n_tiles] start of each tile's frames in payload
+    sizes: np.ndarray              # int64 [n_tiles] bytes of frames per tile
+    minmax: np.ndarray             # float64 [n_tiles, 2] data_min/data_max per tile (normalization.py:149-153)
+    n_samples: np.ndarray          # int64 [n_tiles] samples per channel
+    sample_rates: np.ndarray       # uint32 [n_tiles]
+    channels: int
+    bps: int                       # FLAC bits per sample (16 or 32)
+    bits_per_sample: int           # the reference's notion (16 or 24)
+    blocksize: int
+
+
+class Engine:
+    """One per process / per GPU.  Keeps grow-only workspaces so steady-state calls do not allocate."""
+
+    def __init__(self, device: Optional[torch.device | int | str] = None):
+        nat.require_cuda()
+        if not torch.cuda.is_available():
+            raise nat.NativeError(nat.ERR_NO_DEVICE, "Engine", "torch sees no CUDA device")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.L = nat.lib()
+        self._ws: dict[str, torch.Tensor] = {}
+
+    # ---------------------------------------------------------------- helpers
+    def _buf(self, name: str, nbytes: int) -> torch.Tensor:
+        t = self._ws.get(name)
+        if t is None or t.numel() < nbytes:
+            t = None
+            self._ws.pop(name, None)
+            t = torch.empty(int(nbytes * 1.125) + 4096, dtype=torch.uint8, device=self.device)
+            self._ws[name] = t
+        return t
+
+    def release(self):
+        self._ws.clear()
+
+    # ------------------------------------------------------------------ encode
+    def normalize_tiles(self, raster: torch.Tensor, tiles: np.ndarray, bits_per_sample: Optional[int] = None):
+        """(bands,H,W) device raster -> (audio int32 planar per tile, audio_base, minmax_dev)."""
+        assert raster.is_cuda and raster.is_contiguous() and raster.dim() == 3
+        bands, H, W = raster.shape
+        dt = str(raster.dtype).replace("torch.", "")
+        code = nat.DTYPE_CODES[dt]
+        if bits_per_sample is None:
+            bits_per_sample = 16 if dt in ("uint8", "int8", "uint16", "int16") else 24
+        n_tiles = len(tiles)
+        npx = tiles["h"].astype(np.int64) * tiles["w"].astype(np.int64)
+        base = np.zeros(n_tiles, dtype=np.int64)
+        np.cumsum(npx[:-1] * bands, out=base[1:])
+        total = int((npx * bands).sum())
+        with torch.cuda.device(self.device):
+            s = _stream_ptr()
+            d_tiles = torch.from_numpy(tiles.view(np.uint32).reshape(-1, 4).astype(np.int64)).to(self.device).to(torch.int32) \
+                if False else torch.from_numpy(tiles.view(np.uint8).copy()).to(self.device, non_blocking=True)
+            d_base = torch.from_numpy(base).to(self.device, non_blocking=True)
+            d_minmax = torch.empty(2 * n_tiles, dtype=torch.float64, device=self.device)
+            audio = self._buf("audio", total * 4)
+            nat.check(self.L.frb_minmax_tiles(raster.data_ptr(), code, bands, H, W, d_tiles.data_ptr(), n_tiles,
+                                              d_minmax.data_ptr(), s), "frb_minmax_tiles")
+            nat.check(self.L.frb_normalize_tiles(raster.data_ptr(), code, bands, H, W, d_tiles.data_ptr(), n_tiles,
+                                                 d_minmax.data_ptr(), bits_per_sample, audio.data_ptr(),
+                                                 d_base.data_ptr(), s), "frb_normalize_tiles")
+        return audio, base, npx, d_minmax, bits_per_sample
+
+    def encode_audio(self, audio: torch.Tensor, n_samples: np.ndarray, audio_base: np.ndarray, sample_rates: np.ndarray,
+                     channels: int, bps: int, level: int = 5, blocksize: int = 4096):
+        """int32 planar audio on the device -> (payload uint8 tensor, offsets, sizes). One sync (sizes)."""
+        n_streams = len(n_samples)
+        p = nat.EncodeParams(n_streams, channels, bps, blocksize, level, 0)
+        frames = int(((n_samples + blocksize - 1) // blocksize).sum())
+        ws_bytes = C.c_size_t(0)
+        nat.check(self.L.frb_encode_workspace_size(C.byref(p), frames, C.byref(ws_bytes)), "frb_encode_workspace_size")
+        ws = self._buf("enc_ws", ws_bytes.value)
+        hn = np.ascontiguousarray(n_samples, dtype=np.uint64)
+        hr = np.ascontiguousarray(sample_rates, dtype=np.uint32)
+        hb = np.ascontiguousarray(audio_base, dtype=np.int64)
+        sizes = np.zeros(n_streams, dtype=np.uint64)
+        with torch.cuda.device(self.device):
+            s = _stream_ptr()
+            nat.check(self.L.frb_encode_analyse(C.byref(p), audio.data_ptr(), hn.ctypes.data, hr.ctypes.data, hb.ctypes.data,
+                                                ws.data_ptr(), ws.numel(), None, sizes.ctypes.data, s), "frb_encode_analyse")
+            offsets = np.zeros(n_streams, dtype=np.uint64)
+            np.cumsum(sizes[:-1], out=offsets[1:])
+            total = int(sizes.sum())
+            payload = self._buf("payload", total + 16)
+            nat.check(self.L.frb_encode_emit(C.byref(p), ws.data_ptr(), ws.numel(), offsets.ctypes.data,
+                                             payload.data_ptr(), payload.numel(), None, s), "frb_encode_emit")
+        return payload[:total], offsets.astype(np.int64), sizes.astype(np.int64)
+
+    def encode_tiles(self, raster: torch.Tensor, tiles: np.ndarray, level: int = 5, blocksize: int = 4096) -> EncodedTiles:
+        """Whole pipeline for a batch of tiles of one device-resident raster."""
+        bands = raster.shape[0]
+        if bands > nat.lib() and False:
+            pass
+        audio, base, npx, d_minmax, bits = self.normalize_tiles(raster, tiles)
+        bps = 16 if bits == 16 else 32            # pyflac derives bps from the array dtype (docs/sonos-pyflac.txt:1988-1991)
+        rates = np.array([audio_params_for((int(t["h"]), int(t["w"])), str(raster.dtype).replace("torch.", ""))[0] for t in tiles],
+                         dtype=np.uint32)
+        payload, offsets, sizes = self.encode_audio(audio, npx, base, rates, bands, bps, level, blocksize)
+        minmax = d_minmax.cpu().numpy().reshape(-1, 2)
+        return EncodedTiles(payload, offsets, sizes, minmax, npx, rates, bands, bps, bits, blocksize)
+
+    # ------------------------------------------------------------------ decode
+    def decode_streams(self, data: torch.Tensor, byte_offsets: np.ndarray, byte_lengths: np.ndarray, n_samples: np.ndarray,
+                       sample_rates: np.ndarray, channels: int, bps: int, blocksize: int = 4096, verify_crc: bool = True):
+        """Frames of many streams (device bytes) -> int32 planar audio on the device.
+
+        data must be readable 16 bytes past the last stream.  Returns (audio, audio_base, status[8])."""
+        n_streams = len(n_samples)
+        n_samples = np.asarray(n_samples, dtype=np.int64)
+        frames_per = (n_samples + blocksize - 1) // blocksize
+        st = np.zeros(n_streams, dtype=nat.DECODE_STREAM_DTYPE)
+        st["byte_offset"] = byte_offsets
+        st["byte_length"] = byte_lengths
+        st["n_samples"] = n_samples
+        base = np.zeros(n_streams, dtype=np.int64)
+        np.cumsum(n_samples[:-1] * channels, out=base[1:])
+        st["audio_base"] = base
+        st["sample_rate"] = sample_rates
+        fb = np.zeros(n_streams, dtype=np.int64)
+        np.cumsum(frames_per[:-1], out=fb[1:])
+        st["frame_base"] = fb
+        total_frames = int(frames_per.sum())
+        total = int((n_samples * channels).sum())
+        with torch.cuda.device(self.device):
+            s = _stream_ptr()
+            audio = self._buf("dec_audio", total * 4)
+            d_status = torch.zeros(8, dtype=torch.int32, device=self.device)
+            status = None
+            for max_order in (12, 32):
+                p = nat.DecodeParams(n_streams, channels, bps, blocksize, 1 if verify_crc else 0, max_order)
+                ws_bytes = C.c_size_t(0)
+                nat.check(self.L.frb_decode_workspace_size(C.byref(p), total_frames, C.byref(ws_bytes)), "frb_decode_workspace_size")
+                ws = self._buf("dec_ws", ws_bytes.value)
+                nat.check(self.L.frb_decode_batch(C.byref(p), st.ctypes.data, data.data_ptr(), total_frames, audio.data_ptr(),
+                                                  ws.data_ptr(), ws.numel(), d_status.data_ptr(), s), "frb_decode_batch")
+                status = d_status.cpu().numpy().astype(np.int64)
+                if status[4] == 0:
+                    break
+        return audio, base, status
+
+    def denormalize_tiles(self, audio: torch.Tensor, audio_base: np.ndarray, tiles: np.ndarray, minmax: np.ndarray,
+                          scale: float, out: torch.Tensor):
+        """int32 planar audio -> windows of the (bands,H,W) device raster `out` (denormalize_from_audio, int path)."""
+        bands, H, W = out.shape
+        dt = str(out.dtype).replace("torch.", "")
+        with torch.cuda.device(self.device):
+            s = _stream_ptr()
+            d_tiles = torch.from_numpy(tiles.view(np.uint8).copy()).to(self.device, non_blocking=True)
+            d_base = torch.from_numpy(np.ascontiguousarray(audio_base, dtype=np.int64)).to(self.device, non_blocking=True)
+            d_mm = torch.from_numpy(np.ascontiguousarray(minmax, dtype=np.float64).reshape(-1)).to(self.device, non_blocking=True)
+            nat.check(self.L.frb_denormalize_tiles(audio.data_ptr(), d_base.data_ptr(), d_tiles.data_ptr(), len(tiles),
+                                                   d_mm.data_ptr(), float(scale), out.data_ptr(), nat.DTYPE_CODES[dt],
+                                                   bands, H, W, s), "frb_denormalize_tiles")
+            # keep the staging tensors alive until the kernel has consumed them
+            torch.cuda.current_stream().synchronize()
+        return out
+
+
+_default_engine: Optional[Engine] = None
+
+
+def default_engine() -> Engine:
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine()
+    return _default_engine

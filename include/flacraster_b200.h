@@ -1,0 +1,243 @@
+/*
+ * flacraster_b200.h -- C ABI of libflacraster_b200.so (sm_100a CUDA FLAC engine).
+ *
+ * Drop-in boundary for flac-raster's one data-parallel hot path: raster
+ * samples -> FLAC frames -> raster samples.  Every entry point replaces a
+ * reference interface, cited as (file:line) into yharby/flac-raster:
+ *
+ *   sample mapping      normalization.py:126-202 (normalize_to_audio)
+ *                       normalization.py:205-253 (denormalize_from_audio)
+ *   codec (encode)      pyflac.StreamEncoder.process/finish at converter.py:139-154,
+ *                       spatial_encoder.py:291-304; FFI crossed today:
+ *                       FLAC__stream_encoder_process_interleaved
+ *                       (docs/sonos-pyflac.txt:1994-1997, cdef :3206-3263)
+ *   codec (decode)      pyflac.FileDecoder.process at converter.py:181-182, cli.py:479-480;
+ *                       FFI: FLAC__stream_decoder_process_until_end_of_stream
+ *                       (docs/sonos-pyflac.txt:1621, cdef :2826-2935)
+ *   tile loop           cli.py:553-622 (_create_streaming_flac), cli.py:297-315 (extract)
+ *
+ * Conventions: plain C types only; every function returns an int status
+ * (FRB_OK == 0), never throws, never allocates device memory behind the
+ * caller's back in the *device* API (section 2/3/4: caller passes workspaces;
+ * sizes come from the *_workspace_* queries).  `stream` is a cudaStream_t
+ * passed as void*.  Device-API calls are asynchronous on `stream` unless
+ * documented otherwise.  The host API (section 5) owns its device buffers and
+ * synchronises before returning.
+ */
+#ifndef FLACRASTER_B200_H
+#define FLACRASTER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- status */
+enum {
+    FRB_OK = 0,
+    FRB_ERR_INVALID_ARG = 1,
+    FRB_ERR_CUDA = 2,
+    FRB_ERR_UNSUPPORTED = 3,     /* e.g. variable-blocksize streams, blocksize > 4096 on encode */
+    FRB_ERR_BAD_STREAM = 4,      /* malformed FLAC input */
+    FRB_ERR_CRC = 5,             /* frame CRC-16 / header CRC-8 mismatch */
+    FRB_ERR_OVERFLOW = 6,        /* caller buffer too small */
+    FRB_ERR_NO_DEVICE = 7
+};
+
+/* sample dtype codes (numpy dtype of the raster, normalization.py:7-15) */
+enum {
+    FRB_U8 = 0, FRB_I8 = 1, FRB_U16 = 2, FRB_I16 = 3,
+    FRB_U32 = 4, FRB_I32 = 5, FRB_F32 = 6, FRB_F64 = 7
+};
+
+#define FRB_MAX_CHANNELS 8
+#define FRB_MAX_BLOCKSIZE 4096      /* reference always uses 4096 (converter.py:143) */
+
+/* --------------------------------------------------------- 1. misc/info */
+int frb_version(void);                      /* 100*major + minor */
+const char *frb_error_string(int status);
+const char *frb_last_cuda_error(void);      /* text of the last CUDA failure on this thread */
+int frb_device_count(int *count);
+/* number of kernel launches issued by this library since load (bench gpu_launches) */
+uint64_t frb_launch_count(void);
+
+/* ------------------------------------------------ 2. sample mapping (device)
+ * A "tile" is a window of a planar (bands, H, W) raster resident on the
+ * device; tile t covers rows [row_off, row_off+h) x cols [col_off, col_off+w).
+ * Its audio is `bands` planar channels of n = h*w samples (row-major), the
+ * planar equivalent of the reference's interleaved (H*W, bands) array
+ * (converter.py:99-110): channel c, sample i == pixel i of band c.
+ * Audio is always int32 on the device: tile t, channel c, sample i lives at
+ * audio[audio_base[t] + c*n_t + i].
+ */
+typedef struct frb_tile {
+    uint32_t row_off, col_off, h, w;
+} frb_tile;
+
+/* nanmin/nanmax over all bands of each tile (normalization.py:149-153).
+ * d_minmax: 2*n_tiles doubles {min,max}.  All-NaN tiles give NaN. */
+int frb_minmax_tiles(const void *d_raster, int dtype, uint32_t bands, uint32_t H, uint32_t W,
+                     const frb_tile *d_tiles, uint32_t n_tiles, double *d_minmax, void *stream);
+
+/* normalize_to_audio (normalization.py:156-187) for every tile, fp64, same
+ * operation order as numpy, truncating cast.  bits_per_sample: 16 -> scale
+ * 32767, 24 -> 8388607, else 2147483647.  d_audio_base: n_tiles int64. */
+int frb_normalize_tiles(const void *d_raster, int dtype, uint32_t bands, uint32_t H, uint32_t W,
+                        const frb_tile *d_tiles, uint32_t n_tiles, const double *d_minmax,
+                        int bits_per_sample, int32_t *d_audio, const int64_t *d_audio_base,
+                        void *stream);
+
+/* denormalize_from_audio (normalization.py:222-249), integer path
+ * (audio/scale, fp64), np.round for integer dtypes, scattered back into the
+ * planar raster windows.  scale is the divisor (32767, 8388607, ...). */
+int frb_denormalize_tiles(const int32_t *d_audio, const int64_t *d_audio_base,
+                          const frb_tile *d_tiles, uint32_t n_tiles, const double *d_minmax,
+                          double scale, void *d_raster, int dtype, uint32_t bands, uint32_t H,
+                          uint32_t W, void *stream);
+
+/* Flat elementwise forms used by the drop-in normalize_to_audio /
+ * denormalize_from_audio functions: n elements, any layout, one (min,max).
+ * out16 != 0 writes int16 (16-bit path), else int32. */
+int frb_minmax_flat(const void *d_src, int dtype, uint64_t n, double *d_minmax, void *stream);
+int frb_normalize_flat(const void *d_src, int dtype, uint64_t n, double data_min, double data_max,
+                       int bits_per_sample, void *d_out, int out16, void *stream);
+/* audio_kind: 0 int16, 1 int32, 2 float64 (pyflac's WAV round trip) */
+int frb_denormalize_flat(const void *d_audio, int audio_kind, uint64_t n, double data_min,
+                         double data_max, double scale, void *d_out, int dtype, void *stream);
+
+/* --------------------------------------------------- 3. encode (device)
+ * Batch of independent FLAC streams ("tiles"), all with the same channel
+ * count, bits per sample (16 or 32) and blocksize; per-stream length and
+ * sample rate.  Replaces one StreamEncoder.process/finish pair per tile
+ * (converter.py:139-154).  compression_level 0..8 follows libFLAC's preset
+ * table (docs/sonos-pyflac.txt:6926-6934).
+ */
+typedef struct frb_encode_params {
+    uint32_t n_streams;
+    uint32_t channels;          /* 1..8 */
+    uint32_t bps;               /* 16 or 32 (what pyflac derives, docs/sonos-pyflac.txt:1988-1991) */
+    uint32_t blocksize;         /* 16..4096 */
+    uint32_t level;             /* 0..8 */
+    uint32_t reserved;
+} frb_encode_params;
+
+/* Bytes of device workspace needed by frb_encode_analyse/emit for
+ * `total_frames` frames (sum over streams of ceil(n/blocksize)). */
+int frb_encode_workspace_size(const frb_encode_params *p, uint64_t total_frames, size_t *bytes);
+
+/* Pass 1: analyse + entropy-code every subframe into fixed slots of the
+ * workspace; compute per-frame byte sizes, per-stream payload sizes and the
+ * exclusive scans.  Host arrays (n_streams each): h_n_samples (per channel),
+ * h_sample_rate, h_audio_base (int64 index into d_audio).
+ * d_stream_bytes (device, n_streams uint64, optional) receives each stream's
+ * frame payload size; h_stream_bytes (host, n_streams uint64, optional) is
+ * filled after an internal stream synchronise when non-NULL. */
+int frb_encode_analyse(const frb_encode_params *p, const int32_t *d_audio,
+                       const uint64_t *h_n_samples, const uint32_t *h_sample_rate,
+                       const int64_t *h_audio_base, void *d_workspace, size_t workspace_bytes,
+                       uint64_t *d_stream_bytes, uint64_t *h_stream_bytes, void *stream);
+
+/* Pass 2: assemble frames (header, CRC-8, bit-concatenated subframes,
+ * padding, CRC-16) into d_out.  Stream s's frames are written contiguously
+ * starting at d_out + h_out_offset[s] (host array, bytes; the caller leaves
+ * room for metadata blocks in front of each stream).  d_frame_bytes
+ * (optional, total_frames uint32) receives every frame's size in stream order. */
+int frb_encode_emit(const frb_encode_params *p, void *d_workspace, size_t workspace_bytes,
+                    const uint64_t *h_out_offset, uint8_t *d_out, size_t out_capacity,
+                    uint32_t *d_frame_bytes, void *stream);
+
+/* --------------------------------------------------- 4. decode (device)
+ * Batch of FLAC streams whose bytes are resident on the device.  The host
+ * has parsed the metadata blocks (STREAMINFO) and passes, per stream, the
+ * byte range holding audio frames.  Reference-made streams carry no seek
+ * table and a zeroed STREAMINFO total, so frames are located by
+ * a parallel sync-code + CRC-8 scan.  Fixed-blocksize streams only (all the
+ * reference produces).  Replaces FileDecoder.process (converter.py:181-182).
+ */
+typedef struct frb_decode_stream {
+    uint64_t byte_offset;       /* first audio frame, offset into d_bytes */
+    uint64_t byte_length;       /* bytes of audio frames */
+    uint64_t n_samples;         /* expected samples per channel */
+    int64_t  audio_base;        /* index into d_audio for channel 0 sample 0 */
+    uint32_t sample_rate;
+    uint32_t frame_base;        /* exclusive scan of ceil(n_samples/blocksize) */
+} frb_decode_stream;
+
+typedef struct frb_decode_params {
+    uint32_t n_streams;
+    uint32_t channels;
+    uint32_t bps;
+    uint32_t blocksize;         /* STREAMINFO max blocksize */
+    uint32_t verify_crc16;      /* 1: check every frame's CRC-16 (libFLAC always does) */
+    uint32_t reserved;
+} frb_decode_params;
+
+int frb_decode_workspace_size(const frb_decode_params *p, uint64_t total_frames, size_t *bytes);
+
+/* d_bytes must be readable 16 bytes past the last stream's end.
+ * d_audio: int32 planar, same layout as section 2.  d_status: 4 uint32
+ * {frames_missing, crc16_errors, parse_errors, frames_decoded}. */
+int frb_decode_batch(const frb_decode_params *p, const frb_decode_stream *h_streams,
+                     const uint8_t *d_bytes, uint64_t total_frames, int32_t *d_audio,
+                     void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream);
+
+/* Frame discovery for a stream of unknown length (FileDecoder on a file
+ * whose STREAMINFO total_samples is 0 and no tags are known).  Synchronous.
+ * Returns the number of frames and the total samples per channel. */
+int frb_probe_stream(const uint8_t *d_bytes, uint64_t byte_offset, uint64_t byte_length,
+                     uint32_t channels, uint32_t bps, uint32_t blocksize, uint32_t sample_rate,
+                     uint64_t *n_frames, uint64_t *n_samples, void *stream);
+
+/* ------------------------------------------------------ 5. host API
+ * One-shot calls on HOST buffers (the e2e path: H2D, kernels, D2H inside).
+ * frb_host_encode takes the interleaved int32 buffer pyflac passes to
+ * FLAC__stream_encoder_process_interleaved and returns the frame payload
+ * (no metadata blocks) plus per-frame sizes; frb_host_decode takes the frame
+ * bytes of one stream and returns interleaved int32 samples
+ * (the layout of FLAC__StreamDecoderWriteCallback after column_stack,
+ * docs/sonos-pyflac.txt:1809-1854).
+ */
+int frb_host_encode(const int32_t *interleaved, uint64_t n_samples, uint32_t channels,
+                    uint32_t bps, uint32_t sample_rate, uint32_t level, uint32_t blocksize,
+                    uint64_t first_frame_number,
+                    uint8_t *out, size_t out_capacity, size_t *out_bytes,
+                    uint32_t *frame_bytes, size_t frame_capacity, size_t *n_frames);
+
+int frb_host_decode(const uint8_t *frames, size_t n_bytes, uint32_t channels, uint32_t bps,
+                    uint32_t blocksize, uint32_t sample_rate, uint64_t n_samples_hint,
+                    int32_t *interleaved_out, size_t out_capacity_samples,
+                    uint64_t *n_samples_out);
+
+/* libFLAC-shaped handle API: the exact calls pyflac's cffi layer makes
+ * (docs/sonos-pyflac.txt:2200-2212, :1994-1997, :2003-2014), so a binding
+ * written against FLAC__stream_encoder_* can be retargeted by renaming. */
+typedef struct frb_stream_encoder frb_stream_encoder;
+/* same shape as FLAC__StreamEncoderWriteCallback (docs/sonos-pyflac.txt:3192):
+ * returns 0 on success */
+typedef int (*frb_encoder_write_cb)(const frb_stream_encoder *enc, const uint8_t *buffer,
+                                    size_t bytes, uint32_t samples, uint32_t current_frame,
+                                    void *client_data);
+
+frb_stream_encoder *frb_stream_encoder_new(void);
+void frb_stream_encoder_delete(frb_stream_encoder *enc);
+int frb_stream_encoder_set_channels(frb_stream_encoder *enc, uint32_t v);
+int frb_stream_encoder_set_bits_per_sample(frb_stream_encoder *enc, uint32_t v);
+int frb_stream_encoder_set_sample_rate(frb_stream_encoder *enc, uint32_t v);
+int frb_stream_encoder_set_compression_level(frb_stream_encoder *enc, uint32_t v);
+int frb_stream_encoder_set_blocksize(frb_stream_encoder *enc, uint32_t v);
+int frb_stream_encoder_set_total_samples_estimate(frb_stream_encoder *enc, uint64_t v);
+/* emits "fLaC" + STREAMINFO + VORBIS_COMMENT(vendor) through the callback (samples == 0) */
+int frb_stream_encoder_init_stream(frb_stream_encoder *enc, frb_encoder_write_cb write_cb,
+                                   void *client_data);
+/* returns 1 (true) on success like FLAC__bool */
+int frb_stream_encoder_process_interleaved(frb_stream_encoder *enc, const int32_t *buffer,
+                                           uint32_t samples);
+int frb_stream_encoder_finish(frb_stream_encoder *enc);
+int frb_stream_encoder_get_state(const frb_stream_encoder *enc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLACRASTER_B200_H */
