@@ -77,6 +77,7 @@ _lib = None
 
 _EXPORTS = [
     "frb_version", "frb_error_string", "frb_last_cuda_error", "frb_device_count", "frb_launch_count",
+    "frb_profile_enable", "frb_profile_last_ms",
     "frb_minmax_tiles", "frb_normalize_tiles", "frb_denormalize_tiles",
     "frb_minmax_flat", "frb_normalize_flat", "frb_denormalize_flat",
     "frb_encode_workspace_size", "frb_encode_analyse", "frb_encode_emit",
@@ -110,6 +111,8 @@ def lib():
     L.frb_last_cuda_error.restype = C.c_char_p
     L.frb_device_count.argtypes = [C.POINTER(i32)]
     L.frb_launch_count.restype = u64
+    L.frb_profile_enable.argtypes = [i32]
+    L.frb_profile_last_ms.argtypes = [i32, C.POINTER(C.c_float)]
     L.frb_minmax_tiles.argtypes = [vp, i32, u32, u32, u32, vp, u32, vp, vp]
     L.frb_normalize_tiles.argtypes = [vp, i32, u32, u32, u32, vp, u32, vp, i32, vp, vp, vp]
     L.frb_denormalize_tiles.argtypes = [vp, vp, vp, u32, vp, C.c_double, vp, i32, u32, u32, u32, vp]
@@ -117,7 +120,7 @@ def lib():
     L.frb_normalize_flat.argtypes = [vp, i32, u64, C.c_double, C.c_double, i32, vp, i32, vp]
     L.frb_denormalize_flat.argtypes = [vp, i32, u64, C.c_double, C.c_double, C.c_double, vp, i32, vp]
     L.frb_encode_workspace_size.argtypes = [C.POINTER(EncodeParams), u64, C.POINTER(sz)]
-    L.frb_encode_analyse.argtypes = [C.POINTER(EncodeParams), vp, vp, vp, vp, vp, sz, vp, C.POINTER(u64), vp]
+    L.frb_encode_analyse.argtypes = [C.POINTER(EncodeParams), vp, vp, vp, vp, vp, sz, vp, vp, vp]
     L.frb_encode_emit.argtypes = [C.POINTER(EncodeParams), vp, sz, vp, vp, sz, vp, vp]
     L.frb_decode_workspace_size.argtypes = [C.POINTER(DecodeParams), u64, C.POINTER(sz)]
     L.frb_decode_batch.argtypes = [C.POINTER(DecodeParams), vp, vp, u64, vp, vp, sz, vp, vp]

@@ -1,0 +1,263 @@
+"""Drop-in for flac_raster.converter.RasterFLACConverter (reference src/flac_raster/converter.py).
+
+Same public methods and file formats; the codec work (normalisation, FLAC
+encode/decode, denormalisation) runs on the GPU through the C ABI.  Raster I/O
+(rasterio when present, else tiffio) and VORBIS tags stay in Python.
+"""
+from __future__ import annotations
+
+import json
+import logging
+from pathlib import Path
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import flacfmt
+from .normalization import NormalizationParams, audio_params_for
+from .tiffio import Raster, read_geotiff, write_geotiff
+
+# tag names written by the reference (converter.py:275-297)
+_GEO_FIELDS = [
+    "GEOSPATIAL_CRS", "GEOSPATIAL_WIDTH", "GEOSPATIAL_HEIGHT", "GEOSPATIAL_COUNT", "GEOSPATIAL_DTYPE",
+    "GEOSPATIAL_NODATA", "GEOSPATIAL_DATA_MIN", "GEOSPATIAL_DATA_MAX", "GEOSPATIAL_TRANSFORM",
+    "GEOSPATIAL_BOUNDS", "GEOSPATIAL_SPATIAL_TILING",
+]
+
+
+def affine9(transform) -> list:
+    """list(rasterio Affine) has nine entries (a,b,c,d,e,f,0,0,1); the reference stores that list."""
+    if transform is None:
+        return []
+    t = [float(v) for v in transform[:6]]
+    return t + [0.0, 0.0, 1.0]
+
+
+def metadata_tags(metadata: Dict) -> Dict[str, str]:
+    """VORBIS_COMMENT tags exactly as _embed_metadata_in_flac writes them (converter.py:275-297)."""
+    return {
+        "TITLE": "Geospatial Raster Data",
+        "DESCRIPTION": "TIFF raster converted to FLAC with geospatial metadata",
+        "ENCODER": "FLAC-Raster v0.1.0",
+        "GEOSPATIAL_CRS": str(metadata.get("crs", "")),
+        "GEOSPATIAL_WIDTH": str(metadata.get("width", 0)),
+        "GEOSPATIAL_HEIGHT": str(metadata.get("height", 0)),
+        "GEOSPATIAL_COUNT": str(metadata.get("count", 1)),
+        "GEOSPATIAL_DTYPE": str(metadata.get("dtype", "")),
+        "GEOSPATIAL_NODATA": str(metadata.get("nodata", "")),
+        "GEOSPATIAL_DATA_MIN": str(metadata.get("data_min", "")),
+        "GEOSPATIAL_DATA_MAX": str(metadata.get("data_max", "")),
+        "GEOSPATIAL_TRANSFORM": json.dumps(metadata.get("transform", [])),
+        "GEOSPATIAL_BOUNDS": json.dumps(metadata.get("bounds", [])),
+        "GEOSPATIAL_SPATIAL_TILING": str(metadata.get("spatial_tiling", False)),
+    }
+
+
+def parse_metadata_tags(tags: Dict[str, list]) -> Optional[Dict]:
+    """Inverse of metadata_tags with the reference's type rules (converter.py:356-377)."""
+    if "GEOSPATIAL_CRS" not in tags:
+        return None
+    md: Dict = {}
+    for field in _GEO_FIELDS:
+        if field not in tags:
+            continue
+        value = tags[field][0]
+        key = field.replace("GEOSPATIAL_", "").lower()
+        if key in ("width", "height", "count"):
+            md[key] = int(value) if value else 0
+        elif key in ("data_min", "data_max"):
+            md[key] = float(value) if value else 0.0
+        elif key in ("transform", "bounds"):
+            md[key] = json.loads(value) if value else []
+        elif key == "spatial_tiling":
+            md[key] = value.lower() == "true"
+        elif key == "nodata":
+            md[key] = None if value == "None" else float(value) if value else None
+        else:
+            md[key] = value
+    return md
+
+
+def tile_metadata(width, height, count, dtype, crs, transform, data_min, data_max, nodata, scale_factor) -> Dict:
+    """The raster_metadata dict of tiff_to_flac (converter.py:117-135)."""
+    t = transform or (1.0, 0.0, 0.0, 0.0, -1.0, 0.0)
+    left, top = t[2], t[5]
+    return {
+        "width": width, "height": height, "count": count, "dtype": str(dtype),
+        "crs": crs, "transform": affine9(transform) if transform else None,
+        "bounds": {"left": left, "bottom": top + height * t[4], "right": left + width * t[0], "top": top},
+        "data_min": data_min, "data_max": data_max, "nodata": nodata, "driver": "GTiff",
+        "scale_factor": scale_factor,
+    }
+
+
+def build_flac_file(frames: bytes, n_samples: int, channels: int, bps: int, sample_rate: int, blocksize: int,
+                    metadata: Optional[Dict], padding: int = 0) -> bytes:
+    """STREAMINFO + VORBIS tags (+ padding) + frames: one standalone FLAC file."""
+    si = flacfmt.StreamInfo(blocksize, blocksize, 0, 0, sample_rate, channels, bps, n_samples)
+    tags = metadata_tags(metadata) if metadata else {}
+    return flacfmt.build_header(si, tags, padding=padding) + bytes(frames)
+
+
+class RasterFLACConverter:
+    """Handles conversion between TIFF and FLAC formats for raster data (GPU codec)."""
+
+    def __init__(self):
+        self.metadata_key = "RASTER_METADATA"
+        self.logger = logging.getLogger("flac_raster.converter")
+
+    # ------------------------------------------------------------------ encode
+    def tiff_to_flac(self, tiff_path: Path, flac_path: Path, compression_level: int = 5,
+                     spatial_tiling: bool = False, tile_size: int = 512):
+        """Convert TIFF raster to FLAC format (reference converter.py:41-172)."""
+        tiff_path, flac_path = Path(tiff_path), Path(flac_path)
+        self.logger.info(f"Starting TIFF to FLAC conversion: {tiff_path} -> {flac_path}")
+        if spatial_tiling:
+            from .spatial_encoder import SpatialFLACEncoder
+
+            encoder = SpatialFLACEncoder(tile_size=tile_size)
+            return encoder.encode_spatial_flac(tiff_path, flac_path, compression_level)
+        raster = read_geotiff(tiff_path)
+        data = self.array_to_flac(raster.data, flac_path, compression_level, transform=raster.transform,
+                                  crs=raster.crs, nodata=raster.nodata)
+        out_size, in_size = flac_path.stat().st_size, tiff_path.stat().st_size
+        self.logger.info(f"Conversion complete: {out_size / 1024 / 1024:.2f} MB "
+                         f"(compression: {(1 - out_size / in_size) * 100:.1f}%)")
+        return data
+
+    def array_to_flac(self, data: np.ndarray, flac_path: Path, compression_level: int = 5, transform=None,
+                      crs: Optional[str] = None, nodata=None):
+        """Encode a (bands,H,W) or (H,W) array as one FLAC file (the body of tiff_to_flac)."""
+        import torch
+        from .engine import default_engine, tile_grid
+
+        arr = data if data.ndim == 3 else data[None]
+        bands, H, W = arr.shape
+        if bands > 8:
+            raise ValueError("FLAC supports at most 8 channels (bands)")
+        eng = default_engine()
+        dev = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).to(eng.device)
+        from .engine import TORCH_DTYPES
+        dev = dev.view(TORCH_DTYPES[str(arr.dtype)]).reshape(bands, H, W)
+        tiles = tile_grid(H, W, max(H, W))
+        enc = eng.encode_tiles(dev, tiles, compression_level)
+        frames = enc.payload.cpu().numpy().tobytes()
+        scale = 32767 if enc.bits_per_sample == 16 else 8388607
+        md = tile_metadata(W, H, bands, arr.dtype, crs, transform, float(enc.minmax[0, 0]), float(enc.minmax[0, 1]),
+                           nodata, scale)
+        blob = build_flac_file(frames, int(enc.n_samples[0]), bands, enc.bps, int(enc.sample_rates[0]), enc.blocksize,
+                               md, padding=1024)
+        Path(flac_path).write_bytes(blob)
+        return None
+
+    # ------------------------------------------------------------------ decode
+    def flac_to_tiff(self, flac_path: Path, tiff_path: Path):
+        """Convert FLAC back to TIFF format (reference converter.py:174-261)."""
+        flac_path, tiff_path = Path(flac_path), Path(tiff_path)
+        data, metadata = self.flac_to_array(flac_path)
+        transform = tuple(metadata["transform"][:6]) if metadata.get("transform") else None
+        write_geotiff(tiff_path, data, transform, metadata.get("crs") or None, metadata.get("nodata"))
+        self.logger.info(f"TIFF written successfully: {tiff_path.stat().st_size / 1024 / 1024:.2f} MB")
+
+    def flac_to_array(self, flac_path: Path):
+        """Decode one FLAC file to ((bands,H,W) array in the original dtype, metadata dict)."""
+        flac_path = Path(flac_path)
+        blob = flac_path.read_bytes()
+        hdr = flacfmt.parse_header(blob)
+        metadata = parse_metadata_tags(hdr.tags)
+        if not metadata:
+            sidecar = flac_path.with_suffix(".json")
+            if sidecar.exists():
+                metadata = json.loads(sidecar.read_text())
+        if not metadata:
+            self.logger.error("No metadata found in FLAC file or sidecar file")
+            raise ValueError("No metadata found in FLAC file or sidecar file")
+        return decode_tile_blobs([blob], [hdr], [metadata])[0], metadata
+
+    # kept for signature compatibility with the reference (converter.py:263, :329)
+    def _embed_metadata_in_flac(self, flac_path: Path, metadata: Dict):
+        blob = Path(flac_path).read_bytes()
+        hdr = flacfmt.parse_header(blob)
+        out = flacfmt.build_header(hdr.streaminfo, metadata_tags(metadata), padding=1024) + blob[hdr.first_frame_offset:]
+        Path(flac_path).write_bytes(out)
+
+    def _read_embedded_metadata(self, flac_path: Path) -> Optional[Dict]:
+        try:
+            hdr = flacfmt.parse_header(Path(flac_path).read_bytes())
+            md = parse_metadata_tags(hdr.tags)
+            if md:
+                return md
+        except ValueError as e:
+            self.logger.warning(f"Failed to read embedded metadata: {e}")
+        sidecar = Path(flac_path).with_suffix(".json")
+        if sidecar.exists():
+            return json.loads(sidecar.read_text())
+        return None
+
+
+def decode_tile_blobs(blobs, headers, metadatas, mosaic=None):
+    """Batch-decode complete per-tile FLAC files on the GPU.
+
+    blobs: list of bytes (each a standalone FLAC file as the streaming container holds them,
+    cli.py:594-598); headers/metadatas: parsed per tile.  Returns a list of (bands,h,w) arrays
+    in the original dtype (denormalize_from_audio integer path, normalization.py:222-249).
+    """
+    import torch
+    from . import _native as nat
+    from .engine import TORCH_DTYPES, default_engine
+
+    eng = default_engine()
+    n = len(blobs)
+    si0 = headers[0].streaminfo
+    channels, bps, blocksize = si0.channels, si0.bits_per_sample, si0.max_blocksize
+    offs = np.zeros(n, dtype=np.int64)
+    lens = np.zeros(n, dtype=np.int64)
+    nsamp = np.zeros(n, dtype=np.int64)
+    rates = np.zeros(n, dtype=np.uint32)
+    tiles = np.zeros(n, dtype=nat.TILE_DTYPE)
+    minmax = np.zeros((n, 2), dtype=np.float64)
+    pos = 0
+    parts = []
+    row = 0
+    maxw = 0
+    for i, (b, h, md) in enumerate(zip(blobs, headers, metadatas)):
+        si = h.streaminfo
+        if (si.channels, si.bits_per_sample, si.max_blocksize) != (channels, bps, blocksize):
+            raise ValueError("tiles of one batch must share channels, bits per sample and blocksize")
+        if md["count"] != si.channels:
+            raise ValueError("band count in tags does not match the FLAC channel count")
+        body = memoryview(b)[h.first_frame_offset:]
+        offs[i], lens[i] = pos, len(body)
+        parts.append(body)
+        pad = (-len(body)) % 4
+        if pad:
+            parts.append(b"\0" * pad)
+        pos += len(body) + pad
+        nsamp[i] = md["width"] * md["height"]
+        rates[i] = si.sample_rate
+        tiles[i] = (row, 0, md["height"], md["width"])
+        row += md["height"]
+        maxw = max(maxw, md["width"])
+        minmax[i] = (md["data_min"], md["data_max"])
+    parts.append(b"\0" * 32)
+    host = np.frombuffer(b"".join(parts), dtype=np.uint8)
+    data = torch.from_numpy(host).to(eng.device)
+    audio, base, status = eng.decode_streams(data, offs, lens, nsamp, rates, channels, bps, blocksize)
+    if status[0] or status[2]:
+        raise ValueError(f"malformed FLAC stream (missing frames={status[0]}, parse errors={status[2]})")
+    if status[1]:
+        raise ValueError(f"FLAC frame CRC-16 mismatch in {status[1]} frame(s)")
+    dtype = np.dtype(metadatas[0]["dtype"])
+    # decode default scale by audio width (converter.py:220-229)
+    scale = float(metadatas[0].get("scale_factor") or (32767 if bps == 16 else 8388607))
+    if bps == 16:
+        scale = 32767.0
+    out = torch.zeros(channels * row * maxw * dtype.itemsize, dtype=torch.uint8, device=eng.device)
+    out = out.view(TORCH_DTYPES[str(dtype)]).reshape(channels, row, maxw)
+    eng.denormalize_tiles(audio, base, tiles, minmax, scale, out)
+    host_out = out.reshape(-1).view(torch.uint8).cpu().numpy().view(dtype).reshape(channels, row, maxw)
+    res = []
+    for i in range(n):
+        r0, h_, w_ = int(tiles[i]["row_off"]), int(tiles[i]["h"]), int(tiles[i]["w"])
+        res.append(np.ascontiguousarray(host_out[:, r0:r0 + h_, :w_]))
+    return res

@@ -60,3 +60,13 @@ extern "C" int frb_device_count(int *count) {
     return FRB_OK;
 }
 extern "C" uint64_t frb_launch_count(void) { return frb::g_launches.load(); }
+
+extern "C" int frb_profile_enable(int on) { frb::g_prof_on = on != 0; return FRB_OK; }
+extern "C" int frb_profile_last_ms(int which, float *ms) {
+    if (which < 0 || which > 3 || !ms) return FRB_ERR_INVALID_ARG;
+    frb::ProfSlot &p = frb::g_prof[which];
+    if (!p.valid) return FRB_ERR_INVALID_ARG;
+    FRB_CUDA(cudaEventSynchronize(p.b));
+    FRB_CUDA(cudaEventElapsedTime(ms, p.a, p.b));
+    return FRB_OK;
+}

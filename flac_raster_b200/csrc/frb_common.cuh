@@ -32,6 +32,22 @@ inline int cuda_fail(cudaError_t e, const char *what) {
 
 constexpr int kNumSMs = 148;   // B200
 
+// ---- optional kernel timing (bench roofline) ---------------------------------
+struct ProfSlot { cudaEvent_t a = nullptr, b = nullptr; bool valid = false; };
+static bool g_prof_on = false;
+static ProfSlot g_prof[4];
+inline void prof_begin(int which, cudaStream_t s) {
+    if (!g_prof_on) return;
+    ProfSlot &p = g_prof[which];
+    if (!p.a) { cudaEventCreate(&p.a); cudaEventCreate(&p.b); }
+    cudaEventRecord(p.a, s);
+}
+inline void prof_end(int which, cudaStream_t s) {
+    if (!g_prof_on) return;
+    cudaEventRecord(g_prof[which].b, s);
+    g_prof[which].valid = true;
+}
+
 // ---- big-endian / bit helpers -------------------------------------------
 __device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
 

@@ -480,19 +480,23 @@ extern "C" int frb_decode_batch(const frb_decode_params *p, const frb_decode_str
         if (gx > cap) gx = cap;
         if (gx < 1) gx = 1;
         dim3 grid(gx, p->n_streams);
+        prof_begin(3, s);
         k_sync_scan<<<grid, 256, 0, s>>>(d_bytes, w.streams, p->channels, p->bps, p->blocksize, w.frame_pos, nullptr);
+        prof_end(3, s);
         FRB_LAUNCH_CHECK("k_sync_scan");
     }
     {
         uint32_t threads = kDecWarps * 32;
         uint32_t grid = (uint32_t)((total_frames + threads - 1) / threads);
         const bool wide = p->reserved > 12;
+        prof_begin(1, s);
         if (!wide)
             k_decode_frames<12><<<grid, threads, 0, s>>>(d_bytes, w.streams, p->n_streams, p->channels, p->bps, p->blocksize,
                                                         (uint32_t)total_frames, w.frame_pos, d_audio, w.chassign, d_status);
         else
             k_decode_frames<32><<<grid, threads, 0, s>>>(d_bytes, w.streams, p->n_streams, p->channels, p->bps, p->blocksize,
                                                         (uint32_t)total_frames, w.frame_pos, d_audio, w.chassign, d_status);
+        prof_end(1, s);
         FRB_LAUNCH_CHECK("k_decode_frames");
     }
     if (p->verify_crc16) {

@@ -962,8 +962,10 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const int32_t *d_a
         FRB_CUDA(cudaFuncSetAttribute(k_encode_subframes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncShared)));
         attr_set = true;
     }
+    prof_begin(0, s);
     k_encode_subframes<<<(uint32_t)(frames * p->channels), kEncThreads, sizeof(EncShared), s>>>(
         w.streams, p->n_streams, p->channels, p->bps, p->blocksize, p->level, d_audio, w.window, slot_words, w.slots, w.sub_bits);
+    prof_end(0, s);
     FRB_LAUNCH_CHECK("k_encode_subframes");
     k_frame_sizes<<<(uint32_t)((frames + 255) / 256), 256, 0, s>>>(w.streams, p->n_streams, p->channels, p->blocksize,
                                                                  (uint32_t)frames, w.sub_bits, w.frame_bytes);
@@ -997,9 +999,11 @@ extern "C" int frb_encode_emit(const frb_encode_params *p, void *d_workspace, si
     FRB_CUDA(cudaMemcpyAsync(w.out_offs, h_out_offset, 8 * (size_t)p->n_streams, cudaMemcpyHostToDevice, s));
     k_set_out_offsets<<<(p->n_streams + 255) / 256, 256, 0, s>>>(w.streams, w.out_offs, p->n_streams);
     FRB_LAUNCH_CHECK("k_set_out_offsets");
+    prof_begin(2, s);
     k_emit_frames<<<(uint32_t)frames, kEmitThreads, 0, s>>>(w.streams, p->n_streams, p->channels, p->bps, p->blocksize,
                                                            (uint32_t)frames, w.sub_bits, w.slots, slot_words_for(p->blocksize, p->bps),
                                                            w.frame_bytes, w.frame_off, d_out, (uint64_t)out_capacity, w.err_flag);
+    prof_end(2, s);
     FRB_LAUNCH_CHECK("k_emit_frames");
     if (d_frame_bytes)
         FRB_CUDA(cudaMemcpyAsync(d_frame_bytes, w.frame_bytes, 4 * (size_t)frames, cudaMemcpyDeviceToDevice, s));

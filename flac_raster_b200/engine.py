@@ -103,8 +103,7 @@ class Engine:
         total = int((npx * bands).sum())
         with torch.cuda.device(self.device):
             s = _stream_ptr()
-            d_tiles = torch.from_numpy(tiles.view(np.uint32).reshape(-1, 4).astype(np.int64)).to(self.device).to(torch.int32) \
-                if False else torch.from_numpy(tiles.view(np.uint8).copy()).to(self.device, non_blocking=True)
+            d_tiles = torch.from_numpy(tiles.view(np.uint8).copy()).to(self.device, non_blocking=True)
             d_base = torch.from_numpy(base).to(self.device, non_blocking=True)
             d_minmax = torch.empty(2 * n_tiles, dtype=torch.float64, device=self.device)
             audio = self._buf("audio", total * 4)
@@ -143,8 +142,8 @@ class Engine:
     def encode_tiles(self, raster: torch.Tensor, tiles: np.ndarray, level: int = 5, blocksize: int = 4096) -> EncodedTiles:
         """Whole pipeline for a batch of tiles of one device-resident raster."""
         bands = raster.shape[0]
-        if bands > nat.lib() and False:
-            pass
+        if not (1 <= bands <= 8):
+            raise ValueError("FLAC carries at most 8 channels (bands)")
         audio, base, npx, d_minmax, bits = self.normalize_tiles(raster, tiles)
         bps = 16 if bits == 16 else 32            # pyflac derives bps from the array dtype (docs/sonos-pyflac.txt:1988-1991)
         rates = np.array([audio_params_for((int(t["h"]), int(t["w"])), str(raster.dtype).replace("torch.", ""))[0] for t in tiles],

@@ -1,0 +1,404 @@
+"""Drop-in for flac_raster.spatial_encoder (reference src/flac_raster/spatial_encoder.py) plus the
+streaming container of cli.py:521-639 behind the README API (README.md:195-202):
+
+    SpatialFLACEncoder(tile_size=1024).encode("in.tif", "out.flac", streaming=True)
+    streamer = SpatialFLACStreamer("out.flac")
+    tile, meta = streamer.get_tile_by_id(42)
+    tiles = streamer.get_tiles_by_bbox(xmin, ymin, xmax, ymax)
+
+Streaming container (cli.py:625-630): [u32 BE index length][JSON index][tile FLAC files...];
+every tile is a complete standalone FLAC file with its own per-tile min/max tags, exactly what
+_create_streaming_flac produces by running tiff_to_flac on each window.  All tiles are encoded
+by ONE batched GPU call instead of the reference's serial per-tile loop, and all tiles of a
+bbox query are decoded by one batched call.
+"""
+from __future__ import annotations
+
+import base64
+import gzip
+import json
+import logging
+import struct
+from pathlib import Path
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import flacfmt
+from .converter import (RasterFLACConverter, build_flac_file, decode_tile_blobs, parse_metadata_tags,
+                        tile_metadata)
+from .tiffio import read_geotiff, window_transform
+
+
+class _Window:
+    """Stand-in for rasterio.windows.Window (only the four attributes the index needs)."""
+
+    def __init__(self, col_off, row_off, width, height):
+        self.col_off, self.row_off, self.width, self.height = col_off, row_off, width, height
+
+
+class SpatialFrame:
+    """Represents a spatial FLAC frame with bbox metadata (spatial_encoder.py:34-64)."""
+
+    def __init__(self, frame_id: int, bbox: Tuple[float, float, float, float], window, byte_offset: int = 0,
+                 byte_size: int = 0):
+        self.frame_id = frame_id
+        self.bbox = bbox
+        self.window = window
+        self.byte_offset = byte_offset
+        self.byte_size = byte_size
+
+    def to_dict(self) -> Dict:
+        return {
+            "frame_id": self.frame_id,
+            "bbox": self.bbox,
+            "window": {
+                "row_off": self.window.row_off,
+                "col_off": self.window.col_off,
+                "height": self.window.height,
+                "width": self.window.width,
+            },
+            "byte_offset": self.byte_offset,
+            "byte_size": self.byte_size,
+        }
+
+
+class SpatialIndex:
+    """Spatial index for FLAC frames with bbox lookup (spatial_encoder.py:67-96)."""
+
+    def __init__(self, frames: List[SpatialFrame], crs, transform):
+        self.frames = frames
+        self.crs = crs
+        self.transform = transform
+        self.total_bytes = sum(frame.byte_size for frame in frames)
+
+    def query_bbox(self, bbox: Tuple[float, float, float, float]) -> List[SpatialFrame]:
+        xmin, ymin, xmax, ymax = bbox
+        out = []
+        for frame in self.frames:
+            fxmin, fymin, fxmax, fymax = frame.bbox
+            if xmin < fxmax and xmax > fxmin and ymin < fymax and ymax > fymin:   # strict, spatial_encoder.py:85
+                out.append(frame)
+        return out
+
+    def to_dict(self) -> Dict:
+        return {
+            "crs": str(self.crs),
+            "transform": list(self.transform) if self.transform else [],
+            "frames": [frame.to_dict() for frame in self.frames],
+        }
+
+
+def _tile_bbox(transform, col, row, w, h):
+    """cli.py:561-565: xmin=c, ymax=f of the window transform; north-up assumed."""
+    t = window_transform(transform or (1.0, 0.0, 0.0, 0.0, -1.0, 0.0), col, row)
+    xmin, ymax = t[2], t[5]
+    return [xmin, ymax + h * t[4], xmin + w * t[0], ymax], t
+
+
+def build_streaming_container(raster_dev, transform, crs, nodata, dtype_name: str, tile_size: int,
+                              compression_level: int = 5, tiles: Optional[np.ndarray] = None, engine=None):
+    """Encode every tile of a device-resident (bands,H,W) raster and lay out the container.
+
+    Returns (index dict, list of per-tile header bytes, EncodedTiles).  Tile t's complete FLAC
+    file is headers[t] + payload[offsets[t]:offsets[t]+sizes[t]]; index byte_offset/byte_size are
+    the exclusive scan of the file sizes (cli.py:615-621).
+    """
+    from .engine import default_engine, tile_grid
+
+    eng = engine or default_engine()
+    bands, H, W = raster_dev.shape
+    if tiles is None:
+        tiles = tile_grid(H, W, tile_size)
+    enc = eng.encode_tiles(raster_dev, tiles, compression_level)
+    scale = 32767 if enc.bits_per_sample == 16 else 8388607
+    headers, frames = [], []
+    total = 0
+    a9 = (list(transform[:6]) + [0.0, 0.0, 1.0]) if transform else []
+    for i, t in enumerate(tiles):
+        r, c, h, w = int(t["row_off"]), int(t["col_off"]), int(t["h"]), int(t["w"])
+        bbox, ttrans = _tile_bbox(transform, c, r, w, h)
+        md = tile_metadata(w, h, bands, dtype_name, crs, ttrans if transform else None,
+                           float(enc.minmax[i, 0]), float(enc.minmax[i, 1]), nodata, scale)
+        si = flacfmt.StreamInfo(enc.blocksize, enc.blocksize, 0, 0, int(enc.sample_rates[i]), bands, enc.bps, int(enc.n_samples[i]))
+        from .converter import metadata_tags
+        hdr = flacfmt.build_header(si, metadata_tags(md))
+        headers.append(hdr)
+        size = len(hdr) + int(enc.sizes[i])
+        frames.append({
+            "frame_id": i,
+            "bbox": bbox,
+            "window": {"col_off": c, "row_off": r, "width": w, "height": h},
+            "byte_offset": total,
+            "byte_size": size,
+        })
+        total += size
+    index = {
+        "crs": str(crs), "transform": a9, "width": W, "height": H, "bands": bands, "dtype": dtype_name,
+        "tile_size": tile_size, "frames": frames,
+    }
+    return index, headers, enc
+
+
+def write_streaming_container(path, index: Dict, headers: List[bytes], payload: np.ndarray, offsets, sizes):
+    """cli.py:625-630."""
+    index_json = json.dumps(index, separators=(",", ":")).encode("utf-8")
+    mv = memoryview(payload)
+    with open(path, "wb") as f:
+        f.write(len(index_json).to_bytes(4, "big"))
+        f.write(index_json)
+        for h, o, s in zip(headers, offsets, sizes):
+            f.write(h)
+            f.write(mv[int(o):int(o) + int(s)])
+    return 4 + len(index_json)
+
+
+class SpatialFLACEncoder:
+    """Enhanced FLAC encoder with spatial tiling and bbox metadata (GPU-batched)."""
+
+    def __init__(self, tile_size: int = 512):
+        self.tile_size = tile_size
+        self.logger = logging.getLogger("flac_raster.spatial_encoder")
+        self.frames: List[SpatialFrame] = []
+        self.current_frame_id = 0
+        self.bytes_written = 0
+        self.output_file = None
+
+    def _calculate_tiles(self, height: int, width: int) -> List[Tuple[int, int, int, int]]:
+        tiles = []
+        for row_start in range(0, height, self.tile_size):
+            for col_start in range(0, width, self.tile_size):
+                row_end = min(row_start + self.tile_size, height)
+                col_end = min(col_start + self.tile_size, width)
+                tiles.append((row_start, col_start, row_end - row_start, col_end - col_start))
+        return tiles
+
+    def _tile_to_bbox(self, row_off, col_off, height, width, transform):
+        bbox, _ = _tile_bbox(transform, col_off, row_off, width, height)
+        return tuple(bbox)
+
+    # ---- README API -------------------------------------------------------------------
+    def encode(self, input_path, output_path, streaming: bool = True, compression_level: int = 5,
+               tile_size: Optional[int] = None):
+        """README.md:196-197.  streaming=True writes the Netflix-style container of cli.py:521-639."""
+        if tile_size is not None:
+            self.tile_size = tile_size
+        if not streaming:
+            return self.encode_spatial_flac(Path(input_path), Path(output_path), compression_level)
+        import torch
+        from .engine import TORCH_DTYPES, default_engine
+
+        raster = read_geotiff(input_path)
+        arr = raster.data
+        if arr.shape[0] > 8:
+            raise ValueError("FLAC supports at most 8 channels (bands)")
+        eng = default_engine()
+        dev = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).to(eng.device)
+        dev = dev.view(TORCH_DTYPES[str(arr.dtype)]).reshape(arr.shape)
+        index, headers, enc = build_streaming_container(dev, raster.transform, raster.crs, raster.nodata, str(arr.dtype),
+                                                        self.tile_size, compression_level, engine=eng)
+        payload = enc.payload.cpu().numpy()
+        write_streaming_container(output_path, index, headers, payload, enc.offsets, enc.sizes)
+        self.frames = [SpatialFrame(f["frame_id"], tuple(f["bbox"]),
+                                    _Window(f["window"]["col_off"], f["window"]["row_off"], f["window"]["width"], f["window"]["height"]),
+                                    f["byte_offset"], f["byte_size"]) for f in index["frames"]]
+        return SpatialIndex(self.frames, raster.crs, raster.transform)
+
+    # ---- legacy --spatial format ----------------------------------------------------------
+    def encode_spatial_flac(self, tiff_path: Path, flac_path: Path, compression_level: int = 5,
+                            enable_streaming: bool = True) -> SpatialIndex:
+        """Concatenated per-tile streams + gz/b64 index in stream 0's tags (spatial_encoder.py:155-258).
+
+        Unlike the reference, byte offsets are recorded AFTER stream 0's tags are in place, so they
+        are valid, and each tile stream carries its own min/max tags.
+        """
+        import torch
+        from .converter import metadata_tags
+        from .engine import TORCH_DTYPES, default_engine
+
+        raster = read_geotiff(tiff_path)
+        arr = raster.data
+        eng = default_engine()
+        dev = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).to(eng.device)
+        dev = dev.view(TORCH_DTYPES[str(arr.dtype)]).reshape(arr.shape)
+        index, headers, enc = build_streaming_container(dev, raster.transform, raster.crs, raster.nodata, str(arr.dtype),
+                                                        self.tile_size, compression_level, engine=eng)
+        payload = enc.payload.cpu().numpy()
+        frames_meta = index["frames"]
+
+        def make_index_tag(first_header_len):
+            shift = first_header_len - len(headers[0])
+            fl = []
+            for f in frames_meta:
+                w = f["window"]
+                fl.append({"frame_id": f["frame_id"], "bbox": f["bbox"],
+                           "window": {"row_off": w["row_off"], "col_off": w["col_off"], "height": w["height"], "width": w["width"]},
+                           "byte_offset": f["byte_offset"] + (shift if f["frame_id"] > 0 else 0),
+                           "byte_size": f["byte_size"] + (shift if f["frame_id"] == 0 else 0)})
+            d = {"crs": str(raster.crs), "transform": index["transform"], "frames": fl}
+            raw = json.dumps(d).encode("utf-8")
+            return base64.b64encode(gzip.compress(raw, mtime=0)).decode("ascii"), fl, len(raw)
+
+        hdr0 = flacfmt.parse_header(headers[0])
+        base_tags = {k: v[0] for k, v in hdr0.tags.items()}
+        first_len = len(headers[0])
+        for _ in range(8):       # header length depends on the index text: iterate to a fixed point
+            tag, fl, rawlen = make_index_tag(first_len)
+            tags = dict(base_tags)
+            tags.update({"GEOSPATIAL_SPATIAL_TILING": "True", "GEOSPATIAL_SPATIAL_INDEX": tag,
+                         "GEOSPATIAL_SPATIAL_INDEX_COMPRESSED": "gzip+base64",
+                         "GEOSPATIAL_SPATIAL_INDEX_ORIGINAL_SIZE": str(rawlen)})
+            new0 = flacfmt.build_header(hdr0.streaminfo, tags)
+            if len(new0) == first_len:
+                break
+            first_len = len(new0)
+        headers = [new0] + headers[1:]
+        mv = memoryview(payload)
+        with open(flac_path, "wb") as f:
+            for h, o, s in zip(headers, enc.offsets, enc.sizes):
+                f.write(h)
+                f.write(mv[int(o):int(o) + int(s)])
+        self.frames = [SpatialFrame(d["frame_id"], tuple(d["bbox"]),
+                                    _Window(d["window"]["col_off"], d["window"]["row_off"], d["window"]["width"], d["window"]["height"]),
+                                    d["byte_offset"], d["byte_size"]) for d in fl]
+        return SpatialIndex(self.frames, raster.crs, raster.transform)
+
+
+def _intersects(bbox, fb) -> bool:
+    """Strict intersection test of cli.py:273-278."""
+    return bbox[0] < fb[2] and bbox[2] > fb[0] and bbox[1] < fb[3] and bbox[3] > fb[1]
+
+
+class SpatialFLACStreamer:
+    """Reads tiles from a streaming container or a legacy --spatial file (local path or URL)."""
+
+    def __init__(self, flac_path_or_url):
+        self.source = str(flac_path_or_url)
+        self.logger = logging.getLogger("flac_raster.spatial_encoder")
+        self.is_url = self.source.startswith(("http://", "https://", "s3://", "gs://", "az://"))
+        self.flac_path = None if self.is_url else Path(self.source)
+        self.metadata: Optional[Dict] = None      # streaming container index
+        self.header_size = 0
+        self.spatial_index: Optional[SpatialIndex] = None
+        self._load_spatial_index()
+
+    # ---- byte access ---------------------------------------------------------------------
+    def _read_range(self, start: int, end_inclusive: int) -> bytes:
+        if self.is_url:
+            from .remote import RemoteFile
+
+            return RemoteFile(self.source).read_range(start, end_inclusive)
+        with open(self.flac_path, "rb") as f:
+            f.seek(start)
+            return f.read(end_inclusive - start + 1)
+
+    def _load_spatial_index(self):
+        if not self.is_url and not self.flac_path.exists():
+            raise FileNotFoundError(f"FLAC file not found: {self.flac_path}")
+        head = self._read_range(0, 3)
+        if head == b"fLaC":
+            self._load_legacy_index()
+            return
+        # streaming container: [u32 BE][JSON] (cli.py:224-235)
+        index_size = struct.unpack(">I", head)[0]
+        self.metadata = json.loads(self._read_range(4, 3 + index_size).decode("utf-8"))
+        self.header_size = 4 + index_size
+        frames = [SpatialFrame(f["frame_id"], tuple(f["bbox"]),
+                               _Window(f["window"]["col_off"], f["window"]["row_off"], f["window"]["width"], f["window"]["height"]),
+                               f["byte_offset"], f["byte_size"]) for f in self.metadata["frames"]]
+        self.spatial_index = SpatialIndex(frames, self.metadata.get("crs"), self.metadata.get("transform"))
+
+    def _load_legacy_index(self):
+        """Index from the first stream's VORBIS tags (spatial_encoder.py:434-515)."""
+        blob = self._read_range(0, (1 << 20) - 1)           # same first-MiB probe as the reference
+        hdr = flacfmt.parse_header(blob)
+        tag = hdr.tags.get("GEOSPATIAL_SPATIAL_INDEX")
+        if not tag:
+            raise ValueError("No spatial index found in FLAC metadata")
+        raw = tag[0]
+        if hdr.tags.get("GEOSPATIAL_SPATIAL_INDEX_COMPRESSED", [""])[0] == "gzip+base64":
+            raw = gzip.decompress(base64.b64decode(raw)).decode("utf-8")
+        d = json.loads(raw)
+        frames = [SpatialFrame(f["frame_id"], tuple(f["bbox"]),
+                               _Window(f["window"]["col_off"], f["window"]["row_off"], f["window"]["width"], f["window"]["height"]),
+                               f["byte_offset"], f["byte_size"]) for f in d["frames"]]
+        self.spatial_index = SpatialIndex(frames, d.get("crs"), d.get("transform"))
+        self.header_size = 0
+
+    # ---- reference methods (byte ranges only, spatial_encoder.py:517-567) ----------------------
+    def get_byte_ranges_for_bbox(self, bbox) -> List[Tuple[int, int]]:
+        frames = self.spatial_index.query_bbox(bbox)
+        ranges = sorted((self.header_size + f.byte_offset, self.header_size + f.byte_offset + f.byte_size - 1) for f in frames)
+        merged: List[Tuple[int, int]] = []
+        for s, e in ranges:
+            if merged and s <= merged[-1][1] + 1:
+                merged[-1] = (merged[-1][0], max(merged[-1][1], e))
+            else:
+                merged.append((s, e))
+        return merged
+
+    def stream_bbox_data(self, bbox) -> bytes:
+        return b"".join(self._read_range(s, e) for s, e in self.get_byte_ranges_for_bbox(bbox))
+
+    # ---- README API: decode on the GPU ----------------------------------------------------------
+    def _fetch_tiles(self, frames: List[SpatialFrame]) -> List[bytes]:
+        # merge adjacent ranges so a bbox of neighbouring tiles is one read / one HTTP request
+        order = sorted(range(len(frames)), key=lambda i: frames[i].byte_offset)
+        blobs: List[Optional[bytes]] = [None] * len(frames)
+        i = 0
+        while i < len(order):
+            j = i
+            start = frames[order[i]].byte_offset
+            end = start + frames[order[i]].byte_size
+            while j + 1 < len(order) and frames[order[j + 1]].byte_offset == end:
+                j += 1
+                end += frames[order[j]].byte_size
+            chunk = self._read_range(self.header_size + start, self.header_size + end - 1)
+            for k in range(i, j + 1):
+                f = frames[order[k]]
+                o = f.byte_offset - start
+                blobs[order[k]] = chunk[o:o + f.byte_size]
+            i = j + 1
+        return blobs   # type: ignore[return-value]
+
+    def _decode(self, frames: List[SpatialFrame]):
+        blobs = self._fetch_tiles(frames)
+        headers = [flacfmt.parse_header(b) for b in blobs]
+        metas = []
+        for h in headers:
+            md = parse_metadata_tags(h.tags)
+            if not md:
+                raise ValueError("No metadata found in FLAC file or sidecar file")
+            metas.append(md)
+        arrays = decode_tile_blobs(blobs, headers, metas)
+        out = []
+        for f, a, md in zip(frames, arrays, metas):
+            meta = dict(md)
+            meta.update({"frame_id": f.frame_id, "bbox": list(f.bbox),
+                         "window": {"col_off": f.window.col_off, "row_off": f.window.row_off,
+                                    "width": f.window.width, "height": f.window.height},
+                         "byte_offset": f.byte_offset, "byte_size": f.byte_size})
+            out.append((a, meta))
+        return out
+
+    def get_tile_by_id(self, tile_id: int):
+        """README.md:200-201 -> (tile_data (bands,h,w), metadata).  cli.py:243-247 semantics."""
+        frame = next((f for f in self.spatial_index.frames if f.frame_id == tile_id), None)
+        if frame is None:
+            raise KeyError(f"Tile ID {tile_id} not found")
+        return self._decode([frame])[0]
+
+    def get_tiles_by_bbox(self, xmin, ymin, xmax, ymax):
+        """README.md:202 -> list of (tile_data, metadata) for ALL intersecting tiles (one batched decode)."""
+        frames = [f for f in self.spatial_index.frames if _intersects((xmin, ymin, xmax, ymax), f.bbox)]
+        if not frames:
+            return []
+        return self._decode(frames)
+
+    def get_center_tile(self):
+        """cli.py:250-262: tile whose centroid is nearest the centroid of the union of bboxes."""
+        fr = self.spatial_index.frames
+        cx = (min(f.bbox[0] for f in fr) + max(f.bbox[2] for f in fr)) / 2
+        cy = (min(f.bbox[1] for f in fr) + max(f.bbox[3] for f in fr)) / 2
+        best = min(fr, key=lambda f: ((f.bbox[0] + f.bbox[2]) / 2 - cx) ** 2 + ((f.bbox[1] + f.bbox[3]) / 2 - cy) ** 2)
+        return self._decode([best])[0]

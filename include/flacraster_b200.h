@@ -63,6 +63,12 @@ int frb_device_count(int *count);
 /* number of kernel launches issued by this library since load (bench gpu_launches) */
 uint64_t frb_launch_count(void);
 
+/* Optional per-kernel timing: when enabled the library brackets its dominant kernels with
+ * cudaEvents on the caller's stream.  which: 0 k_encode_subframes, 1 k_decode_frames,
+ * 2 k_emit_frames, 3 k_sync_scan.  frb_profile_last_ms synchronises on the end event. */
+int frb_profile_enable(int on);
+int frb_profile_last_ms(int which, float *ms);
+
 /* ------------------------------------------------ 2. sample mapping (device)
  * A "tile" is a window of a planar (bands, H, W) raster resident on the
  * device; tile t covers rows [row_off, row_off+h) x cols [col_off, col_off+w).

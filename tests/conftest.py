@@ -1,0 +1,54 @@
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+GOLDEN = ROOT / "tests" / "golden"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import flac_oracle
+    flac_oracle.build()
+    return flac_oracle
+
+
+@pytest.fixture(scope="session")
+def rgb_pcm(oracle):
+    pcm, _ = oracle.decode((GOLDEN / "sample_rgb.flac").read_bytes())
+    return pcm
+
+
+def signal_cases(seed=7):
+    """Seeded (N,C) int32 signals with their FLAC bits per sample; shared by oracle and GPU tests."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(50000)
+    c = {}
+    c["sine16_1ch"] = ((8000 * np.sin(t / 37.0) + 500 * rng.standard_normal(t.size)).astype(np.int32).reshape(-1, 1), 16)
+    c["noise16_3ch"] = (rng.integers(-32768, 32767, size=(20000, 3)).astype(np.int32), 16)
+    c["smooth16_8ch"] = (np.cumsum(rng.integers(-20, 21, size=(30000, 8)), axis=0).astype(np.int32), 16)
+    c["const16"] = (np.full((9000, 1), -32767, dtype=np.int32), 16)
+    c["zeros32"] = (np.zeros((8192, 1), dtype=np.int32), 32)
+    c["wasted16_2ch"] = ((rng.integers(-2000, 2000, size=(12000, 2)) * 8).astype(np.int32), 16)
+    c["dem24_1ch"] = ((4e6 * np.sin(t / 300.0) + 2000 * rng.standard_normal(t.size)).astype(np.int32).reshape(-1, 1), 32)
+    c["noise24_2ch"] = (rng.integers(-8388607, 8388607, size=(10000, 2)).astype(np.int32), 32)
+    c["tiny3"] = (np.array([[1], [2], [-3]], dtype=np.int32), 16)
+    c["tail17"] = ((1000 * np.sin(np.arange(4096 + 17) / 9.0)).astype(np.int32).reshape(-1, 1), 16)
+    c["exact8192"] = ((1000 * np.sin(np.arange(8192) / 9.0)).astype(np.int32).reshape(-1, 1), 16)
+    c["extremes16"] = (np.where(rng.random((6000, 1)) < 0.5, -32767, 32767).astype(np.int32), 16)
+    c["ramp24"] = ((np.arange(20000) * 397 - 4000000).astype(np.int32).reshape(-1, 1), 32)
+    return c

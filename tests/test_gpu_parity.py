@@ -1,0 +1,384 @@
+"""GPU parity suite (-m gpu): the CUDA path through the C ABI vs the oracle and the golden fixtures."""
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, signal_cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nat():
+    from flac_raster_b200 import _native
+    _native.require_cuda()
+    return _native
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _full_stream(payload, x, bps, rate):
+    from flac_raster_b200 import flacfmt
+    si = flacfmt.StreamInfo(4096, 4096, 0, 0, rate, x.shape[1], bps, x.shape[0])
+    return flacfmt.build_header(si) + bytes(payload)
+
+
+# ------------------------------------------------------------------ sample mapping
+def test_normalize_kernels_match_reference_vectors(nat, torch_cuda):
+    """Bit-identical to the real reference module's outputs for all 8 dtypes, NaN, constant arrays."""
+    from flac_raster_b200 import NormalizationParams, denormalize_from_audio, normalize_to_audio
+    z = np.load(GOLDEN / "normalization_vectors.npz")
+    keys = sorted(set(k.rsplit("__", 1)[0] for k in z.files if k.endswith("__in")))
+    for k in keys:
+        x, a, b, p = z[k + "__in"], z[k + "__audio"], z[k + "__back"], z[k + "__params"]
+        audio, params = normalize_to_audio(x.reshape(-1, 3), int(p[2]))
+        assert audio.dtype == a.dtype and np.array_equal(audio, a), k
+        assert params.scale_factor == int(p[3]) and params.original_dtype == str(x.dtype)
+        assert params.data_min == p[0] or (np.isnan(params.data_min) and np.isnan(p[0]))
+        assert params.data_max == p[1] or (np.isnan(params.data_max) and np.isnan(p[1]))
+        back = denormalize_from_audio(audio, params)
+        assert back.dtype == b.dtype and np.array_equal(back, b, equal_nan=True), k
+
+
+def test_normalize_large_random_vs_oracle(nat, torch_cuda):
+    from flac_raster_b200 import denormalize_from_audio, normalize_to_audio
+    from oracle import normalization_oracle as no
+    rng = np.random.default_rng(3)
+    for dt, bits in (("uint16", 16), ("int16", 16), ("float32", 24), ("int32", 24), ("uint8", 16), ("float64", 24)):
+        if dt.startswith("float"):
+            x = (rng.standard_normal((700, 1031)) * 1e3).astype(dt)
+            x[5, 7] = np.nan
+            x[9, 9] = np.inf if dt == "float64" else x[9, 9]
+        else:
+            info = np.iinfo(dt)
+            x = rng.integers(info.min, info.max, size=(700, 1031), endpoint=True).astype(dt)
+        a, p = normalize_to_audio(x, bits)
+        a2, p2 = no.normalize_to_audio(x, bits)
+        assert np.array_equal(a, a2) and p.data_min == p2["data_min"] and p.data_max == p2["data_max"], dt
+        if not np.isinf(p.data_max):
+            b = denormalize_from_audio(a, p)
+            b2 = no.denormalize_from_audio(a2, p2["data_min"], p2["data_max"], dt, p2["scale_factor"])
+            assert np.array_equal(b, b2, equal_nan=True), dt
+    # explicit min/max override and the float (pyflac WAV) branch of denormalize
+    x = rng.integers(0, 4000, size=5000).astype(np.uint16)
+    a, p = normalize_to_audio(x, 16, data_min=0.0, data_max=11672.0)
+    a2, _ = no.normalize_to_audio(x, 16, 0.0, 11672.0)
+    assert np.array_equal(a, a2)
+    f = a.astype(np.float64) / 32768.0
+    assert np.array_equal(denormalize_from_audio(f, p), no.denormalize_from_audio(f, 0.0, 11672.0, "uint16", 32767))
+
+
+# ------------------------------------------------------------------ decode
+def test_decode_reference_goldens(nat, oracle):
+    """Reference-encoded files decode bit-exactly through the GPU decoder (north_star part 2)."""
+    from flac_raster_b200 import flacfmt
+    data = (GOLDEN / "sample_rgb.flac").read_bytes()
+    hdr = flacfmt.parse_header(data)
+    ref, _ = oracle.decode(data)
+    si = hdr.streaminfo
+    for hint in (65536, 0):           # with and without the sample count (STREAMINFO total is 0 in reference files)
+        out = nat.host_decode(data[hdr.first_frame_offset:], si.channels, si.bits_per_sample, si.max_blocksize, si.sample_rate, hint)
+        assert np.array_equal(out, ref)
+    data = (GOLDEN / "sample_dem.flac").read_bytes()
+    pos = 0
+    while pos < len(data):
+        ref, info = oracle.decode(data[pos:])
+        h = flacfmt.parse_header(data[pos:])
+        seg = data[pos + h.first_frame_offset: pos + int(info.bytes_consumed)]
+        out = nat.host_decode(seg, 1, 32, 4096, 44100, 0)
+        assert np.array_equal(out, ref)
+        pos += int(info.bytes_consumed)
+
+
+@pytest.mark.parametrize("level", [0, 5, 8])
+def test_decode_oracle_encoded_streams(nat, oracle, level):
+    from flac_raster_b200 import flacfmt
+    for name, (x, bps) in signal_cases().items():
+        enc, _ = oracle.encode(x, bps, 48000, level)
+        h = flacfmt.parse_header(enc)
+        out = nat.host_decode(enc[h.first_frame_offset:], x.shape[1], bps, 4096, 48000, x.shape[0])
+        assert np.array_equal(out, x), (name, level)
+
+
+def test_decode_detects_corruption(nat, oracle):
+    x, bps = signal_cases()["sine16_1ch"]
+    enc, _ = oracle.encode(x, bps, 44100, 5)
+    from flac_raster_b200 import flacfmt
+    off = flacfmt.parse_header(enc).first_frame_offset
+    bad = bytearray(enc[off:])
+    bad[len(bad) // 2] ^= 0x04
+    with pytest.raises(nat.NativeError) as ei:
+        nat.host_decode(bytes(bad), 1, 16, 4096, 44100, x.shape[0])
+    assert ei.value.status in (nat.ERR_CRC, nat.ERR_BAD_STREAM)
+    with pytest.raises(nat.NativeError):                      # truncated stream: frames missing
+        nat.host_decode(bytes(enc[off:off + 3000]), 1, 16, 4096, 44100, x.shape[0])
+
+
+# ------------------------------------------------------------------ encode
+@pytest.mark.parametrize("level", [0, 1, 2, 3, 4, 5, 6, 7, 8])
+def test_encode_matches_oracle_and_roundtrips(nat, oracle, level):
+    """GPU frames: decoded bit-exactly by the oracle decoder, byte-identical to the libFLAC-procedure
+    oracle encoder, and (as a size gate) never more than 1 % larger."""
+    for name, (x, bps) in signal_cases().items():
+        payload, fs = nat.host_encode(x, bps, 44100, level)
+        assert int(fs.sum()) == len(payload)
+        dec, info = oracle.decode(_full_stream(payload, x, bps, 44100))
+        assert np.array_equal(dec, x), (name, level)
+        oenc, ofs = oracle.encode(x, bps, 44100, level)
+        osz = int(ofs.sum())
+        assert len(payload) <= 1.01 * osz + 16, (name, level, len(payload), osz)
+        assert bytes(payload) == oenc[len(oenc) - osz:], (name, level)
+        assert list(fs) == list(ofs)
+        back = nat.host_decode(payload, x.shape[1], bps, 4096, 44100, x.shape[0])
+        assert np.array_equal(back, x)
+
+
+def test_encode_golden_rgb_is_byte_identical_to_libflac(nat, rgb_pcm):
+    """Level 5 on normalize_to_audio(sample_rgb.tif): the GPU emits libFLAC 1.4.3's exact frame bytes."""
+    golden = (GOLDEN / "sample_rgb.flac").read_bytes()
+    payload, fs = nat.host_encode(rgb_pcm, 16, 44100, 5)
+    assert len(payload) == 178857 <= 1.01 * 178857
+    assert bytes(payload) == golden[86:]
+
+
+def test_gpu_streams_accepted_by_ffmpeg(nat):
+    ff = pytest.importorskip("oracle.ffmpeg_flac")
+    if not ff.available():
+        pytest.skip("bundled FFmpeg libraries not found")
+    from flac_raster_b200 import flacfmt
+    for name, (x, bps) in signal_cases().items():
+        if name == "tiny3":
+            continue
+        payload, _ = nat.host_encode(x, bps, 48000, 8)
+        si = flacfmt.StreamInfo(4096, 4096, 0, 0, 48000, x.shape[1], bps, x.shape[0])
+        out = ff.decode_bytes(flacfmt.build_header(si) + bytes(payload), x.shape[1])
+        assert np.array_equal(out, x), name
+
+
+def test_pyflac_shim_callback_contract(nat, oracle, tmp_path):
+    """StreamEncoder/FileDecoder behave like pyflac's (header chunks with num_samples == 0 first, then
+    one callback per frame with current_frame == index), and the written file decodes everywhere."""
+    from flac_raster_b200 import codec
+    x = signal_cases()["smooth16_8ch"][0].astype(np.int16)
+    calls = []
+    path = tmp_path / "shim.flac"
+    fh = open(path, "wb")
+
+    def cb(data, num_bytes, num_samples, current_frame):
+        calls.append((num_bytes, num_samples, current_frame))
+        fh.write(data[:num_bytes])
+
+    enc = codec.StreamEncoder(write_callback=cb, sample_rate=48000, compression_level=5, blocksize=4096)
+    enc._channels, enc._bits_per_sample = 8, 16
+    enc.process(x)
+    assert enc.finish() is True
+    fh.close()
+    hdr_calls = [c for c in calls if c[1] == 0]
+    frame_calls = [c for c in calls if c[1] != 0]
+    assert calls[:len(hdr_calls)] == hdr_calls and hdr_calls[0][0] == 4
+    assert [c[2] for c in frame_calls] == list(range(len(frame_calls))) == list(range((len(x) + 4095) // 4096))
+    assert frame_calls[-1][1] == len(x) - 4096 * (len(frame_calls) - 1)
+    dec, info = oracle.decode(path.read_bytes())
+    assert np.array_equal(dec, x.astype(np.int32)) and info.total_samples_streaminfo == 0
+    audio, rate = codec.FileDecoder(str(path)).process()
+    assert rate == 48000 and audio.dtype == np.int16 and np.array_equal(audio, x)
+    f64, _ = codec.FileDecoder(str(path), compat_pyflac_float=True).process()
+    assert f64.dtype == np.float64 and np.array_equal(f64, x / 32768.0)
+    # reference-made file through the shim
+    g, r = codec.FileDecoder(str(GOLDEN / "sample_rgb.flac")).process()
+    assert r == 44100 and g.shape == (65536, 3)
+
+
+# ------------------------------------------------------------------ public API (configs C1, C2)
+def test_config1_dem_roundtrip(nat, oracle, tmp_path):
+    """BASELINE config 1: sample_dem.tif -> FLAC -> TIFF, level 5, bit-exact; file is a valid tagged FLAC."""
+    from flac_raster_b200 import RasterFLACConverter, flacfmt
+    from flac_raster_b200.tiffio import read_geotiff
+    from oracle import normalization_oracle as no
+    conv = RasterFLACConverter()
+    flac, tif = tmp_path / "dem.flac", tmp_path / "dem.tif"
+    conv.tiff_to_flac(GOLDEN / "sample_dem.tif", flac, compression_level=5)
+    conv.flac_to_tiff(flac, tif)
+    a, b = read_geotiff(GOLDEN / "sample_dem.tif"), read_geotiff(tif)
+    assert np.array_equal(a.data, b.data) and a.data.dtype == b.data.dtype
+    assert a.transform == b.transform and a.crs == b.crs
+    blob = flac.read_bytes()
+    h = flacfmt.parse_header(blob)
+    assert h.tags["GEOSPATIAL_WIDTH"] == ["512"] and h.tags["GEOSPATIAL_DTYPE"] == ["int16"]
+    assert h.tags["GEOSPATIAL_DATA_MIN"] == ["577.0"] and h.tags["GEOSPATIAL_DATA_MAX"] == ["1492.0"]
+    dec, info = oracle.decode(blob)                       # samples == reference normalisation of the raster
+    want, _ = no.normalize_to_audio(a.data.reshape(-1, 1), 16)
+    assert np.array_equal(dec, want.astype(np.int32)) and (info.sample_rate, info.bps) == (44100, 16)
+    # byte-identical frames to the libFLAC-procedure oracle on the same samples
+    oenc, ofs = oracle.encode(want, 16, 44100, 5)
+    assert blob[h.first_frame_offset:] == oenc[len(oenc) - int(ofs.sum()):]
+    with pytest.raises(ValueError, match="No metadata found"):
+        bare = tmp_path / "bare.flac"
+        bare.write_bytes(oenc)
+        conv.flac_to_tiff(bare, tmp_path / "x.tif")
+
+
+def test_config2_rgb_streaming_tile512(nat, oracle, tmp_path):
+    """BASELINE config 2: sample_rgb.tif, streaming, tile_size 512, encode + get_tile_by_id."""
+    from flac_raster_b200 import SpatialFLACEncoder, SpatialFLACStreamer
+    from flac_raster_b200.tiffio import read_geotiff
+    out = tmp_path / "rgb_stream.flac"
+    SpatialFLACEncoder(tile_size=512).encode(GOLDEN / "sample_rgb.tif", out, streaming=True)
+    blob = out.read_bytes()
+    (n,) = struct.unpack(">I", blob[:4])
+    index = json.loads(blob[4:4 + n])
+    assert index["width"] == 256 and index["bands"] == 3 and index["dtype"] == "uint8" and index["tile_size"] == 512
+    assert len(index["frames"]) == 1 and index["frames"][0]["byte_offset"] == 0
+    f0 = index["frames"][0]
+    tile_file = blob[4 + n: 4 + n + f0["byte_size"]]
+    assert 4 + n + f0["byte_size"] == len(blob) and tile_file[:4] == b"fLaC"
+    golden = (GOLDEN / "sample_rgb.flac").read_bytes()
+    from flac_raster_b200 import flacfmt
+    off = flacfmt.parse_header(tile_file).first_frame_offset
+    assert tile_file[off:] == golden[86:]                 # same frames libFLAC produced for this raster
+    tile, meta = SpatialFLACStreamer(out).get_tile_by_id(0)
+    src = read_geotiff(GOLDEN / "sample_rgb.tif")
+    assert np.array_equal(tile, src.data) and tile.dtype == np.uint8
+    assert meta["width"] == 256 and meta["count"] == 3 and meta["frame_id"] == 0
+    with pytest.raises(KeyError):
+        SpatialFLACStreamer(out).get_tile_by_id(7)
+
+
+def test_streaming_small_tiles_bbox_and_center(nat, oracle, tmp_path):
+    """CI smoke of the reference (--streaming --tile-size 128 + extract) plus multi-tile bbox decode."""
+    from flac_raster_b200 import SpatialFLACEncoder, SpatialFLACStreamer
+    from flac_raster_b200.tiffio import read_geotiff
+    from oracle import normalization_oracle as no
+    src = read_geotiff(GOLDEN / "sample_dem.tif")
+    out = tmp_path / "dem_stream.flac"
+    idx = SpatialFLACEncoder(tile_size=200).encode(GOLDEN / "sample_dem.tif", out, streaming=True, compression_level=8)
+    assert len(idx.frames) == 9                          # 3x3 grid with 112-wide edge tiles
+    s = SpatialFLACStreamer(out)
+    blob = out.read_bytes()
+    total = 0
+    for f in s.spatial_index.frames:
+        w = f.window
+        tile_file = blob[s.header_size + f.byte_offset: s.header_size + f.byte_offset + f.byte_size]
+        dec, info = oracle.decode(tile_file)              # every tile is a standalone FLAC file
+        win = src.data[:, w.row_off:w.row_off + w.height, w.col_off:w.col_off + w.width]
+        want, _ = no.normalize_to_audio(win.transpose(1, 2, 0).reshape(-1, 1), 16)     # per-tile min/max
+        assert np.array_equal(dec, want.astype(np.int32)) and info.sample_rate == 44100
+        assert f.byte_offset == total
+        total += f.byte_size
+    assert s.header_size + total == len(blob)
+    t = src.transform
+    res = s.get_tiles_by_bbox(t[2] + 150 * t[0], t[5] + 450 * t[4], t[2] + 450 * t[0], t[5] + 150 * t[4])
+    assert sorted(m["frame_id"] for _, m in res) == [0, 1, 2, 3, 4, 5, 6, 7, 8]
+    for tile, m in res:
+        w = m["window"]
+        assert np.array_equal(tile, src.data[:, w["row_off"]:w["row_off"] + w["height"], w["col_off"]:w["col_off"] + w["width"]])
+    res = s.get_tiles_by_bbox(t[2] + 10 * t[0], t[5] + 190 * t[4], t[2] + 190 * t[0], t[5] + 10 * t[4])
+    assert [m["frame_id"] for _, m in res] == [0]
+    assert s.get_tiles_by_bbox(1e6, 1e6, 2e6, 2e6) == []
+    tile, m = s.get_center_tile()
+    assert m["frame_id"] == 4
+    # legacy --spatial layout: concatenated streams with a valid embedded index
+    leg = tmp_path / "legacy.flac"
+    SpatialFLACEncoder(tile_size=256).encode(GOLDEN / "sample_dem.tif", leg, streaming=False)
+    ls = SpatialFLACStreamer(leg)
+    lblob = leg.read_bytes()
+    for f in ls.spatial_index.frames:
+        assert lblob[f.byte_offset:f.byte_offset + 4] == b"fLaC"
+    tile, m = ls.get_tile_by_id(3)
+    assert np.array_equal(tile, src.data[:, 256:, 256:])
+
+
+@pytest.mark.parametrize("dt", ["uint8", "int8", "uint16", "int16", "uint32", "int32", "float32", "float64"])
+def test_all_dtypes_roundtrip_equals_reference_semantics(nat, tmp_path, dt):
+    """Reconstruction equals denormalize(normalize(x)) of the reference for every dtype."""
+    from flac_raster_b200 import RasterFLACConverter
+    from oracle import normalization_oracle as no
+    rng = np.random.default_rng(11)
+    if dt.startswith("float"):
+        x = (500 + 300 * np.sin(np.arange(3 * 130 * 170) / 50.0) + rng.standard_normal(3 * 130 * 170)).astype(dt)
+    else:
+        info = np.iinfo(dt)
+        lo, hi = max(info.min, -8000), min(info.max, 8000)    # range < 32767: exact under truncation
+        x = rng.integers(lo, hi, size=3 * 130 * 170, endpoint=True).astype(dt)
+    x = x.reshape(3, 130, 170)
+    conv = RasterFLACConverter()
+    p = tmp_path / f"{dt}.flac"
+    conv.array_to_flac(x, p, 5, transform=(1.0, 0.0, 0.0, 0.0, -1.0, 0.0), crs="EPSG:4326")
+    back, md = conv.flac_to_array(p)
+    bits = 16 if dt in ("uint8", "int8", "uint16", "int16") else 24
+    a, prm = no.normalize_to_audio(x.transpose(1, 2, 0).reshape(-1, 3), bits)
+    want = no.denormalize_from_audio(a, prm["data_min"], prm["data_max"], dt, prm["scale_factor"])
+    want = want.reshape(130, 170, 3).transpose(2, 0, 1)
+    assert back.dtype == x.dtype and np.array_equal(back, want)
+    if bits == 16:
+        assert np.array_equal(back, x)        # 8/16-bit rasters with range <= 32767 are lossless
+
+
+# ------------------------------------------------------------------ full-size properties
+def _roundtrip_on_device(torch, raster, tile_size, level):
+    from flac_raster_b200.engine import default_engine, tile_grid
+    eng = default_engine()
+    bands, H, W = raster.shape
+    tiles = tile_grid(H, W, tile_size)
+    enc = eng.encode_tiles(raster, tiles, level)
+    payload = torch.cat([enc.payload, torch.zeros(64, dtype=torch.uint8, device=raster.device)])
+    audio, base, status = eng.decode_streams(payload, enc.offsets, enc.sizes, enc.n_samples, enc.sample_rates,
+                                             bands, enc.bps, enc.blocksize)
+    assert status[0] == 0 and status[1] == 0 and status[2] == 0, status
+    assert status[3] == int(((enc.n_samples + 4095) // 4096).sum())
+    out = torch.zeros_like(raster)
+    scale = 32767.0 if enc.bits_per_sample == 16 else 8388607.0
+    eng.denormalize_tiles(audio, base, tiles, enc.minmax, scale, out)
+    return enc, out
+
+
+def test_fullsize_c5_tiles_int16_roundtrip(nat, torch_cuda):
+    """Config 5 corpus (4096 tiles of 512x512 int16, or FRB_TEST_TILES): encode -> decode -> raster identical."""
+    torch = torch_cuda
+    from flac_raster_b200.synth import dem_int16_tiles
+    n = int(os.environ.get("FRB_TEST_TILES", "4096"))
+    raster = dem_int16_tiles(n, 512)
+    enc, out = _roundtrip_on_device(torch, raster, 512, 5)
+    assert torch.equal(out, raster)
+    assert len(enc.sizes) == n and int(enc.sizes.sum()) < raster.numel() * 2 * 0.8
+
+
+def test_fullsize_c3_sentinel_like_roundtrip(nat, torch_cuda):
+    """Config 3 (10980^2 x 8 uint16, tile 1024 -> 121 tiles incl. 740-wide edges): lossless on device."""
+    torch = torch_cuda
+    from flac_raster_b200.synth import sentinel2_like
+    side = int(os.environ.get("FRB_TEST_C3_SIDE", "10980"))
+    raster = sentinel2_like(side, side, 8)
+    enc, out = _roundtrip_on_device(torch, raster, 1024, 5)
+    assert torch.equal(out.view(torch.int16), raster.view(torch.int16))
+    if side == 10980:
+        assert len(enc.sizes) == 121 and set(enc.sample_rates.tolist()) == {44100, 48000}
+
+
+def test_fullsize_c4_float32_level8_roundtrip(nat, torch_cuda):
+    """Config 4 shape family (float32 DEM, level 8, 32-bps stream): decode(encode(x)) == normalise(x)
+    sample-for-sample, and reconstruction equals the reference's 24-bit quantisation."""
+    torch = torch_cuda
+    from flac_raster_b200.engine import default_engine, tile_grid
+    from flac_raster_b200.synth import dem_float32
+    side = int(os.environ.get("FRB_TEST_C4_SIDE", "8192"))
+    raster = dem_float32(side, side)
+    eng = default_engine()
+    tiles = tile_grid(side, side, side)
+    enc = eng.encode_tiles(raster, tiles, 8)
+    assert enc.bps == 32 and enc.sample_rates[0] == (96000 if side * side < 100_000_000 else 192000)
+    audio_ref, base_ref, npx, d_mm, bits = eng.normalize_tiles(raster, tiles)
+    ref = audio_ref[:side * side * 4].view(torch.int32).clone()
+    payload = torch.cat([enc.payload, torch.zeros(64, dtype=torch.uint8, device=raster.device)])
+    audio, base, status = eng.decode_streams(payload, enc.offsets, enc.sizes, enc.n_samples, enc.sample_rates, 1, 32, 4096)
+    assert list(status[:3]) == [0, 0, 0]
+    assert torch.equal(audio[:side * side * 4].view(torch.int32), ref)
+    assert int(enc.sizes.sum()) < side * side * 4 * 0.75

@@ -1,0 +1,181 @@
+"""CPU suite part 2: host-side logic and the C-ABI surface (no compute calls without a GPU)."""
+import ctypes
+import json
+import re
+import struct
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    """Every function declared in include/flacraster_b200.h is exported by the built .so."""
+    from flac_raster_b200 import _native as nat
+    nat.build()
+    hdr = (ROOT / "include" / "flacraster_b200.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(frb_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"frb_encoder_write_cb"}
+    assert len(declared) >= 30
+    lib = ctypes.CDLL(str(nat.LIB_PATH))
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert set(nat._EXPORTS) <= declared
+    assert nat.lib().frb_version() >= 1
+    assert nat.lib().frb_error_string(5) == b"CRC mismatch"
+
+
+def test_product_fails_loudly_without_gpu():
+    """No CPU fallback: compute entry points raise when no CUDA device is present."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from flac_raster_b200 import _native as nat, normalize_to_audio
+    with pytest.raises(nat.NativeError):
+        nat.host_encode(np.zeros((10, 1), np.int32), 16, 44100)
+    with pytest.raises(nat.NativeError):
+        normalize_to_audio(np.arange(10, dtype=np.uint8), 16)
+
+
+def test_product_never_imports_oracle():
+    for p in (ROOT / "flac_raster_b200").rglob("*.py"):
+        src = p.read_text()
+        assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S).replace("# oracle", ""), p
+
+
+def test_flac_header_parse_golden_files():
+    from flac_raster_b200 import flacfmt
+    h = flacfmt.parse_header((GOLDEN / "sample_rgb.flac").read_bytes())
+    si = h.streaminfo
+    assert (si.sample_rate, si.channels, si.bits_per_sample, si.max_blocksize, si.total_samples) == (44100, 3, 16, 4096, 0)
+    assert h.vendor == "reference libFLAC 1.4.3 20230623" and h.first_frame_offset == 86
+    h = flacfmt.parse_header((GOLDEN / "sample_dem.flac").read_bytes())
+    assert h.streaminfo.bits_per_sample == 32 and h.first_frame_offset == 2058
+    assert h.tags["GEOSPATIAL_CRS"] == ["EPSG:4326"]
+    assert "GEOSPATIAL_SPATIAL_INDEX" in h.tags
+
+
+def test_flac_header_roundtrip_and_oracle_accepts_it(oracle):
+    from flac_raster_b200 import flacfmt
+    si = flacfmt.StreamInfo(4096, 4096, 0, 0, 192000, 8, 32, (1 << 35) + 5)
+    blob = flacfmt.build_header(si, {"GEOSPATIAL_CRS": "EPSG:4326", "K": "v=1"}, padding=100)
+    h = flacfmt.parse_header(blob + b"\xff\xf8")
+    assert h.streaminfo == si and h.tags == {"GEOSPATIAL_CRS": ["EPSG:4326"], "K": ["v=1"]}
+    assert h.first_frame_offset == len(blob)
+    # a header written by flacfmt followed by oracle frames is a stream the oracle decodes
+    x = (1000 * np.sin(np.arange(9000) / 7.0)).astype(np.int32).reshape(-1, 1)
+    enc, fs = oracle.encode(x, 16, 44100, 5)
+    frames = enc[len(enc) - int(fs.sum()):]
+    mine = flacfmt.build_header(flacfmt.StreamInfo(4096, 4096, 0, 0, 44100, 1, 16, 9000), {"A": "b"}) + frames
+    dec, _ = oracle.decode(mine)
+    assert np.array_equal(dec, x)
+
+
+def test_metadata_tags_roundtrip():
+    from flac_raster_b200.converter import metadata_tags, parse_metadata_tags, tile_metadata
+    md = tile_metadata(740, 512, 3, "uint16", "EPSG:32633", (10.0, 0.0, 5e5, 0.0, -10.0, 4e6), 0.0, 11672.0, None, 32767)
+    tags = {k: [v] for k, v in metadata_tags(md).items()}
+    back = parse_metadata_tags(tags)
+    assert back["width"] == 740 and back["height"] == 512 and back["count"] == 3 and back["dtype"] == "uint16"
+    assert back["data_min"] == 0.0 and back["data_max"] == 11672.0 and back["nodata"] is None
+    assert back["transform"][:6] == [10.0, 0.0, 5e5, 0.0, -10.0, 4e6] and len(back["transform"]) == 9
+    assert back["bounds"] == {"left": 5e5, "bottom": 4e6 - 5120.0, "right": 5e5 + 7400.0, "top": 4e6}
+    # float repr round-trips exactly
+    md2 = tile_metadata(1, 1, 1, "float32", None, None, 0.1 + 0.2, -1e-300, -9999.0, 8388607)
+    b2 = parse_metadata_tags({k: [v] for k, v in metadata_tags(md2).items()})
+    assert b2["data_min"] == 0.1 + 0.2 and b2["data_max"] == -1e-300 and b2["nodata"] == -9999.0
+
+
+def test_tiff_roundtrip(tmp_path):
+    from flac_raster_b200.tiffio import read_geotiff, write_geotiff
+    r = read_geotiff(GOLDEN / "sample_dem.tif")
+    assert r.data.shape == (1, 512, 512) and r.data.dtype == np.int16 and r.crs == "EPSG:4326"
+    assert r.transform == (0.001, 0.0, -105.5, 0.0, -0.001, 40.5)
+    rng = np.random.default_rng(0)
+    for dt in ("uint8", "int8", "uint16", "int16", "uint32", "int32", "float32", "float64"):
+        a = (rng.random((3, 19, 23)) * 100).astype(dt)
+        p = tmp_path / f"{dt}.tif"
+        write_geotiff(p, a, (2.0, 0.0, 100.0, 0.0, -2.0, 50.0), "EPSG:32633", -1.0)
+        b = read_geotiff(p)
+        assert np.array_equal(a, b.data) and b.data.dtype == a.dtype
+        assert b.transform == (2.0, 0.0, 100.0, 0.0, -2.0, 50.0) and b.crs == "EPSG:32633" and b.nodata == -1.0
+
+
+def test_tile_grid_matches_reference_enumeration():
+    from flac_raster_b200.engine import tile_grid
+    t = tile_grid(10980, 10980, 1024)                     # config C3: 121 tiles, edge 740
+    assert len(t) == 121
+    assert (t[0]["h"], t[0]["w"]) == (1024, 1024) and (t[10]["h"], t[10]["w"]) == (1024, 740)
+    assert (t[120]["row_off"], t[120]["col_off"], t[120]["h"], t[120]["w"]) == (10240, 10240, 740, 740)
+    assert sum(int(a["h"]) * int(a["w"]) for a in t) == 10980 * 10980
+    # row-major order, frame_id increments along columns first (cli.py:553-554)
+    assert (t[1]["row_off"], t[1]["col_off"]) == (0, 1024) and (t[11]["row_off"], t[11]["col_off"]) == (1024, 0)
+
+
+def test_audio_params_table():
+    from flac_raster_b200.normalization import audio_params_for, estimate_precision_loss
+    assert audio_params_for((512, 512), "int16") == (44100, 16)
+    assert audio_params_for((1024, 1024), "uint16") == (48000, 16)
+    assert audio_params_for((8, 10980, 10980), "uint16") == (192000, 16)
+    assert audio_params_for((32768, 32768), "float32") == (192000, 24)
+    assert audio_params_for((740, 1024), "uint8") == (44100, 16)
+    e = estimate_precision_loss("uint16", 0.0, 65535.0, 16)
+    assert e["quantization_levels"] == 65534 and not e["is_lossless"]
+    assert estimate_precision_loss("uint8", 0, 255, 16)["is_lossless"]
+
+
+def test_spatial_index_and_streamer_on_synthetic_container(tmp_path):
+    """Index/byte-range logic of the streamer (no decode): strict bbox test, merged ranges."""
+    from flac_raster_b200.spatial_encoder import SpatialFLACStreamer
+    frames = []
+    off = 0
+    for i in range(4):
+        r, c = divmod(i, 2)
+        frames.append({"frame_id": i, "bbox": [c * 10.0, 20.0 - (r + 1) * 10.0, (c + 1) * 10.0, 20.0 - r * 10.0],
+                       "window": {"col_off": c * 10, "row_off": r * 10, "width": 10, "height": 10},
+                       "byte_offset": off, "byte_size": 100 + i})
+        off += 100 + i
+    index = {"crs": "EPSG:4326", "transform": [1, 0, 0, 0, -1, 20, 0, 0, 1], "width": 20, "height": 20, "bands": 1,
+             "dtype": "uint8", "tile_size": 10, "frames": frames}
+    js = json.dumps(index, separators=(",", ":")).encode()
+    p = tmp_path / "c.flac"
+    p.write_bytes(len(js).to_bytes(4, "big") + js + bytes(off))
+    s = SpatialFLACStreamer(p)
+    assert s.header_size == 4 + len(js) and len(s.spatial_index.frames) == 4
+    assert [f.frame_id for f in s.spatial_index.query_bbox((0, 0, 20, 20))] == [0, 1, 2, 3]
+    assert [f.frame_id for f in s.spatial_index.query_bbox((10, 10, 20, 20))] == [1]      # touching edges excluded
+    assert s.get_byte_ranges_for_bbox((0, 10.5, 20, 20)) == [(s.header_size, s.header_size + 200)]
+    assert s.get_byte_ranges_for_bbox((100, 100, 101, 101)) == []
+    assert len(s.stream_bbox_data((0, 0, 5, 5))) == 102
+    with pytest.raises(FileNotFoundError):
+        SpatialFLACStreamer(tmp_path / "missing.flac")
+
+
+def test_shard_range_partitions():
+    from flac_raster_b200.distributed import exclusive_scan, shard_range
+    for n, w in ((121, 8), (4096, 8), (3, 8), (1, 1), (484, 4)):
+        spans = [shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+    assert list(exclusive_scan(np.array([5, 7, 9]))) == [0, 5, 12]
+
+
+def test_pyflac_shim_signatures():
+    """Constructor/method surface of pyflac 3.0.0 that the reference uses."""
+    import inspect
+    from flac_raster_b200 import codec
+    sig = inspect.signature(codec.StreamEncoder.__init__)
+    assert list(sig.parameters)[1:] == ["sample_rate", "write_callback", "seek_callback", "tell_callback", "metadata_callback",
+                                        "compression_level", "blocksize", "streamable_subset", "verify", "limit_min_bitrate"]
+    assert sig.parameters["compression_level"].default == 5 and sig.parameters["blocksize"].default == 0
+    enc = codec.StreamEncoder(write_callback=lambda *a: None, sample_rate=44100, compression_level=5, blocksize=4096)
+    enc._channels, enc._bits_per_sample = 3, 24                 # the reference's dead writes (converter.py:147-148)
+    with pytest.raises(TypeError):
+        enc.process([1, 2, 3])
+    with pytest.raises(codec.DecoderInitException):
+        codec.FileDecoder("/nonexistent/file.flac")
+    assert enc.finish() is False
