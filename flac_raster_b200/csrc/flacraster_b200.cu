@@ -33,6 +33,26 @@ static int ensure_tables_impl() {
     }
     FRB_CUDA(cudaMemcpyToSymbol(c_crc8, t8, sizeof t8));
     FRB_CUDA(cudaMemcpyToSymbol(c_crc16, t16, sizeof t16));
+    {
+        static CrcTables T;
+        for (int b = 0; b < 256; b++) {
+            uint32_t c = t16[b];                                  // byte b followed by 0 zero bytes
+            T.s4[b] = (uint16_t)c;
+            for (int k = 1; k < 4; k++) { c = ((c << 8) & 0xFFFFu) ^ t16[c >> 8]; T.s4[k * 256 + b] = (uint16_t)c; }
+        }
+        const uint32_t K = gf16_xpow8(496);
+        for (int b = 0; b < 256; b++) {
+            T.k496[b] = (uint16_t)gf16_mul((uint32_t)b << 8, K);
+            T.k496[256 + b] = (uint16_t)gf16_mul((uint32_t)b, K);
+        }
+        const uint32_t K2 = gf16_xpow8(2032);
+        for (int b = 0; b < 256; b++) {
+            T.k2032[b] = (uint16_t)gf16_mul((uint32_t)b << 8, K2);
+            T.k2032[256 + b] = (uint16_t)gf16_mul((uint32_t)b, K2);
+        }
+        for (int i = 0; i < 2048; i++) T.xp[i] = (uint16_t)gf16_xpow8((uint64_t)i);
+        FRB_CUDA(cudaMemcpyToSymbol(c_crct, &T, sizeof T));
+    }
     if (dev >= 0 && dev < 64) done[dev] = true;
     return FRB_OK;
 }

@@ -126,261 +126,9 @@ k_sync_scan(const uint8_t *__restrict__ bytes, const DecStreamDev *__restrict__ 
     }
 }
 
-// ---- per-thread MSB-first bit reader over global memory ----------------------
-struct BitReader {
-    const uint32_t *wp;     // next aligned word to load
-    const uint32_t *wend;   // first word that may not be read (reads past it yield all-ones, which ends any unary run)
-    uint64_t buf;           // MSB-aligned bit window
-    int avail;              // valid bits in buf
-    int64_t loaded_bits;    // bits loaded since byte0 (for position bookkeeping)
-    __device__ __forceinline__ void init(const uint8_t *base, uint64_t byte_pos, uint64_t byte_end) {
-        uint64_t addr = byte_pos;
-        wp = (const uint32_t *)base + (addr >> 2);
-        wend = (const uint32_t *)base + ((byte_end + 3) >> 2) + 1;
-        int skip = (int)(addr & 3) * 8;
-        uint32_t a = bswap32(__ldg(wp)), b = bswap32(__ldg(wp + 1));
-        wp += 2;
-        buf = (((uint64_t)a << 32) | b) << skip;
-        avail = 64 - skip;
-        loaded_bits = 64 - skip;
-    }
-    __device__ __forceinline__ void refill() {        // afterwards avail >= 33
-        if (avail <= 32) {
-            const uint32_t w = wp < wend ? bswap32(__ldg(wp)) : 0xFFFFFFFFu;
-            wp++;
-            buf |= (uint64_t)w << (32 - avail);
-            avail += 32;
-            loaded_bits += 32;
-        }
-    }
-    __device__ __forceinline__ uint32_t get(int n) {  // n in 0..32
-        refill();
-        uint32_t v = n ? (uint32_t)(buf >> (64 - n)) : 0u;
-        buf <<= n; avail -= n;
-        return v;
-    }
-    __device__ __forceinline__ int32_t get_signed(int n) {   // n in 0..33 (side channel of 32-bps)
-        if (n == 0) return 0;
-        if (n > 32) { (void)get(n - 32); n = 32; }            // value fits 32 bits for our data; top bits are sign copies
-        uint32_t v = get(n);
-        uint32_t m = 1u << (n - 1);
-        return (int32_t)((v ^ m) - m);
-    }
-    __device__ __forceinline__ uint32_t unary() {             // zeros before the next 1
-        uint32_t q = 0;
-        while (true) {
-            refill();
-            uint32_t hi = (uint32_t)(buf >> 32);
-            if (hi) { int z = __clz(hi); q += z; buf <<= (z + 1); avail -= (z + 1); return q; }
-            q += 32; buf <<= 32; avail -= 32;
-        }
-    }
-    __device__ __forceinline__ int64_t consumed_bits() const { return loaded_bits - avail; }
-};
 
-constexpr int kDecWarps = 4;
-constexpr int kTileStride = 33;
+#include "frb_decode_kernels.cuh"   // bit reader, skim, subframe decode, CRC-16 (inside namespace frb)
 
-// status words: 0 frames_missing, 1 crc16_errors, 2 parse_errors, 3 frames_decoded, 4 order_overflow
-template <int MAXORD>
-__global__ void __launch_bounds__(kDecWarps * 32)
-k_decode_frames(const uint8_t *__restrict__ bytes, const DecStreamDev *__restrict__ streams, uint32_t n_streams,
-                uint32_t channels, uint32_t bps, uint32_t blocksize, uint32_t total_frames,
-                const unsigned long long *__restrict__ frame_pos, int32_t *__restrict__ audio,
-                uint8_t *__restrict__ frame_chassign, uint32_t *__restrict__ status) {
-    __shared__ int32_t s_tile[kDecWarps][32 * kTileStride];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int32_t *tile = s_tile[warp];
-    int32_t *row = tile + lane * kTileStride;
-    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-
-    // locate stream by binary search over frame_base
-    bool alive = f < total_frames;
-    uint32_t n = 0, ch_assign = 0;
-    int64_t dst0 = 0, chan_stride = 0;
-    uint64_t fstart = 0, fend = 0;
-    if (alive) {
-        uint32_t lo = 0, hi = n_streams - 1;
-        while (lo < hi) {
-            uint32_t mid = (lo + hi + 1) >> 1;
-            if (streams[mid].frame_base <= f) lo = mid; else hi = mid - 1;
-        }
-        const DecStreamDev st = streams[lo];
-        uint32_t k = f - st.frame_base;
-        unsigned long long p0 = frame_pos[f];
-        unsigned long long p1 = (k + 1 < st.n_frames) ? frame_pos[f + 1] : (st.byte_offset + st.byte_length);
-        n = (k + 1 < st.n_frames) ? blocksize : (uint32_t)(st.n_samples - (uint64_t)k * blocksize);
-        dst0 = st.audio_base + (int64_t)k * blocksize;
-        chan_stride = (int64_t)st.n_samples;
-        if (p0 == kNoPos || p1 == kNoPos || p1 <= p0) { alive = false; atomicAdd(&status[0], 1u); }
-        fstart = p0; fend = p1;
-    }
-    BitReader br;
-    bool err = false;
-    uint32_t hdr_bytes = 0;
-    if (alive) {
-        FrameHdr h;
-        if (!parse_frame_header(bytes + fstart, fend - fstart, 0, bps, &h)) { err = true; }
-        else {
-            ch_assign = h.ch_assign;
-            br.init(bytes, fstart + h.header_bytes, fend);
-            hdr_bytes = h.header_bytes;
-            frame_chassign[f] = (uint8_t)h.ch_assign;
-        }
-    }
-    if (!alive || err) { br.wp = (const uint32_t *)bytes; br.wend = br.wp; br.buf = 0; br.avail = 64; br.loaded_bits = 64; }
-    const uint32_t n_eff = (alive && !err) ? n : 0;
-
-    int32_t cf[MAXORD];
-    for (uint32_t c = 0; c < channels; c++) {
-        // per-subframe state
-        uint32_t type = 0, order = 0, wasted = 0, sbps = bps, k = 0, part_left = 0, part_n = 0;
-        int shift = 0; bool escape = false; uint32_t raw_bits = 0; int plen = 4;
-        int32_t const_val = 0;
-#pragma unroll
-        for (int j = 0; j < MAXORD; j++) cf[j] = 0;
-        if ((ch_assign == 8 && c == 1) || (ch_assign == 9 && c == 0) || (ch_assign == 10 && c == 1)) sbps++;
-
-        for (uint32_t chunk = 0; chunk * 32 < blocksize; chunk++) {
-            for (uint32_t j = 0; j < 32; j++) {
-                const uint32_t i = chunk * 32 + j;
-                if (i < n_eff && !err) {
-                    if (i == 0) {
-                        uint32_t hd = br.get(8);
-                        if (hd & 0x80) err = true;
-                        uint32_t t = (hd >> 1) & 0x3F;
-                        if (hd & 1) wasted = br.unary() + 1;
-                        if (wasted >= sbps) { err = true; wasted = 0; }
-                        sbps -= wasted;
-                        if (t == 0) { type = 0; order = 0; const_val = br.get_signed((int)sbps); }
-                        else if (t == 1) { type = 1; order = n; }
-                        else if (t >= 8 && t <= 12) {
-                            type = 2; order = t - 8; shift = 0;
-                            if (order >= 1) { cf[0] = order == 1 ? 1 : order == 2 ? 2 : order == 3 ? 3 : 4; }
-                            if (MAXORD > 1 && order >= 2) cf[1] = order == 2 ? -1 : order == 3 ? -3 : -6;
-                            if (MAXORD > 2 && order >= 3) cf[2] = order == 3 ? 1 : 4;
-                            if (MAXORD > 3 && order >= 4) cf[3] = -1;
-                        }
-                        else if (t >= 32) { type = 3; order = t - 31; if (order > (uint32_t)MAXORD) { err = true; atomicAdd(&status[4], 1u); order = 0; type = 0; } }
-                        else err = true;
-                        if (order > n && type != 1) err = true;
-                    }
-                    int32_t val;
-                    if (type == 0) val = const_val;
-                    else if (i < order) val = br.get_signed((int)sbps);
-                    else {
-                        if (i == order) {
-                            if (type == 3) {
-                                uint32_t prec = br.get(4) + 1;
-                                if (prec == 16) err = true;
-                                shift = (int)br.get(5);
-                                if (shift & 16) err = true;     // negative shift is invalid
-#pragma unroll
-                                for (int q = 0; q < MAXORD; q++)
-                                    if ((uint32_t)q < order) cf[q] = br.get_signed((int)prec);
-                            }
-                            uint32_t m = br.get(2);
-                            if (m > 1) err = true;
-                            plen = m ? 5 : 4;
-                            uint32_t po = br.get(4);
-                            part_n = n >> po;
-                            if (po > 0 && ((n & ((1u << po) - 1)) || part_n < order)) err = true;
-                            part_left = part_n - order;
-                            if (part_n < order) part_left = 0;
-                            k = br.get(plen);
-                            escape = (k == (plen == 5 ? 31u : 15u));
-                            if (escape) raw_bits = br.get(5);
-                            // an empty first partition (n>>po == order) moves straight to the next
-                            while (part_left == 0 && !err) {
-                                k = br.get(plen);
-                                escape = (k == (plen == 5 ? 31u : 15u));
-                                if (escape) raw_bits = br.get(5);
-                                part_left = part_n;
-                                if (part_n == 0) err = true;
-                            }
-                        }
-                        int32_t r;
-                        if (escape) r = br.get_signed((int)raw_bits);
-                        else {
-                            uint32_t q = br.unary();
-                            uint32_t u = (q << k) | br.get((int)k);
-                            r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
-                        }
-                        if (--part_left == 0 && i + 1 < n) {
-                            k = br.get(plen);
-                            escape = (k == (plen == 5 ? 31u : 15u));
-                            if (escape) raw_bits = br.get(5);
-                            part_left = part_n;
-                        }
-                        int64_t acc = 0;
-#pragma unroll
-                        for (int q = 0; q < MAXORD; q++)
-                            acc += (int64_t)cf[q] * (int64_t)row[(i - 1 - q) & 31];
-                        val = r + (int32_t)(acc >> shift);
-                    }
-                    row[i & 31] = val;
-                }
-            }
-            __syncwarp();
-            // flush 32 rows x 32 samples, one 128-byte row per store
-            {
-                const int64_t my_dst = dst0 + (int64_t)c * chan_stride;
-                const uint32_t idx = chunk * 32 + lane;
-#pragma unroll 4
-                for (int r = 0; r < 32; r++) {
-                    int64_t d = __shfl_sync(0xFFFFFFFFu, my_dst, r);
-                    uint32_t nr = __shfl_sync(0xFFFFFFFFu, n_eff, r);
-                    uint32_t wr = __shfl_sync(0xFFFFFFFFu, wasted, r);
-                    if (idx < nr) audio[d + idx] = (int32_t)((uint32_t)tile[r * kTileStride + lane] << wr);
-                }
-            }
-            __syncwarp();
-        }
-    }
-    if (alive) {
-        if (!err) {
-            // frame must end (after byte padding) exactly 2 bytes before the next frame
-            int64_t bits = br.consumed_bits();
-            // consumed_bits counts from the header end
-            const uint64_t end_byte = fstart + hdr_bytes + (uint64_t)((bits + 7) >> 3);
-            if (end_byte + 2 != fend) err = true;
-        }
-        if (err) atomicAdd(&status[2], 1u); else atomicAdd(&status[3], 1u);
-    }
-}
-
-// one warp per frame: CRC-16 over [pos, next_pos-2) must equal the trailing 2 bytes
-__global__ void __launch_bounds__(256)
-k_crc16_frames(const uint8_t *__restrict__ bytes, const DecStreamDev *__restrict__ streams, uint32_t n_streams,
-               uint32_t total_frames, const unsigned long long *__restrict__ frame_pos, uint32_t *__restrict__ status) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (f >= total_frames) return;
-    uint32_t lo = 0, hi = n_streams - 1;
-    while (lo < hi) {
-        uint32_t mid = (lo + hi + 1) >> 1;
-        if (streams[mid].frame_base <= f) lo = mid; else hi = mid - 1;
-    }
-    const DecStreamDev st = streams[lo];
-    uint32_t k = f - st.frame_base;
-    unsigned long long p0 = frame_pos[f];
-    unsigned long long p1 = (k + 1 < st.n_frames) ? frame_pos[f + 1] : (st.byte_offset + st.byte_length);
-    if (p0 == kNoPos || p1 == kNoPos || p1 < p0 + 3) return;     // counted as missing by the decoder
-    const uint64_t len = p1 - p0 - 2;
-    const uint64_t seg = (len + 31) / 32;
-    uint64_t a = (uint64_t)lane * seg, b = a + seg;
-    if (a > len) a = len;
-    if (b > len) b = len;
-    uint32_t crc = 0;
-    for (uint64_t i = a; i < b; i++) crc = ((crc << 8) & 0xFFFFu) ^ c_crc16[(crc >> 8) ^ bytes[p0 + i]];
-    crc = gf16_mul(crc, gf16_xpow8(len - b));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) crc ^= __shfl_xor_sync(0xFFFFFFFFu, crc, o);
-    if (lane == 0) {
-        uint32_t want = ((uint32_t)bytes[p1 - 2] << 8) | bytes[p1 - 1];
-        if (crc != want) atomicAdd(&status[1], 1u);
-    }
-}
 
 // one CTA per frame; only frames with ch_assign 8/9/10 do work
 __global__ void __launch_bounds__(128)
@@ -417,9 +165,10 @@ struct DecWorkspace {
     DecStreamDev *streams;
     unsigned long long *frame_pos;
     uint8_t *chassign;
+    uint32_t *sub_bitoff;      // only used when channels > 1
 };
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
-static inline size_t dec_ws_layout(uint32_t n_streams, uint64_t total_frames, void *base, DecWorkspace *w) {
+static inline size_t dec_ws_layout(uint32_t n_streams, uint32_t channels, uint64_t total_frames, void *base, DecWorkspace *w) {
     size_t off = 0;
     uint8_t *b = (uint8_t *)base;
     if (w) w->streams = (DecStreamDev *)(b + off);
@@ -428,6 +177,8 @@ static inline size_t dec_ws_layout(uint32_t n_streams, uint64_t total_frames, vo
     off += align256(8 * (size_t)(total_frames + 1));
     if (w) w->chassign = b + off;
     off += align256((size_t)total_frames + 1);
+    if (w) w->sub_bitoff = (uint32_t *)(b + off);
+    off += align256(4 * (size_t)(total_frames * channels + 1));
     return off;
 }
 
@@ -435,7 +186,7 @@ static inline size_t dec_ws_layout(uint32_t n_streams, uint64_t total_frames, vo
 
 extern "C" int frb_decode_workspace_size(const frb_decode_params *p, uint64_t total_frames, size_t *bytes) {
     if (!p || !bytes) return FRB_ERR_INVALID_ARG;
-    *bytes = frb::dec_ws_layout(p->n_streams, total_frames, nullptr, nullptr);
+    *bytes = frb::dec_ws_layout(p->n_streams, p->channels, total_frames, nullptr, nullptr);
     return FRB_OK;
 }
 
@@ -450,7 +201,8 @@ extern "C" int frb_decode_batch(const frb_decode_params *p, const frb_decode_str
     int rc = ensure_tables_impl();
     if (rc) return rc;
     DecWorkspace w;
-    if (dec_ws_layout(p->n_streams, total_frames, d_workspace, &w) > workspace_bytes) return FRB_ERR_OVERFLOW;
+    if (dec_ws_layout(p->n_streams, p->channels, total_frames, d_workspace, &w) > workspace_bytes) return FRB_ERR_OVERFLOW;
+    if (reinterpret_cast<uintptr_t>(d_bytes) & 15u) return FRB_ERR_INVALID_ARG;   // vector loads need a 16-byte aligned base
     cudaStream_t s = (cudaStream_t)stream;
     // stream table (host -> device). Pageable source: staged by the runtime before return.
     std::vector<DecStreamDev> hs(p->n_streams);
@@ -486,22 +238,31 @@ extern "C" int frb_decode_batch(const frb_decode_params *p, const frb_decode_str
         FRB_LAUNCH_CHECK("k_sync_scan");
     }
     {
-        uint32_t threads = kDecWarps * 32;
-        uint32_t grid = (uint32_t)((total_frames + threads - 1) / threads);
-        const bool wide = p->reserved > 12;
+        const uint32_t *sub_bitoff = nullptr;
+        if (p->channels > 1) {
+            // subframes of a frame are bit-packed back to back: find their starts first
+            k_skim_subframes<<<(uint32_t)((total_frames + 127) / 128), 128, 0, s>>>(
+                d_bytes, w.streams, p->n_streams, p->channels, p->bps, p->blocksize, (uint32_t)total_frames, w.frame_pos,
+                w.sub_bitoff, w.chassign, d_status);
+            FRB_LAUNCH_CHECK("k_skim_subframes");
+            sub_bitoff = w.sub_bitoff;
+        }
+        const uint64_t total_sub = total_frames * p->channels;
+        const uint32_t grid = (uint32_t)((total_sub + 127) / 128);
+        const bool big = p->reserved > 12;
         prof_begin(1, s);
-        if (!wide)
-            k_decode_frames<12><<<grid, threads, 0, s>>>(d_bytes, w.streams, p->n_streams, p->channels, p->bps, p->blocksize,
-                                                        (uint32_t)total_frames, w.frame_pos, d_audio, w.chassign, d_status);
+        if (!big)
+            k_decode_subframes<false><<<grid, 128, 0, s>>>(d_bytes, w.streams, p->n_streams, p->channels, p->bps, p->blocksize,
+                                                          (uint32_t)total_frames, w.frame_pos, sub_bitoff, d_audio, w.chassign, d_status);
         else
-            k_decode_frames<32><<<grid, threads, 0, s>>>(d_bytes, w.streams, p->n_streams, p->channels, p->bps, p->blocksize,
-                                                        (uint32_t)total_frames, w.frame_pos, d_audio, w.chassign, d_status);
+            k_decode_subframes<true><<<grid, 128, 0, s>>>(d_bytes, w.streams, p->n_streams, p->channels, p->bps, p->blocksize,
+                                                         (uint32_t)total_frames, w.frame_pos, sub_bitoff, d_audio, w.chassign, d_status);
         prof_end(1, s);
-        FRB_LAUNCH_CHECK("k_decode_frames");
+        FRB_LAUNCH_CHECK("k_decode_subframes");
     }
     if (p->verify_crc16) {
-        uint64_t threads = total_frames * 32;
-        k_crc16_frames<<<(uint32_t)((threads + 255) / 256), 256, 0, s>>>(d_bytes, w.streams, p->n_streams,
+        const uint64_t threads = total_frames * 32;
+        k_crc16_frames<<<(uint32_t)((threads + 255) / 256), 256, 0, s>>>(d_bytes, w.streams, p->n_streams, p->blocksize,
                                                                         (uint32_t)total_frames, w.frame_pos, d_status);
         FRB_LAUNCH_CHECK("k_crc16_frames");
     }

@@ -1,0 +1,411 @@
+// frb_decode_kernels.cuh -- included inside namespace frb by frb_decode.cuh.
+//
+// v2 decode pipeline (justified by profiles/r01_ncu_dec_v1_raw_subset.csv: the v1 thread-per-frame
+// kernel ran at 9.7 % occupancy on 8-band tiles and spent 228 instructions per sample):
+//   k_skim_subframes    (channels > 1 only) one thread per frame walks the Rice codes without
+//                       reconstructing anything and records each subframe's bit offset
+//   k_decode_subframes  one thread per SUBFRAME; 32-bit funnel-shift bit window with a prefetched
+//                       third word; LPC history in registers (sliding window, 4 samples per group,
+//                       taps padded to the warp's order class 4/8/12); 128-bit stores
+//   k_crc16_frames      one warp per frame, 16-byte chunks per lane, slice-by-4 tables in shared
+//                       memory, Horner combination with x^(8*512) and a final x^(8*n) weight
+
+// ---- 32-bit window bit reader over global memory (MSB first) -----------------------------------
+struct BitReader {
+    const uint32_t *wp;      // next word to prefetch
+    const uint32_t *wend;    // reads at/after this address yield all-ones (terminates any unary run)
+    uint32_t hi, lo, nxt;
+    uint32_t pos;            // consumed bits of hi, 0..31
+    __device__ __forceinline__ uint32_t fetch() {
+        const uint32_t v = wp < wend ? bswap32(__ldg(wp)) : 0xFFFFFFFFu;
+        wp++;
+        return v;
+    }
+    __device__ __forceinline__ void init(const uint8_t *base, uint64_t bitpos, uint64_t byte_end) {
+        const uint32_t *words = (const uint32_t *)base;
+        wp = words + (bitpos >> 5);
+        wend = words + ((byte_end + 3) >> 2) + 1;
+        hi = fetch(); lo = fetch(); nxt = fetch();
+        pos = (uint32_t)bitpos & 31u;
+    }
+    __device__ __forceinline__ uint64_t bitpos(const uint8_t *base) const {
+        return (uint64_t)((wp - 3) - (const uint32_t *)base) * 32u + pos;
+    }
+    __device__ __forceinline__ uint32_t window() const { return __funnelshift_l(lo, hi, pos); }
+    __device__ __forceinline__ void consume(uint32_t nb) {          // nb <= 32
+        pos += nb;
+        if (pos >= 32) { pos -= 32; hi = lo; lo = nxt; nxt = fetch(); }
+    }
+    __device__ __forceinline__ uint32_t get(uint32_t nb) {          // nb in 0..32
+        const uint32_t v = __funnelshift_lc(window(), 0u, nb);      // window >> (32 - nb), 0 for nb == 0
+        consume(nb);
+        return v;
+    }
+    __device__ __forceinline__ int32_t get_signed(uint32_t nb) {    // nb in 0..33
+        if (nb == 0) return 0;
+        if (nb > 32) { consume(nb - 32); nb = 32; }                 // top bits are sign copies for in-range data
+        const uint32_t v = get(nb);
+        const uint32_t sh = 32 - nb;
+        return (int32_t)(v << sh) >> sh;
+    }
+    __device__ __forceinline__ uint32_t unary() {
+        uint32_t q = 0;
+        for (;;) {
+            const uint32_t w = window();
+            if (w) { const uint32_t z = __clz(w); consume(z + 1); return q + z; }
+            q += 32; consume(32);
+        }
+    }
+    // zig-zag folded Rice value with parameter k (<= 30)
+    __device__ __forceinline__ uint32_t rice_u(uint32_t k) {
+        const uint32_t w = window();
+        const uint32_t z = __clz(w);
+        const uint32_t len = z + 1 + k;
+        if (len <= 32) {
+            const uint32_t t = __funnelshift_lc(0u, w, z + 1);      // w << (z+1), 0 when z+1 == 32
+            const uint32_t low = __funnelshift_lc(t, 0u, k);        // t >> (32-k), 0 when k == 0
+            consume(len);
+            return (z << k) | low;
+        }
+        const uint32_t q = unary();
+        const uint32_t low = get(k);
+        return (q << k) | low;
+    }
+    __device__ __forceinline__ void skip_rice(uint32_t k) {
+        const uint32_t w = window();
+        const uint32_t len = __clz(w) + 1 + k;
+        if (len <= 32) { consume(len); return; }
+        (void)unary();
+        consume(k);
+    }
+    __device__ __forceinline__ void seek(const uint8_t *base, uint64_t bits_forward, uint64_t byte_end) {
+        init(base, bitpos(base) + bits_forward, byte_end);
+    }
+};
+
+__device__ __forceinline__ int32_t unzigzag(uint32_t u) { return (int32_t)(u >> 1) ^ -(int32_t)(u & 1u); }
+
+struct FrameLoc {
+    uint64_t start, end;      // byte range [start, end) of the frame incl. CRC-16
+    uint32_t k, n, stream;    // frame number in stream, blocksize of this frame
+    bool ok;
+};
+
+__device__ __forceinline__ FrameLoc locate_frame(const DecStreamDev *__restrict__ streams, uint32_t n_streams,
+                                                 uint32_t blocksize, uint32_t f,
+                                                 const unsigned long long *__restrict__ frame_pos, DecStreamDev *st_out) {
+    uint32_t lo = 0, hi = n_streams - 1;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (streams[mid].frame_base <= f) lo = mid; else hi = mid - 1;
+    }
+    const DecStreamDev st = streams[lo];
+    FrameLoc L;
+    L.stream = lo;
+    L.k = f - st.frame_base;
+    const unsigned long long p0 = frame_pos[f];
+    const unsigned long long p1 = (L.k + 1 < st.n_frames) ? frame_pos[f + 1] : (st.byte_offset + st.byte_length);
+    L.n = (L.k + 1 < st.n_frames) ? blocksize : (uint32_t)(st.n_samples - (uint64_t)L.k * blocksize);
+    L.ok = !(p0 == kNoPos || p1 == kNoPos || p1 <= p0 + 4);
+    L.start = p0; L.end = p1;
+    *st_out = st;
+    return L;
+}
+
+// status words: 0 frames_missing, 1 crc16_errors, 2 parse_errors, 3 frames_decoded, 4 order_overflow
+
+// ---- skim: subframe bit offsets for multi-channel frames ------------------------------------------
+// sub_bitoff[f*channels + c] = bit offset of subframe c from the frame start; 0 marks a bad frame.
+// One thread per frame walks subframes 0..C-2 (the last one only needs its start; its end is checked by
+// the decode kernel).  The walk is ONE flat loop with a per-lane state machine: nested
+// partition/sample loops made lanes with different partition orders wait for each other at every
+// reconvergence point (15.9 ms on C3, profiles/r01_launches_c3_v2.csv).
+__global__ void __launch_bounds__(128)
+k_skim_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__restrict__ streams, uint32_t n_streams,
+                 uint32_t channels, uint32_t bps, uint32_t blocksize, uint32_t total_frames,
+                 const unsigned long long *__restrict__ frame_pos, uint32_t *__restrict__ sub_bitoff,
+                 uint8_t *__restrict__ frame_chassign, uint32_t *__restrict__ status) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= total_frames) return;
+    DecStreamDev st;
+    const FrameLoc L = locate_frame(streams, n_streams, blocksize, f, frame_pos, &st);
+    uint32_t *off_out = sub_bitoff + (size_t)f * channels;
+    for (uint32_t c = 0; c < channels; c++) off_out[c] = 0;
+    if (!L.ok) { atomicAdd(&status[0], 1u); return; }
+    FrameHdr h;
+    if (!parse_frame_header(bytes + L.start, L.end - L.start, 0, bps, &h)) { atomicAdd(&status[2], 1u); return; }
+    frame_chassign[f] = (uint8_t)h.ch_assign;
+    const uint64_t frame_bit0 = L.start * 8;
+    BitReader br;
+    br.init(bytes, frame_bit0 + (uint64_t)h.header_bytes * 8, L.end);
+    const uint32_t n = L.n;
+    bool err = false, in_res = false;
+    uint32_t c = 0, left = 0, parts_left = 0, k = 0, plen = 4, esc = 15, psize = 0;
+    off_out[0] = h.header_bytes * 8;
+    while (!err && c + 1 < channels) {
+        if (!in_res) {
+            uint32_t sbps = bps;
+            if ((h.ch_assign == 8 && c == 1) || (h.ch_assign == 9 && c == 0) || (h.ch_assign == 10 && c == 1)) sbps++;
+            const uint32_t hd = br.get(8);
+            const uint32_t t = (hd >> 1) & 0x3F;
+            uint32_t wasted = 0;
+            if (hd & 1) wasted = br.unary() + 1;
+            if ((hd & 0x80) || wasted >= sbps) { err = true; break; }
+            sbps -= wasted;
+            uint32_t order = 0;
+            bool coded = false;
+            if (t == 0) br.seek(bytes, sbps, L.end);
+            else if (t == 1) br.seek(bytes, (uint64_t)sbps * n, L.end);
+            else if (t >= 8 && t <= 12) { order = t - 8; coded = true; }
+            else if (t >= 32) { order = t - 31; coded = true; }
+            else { err = true; break; }
+            if (coded) {
+                if (order > n) { err = true; break; }
+                br.seek(bytes, (uint64_t)order * sbps, L.end);
+                if (t >= 32) {
+                    const uint32_t prec = br.get(4) + 1;
+                    if (prec == 16) { err = true; break; }
+                    br.seek(bytes, 5 + (uint64_t)order * prec, L.end);
+                }
+                const uint32_t m = br.get(2);
+                const uint32_t po = br.get(4);
+                plen = m ? 5u : 4u; esc = m ? 31u : 15u;
+                psize = n >> po;
+                if (m > 1 || (po > 0 && (n & ((1u << po) - 1))) || psize < order) { err = true; break; }
+                parts_left = 1u << po;
+                left = psize - order;
+                in_res = true;
+                // settle on the first partition that actually holds Rice-coded residuals
+                for (;;) {
+                    k = br.get(plen);
+                    if (k == esc) { const uint32_t raw = br.get(5); br.seek(bytes, (uint64_t)raw * left, L.end); left = 0; }
+                    if (left) break;
+                    if (--parts_left == 0) { in_res = false; break; }
+                    left = psize;
+                    if (psize == 0) { err = true; break; }
+                }
+            }
+            if (!in_res) { c++; off_out[c] = (uint32_t)(br.bitpos(bytes) - frame_bit0); }
+        } else {
+            br.skip_rice(k);
+            if (--left == 0) {
+                for (;;) {
+                    if (--parts_left == 0) { in_res = false; break; }
+                    left = psize;
+                    k = br.get(plen);
+                    if (k == esc) { const uint32_t raw = br.get(5); br.seek(bytes, (uint64_t)raw * left, L.end); left = 0; }
+                    if (left) break;
+                }
+                if (!in_res) { c++; off_out[c] = (uint32_t)(br.bitpos(bytes) - frame_bit0); }
+            }
+        }
+    }
+    if (!err && br.bitpos(bytes) > L.end * 8) err = true;
+    if (err) {
+        atomicAdd(&status[2], 1u);
+        for (uint32_t q = 0; q < channels; q++) off_out[q] = 0;
+    }
+}
+
+// ---- subframe decode -------------------------------------------------------------------------------
+template <int MAXORD, bool WIDE>
+__device__ __forceinline__ int32_t lpc_predict(const int32_t (&cf)[MAXORD], const int32_t *Hj, int shift) {
+    // Hj points at the newest history sample; taps walk backwards (static indices after unrolling)
+    if (WIDE) {
+        long long acc = 0;
+#pragma unroll
+        for (int q = 0; q < MAXORD; q++) acc += (long long)cf[q] * (long long)Hj[-q];
+        return (int32_t)(acc >> shift);
+    } else {
+        int32_t acc = 0;
+#pragma unroll
+        for (int q = 0; q < MAXORD; q++) acc += cf[q] * Hj[-q];
+        return acc >> shift;
+    }
+}
+
+struct SubCtx {
+    BitReader br;
+    int32_t *dst;            // first sample of this subframe in the planar audio buffer
+    uint32_t n, order, sbps, wasted, type;
+    bool aligned16;
+    bool err;
+};
+
+template <int MAXORD, bool WIDE>
+__device__ __forceinline__ void decode_predictive(SubCtx &S, uint32_t *status) {
+    BitReader &br = S.br;
+    const uint32_t n = S.n, order = S.order, wasted = S.wasted;
+    int32_t *dst = S.dst;
+    int32_t H[MAXORD + 4];
+    int32_t cf[MAXORD];
+#pragma unroll
+    for (int q = 0; q < MAXORD + 4; q++) H[q] = 0;
+#pragma unroll
+    for (int q = 0; q < MAXORD; q++) cf[q] = 0;
+    // warm-up samples
+    for (uint32_t i = 0; i < order; i++) {
+        const int32_t v = br.get_signed(S.sbps);
+#pragma unroll
+        for (int q = 0; q < MAXORD - 1; q++) H[q] = H[q + 1];
+        H[MAXORD - 1] = v;
+        dst[i] = (int32_t)((uint32_t)v << wasted);
+    }
+    int shift = 0;
+    if (S.type == 3) {
+        const uint32_t prec = br.get(4) + 1;
+        if (prec == 16) { S.err = true; return; }
+        const uint32_t sh = br.get(5);
+        if (sh & 16) { S.err = true; return; }
+        shift = (int)sh;
+#pragma unroll
+        for (int q = 0; q < MAXORD; q++) if ((uint32_t)q < order) cf[q] = br.get_signed(prec);
+    } else {
+        if (order >= 1) cf[0] = order == 1 ? 1 : order == 2 ? 2 : order == 3 ? 3 : 4;
+        if (MAXORD > 1 && order >= 2) cf[1] = order == 2 ? -1 : order == 3 ? -3 : -6;
+        if (MAXORD > 2 && order >= 3) cf[2] = order == 3 ? 1 : 4;
+        if (MAXORD > 3 && order >= 4) cf[3] = -1;
+    }
+    const uint32_t m = br.get(2);
+    if (m > 1) { S.err = true; return; }
+    const uint32_t plen = m ? 5u : 4u, esc = m ? 31u : 15u;
+    const uint32_t po = br.get(4);
+    const uint32_t psize = n >> po;
+    if ((po > 0 && (n & ((1u << po) - 1))) || psize < order) { S.err = true; return; }
+    uint32_t k = br.get(plen);
+    bool escape = (k == esc);
+    uint32_t raw_bits = escape ? br.get(5) : 0;
+    uint32_t part_left = psize - order;
+    uint32_t i = order;
+    while (part_left == 0 && i < n) {
+        if (psize == 0) { S.err = true; return; }
+        k = br.get(plen); escape = (k == esc); raw_bits = escape ? br.get(5) : 0; part_left = psize;
+    }
+    while (i < n) {
+        if (!escape && part_left >= 4 && (i & 3u) == 0 && i + 4 <= n) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int32_t r = unzigzag(br.rice_u(k));
+                H[MAXORD + j] = r + lpc_predict<MAXORD, WIDE>(cf, &H[MAXORD - 1 + j], shift);
+            }
+            if (S.aligned16) {
+                *reinterpret_cast<int4 *>(dst + i) = make_int4((int32_t)((uint32_t)H[MAXORD] << wasted), (int32_t)((uint32_t)H[MAXORD + 1] << wasted),
+                                                              (int32_t)((uint32_t)H[MAXORD + 2] << wasted), (int32_t)((uint32_t)H[MAXORD + 3] << wasted));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) dst[i + j] = (int32_t)((uint32_t)H[MAXORD + j] << wasted);
+            }
+#pragma unroll
+            for (int q = 0; q < MAXORD; q++) H[q] = H[q + 4];
+            part_left -= 4; i += 4;
+        } else {
+            const int32_t r = escape ? br.get_signed(raw_bits) : unzigzag(br.rice_u(k));
+            const int32_t v = r + lpc_predict<MAXORD, WIDE>(cf, &H[MAXORD - 1], shift);
+#pragma unroll
+            for (int q = 0; q < MAXORD - 1; q++) H[q] = H[q + 1];
+            H[MAXORD - 1] = v;
+            dst[i] = (int32_t)((uint32_t)v << wasted);
+            part_left--; i++;
+        }
+        if (part_left == 0 && i < n) {
+            k = br.get(plen); escape = (k == esc); raw_bits = escape ? br.get(5) : 0; part_left = psize;
+        }
+    }
+}
+
+template <bool BIGORDER>
+__global__ void __launch_bounds__(128)
+k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__restrict__ streams, uint32_t n_streams,
+                   uint32_t channels, uint32_t bps, uint32_t blocksize, uint32_t total_frames,
+                   const unsigned long long *__restrict__ frame_pos, const uint32_t *__restrict__ sub_bitoff,
+                   int32_t *__restrict__ audio, uint8_t *__restrict__ frame_chassign, uint32_t *__restrict__ status) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t total_sub = total_frames * channels;
+    bool alive = s < total_sub;
+    const uint32_t f = alive ? s / channels : 0, c = alive ? s - f * channels : 0;
+    SubCtx S;
+    S.err = false; S.type = 0; S.order = 0; S.n = 0; S.wasted = 0; S.sbps = bps; S.dst = audio; S.aligned16 = false;
+    FrameLoc L; L.ok = false; L.start = L.end = 0; L.k = 0; L.n = 0;
+    uint32_t hdr_bytes = 0;
+    if (alive) {
+        DecStreamDev st;
+        L = locate_frame(streams, n_streams, blocksize, f, frame_pos, &st);
+        if (!L.ok) { alive = false; if (c == 0 && !sub_bitoff) atomicAdd(&status[0], 1u); }
+        else {
+            uint32_t ch_assign = 0;
+            uint64_t bit0;
+            if (sub_bitoff) {
+                const uint32_t off = sub_bitoff[s];
+                if (off == 0) alive = false;               // the skim pass already counted the error
+                bit0 = L.start * 8 + off;
+                ch_assign = frame_chassign[f];
+            } else {
+                FrameHdr h;
+                if (!parse_frame_header(bytes + L.start, L.end - L.start, 0, bps, &h)) { alive = false; atomicAdd(&status[2], 1u); }
+                else { hdr_bytes = h.header_bytes; ch_assign = h.ch_assign; frame_chassign[f] = (uint8_t)h.ch_assign; }
+                bit0 = (L.start + hdr_bytes) * 8;
+            }
+            if (alive) {
+                S.br.init(bytes, bit0, L.end);
+                S.n = L.n;
+                const int64_t idx = st.audio_base + (int64_t)c * (int64_t)st.n_samples + (int64_t)L.k * blocksize;
+                S.dst = audio + idx;
+                S.aligned16 = ((reinterpret_cast<uintptr_t>(S.dst) & 15u) == 0);
+                if ((ch_assign == 8 && c == 1) || (ch_assign == 9 && c == 0) || (ch_assign == 10 && c == 1)) S.sbps++;
+                const uint32_t hd = S.br.get(8);
+                if (hd & 0x80) S.err = true;
+                const uint32_t t = (hd >> 1) & 0x3F;
+                if (hd & 1) S.wasted = S.br.unary() + 1;
+                if (S.wasted >= S.sbps) { S.err = true; S.wasted = 0; }
+                S.sbps -= S.wasted;
+                if (t == 0) S.type = 0;
+                else if (t == 1) S.type = 1;
+                else if (t >= 8 && t <= 12) { S.type = 2; S.order = t - 8; }
+                else if (t >= 32) { S.type = 3; S.order = t - 31; }
+                else S.err = true;
+                if (S.order > S.n) S.err = true;
+            }
+        }
+    }
+    const bool run = alive && !S.err;
+    // warp-uniform code path: taps padded to the largest order in the warp, 64-bit MACs if any lane needs them
+    uint32_t my_ord = (run && S.type >= 2) ? S.order : 0;
+    if (!BIGORDER && my_ord > 12) { my_ord = 0; }
+    const uint32_t cls = __reduce_max_sync(0xFFFFFFFFu, my_ord);
+    bool wide_lane = false;
+    if (run && S.type >= 2) {
+        // libFLAC's rule: 32-bit arithmetic is exact when bps + precision + ilog2(order) <= 32 (fixed: bps + order)
+        wide_lane = S.sbps + (S.type == 3 ? 15u + (uint32_t)(31 - __clz(S.order | 1u)) : S.order) > 32u;
+    }
+    const bool wide = __any_sync(0xFFFFFFFFu, wide_lane);
+    if (run) {
+        if (S.type == 0) {
+            const int32_t v = (int32_t)((uint32_t)S.br.get_signed(S.sbps) << S.wasted);
+            for (uint32_t i = 0; i < S.n; i++) S.dst[i] = v;
+        } else if (S.type == 1) {
+            for (uint32_t i = 0; i < S.n; i++) S.dst[i] = (int32_t)((uint32_t)S.br.get_signed(S.sbps) << S.wasted);
+        } else if (!BIGORDER && S.order > 12) {
+            S.err = true;
+            atomicAdd(&status[4], 1u);
+        } else if (BIGORDER) {
+            decode_predictive<32, true>(S, status);
+        } else if (cls <= 4) {
+            if (wide) decode_predictive<4, true>(S, status); else decode_predictive<4, false>(S, status);
+        } else if (cls <= 8) {
+            if (wide) decode_predictive<8, true>(S, status); else decode_predictive<8, false>(S, status);
+        } else {
+            if (wide) decode_predictive<12, true>(S, status); else decode_predictive<12, false>(S, status);
+        }
+    }
+    if (alive) {
+        if (!S.err && c + 1 == channels) {
+            // the last subframe must end (after byte padding) exactly 2 bytes before the next frame
+            const uint64_t bits = S.br.bitpos(bytes) - L.start * 8;
+            if (L.start + ((bits + 7) >> 3) + 2 != L.end) S.err = true;
+        }
+        if (S.err) atomicAdd(&status[2], 1u);
+        else if (c + 1 == channels) atomicAdd(&status[3], 1u);
+    }
+}
+
+#include "frb_crc16.cuh"   // warp-cooperative CRC-16 + k_crc16_frames

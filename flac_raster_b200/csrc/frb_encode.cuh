@@ -28,6 +28,11 @@ constexpr int kSPT = 16;                 // samples per thread at blocksize 4096
 constexpr int kMaxBlock = kEncThreads * kSPT;   // 4096
 constexpr int kMaxOrd = 12;              // libFLAC presets never exceed 12
 constexpr int kMaxPO = 8;
+// Shared sample/residual buffers are indexed through PX(): one pad word after every 16 samples, so a
+// thread's 16-sample chunk (stride 17 words) is bank-conflict free across the warp.  The linear
+// layout gave 16-way conflicts (5.2e9 conflict cycles, profiles/r01_ncu_enc_v1_raw_subset.csv).
+#define PX(i) ((i) + ((uint32_t)(i) >> 4))
+constexpr int kBufWords = kMaxBlock + kMaxBlock / 16;
 
 struct EncStreamDev {
     uint64_t n_samples;
@@ -71,7 +76,7 @@ struct Choice {
 
 struct EncShared {
     // [resA | x | resB]: the bit buffer aliases x plus the non-best residual buffer
-    int32_t buf[3][kMaxBlock];
+    int32_t buf[3][kBufWords];
     unsigned long long psum[1 << (kMaxPO + 1)];
     uint32_t pbits[1 << (kMaxPO + 1)];
     uint8_t pk[1 << (kMaxPO + 1)];
@@ -194,6 +199,7 @@ __device__ __forceinline__ uint32_t max_po_for(uint32_t limit, uint32_t n, uint3
 
 // Compute the residual of predictor (coefs, order, shift) into res[i] (indexed by sample), for this
 // thread's samples.  Returns false if any residual does not fit in int32 (or is INT32_MIN).
+template <bool WIDE>
 __device__ __forceinline__ bool compute_residual(const int32_t *x, int32_t *res, uint32_t n, int order, int shift,
                                                  const int32_t *coefs /*smem, kMaxOrd padded*/) {
     const uint32_t i0 = threadIdx.x * kSPT;
@@ -201,7 +207,7 @@ __device__ __forceinline__ bool compute_residual(const int32_t *x, int32_t *res,
 #pragma unroll
     for (int j = 0; j < kSPT + kMaxOrd; j++) {
         int idx = (int)i0 - kMaxOrd + j;
-        xv[j] = (idx >= 0 && (uint32_t)idx < n) ? x[idx] : 0;
+        xv[j] = (idx >= 0 && (uint32_t)idx < n) ? x[PX(idx)] : 0;
     }
     int32_t cf[kMaxOrd];
 #pragma unroll
@@ -210,15 +216,24 @@ __device__ __forceinline__ bool compute_residual(const int32_t *x, int32_t *res,
 #pragma unroll
     for (int s = 0; s < kSPT; s++) {
         const uint32_t i = i0 + s;
-        long long acc = 0;
+        long long r;
+        if (WIDE) {
+            long long acc = 0;
 #pragma unroll
-        for (int j = 0; j < kMaxOrd; j++) acc += (long long)cf[j] * (long long)xv[kMaxOrd + s - 1 - j];
-        long long r = (long long)xv[kMaxOrd + s] - (acc >> shift);
+            for (int j = 0; j < kMaxOrd; j++) acc += (long long)cf[j] * (long long)xv[kMaxOrd + s - 1 - j];
+            r = (long long)xv[kMaxOrd + s] - (acc >> shift);
+        } else {
+            // <= 16-bit samples, precision <= 32 - bps - ilog2(order): every partial sum fits int32 (libFLAC's rule)
+            int32_t acc = 0;
+#pragma unroll
+            for (int j = 0; j < kMaxOrd; j++) acc += cf[j] * xv[kMaxOrd + s - 1 - j];
+            r = (long long)(xv[kMaxOrd + s] - (acc >> shift));
+        }
         if (i < n) {
             if (i >= (uint32_t)order) {
                 if (r > 2147483647ll || r <= -2147483648ll) ok = false;
-                res[i] = (int32_t)r;
-            } else res[i] = 0;
+                res[PX(i)] = (int32_t)r;
+            } else res[PX(i)] = 0;
         }
     }
     return ok;
@@ -235,7 +250,7 @@ __device__ __forceinline__ uint32_t search_partitions(const int32_t *res, uint32
         unsigned long long s = 0;
         const uint32_t a = p * psize, b = a + psize;
         for (uint32_t i = a + lane; i < b; i += 32) {
-            if (i >= (uint32_t)order) { int32_t v = res[i]; s += (unsigned long long)(v < 0 ? -(long long)v : (long long)v); }
+            if (i >= (uint32_t)order) { int32_t v = res[PX(i)]; s += (unsigned long long)(v < 0 ? -(long long)v : (long long)v); }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
@@ -314,7 +329,7 @@ __device__ __forceinline__ void consider_candidate(uint32_t cand_bits, int cand_
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kEncThreads)
+__global__ void __launch_bounds__(kEncThreads, 3)
 k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint32_t channels, uint32_t bps_stream,
                    uint32_t blocksize, uint32_t level, const int32_t *__restrict__ audio,
                    const float *__restrict__ window, uint32_t slot_words, uint32_t *__restrict__ slots,
@@ -346,7 +361,7 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
 #pragma unroll
     for (int s = 0; s < kSPT; s++) {
         const uint32_t i = i0 + s;
-        if (i < n) { int32_t v = __ldg(src + i); X[i] = v; orv |= (uint32_t)v; diff |= (uint32_t)(v ^ x_first); }
+        if (i < n) { int32_t v = __ldg(src + i); X[PX(i)] = v; orv |= (uint32_t)v; diff |= (uint32_t)(v ^ x_first); }
     }
     orv = block_or(orv, S);
     diff = block_or(diff, S);
@@ -355,7 +370,7 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
     const uint32_t bps = bps_stream - wasted;
     if (wasted) {
 #pragma unroll
-        for (int s = 0; s < kSPT; s++) { const uint32_t i = i0 + s; if (i < n) X[i] >>= wasted; }
+        for (int s = 0; s < kSPT; s++) { const uint32_t i = i0 + s; if (i < n) X[PX(i)] >>= wasted; }
     }
     if (tid == 0) {
         S.best.type = 1; S.best.order = 0; S.best.wasted = (int)wasted; S.best.precision = 0; S.best.shift = 0;
@@ -375,7 +390,7 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
             {
                 int32_t xv[kSPT + 4];
 #pragma unroll
-                for (int j = 0; j < kSPT + 4; j++) { int idx = (int)i0 - 4 + j; xv[j] = (idx >= 0 && (uint32_t)idx < n) ? X[idx] : 0; }
+                for (int j = 0; j < kSPT + 4; j++) { int idx = (int)i0 - 4 + j; xv[j] = (idx >= 0 && (uint32_t)idx < n) ? X[PX(idx)] : 0; }
 #pragma unroll
                 for (int s = 0; s < kSPT; s++) {
                     const uint32_t i = i0 + s;
@@ -412,7 +427,8 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
                 }
                 __syncthreads();
                 int32_t *R = S.buf[cand_buf];
-                bool ok = compute_residual(X, R, n, (int)guess, 0, S.cand.coefs);
+                bool ok = bps_stream <= 16 ? compute_residual<false>(X, R, n, (int)guess, 0, S.cand.coefs)
+                                            : compute_residual<true>(X, R, n, (int)guess, 0, S.cand.coefs);
                 int bad = __syncthreads_or(ok ? 0 : 1);
                 if (!bad) {
                     uint32_t rb = search_partitions(R, n, (int)guess, (uint32_t)cfg.max_po, k_limit, S);
@@ -448,7 +464,7 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
                                     else if (local < part) wv = __ldg(window + local);
                                     else if (local < 2 * part) wv = __ldg(window + (n - 2 * part + local));
                                     else wv = 0.0f;
-                                    v = (double)__fmul_rn((float)X[idx], wv);
+                                    v = (double)__fmul_rn((float)X[PX(idx)], wv);
                                 }
                                 dd[j] = v;
                             }
@@ -567,7 +583,8 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
                             cand_buf = (S.best_buf == 0 && (S.best.type >= 2)) ? 2 : 0;
                             const int order = S.cand.order, sh = S.cand.shift;
                             int32_t *R = S.buf[cand_buf];
-                            bool ok = compute_residual(X, R, n, order, sh, S.cand.coefs);
+                            bool ok = bps_stream <= 16 ? compute_residual<false>(X, R, n, order, sh, S.cand.coefs)
+                                                        : compute_residual<true>(X, R, n, order, sh, S.cand.coefs);
                             int bad = __syncthreads_or(ok ? 0 : 1);
                             if (!bad) {
                                 uint32_t rb = search_partitions(R, n, order, (uint32_t)cfg.max_po, k_limit, S);
@@ -597,7 +614,7 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
             if (i < n && i >= (uint32_t)order) {
                 const uint32_t p = i / psize;
                 const uint32_t k = S.best.params[p];
-                const uint32_t u = zigzag(R[i]);
+                const uint32_t u = zigzag(R[PX(i)]);
                 my_bits += (u >> k) + 1 + k;
                 if (i == p * psize || i == (uint32_t)order) my_bits += plen;
             }
@@ -620,21 +637,21 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
     int32_t xfirst_shifted = 0;
     if (tid == 0) {
 #pragma unroll
-        for (int j = 0; j < kMaxOrd; j++) warm[j] = (j < order && (uint32_t)j < n) ? X[j] : 0;
+        for (int j = 0; j < kMaxOrd; j++) warm[j] = (j < order && (uint32_t)j < n) ? X[PX(j)] : 0;
         xfirst_shifted = n ? X[0] : 0;
     }
     uint32_t *bitbuf;
     int32_t xv_verb[kSPT];
     if (type == 1) {
 #pragma unroll
-        for (int s = 0; s < kSPT; s++) { const uint32_t i = i0 + s; xv_verb[s] = (i < n) ? X[i] : 0; }
+        for (int s = 0; s < kSPT; s++) { const uint32_t i = i0 + s; xv_verb[s] = (i < n) ? X[PX(i)] : 0; }
         bitbuf = (uint32_t *)S.buf[1];              // X + resB: nothing else is needed any more
     } else {
         bitbuf = (S.best_buf == 0) ? (uint32_t *)S.buf[1] : (uint32_t *)S.buf[0];
     }
     __syncthreads();
     const uint32_t nwords = (total_bits + 31) / 32;
-    for (uint32_t wd = tid; wd < nwords + 1 && wd < 2 * kMaxBlock; wd += kEncThreads) bitbuf[wd] = 0;
+    for (uint32_t wd = tid; wd < nwords + 1 && wd < 2 * kBufWords; wd += kEncThreads) bitbuf[wd] = 0;
     __syncthreads();
 
     const uint32_t mask_bps = bps >= 32 ? 0xFFFFFFFFu : ((1u << bps) - 1u);
@@ -674,7 +691,7 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
                 const uint32_t p = i / psize;
                 const uint32_t k = S.best.params[p];
                 if (i == p * psize || i == (uint32_t)order) bw.put(k, plen);
-                const uint32_t u = zigzag(R[i]);
+                const uint32_t u = zigzag(R[PX(i)]);
                 bw.zeros(u >> k);
                 bw.put((1u << k) | (u & ((1u << k) - 1u)), k + 1);
             }
@@ -751,8 +768,48 @@ __global__ void k_set_out_offsets(EncStreamDev *streams, const unsigned long lon
     if (i < n) streams[i].out_offset = offs[i];
 }
 
-// ---- frame assembly ------------------------------------------------------------
+// ---- frame assembly ------------------------------------------------------------------------------
+// One 128-thread CTA per frame.  The frame's bytes are produced in 16-byte chunks aligned to the
+// GLOBAL address (coalesced 128-bit stores; the first/last chunk of a frame is partial and written
+// bytewise), each chunk gathered from the header words / subframe slots with funnel shifts.  CRC-16:
+// per-thread Horner over its chunks (stride 128 chunks = 2048 bytes) with slice-by-4 tables, then
+// weights x^(128*(127-t)) and small tail powers, XOR-reduced over the CTA (see frb_crc16.cuh).
+// v1 stored single bytes and ran a byte-serial CRC per thread: 13.8 ms on C3 (profiles/r01_launches_c3_v1.csv).
 constexpr int kEmitThreads = 128;
+
+struct EmitShared {
+    CrcTables T;
+    uint32_t hdr[6];
+    uint32_t seg_start[FRB_MAX_CHANNELS + 2];
+    uint32_t red[kEmitThreads / 32];
+};
+
+// 32 bits of the frame bitstream starting at bit position P (P + 32 may run past the end: zero padded)
+__device__ __forceinline__ uint32_t emit_gather32(uint32_t P, const EmitShared &S, uint32_t channels, uint32_t hdr_bits,
+                                                  uint32_t end_bits, const uint32_t *__restrict__ slots_f, uint32_t slot_words) {
+    uint32_t need = 32, val = 0;
+    while (need) {
+        uint32_t take, bits;
+        if (P < hdr_bits) {
+            take = min(need, hdr_bits - P);
+            const uint32_t wi = P >> 5, sh = P & 31;
+            const uint32_t v = __funnelshift_l(S.hdr[wi + 1], S.hdr[wi], sh);
+            bits = take == 32 ? v : (v >> (32 - take));
+        } else if (P < end_bits) {
+            uint32_t c = 0;
+            while (S.seg_start[c + 1] <= P) c++;
+            const uint32_t o = P - S.seg_start[c];
+            take = min(need, S.seg_start[c + 1] - P);
+            const uint32_t *sl = slots_f + (size_t)c * slot_words;
+            const uint32_t wi = o >> 5, sh = o & 31;
+            const uint32_t v = __funnelshift_l(__ldg(sl + wi + 1), __ldg(sl + wi), sh);
+            bits = take == 32 ? v : (v >> (32 - take));
+        } else { take = need; bits = 0; }
+        val = take == 32 ? bits : ((val << take) | bits);
+        need -= take; P += take;
+    }
+    return val;
+}
 
 __global__ void __launch_bounds__(kEmitThreads)
 k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint32_t channels, uint32_t bps_stream,
@@ -760,12 +817,10 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
               const uint32_t *__restrict__ slots, uint32_t slot_words, const uint32_t *__restrict__ frame_bytes,
               const unsigned long long *__restrict__ frame_off, uint8_t *__restrict__ out, uint64_t out_capacity,
               uint32_t *__restrict__ err_flag) {
-    __shared__ uint32_t s_hdr[6];             // header bits, MSB-first words
-    __shared__ uint32_t s_seg_start[FRB_MAX_CHANNELS + 2];   // bit start of each segment within the frame
-    __shared__ uint16_t s_crc_tab[256];
-    __shared__ uint32_t s_crc_part[kEmitThreads];
+    __shared__ EmitShared S;
     const uint32_t f = blockIdx.x;
     const int tid = threadIdx.x;
+    crc_tables_to_smem(&S.T);
     uint32_t lo = 0, hi = n_streams - 1;
     while (lo < hi) {
         uint32_t mid = (lo + hi + 1) >> 1;
@@ -776,7 +831,6 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
     const uint32_t n = (k + 1 < st.n_frames) ? blocksize : (uint32_t)(st.n_samples - (uint64_t)k * blocksize);
     const uint32_t total = frame_bytes[f];
     const uint64_t dst_off = st.out_offset + frame_off[f];
-    for (int i = tid; i < 256; i += kEmitThreads) s_crc_tab[i] = c_crc16[i];
     if (tid == 0) {
         uint8_t hb[16];
         int bh, sh;
@@ -804,68 +858,78 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
         for (uint32_t q = 0; q < i; q++) crc = c_crc8[crc ^ hb[q]];
         hb[i++] = crc;
         for (uint32_t q = i; q < 16; q++) hb[q] = 0;
-        for (int w = 0; w < 4; w++) s_hdr[w] = ((uint32_t)hb[4 * w] << 24) | ((uint32_t)hb[4 * w + 1] << 16) | ((uint32_t)hb[4 * w + 2] << 8) | hb[4 * w + 3];
-        s_hdr[4] = 0; s_hdr[5] = 0;
+        for (int w = 0; w < 4; w++) S.hdr[w] = ((uint32_t)hb[4 * w] << 24) | ((uint32_t)hb[4 * w + 1] << 16) | ((uint32_t)hb[4 * w + 2] << 8) | hb[4 * w + 3];
+        S.hdr[4] = 0; S.hdr[5] = 0;
         uint32_t pos = i * 8;
-        s_seg_start[0] = pos;                       // segment c+... : subframe c starts here
-        for (uint32_t c = 0; c < channels; c++) { pos += sub_bits[(size_t)f * channels + c]; s_seg_start[c + 1] = pos; }
+        S.seg_start[0] = pos;
+        for (uint32_t c = 0; c < channels; c++) { pos += sub_bits[(size_t)f * channels + c]; S.seg_start[c + 1] = pos; }
         if (((pos + 7) >> 3) + 2 != total || dst_off + total > out_capacity) atomicExch(err_flag, 1u);
     }
     __syncthreads();
-    const uint32_t payload = total - 2;                    // bytes covered by the CRC
     if (dst_off + total > out_capacity) return;
-    const uint32_t nwords = (payload + 3) / 4;
-    const uint32_t wpt = (nwords + kEmitThreads - 1) / kEmitThreads;
-    const uint32_t w_begin = tid * wpt, w_end = min(nwords, w_begin + wpt);
-    const uint32_t hdr_bits = s_seg_start[0], end_bits = s_seg_start[channels];
+    const uint32_t payload = total - 2;                        // bytes covered by the CRC-16
+    const uint32_t hdr_bits = S.seg_start[0], end_bits = S.seg_start[channels];
+    const uint32_t *slots_f = slots + (size_t)f * channels * slot_words;
     uint8_t *dst = out + dst_off;
-    uint32_t crc = 0;
-    for (uint32_t w = w_begin; w < w_end; w++) {
-        // gather 32 bits starting at frame bit position P
-        uint32_t P = w * 32, need = 32, val = 0;
-        while (need) {
-            uint32_t take, bits;
-            if (P < hdr_bits) {
-                take = min(need, hdr_bits - P);
-                uint32_t wi = P >> 5, sh = P & 31;
-                uint32_t v = __funnelshift_l(s_hdr[wi + 1], s_hdr[wi], sh);
-                bits = take == 32 ? v : (v >> (32 - take));
-            } else if (P < end_bits) {
-                uint32_t c = 0;
-                while (s_seg_start[c + 1] <= P) c++;
-                uint32_t o = P - s_seg_start[c];
-                take = min(need, s_seg_start[c + 1] - P);
-                const uint32_t *sl = slots + ((size_t)f * channels + c) * slot_words;
-                uint32_t wi = o >> 5, sh = o & 31;
-                uint32_t v = __funnelshift_l(__ldg(sl + wi + 1), __ldg(sl + wi), sh);
-                bits = take == 32 ? v : (v >> (32 - take));
-            } else { take = need; bits = 0; }
-            val = take == 32 ? bits : ((val << take) | bits);
-            need -= take; P += take;
-        }
-        const uint32_t nb = min(4u, payload - w * 4);
+    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);   // bytes of the first chunk that are not ours
+    uint8_t *g0 = dst - a;
+    const uint32_t span = a + payload;
+    const uint32_t nfull = span >> 4, tl = span & 15;
+    const uint32_t rows = nfull / kEmitThreads, rem = nfull % kEmitThreads;
+    const CrcTables &T = S.T;
+
+    // produce chunk c: returns its four big-endian words (head-masked), stores its bytes
+    auto do_chunk = [&](uint32_t c, uint32_t (&w)[4], uint32_t nbytes /* valid bytes from the chunk start, 16 = full */) {
+        const int32_t b0 = (int32_t)(16 * c) - (int32_t)a;    // frame byte of the chunk's first byte (negative in the head chunk)
+        if (b0 >= 0 && nbytes == 16) {
 #pragma unroll
-        for (uint32_t q = 0; q < 4; q++) {
-            if (q < nb) {
-                uint8_t byte = (uint8_t)(val >> (24 - 8 * q));
-                dst[w * 4 + q] = byte;
-                crc = ((crc << 8) & 0xFFFFu) ^ s_crc_tab[((crc >> 8) ^ byte) & 0xFF];
+            for (int q = 0; q < 4; q++) w[q] = emit_gather32(8u * (uint32_t)b0 + 32u * q, S, channels, hdr_bits, end_bits, slots_f, slot_words);
+            *reinterpret_cast<uint4 *>(g0 + 16 * (size_t)c) = make_uint4(bswap32(w[0]), bswap32(w[1]), bswap32(w[2]), bswap32(w[3]));
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) w[q] = 0;
+            for (uint32_t j = 0; j < nbytes; j++) {
+                const int32_t b = b0 + (int32_t)j;
+                if (b < 0) continue;
+                const uint32_t byte = emit_gather32(8u * (uint32_t)b, S, channels, hdr_bits, end_bits, slots_f, slot_words) >> 24;
+                w[j >> 2] |= byte << (24 - 8 * (j & 3));
+                g0[16 * (size_t)c + j] = (uint8_t)byte;
             }
         }
+    };
+
+    uint32_t acc = 0;
+    for (uint32_t m = 0; m < rows; m++) {
+        uint32_t w[4];
+        do_chunk(m * kEmitThreads + tid, w, 16);
+        acc = (uint32_t)T.k2032[acc >> 8] ^ T.k2032[256 + (acc & 0xFF)];
+        acc = crc16_words4(acc, w, T.s4);
     }
-    // combine partial CRCs
-    {
-        uint64_t my_end = min((uint64_t)w_end * 4, (uint64_t)payload);
-        if (w_begin >= w_end) { crc = 0; my_end = payload; }
-        s_crc_part[tid] = gf16_mul(crc, gf16_xpow8(payload - my_end));
+    uint32_t v = gf16_mul(gf16_mul(acc, T.xp[16 * (kEmitThreads - 1 - tid)]), T.xp[16 * rem + tl]);
+    if ((uint32_t)tid < rem) {
+        uint32_t w[4];
+        do_chunk(rows * kEmitThreads + tid, w, 16);
+        v ^= gf16_mul(crc16_words4(0, w, T.s4), T.xp[16 * (rem - 1 - tid) + tl]);
     }
-    __syncthreads();
-    if (tid < 32) {
-        uint32_t v = 0;
-        for (int i = tid; i < kEmitThreads; i += 32) v ^= s_crc_part[i];
+    if (tid == kEmitThreads - 1 && tl) {
+        uint32_t w[4];
+        do_chunk(nfull, w, tl);
+        uint32_t c = 0;
+        for (uint32_t q = 0; q < tl; q++) {
+            const uint32_t byte = (w[q >> 2] >> (24 - 8 * (q & 3))) & 0xFF;
+            c = ((c << 8) & 0xFFFFu) ^ T.s4[((c >> 8) ^ byte) & 0xFF];
+        }
+        v ^= c;
+    }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(0xFFFFFFFFu, v, o);
-        if (tid == 0) { dst[payload] = (uint8_t)(v >> 8); dst[payload + 1] = (uint8_t)v; }
+    for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if ((tid & 31) == 0) S.red[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t crc = 0;
+        for (int w = 0; w < kEmitThreads / 32; w++) crc ^= S.red[w];
+        dst[payload] = (uint8_t)(crc >> 8);
+        dst[payload + 1] = (uint8_t)crc;
     }
 }
 
