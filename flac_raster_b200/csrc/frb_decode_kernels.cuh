@@ -10,31 +10,69 @@
 //   k_crc16_frames      one warp per frame, 16-byte chunks per lane, slice-by-4 tables in shared
 //                       memory, Horner combination with x^(8*512) and a final x^(8*n) weight
 
-// ---- 32-bit window bit reader over global memory (MSB first) -----------------------------------
+// ---- 32-bit window bit reader fed by a per-thread shared-memory ring (MSB first) ------------------
+// Lanes consume their streams at different rates, so in any iteration some lane needs a new word.
+// Reading that word straight from global memory (v2) made the whole warp wait for a DRAM/L2 round
+// trip almost every sample (~1000 cycles per sample on both the skim and the decode kernel,
+// profiles/r01_launches_c3_v2.csv).  Here every thread owns a ring of kRing words in shared memory,
+// refilled kRing-2 words ahead with 4-byte cp.async (no register scoreboard, no warp stall); a refill
+// is one conflict-free LDS (layout [slot][thread]) plus the next asynchronous prefetch.
+constexpr int kRing = 16;
+constexpr int kDecThreads = 128;
+
+__device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gsrc) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
 struct BitReader {
-    const uint32_t *wp;      // next word to prefetch
-    const uint32_t *wend;    // reads at/after this address yield all-ones (terminates any unary run)
-    uint32_t hi, lo, nxt;
+    uint32_t *ring;          // this thread's column: word j lives at ring[(j % kRing) * kDecThreads]
+    const uint32_t *gp;      // global address of the next word to prefetch
+    const uint32_t *gend;    // words at/after this address read as all-ones (terminates any unary run)
+    const uint32_t *g0;      // global address of the word currently in `hi` (position bookkeeping)
+    uint32_t rd;             // ring slot of the next word to move into `lo`
+    uint32_t hi, lo;
     uint32_t pos;            // consumed bits of hi, 0..31
-    __device__ __forceinline__ uint32_t fetch() {
-        const uint32_t v = wp < wend ? bswap32(__ldg(wp)) : 0xFFFFFFFFu;
-        wp++;
-        return v;
+    __device__ __forceinline__ void prefetch(uint32_t slot) {
+        uint32_t *dst = ring + slot * kDecThreads;
+        if (gp < gend) cp_async4(dst, gp); else *dst = 0xFFFFFFFFu;
+        cp_async_commit();
+        gp++;
     }
-    __device__ __forceinline__ void init(const uint8_t *base, uint64_t bitpos, uint64_t byte_end) {
+    __device__ __forceinline__ void init(uint32_t *ring_col, const uint8_t *base, uint64_t bitpos, uint64_t byte_end) {
         const uint32_t *words = (const uint32_t *)base;
-        wp = words + (bitpos >> 5);
-        wend = words + ((byte_end + 3) >> 2) + 1;
-        hi = fetch(); lo = fetch(); nxt = fetch();
+        ring = ring_col;
+        gp = words + (bitpos >> 5);
+        g0 = gp;
+        gend = words + ((byte_end + 3) >> 2) + 1;
+#pragma unroll
+        for (int j = 0; j < kRing; j++) prefetch(j);
+        cp_async_wait<0>();
+        hi = bswap32(ring[0]);
+        lo = bswap32(ring[kDecThreads]);
+        rd = 2;
+        prefetch(0); prefetch(1);
         pos = (uint32_t)bitpos & 31u;
     }
     __device__ __forceinline__ uint64_t bitpos(const uint8_t *base) const {
-        return (uint64_t)((wp - 3) - (const uint32_t *)base) * 32u + pos;
+        return (uint64_t)(g0 - (const uint32_t *)base) * 32u + pos;
     }
     __device__ __forceinline__ uint32_t window() const { return __funnelshift_l(lo, hi, pos); }
     __device__ __forceinline__ void consume(uint32_t nb) {          // nb <= 32
         pos += nb;
-        if (pos >= 32) { pos -= 32; hi = lo; lo = nxt; nxt = fetch(); }
+        if (pos >= 32) {
+            pos -= 32;
+            hi = lo;
+            // the word in slot rd was requested kRing refills ago: all but the newest kRing-1 groups must be complete
+            cp_async_wait<kRing - 1>();
+            lo = bswap32(ring[rd * kDecThreads]);
+            prefetch(rd);
+            rd = (rd + 1) & (kRing - 1);
+            g0++;
+        }
     }
     __device__ __forceinline__ uint32_t get(uint32_t nb) {          // nb in 0..32
         const uint32_t v = __funnelshift_lc(window(), 0u, nb);      // window >> (32 - nb), 0 for nb == 0
@@ -79,7 +117,9 @@ struct BitReader {
         consume(k);
     }
     __device__ __forceinline__ void seek(const uint8_t *base, uint64_t bits_forward, uint64_t byte_end) {
-        init(base, bitpos(base) + bits_forward, byte_end);
+        const uint64_t target = bitpos(base) + bits_forward;
+        cp_async_wait<0>();                                          // nothing may land in the ring after re-initialisation
+        init(ring, base, target, byte_end);
     }
 };
 
@@ -120,11 +160,12 @@ __device__ __forceinline__ FrameLoc locate_frame(const DecStreamDev *__restrict_
 // the decode kernel).  The walk is ONE flat loop with a per-lane state machine: nested
 // partition/sample loops made lanes with different partition orders wait for each other at every
 // reconvergence point (15.9 ms on C3, profiles/r01_launches_c3_v2.csv).
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kDecThreads)
 k_skim_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__restrict__ streams, uint32_t n_streams,
                  uint32_t channels, uint32_t bps, uint32_t blocksize, uint32_t total_frames,
                  const unsigned long long *__restrict__ frame_pos, uint32_t *__restrict__ sub_bitoff,
                  uint8_t *__restrict__ frame_chassign, uint32_t *__restrict__ status) {
+    __shared__ uint32_t s_ring[kRing * kDecThreads];
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= total_frames) return;
     DecStreamDev st;
@@ -137,7 +178,7 @@ k_skim_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__restri
     frame_chassign[f] = (uint8_t)h.ch_assign;
     const uint64_t frame_bit0 = L.start * 8;
     BitReader br;
-    br.init(bytes, frame_bit0 + (uint64_t)h.header_bytes * 8, L.end);
+    br.init(s_ring + threadIdx.x, bytes, frame_bit0 + (uint64_t)h.header_bytes * 8, L.end);
     const uint32_t n = L.n;
     bool err = false, in_res = false;
     uint32_t c = 0, left = 0, parts_left = 0, k = 0, plen = 4, esc = 15, psize = 0;
@@ -314,11 +355,12 @@ __device__ __forceinline__ void decode_predictive(SubCtx &S, uint32_t *status) {
 }
 
 template <bool BIGORDER>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kDecThreads)
 k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__restrict__ streams, uint32_t n_streams,
                    uint32_t channels, uint32_t bps, uint32_t blocksize, uint32_t total_frames,
                    const unsigned long long *__restrict__ frame_pos, const uint32_t *__restrict__ sub_bitoff,
                    int32_t *__restrict__ audio, uint8_t *__restrict__ frame_chassign, uint32_t *__restrict__ status) {
+    __shared__ uint32_t s_ring[kRing * kDecThreads];
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t total_sub = total_frames * channels;
     bool alive = s < total_sub;
@@ -346,7 +388,7 @@ k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__rest
                 bit0 = (L.start + hdr_bytes) * 8;
             }
             if (alive) {
-                S.br.init(bytes, bit0, L.end);
+                S.br.init(s_ring + threadIdx.x, bytes, bit0, L.end);
                 S.n = L.n;
                 const int64_t idx = st.audio_base + (int64_t)c * (int64_t)st.n_samples + (int64_t)L.k * blocksize;
                 S.dst = audio + idx;

@@ -91,6 +91,7 @@ struct EncShared {
     int best_buf;          // 0 -> resA holds best residual, 2 -> resB
     int flag, flag2;
     uint32_t misc[8];
+    double ord_bits[kMaxOrd], ord_eb2[kMaxOrd];
 };
 
 // ---- block reductions -------------------------------------------------------
@@ -391,17 +392,41 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
                 int32_t xv[kSPT + 4];
 #pragma unroll
                 for (int j = 0; j < kSPT + 4; j++) { int idx = (int)i0 - 4 + j; xv[j] = (idx >= 0 && (uint32_t)idx < n) ? X[PX(idx)] : 0; }
+                if (bps_stream <= 16) {
+                    // successive differences in 32-bit: |4th difference| <= 16 * 2^15, 16 samples per thread
+                    uint32_t e32[5] = {0, 0, 0, 0, 0};
+                    int32_t d1[kSPT + 3], d2[kSPT + 2], d3[kSPT + 1], d4[kSPT];
 #pragma unroll
-                for (int s = 0; s < kSPT; s++) {
-                    const uint32_t i = i0 + s;
-                    if (i >= 4 && i < n) {
-                        long long a = xv[s + 4], b = xv[s + 3], cc = xv[s + 2], d = xv[s + 1], ee = xv[s];
-                        long long r0 = a, r1 = a - b, r2 = a - 2 * b + cc, r3 = a - 3 * b + 3 * cc - d, r4 = a - 4 * b + 6 * cc - 4 * d + ee;
-                        e[0] += (unsigned long long)(r0 < 0 ? -r0 : r0);
-                        e[1] += (unsigned long long)(r1 < 0 ? -r1 : r1);
-                        e[2] += (unsigned long long)(r2 < 0 ? -r2 : r2);
-                        e[3] += (unsigned long long)(r3 < 0 ? -r3 : r3);
-                        e[4] += (unsigned long long)(r4 < 0 ? -r4 : r4);
+                    for (int j = 0; j < kSPT + 3; j++) d1[j] = xv[j + 1] - xv[j];
+#pragma unroll
+                    for (int j = 0; j < kSPT + 2; j++) d2[j] = d1[j + 1] - d1[j];
+#pragma unroll
+                    for (int j = 0; j < kSPT + 1; j++) d3[j] = d2[j + 1] - d2[j];
+#pragma unroll
+                    for (int j = 0; j < kSPT; j++) d4[j] = d3[j + 1] - d3[j];
+#pragma unroll
+                    for (int s = 0; s < kSPT; s++) {
+                        const uint32_t i = i0 + s;
+                        if (i >= 4 && i < n) {
+                            e32[0] += (uint32_t)abs(xv[s + 4]); e32[1] += (uint32_t)abs(d1[s + 3]); e32[2] += (uint32_t)abs(d2[s + 2]);
+                            e32[3] += (uint32_t)abs(d3[s + 1]); e32[4] += (uint32_t)abs(d4[s]);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 5; q++) e[q] = e32[q];
+                } else {
+#pragma unroll
+                    for (int s = 0; s < kSPT; s++) {
+                        const uint32_t i = i0 + s;
+                        if (i >= 4 && i < n) {
+                            long long a = xv[s + 4], b = xv[s + 3], cc = xv[s + 2], d = xv[s + 1], ee = xv[s];
+                            long long r0 = a, r1 = a - b, r2 = a - 2 * b + cc, r3 = a - 3 * b + 3 * cc - d, r4 = a - 4 * b + 6 * cc - 4 * d + ee;
+                            e[0] += (unsigned long long)(r0 < 0 ? -r0 : r0);
+                            e[1] += (unsigned long long)(r1 < 0 ? -r1 : r1);
+                            e[2] += (unsigned long long)(r2 < 0 ? -r2 : r2);
+                            e[3] += (unsigned long long)(r3 < 0 ? -r3 : r3);
+                            e[4] += (unsigned long long)(r4 < 0 ? -r4 : r4);
+                        }
                     }
                 }
             }
@@ -496,46 +521,56 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
                             if ((uint32_t)tid < max_lpc) S.autoc[tid] = S.autoc_root[tid] - S.autoc[tid];
                             __syncthreads();
                         }
-                        // ---- Levinson-Durbin, order estimate, quantisation (one thread) ----
-                        if (tid == 0) {
-                            S.flag = 0;
-                            if (have_ac && S.autoc[0] != 0.0) {
-                                double lpc[kMaxOrd];
-                                double err = S.autoc[0];
-                                uint32_t mo = max_lpc;
-                                for (uint32_t i = 0; i < max_lpc; i++) {
-                                    double r = -S.autoc[i + 1];
-                                    for (uint32_t j = 0; j < i; j++) r = __dsub_rn(r, __dmul_rn(lpc[j], S.autoc[i - j]));
-                                    r = __ddiv_rn(r, err);
-                                    lpc[i] = r;
-                                    uint32_t j;
-                                    for (j = 0; j < (i >> 1); j++) {
-                                        double tmp = lpc[j];
-                                        lpc[j] = __dadd_rn(lpc[j], __dmul_rn(r, lpc[i - 1 - j]));
-                                        lpc[i - 1 - j] = __dadd_rn(lpc[i - 1 - j], __dmul_rn(r, tmp));
+                        // ---- Levinson-Durbin (lane 0), expected bits per order (one lane per order, the
+                        // logarithms dominated the serial section), order pick + quantisation (lane 0) ----
+                        if (warp == 0) {
+                            if (lane == 0) {
+                                S.flag = 0; S.misc[0] = 0;
+                                if (have_ac && S.autoc[0] != 0.0) {
+                                    double lpc[kMaxOrd];
+                                    double err = S.autoc[0];
+                                    uint32_t mo = max_lpc;
+                                    for (uint32_t i = 0; i < max_lpc; i++) {
+                                        double r = -S.autoc[i + 1];
+                                        for (uint32_t j = 0; j < i; j++) r = __dsub_rn(r, __dmul_rn(lpc[j], S.autoc[i - j]));
+                                        r = __ddiv_rn(r, err);
+                                        lpc[i] = r;
+                                        uint32_t j;
+                                        for (j = 0; j < (i >> 1); j++) {
+                                            double tmp = lpc[j];
+                                            lpc[j] = __dadd_rn(lpc[j], __dmul_rn(r, lpc[i - 1 - j]));
+                                            lpc[i - 1 - j] = __dadd_rn(lpc[i - 1 - j], __dmul_rn(r, tmp));
+                                        }
+                                        if (i & 1) lpc[j] = __dadd_rn(lpc[j], __dmul_rn(lpc[j], r));
+                                        err = __dmul_rn(err, __dsub_rn(1.0, __dmul_rn(r, r)));
+                                        for (j = 0; j <= i; j++) S.lp[i][j] = (float)(-lpc[j]);
+                                        S.lp_err[i] = err;
+                                        if (err == 0.0) { mo = i + 1; break; }
                                     }
-                                    if (i & 1) lpc[j] = __dadd_rn(lpc[j], __dmul_rn(lpc[j], r));
-                                    err = __dmul_rn(err, __dsub_rn(1.0, __dmul_rn(r, r)));
-                                    for (j = 0; j <= i; j++) S.lp[i][j] = (float)(-lpc[j]);
-                                    S.lp_err[i] = err;
-                                    if (err == 0.0) { mo = i + 1; break; }
+                                    S.misc[0] = mo;
                                 }
-                                // FLAC__lpc_compute_best_order
-                                const double scale = 0.5 / (double)n;
+                            }
+                            __syncwarp();
+                            const uint32_t mo = S.misc[0];
+                            if ((uint32_t)lane < mo) {
+                                // FLAC__lpc_compute_best_order term and the "don't even try" estimate for this order
+                                const double le = S.lp_err[lane];
+                                const uint32_t ord = (uint32_t)lane + 1;
+                                const double scale = 0.5 / (double)n, scale2 = 0.5 / (double)(n - ord);
+                                double eb, eb2;
+                                if (le > 0.0) {
+                                    eb = 0.5 * log(scale * le) / 0.69314718055994530942; if (eb < 0.0) eb = 0.0;
+                                    eb2 = 0.5 * log(scale2 * le) / 0.69314718055994530942; if (eb2 < 0.0) eb2 = 0.0;
+                                } else if (le < 0.0) { eb = 1e32; eb2 = 1e32; } else { eb = 0.0; eb2 = 0.0; }
+                                S.ord_bits[lane] = eb * (double)(n - ord) + (double)(ord * (bps + qprec_cfg));
+                                S.ord_eb2[lane] = eb2;
+                            }
+                            __syncwarp();
+                            if (lane == 0 && mo > 0) {
                                 uint32_t best_i = 0; double best_b = 4294967295.0;
-                                const uint32_t overhead = bps + qprec_cfg;
-                                for (uint32_t i = 0; i < mo; i++) {
-                                    double le = S.lp_err[i], eb;
-                                    if (le > 0.0) { eb = 0.5 * log(scale * le) / 0.69314718055994530942; if (eb < 0.0) eb = 0.0; }
-                                    else if (le < 0.0) eb = 1e32; else eb = 0.0;
-                                    double bits = eb * (double)(n - (i + 1)) + (double)((i + 1) * overhead);
-                                    if (bits < best_b) { best_b = bits; best_i = i; }
-                                }
+                                for (uint32_t i = 0; i < mo; i++) { const double bits = S.ord_bits[i]; if (bits < best_b) { best_b = bits; best_i = i; } }
                                 const uint32_t order = best_i + 1;
-                                double le = S.lp_err[order - 1], eb;
-                                const double scale2 = 0.5 / (double)(n - order);
-                                if (le > 0.0) { eb = 0.5 * log(scale2 * le) / 0.69314718055994530942; if (eb < 0.0) eb = 0.0; }
-                                else if (le < 0.0) eb = 1e32; else eb = 0.0;
+                                const double eb = S.ord_eb2[order - 1];
                                 if (!(eb >= (double)bps)) {
                                     uint32_t prec = qprec_cfg;
                                     if (bps <= 17) { uint32_t lim = 32 - bps - (uint32_t)ilog2_u32(order); if (lim < prec) prec = lim; }
@@ -607,16 +642,26 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
     const uint32_t plen = method ? 5u : 4u;
     const uint32_t psize = n >> po;
     uint32_t my_bits = 0;
-    if (type >= 2) {
+    // folded residuals and their Rice parameters stay in registers between the length pass and the pack pass;
+    // the partition index is tracked incrementally (one division per thread instead of two per sample)
+    uint32_t u_reg[kSPT], k_reg[kSPT];
+    uint32_t pstart_mask = 0;                    // bit s: sample i0+s is the first residual of its partition
+    if (type >= 2 && i0 < n) {
+        uint32_t p = i0 / psize;
+        uint32_t next_b = (p + 1) * psize;
+        uint32_t kcur = S.best.params[p];
 #pragma unroll
         for (int s = 0; s < kSPT; s++) {
             const uint32_t i = i0 + s;
-            if (i < n && i >= (uint32_t)order) {
-                const uint32_t p = i / psize;
-                const uint32_t k = S.best.params[p];
-                const uint32_t u = zigzag(R[PX(i)]);
-                my_bits += (u >> k) + 1 + k;
-                if (i == p * psize || i == (uint32_t)order) my_bits += plen;
+            u_reg[s] = 0; k_reg[s] = 0;
+            if (i < n) {
+                if (i == next_b) { p++; next_b += psize; kcur = S.best.params[p]; }
+                if (i >= (uint32_t)order) {
+                    const uint32_t u = zigzag(R[PX(i)]);
+                    u_reg[s] = u; k_reg[s] = kcur;
+                    my_bits += (u >> kcur) + 1 + kcur;
+                    if (i + psize == next_b || i == (uint32_t)order) { my_bits += plen; pstart_mask |= 1u << s; }
+                }
             }
         }
     }
@@ -688,12 +733,12 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
         for (int s = 0; s < kSPT; s++) {
             const uint32_t i = i0 + s;
             if (i < n && i >= (uint32_t)order) {
-                const uint32_t p = i / psize;
-                const uint32_t k = S.best.params[p];
-                if (i == p * psize || i == (uint32_t)order) bw.put(k, plen);
-                const uint32_t u = zigzag(R[PX(i)]);
-                bw.zeros(u >> k);
-                bw.put((1u << k) | (u & ((1u << k) - 1u)), k + 1);
+                const uint32_t k = k_reg[s], u = u_reg[s];
+                if (pstart_mask & (1u << s)) bw.put(k, plen);
+                const uint32_t q = u >> k;
+                const uint32_t tailv = (1u << k) | (u & ((1u << k) - 1u));
+                if (q + k + 1 <= 32) bw.put(tailv, q + k + 1);       // zeros, stop bit and LSBs in one write
+                else { bw.zeros(q); bw.put(tailv, k + 1); }
             }
         }
         bw.finish();
