@@ -19,59 +19,60 @@
 // is one conflict-free LDS (layout [slot][thread]) plus the next asynchronous prefetch.
 constexpr int kRing = 16;
 constexpr int kDecThreads = 128;
+constexpr uint32_t kRingBytes = kRing * kDecThreads * 4;      // 8 KB per CTA; slot stride kDecThreads*4 bytes
 
-__device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gsrc) {
-    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc) : "memory");
+__device__ __forceinline__ void cp_async4_s(uint32_t smem_addr, const uint32_t *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_addr), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t smem_addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(smem_addr) : "memory");
+    return v;
+}
 
 struct BitReader {
-    uint32_t *ring;          // this thread's column: word j lives at ring[(j % kRing) * kDecThreads]
-    const uint32_t *gp;      // global address of the next word to prefetch
-    const uint32_t *gend;    // words at/after this address read as all-ones (terminates any unary run)
-    const uint32_t *g0;      // global address of the word currently in `hi` (position bookkeeping)
-    uint32_t rd;             // ring slot of the next word to move into `lo`
+    const uint32_t *gwords;  // 4-byte view of the input buffer (kernel-uniform)
+    uint32_t sbase;          // shared-space address of this thread's ring column (slot 0)
+    uint32_t soff;           // byte offset (multiple of kDecThreads*4, < kRingBytes) of the next slot to read
+    uint32_t widx;           // word index of the next word to prefetch; the word in `hi` is widx - (kRing + 2)
+    uint32_t wlast;          // prefetches are clamped to this word index (one word past the frame end)
     uint32_t hi, lo;
     uint32_t pos;            // consumed bits of hi, 0..31
-    __device__ __forceinline__ void prefetch(uint32_t slot) {
-        uint32_t *dst = ring + slot * kDecThreads;
-        if (gp < gend) cp_async4(dst, gp); else *dst = 0xFFFFFFFFu;
+    __device__ __forceinline__ void prefetch(uint32_t slot_off) {
+        cp_async4_s(sbase + slot_off, gwords + min(widx, wlast));
         cp_async_commit();
-        gp++;
+        widx++;
     }
-    __device__ __forceinline__ void init(uint32_t *ring_col, const uint8_t *base, uint64_t bitpos, uint64_t byte_end) {
-        const uint32_t *words = (const uint32_t *)base;
-        ring = ring_col;
-        gp = words + (bitpos >> 5);
-        g0 = gp;
-        gend = words + ((byte_end + 3) >> 2) + 1;
+    __device__ __forceinline__ void init(uint32_t ring_col_saddr, const uint8_t *base, uint64_t bitpos, uint64_t byte_end) {
+        gwords = (const uint32_t *)base;
+        sbase = ring_col_saddr;
+        widx = (uint32_t)(bitpos >> 5);
+        wlast = (uint32_t)((byte_end + 3) >> 2);
 #pragma unroll
-        for (int j = 0; j < kRing; j++) prefetch(j);
+        for (int j = 0; j < kRing; j++) prefetch(j * kDecThreads * 4);
         cp_async_wait<0>();
-        hi = bswap32(ring[0]);
-        lo = bswap32(ring[kDecThreads]);
-        rd = 2;
-        prefetch(0); prefetch(1);
+        hi = bswap32(lds_u32(sbase));
+        lo = bswap32(lds_u32(sbase + kDecThreads * 4));
+        prefetch(0); prefetch(kDecThreads * 4);
+        soff = 2 * kDecThreads * 4;
         pos = (uint32_t)bitpos & 31u;
     }
-    __device__ __forceinline__ uint64_t bitpos(const uint8_t *base) const {
-        return (uint64_t)(g0 - (const uint32_t *)base) * 32u + pos;
-    }
+    __device__ __forceinline__ uint64_t bitpos() const { return (uint64_t)(widx - (kRing + 2)) * 32u + pos; }
+    __device__ __forceinline__ bool overrun() const { return widx - (kRing + 2) > wlast + 1; }
     __device__ __forceinline__ uint32_t window() const { return __funnelshift_l(lo, hi, pos); }
     __device__ __forceinline__ void consume(uint32_t nb) {          // nb <= 32
         pos += nb;
         if (pos >= 32) {
             pos -= 32;
             hi = lo;
-            // the word in slot rd was requested kRing refills ago: all but the newest kRing-1 groups must be complete
+            // the word in this slot was requested kRing refills ago: all but the newest kRing-1 groups must be complete
             cp_async_wait<kRing - 1>();
-            lo = bswap32(ring[rd * kDecThreads]);
-            prefetch(rd);
-            rd = (rd + 1) & (kRing - 1);
-            g0++;
+            lo = bswap32(lds_u32(sbase + soff));
+            prefetch(soff);
+            soff = (soff + kDecThreads * 4) & (kRingBytes - 1);
         }
     }
     __device__ __forceinline__ uint32_t get(uint32_t nb) {          // nb in 0..32
@@ -92,6 +93,7 @@ struct BitReader {
             const uint32_t w = window();
             if (w) { const uint32_t z = __clz(w); consume(z + 1); return q + z; }
             q += 32; consume(32);
+            if (overrun()) return q;                                // ran past the frame: corrupt stream
         }
     }
     // zig-zag folded Rice value with parameter k (<= 30)
@@ -110,16 +112,15 @@ struct BitReader {
         return (q << k) | low;
     }
     __device__ __forceinline__ void skip_rice(uint32_t k) {
-        const uint32_t w = window();
-        const uint32_t len = __clz(w) + 1 + k;
+        const uint32_t len = __clz(window()) + 1 + k;
         if (len <= 32) { consume(len); return; }
         (void)unary();
         consume(k);
     }
     __device__ __forceinline__ void seek(const uint8_t *base, uint64_t bits_forward, uint64_t byte_end) {
-        const uint64_t target = bitpos(base) + bits_forward;
+        const uint64_t target = bitpos() + bits_forward;
         cp_async_wait<0>();                                          // nothing may land in the ring after re-initialisation
-        init(ring, base, target, byte_end);
+        init(sbase, base, target, byte_end);
     }
 };
 
@@ -178,13 +179,32 @@ k_skim_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__restri
     frame_chassign[f] = (uint8_t)h.ch_assign;
     const uint64_t frame_bit0 = L.start * 8;
     BitReader br;
-    br.init(s_ring + threadIdx.x, bytes, frame_bit0 + (uint64_t)h.header_bytes * 8, L.end);
+    br.init((uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x), bytes, frame_bit0 + (uint64_t)h.header_bytes * 8, L.end);
     const uint32_t n = L.n;
     bool err = false, in_res = false;
     uint32_t c = 0, left = 0, parts_left = 0, k = 0, plen = 4, esc = 15, psize = 0;
     off_out[0] = h.header_bytes * 8;
-    while (!err && c + 1 < channels) {
-        if (!in_res) {
+    // hot path first: one Rice code per iteration; header / partition transitions are the rare branch
+    if (channels > 1) for (;;) {
+        if (left) {
+            br.skip_rice(k);
+            left--;
+            continue;
+        }
+        if (in_res) {
+            // partition exhausted: next partition, or the subframe is finished
+            for (;;) {
+                if (--parts_left == 0) { in_res = false; break; }
+                left = psize;
+                k = br.get(plen);
+                if (k == esc) { const uint32_t raw = br.get(5); br.seek(bytes, (uint64_t)raw * left, L.end); left = 0; }
+                if (left) break;
+            }
+            if (!in_res) { c++; off_out[c] = (uint32_t)(br.bitpos() - frame_bit0); }
+            continue;
+        }
+        if (err || c + 1 >= channels) break;
+        {
             uint32_t sbps = bps;
             if ((h.ch_assign == 8 && c == 1) || (h.ch_assign == 9 && c == 0) || (h.ch_assign == 10 && c == 1)) sbps++;
             const uint32_t hd = br.get(8);
@@ -226,22 +246,11 @@ k_skim_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__restri
                     if (psize == 0) { err = true; break; }
                 }
             }
-            if (!in_res) { c++; off_out[c] = (uint32_t)(br.bitpos(bytes) - frame_bit0); }
-        } else {
-            br.skip_rice(k);
-            if (--left == 0) {
-                for (;;) {
-                    if (--parts_left == 0) { in_res = false; break; }
-                    left = psize;
-                    k = br.get(plen);
-                    if (k == esc) { const uint32_t raw = br.get(5); br.seek(bytes, (uint64_t)raw * left, L.end); left = 0; }
-                    if (left) break;
-                }
-                if (!in_res) { c++; off_out[c] = (uint32_t)(br.bitpos(bytes) - frame_bit0); }
-            }
+            if (!in_res) { c++; off_out[c] = (uint32_t)(br.bitpos() - frame_bit0); }
         }
+        if (err) break;
     }
-    if (!err && br.bitpos(bytes) > L.end * 8) err = true;
+    if (!err && br.bitpos() > L.end * 8) err = true;
     if (err) {
         atomicAdd(&status[2], 1u);
         for (uint32_t q = 0; q < channels; q++) off_out[q] = 0;
@@ -388,7 +397,7 @@ k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__rest
                 bit0 = (L.start + hdr_bytes) * 8;
             }
             if (alive) {
-                S.br.init(s_ring + threadIdx.x, bytes, bit0, L.end);
+                S.br.init((uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x), bytes, bit0, L.end);
                 S.n = L.n;
                 const int64_t idx = st.audio_base + (int64_t)c * (int64_t)st.n_samples + (int64_t)L.k * blocksize;
                 S.dst = audio + idx;
@@ -442,7 +451,7 @@ k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__rest
     if (alive) {
         if (!S.err && c + 1 == channels) {
             // the last subframe must end (after byte padding) exactly 2 bytes before the next frame
-            const uint64_t bits = S.br.bitpos(bytes) - L.start * 8;
+            const uint64_t bits = S.br.bitpos() - L.start * 8;
             if (L.start + ((bits + 7) >> 3) + 2 != L.end) S.err = true;
         }
         if (S.err) atomicAdd(&status[2], 1u);
