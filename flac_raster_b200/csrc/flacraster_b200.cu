@@ -9,6 +9,7 @@ namespace frb {
 static int ensure_tables_impl();
 }
 #include "frb_normalize.cuh"
+#include "frb_tilemap.cuh"
 #include "frb_decode.cuh"
 #include "frb_encode.cuh"
 #include "frb_host.cuh"

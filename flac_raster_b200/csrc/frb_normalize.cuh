@@ -111,28 +111,6 @@ __device__ __forceinline__ void block_minmax_commit(unsigned long long kmin, uns
     }
 }
 
-// grid: (chunks, n_tiles). Each CTA reduces a slice of one tile (all bands).
-__global__ void __launch_bounds__(256)
-k_minmax_tiles(const void *__restrict__ raster, int dtype, uint32_t bands, uint32_t H, uint32_t W,
-               const frb_tile *__restrict__ tiles, unsigned long long *keys) {
-    const frb_tile t = tiles[blockIdx.y];
-    const uint32_t n = t.h * t.w;   // tiles hold < 2^32 pixels per band
-    unsigned long long kmin = kKeyMinInit, kmax = kKeyMaxInit;
-    for (uint32_t c = 0; c < bands; c++)
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
-        const uint64_t i = (uint64_t)c * n + r;
-        uint32_t y = r / t.w, x = r - y * t.w;
-        uint64_t src = ((uint64_t)c * H + (t.row_off + y)) * W + (t.col_off + x);
-        double v = load_as_double(raster, dtype, src);
-        if (v == v) {
-            unsigned long long k = dkey(v);
-            kmin = k < kmin ? k : kmin;
-            kmax = k > kmax ? k : kmax;
-        }
-    }
-    block_minmax_commit(kmin, kmax, keys + 2 * (size_t)blockIdx.y);
-}
-
 __global__ void __launch_bounds__(256)
 k_minmax_flat(const void *__restrict__ src, int dtype, uint64_t n, unsigned long long *keys) {
     unsigned long long kmin = kKeyMinInit, kmax = kKeyMaxInit;
@@ -166,25 +144,6 @@ __device__ __forceinline__ double scale_for_bits(int bits) {
 }
 
 __global__ void __launch_bounds__(256)
-k_normalize_tiles(const void *__restrict__ raster, int dtype, uint32_t bands, uint32_t H, uint32_t W,
-                  const frb_tile *__restrict__ tiles, const double *__restrict__ minmax, int bits,
-                  int32_t *__restrict__ audio, const int64_t *__restrict__ audio_base) {
-    const frb_tile t = tiles[blockIdx.y];
-    const uint32_t n = t.h * t.w;   // tiles hold < 2^32 pixels per band
-    const double mn = minmax[2 * blockIdx.y], mx = minmax[2 * blockIdx.y + 1];
-    const double range = (mx <= mn) ? 1.0 : __dsub_rn(mx, mn);
-    const double scale = scale_for_bits(bits);
-    int32_t *dst = audio + audio_base[blockIdx.y];
-    for (uint32_t c = 0; c < bands; c++)
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
-        const uint64_t i = (uint64_t)c * n + r;
-        uint32_t y = r / t.w, x = r - y * t.w;
-        uint64_t src = ((uint64_t)c * H + (t.row_off + y)) * W + (t.col_off + x);
-        dst[i] = normalize_one(load_as_double(raster, dtype, src), mn, range, scale);
-    }
-}
-
-__global__ void __launch_bounds__(256)
 k_normalize_flat(const void *__restrict__ src, int dtype, uint64_t n, double mn, double mx, int bits,
                  void *__restrict__ out, int out16) {
     const double range = (mx <= mn) ? 1.0 : __dsub_rn(mx, mn);
@@ -193,24 +152,6 @@ k_normalize_flat(const void *__restrict__ src, int dtype, uint64_t n, double mn,
          i += (uint64_t)gridDim.x * blockDim.x) {
         int32_t v = normalize_one(load_as_double(src, dtype, i), mn, range, scale);
         if (out16) ((int16_t *)out)[i] = (int16_t)v; else ((int32_t *)out)[i] = v;
-    }
-}
-
-__global__ void __launch_bounds__(256)
-k_denormalize_tiles(const int32_t *__restrict__ audio, const int64_t *__restrict__ audio_base,
-                    const frb_tile *__restrict__ tiles, const double *__restrict__ minmax, double scale,
-                    void *__restrict__ raster, int dtype, uint32_t bands, uint32_t H, uint32_t W) {
-    const frb_tile t = tiles[blockIdx.y];
-    const uint32_t n = t.h * t.w;   // tiles hold < 2^32 pixels per band
-    const double mn = minmax[2 * blockIdx.y], mx = minmax[2 * blockIdx.y + 1];
-    const double range = __dsub_rn(mx, mn);     // denormalize uses max-min unconditionally (:239)
-    const int32_t *src = audio + audio_base[blockIdx.y];
-    for (uint32_t c = 0; c < bands; c++)
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
-        const uint64_t i = (uint64_t)c * n + r;
-        uint32_t y = r / t.w, x = r - y * t.w;
-        uint64_t d = ((uint64_t)c * H + (t.row_off + y)) * W + (t.col_off + x);
-        store_denorm(raster, dtype, d, denormalize_one((double)src[i], scale, mn, range));
     }
 }
 
@@ -236,57 +177,6 @@ static inline uint32_t grid_for(uint64_t n, uint32_t per_cta, uint32_t max_ctas)
 }  // namespace frb
 
 // ------------------------------------------------------------------ C ABI
-extern "C" int frb_minmax_tiles(const void *d_raster, int dtype, uint32_t bands, uint32_t H, uint32_t W,
-                                const frb_tile *d_tiles, uint32_t n_tiles, double *d_minmax, void *stream) {
-    using namespace frb;
-    if (!d_raster || !d_tiles || !d_minmax || dtype < 0 || dtype > FRB_F64 || !bands || !n_tiles) return FRB_ERR_INVALID_ARG;
-    cudaStream_t s = (cudaStream_t)stream;
-    k_minmax_init<<<(n_tiles + 255) / 256, 256, 0, s>>>((unsigned long long *)d_minmax, n_tiles);
-    FRB_LAUNCH_CHECK("k_minmax_init");
-    // enough CTAs per tile to fill 148 SMs x 8 resident CTAs even for few tiles
-    uint32_t per_tile = (kNumSMs * 8 + n_tiles - 1) / n_tiles;
-    if (per_tile > 64) per_tile = 64;
-    if (per_tile < 1) per_tile = 1;
-    dim3 grid(per_tile, n_tiles);
-    k_minmax_tiles<<<grid, 256, 0, s>>>(d_raster, dtype, bands, H, W, d_tiles, (unsigned long long *)d_minmax);
-    FRB_LAUNCH_CHECK("k_minmax_tiles");
-    k_minmax_finish<<<(n_tiles + 255) / 256, 256, 0, s>>>((unsigned long long *)d_minmax, n_tiles);
-    FRB_LAUNCH_CHECK("k_minmax_finish");
-    return FRB_OK;
-}
-
-extern "C" int frb_normalize_tiles(const void *d_raster, int dtype, uint32_t bands, uint32_t H, uint32_t W,
-                                   const frb_tile *d_tiles, uint32_t n_tiles, const double *d_minmax,
-                                   int bits_per_sample, int32_t *d_audio, const int64_t *d_audio_base,
-                                   void *stream) {
-    using namespace frb;
-    if (!d_raster || !d_tiles || !d_minmax || !d_audio || !d_audio_base || dtype < 0 || dtype > FRB_F64 || !bands || !n_tiles)
-        return FRB_ERR_INVALID_ARG;
-    uint32_t per_tile = (kNumSMs * 8 + n_tiles - 1) / n_tiles;
-    if (per_tile > 64) per_tile = 64;
-    dim3 grid(per_tile, n_tiles);
-    k_normalize_tiles<<<grid, 256, 0, (cudaStream_t)stream>>>(d_raster, dtype, bands, H, W, d_tiles, d_minmax,
-                                                             bits_per_sample, d_audio, d_audio_base);
-    FRB_LAUNCH_CHECK("k_normalize_tiles");
-    return FRB_OK;
-}
-
-extern "C" int frb_denormalize_tiles(const int32_t *d_audio, const int64_t *d_audio_base,
-                                     const frb_tile *d_tiles, uint32_t n_tiles, const double *d_minmax,
-                                     double scale, void *d_raster, int dtype, uint32_t bands, uint32_t H,
-                                     uint32_t W, void *stream) {
-    using namespace frb;
-    if (!d_raster || !d_tiles || !d_minmax || !d_audio || !d_audio_base || dtype < 0 || dtype > FRB_F64 || !bands || !n_tiles)
-        return FRB_ERR_INVALID_ARG;
-    uint32_t per_tile = (kNumSMs * 8 + n_tiles - 1) / n_tiles;
-    if (per_tile > 64) per_tile = 64;
-    dim3 grid(per_tile, n_tiles);
-    k_denormalize_tiles<<<grid, 256, 0, (cudaStream_t)stream>>>(d_audio, d_audio_base, d_tiles, d_minmax, scale,
-                                                               d_raster, dtype, bands, H, W);
-    FRB_LAUNCH_CHECK("k_denormalize_tiles");
-    return FRB_OK;
-}
-
 extern "C" int frb_minmax_flat(const void *d_src, int dtype, uint64_t n, double *d_minmax, void *stream) {
     using namespace frb;
     if (!d_src || !d_minmax || dtype < 0 || dtype > FRB_F64) return FRB_ERR_INVALID_ARG;

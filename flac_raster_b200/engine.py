@@ -84,6 +84,11 @@ class Engine:
             self._ws[name] = t
         return t
 
+    def _map_ws(self, n_tiles: int) -> torch.Tensor:
+        nbytes = C.c_size_t(0)
+        nat.check(self.L.frb_sample_map_workspace_size(n_tiles, C.byref(nbytes)), "frb_sample_map_workspace_size")
+        return self._buf("map_ws", nbytes.value)
+
     def release(self):
         self._ws.clear()
 
@@ -109,9 +114,10 @@ class Engine:
             audio = self._buf("audio", total * 4)
             nat.check(self.L.frb_minmax_tiles(raster.data_ptr(), code, bands, H, W, d_tiles.data_ptr(), n_tiles,
                                               d_minmax.data_ptr(), s), "frb_minmax_tiles")
+            mws = self._map_ws(n_tiles)
             nat.check(self.L.frb_normalize_tiles(raster.data_ptr(), code, bands, H, W, d_tiles.data_ptr(), n_tiles,
                                                  d_minmax.data_ptr(), bits_per_sample, audio.data_ptr(),
-                                                 d_base.data_ptr(), s), "frb_normalize_tiles")
+                                                 d_base.data_ptr(), mws.data_ptr(), mws.numel(), s), "frb_normalize_tiles")
         return audio, base, npx, d_minmax, bits_per_sample
 
     def encode_audio(self, audio: torch.Tensor, n_samples: np.ndarray, audio_base: np.ndarray, sample_rates: np.ndarray,
@@ -201,9 +207,10 @@ class Engine:
             d_tiles = torch.from_numpy(tiles.view(np.uint8).copy()).to(self.device, non_blocking=True)
             d_base = torch.from_numpy(np.ascontiguousarray(audio_base, dtype=np.int64)).to(self.device, non_blocking=True)
             d_mm = torch.from_numpy(np.ascontiguousarray(minmax, dtype=np.float64).reshape(-1)).to(self.device, non_blocking=True)
+            mws = self._map_ws(len(tiles))
             nat.check(self.L.frb_denormalize_tiles(audio.data_ptr(), d_base.data_ptr(), d_tiles.data_ptr(), len(tiles),
                                                    d_mm.data_ptr(), float(scale), out.data_ptr(), nat.DTYPE_CODES[dt],
-                                                   bands, H, W, s), "frb_denormalize_tiles")
+                                                   bands, H, W, mws.data_ptr(), mws.numel(), s), "frb_denormalize_tiles")
             # keep the staging tensors alive until the kernel has consumed them
             torch.cuda.current_stream().synchronize()
         return out

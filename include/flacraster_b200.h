@@ -93,7 +93,12 @@ int frb_minmax_tiles(const void *d_raster, int dtype, uint32_t bands, uint32_t H
 int frb_normalize_tiles(const void *d_raster, int dtype, uint32_t bands, uint32_t H, uint32_t W,
                         const frb_tile *d_tiles, uint32_t n_tiles, const double *d_minmax,
                         int bits_per_sample, int32_t *d_audio, const int64_t *d_audio_base,
-                        void *stream);
+                        void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* Optional device workspace for frb_normalize_tiles / frb_denormalize_tiles: exact lookup tables that
+ * replace the per-sample fp64 divisions (entries are computed with the same operations, so results
+ * are unchanged).  Pass NULL/0 to compute every sample directly. */
+int frb_sample_map_workspace_size(uint32_t n_tiles, size_t *bytes);
 
 /* denormalize_from_audio (normalization.py:222-249), integer path
  * (audio/scale, fp64), np.round for integer dtypes, scattered back into the
@@ -101,7 +106,7 @@ int frb_normalize_tiles(const void *d_raster, int dtype, uint32_t bands, uint32_
 int frb_denormalize_tiles(const int32_t *d_audio, const int64_t *d_audio_base,
                           const frb_tile *d_tiles, uint32_t n_tiles, const double *d_minmax,
                           double scale, void *d_raster, int dtype, uint32_t bands, uint32_t H,
-                          uint32_t W, void *stream);
+                          uint32_t W, void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* Flat elementwise forms used by the drop-in normalize_to_audio /
  * denormalize_from_audio functions: n elements, any layout, one (min,max).
