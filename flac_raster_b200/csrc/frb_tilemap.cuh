@@ -2,32 +2,34 @@
 // (bands,H,W) raster resident in HBM.  Reference: normalization.py:149-187 and :222-249, applied per tile
 // as cli.py:553-594 does.
 //
-// v1 (profiles/r01_launches_c3_v1.csv) spent 3.8 / 2.6 / 4.2 ms on C3 where the HBM floor is ~0.9 / 0.3 /
-// 0.9 ms: a runtime dtype switch and an integer division per element, plus ~40 fp64 instructions per
-// sample (two IEEE divisions) on a 64-lane fp64 pipe.  v2: kernels are templated on the element type,
-// walk (band,row) pairs so no per-element division is needed, and replace the per-sample fp64 division
-// by exact lookup tables whose entries are computed with the very same operations:
-//   * normalise, 8/16-bit sources: per-tile table over the tile's value range [min,max] (when it spans
-//     fewer than kNormLutCap values), entry = normalize_one(value);
-//   * denormalise, 16-bit audio (scale 32767): one table t[a] = (a/32767 + 1)/2 shared by all tiles, then
-//     x = t*range + min with the same two rounded operations.
+// These three kernels are pure HBM streams (algorithmic bytes per sample: sizeof(T), sizeof(T)+4, 4+sizeof(T)).
+// v1 (profiles/r01_launches_c3_v1.csv) spent 3.8 / 2.6 / 4.2 ms on C3 where the HBM floor is ~0.3 / 0.9 /
+// 0.9 ms: a runtime dtype switch and an integer division per element.  v2 (typed, one CTA per row, one
+// element per thread and iteration, table gathers) still took 2.3 / 2.7 / 4.9 ms
+// (profiles/r01_launches_c3_v3.csv): with 2-4 bytes per load and a dependent loop there were far too few
+// bytes in flight per SM to cover DRAM latency.  v3 (this file):
+//   * one WARP per (band,row) of the tile; the row is walked in 16-byte vectors of the raster type (aligned
+//     head/tail handled by single lanes), four independent vectors in flight per lane;
+//   * the int32 audio side is accessed with 16-byte vectors as well whenever the row is 16-byte aligned
+//     (always for the BASELINE shapes), else with scalar accesses;
+//   * normalise, 8/16-bit sources: per-tile exact table over the tile's value range [min,max] (when it
+//     spans fewer than kNormLutCap values), entry = normalize_one(value), so the fp64 pipe is idle;
+//     everything else is computed directly with the reference's fp64 operation order.
 #pragma once
 #include "frb_normalize.cuh"
 
 namespace frb {
 
 constexpr uint32_t kNormLutCap = 16384;      // per-tile normalise table entries (int32)
-constexpr uint32_t kDenormLutN = 65536;      // audio value + 32768
+constexpr int kMapThreads = 256;
+constexpr int kMapWarps = kMapThreads / 32;
 
 struct MapWorkspace {
     int32_t *norm_lut;       // n_tiles * kNormLutCap
-    double *denorm_lut;      // kDenormLutN
 };
 static inline size_t map_ws_layout(uint32_t n_tiles, void *base, MapWorkspace *w) {
     size_t off = 0;
     uint8_t *b = (uint8_t *)base;
-    if (w) w->denorm_lut = (double *)(b + off);
-    off += (size_t)kDenormLutN * 8;
     if (w) w->norm_lut = (int32_t *)(b + off);
     off += (size_t)n_tiles * kNormLutCap * 4;
     return off + 256;
@@ -38,32 +40,95 @@ template <> struct is_small_int<uint8_t> { static constexpr bool value = true; }
 template <> struct is_small_int<int8_t> { static constexpr bool value = true; };
 template <> struct is_small_int<uint16_t> { static constexpr bool value = true; };
 template <> struct is_small_int<int16_t> { static constexpr bool value = true; };
+template <typename T> struct is_fp { static constexpr bool value = false; };
+template <> struct is_fp<float> { static constexpr bool value = true; };
+template <> struct is_fp<double> { static constexpr bool value = true; };
+
+// A group of G consecutive elements: the unit of the row walk.  G*sizeof(T) and G*4 are multiples of 16.
+template <typename T> struct MapGroup {
+    static constexpr int G = (16 / sizeof(T)) > 4 ? (16 / sizeof(T)) : 4;
+    static constexpr int TV = G * sizeof(T) / 16;     // 16-byte vectors on the raster side
+    static constexpr int AV = G * 4 / 16;             // 16-byte vectors on the int32 audio side
+};
+
+__device__ __forceinline__ uint4 ld_stream16(const void *p) { return __ldcs(reinterpret_cast<const uint4 *>(p)); }
+__device__ __forceinline__ void st_stream16(void *p, uint4 v) { __stcs(reinterpret_cast<uint4 *>(p), v); }
+
+template <typename T>
+__device__ __forceinline__ void load_group(const T *p, T (&e)[MapGroup<T>::G]) {
+    union { uint4 v[MapGroup<T>::TV]; T e[MapGroup<T>::G]; } u;
+#pragma unroll
+    for (int q = 0; q < MapGroup<T>::TV; q++) u.v[q] = ld_stream16(reinterpret_cast<const uint8_t *>(p) + 16 * q);
+#pragma unroll
+    for (int j = 0; j < MapGroup<T>::G; j++) e[j] = u.e[j];
+}
+template <typename T>
+__device__ __forceinline__ void store_group(T *p, const T (&e)[MapGroup<T>::G]) {
+    union { uint4 v[MapGroup<T>::TV]; T e[MapGroup<T>::G]; } u;
+#pragma unroll
+    for (int j = 0; j < MapGroup<T>::G; j++) u.e[j] = e[j];
+#pragma unroll
+    for (int q = 0; q < MapGroup<T>::TV; q++) st_stream16(reinterpret_cast<uint8_t *>(p) + 16 * q, u.v[q]);
+}
+
+// Row geometry shared by the three kernels: elements [0,head) and [tail0,w) are handled one per lane,
+// groups g in [0,ngroups) start at element head + g*G (16-byte aligned on the raster side).
+template <typename T>
+struct RowSplit {
+    uint32_t head, ngroups, tail0;
+    __device__ __forceinline__ RowSplit(const T *row, uint32_t w) {
+        constexpr uint32_t G = MapGroup<T>::G;
+        uint32_t h = (uint32_t)(((16u - (uint32_t)(reinterpret_cast<uintptr_t>(row) & 15u)) & 15u) / sizeof(T));
+        head = h < w ? h : w;
+        ngroups = (w - head) / G;
+        tail0 = head + ngroups * G;
+    }
+};
 
 // ---------------------------------------------------------------- min/max
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kMapThreads)
 k_minmax_tiles(const T *__restrict__ raster, uint32_t bands, uint32_t H, uint32_t W,
                const frb_tile *__restrict__ tiles, unsigned long long *keys) {
+    constexpr int G = MapGroup<T>::G;
     const frb_tile t = tiles[blockIdx.y];
     const uint32_t rows = bands * t.h;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     bool any = false;
-    double mn = 0.0, mx = 0.0;
-    for (uint32_t ry = blockIdx.x; ry < rows; ry += gridDim.x) {
+    T mn = T(0), mx = T(0);
+    auto take = [&](T v) {
+        if (is_fp<T>::value && v != v) return;
+        if (!any) { mn = mx = v; any = true; }
+        else { mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
+    };
+    for (uint32_t ry = blockIdx.x * kMapWarps + warp; ry < rows; ry += gridDim.x * kMapWarps) {
         const uint32_t c = ry / t.h, y = ry - c * t.h;
         const T *src = raster + ((size_t)c * H + (t.row_off + y)) * W + t.col_off;
-        for (uint32_t x = threadIdx.x; x < t.w; x += blockDim.x) {
-            const double v = (double)src[x];
-            if (v == v) {
-                if (!any) { mn = mx = v; any = true; }
-                else { mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
-            }
+        const RowSplit<T> rs(src, t.w);
+        if ((uint32_t)lane < rs.head) take(src[lane]);
+        if (rs.tail0 + lane < t.w) take(src[rs.tail0 + lane]);
+        const T *body = src + rs.head;
+        uint32_t g = lane;
+        for (; g + 96 < rs.ngroups; g += 128) {
+            T e0[G], e1[G], e2[G], e3[G];
+            load_group(body + (size_t)g * G, e0);
+            load_group(body + (size_t)(g + 32) * G, e1);
+            load_group(body + (size_t)(g + 64) * G, e2);
+            load_group(body + (size_t)(g + 96) * G, e3);
+#pragma unroll
+            for (int j = 0; j < G; j++) { take(e0[j]); take(e1[j]); take(e2[j]); take(e3[j]); }
+        }
+        for (; g < rs.ngroups; g += 32) {
+            T e0[G];
+            load_group(body + (size_t)g * G, e0);
+#pragma unroll
+            for (int j = 0; j < G; j++) take(e0[j]);
         }
     }
-    block_minmax_commit(any ? dkey(mn) : kKeyMinInit, any ? dkey(mx) : kKeyMaxInit, keys + 2 * (size_t)blockIdx.y);
+    block_minmax_commit(any ? dkey((double)mn) : kKeyMinInit, any ? dkey((double)mx) : kKeyMaxInit, keys + 2 * (size_t)blockIdx.y);
 }
 
 // ---------------------------------------------------------------- normalise
-template <typename T>
 __global__ void __launch_bounds__(256)
 k_build_norm_lut(const double *__restrict__ minmax, int bits, int32_t *__restrict__ lut) {
     const double mn = minmax[2 * blockIdx.y], mx = minmax[2 * blockIdx.y + 1];
@@ -77,11 +142,12 @@ k_build_norm_lut(const double *__restrict__ minmax, int bits, int32_t *__restric
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kMapThreads)
 k_normalize_tiles(const T *__restrict__ raster, uint32_t bands, uint32_t H, uint32_t W,
                   const frb_tile *__restrict__ tiles, const double *__restrict__ minmax, int bits,
                   int32_t *__restrict__ audio, const int64_t *__restrict__ audio_base,
                   const int32_t *__restrict__ lut_all) {
+    constexpr int G = MapGroup<T>::G, AV = MapGroup<T>::AV;
     const frb_tile t = tiles[blockIdx.y];
     const uint32_t n = t.h * t.w;
     const double mn = minmax[2 * blockIdx.y], mx = minmax[2 * blockIdx.y + 1];
@@ -89,64 +155,122 @@ k_normalize_tiles(const T *__restrict__ raster, uint32_t bands, uint32_t H, uint
     const double scale = scale_for_bits(bits);
     int32_t *dst = audio + audio_base[blockIdx.y];
     const uint32_t rows = bands * t.h;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool use_lut = is_small_int<T>::value && lut_all != nullptr && (mx - mn < (double)kNormLutCap);
     const int32_t *lut = lut_all ? lut_all + (size_t)blockIdx.y * kNormLutCap : nullptr;
     const int32_t vmin = use_lut ? (int32_t)mn : 0;
-    for (uint32_t ry = blockIdx.x; ry < rows; ry += gridDim.x) {
+    auto map = [&](T v) -> int32_t {
+        if (is_small_int<T>::value && use_lut) return __ldg(lut + ((int32_t)v - vmin));
+        return normalize_one((double)v, mn, range, scale);
+    };
+    for (uint32_t ry = blockIdx.x * kMapWarps + warp; ry < rows; ry += gridDim.x * kMapWarps) {
         const uint32_t c = ry / t.h, y = ry - c * t.h;
         const T *src = raster + ((size_t)c * H + (t.row_off + y)) * W + t.col_off;
         int32_t *out = dst + (size_t)c * n + (size_t)y * t.w;
-        if (use_lut) {
-            for (uint32_t x = threadIdx.x; x < t.w; x += blockDim.x) out[x] = __ldg(lut + ((int32_t)src[x] - vmin));
-        } else {
-            for (uint32_t x = threadIdx.x; x < t.w; x += blockDim.x) out[x] = normalize_one((double)src[x], mn, range, scale);
+        const RowSplit<T> rs(src, t.w);
+        if ((uint32_t)lane < rs.head) out[lane] = map(src[lane]);
+        if (rs.tail0 + lane < t.w) out[rs.tail0 + lane] = map(src[rs.tail0 + lane]);
+        const T *body = src + rs.head;
+        int32_t *obody = out + rs.head;
+        const bool ovec = (reinterpret_cast<uintptr_t>(obody) & 15u) == 0;
+        auto emit = [&](uint32_t g, const T (&e)[G]) {
+            int32_t r[G];
+#pragma unroll
+            for (int j = 0; j < G; j++) r[j] = map(e[j]);
+            int32_t *o = obody + (size_t)g * G;
+            if (ovec) {
+#pragma unroll
+                for (int q = 0; q < AV; q++)
+                    st_stream16(o + 4 * q, make_uint4((uint32_t)r[4 * q], (uint32_t)r[4 * q + 1], (uint32_t)r[4 * q + 2], (uint32_t)r[4 * q + 3]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < G; j++) o[j] = r[j];
+            }
+        };
+        uint32_t g = lane;
+        for (; g + 96 < rs.ngroups; g += 128) {
+            T e0[G], e1[G], e2[G], e3[G];
+            load_group(body + (size_t)g * G, e0);
+            load_group(body + (size_t)(g + 32) * G, e1);
+            load_group(body + (size_t)(g + 64) * G, e2);
+            load_group(body + (size_t)(g + 96) * G, e3);
+            emit(g, e0); emit(g + 32, e1); emit(g + 64, e2); emit(g + 96, e3);
+        }
+        for (; g < rs.ngroups; g += 32) {
+            T e0[G];
+            load_group(body + (size_t)g * G, e0);
+            emit(g, e0);
         }
     }
 }
 
 // ---------------------------------------------------------------- denormalise
-__global__ void __launch_bounds__(256)
-k_build_denorm_lut(double scale, double *__restrict__ lut) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < kDenormLutN) {
-        const double a = (double)((int32_t)j - 32768);
-        lut[j] = __ddiv_rn(__dadd_rn(__ddiv_rn(a, scale), 1.0), 2.0);      // (a/scale + 1)/2, same ops as denormalize_one
-    }
-}
-
 template <typename T> __device__ __forceinline__ T denorm_cast(double v) { return cast_round_out<T>(v); }
 template <> __device__ __forceinline__ float denorm_cast<float>(double v) { return __double2float_rn(v); }
 template <> __device__ __forceinline__ double denorm_cast<double>(double v) { return v; }
 
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kMapThreads)
 k_denormalize_tiles(const int32_t *__restrict__ audio, const int64_t *__restrict__ audio_base,
                     const frb_tile *__restrict__ tiles, const double *__restrict__ minmax, double scale,
-                    T *__restrict__ raster, uint32_t bands, uint32_t H, uint32_t W, const double *__restrict__ lut) {
+                    T *__restrict__ raster, uint32_t bands, uint32_t H, uint32_t W) {
+    constexpr int G = MapGroup<T>::G, AV = MapGroup<T>::AV;
     const frb_tile t = tiles[blockIdx.y];
     const uint32_t n = t.h * t.w;
     const double mn = minmax[2 * blockIdx.y], mx = minmax[2 * blockIdx.y + 1];
     const double range = __dsub_rn(mx, mn);                 // denormalize uses max-min unconditionally (:239)
     const int32_t *src = audio + audio_base[blockIdx.y];
     const uint32_t rows = bands * t.h;
-    for (uint32_t ry = blockIdx.x; ry < rows; ry += gridDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    auto map = [&](int32_t a) -> T { return denorm_cast<T>(denormalize_one((double)a, scale, mn, range)); };
+    for (uint32_t ry = blockIdx.x * kMapWarps + warp; ry < rows; ry += gridDim.x * kMapWarps) {
         const uint32_t c = ry / t.h, y = ry - c * t.h;
         T *out = raster + ((size_t)c * H + (t.row_off + y)) * W + t.col_off;
         const int32_t *in = src + (size_t)c * n + (size_t)y * t.w;
-        for (uint32_t x = threadIdx.x; x < t.w; x += blockDim.x) {
-            const int32_t a = in[x];
-            double v;
-            if (lut != nullptr && a >= -32768 && a <= 32767)
-                v = __dadd_rn(__dmul_rn(__ldg(lut + (a + 32768)), range), mn);
-            else
-                v = denormalize_one((double)a, scale, mn, range);
-            out[x] = denorm_cast<T>(v);
+        const RowSplit<T> rs(out, t.w);
+        if ((uint32_t)lane < rs.head) out[lane] = map(in[lane]);
+        if (rs.tail0 + lane < t.w) out[rs.tail0 + lane] = map(in[rs.tail0 + lane]);
+        T *obody = out + rs.head;
+        const int32_t *ibody = in + rs.head;
+        const bool ivec = (reinterpret_cast<uintptr_t>(ibody) & 15u) == 0;
+        auto fetch = [&](uint32_t g, int32_t (&a)[G]) {
+            const int32_t *p = ibody + (size_t)g * G;
+            if (ivec) {
+#pragma unroll
+                for (int q = 0; q < AV; q++) {
+                    const uint4 v = ld_stream16(p + 4 * q);
+                    a[4 * q] = (int32_t)v.x; a[4 * q + 1] = (int32_t)v.y; a[4 * q + 2] = (int32_t)v.z; a[4 * q + 3] = (int32_t)v.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < G; j++) a[j] = __ldcs(p + j);
+            }
+        };
+        auto emit = [&](uint32_t g, const int32_t (&a)[G]) {
+            T e[G];
+#pragma unroll
+            for (int j = 0; j < G; j++) e[j] = map(a[j]);
+            store_group(obody + (size_t)g * G, e);
+        };
+        uint32_t g = lane;
+        for (; g + 32 < rs.ngroups; g += 64) {
+            int32_t a0[G], a1[G];
+            fetch(g, a0); fetch(g + 32, a1);
+            emit(g, a0); emit(g + 32, a1);
+        }
+        for (; g < rs.ngroups; g += 32) {
+            int32_t a0[G];
+            fetch(g, a0);
+            emit(g, a0);
         }
     }
 }
 
-static inline dim3 tile_grid_dims(uint32_t n_tiles) {
-    uint32_t per_tile = (kNumSMs * 8 + n_tiles - 1) / n_tiles;
+static inline dim3 tile_grid_dims(uint32_t n_tiles, uint32_t max_rows) {
+    // ~16 CTAs per SM in total, but never more CTAs per tile than it has (band,row) groups of kMapWarps
+    uint32_t per_tile = (kNumSMs * 16 + n_tiles - 1) / n_tiles;
+    const uint32_t cap = (max_rows + kMapWarps - 1) / kMapWarps;
+    if (per_tile > cap) per_tile = cap;
     if (per_tile < 1) per_tile = 1;
     return dim3(per_tile, n_tiles);
 }
@@ -178,8 +302,8 @@ extern "C" int frb_minmax_tiles(const void *d_raster, int dtype, uint32_t bands,
     cudaStream_t s = (cudaStream_t)stream;
     k_minmax_init<<<(n_tiles + 255) / 256, 256, 0, s>>>((unsigned long long *)d_minmax, n_tiles);
     FRB_LAUNCH_CHECK("k_minmax_init");
-    const dim3 grid = tile_grid_dims(n_tiles);
-    FRB_DISPATCH_DTYPE(dtype, (k_minmax_tiles<T><<<grid, 256, 0, s>>>((const T *)d_raster, bands, H, W, d_tiles, (unsigned long long *)d_minmax)));
+    const dim3 grid = tile_grid_dims(n_tiles, bands * H);
+    FRB_DISPATCH_DTYPE(dtype, (k_minmax_tiles<T><<<grid, kMapThreads, 0, s>>>((const T *)d_raster, bands, H, W, d_tiles, (unsigned long long *)d_minmax)));
     FRB_LAUNCH_CHECK("k_minmax_tiles");
     k_minmax_finish<<<(n_tiles + 255) / 256, 256, 0, s>>>((unsigned long long *)d_minmax, n_tiles);
     FRB_LAUNCH_CHECK("k_minmax_finish");
@@ -198,13 +322,13 @@ extern "C" int frb_normalize_tiles(const void *d_raster, int dtype, uint32_t ban
     if (d_workspace && dtype <= FRB_I16) {
         MapWorkspace w;
         if (map_ws_layout(n_tiles, d_workspace, &w) > workspace_bytes) return FRB_ERR_OVERFLOW;
-        k_build_norm_lut<int><<<dim3(8, n_tiles), 256, 0, s>>>(d_minmax, bits_per_sample, w.norm_lut);
+        k_build_norm_lut<<<dim3(8, n_tiles), 256, 0, s>>>(d_minmax, bits_per_sample, w.norm_lut);
         FRB_LAUNCH_CHECK("k_build_norm_lut");
         lut = w.norm_lut;
     }
-    const dim3 grid = tile_grid_dims(n_tiles);
-    FRB_DISPATCH_DTYPE(dtype, (k_normalize_tiles<T><<<grid, 256, 0, s>>>((const T *)d_raster, bands, H, W, d_tiles, d_minmax,
-                                                                        bits_per_sample, d_audio, d_audio_base, lut)));
+    const dim3 grid = tile_grid_dims(n_tiles, bands * H);
+    FRB_DISPATCH_DTYPE(dtype, (k_normalize_tiles<T><<<grid, kMapThreads, 0, s>>>((const T *)d_raster, bands, H, W, d_tiles, d_minmax,
+                                                                                bits_per_sample, d_audio, d_audio_base, lut)));
     FRB_LAUNCH_CHECK("k_normalize_tiles");
     return FRB_OK;
 }
@@ -214,20 +338,13 @@ extern "C" int frb_denormalize_tiles(const int32_t *d_audio, const int64_t *d_au
                                      double scale, void *d_raster, int dtype, uint32_t bands, uint32_t H,
                                      uint32_t W, void *d_workspace, size_t workspace_bytes, void *stream) {
     using namespace frb;
+    (void)d_workspace; (void)workspace_bytes;       // the denormalise direction needs no tables
     if (!d_raster || !d_tiles || !d_minmax || !d_audio || !d_audio_base || dtype < 0 || dtype > FRB_F64 || !bands || !n_tiles)
         return FRB_ERR_INVALID_ARG;
     cudaStream_t s = (cudaStream_t)stream;
-    const double *lut = nullptr;
-    if (d_workspace && scale == 32767.0) {
-        MapWorkspace w;
-        if (map_ws_layout(n_tiles, d_workspace, &w) > workspace_bytes) return FRB_ERR_OVERFLOW;
-        k_build_denorm_lut<<<kDenormLutN / 256, 256, 0, s>>>(scale, w.denorm_lut);
-        FRB_LAUNCH_CHECK("k_build_denorm_lut");
-        lut = w.denorm_lut;
-    }
-    const dim3 grid = tile_grid_dims(n_tiles);
-    FRB_DISPATCH_DTYPE(dtype, (k_denormalize_tiles<T><<<grid, 256, 0, s>>>(d_audio, d_audio_base, d_tiles, d_minmax, scale,
-                                                                          (T *)d_raster, bands, H, W, lut)));
+    const dim3 grid = tile_grid_dims(n_tiles, bands * H);
+    FRB_DISPATCH_DTYPE(dtype, (k_denormalize_tiles<T><<<grid, kMapThreads, 0, s>>>(d_audio, d_audio_base, d_tiles, d_minmax, scale,
+                                                                                  (T *)d_raster, bands, H, W)));
     FRB_LAUNCH_CHECK("k_denormalize_tiles");
     return FRB_OK;
 }

@@ -121,7 +121,7 @@ class Engine:
         return audio, base, npx, d_minmax, bits_per_sample
 
     def encode_audio(self, audio: torch.Tensor, n_samples: np.ndarray, audio_base: np.ndarray, sample_rates: np.ndarray,
-                     channels: int, bps: int, level: int = 5, blocksize: int = 4096):
+                     channels: int, bps: int, level: int = 5, blocksize: int = 4096, payload_name: str = "payload"):
         """int32 planar audio on the device -> (payload uint8 tensor, offsets, sizes). One sync (sizes)."""
         n_streams = len(n_samples)
         p = nat.EncodeParams(n_streams, channels, bps, blocksize, level, 0)
@@ -140,12 +140,13 @@ class Engine:
             offsets = np.zeros(n_streams, dtype=np.uint64)
             np.cumsum(sizes[:-1], out=offsets[1:])
             total = int(sizes.sum())
-            payload = self._buf("payload", total + 16)
+            payload = self._buf(payload_name, total + 16)
             nat.check(self.L.frb_encode_emit(C.byref(p), ws.data_ptr(), ws.numel(), offsets.ctypes.data,
                                              payload.data_ptr(), payload.numel(), None, s), "frb_encode_emit")
         return payload[:total], offsets.astype(np.int64), sizes.astype(np.int64)
 
-    def encode_tiles(self, raster: torch.Tensor, tiles: np.ndarray, level: int = 5, blocksize: int = 4096) -> EncodedTiles:
+    def encode_tiles(self, raster: torch.Tensor, tiles: np.ndarray, level: int = 5, blocksize: int = 4096,
+                     payload_name: str = "payload") -> EncodedTiles:
         """Whole pipeline for a batch of tiles of one device-resident raster."""
         bands = raster.shape[0]
         if not (1 <= bands <= 8):
@@ -154,9 +155,115 @@ class Engine:
         bps = 16 if bits == 16 else 32            # pyflac derives bps from the array dtype (docs/sonos-pyflac.txt:1988-1991)
         rates = np.array([audio_params_for((int(t["h"]), int(t["w"])), str(raster.dtype).replace("torch.", ""))[0] for t in tiles],
                          dtype=np.uint32)
-        payload, offsets, sizes = self.encode_audio(audio, npx, base, rates, bands, bps, level, blocksize)
+        payload, offsets, sizes = self.encode_audio(audio, npx, base, rates, bands, bps, level, blocksize, payload_name)
         minmax = d_minmax.cpu().numpy().reshape(-1, 2)
         return EncodedTiles(payload, offsets, sizes, minmax, npx, rates, bands, bps, bits, blocksize)
+
+    # ------------------------------------------------------------------ encode, host buffers (pipelined)
+    @staticmethod
+    def _row_groups(tiles: np.ndarray) -> List[Tuple[int, int, int, int]]:
+        """Consecutive runs of tiles that share a row band: [(first, last+1, row0, row1)].  A row-major tile grid
+        (cli.py:553-556) gives one group per tile row; any other ordering still works (more, smaller groups)."""
+        groups = []
+        i, n = 0, len(tiles)
+        while i < n:
+            r0, r1 = int(tiles[i]["row_off"]), int(tiles[i]["row_off"]) + int(tiles[i]["h"])
+            j = i + 1
+            while j < n and int(tiles[j]["row_off"]) == r0 and int(tiles[j]["row_off"]) + int(tiles[j]["h"]) == r1:
+                j += 1
+            groups.append((i, j, r0, r1))
+            i = j
+        return groups
+
+    def _pinned(self, name: str, nbytes: int) -> torch.Tensor:
+        t = self._ws.get(name)
+        if t is None or t.numel() < nbytes:
+            self._ws.pop(name, None)
+            t = torch.empty(int(nbytes) + 4096, dtype=torch.uint8).pin_memory()
+            self._ws[name] = t
+        return t
+
+    def encode_tiles_host(self, host_raster: torch.Tensor, tiles: np.ndarray, level: int = 5, blocksize: int = 4096,
+                          host_out: Optional[torch.Tensor] = None) -> EncodedTiles:
+        """Host (bands,H,W) raster in, host frames out: the end-to-end form of encode_tiles.
+
+        The reference walks tiles serially (cli.py:553-622).  Here the tile rows are pipelined over three
+        streams so PCIe and the GPU work concurrently: H2D of tile row g+1 (double-buffered slab) overlaps
+        the encode of row g, which overlaps the D2H of row g-1's frames (double-buffered payload).
+        `host_raster` and `host_out` should be pinned; the returned EncodedTiles.payload is a CPU tensor
+        (a view of host_out)."""
+        assert not host_raster.is_cuda and host_raster.is_contiguous() and host_raster.dim() == 3
+        bands, H, W = host_raster.shape
+        esize = host_raster.element_size()
+        groups = self._row_groups(tiles)
+        max_rows = max(r1 - r0 for _, _, r0, r1 in groups)
+        if host_out is None:
+            frames = int(sum((int(t["h"]) * int(t["w"]) + blocksize - 1) // blocksize for t in tiles))
+            cap = int(host_raster.numel()) * (2 if esize <= 2 else 4) + frames * (32 + 8 * bands) + 4096
+            host_out = self._pinned("host_out", cap)
+        with torch.cuda.device(self.device):
+            if not hasattr(self, "_streams"):
+                self._streams = (torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream())
+            s_h2d, s_comp, s_d2h = self._streams
+            entry = torch.cuda.current_stream()
+            for st in self._streams:
+                st.wait_stream(entry)
+            slabs = [self._buf(f"slab{k}", bands * max_rows * W * esize) for k in range(2)]
+            ev_h2d: List[torch.cuda.Event] = []
+            ev_comp: List[torch.cuda.Event] = []
+            ev_d2h: List[torch.cuda.Event] = []
+
+            def slab_view(g):
+                _, _, r0, r1 = groups[g]
+                return slabs[g % 2][: bands * (r1 - r0) * W * esize].view(host_raster.dtype).reshape(bands, r1 - r0, W)
+
+            def enqueue_h2d(g):
+                _, _, r0, r1 = groups[g]
+                with torch.cuda.stream(s_h2d):
+                    if g >= 2:
+                        s_h2d.wait_event(ev_comp[g - 2])          # slab g%2 is free once row g-2 has been encoded
+                    dst = slab_view(g)
+                    for b in range(bands):                          # each band's rows are one contiguous block
+                        dst[b].copy_(host_raster[b, r0:r1], non_blocking=True)
+                    e = torch.cuda.Event()
+                    e.record(s_h2d)
+                    ev_h2d.append(e)
+
+            parts: List[EncodedTiles] = []
+            total = 0
+            enqueue_h2d(0)
+            for g, (i0, i1, r0, r1) in enumerate(groups):
+                if g + 1 < len(groups):
+                    enqueue_h2d(g + 1)
+                local = tiles[i0:i1].copy()
+                local["row_off"] -= r0
+                with torch.cuda.stream(s_comp):
+                    s_comp.wait_event(ev_h2d[g])
+                    if g >= 2:
+                        s_comp.wait_event(ev_d2h[g - 2])          # payload g%2 has left the device
+                    enc = self.encode_tiles(slab_view(g), local, level, blocksize, payload_name=f"payload{g % 2}")
+                    e = torch.cuda.Event()
+                    e.record(s_comp)
+                    ev_comp.append(e)
+                n = int(enc.payload.numel())
+                if total + n > host_out.numel():
+                    raise nat.NativeError(nat.ERR_OVERFLOW, "encode_tiles_host", "host_out too small")
+                with torch.cuda.stream(s_d2h):
+                    s_d2h.wait_event(ev_comp[g])
+                    host_out[total:total + n].copy_(enc.payload, non_blocking=True)
+                    e = torch.cuda.Event()
+                    e.record(s_d2h)
+                    ev_d2h.append(e)
+                enc.offsets = enc.offsets + total
+                parts.append(enc)
+                total += n
+            for st in self._streams:
+                entry.wait_stream(st)
+            s_d2h.synchronize()
+        p0 = parts[0]
+        return EncodedTiles(host_out[:total], np.concatenate([p.offsets for p in parts]), np.concatenate([p.sizes for p in parts]),
+                            np.concatenate([p.minmax for p in parts]), np.concatenate([p.n_samples for p in parts]),
+                            np.concatenate([p.sample_rates for p in parts]), p0.channels, p0.bps, p0.bits_per_sample, p0.blocksize)
 
     # ------------------------------------------------------------------ decode
     def decode_streams(self, data: torch.Tensor, byte_offsets: np.ndarray, byte_lengths: np.ndarray, n_samples: np.ndarray,

@@ -110,7 +110,10 @@ def build_streaming_container(raster_dev, transform, crs, nodata, dtype_name: st
     bands, H, W = raster_dev.shape
     if tiles is None:
         tiles = tile_grid(H, W, tile_size)
-    enc = eng.encode_tiles(raster_dev, tiles, compression_level)
+    if raster_dev.is_cuda:
+        enc = eng.encode_tiles(raster_dev, tiles, compression_level)
+    else:       # host raster: tile rows pipelined over copy / compute / copy streams (Engine.encode_tiles_host)
+        enc = eng.encode_tiles_host(raster_dev, tiles, compression_level)
     scale = 32767 if enc.bits_per_sample == 16 else 8388607
     headers, frames = [], []
     total = 0
@@ -193,9 +196,8 @@ class SpatialFLACEncoder:
         if arr.shape[0] > 8:
             raise ValueError("FLAC supports at most 8 channels (bands)")
         eng = default_engine()
-        dev = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).to(eng.device)
-        dev = dev.view(TORCH_DTYPES[str(arr.dtype)]).reshape(arr.shape)
-        index, headers, enc = build_streaming_container(dev, raster.transform, raster.crs, raster.nodata, str(arr.dtype),
+        host = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).view(TORCH_DTYPES[str(arr.dtype)]).reshape(arr.shape)
+        index, headers, enc = build_streaming_container(host, raster.transform, raster.crs, raster.nodata, str(arr.dtype),
                                                         self.tile_size, compression_level, engine=eng)
         payload = enc.payload.cpu().numpy()
         write_streaming_container(output_path, index, headers, payload, enc.offsets, enc.sizes)

@@ -382,3 +382,67 @@ def test_fullsize_c4_float32_level8_roundtrip(nat, torch_cuda):
     assert list(status[:3]) == [0, 0, 0]
     assert torch.equal(audio[:side * side * 4].view(torch.int32), ref)
     assert int(enc.sizes.sum()) < side * side * 4 * 0.75
+
+
+def test_host_pipeline_equals_device_path(nat, torch_cuda):
+    """encode_tiles_host (tile rows pipelined over copy/compute/copy streams, host buffers) produces exactly the
+    bytes, offsets and min/max of the one-shot device path, including ragged edge tiles."""
+    torch = torch_cuda
+    from flac_raster_b200.engine import default_engine, tile_grid
+    from flac_raster_b200.synth import sentinel2_like
+    raster = sentinel2_like(1500, 1300, 3)
+    eng = default_engine()
+    tiles = tile_grid(1500, 1300, 512)              # 3 x 3 tiles, last row/col ragged (476 / 276)
+    ref = eng.encode_tiles(raster, tiles, 5)
+    ref_bytes = ref.payload.cpu().numpy().copy()
+    host = raster.cpu().pin_memory()
+    for _ in range(2):                               # second pass reuses slabs/payload buffers
+        got = eng.encode_tiles_host(host, tiles, 5)
+        assert not got.payload.is_cuda
+        assert np.array_equal(got.sizes, ref.sizes) and np.array_equal(got.offsets, ref.offsets)
+        assert np.array_equal(got.minmax, ref.minmax)
+        assert np.array_equal(got.payload.numpy(), ref_bytes)
+
+
+@pytest.mark.parametrize("dt", ["uint8", "int16", "uint16", "float32", "float64", "int32"])
+def test_tile_mapping_odd_alignment_vs_oracle(nat, torch_cuda, dt):
+    """Per-tile min/max, normalise and denormalise on windows whose rows start at odd element offsets and
+    have widths that are not multiples of the 16-byte vector (head/tail lanes, scalar audio accesses)."""
+    torch = torch_cuda
+    from flac_raster_b200.engine import default_engine
+    from flac_raster_b200 import _native as natmod
+    from oracle import normalization_oracle as no
+    rng = np.random.default_rng(5)
+    bands, H, W = 2, 67, 211
+    if dt.startswith("float"):
+        x = (rng.standard_normal((bands, H, W)) * 1000).astype(dt)
+        x[0, 3, 5] = np.nan
+    else:
+        info = np.iinfo(dt)
+        x = rng.integers(max(info.min, -30000), min(info.max, 30000), size=(bands, H, W), endpoint=True).astype(dt)
+    tiles = np.zeros(4, dtype=natmod.TILE_DTYPE)
+    tiles[0] = (0, 0, 67, 211); tiles[1] = (1, 3, 5, 1); tiles[2] = (7, 13, 33, 37); tiles[3] = (2, 1, 60, 209)
+    eng = default_engine()
+    dev = torch.from_numpy(x.view(np.uint8).reshape(-1)).cuda().view(getattr(torch, dt)).reshape(bands, H, W)
+    audio, base, npx, d_mm, bits = eng.normalize_tiles(dev, tiles)
+    mm = d_mm.cpu().numpy().reshape(-1, 2)
+    a = audio[: int((npx * bands).sum()) * 4].view(torch.int32).cpu().numpy()
+    out = torch.zeros_like(dev)
+    scale = 32767.0 if bits == 16 else 8388607.0
+    for i, t in enumerate(tiles):
+        r, c, h, w = (int(t[k]) for k in ("row_off", "col_off", "h", "w"))
+        win = x[:, r:r + h, c:c + w]
+        assert mm[i, 0] == np.nanmin(win) and mm[i, 1] == np.nanmax(win)
+        want, prm = no.normalize_to_audio(win.reshape(bands, -1).T, bits)
+        got = a[base[i]: base[i] + bands * h * w].reshape(bands, h * w).T
+        assert np.array_equal(got, want.astype(np.int32)), (dt, i)
+    # denormalise tile by tile (tiles overlap) and compare with the reference semantics
+    for i, t in enumerate(tiles):
+        r, c, h, w = (int(t[k]) for k in ("row_off", "col_off", "h", "w"))
+        out.zero_()
+        eng.denormalize_tiles(audio, base[i:i + 1], tiles[i:i + 1], mm[i:i + 1], scale, out)
+        win = x[:, r:r + h, c:c + w]
+        an, prm = no.normalize_to_audio(win.reshape(bands, -1).T, bits)
+        want = no.denormalize_from_audio(an, prm["data_min"], prm["data_max"], dt, prm["scale_factor"]).T.reshape(bands, h, w)
+        got = out.cpu().numpy()[:, r:r + h, c:c + w]
+        assert np.array_equal(got, want, equal_nan=True), (dt, i)
