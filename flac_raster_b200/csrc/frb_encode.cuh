@@ -334,10 +334,10 @@ __global__ void __launch_bounds__(kEncThreads, 3)
 k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint32_t channels, uint32_t bps_stream,
                    uint32_t blocksize, uint32_t level, const int32_t *__restrict__ audio,
                    const float *__restrict__ window, uint32_t slot_words, uint32_t *__restrict__ slots,
-                   uint32_t *__restrict__ sub_bits) {
+                   uint32_t *__restrict__ sub_bits, const uint32_t *__restrict__ task_list) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EncShared &S = *reinterpret_cast<EncShared *>(smem_raw);
-    const uint32_t task = blockIdx.x;
+    const uint32_t task = task_list ? task_list[blockIdx.x] : blockIdx.x;
     const uint32_t f = task / channels, c = task - f * channels;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -753,6 +753,8 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
     if (tid == 0) sub_bits[task] = total_bits;
 }
 
+#include "frb_encode_fast.cuh"
+
 // ---- frame sizes / scans -------------------------------------------------------
 __device__ __forceinline__ uint32_t frame_header_bytes(uint32_t n, uint32_t sample_rate, uint64_t number) {
     int bh, sh;
@@ -988,6 +990,11 @@ struct EncWorkspace {
     unsigned long long *out_offs;
     uint32_t *err_flag;
     float *window;
+    EncSubStats *stats;
+    double *autoc;
+    EncCand *cands;
+    uint32_t *slow_tasks;
+    FrameDesc *frame_table;
     uint32_t *slots;
 };
 static inline size_t enc_ws_layout(const frb_encode_params *p, uint64_t total_frames, void *base, EncWorkspace *w) {
@@ -1005,6 +1012,11 @@ static inline size_t enc_ws_layout(const frb_encode_params *p, uint64_t total_fr
     FRB_TAKE(out_offs, unsigned long long, p->n_streams)
     FRB_TAKE(err_flag, uint32_t, 64)
     FRB_TAKE(window, float, FRB_MAX_BLOCKSIZE)
+    FRB_TAKE(stats, EncSubStats, subs)
+    FRB_TAKE(autoc, double, subs * kMaxSets * kLags)
+    FRB_TAKE(cands, EncCand, subs * kMaxCands)
+    FRB_TAKE(slow_tasks, uint32_t, subs)
+    FRB_TAKE(frame_table, FrameDesc, total_frames)
     FRB_TAKE(slots, uint32_t, subs * slot_words_for(p->blocksize, p->bps))
 #undef FRB_TAKE
     return off;
@@ -1071,11 +1083,66 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const int32_t *d_a
         FRB_CUDA(cudaFuncSetAttribute(k_encode_subframes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncShared)));
         attr_set = true;
     }
+    // Full, 16-byte aligned 4096-sample blocks go through the three-kernel fast path; everything else (the short
+    // last frame of a stream, channels that start at an unaligned sample) is listed for the one-kernel encoder.
+    const LevelCfg cfg = level_cfg(p->level);
+    const bool fast = p->blocksize == (uint32_t)kMaxBlock && cfg.max_po >= 3 && cfg.max_po <= 6;
+    std::vector<uint32_t> slow;
+    const uint32_t total_tasks = (uint32_t)(frames * p->channels);
+    if (fast) {
+        const uint64_t base_words = (uint64_t)(reinterpret_cast<uintptr_t>(d_audio) >> 2);
+        if (reinterpret_cast<uintptr_t>(d_audio) & 3u) return FRB_ERR_INVALID_ARG;
+        for (uint32_t i = 0; i < p->n_streams; i++) {
+            const EncStreamDev &d = hs[i];
+            const bool tail = (d.n_samples % p->blocksize) != 0;
+            for (uint32_t c = 0; c < p->channels; c++) {
+                const bool aligned = ((base_words + (uint64_t)d.audio_base + (uint64_t)c * d.n_samples) & 3u) == 0;
+                for (uint32_t k = aligned ? (tail ? d.n_frames - 1 : d.n_frames) : 0; k < d.n_frames; k++)
+                    slow.push_back((d.frame_base + k) * p->channels + c);
+            }
+        }
+        if (!slow.empty()) {
+            FRB_CUDA(cudaMemcpyAsync(w.slow_tasks, slow.data(), 4 * slow.size(), cudaMemcpyHostToDevice, s));
+            FRB_CUDA(cudaStreamSynchronize(s));
+        }
+    }
     prof_begin(0, s);
-    k_encode_subframes<<<(uint32_t)(frames * p->channels), kEncThreads, sizeof(EncShared), s>>>(
-        w.streams, p->n_streams, p->channels, p->bps, p->blocksize, p->level, d_audio, w.window, slot_words, w.slots, w.sub_bits);
+    if (fast && slow.size() < total_tasks) {
+        const uint32_t windows = (uint32_t)cfg.windows, max_lpc = (uint32_t)cfg.max_lpc_order;
+        const uint32_t n_cands = max_lpc == 0 ? 1u : windows == 1 ? 2u : windows == 2 ? 4u : 10u;
+        const bool wide = p->bps > 16;
+        const dim3 grid((uint32_t)frames, p->channels);
+        k_frame_table<<<(uint32_t)((frames + 255) / 256), 256, 0, s>>>(w.streams, p->n_streams, p->blocksize, (uint32_t)frames, w.frame_table);
+        FRB_LAUNCH_CHECK("k_frame_table");
+#define FRB_STATS(W, NL) k_enc_stats<W, NL><<<grid, kEncThreads, 0, s>>>(w.frame_table, p->channels, p->bps, windows, d_audio, \
+            w.window, w.stats, w.autoc)
+        if (max_lpc == 0) { if (wide) FRB_STATS(true, 0); else FRB_STATS(false, 0); }
+        else if (max_lpc <= 8) { if (wide) FRB_STATS(true, 9); else FRB_STATS(false, 9); }
+        else { if (wide) FRB_STATS(true, 13); else FRB_STATS(false, 13); }
+#undef FRB_STATS
+        FRB_LAUNCH_CHECK("k_enc_stats");
+        const uint32_t model_threads = total_tasks * n_cands;
+#define FRB_MODEL(MO) k_enc_model<MO><<<(model_threads + 127) / 128, 128, 0, s>>>(w.frame_table, p->channels, p->bps, \
+            p->blocksize, windows, max_lpc, n_cands, total_tasks, d_audio, w.stats, w.autoc, w.cands)
+        if (max_lpc == 0) FRB_MODEL(0); else if (max_lpc <= 8) FRB_MODEL(8); else FRB_MODEL(12);
+#undef FRB_MODEL
+        FRB_LAUNCH_CHECK("k_enc_model");
+        if (wide)
+            k_enc_code<true><<<grid, kEncThreads, 0, s>>>(w.frame_table, p->channels, p->bps, (uint32_t)cfg.max_po, n_cands, d_audio,
+                                                          w.stats, w.cands, slot_words, w.slots, w.sub_bits);
+        else
+            k_enc_code<false><<<grid, kEncThreads, 0, s>>>(w.frame_table, p->channels, p->bps, (uint32_t)cfg.max_po, n_cands, d_audio,
+                                                           w.stats, w.cands, slot_words, w.slots, w.sub_bits);
+        FRB_LAUNCH_CHECK("k_enc_code");
+    }
+    if (!fast || !slow.empty()) {
+        const uint32_t grid = fast ? (uint32_t)slow.size() : total_tasks;
+        k_encode_subframes<<<grid, kEncThreads, sizeof(EncShared), s>>>(
+            w.streams, p->n_streams, p->channels, p->bps, p->blocksize, p->level, d_audio, w.window, slot_words, w.slots, w.sub_bits,
+            fast ? w.slow_tasks : nullptr);
+        FRB_LAUNCH_CHECK("k_encode_subframes");
+    }
     prof_end(0, s);
-    FRB_LAUNCH_CHECK("k_encode_subframes");
     k_frame_sizes<<<(uint32_t)((frames + 255) / 256), 256, 0, s>>>(w.streams, p->n_streams, p->channels, p->blocksize,
                                                                  (uint32_t)frames, w.sub_bits, w.frame_bytes);
     FRB_LAUNCH_CHECK("k_frame_sizes");

@@ -1,0 +1,857 @@
+// frb_encode_fast.cuh -- three-kernel subframe encoder for full 4096-sample blocks (the common case:
+// every frame of a stream except its last one).  Included by frb_encode.cuh inside namespace frb.
+//
+// The one-kernel encoder (k_encode_subframes, kept for short tail frames and unaligned channels) executed
+// 16.6 warp instructions per sample at 48 % issue utilisation (profiles/r01_ncu_enc_v2_*): every phase went
+// through padded shared-memory sample/residual buffers with per-element bounds checks, all reductions were
+// 64-bit shuffles, and 255 of 256 threads idled at a barrier while lane 0 ran Levinson-Durbin, the order
+// estimate (logarithms) and the coefficient quantisation in fp64.  Here the work is split where the data
+// dependencies are:
+//   k_enc_stats   CTA per subframe, 16 samples per thread held in REGISTERS (+12 halo samples read
+//                 straight from global/L1): wasted bits, constant check, fixed-predictor abs sums
+//                 (32-bit, REDUX warp sums), windowed autocorrelation for every apodization of the
+//                 level (fp64 FMA chain in registers) -> ~200 bytes of statistics per subframe
+//   k_enc_model   ONE THREAD per (subframe, apodization): Levinson-Durbin, libFLAC's order estimate
+//                 and coefficient quantisation -- the serial fp64 section now runs 32 subframes per
+//                 warp instead of one lane per CTA -> candidate predictors (64 bytes each)
+//   k_enc_code    CTA per subframe: residual of each candidate in registers, partition sums by a
+//                 segmented warp butterfly, libFLAC's Rice estimate, winner selection, exact bit
+//                 lengths, CTA scan, 64-bit per-thread bit accumulator with plain interior word stores,
+//                 128-bit slot copy
+// All decisions are the same as the one-kernel encoder's (and the oracle's): same estimates, same
+// tie-breaks, same fp64 operation order in the model; the autocorrelation uses the same per-thread /
+// butterfly / cross-warp summation tree as before.
+#pragma once
+
+constexpr int kMaxSets = 6;        // autocorrelation sets per subframe: root, 2 halves, 3 thirds (level 8)
+constexpr int kMaxCands = 10;      // fixed + up to 9 LPC candidates (level 8: 1 + 2 + 6)
+constexpr int kLags = kMaxOrd + 1;
+
+struct EncSubStats {
+    unsigned long long e[5];       // fixed-predictor abs sums over i in [4, n)
+    uint32_t wasted, flags;        // flags bit 0: constant signal
+};
+struct EncCand {                   // type 0 = no candidate, 2 FIXED, 3 LPC
+    int32_t type, order, precision, shift;
+    int32_t coefs[kMaxOrd];
+};
+
+// Per-frame descriptor table (k_frame_table, one binary search per FRAME): the three kernels index it
+// directly instead of searching the stream table once per CTA (7 dependent loads before any work).
+struct FrameDesc {
+    int64_t src0;          // audio index of channel 0's first sample of this frame
+    uint64_t ns;           // samples per channel of the stream (channel stride)
+    uint32_t n, stream;    // samples in this frame, stream index
+};
+__global__ void __launch_bounds__(256)
+k_frame_table(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint32_t blocksize, uint32_t total_frames,
+              FrameDesc *__restrict__ out) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= total_frames) return;
+    uint32_t lo = 0, hi = n_streams - 1;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (streams[mid].frame_base <= f) lo = mid; else hi = mid - 1;
+    }
+    const EncStreamDev st = streams[lo];
+    const uint32_t kf = f - st.frame_base;
+    FrameDesc d;
+    d.src0 = st.audio_base + (int64_t)kf * blocksize;
+    d.ns = st.n_samples;
+    d.n = (kf + 1 < st.n_frames) ? blocksize : (uint32_t)(st.n_samples - (uint64_t)kf * blocksize);
+    d.stream = lo;
+    out[f] = d;
+}
+
+struct TaskLoc {
+    uint32_t n;
+    const int32_t *src;
+};
+__device__ __forceinline__ TaskLoc locate_task(const FrameDesc *__restrict__ frames, const int32_t *__restrict__ audio,
+                                               uint32_t f, uint32_t c) {
+    const FrameDesc d = frames[f];
+    TaskLoc L;
+    L.n = d.n;
+    L.src = audio + d.src0 + (int64_t)c * (int64_t)d.ns;
+    return L;
+}
+// The fast path handles full 4096-sample blocks whose first sample is 16-byte aligned (the host lists every
+// other subframe for the one-kernel encoder with the same predicate, see frb_encode_analyse).
+__device__ __forceinline__ bool fast_eligible(const TaskLoc &L) {
+    return L.n == (uint32_t)kMaxBlock && (reinterpret_cast<uintptr_t>(L.src) & 15u) == 0;
+}
+
+// 16 own samples at xs[12..27], 12 halo samples (previous thread's tail, zeros for thread 0) at xs[0..11]
+__device__ __forceinline__ void load_samples28(const int32_t *__restrict__ src, int tid, int32_t (&xs)[28]) {
+    const int4 *p = reinterpret_cast<const int4 *>(src + tid * kSPT);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int4 v = __ldg(p + q);
+        xs[12 + 4 * q] = v.x; xs[13 + 4 * q] = v.y; xs[14 + 4 * q] = v.z; xs[15 + 4 * q] = v.w;
+    }
+    if (tid > 0) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const int4 v = __ldg(p - 3 + q);
+            xs[4 * q] = v.x; xs[4 * q + 1] = v.y; xs[4 * q + 2] = v.z; xs[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 12; q++) xs[q] = 0;
+    }
+}
+
+// Sum N doubles per lane over the warp with the SAME pairing tree as a plain xor butterfly (16, 8, 4, 2, 1),
+// but lanes split the values between them while there is more than one left: 8 values cost 9 double
+// shuffles instead of 40.  On return lane L holds in v[0] the warp total of value index
+// ((L>>4)&1)*4 + ((L>>3)&1)*2 + ((L>>2)&1) (for N == 8; N == 4 uses bits 4,3; N == 1 is the plain butterfly).
+__device__ __forceinline__ double shfl_xor_f64(double v, int o) { return __shfl_xor_sync(0xFFFFFFFFu, v, o); }
+template <int N>
+__device__ __forceinline__ void warp_sum_split(double (&v)[N], int lane) {
+    static_assert(N == 8 || N == 4 || N == 1, "power of two up to 8");
+    int o = 16;
+    if (N >= 8) {
+        const bool up = lane & o;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const double send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i]; v[i] = keep + shfl_xor_f64(send, o); }
+        o >>= 1;
+    }
+    if (N >= 4) {
+        const bool up = lane & o;
+#pragma unroll
+        for (int i = 0; i < 2; i++) { const double send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i]; v[i] = keep + shfl_xor_f64(send, o); }
+        o >>= 1;
+        const bool up2 = lane & o;
+        { const double send = up2 ? v[0] : v[1], keep = up2 ? v[1] : v[0]; v[0] = keep + shfl_xor_f64(send, o); }
+        o >>= 1;
+    }
+    for (; o > 0; o >>= 1) v[0] += shfl_xor_f64(v[0], o);
+}
+
+// ------------------------------------------------------------------------------------------------ stats
+struct StatsShared {
+    uint32_t orv[8], diff[8];
+    unsigned long long e[8][5];
+    double ac[8][kLags];
+};
+
+template <bool WIDE, int NLAGS>
+__global__ void __launch_bounds__(kEncThreads, (NLAGS > 9 || WIDE) ? 2 : 3)
+k_enc_stats(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps_stream,
+            uint32_t windows, const int32_t *__restrict__ audio,
+            const float *__restrict__ window, EncSubStats *__restrict__ stats, double *__restrict__ autoc_out) {
+    __shared__ StatsShared S;
+    const uint32_t task = blockIdx.x * channels + blockIdx.y;
+    const TaskLoc L = locate_task(frames, audio, blockIdx.x, blockIdx.y);
+    if (!fast_eligible(L)) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr uint32_t n = kMaxBlock;
+    constexpr int HALO = NLAGS > 0 ? NLAGS - 1 : 0;         // 8 or 12: multiples of 4, so the window reads stay 16-byte aligned
+    int32_t xs[28];
+    load_samples28(L.src, tid, xs);
+    // full-length window for this thread's samples and halo, fetched together with the samples
+    float wv[kSPT + HALO + 1];
+    if (NLAGS > 0) {
+        const float4 *wp = reinterpret_cast<const float4 *>(window + tid * kSPT) - HALO / 4;
+#pragma unroll
+        for (int q = 0; q < (kSPT + HALO) / 4; q++) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tid > 0 || q >= HALO / 4) v = __ldg(wp + q);
+            wv[4 * q] = v.x; wv[4 * q + 1] = v.y; wv[4 * q + 2] = v.z; wv[4 * q + 3] = v.w;
+        }
+    }
+    // ---- wasted bits / constant ----
+    uint32_t orv = 0, diff = 0;
+    const int32_t x_first = __ldg(L.src);
+#pragma unroll
+    for (int s = 0; s < kSPT; s++) { orv |= (uint32_t)xs[12 + s]; diff |= (uint32_t)(xs[12 + s] ^ x_first); }
+    orv = __reduce_or_sync(0xFFFFFFFFu, orv);
+    diff = __reduce_or_sync(0xFFFFFFFFu, diff);
+    if (lane == 0) { S.orv[warp] = orv; S.diff[warp] = diff; }
+    __syncthreads();
+    orv = 0; diff = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { orv |= S.orv[w]; diff |= S.diff[w]; }
+    uint32_t wasted = orv ? (uint32_t)(__ffs((int)orv) - 1) : 0;
+    if (wasted > bps_stream) wasted = bps_stream;
+    if (wasted) {
+#pragma unroll
+        for (int j = 0; j < 28; j++) xs[j] >>= wasted;
+    }
+    // ---- fixed predictor abs-error sums over i in [4, n) ----
+    unsigned long long e[5];
+    if (!WIDE) {
+        // successive differences in 32 bits: |4th difference| <= 16 * 2^15, 16 samples per thread, 32 per warp
+        uint32_t e32[5] = {0, 0, 0, 0, 0};
+        int32_t d1[kSPT + 3], d2[kSPT + 2], d3[kSPT + 1], d4[kSPT];
+#pragma unroll
+        for (int j = 0; j < kSPT + 3; j++) d1[j] = xs[9 + j] - xs[8 + j];
+#pragma unroll
+        for (int j = 0; j < kSPT + 2; j++) d2[j] = d1[j + 1] - d1[j];
+#pragma unroll
+        for (int j = 0; j < kSPT + 1; j++) d3[j] = d2[j + 1] - d2[j];
+#pragma unroll
+        for (int j = 0; j < kSPT; j++) d4[j] = d3[j + 1] - d3[j];
+#pragma unroll
+        for (int s = 0; s < kSPT; s++) {
+            if (s >= 4 || tid > 0) {
+                e32[0] += (uint32_t)abs(xs[12 + s]); e32[1] += (uint32_t)abs(d1[s + 3]); e32[2] += (uint32_t)abs(d2[s + 2]);
+                e32[3] += (uint32_t)abs(d3[s + 1]); e32[4] += (uint32_t)abs(d4[s]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 5; q++) e[q] = __reduce_add_sync(0xFFFFFFFFu, e32[q]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 5; q++) e[q] = 0;
+#pragma unroll
+        for (int s = 0; s < kSPT; s++) {
+            if (s >= 4 || tid > 0) {
+                const long long a = xs[12 + s], b = xs[11 + s], cc = xs[10 + s], d = xs[9 + s], ee = xs[8 + s];
+                const long long r0 = a, r1 = a - b, r2 = a - 2 * b + cc, r3 = a - 3 * b + 3 * cc - d, r4 = a - 4 * b + 6 * cc - 4 * d + ee;
+                e[0] += (unsigned long long)(r0 < 0 ? -r0 : r0);
+                e[1] += (unsigned long long)(r1 < 0 ? -r1 : r1);
+                e[2] += (unsigned long long)(r2 < 0 ? -r2 : r2);
+                e[3] += (unsigned long long)(r3 < 0 ? -r3 : r3);
+                e[4] += (unsigned long long)(r4 < 0 ? -r4 : r4);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 5; q++)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) e[q] += __shfl_xor_sync(0xFFFFFFFFu, e[q], o);
+    }
+    if (lane == 0)
+#pragma unroll
+        for (int q = 0; q < 5; q++) S.e[warp][q] = e[q];
+    __syncthreads();
+    if (tid < 5) {
+        unsigned long long s = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) s += S.e[w][tid];
+        stats[task].e[tid] = s;
+    }
+    if (tid == 5) { stats[task].wasted = wasted; stats[task].flags = diff == 0 ? 1u : 0u; }
+    if (NLAGS == 0 || diff == 0) return;
+    // ---- windowed autocorrelation, one set per apodization (root, halves, thirds) ----
+    const uint32_t i0 = tid * kSPT;
+    int set = 0;
+    for (uint32_t b = 1; b <= windows; b++) {
+        const uint32_t nsub = (b == 1) ? 1u : b;
+        for (uint32_t sub = 0; sub < nsub; sub++, set++) {
+            uint32_t wshift = 0, wlen = n, part = 0;
+            if (b > 1) { part = n / b / 2; wshift = (sub * n) / b; wlen = n / b; }
+            double ac[NLAGS > 0 ? NLAGS : 1];
+#pragma unroll
+            for (int l = 0; l < NLAGS; l++) ac[l] = 0.0;
+            // threads whose 16 samples lie outside the window contribute nothing
+            if (i0 + kSPT > wshift && i0 < wshift + wlen) {
+                float df[kSPT + HALO];                   // windowed samples (libFLAC windows in single precision)
+                if (b == 1) {
+                    // full window: thread 0's halo samples are zero, so no range checks are needed
+#pragma unroll
+                    for (int j = 0; j < kSPT + HALO; j++) df[j] = __fmul_rn((float)xs[12 - HALO + j], wv[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kSPT + HALO; j++) {
+                        const int idx = (int)i0 - HALO + j;
+                        float v = 0.0f;
+                        if (idx >= (int)wshift && (uint32_t)idx < wshift + wlen) {
+                            const uint32_t local = (uint32_t)idx - wshift;
+                            float w1;
+                            if (local < part) w1 = __ldg(window + local);
+                            else if (local < 2 * part) w1 = __ldg(window + (n - 2 * part + local));
+                            else w1 = 0.0f;
+                            v = __fmul_rn((float)xs[12 - HALO + j], w1);
+                        }
+                        df[j] = v;
+                    }
+                }
+                // sliding window of the last NLAGS samples in double: one conversion per sample, few live registers
+                double win[NLAGS > 0 ? NLAGS : 1];
+#pragma unroll
+                for (int l = 1; l < NLAGS; l++) win[l] = (double)df[HALO - l];
+#pragma unroll
+                for (int s = 0; s < kSPT; s++) {
+                    if (s > 0) {
+#pragma unroll
+                        for (int l = NLAGS - 1; l >= 1; l--) win[l] = win[l - 1];
+                    }
+                    win[0] = (double)df[HALO + s];
+#pragma unroll
+                    for (int l = 0; l < NLAGS; l++) ac[l] = fma(win[0], win[l], ac[l]);
+                }
+            }
+            // warp sums (same pairing tree as an xor butterfly per lag), lags 0-7 split over the lanes
+            {
+                double g8[8];
+#pragma unroll
+                for (int l = 0; l < 8; l++) g8[l] = ac[l];
+                warp_sum_split<8>(g8, lane);
+                double g1[1] = {ac[8]};
+                warp_sum_split<1>(g1, lane);
+                __syncthreads();                          // previous set's S.ac has been consumed
+                if ((lane & 3) == 0) S.ac[warp][((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = g8[0];
+                if (lane == 0) S.ac[warp][8] = g1[0];
+                if (NLAGS > 9) {
+                    double g4[4];
+#pragma unroll
+                    for (int l = 0; l < 4; l++) g4[l] = ac[(NLAGS > 9 ? 9 : 0) + l];
+                    warp_sum_split<4>(g4, lane);
+                    if ((lane & 7) == 0) S.ac[warp][9 + ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)] = g4[0];
+                }
+            }
+            __syncthreads();
+            if (tid < NLAGS) {
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; w++) s += S.ac[w][tid];
+                autoc_out[((size_t)task * kMaxSets + set) * kLags + tid] = s;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ model
+// Levinson-Durbin with fully static indexing (registers): runs the recursion up to `upto` orders and
+// returns the number of orders actually computed (stops early when the error reaches zero).
+template <int MAXO>
+__device__ __forceinline__ uint32_t levinson_static(const double (&autoc)[MAXO + 1], uint32_t upto, double (&lpc)[MAXO],
+                                                    double (&lp_err)[MAXO]) {
+    double err = autoc[0];
+    uint32_t mo = upto;
+    bool done = false;
+#pragma unroll
+    for (int i = 0; i < MAXO; i++) {
+        if (!done && (uint32_t)i < upto) {
+            double r = -autoc[i + 1];
+#pragma unroll
+            for (int j = 0; j < i; j++) r = __dsub_rn(r, __dmul_rn(lpc[j], autoc[i - j]));
+            r = __ddiv_rn(r, err);
+            lpc[i] = r;
+#pragma unroll
+            for (int j = 0; j < (i >> 1); j++) {
+                const double tmp = lpc[j];
+                lpc[j] = __dadd_rn(lpc[j], __dmul_rn(r, lpc[i - 1 - j]));
+                lpc[i - 1 - j] = __dadd_rn(lpc[i - 1 - j], __dmul_rn(r, tmp));
+            }
+            if (i & 1) lpc[i >> 1] = __dadd_rn(lpc[i >> 1], __dmul_rn(lpc[i >> 1], r));
+            err = __dmul_rn(err, __dsub_rn(1.0, __dmul_rn(r, r)));
+            lp_err[i] = err;
+            if (err == 0.0) { mo = i + 1; done = true; }
+        }
+    }
+    return mo;
+}
+
+template <int MAXO>
+__device__ __forceinline__ void model_one(const double (&autoc)[MAXO + 1], uint32_t max_lpc, uint32_t n, uint32_t bps,
+                                          uint32_t qprec_cfg, EncCand &C) {
+    C.type = 0;
+    if (autoc[0] == 0.0) return;
+    double lpc[MAXO], lp_err[MAXO];
+#pragma unroll
+    for (int j = 0; j < MAXO; j++) { lpc[j] = 0.0; lp_err[j] = 0.0; }
+    const uint32_t mo = levinson_static<MAXO>(autoc, max_lpc, lpc, lp_err);
+    // FLAC__lpc_compute_best_order and the "don't even try" estimate
+    uint32_t best_i = 0;
+    double best_b = 4294967295.0, best_eb2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < MAXO; i++) {
+        if ((uint32_t)i < mo) {
+            const double le = lp_err[i];
+            const uint32_t ord = (uint32_t)i + 1;
+            const double scale = 0.5 / (double)n, scale2 = 0.5 / (double)(n - ord);
+            double eb, eb2;
+            if (le > 0.0) {
+                eb = 0.5 * log(scale * le) / 0.69314718055994530942; if (eb < 0.0) eb = 0.0;
+                eb2 = 0.5 * log(scale2 * le) / 0.69314718055994530942; if (eb2 < 0.0) eb2 = 0.0;
+            } else if (le < 0.0) { eb = 1e32; eb2 = 1e32; } else { eb = 0.0; eb2 = 0.0; }
+            const double bits = eb * (double)(n - ord) + (double)(ord * (bps + qprec_cfg));
+            if (bits < best_b) { best_b = bits; best_i = (uint32_t)i; best_eb2 = eb2; }
+        }
+    }
+    if (mo == 0) return;
+    const uint32_t order = best_i + 1;
+    if (best_eb2 >= (double)bps) return;
+    uint32_t prec = qprec_cfg;
+    if (bps <= 17) { const uint32_t lim = 32 - bps - (uint32_t)ilog2_u32(order); if (lim < prec) prec = lim; }
+    // coefficients of the chosen order: rerun the (deterministic) recursion up to it
+#pragma unroll
+    for (int j = 0; j < MAXO; j++) lpc[j] = 0.0;
+    (void)levinson_static<MAXO>(autoc, order, lpc, lp_err);
+    float lpv[MAXO];
+#pragma unroll
+    for (int j = 0; j < MAXO; j++) lpv[j] = (float)(-lpc[j]);
+    // FLAC__lpc_quantize_coefficients
+    const int p1 = (int)prec - 1;
+    const int qmax = (1 << p1) - 1, qmin = -(1 << p1);
+    double cmax = 0.0;
+#pragma unroll
+    for (int i = 0; i < MAXO; i++) if ((uint32_t)i < order) { const double d = fabs((double)lpv[i]); if (d > cmax) cmax = d; }
+    if (!(cmax > 0.0)) return;
+    int log2cmax; (void)frexp(cmax, &log2cmax); log2cmax--;
+    int sh = p1 - log2cmax - 1;
+    if (sh > 15) sh = 15; else if (sh < -16) return;
+#pragma unroll
+    for (int j = 0; j < kMaxOrd; j++) C.coefs[j] = 0;
+    double er = 0.0;
+    if (sh >= 0) {
+#pragma unroll
+        for (int i = 0; i < MAXO; i++) if ((uint32_t)i < order) {
+            er = __dadd_rn(er, __dmul_rn((double)lpv[i], (double)(1 << sh)));
+            long long q = llround(er);
+            if (q > qmax) q = qmax; else if (q < qmin) q = qmin;
+            er = __dsub_rn(er, (double)q); C.coefs[i] = (int32_t)q;
+        }
+    } else {
+        const int ns = -sh;
+#pragma unroll
+        for (int i = 0; i < MAXO; i++) if ((uint32_t)i < order) {
+            er = __dadd_rn(er, __ddiv_rn((double)lpv[i], (double)(1 << ns)));
+            long long q = llround(er);
+            if (q > qmax) q = qmax; else if (q < qmin) q = qmin;
+            er = __dsub_rn(er, (double)q); C.coefs[i] = (int32_t)q;
+        }
+        sh = 0;
+    }
+    C.type = 3; C.order = (int)order; C.precision = (int)prec; C.shift = sh;
+}
+
+// thread per (subframe, candidate slot): slot 0 = FIXED guess, slots 1.. = LPC candidates in libFLAC's
+// evaluation order (b = 1: full window; b = 2: halves; b = 3: third, punch-out, third, punch-out, ...)
+template <int MAXO>
+__global__ void __launch_bounds__(128)
+k_enc_model(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps_stream,
+            uint32_t blocksize, uint32_t windows, uint32_t max_lpc_cfg, uint32_t n_cands, uint32_t total_tasks,
+            const int32_t *__restrict__ audio, const EncSubStats *__restrict__ stats, const double *__restrict__ autoc_in,
+            EncCand *__restrict__ cands) {
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t task = gid / n_cands, slot = gid - task * n_cands;
+    if (task >= total_tasks) return;
+    const uint32_t f = task / channels;
+    const TaskLoc L = locate_task(frames, audio, f, task - f * channels);
+    if (!fast_eligible(L)) return;
+    constexpr uint32_t n = kMaxBlock;
+    EncCand C;
+    C.type = 0; C.order = 0; C.precision = 0; C.shift = 0;
+#pragma unroll
+    for (int j = 0; j < kMaxOrd; j++) C.coefs[j] = 0;
+    const EncSubStats st = stats[task];
+    const uint32_t bps = bps_stream - st.wasted;
+    if (!(st.flags & 1u)) {
+        if (slot == 0) {
+            const unsigned long long *e = st.e;
+            uint32_t guess;
+            const unsigned long long m1234 = min(min(e[1], e[2]), min(e[3], e[4]));
+            const unsigned long long m234 = min(e[2], min(e[3], e[4]));
+            const unsigned long long m34 = min(e[3], e[4]);
+            if (e[0] <= m1234) guess = 0; else if (e[1] <= m234) guess = 1; else if (e[2] <= m34) guess = 2; else if (e[3] <= e[4]) guess = 3; else guess = 4;
+            const float fbits_guess = (float)(e[guess] > 0 ? log(0.69314718055994530942 * (double)e[guess] / (double)(n - 4)) / 0.69314718055994530942 : 0.0);
+            if (!(fbits_guess >= (float)bps)) {
+                C.type = 2; C.order = (int)guess;
+                if (guess == 1) { C.coefs[0] = 1; }
+                else if (guess == 2) { C.coefs[0] = 2; C.coefs[1] = -1; }
+                else if (guess == 3) { C.coefs[0] = 3; C.coefs[1] = -3; C.coefs[2] = 1; }
+                else if (guess == 4) { C.coefs[0] = 4; C.coefs[1] = -6; C.coefs[2] = 4; C.coefs[3] = -1; }
+            }
+        } else if constexpr (MAXO > 0) {
+            // map the slot to (set, punch-out?)
+            uint32_t lpc_i = slot - 1, set = 0;
+            bool punch = false;
+            if (lpc_i == 0) set = 0;
+            else if (lpc_i <= 2) set = lpc_i;                       // halves: sets 1, 2
+            else { const uint32_t ci = lpc_i - 3; set = 3 + ci / 2; punch = (ci & 1u) != 0; }   // thirds: sets 3, 4, 5
+            const double *a = autoc_in + ((size_t)task * kMaxSets + set) * kLags;
+            double autoc[MAXO + 1];
+#pragma unroll
+            for (int l = 0; l <= MAXO; l++) autoc[l] = a[l];
+            uint32_t max_lpc = max_lpc_cfg;
+            if (punch) {
+                const double *root = autoc_in + (size_t)task * kMaxSets * kLags;
+                // libFLAC subtracts lags [0, max_lpc_order) only; the last lag keeps the partial window's value
+#pragma unroll
+                for (int l = 0; l < MAXO; l++) if ((uint32_t)l < max_lpc) autoc[l] = root[l] - autoc[l];
+            }
+            model_one<MAXO>(autoc, max_lpc, n, bps, qlp_precision_for(bps_stream, blocksize), C);
+        }
+    }
+    cands[(size_t)task * kMaxCands + slot] = C;
+}
+
+// ------------------------------------------------------------------------------------------------ code
+template <bool WIDE>
+struct CodeShared {
+    uint32_t bitbuf[WIDE ? 4100 : 2052];
+    unsigned long long wsum[2][8];              // warp totals of |residual|, double-buffered by candidate parity
+    unsigned long long wbits[2][8][4];          // per warp, per in-warp level: estimated bits
+    uint8_t best_params[64];
+    uint32_t scan[kEncThreads / 32];
+};
+
+// v < 2^len, 1 <= len <= 32: OR the bits into a zeroed MSB-first word buffer at bit position pos
+__device__ __forceinline__ void put_bits_atomic(uint32_t *buf, uint32_t pos, uint32_t v, uint32_t len) {
+    const uint32_t o = pos & 31u;
+    const unsigned long long x = (unsigned long long)v << (64u - o - len);
+    const uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x;
+    if (hi) atomicOr(&buf[pos >> 5], hi);
+    if (lo) atomicOr(&buf[(pos >> 5) + 1], lo);
+}
+
+// Per-thread bit accumulator over the zeroed shared word buffer (MSB first): 64-bit window, completed words
+// are OR-ed in (a thread's first and last word can be shared with its neighbours).
+struct PackWriter {
+    uint32_t *buf;
+    uint32_t widx, fill;
+    unsigned long long acc;
+    __device__ __forceinline__ void init(uint32_t *b, uint32_t bitpos) { buf = b; widx = bitpos >> 5; fill = bitpos & 31u; acc = 0; }
+    __device__ __forceinline__ void flush_hi() {
+        atomicOr(&buf[widx], (uint32_t)(acc >> 32));
+        widx++; acc <<= 32; fill -= 32;
+    }
+    __device__ __forceinline__ void put(uint32_t v, uint32_t len) {        // 1 <= len <= 32, v < 2^len
+        acc |= (unsigned long long)v << (64u - fill - len);
+        fill += len;
+        if (fill >= 32) flush_hi();
+    }
+    __device__ __forceinline__ void zeros(uint32_t q) {
+        fill += q;
+        while (fill >= 32) flush_hi();
+    }
+    __device__ __forceinline__ void finish() {
+        const uint32_t w = (uint32_t)(acc >> 32);
+        if (w) atomicOr(&buf[widx], w);
+    }
+};
+
+// libFLAC's Rice parameter estimate and bit estimate for one partition (set_partitioned_rice_ with the
+// 18-bit fixed-point mean): np samples, abs sum `sum`.
+__device__ __forceinline__ void rice_estimate(unsigned long long sum, uint32_t np, uint32_t k_limit, uint32_t *k_out, uint32_t *bits_out) {
+    const uint32_t div = 0x40000u / np;
+    const unsigned long long t = sum < 2 ? 0ull : (((sum - 1) * div) >> 18);
+    uint32_t k = t == 0 ? 0u : (uint32_t)ilog2_u64(t) + 1u;
+    if (k >= k_limit) k = k_limit - 1;
+    *k_out = k;
+    *bits_out = rice_bits_estimate(k, np, sum);
+}
+
+// Residual of this thread's 16 samples.  Returns the OR of |r| (>= 2^30 means an exact overflow check is needed).
+template <bool WIDE, int TAPS>
+__device__ __forceinline__ uint32_t residual16(const int32_t (&xs)[28], const int32_t (&cf)[kMaxOrd], int shift, int32_t (&r)[kSPT],
+                                               uint32_t *hi_mismatch) {
+    uint32_t ora = 0, bad = 0;
+#pragma unroll
+    for (int s = 0; s < kSPT; s++) {
+        if (WIDE) {
+            long long acc = 0;
+#pragma unroll
+            for (int j = 0; j < TAPS; j++) acc += (long long)cf[j] * (long long)xs[12 + s - 1 - j];
+            const long long v = (long long)xs[12 + s] - (acc >> shift);
+            r[s] = (int32_t)v;
+            bad |= (uint32_t)((int32_t)(v >> 32) ^ (r[s] >> 31));        // non-zero iff v is not the sign extension of r
+        } else {
+            // <= 16-bit samples, precision <= 32 - bps - ilog2(order): every partial sum fits int32 (libFLAC's rule);
+            // the subtraction may wrap only if |prediction| >= 2^31 - 2^16, which leaves |r| >= 2^30: caught through ora
+            int32_t acc = 0;
+#pragma unroll
+            for (int j = 0; j < TAPS; j++) acc += cf[j] * xs[12 + s - 1 - j];
+            r[s] = (int32_t)((uint32_t)xs[12 + s] - (uint32_t)(acc >> shift));
+        }
+        ora |= (uint32_t)abs(r[s]);
+    }
+    *hi_mismatch = bad;
+    return ora;
+}
+
+// Rare path (a residual magnitude reached 2^30): the oracle's exact test r > INT32_MAX || r <= INT32_MIN in 64-bit
+// arithmetic for this thread's samples, read back from global memory so the hot path keeps its arrays in registers.
+__device__ __noinline__ bool residual_overflows(const int32_t *__restrict__ src, uint32_t wasted, const EncCand *__restrict__ C, int tid) {
+    const int order = C->order, shift = C->shift;
+    bool bad = false;
+    for (int s = 0; s < kSPT; s++) {
+        const int i = tid * kSPT + s;
+        if (i < order) continue;
+        long long acc = 0;
+        for (int j = 0; j < order; j++) acc += (long long)C->coefs[j] * (long long)(src[i - 1 - j] >> wasted);
+        const long long v = (long long)(src[i] >> wasted) - (acc >> shift);
+        if (v > 2147483647ll || v <= -2147483648ll) bad = true;
+    }
+    return bad;
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(kEncThreads, WIDE ? 2 : 3)
+k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps_stream,
+           uint32_t max_po_cfg, uint32_t n_cands, const int32_t *__restrict__ audio,
+           const EncSubStats *__restrict__ stats, const EncCand *__restrict__ cands, uint32_t slot_words,
+           uint32_t *__restrict__ slots, uint32_t *__restrict__ sub_bits) {
+    __shared__ __align__(16) CodeShared<WIDE> S;
+    const uint32_t task = blockIdx.x * channels + blockIdx.y;
+    const TaskLoc L = locate_task(frames, audio, blockIdx.x, blockIdx.y);
+    if (!fast_eligible(L)) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr uint32_t n = kMaxBlock;
+    const uint32_t k_limit = bps_stream > 16 ? 31u : 15u;
+    const EncSubStats st = stats[task];
+    const uint32_t wasted = st.wasted;
+    const uint32_t bps = bps_stream - wasted;
+    int32_t xs[28];
+    load_samples28(L.src, tid, xs);
+    if (wasted) {
+#pragma unroll
+        for (int j = 0; j < 28; j++) xs[j] >>= wasted;
+    }
+    {   // zero the bit buffer
+        constexpr int nq = (int)(sizeof(S.bitbuf) / 16);
+        uint4 *b4 = reinterpret_cast<uint4 *>(S.bitbuf);
+        for (int q = tid; q < nq; q += kEncThreads) b4[q] = make_uint4(0, 0, 0, 0);
+    }
+    const uint32_t verbatim_bits = 8 + wasted + n * bps;
+    int best_type = 1, best_order = 0, best_prec = 0, best_shift = 0, best_slot = -1, best_po = 0;
+    uint32_t best_bits = verbatim_bits;
+    int32_t r[kSPT];
+    int cur_slot = -1;           // candidate whose residual is in r[]
+    // Partition geometry: finest order P = max_po_cfg (3..6 for n = 4096), 2^tpp_log threads per finest
+    // partition; level l (order P - l) groups 2^(tpp_log + l) lanes; levels 0..lw live inside one warp.
+    const uint32_t P = max_po_cfg;
+    const uint32_t tpp_log = 8 - P;
+    const uint32_t lw = 5 - tpp_log;
+
+    // residual of candidate C into r[] (warm-up positions of thread 0 zeroed).  Returns OR |r|, sets *bad.
+    auto eval_residual = [&](const EncCand &C, const EncCand *Cg, bool *bad_out) -> uint32_t {
+        int32_t cf[kMaxOrd];
+#pragma unroll
+        for (int j = 0; j < kMaxOrd; j++) cf[j] = C.coefs[j];
+        uint32_t ora, him;
+        if (C.order <= 4) ora = residual16<WIDE, 4>(xs, cf, C.shift, r, &him);
+        else if (C.order <= 8) ora = residual16<WIDE, 8>(xs, cf, C.shift, r, &him);
+        else ora = residual16<WIDE, 12>(xs, cf, C.shift, r, &him);
+        if (tid == 0) {
+            ora = 0;
+#pragma unroll
+            for (int s = 0; s < kSPT; s++) { if (s < C.order) r[s] = 0; ora |= (uint32_t)abs(r[s]); }   // order <= 12 < 16
+        }
+        bool bad = false;
+        if ((WIDE && him) || ora >= 0x40000000u) bad = residual_overflows(L.src, wasted, Cg, tid);
+        *bad_out = bad;
+        return ora;
+    };
+
+    if (st.flags & 1u) {
+        const uint32_t b = 8 + wasted + bps;
+        if (b < best_bits) { best_type = 0; best_bits = b; }
+    } else {
+        uint32_t par = 0;
+        for (uint32_t slot = 0; slot < n_cands; slot++) {
+            const EncCand *Cg = cands + (size_t)task * kMaxCands + slot;
+            const EncCand C = *Cg;
+            if (C.type == 0) continue;                       // uniform over the CTA
+            bool bad_lane;
+            const uint32_t ora = eval_residual(C, Cg, &bad_lane);
+            cur_slot = (int)slot;
+            const uint32_t order = (uint32_t)C.order;
+            // ---- per-thread abs sum (32-bit unless a residual is huge) ----
+            unsigned long long s64;
+            if (ora < 0x08000000u) {
+                uint32_t s32 = 0;
+#pragma unroll
+                for (int s = 0; s < kSPT; s++) s32 += (uint32_t)abs(r[s]);
+                s64 = s32;
+            } else {
+                s64 = 0;
+#pragma unroll
+                for (int s = 0; s < kSPT; s++) s64 += (unsigned long long)(uint32_t)abs(r[s]);
+            }
+            // ---- segmented butterfly: after step g every lane holds the sum of its 2^(g+1)-lane group.  The
+            // entry (level l, group) is estimated by lane group_base + l, so each lane estimates at most once.
+            unsigned long long mysum = 0;
+            uint32_t my_level = 0xFFFFFFFFu;
+#pragma unroll
+            for (int step = 0; step < 5; step++) {
+                s64 += __shfl_xor_sync(0xFFFFFFFFu, s64, 1 << step);
+                const uint32_t glog = (uint32_t)step + 1;
+                if (glog >= tpp_log) {
+                    const uint32_t l = glog - tpp_log;
+                    if (((uint32_t)lane & ((1u << glog) - 1u)) == l) { mysum = s64; my_level = l; }
+                }
+            }
+            uint32_t myk = 0, mybits = 0;
+            if (my_level != 0xFFFFFFFFu) {
+                const uint32_t po = P - my_level;
+                uint32_t np = n >> po;
+                if (((uint32_t)tid >> (tpp_log + my_level)) == 0) np -= order;       // partition 0 of this level
+                rice_estimate(mysum, np, k_limit, &myk, &mybits);
+            }
+#pragma unroll
+            for (int l = 0; l < 4; l++) {
+                if ((uint32_t)l <= lw) {
+                    const uint32_t v = my_level == (uint32_t)l ? mybits : 0u;
+                    const uint32_t lo = __reduce_add_sync(0xFFFFFFFFu, v & 0xFFFFu), hi = __reduce_add_sync(0xFFFFFFFFu, v >> 16);
+                    if (lane == 0) S.wbits[par][warp][l] = ((unsigned long long)hi << 16) + lo;
+                }
+            }
+            if (lane == 0) S.wsum[par][warp] = s64;
+            const int bad = __syncthreads_or(bad_lane ? 1 : 0);
+            if (bad) { par ^= 1; continue; }                 // uniform
+            // ---- every warp finishes the search on its own: levels above one warp from the 8 warp totals
+            // (lanes 8..14), in-warp levels summed over the warps (lanes 0..lw), then a shuffle gather ----
+            uint32_t upk = 0, upbits = 0, lvl_bits = 0;
+            if (lane >= 8 && lane < 15) {
+                const uint32_t j = (uint32_t)lane - 8;
+                const uint32_t up = j < 4 ? 1u : j < 6 ? 2u : 3u;
+                const uint32_t idx = j < 4 ? j : j < 6 ? j - 4u : 0u;
+                unsigned long long s = 0;
+                for (uint32_t q = 0; q < (1u << up); q++) s += S.wsum[par][(idx << up) + q];
+                uint32_t np = n >> (P - lw - up);
+                if (idx == 0) np -= order;
+                rice_estimate(s, np, k_limit, &upk, &upbits);
+            } else if ((uint32_t)lane <= lw) {
+                unsigned long long s = 6;
+#pragma unroll
+                for (int w = 0; w < 8; w++) s += S.wbits[par][w][lane];
+                lvl_bits = s > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)s;
+            }
+            uint32_t best_l = 0, rb = __shfl_sync(0xFFFFFFFFu, lvl_bits, 0);
+#pragma unroll
+            for (int l = 1; l < 4; l++) {
+                const uint32_t b = __shfl_sync(0xFFFFFFFFu, lvl_bits, l);
+                if ((uint32_t)l <= lw && b < rb) { rb = b; best_l = (uint32_t)l; }
+            }
+            {
+                unsigned long long u1 = 6, u2 = 6, u3 = 6;
+#pragma unroll
+                for (int j = 0; j < 7; j++) {
+                    const uint32_t b = __shfl_sync(0xFFFFFFFFu, upbits, 8 + j);
+                    if (j < 4) u1 += b; else if (j < 6) u2 += b; else u3 += b;
+                }
+                const uint32_t c1 = u1 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)u1;
+                const uint32_t c2 = u2 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)u2;
+                const uint32_t c3 = u3 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)u3;
+                if (c1 < rb) { rb = c1; best_l = lw + 1; }
+                if (c2 < rb) { rb = c2; best_l = lw + 2; }
+                if (c3 < rb) { rb = c3; best_l = lw + 3; }
+            }
+            const uint32_t total = (C.type == 2) ? 8 + wasted + order * bps + rb
+                                                 : 8 + wasted + 4 + 5 + order * ((uint32_t)C.precision + bps) + rb;
+            if (total < best_bits) {
+                best_bits = total; best_type = C.type; best_order = C.order; best_prec = C.precision; best_shift = C.shift;
+                best_slot = (int)slot; best_po = (int)(P - best_l);
+                if (best_l <= lw) {
+                    if (my_level == best_l) S.best_params[(uint32_t)tid >> (tpp_log + best_l)] = (uint8_t)myk;
+                } else if (warp == 0 && lane >= 8 && lane < 15) {
+                    const uint32_t j = (uint32_t)lane - 8;
+                    const uint32_t up = j < 4 ? 1u : j < 6 ? 2u : 3u;
+                    const uint32_t idx = j < 4 ? j : j < 6 ? j - 4u : 0u;
+                    if (lw + up == best_l) S.best_params[idx] = (uint8_t)upk;
+                }
+            }
+            par ^= 1;
+        }
+    }
+    __syncthreads();
+
+    // ---- exact bit lengths, fallback to VERBATIM, pack -------------------------------------------
+    int type = best_type;
+    const int order = best_order;
+    uint32_t my_bits = 0, kcur = 0, plen = 4, method = 0;
+    bool pstart = false;
+    if (type >= 2) {
+        if (cur_slot != best_slot) {
+            const EncCand *Cg = cands + (size_t)task * kMaxCands + best_slot;
+            const EncCand C = *Cg;
+            bool dummy;
+            (void)eval_residual(C, Cg, &dummy);
+        }
+        const uint32_t tl = 8 - (uint32_t)best_po;           // log2 threads per partition (psize = 4096 >> po >= 16)
+        kcur = S.best_params[(uint32_t)tid >> tl];
+        if (WIDE) {
+            // Rice2 (5-bit parameters) as soon as any parameter of the chosen order needs it
+            const uint32_t cnt = 1u << best_po;
+            method = __syncthreads_or(((uint32_t)tid < cnt && S.best_params[tid < 64 ? tid : 0] >= 15) ? 1 : 0) ? 1u : 0u;
+        }
+        plen = method ? 5u : 4u;
+        pstart = ((uint32_t)tid & ((1u << tl) - 1u)) == 0;
+        uint32_t qsum = 0;
+#pragma unroll
+        for (int s = 0; s < kSPT; s++) { r[s] = (int32_t)zigzag(r[s]); qsum += (uint32_t)r[s] >> kcur; }
+        const uint32_t cnt = tid == 0 ? kSPT - (uint32_t)order : (uint32_t)kSPT;    // warm-up slots hold 0 and add nothing to qsum
+        my_bits = qsum + cnt * (1 + kcur) + (pstart ? plen : 0u);
+    }
+    uint32_t hdr_bits = 8 + wasted;
+    if (type == 0) hdr_bits += bps;
+    else if (type == 2) hdr_bits += (uint32_t)order * bps + 6;
+    else if (type == 3) hdr_bits += (uint32_t)order * bps + 9 + (uint32_t)(order * best_prec) + 6;
+    // CTA exclusive scan of my_bits
+    uint32_t total_res, my_off;
+    {
+        uint32_t inc = my_bits;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) S.scan[warp] = inc;
+        __syncthreads();
+        uint32_t base = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kEncThreads / 32; w++) { const uint32_t s = S.scan[w]; if (w < warp) base += s; tot += s; }
+        total_res = tot; my_off = base + inc - my_bits;
+    }
+    if (type >= 2 && hdr_bits + total_res > verbatim_bits) type = 1;     // exactness guard
+    uint32_t total_bits;
+    if (type == 1) { hdr_bits = 8 + wasted; total_bits = verbatim_bits; }
+    else total_bits = hdr_bits + total_res;
+
+    // ---- subframe header, written cooperatively (one field per thread, atomic ORs into the zeroed buffer) ----
+    const uint32_t mask_bps = bps >= 32 ? 0xFFFFFFFFu : ((1u << bps) - 1u);
+    const uint32_t pos0 = 8 + wasted;                        // first bit after the type byte and the wasted-bits unary code
+    if (tid == 0) {
+        const uint32_t typecode = type == 0 ? 0u : type == 1 ? 1u : type == 2 ? (8u | (uint32_t)order) : (32u | (uint32_t)(order - 1));
+        put_bits_atomic(S.bitbuf, 0, (typecode << 1) | (wasted ? 1u : 0u), 8);
+        if (wasted) put_bits_atomic(S.bitbuf, 8 + wasted - 1, 1, 1);
+        if (type == 0 && bps) put_bits_atomic(S.bitbuf, pos0, (uint32_t)xs[12] & mask_bps, bps);
+    }
+    if (type >= 2) {
+        if (tid >= 32 && tid < 32 + order)                   // warm-up sample j = tid - 32
+            put_bits_atomic(S.bitbuf, pos0 + (uint32_t)(tid - 32) * bps, (uint32_t)(__ldg(L.src + (tid - 32)) >> wasted) & mask_bps, bps);
+        const uint32_t pos1 = pos0 + (uint32_t)order * bps;
+        if (type == 3) {
+            const uint32_t prec = (uint32_t)best_prec;
+            if (tid == 96) put_bits_atomic(S.bitbuf, pos1, ((prec - 1) << 5) | ((uint32_t)best_shift & 31u), 9);
+            if (tid >= 64 && tid < 64 + order)
+                put_bits_atomic(S.bitbuf, pos1 + 9 + (uint32_t)(tid - 64) * prec,
+                                (uint32_t)cands[(size_t)task * kMaxCands + best_slot].coefs[tid - 64] & ((1u << prec) - 1u), prec);
+        }
+        if (tid == 128) put_bits_atomic(S.bitbuf, hdr_bits - 6, (method << 4) | (uint32_t)best_po, 6);
+    }
+    PackWriter bw;
+    if (type == 1) {
+        bw.init(S.bitbuf, hdr_bits + (uint32_t)tid * kSPT * bps);
+        if (bps) {
+#pragma unroll
+            for (int s = 0; s < kSPT; s++) bw.put((uint32_t)xs[12 + s] & mask_bps, bps);
+        }
+        bw.finish();
+    } else if (type >= 2) {
+        bw.init(S.bitbuf, hdr_bits + my_off);
+        if (pstart) bw.put(kcur, plen);
+        const uint32_t kbit = 1u << kcur, kmask = kbit - 1u, k1 = kcur + 1;
+#pragma unroll
+        for (int s = 0; s < kSPT; s++) {
+            if (tid != 0 || s >= order) {
+                const uint32_t u = (uint32_t)r[s];
+                const uint32_t q = u >> kcur;
+                const uint32_t tailv = kbit | (u & kmask);
+                if (q + k1 <= 32) bw.put(tailv, q + k1);     // zeros, stop bit and LSBs in one write
+                else { bw.zeros(q); bw.put(tailv, k1); }
+            }
+        }
+        bw.finish();
+    }
+    __syncthreads();
+    // ---- slot store (128-bit, coalesced) ----
+    const uint32_t nwords = (total_bits + 31) / 32;
+    uint32_t *slot = slots + (size_t)task * slot_words;
+    const uint32_t nq = (nwords + 1 + 3) / 4;          // one extra word so the emitter can funnel-read past the end
+    const uint4 *b4 = reinterpret_cast<const uint4 *>(S.bitbuf);
+    uint4 *s4 = reinterpret_cast<uint4 *>(slot);
+    for (uint32_t q = tid; q < nq && q * 4 < slot_words; q += kEncThreads) s4[q] = b4[q];
+    if (tid == 0) sub_bits[task] = total_bits;
+}
