@@ -995,6 +995,7 @@ struct EncWorkspace {
     EncCand *cands;
     uint32_t *slow_tasks;
     FrameDesc *frame_table;
+    unsigned long long *fx_fin;
     uint32_t *slots;
 };
 static inline size_t enc_ws_layout(const frb_encode_params *p, uint64_t total_frames, void *base, EncWorkspace *w) {
@@ -1017,6 +1018,7 @@ static inline size_t enc_ws_layout(const frb_encode_params *p, uint64_t total_fr
     FRB_TAKE(cands, EncCand, subs * kMaxCands)
     FRB_TAKE(slow_tasks, uint32_t, subs)
     FRB_TAKE(frame_table, FrameDesc, total_frames)
+    FRB_TAKE(fx_fin, unsigned long long, subs * 64)
     FRB_TAKE(slots, uint32_t, subs * slot_words_for(p->blocksize, p->bps))
 #undef FRB_TAKE
     return off;
@@ -1109,24 +1111,30 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const int32_t *d_a
     prof_begin(0, s);
     if (fast && slow.size() < total_tasks) {
         const uint32_t windows = (uint32_t)cfg.windows, max_lpc = (uint32_t)cfg.max_lpc_order;
-        const uint32_t n_cands = max_lpc == 0 ? 1u : windows == 1 ? 2u : windows == 2 ? 4u : 10u;
+        const uint32_t n_cands = max_lpc == 0 ? 0u : windows == 1 ? 1u : windows == 2 ? 3u : 9u;     // LPC candidates
         const bool wide = p->bps > 16;
         const dim3 grid((uint32_t)frames, p->channels);
         k_frame_table<<<(uint32_t)((frames + 255) / 256), 256, 0, s>>>(w.streams, p->n_streams, p->blocksize, (uint32_t)frames, w.frame_table);
         FRB_LAUNCH_CHECK("k_frame_table");
-#define FRB_STATS(W, NL) k_enc_stats<W, NL><<<grid, kEncThreads, 0, s>>>(w.frame_table, p->channels, p->bps, windows, d_audio, \
-            w.window, w.stats, w.autoc)
+#define FRB_STATS(W, NL) k_enc_stats<W, NL><<<grid, kEncThreads, 0, s>>>(w.frame_table, p->channels, p->bps, windows, (uint32_t)cfg.max_po, d_audio, \
+            w.window, w.stats, w.autoc, w.fx_fin)
         if (max_lpc == 0) { if (wide) FRB_STATS(true, 0); else FRB_STATS(false, 0); }
         else if (max_lpc <= 8) { if (wide) FRB_STATS(true, 9); else FRB_STATS(false, 9); }
         else { if (wide) FRB_STATS(true, 13); else FRB_STATS(false, 13); }
 #undef FRB_STATS
         FRB_LAUNCH_CHECK("k_enc_stats");
-        const uint32_t model_threads = total_tasks * n_cands;
+        k_enc_fixed<<<(total_tasks + 3) / 4, 128, 0, s>>>(w.frame_table, p->channels, p->bps, (uint32_t)cfg.max_po, total_tasks, d_audio,
+                                                        w.stats, w.fx_fin);
+        FRB_LAUNCH_CHECK("k_enc_fixed");
+        const uint32_t n_slots = n_cands;
+        const uint32_t model_threads = total_tasks * n_slots;
+        if (n_cands) {
 #define FRB_MODEL(MO) k_enc_model<MO><<<(model_threads + 127) / 128, 128, 0, s>>>(w.frame_table, p->channels, p->bps, \
-            p->blocksize, windows, max_lpc, n_cands, total_tasks, d_audio, w.stats, w.autoc, w.cands)
-        if (max_lpc == 0) FRB_MODEL(0); else if (max_lpc <= 8) FRB_MODEL(8); else FRB_MODEL(12);
+            p->blocksize, windows, max_lpc, n_slots, total_tasks, d_audio, w.stats, w.autoc, w.cands)
+        if (max_lpc <= 8) FRB_MODEL(8); else FRB_MODEL(12);
 #undef FRB_MODEL
         FRB_LAUNCH_CHECK("k_enc_model");
+        }
         if (wide)
             k_enc_code<true><<<grid, kEncThreads, 0, s>>>(w.frame_table, p->channels, p->bps, (uint32_t)cfg.max_po, n_cands, d_audio,
                                                           w.stats, w.cands, slot_words, w.slots, w.sub_bits);

@@ -24,12 +24,14 @@
 #pragma once
 
 constexpr int kMaxSets = 6;        // autocorrelation sets per subframe: root, 2 halves, 3 thirds (level 8)
-constexpr int kMaxCands = 10;      // fixed + up to 9 LPC candidates (level 8: 1 + 2 + 6)
+constexpr int kMaxCands = 9;       // LPC candidates per subframe (level 8: 1 + 2 + 6); the FIXED candidate is searched in k_enc_stats
 constexpr int kLags = kMaxOrd + 1;
 
 struct EncSubStats {
     unsigned long long e[5];       // fixed-predictor abs sums over i in [4, n)
-    uint32_t wasted, flags;        // flags bit 0: constant signal
+    uint32_t wasted, flags;        // flags bit 0: constant signal, bit 1: FIXED candidate evaluated (fx_* valid)
+    uint32_t fx_order, fx_bits, fx_po, fx_bad;     // guessed FIXED order, its estimated subframe bits, partition order; residual overflow
+    uint8_t fx_params[64];         // Rice parameters of the FIXED candidate's best partition order
 };
 struct EncCand {                   // type 0 = no candidate, 2 FIXED, 3 LPC
     int32_t type, order, precision, shift;
@@ -128,6 +130,118 @@ __device__ __forceinline__ void warp_sum_split(double (&v)[N], int lane) {
     for (; o > 0; o >>= 1) v[0] += shfl_xor_f64(v[0], o);
 }
 
+// ------------------------------------------------------------------------------------------------ Rice search
+// libFLAC's Rice parameter estimate and bit estimate for one partition (set_partitioned_rice_ with the
+// 18-bit fixed-point mean): np samples, abs sum `sum`.
+__device__ __forceinline__ void rice_estimate(unsigned long long sum, uint32_t np, uint32_t k_limit, uint32_t *k_out, uint32_t *bits_out) {
+    const uint32_t div = 0x40000u / np;
+    const unsigned long long t = sum < 2 ? 0ull : (((sum - 1) * div) >> 18);
+    uint32_t k = t == 0 ? 0u : (uint32_t)ilog2_u64(t) + 1u;
+    if (k >= k_limit) k = k_limit - 1;
+    *k_out = k;
+    *bits_out = rice_bits_estimate(k, np, sum);
+}
+
+struct SearchShared {
+    unsigned long long fin[64];                 // |residual| sums of the finest partitions (order P)
+    uint8_t params[64];                         // Rice parameters of the chosen order
+    uint32_t rb, best_l;                        // estimated residual bits (incl. the 6 method/order bits), chosen level
+};
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int o) { return __shfl_xor_sync(0xFFFFFFFFu, v, o); }
+
+// sum over the warp of capped 32-bit values without overflow (two REDUX on 16-bit halves)
+__device__ __forceinline__ unsigned long long warp_sum_u32(uint32_t lo16sum, uint32_t hi16sum) {
+    return ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, hi16sum) << 16) + __reduce_add_sync(0xFFFFFFFFu, lo16sum);
+}
+
+// find_best_partition_order_ for one full block (n = 4096, 256 threads x 16 samples) in two parts.
+// (1) finest_sums, all 256 threads: s64 = this thread's |residual| sum (warm-up samples excluded); tpp_log
+//     xor-shuffle steps give the 2^P finest partition sums (P = 3..6), stored by the group leaders.
+// (2) warp_search, ONE warp: lane i owns the finest pair (2i, 2i+1): levels 0 and 1 directly, levels >= 2
+//     from an xor butterfly over the pair sums (the entry of level j >= 2 and group g is estimated by the
+//     lane of that group with j-2 trailing one bits, so every lane estimates at most one of them); when the
+//     pairs fill only half the warp (P <= 5) the upper half takes the second entry of each pair and the
+//     levels >= 2, so the four estimates become two; per-level totals with REDUX, order choice, parameters.
+// v2 estimated the in-warp levels in all eight warps and the upper levels redundantly in every warp (~330
+// instructions in every thread): the search is ~5 % of the arithmetic of a subframe but was a third of its
+// instructions (profiles/r01_ncu_enc_v4_*).
+__device__ __forceinline__ void finest_sums(unsigned long long s64, uint32_t P, int tid, unsigned long long *fin) {
+    const int lane = tid & 31;
+    const uint32_t tpp_log = 8 - P;             // log2(threads per finest partition): 2..5
+#pragma unroll
+    for (int step = 0; step < 5; step++)
+        if ((uint32_t)step < tpp_log) s64 += shfl_xor_u64(s64, 1 << step);
+    if (((uint32_t)lane & ((1u << tpp_log) - 1u)) == 0) fin[(uint32_t)tid >> tpp_log] = s64;
+}
+
+__device__ __forceinline__ void warp_search(const unsigned long long *fin, uint32_t order, uint32_t P, uint32_t k_limit, int lane,
+                                            uint8_t *params, uint32_t *rb_out, uint32_t *best_l_out) {
+    constexpr uint32_t n = kMaxBlock;
+    const uint32_t M = 1u << (P - 1);           // pairs of finest partitions: 4..32 lanes
+    const bool act = (uint32_t)lane < M;
+    const unsigned long long a = act ? fin[2 * lane] : 0ull, b = act ? fin[2 * lane + 1] : 0ull;
+    // levels >= 2: butterfly over the pair sums; lane with t trailing ones takes level t + 2
+    const uint32_t t1 = (uint32_t)__ffs(~lane) - 1u;       // trailing ones of the lane index (0..5)
+    const uint32_t myl = t1 + 2;
+    unsigned long long v = a + b, mine = 0;
+#pragma unroll
+    for (int step = 0; step < 5; step++) {
+        v += shfl_xor_u64(v, 1 << step);
+        if ((uint32_t)step == t1) mine = v;
+    }
+    const bool actd = act && myl <= P;
+    const uint32_t np0 = n >> P, np1 = n >> (P - 1);
+    uint32_t ka = 0, kb = 0, kc = 0, kd = 0, ba = 0, bb = 0, bc = 0, bd = 0;
+    if (P <= 5) {
+        // the upper half-warp mirrors lane - 16: first call (a | b), second call (pair sum | level >= 2)
+        const int src = lane & 15;
+        const bool hi = lane >= 16;
+        const unsigned long long b_m = __shfl_sync(0xFFFFFFFFu, b, src), mine_m = __shfl_sync(0xFFFFFFFFu, mine, src);
+        const uint32_t myl_m = __shfl_sync(0xFFFFFFFFu, myl, src);
+        const bool act_m = (uint32_t)src < M, actd_m = act_m && myl_m <= P;
+        uint32_t k1 = 0, b1 = 0, k2 = 0, b2 = 0;
+        if (act_m) rice_estimate(hi ? b_m : a, (!hi && lane == 0) ? np0 - order : np0, k_limit, &k1, &b1);
+        if (hi ? actd_m : act_m) {
+            uint32_t np = hi ? (n >> (P - myl_m)) : np1;
+            if (hi ? (((uint32_t)src >> (myl_m - 1)) == 0) : (lane == 0)) np -= order;
+            rice_estimate(hi ? mine_m : a + b, np, k_limit, &k2, &b2);
+        }
+        // hand the mirrored results back to the owning lanes
+        const uint32_t kb_u = __shfl_sync(0xFFFFFFFFu, k1, src + 16), bb_u = __shfl_sync(0xFFFFFFFFu, b1, src + 16);
+        const uint32_t kd_u = __shfl_sync(0xFFFFFFFFu, k2, src + 16), bd_u = __shfl_sync(0xFFFFFFFFu, b2, src + 16);
+        if (!hi) { ka = k1; ba = b1; kb = kb_u; bb = bb_u; kc = k2; bc = b2; kd = kd_u; bd = bd_u; }
+    } else {
+        if (act) {
+            rice_estimate(a, lane == 0 ? np0 - order : np0, k_limit, &ka, &ba);
+            rice_estimate(b, np0, k_limit, &kb, &bb);
+            rice_estimate(a + b, lane == 0 ? np1 - order : np1, k_limit, &kc, &bc);
+        }
+        if (actd) {
+            uint32_t np = n >> (P - myl);
+            if (((uint32_t)lane >> (myl - 1)) == 0) np -= order;
+            rice_estimate(mine, np, k_limit, &kd, &bd);
+        }
+    }
+    // totals per level (each + 6 bits for method and order), strict improvement from the finest order downwards
+    unsigned long long tot = warp_sum_u32((ba & 0xFFFFu) + (bb & 0xFFFFu), (ba >> 16) + (bb >> 16)) + 6;
+    uint32_t rb = tot > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)tot, best_l = 0;
+    tot = warp_sum_u32(bc & 0xFFFFu, bc >> 16) + 6;
+    { const uint32_t c = tot > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)tot; if (c < rb) { rb = c; best_l = 1; } }
+#pragma unroll
+    for (int l = 2; l <= 6; l++) {
+        if ((uint32_t)l <= P) {
+            const uint32_t x = (actd && myl == (uint32_t)l) ? bd : 0u;
+            tot = warp_sum_u32(x & 0xFFFFu, x >> 16) + 6;
+            const uint32_t c = tot > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)tot;
+            if (c < rb) { rb = c; best_l = (uint32_t)l; }
+        }
+    }
+    if (best_l == 0) { if (act) { params[2 * lane] = (uint8_t)ka; params[2 * lane + 1] = (uint8_t)kb; } }
+    else if (best_l == 1) { if (act) params[lane] = (uint8_t)kc; }
+    else if (actd && myl == best_l) params[(uint32_t)lane >> (myl - 1)] = (uint8_t)kd;
+    *rb_out = rb; *best_l_out = best_l;
+}
+
 // ------------------------------------------------------------------------------------------------ stats
 struct StatsShared {
     uint32_t orv[8], diff[8];
@@ -138,8 +252,9 @@ struct StatsShared {
 template <bool WIDE, int NLAGS>
 __global__ void __launch_bounds__(kEncThreads, (NLAGS > 9 || WIDE) ? 2 : 3)
 k_enc_stats(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps_stream,
-            uint32_t windows, const int32_t *__restrict__ audio,
-            const float *__restrict__ window, EncSubStats *__restrict__ stats, double *__restrict__ autoc_out) {
+            uint32_t windows, uint32_t max_po_cfg, const int32_t *__restrict__ audio,
+            const float *__restrict__ window, EncSubStats *__restrict__ stats, double *__restrict__ autoc_out,
+            unsigned long long *__restrict__ fx_fin) {
     __shared__ StatsShared S;
     const uint32_t task = blockIdx.x * channels + blockIdx.y;
     const TaskLoc L = locate_task(frames, audio, blockIdx.x, blockIdx.y);
@@ -178,11 +293,13 @@ k_enc_stats(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bp
 #pragma unroll
         for (int j = 0; j < 28; j++) xs[j] >>= wasted;
     }
-    // ---- fixed predictor abs-error sums over i in [4, n) ----
-    unsigned long long e[5];
+    // ---- fixed predictor abs-error sums over i in [4, n) (libFLAC's order guess) and, for thread 0, the extra
+    // terms i in [q, 4) that belong to the order-q residual but not to the guess statistic ----
+    unsigned long long e[5], pe[5];           // warp-reduced / per-thread
+    uint32_t fx_badmask = 0;                  // WIDE: bit q set if an order-q residual of this thread does not fit int32
     if (!WIDE) {
         // successive differences in 32 bits: |4th difference| <= 16 * 2^15, 16 samples per thread, 32 per warp
-        uint32_t e32[5] = {0, 0, 0, 0, 0};
+        uint32_t e32[5] = {0, 0, 0, 0, 0}, x32[4] = {0, 0, 0, 0};
         int32_t d1[kSPT + 3], d2[kSPT + 2], d3[kSPT + 1], d4[kSPT];
 #pragma unroll
         for (int j = 0; j < kSPT + 3; j++) d1[j] = xs[9 + j] - xs[8 + j];
@@ -197,25 +314,43 @@ k_enc_stats(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bp
             if (s >= 4 || tid > 0) {
                 e32[0] += (uint32_t)abs(xs[12 + s]); e32[1] += (uint32_t)abs(d1[s + 3]); e32[2] += (uint32_t)abs(d2[s + 2]);
                 e32[3] += (uint32_t)abs(d3[s + 1]); e32[4] += (uint32_t)abs(d4[s]);
+            } else {
+                x32[0] += (uint32_t)abs(xs[12 + s]);
+                if (s >= 1) x32[1] += (uint32_t)abs(d1[s + 3]);
+                if (s >= 2) x32[2] += (uint32_t)abs(d2[s + 2]);
+                if (s >= 3) x32[3] += (uint32_t)abs(d3[s + 1]);
             }
         }
 #pragma unroll
-        for (int q = 0; q < 5; q++) e[q] = __reduce_add_sync(0xFFFFFFFFu, e32[q]);
+        for (int q = 0; q < 5; q++) { pe[q] = e32[q] + (q < 4 ? x32[q < 4 ? q : 0] : 0u); e[q] = __reduce_add_sync(0xFFFFFFFFu, e32[q]); }
     } else {
+        unsigned long long xe[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int q = 0; q < 5; q++) e[q] = 0;
 #pragma unroll
         for (int s = 0; s < kSPT; s++) {
+            const long long a = xs[12 + s], b = xs[11 + s], cc = xs[10 + s], d = xs[9 + s], ee = xs[8 + s];
+            const long long r0 = a, r1 = a - b, r2 = a - 2 * b + cc, r3 = a - 3 * b + 3 * cc - d, r4 = a - 4 * b + 6 * cc - 4 * d + ee;
+            const unsigned long long a0 = (unsigned long long)(r0 < 0 ? -r0 : r0), a1 = (unsigned long long)(r1 < 0 ? -r1 : r1),
+                                     a2 = (unsigned long long)(r2 < 0 ? -r2 : r2), a3 = (unsigned long long)(r3 < 0 ? -r3 : r3),
+                                     a4 = (unsigned long long)(r4 < 0 ? -r4 : r4);
             if (s >= 4 || tid > 0) {
-                const long long a = xs[12 + s], b = xs[11 + s], cc = xs[10 + s], d = xs[9 + s], ee = xs[8 + s];
-                const long long r0 = a, r1 = a - b, r2 = a - 2 * b + cc, r3 = a - 3 * b + 3 * cc - d, r4 = a - 4 * b + 6 * cc - 4 * d + ee;
-                e[0] += (unsigned long long)(r0 < 0 ? -r0 : r0);
-                e[1] += (unsigned long long)(r1 < 0 ? -r1 : r1);
-                e[2] += (unsigned long long)(r2 < 0 ? -r2 : r2);
-                e[3] += (unsigned long long)(r3 < 0 ? -r3 : r3);
-                e[4] += (unsigned long long)(r4 < 0 ? -r4 : r4);
+                e[0] += a0; e[1] += a1; e[2] += a2; e[3] += a3; e[4] += a4;
+                // residual must satisfy INT32_MIN < r <= INT32_MAX (the oracle's / libFLAC's limit)
+                fx_badmask |= (r0 > 2147483647ll || r0 <= -2147483648ll) ? 1u : 0u;
+                fx_badmask |= (r1 > 2147483647ll || r1 <= -2147483648ll) ? 2u : 0u;
+                fx_badmask |= (r2 > 2147483647ll || r2 <= -2147483648ll) ? 4u : 0u;
+                fx_badmask |= (r3 > 2147483647ll || r3 <= -2147483648ll) ? 8u : 0u;
+                fx_badmask |= (r4 > 2147483647ll || r4 <= -2147483648ll) ? 16u : 0u;
+            } else {
+                xe[0] += a0; fx_badmask |= (r0 > 2147483647ll || r0 <= -2147483648ll) ? 1u : 0u;
+                if (s >= 1) { xe[1] += a1; fx_badmask |= (r1 > 2147483647ll || r1 <= -2147483648ll) ? 2u : 0u; }
+                if (s >= 2) { xe[2] += a2; fx_badmask |= (r2 > 2147483647ll || r2 <= -2147483648ll) ? 4u : 0u; }
+                if (s >= 3) { xe[3] += a3; fx_badmask |= (r3 > 2147483647ll || r3 <= -2147483648ll) ? 8u : 0u; }
             }
         }
+#pragma unroll
+        for (int q = 0; q < 5; q++) pe[q] = e[q] + (q < 4 ? xe[q < 4 ? q : 0] : 0ull);
 #pragma unroll
         for (int q = 0; q < 5; q++)
 #pragma unroll
@@ -224,14 +359,35 @@ k_enc_stats(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bp
     if (lane == 0)
 #pragma unroll
         for (int q = 0; q < 5; q++) S.e[warp][q] = e[q];
+    if (tid == 6) stats[task].fx_bad = 0;
     __syncthreads();
-    if (tid < 5) {
-        unsigned long long s = 0;
+    // every warp totals the five sums on its own (lanes 0..4) and broadcasts them: no further barrier
+    unsigned long long et = 0;
+    if (lane < 5) {
 #pragma unroll
-        for (int w = 0; w < 8; w++) s += S.e[w][tid];
-        stats[task].e[tid] = s;
+        for (int w = 0; w < 8; w++) et += S.e[w][lane];
     }
-    if (tid == 5) { stats[task].wasted = wasted; stats[task].flags = diff == 0 ? 1u : 0u; }
+#pragma unroll
+    for (int q = 0; q < 5; q++) e[q] = __shfl_sync(0xFFFFFFFFu, et, q);
+    if (tid < 5) stats[task].e[tid] = et;
+    const uint32_t bps = bps_stream - wasted;
+    uint32_t flags = diff == 0 ? 1u : 0u;
+    if (diff != 0) {
+        // ---- FIXED candidate: libFLAC's order guess; the per-thread |residual| sums of that order are already in
+        // registers, so only the finest partition sums are stored and k_enc_fixed (one warp per subframe) runs the
+        // Rice search: no residual pass and no idle warps for it ----
+        uint32_t guess;
+        const unsigned long long m1234 = min(min(e[1], e[2]), min(e[3], e[4]));
+        const unsigned long long m234 = min(e[2], min(e[3], e[4]));
+        const unsigned long long m34 = min(e[3], e[4]);
+        if (e[0] <= m1234) guess = 0; else if (e[1] <= m234) guess = 1; else if (e[2] <= m34) guess = 2; else if (e[3] <= e[4]) guess = 3; else guess = 4;
+        const unsigned long long ps = guess == 0 ? pe[0] : guess == 1 ? pe[1] : guess == 2 ? pe[2] : guess == 3 ? pe[3] : pe[4];
+        finest_sums(ps, max_po_cfg, tid, fx_fin + (size_t)task * 64);
+        if (WIDE && ((fx_badmask >> guess) & 1u)) atomicOr(&stats[task].fx_bad, 1u);
+        if (tid == 6) stats[task].fx_order = guess;
+        flags |= 2u;
+    }
+    if (tid == 5) { stats[task].wasted = wasted; stats[task].flags = flags; }
     if (NLAGS == 0 || diff == 0) return;
     // ---- windowed autocorrelation, one set per apodization (root, halves, thirds) ----
     const uint32_t i0 = tid * kSPT;
@@ -310,6 +466,37 @@ k_enc_stats(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bp
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------ fixed search
+// One warp per subframe: libFLAC's "is FIXED worth trying" estimate and the Rice search of the FIXED candidate
+// from the finest partition sums k_enc_stats stored.
+__global__ void __launch_bounds__(128)
+k_enc_fixed(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps_stream, uint32_t max_po_cfg, uint32_t total_tasks,
+            const int32_t *__restrict__ audio, EncSubStats *__restrict__ stats, const unsigned long long *__restrict__ fx_fin) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (task >= total_tasks) return;
+    const uint32_t f = task / channels;
+    const TaskLoc L = locate_task(frames, audio, f, task - f * channels);
+    if (!fast_eligible(L)) return;
+    EncSubStats *st = stats + task;
+    const uint32_t flags = st->flags;
+    if (!(flags & 2u)) return;
+    constexpr uint32_t n = kMaxBlock;
+    const uint32_t wasted = st->wasted, guess = st->fx_order;
+    const uint32_t bps = bps_stream - wasted;
+    // FLAC__fixed_compute_best_predictor's estimate for the guessed order; >= bps means "do not even try"
+    const unsigned long long eg = st->e[guess];
+    const float fbits_guess = (float)(eg > 0 ? log(0.69314718055994530942 * (double)eg / (double)(n - 4)) / 0.69314718055994530942 : 0.0);
+    if (fbits_guess >= (float)bps || st->fx_bad) {
+        __syncwarp();
+        if (lane == 0) st->flags = flags & ~2u;
+        return;
+    }
+    uint32_t rb, best_l;
+    warp_search(fx_fin + (size_t)task * 64, guess, max_po_cfg, bps_stream > 16 ? 31u : 15u, lane, st->fx_params, &rb, &best_l);
+    if (lane == 0) { st->fx_bits = 8 + wasted + guess * bps + rb; st->fx_po = max_po_cfg - best_l; }
 }
 
 // ------------------------------------------------------------------------------------------------ model
@@ -418,13 +605,13 @@ __device__ __forceinline__ void model_one(const double (&autoc)[MAXO + 1], uint3
     C.type = 3; C.order = (int)order; C.precision = (int)prec; C.shift = sh;
 }
 
-// thread per (subframe, candidate slot): slot 0 = FIXED guess, slots 1.. = LPC candidates in libFLAC's
-// evaluation order (b = 1: full window; b = 2: halves; b = 3: third, punch-out, third, punch-out, ...)
+// thread per (subframe, LPC candidate slot), slots in libFLAC's evaluation order
+// (b = 1: full window; b = 2: halves; b = 3: third, punch-out, third, punch-out, ...)
 template <int MAXO>
 __global__ void __launch_bounds__(128)
 k_enc_model(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps_stream,
             uint32_t blocksize, uint32_t windows, uint32_t max_lpc_cfg, uint32_t n_cands, uint32_t total_tasks,
-            const int32_t *__restrict__ audio, const EncSubStats *__restrict__ stats, const double *__restrict__ autoc_in,
+            const int32_t *__restrict__ audio, EncSubStats *__restrict__ stats, const double *__restrict__ autoc_in,
             EncCand *__restrict__ cands) {
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t task = gid / n_cands, slot = gid - task * n_cands;
@@ -437,36 +624,22 @@ k_enc_model(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bp
     C.type = 0; C.order = 0; C.precision = 0; C.shift = 0;
 #pragma unroll
     for (int j = 0; j < kMaxOrd; j++) C.coefs[j] = 0;
-    const EncSubStats st = stats[task];
-    const uint32_t bps = bps_stream - st.wasted;
-    if (!(st.flags & 1u)) {
-        if (slot == 0) {
-            const unsigned long long *e = st.e;
-            uint32_t guess;
-            const unsigned long long m1234 = min(min(e[1], e[2]), min(e[3], e[4]));
-            const unsigned long long m234 = min(e[2], min(e[3], e[4]));
-            const unsigned long long m34 = min(e[3], e[4]);
-            if (e[0] <= m1234) guess = 0; else if (e[1] <= m234) guess = 1; else if (e[2] <= m34) guess = 2; else if (e[3] <= e[4]) guess = 3; else guess = 4;
-            const float fbits_guess = (float)(e[guess] > 0 ? log(0.69314718055994530942 * (double)e[guess] / (double)(n - 4)) / 0.69314718055994530942 : 0.0);
-            if (!(fbits_guess >= (float)bps)) {
-                C.type = 2; C.order = (int)guess;
-                if (guess == 1) { C.coefs[0] = 1; }
-                else if (guess == 2) { C.coefs[0] = 2; C.coefs[1] = -1; }
-                else if (guess == 3) { C.coefs[0] = 3; C.coefs[1] = -3; C.coefs[2] = 1; }
-                else if (guess == 4) { C.coefs[0] = 4; C.coefs[1] = -6; C.coefs[2] = 4; C.coefs[3] = -1; }
-            }
-        } else if constexpr (MAXO > 0) {
+    const EncSubStats *stp = stats + task;
+    const uint32_t st_flags = stp->flags;
+    const uint32_t bps = bps_stream - stp->wasted;
+    if (!(st_flags & 1u)) {
+        if constexpr (MAXO > 0) {
             // map the slot to (set, punch-out?)
-            uint32_t lpc_i = slot - 1, set = 0;
+            uint32_t set = 0;
             bool punch = false;
-            if (lpc_i == 0) set = 0;
-            else if (lpc_i <= 2) set = lpc_i;                       // halves: sets 1, 2
-            else { const uint32_t ci = lpc_i - 3; set = 3 + ci / 2; punch = (ci & 1u) != 0; }   // thirds: sets 3, 4, 5
+            if (slot == 0) set = 0;
+            else if (slot <= 2) set = slot;                        // halves: sets 1, 2
+            else { const uint32_t ci = slot - 3; set = 3 + ci / 2; punch = (ci & 1u) != 0; }   // thirds: sets 3, 4, 5
             const double *a = autoc_in + ((size_t)task * kMaxSets + set) * kLags;
             double autoc[MAXO + 1];
 #pragma unroll
             for (int l = 0; l <= MAXO; l++) autoc[l] = a[l];
-            uint32_t max_lpc = max_lpc_cfg;
+            const uint32_t max_lpc = max_lpc_cfg;
             if (punch) {
                 const double *root = autoc_in + (size_t)task * kMaxSets * kLags;
                 // libFLAC subtracts lags [0, max_lpc_order) only; the last lag keeps the partial window's value
@@ -483,8 +656,7 @@ k_enc_model(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bp
 template <bool WIDE>
 struct CodeShared {
     uint32_t bitbuf[WIDE ? 4100 : 2052];
-    unsigned long long wsum[2][8];              // warp totals of |residual|, double-buffered by candidate parity
-    unsigned long long wbits[2][8][4];          // per warp, per in-warp level: estimated bits
+    SearchShared search;
     uint8_t best_params[64];
     uint32_t scan[kEncThreads / 32];
 };
@@ -523,17 +695,6 @@ struct PackWriter {
         if (w) atomicOr(&buf[widx], w);
     }
 };
-
-// libFLAC's Rice parameter estimate and bit estimate for one partition (set_partitioned_rice_ with the
-// 18-bit fixed-point mean): np samples, abs sum `sum`.
-__device__ __forceinline__ void rice_estimate(unsigned long long sum, uint32_t np, uint32_t k_limit, uint32_t *k_out, uint32_t *bits_out) {
-    const uint32_t div = 0x40000u / np;
-    const unsigned long long t = sum < 2 ? 0ull : (((sum - 1) * div) >> 18);
-    uint32_t k = t == 0 ? 0u : (uint32_t)ilog2_u64(t) + 1u;
-    if (k >= k_limit) k = k_limit - 1;
-    *k_out = k;
-    *bits_out = rice_bits_estimate(k, np, sum);
-}
 
 // Residual of this thread's 16 samples.  Returns the OR of |r| (>= 2^30 means an exact overflow check is needed).
 template <bool WIDE, int TAPS>
@@ -592,8 +753,8 @@ k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr uint32_t n = kMaxBlock;
     const uint32_t k_limit = bps_stream > 16 ? 31u : 15u;
-    const EncSubStats st = stats[task];
-    const uint32_t wasted = st.wasted;
+    const EncSubStats *stp = stats + task;
+    const uint32_t wasted = stp->wasted, st_flags = stp->flags;
     const uint32_t bps = bps_stream - wasted;
     int32_t xs[28];
     load_samples28(L.src, tid, xs);
@@ -610,12 +771,8 @@ k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps
     int best_type = 1, best_order = 0, best_prec = 0, best_shift = 0, best_slot = -1, best_po = 0;
     uint32_t best_bits = verbatim_bits;
     int32_t r[kSPT];
-    int cur_slot = -1;           // candidate whose residual is in r[]
-    // Partition geometry: finest order P = max_po_cfg (3..6 for n = 4096), 2^tpp_log threads per finest
-    // partition; level l (order P - l) groups 2^(tpp_log + l) lanes; levels 0..lw live inside one warp.
-    const uint32_t P = max_po_cfg;
-    const uint32_t tpp_log = 8 - P;
-    const uint32_t lw = 5 - tpp_log;
+    int cur_slot = -1;           // LPC candidate whose residual is in r[]
+    const uint32_t P = max_po_cfg;   // finest partition order (3..6 for n = 4096)
 
     // residual of candidate C into r[] (warm-up positions of thread 0 zeroed).  Returns OR |r|, sets *bad.
     auto eval_residual = [&](const EncCand &C, const EncCand *Cg, bool *bad_out) -> uint32_t {
@@ -632,16 +789,20 @@ k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps
             for (int s = 0; s < kSPT; s++) { if (s < C.order) r[s] = 0; ora |= (uint32_t)abs(r[s]); }   // order <= 12 < 16
         }
         bool bad = false;
-        if ((WIDE && him) || ora >= 0x40000000u) bad = residual_overflows(L.src, wasted, Cg, tid);
+        if (Cg != nullptr && ((WIDE && him) || ora >= 0x40000000u)) bad = residual_overflows(L.src, wasted, Cg, tid);
         *bad_out = bad;
         return ora;
     };
 
-    if (st.flags & 1u) {
+    if (st_flags & 1u) {
         const uint32_t b = 8 + wasted + bps;
         if (b < best_bits) { best_type = 0; best_bits = b; }
     } else {
-        uint32_t par = 0;
+        // FIXED candidate: searched by k_enc_stats from the abs sums it had in registers
+        if ((st_flags & 2u) && stp->fx_bits < best_bits) {
+            best_bits = stp->fx_bits; best_type = 2; best_order = (int)stp->fx_order; best_po = (int)stp->fx_po; best_slot = -2;
+            if (tid < 64) S.best_params[tid] = stp->fx_params[tid];
+        }
         for (uint32_t slot = 0; slot < n_cands; slot++) {
             const EncCand *Cg = cands + (size_t)task * kMaxCands + slot;
             const EncCand C = *Cg;
@@ -662,90 +823,22 @@ k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps
 #pragma unroll
                 for (int s = 0; s < kSPT; s++) s64 += (unsigned long long)(uint32_t)abs(r[s]);
             }
-            // ---- segmented butterfly: after step g every lane holds the sum of its 2^(g+1)-lane group.  The
-            // entry (level l, group) is estimated by lane group_base + l, so each lane estimates at most once.
-            unsigned long long mysum = 0;
-            uint32_t my_level = 0xFFFFFFFFu;
-#pragma unroll
-            for (int step = 0; step < 5; step++) {
-                s64 += __shfl_xor_sync(0xFFFFFFFFu, s64, 1 << step);
-                const uint32_t glog = (uint32_t)step + 1;
-                if (glog >= tpp_log) {
-                    const uint32_t l = glog - tpp_log;
-                    if (((uint32_t)lane & ((1u << glog) - 1u)) == l) { mysum = s64; my_level = l; }
-                }
+            finest_sums(s64, P, tid, S.search.fin);
+            if (__syncthreads_or(bad_lane ? 1 : 0)) continue;                // uniform
+            if (warp == 0) {
+                uint32_t rb, bl;
+                warp_search(S.search.fin, order, P, k_limit, lane, S.search.params, &rb, &bl);
+                if (lane == 0) { S.search.rb = rb; S.search.best_l = bl; }
             }
-            uint32_t myk = 0, mybits = 0;
-            if (my_level != 0xFFFFFFFFu) {
-                const uint32_t po = P - my_level;
-                uint32_t np = n >> po;
-                if (((uint32_t)tid >> (tpp_log + my_level)) == 0) np -= order;       // partition 0 of this level
-                rice_estimate(mysum, np, k_limit, &myk, &mybits);
-            }
-#pragma unroll
-            for (int l = 0; l < 4; l++) {
-                if ((uint32_t)l <= lw) {
-                    const uint32_t v = my_level == (uint32_t)l ? mybits : 0u;
-                    const uint32_t lo = __reduce_add_sync(0xFFFFFFFFu, v & 0xFFFFu), hi = __reduce_add_sync(0xFFFFFFFFu, v >> 16);
-                    if (lane == 0) S.wbits[par][warp][l] = ((unsigned long long)hi << 16) + lo;
-                }
-            }
-            if (lane == 0) S.wsum[par][warp] = s64;
-            const int bad = __syncthreads_or(bad_lane ? 1 : 0);
-            if (bad) { par ^= 1; continue; }                 // uniform
-            // ---- every warp finishes the search on its own: levels above one warp from the 8 warp totals
-            // (lanes 8..14), in-warp levels summed over the warps (lanes 0..lw), then a shuffle gather ----
-            uint32_t upk = 0, upbits = 0, lvl_bits = 0;
-            if (lane >= 8 && lane < 15) {
-                const uint32_t j = (uint32_t)lane - 8;
-                const uint32_t up = j < 4 ? 1u : j < 6 ? 2u : 3u;
-                const uint32_t idx = j < 4 ? j : j < 6 ? j - 4u : 0u;
-                unsigned long long s = 0;
-                for (uint32_t q = 0; q < (1u << up); q++) s += S.wsum[par][(idx << up) + q];
-                uint32_t np = n >> (P - lw - up);
-                if (idx == 0) np -= order;
-                rice_estimate(s, np, k_limit, &upk, &upbits);
-            } else if ((uint32_t)lane <= lw) {
-                unsigned long long s = 6;
-#pragma unroll
-                for (int w = 0; w < 8; w++) s += S.wbits[par][w][lane];
-                lvl_bits = s > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)s;
-            }
-            uint32_t best_l = 0, rb = __shfl_sync(0xFFFFFFFFu, lvl_bits, 0);
-#pragma unroll
-            for (int l = 1; l < 4; l++) {
-                const uint32_t b = __shfl_sync(0xFFFFFFFFu, lvl_bits, l);
-                if ((uint32_t)l <= lw && b < rb) { rb = b; best_l = (uint32_t)l; }
-            }
-            {
-                unsigned long long u1 = 6, u2 = 6, u3 = 6;
-#pragma unroll
-                for (int j = 0; j < 7; j++) {
-                    const uint32_t b = __shfl_sync(0xFFFFFFFFu, upbits, 8 + j);
-                    if (j < 4) u1 += b; else if (j < 6) u2 += b; else u3 += b;
-                }
-                const uint32_t c1 = u1 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)u1;
-                const uint32_t c2 = u2 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)u2;
-                const uint32_t c3 = u3 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)u3;
-                if (c1 < rb) { rb = c1; best_l = lw + 1; }
-                if (c2 < rb) { rb = c2; best_l = lw + 2; }
-                if (c3 < rb) { rb = c3; best_l = lw + 3; }
-            }
-            const uint32_t total = (C.type == 2) ? 8 + wasted + order * bps + rb
-                                                 : 8 + wasted + 4 + 5 + order * ((uint32_t)C.precision + bps) + rb;
+            __syncthreads();
+            const uint32_t total = 8 + wasted + 4 + 5 + order * ((uint32_t)C.precision + bps) + S.search.rb;
             if (total < best_bits) {
-                best_bits = total; best_type = C.type; best_order = C.order; best_prec = C.precision; best_shift = C.shift;
-                best_slot = (int)slot; best_po = (int)(P - best_l);
-                if (best_l <= lw) {
-                    if (my_level == best_l) S.best_params[(uint32_t)tid >> (tpp_log + best_l)] = (uint8_t)myk;
-                } else if (warp == 0 && lane >= 8 && lane < 15) {
-                    const uint32_t j = (uint32_t)lane - 8;
-                    const uint32_t up = j < 4 ? 1u : j < 6 ? 2u : 3u;
-                    const uint32_t idx = j < 4 ? j : j < 6 ? j - 4u : 0u;
-                    if (lw + up == best_l) S.best_params[idx] = (uint8_t)upk;
-                }
+                best_bits = total; best_type = 3; best_order = C.order; best_prec = C.precision; best_shift = C.shift;
+                best_slot = (int)slot; best_po = (int)(P - S.search.best_l);
+                // (the FIXED parameters, if any, were stored before the barriers inside partition_search; S.search.params is
+                // rewritten by warp 0 only after the first barrier of the next search)
+                if (tid < 64) S.best_params[tid] = S.search.params[tid];
             }
-            par ^= 1;
         }
     }
     __syncthreads();
@@ -756,7 +849,18 @@ k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps
     uint32_t my_bits = 0, kcur = 0, plen = 4, method = 0;
     bool pstart = false;
     if (type >= 2) {
-        if (cur_slot != best_slot) {
+        if (best_slot == -2) {
+            EncCand C;
+            C.type = 2; C.order = order; C.precision = 0; C.shift = 0;
+#pragma unroll
+            for (int j = 0; j < kMaxOrd; j++) C.coefs[j] = 0;
+            if (order == 1) { C.coefs[0] = 1; }
+            else if (order == 2) { C.coefs[0] = 2; C.coefs[1] = -1; }
+            else if (order == 3) { C.coefs[0] = 3; C.coefs[1] = -3; C.coefs[2] = 1; }
+            else if (order == 4) { C.coefs[0] = 4; C.coefs[1] = -6; C.coefs[2] = 4; C.coefs[3] = -1; }
+            bool dummy;
+            (void)eval_residual(C, nullptr, &dummy);        // its overflow check was done by k_enc_stats
+        } else if (cur_slot != best_slot) {
             const EncCand *Cg = cands + (size_t)task * kMaxCands + best_slot;
             const EncCand C = *Cg;
             bool dummy;
