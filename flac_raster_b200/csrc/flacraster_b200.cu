@@ -1,6 +1,7 @@
 // flacraster_b200.cu -- unity build of libflacraster_b200.so (sm_100a only).
 //   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 #include <vector>
+#include <cstdlib>
 #include <cmath>
 #include <mutex>
 #include "frb_common.cuh"

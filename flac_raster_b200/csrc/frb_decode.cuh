@@ -241,9 +241,12 @@ extern "C" int frb_decode_batch(const frb_decode_params *p, const frb_decode_str
         const uint32_t *sub_bitoff = nullptr;
         if (p->channels > 1) {
             // subframes of a frame are bit-packed back to back: find their starts first
-            k_skim_subframes<<<(uint32_t)((total_frames + 127) / 128), 128, 0, s>>>(
+            static uint32_t skim_lanes = 0;
+            if (!skim_lanes) { const char *e = getenv("FRB_SKIM_LANES"); skim_lanes = e ? (uint32_t)atoi(e) : 32u; if (skim_lanes < 1 || skim_lanes > 32) skim_lanes = 32; }
+            const uint32_t frames_per_cta = (kDecThreads / 32) * skim_lanes;
+            k_skim_subframes<<<(uint32_t)((total_frames + frames_per_cta - 1) / frames_per_cta), kDecThreads, 0, s>>>(
                 d_bytes, w.streams, p->n_streams, p->channels, p->bps, p->blocksize, (uint32_t)total_frames, w.frame_pos,
-                w.sub_bitoff, w.chassign, d_status);
+                w.sub_bitoff, w.chassign, d_status, skim_lanes);
             FRB_LAUNCH_CHECK("k_skim_subframes");
             sub_bitoff = w.sub_bitoff;
         }

@@ -158,37 +158,206 @@ __device__ __forceinline__ FrameLoc locate_frame(const DecStreamDev *__restrict_
 // ---- skim: subframe bit offsets for multi-channel frames ------------------------------------------
 // sub_bitoff[f*channels + c] = bit offset of subframe c from the frame start; 0 marks a bad frame.
 // One thread per frame walks subframes 0..C-2 (the last one only needs its start; its end is checked by
-// the decode kernel).  The walk is ONE flat loop with a per-lane state machine: nested
-// partition/sample loops made lanes with different partition orders wait for each other at every
-// reconvergence point (15.9 ms on C3, profiles/r01_launches_c3_v2.csv).
+// the decode kernel).
+//
+// With 32 independent frames per warp every data-dependent branch is taken by SOME lane in almost every
+// step, so the warp pays for the union of all paths: the v3 skim (shared-memory word ring, one Rice code
+// per loop trip, refill branch) and a v4 trial (16-byte ring slots + register queue) executed 50-100 warp
+// instructions per code (5.8 / 12.8 ms on C3, profiles/r01_ncu_skim_v4.txt).  This version keeps the hot
+// loop free of data-dependent branches:
+//   * codes are skipped in batches of kSkimBatch with predication (lane inactive once its partition is
+//     exhausted); a code longer than 32 bits is the only branch in the batch;
+//   * the window is (hi, lo) plus a pre-loaded next word; crossing a word boundary is three selects and a
+//     predicated 4-byte LDS from the thread's ring, never a wait;
+//   * the ring (16-byte chunks, cp.async) is topped up ONCE per batch at a warp-uniform point with
+//     predicated copies, and one wait_group per batch covers every word the batch can touch.
+constexpr int kSkimRing = 16;                                   // 16-byte chunks per thread (256 contiguous bytes)
+constexpr int kSkimBatch = 8;                                   // codes per batch: <= 8 words = 2 chunks
+
+// 64-bit left-aligned window (hi:lo, the top vb >= 32 bits valid) + two pre-loaded words.  The dependent chain
+// per code is clz -> add -> funnel shift (-> or, when a word is merged); everything else hangs off it.
+// Ring: the thread's 16 chunks are contiguous in shared memory, chunk index XOR-swizzled with the lane so that
+// lanes reading the same word offset spread over the banks.
+struct SkimReader {
+    const uint4 *gq;         // 16-byte view of the input buffer (16-byte aligned base)
+    uint32_t sbase;          // shared-space address of this thread's 256-byte ring
+    uint32_t swz;            // (lane & 15) << 4
+    uint32_t wnext;          // word index (32-bit words from the buffer base) of the next word to load; nx = wnext-2, nx2 = wnext-1
+    uint32_t cissue;         // next chunk to copy into the ring
+    uint32_t qlast;          // copies are clamped to this chunk (16 readable bytes follow the frame end)
+    uint32_t hi, lo, nx, nx2raw;   // nx2raw: word wnext-1 as loaded (little-endian), byte-swapped when it becomes nx
+    int32_t vb;              // valid bits in hi:lo
+    __device__ __forceinline__ uint32_t load_raw(uint32_t a) const { return lds_u32(sbase + ((((a << 2) & 252u)) ^ swz)); }
+    __device__ __forceinline__ uint32_t load_word(uint32_t a) const { return bswap32(load_raw(a)); }
+    __device__ __forceinline__ void copy_chunk(uint32_t c) const {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sbase + (((c & (kSkimRing - 1)) << 4) ^ swz)),
+                     "l"(gq + min(c, qlast)) : "memory");
+    }
+    // Copy ahead without overwriting anything still needed: chunk c may replace chunk c - kSkimRing once that one
+    // lies before the chunk of the oldest pre-loaded word.  At most two chunks per call (a batch consumes at most two).
+    __device__ __forceinline__ void top_up() {
+        const uint32_t lim = ((wnext - 2) >> 2) + kSkimRing - 1;
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+            if (cissue < lim) { copy_chunk(cissue); cissue++; }
+        cp_async_commit();
+        // a chunk is read at least (kSkimRing - 3) / 2 batches after it was requested
+        cp_async_wait<(kSkimRing - 3) / 2 - 1>();
+    }
+    __device__ __forceinline__ void init(uint32_t ring_saddr, uint32_t lane, const uint8_t *base, uint64_t bitpos, uint64_t byte_end) {
+        gq = (const uint4 *)base;
+        sbase = ring_saddr;
+        swz = (lane & 15u) << 4;
+        const uint32_t w = (uint32_t)(bitpos >> 5);
+        qlast = (uint32_t)(byte_end >> 4);
+        cissue = w >> 2;
+        for (int j = 0; j < kSkimRing - 1; j++) { copy_chunk(cissue); cissue++; }
+        cp_async_commit();
+        cp_async_wait<0>();
+        hi = load_word(w); lo = load_word(w + 1); nx = load_word(w + 2); nx2raw = load_raw(w + 3);
+        wnext = w + 4;
+        vb = 64;
+        consume((uint32_t)bitpos & 31u);
+    }
+    __device__ __forceinline__ uint64_t bitpos() const { return (uint64_t)(wnext - 2) * 32u - (uint32_t)vb; }
+    __device__ __forceinline__ bool overrun() const { return (wnext >> 2) > qlast + 2; }
+    __device__ __forceinline__ uint32_t window() const { return hi; }
+    __device__ __forceinline__ void merge_word() {                 // vb < 32: append nx below the valid bits
+        hi |= __funnelshift_rc(nx, 0u, (uint32_t)vb);
+        lo = __funnelshift_lc(0u, nx, 32u - (uint32_t)vb);
+        vb += 32;
+        nx = bswap32(nx2raw); nx2raw = load_raw(wnext); wnext++;
+    }
+    // The same as `if (vb < 32) merge_word();` as straight-line predicated code: with 32 independent streams per warp
+    // some lane merges in almost every step, so a branch would cost every lane the divergent path plus its
+    // reconvergence; the freshly loaded word is not touched before the next merge (no wait on the LDS).
+    __device__ __forceinline__ void merge_word_predicated() {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b32 t, a;\n\t"
+            "setp.lt.s32 p, %4, 32;\n\t"
+            "@p shf.r.clamp.b32 t, %2, 0, %4;\n\t"
+            "@p or.b32 %0, %0, t;\n\t"
+            "@p sub.s32 t, 32, %4;\n\t"
+            "@p shf.l.clamp.b32 %1, 0, %2, t;\n\t"
+            "@p add.s32 %4, %4, 32;\n\t"
+            "@p prmt.b32 %2, %3, 0, 0x0123;\n\t"
+            "@p shl.b32 a, %5, 2;\n\t"
+            "@p and.b32 a, a, 252;\n\t"
+            "@p xor.b32 a, a, %6;\n\t"
+            "@p add.u32 a, a, %7;\n\t"
+            "@p ld.shared.u32 %3, [a];\n\t"
+            "@p add.u32 %5, %5, 1;\n\t"
+            "}\n"
+            : "+r"(hi), "+r"(lo), "+r"(nx), "+r"(nx2raw), "+r"(vb), "+r"(wnext)
+            : "r"(swz), "r"(sbase)
+            : "memory");
+    }
+    __device__ __forceinline__ void consume(uint32_t nb) {         // nb <= 32
+        hi = __funnelshift_lc(lo, hi, nb);
+        lo = __funnelshift_lc(0u, lo, nb);
+        vb -= (int32_t)nb;
+        if (vb < 32) merge_word();
+    }
+    // generic (rare) operations for headers, escapes and over-long codes; callers top up between them
+    __device__ __forceinline__ uint32_t get(uint32_t nb) {          // nb in 0..32
+        const uint32_t v = __funnelshift_lc(hi, 0u, nb);            // hi >> (32 - nb), 0 for nb == 0
+        consume(nb);
+        return v;
+    }
+    __device__ __forceinline__ uint32_t unary() {
+        uint32_t q = 0;
+        for (;;) {
+            if (hi) { const uint32_t z = __clz(hi); consume(z + 1); return q + z; }
+            q += 32; consume(32);
+            top_up();
+            if (overrun()) return q;                                // ran past the frame: corrupt stream
+        }
+    }
+    __device__ __forceinline__ void seek(const uint8_t *base, uint64_t bits_forward, uint64_t byte_end) {
+        const uint64_t target = bitpos() + bits_forward;
+        cp_async_wait<0>();                                          // nothing may land in the ring after re-initialisation
+        init(sbase, swz >> 4, base, target, byte_end);
+    }
+};
+
 __global__ void __launch_bounds__(kDecThreads)
 k_skim_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__restrict__ streams, uint32_t n_streams,
                  uint32_t channels, uint32_t bps, uint32_t blocksize, uint32_t total_frames,
                  const unsigned long long *__restrict__ frame_pos, uint32_t *__restrict__ sub_bitoff,
-                 uint8_t *__restrict__ frame_chassign, uint32_t *__restrict__ status) {
-    __shared__ uint32_t s_ring[kRing * kDecThreads];
-    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= total_frames) return;
+                 uint8_t *__restrict__ frame_chassign, uint32_t *__restrict__ status, uint32_t lanes_per_warp) {
+    __shared__ __align__(256) uint4 s_ring[kSkimRing * kDecThreads];
+    // Only `lanes_per_warp` lanes of every warp take a frame: the walk is a long dependent chain, and there are far
+    // fewer frames than the machine has thread slots, so spreading them over more warps buys latency hiding (and
+    // less divergence per warp) for issue slots that would otherwise idle.
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t f = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * lanes_per_warp + lane;
+    // No lane leaves before the walk is over: the loop below re-converges the whole warp at every trip
+    // (__any_sync).  Without that, lanes in different phases (batch / partition change / subframe header) ran
+    // their phases one after the other and a warp executed 3.3x the batches a single lane needs
+    // (profiles/r01_ncu_skim_v5.txt).
+    bool done = !(lane < lanes_per_warp && f < total_frames) || channels <= 1;
     DecStreamDev st;
-    const FrameLoc L = locate_frame(streams, n_streams, blocksize, f, frame_pos, &st);
-    uint32_t *off_out = sub_bitoff + (size_t)f * channels;
-    for (uint32_t c = 0; c < channels; c++) off_out[c] = 0;
-    if (!L.ok) { atomicAdd(&status[0], 1u); return; }
-    FrameHdr h;
-    if (!parse_frame_header(bytes + L.start, L.end - L.start, 0, bps, &h)) { atomicAdd(&status[2], 1u); return; }
-    frame_chassign[f] = (uint8_t)h.ch_assign;
-    const uint64_t frame_bit0 = L.start * 8;
-    BitReader br;
-    br.init((uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x), bytes, frame_bit0 + (uint64_t)h.header_bytes * 8, L.end);
+    FrameLoc L; L.ok = false; L.start = L.end = 0; L.k = 0; L.n = 0; L.stream = 0;
+    FrameHdr h; h.header_bytes = 0; h.ch_assign = 0;
+    uint32_t *off_out = sub_bitoff + (size_t)(done ? 0 : f) * channels;
+    uint64_t frame_bit0 = 0;
+    SkimReader br;
+    br.gq = (const uint4 *)bytes; br.sbase = (uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x * kSkimRing); br.swz = (lane & 15u) << 4;
+    br.wnext = 2; br.cissue = 0; br.qlast = 0; br.hi = br.lo = br.nx = br.nx2raw = 0; br.vb = 64;
+    if (lane < lanes_per_warp && f < total_frames) {
+        L = locate_frame(streams, n_streams, blocksize, f, frame_pos, &st);
+        for (uint32_t c = 0; c < channels; c++) off_out[c] = 0;
+        if (!L.ok) { atomicAdd(&status[0], 1u); done = true; }
+        else if (!parse_frame_header(bytes + L.start, L.end - L.start, 0, bps, &h)) { atomicAdd(&status[2], 1u); done = true; }
+        else {
+            frame_chassign[f] = (uint8_t)h.ch_assign;
+            frame_bit0 = L.start * 8;
+            off_out[0] = h.header_bytes * 8;
+            if (!done) br.init(br.sbase, lane, bytes, frame_bit0 + (uint64_t)h.header_bytes * 8, L.end);
+        }
+    }
     const uint32_t n = L.n;
     bool err = false, in_res = false;
     uint32_t c = 0, left = 0, parts_left = 0, k = 0, plen = 4, esc = 15, psize = 0;
-    off_out[0] = h.header_bytes * 8;
-    // hot path first: one Rice code per iteration; header / partition transitions are the rare branch
-    if (channels > 1) for (;;) {
+    while (__any_sync(0xFFFFFFFFu, !done)) {
+        if (done) continue;
+        br.top_up();
+        if (left >= (uint32_t)kSkimBatch) {
+            // ---- a full batch of Rice codes without data-dependent branches; a code longer than 32 bits (long unary
+            // run or corrupt data) is detected once per batch and the batch is then redone one code at a time ----
+            const SkimReader snap = br;
+            const uint32_t k1 = k + 1;
+            uint32_t maxlen = 0;
+#pragma unroll
+            for (int i = 0; i < kSkimBatch; i++) {
+                const uint32_t len = (uint32_t)__clz(br.hi) + k1;
+                maxlen = max(maxlen, len);
+                br.hi = __funnelshift_lc(br.lo, br.hi, len);
+                br.lo = __funnelshift_lc(0u, br.lo, len);
+                br.vb -= (int32_t)len;
+                br.merge_word_predicated();
+            }
+            if (maxlen <= 32) { left -= kSkimBatch; continue; }
+            br = snap;
+        }
         if (left) {
-            br.skip_rice(k);
-            left--;
+            // ---- one batch of Rice codes, predicated on the lane still having codes in this partition ----
+            const uint32_t m = left < (uint32_t)kSkimBatch ? left : (uint32_t)kSkimBatch;
+            const uint32_t k1 = k + 1;
+#pragma unroll
+            for (int i = 0; i < kSkimBatch; i++) {
+                const uint32_t w = br.window();
+                uint32_t len = (uint32_t)__clz(w) + k1;
+                const bool active = (uint32_t)i < m;
+                if (active && len > 32) {                    // rare: long unary run (or a corrupt stream)
+                    (void)br.unary();
+                    len = k;
+                    if (br.overrun()) { err = true; len = 0; }
+                }
+                br.consume(active ? len : 0u);
+            }
+            left -= m;
+            if (err) done = true;
             continue;
         }
         if (in_res) {
@@ -203,7 +372,7 @@ k_skim_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__restri
             if (!in_res) { c++; off_out[c] = (uint32_t)(br.bitpos() - frame_bit0); }
             continue;
         }
-        if (err || c + 1 >= channels) break;
+        if (err || c + 1 >= channels) { done = true; continue; }
         {
             uint32_t sbps = bps;
             if ((h.ch_assign == 8 && c == 1) || (h.ch_assign == 9 && c == 0) || (h.ch_assign == 10 && c == 1)) sbps++;
@@ -211,7 +380,7 @@ k_skim_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__restri
             const uint32_t t = (hd >> 1) & 0x3F;
             uint32_t wasted = 0;
             if (hd & 1) wasted = br.unary() + 1;
-            if ((hd & 0x80) || wasted >= sbps) { err = true; break; }
+            if ((hd & 0x80) || wasted >= sbps) { err = true; done = true; continue; }
             sbps -= wasted;
             uint32_t order = 0;
             bool coded = false;
@@ -219,20 +388,20 @@ k_skim_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__restri
             else if (t == 1) br.seek(bytes, (uint64_t)sbps * n, L.end);
             else if (t >= 8 && t <= 12) { order = t - 8; coded = true; }
             else if (t >= 32) { order = t - 31; coded = true; }
-            else { err = true; break; }
+            else { err = true; done = true; continue; }
             if (coded) {
-                if (order > n) { err = true; break; }
+                if (order > n) { err = true; done = true; continue; }
                 br.seek(bytes, (uint64_t)order * sbps, L.end);
                 if (t >= 32) {
                     const uint32_t prec = br.get(4) + 1;
-                    if (prec == 16) { err = true; break; }
+                    if (prec == 16) { err = true; done = true; continue; }
                     br.seek(bytes, 5 + (uint64_t)order * prec, L.end);
                 }
                 const uint32_t m = br.get(2);
                 const uint32_t po = br.get(4);
                 plen = m ? 5u : 4u; esc = m ? 31u : 15u;
                 psize = n >> po;
-                if (m > 1 || (po > 0 && (n & ((1u << po) - 1))) || psize < order) { err = true; break; }
+                if (m > 1 || (po > 0 && (n & ((1u << po) - 1))) || psize < order) { err = true; done = true; continue; }
                 parts_left = 1u << po;
                 left = psize - order;
                 in_res = true;
@@ -248,10 +417,11 @@ k_skim_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__restri
             }
             if (!in_res) { c++; off_out[c] = (uint32_t)(br.bitpos() - frame_bit0); }
         }
-        if (err) break;
+        if (err) done = true;
     }
-    if (!err && br.bitpos() > L.end * 8) err = true;
-    if (err) {
+    const bool mine = lane < lanes_per_warp && f < total_frames && channels > 1 && L.ok && h.header_bytes != 0;
+    if (mine && !err && br.bitpos() > L.end * 8) err = true;
+    if (mine && err) {
         atomicAdd(&status[2], 1u);
         for (uint32_t q = 0; q < channels; q++) off_out[q] = 0;
     }
