@@ -10,20 +10,8 @@
 //   k_crc16_frames      one warp per frame, 16-byte chunks per lane, slice-by-4 tables in shared
 //                       memory, Horner combination with x^(8*512) and a final x^(8*n) weight
 
-// ---- 32-bit window bit reader fed by a per-thread shared-memory ring (MSB first) ------------------
-// Lanes consume their streams at different rates, so in any iteration some lane needs a new word.
-// Reading that word straight from global memory (v2) made the whole warp wait for a DRAM/L2 round
-// trip almost every sample (~1000 cycles per sample on both the skim and the decode kernel,
-// profiles/r01_launches_c3_v2.csv).  Here every thread owns a ring of kRing words in shared memory,
-// refilled kRing-2 words ahead with 4-byte cp.async (no register scoreboard, no warp stall); a refill
-// is one conflict-free LDS (layout [slot][thread]) plus the next asynchronous prefetch.
-constexpr int kRing = 16;
+// ---- cp.async / shared-memory helpers ------------------------------------------------------------------
 constexpr int kDecThreads = 128;
-constexpr uint32_t kRingBytes = kRing * kDecThreads * 4;      // 8 KB per CTA; slot stride kDecThreads*4 bytes
-
-__device__ __forceinline__ void cp_async4_s(uint32_t smem_addr, const uint32_t *gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_addr), "l"(gsrc) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
@@ -32,97 +20,6 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t smem_addr) {
     asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(smem_addr) : "memory");
     return v;
 }
-
-struct BitReader {
-    const uint32_t *gwords;  // 4-byte view of the input buffer (kernel-uniform)
-    uint32_t sbase;          // shared-space address of this thread's ring column (slot 0)
-    uint32_t soff;           // byte offset (multiple of kDecThreads*4, < kRingBytes) of the next slot to read
-    uint32_t widx;           // word index of the next word to prefetch; the word in `hi` is widx - (kRing + 2)
-    uint32_t wlast;          // prefetches are clamped to this word index (one word past the frame end)
-    uint32_t hi, lo;
-    uint32_t pos;            // consumed bits of hi, 0..31
-    __device__ __forceinline__ void prefetch(uint32_t slot_off) {
-        cp_async4_s(sbase + slot_off, gwords + min(widx, wlast));
-        cp_async_commit();
-        widx++;
-    }
-    __device__ __forceinline__ void init(uint32_t ring_col_saddr, const uint8_t *base, uint64_t bitpos, uint64_t byte_end) {
-        gwords = (const uint32_t *)base;
-        sbase = ring_col_saddr;
-        widx = (uint32_t)(bitpos >> 5);
-        wlast = (uint32_t)((byte_end + 3) >> 2);
-#pragma unroll
-        for (int j = 0; j < kRing; j++) prefetch(j * kDecThreads * 4);
-        cp_async_wait<0>();
-        hi = bswap32(lds_u32(sbase));
-        lo = bswap32(lds_u32(sbase + kDecThreads * 4));
-        prefetch(0); prefetch(kDecThreads * 4);
-        soff = 2 * kDecThreads * 4;
-        pos = (uint32_t)bitpos & 31u;
-    }
-    __device__ __forceinline__ uint64_t bitpos() const { return (uint64_t)(widx - (kRing + 2)) * 32u + pos; }
-    __device__ __forceinline__ bool overrun() const { return widx - (kRing + 2) > wlast + 1; }
-    __device__ __forceinline__ uint32_t window() const { return __funnelshift_l(lo, hi, pos); }
-    __device__ __forceinline__ void consume(uint32_t nb) {          // nb <= 32
-        pos += nb;
-        if (pos >= 32) {
-            pos -= 32;
-            hi = lo;
-            // the word in this slot was requested kRing refills ago: all but the newest kRing-1 groups must be complete
-            cp_async_wait<kRing - 1>();
-            lo = bswap32(lds_u32(sbase + soff));
-            prefetch(soff);
-            soff = (soff + kDecThreads * 4) & (kRingBytes - 1);
-        }
-    }
-    __device__ __forceinline__ uint32_t get(uint32_t nb) {          // nb in 0..32
-        const uint32_t v = __funnelshift_lc(window(), 0u, nb);      // window >> (32 - nb), 0 for nb == 0
-        consume(nb);
-        return v;
-    }
-    __device__ __forceinline__ int32_t get_signed(uint32_t nb) {    // nb in 0..33
-        if (nb == 0) return 0;
-        if (nb > 32) { consume(nb - 32); nb = 32; }                 // top bits are sign copies for in-range data
-        const uint32_t v = get(nb);
-        const uint32_t sh = 32 - nb;
-        return (int32_t)(v << sh) >> sh;
-    }
-    __device__ __forceinline__ uint32_t unary() {
-        uint32_t q = 0;
-        for (;;) {
-            const uint32_t w = window();
-            if (w) { const uint32_t z = __clz(w); consume(z + 1); return q + z; }
-            q += 32; consume(32);
-            if (overrun()) return q;                                // ran past the frame: corrupt stream
-        }
-    }
-    // zig-zag folded Rice value with parameter k (<= 30)
-    __device__ __forceinline__ uint32_t rice_u(uint32_t k) {
-        const uint32_t w = window();
-        const uint32_t z = __clz(w);
-        const uint32_t len = z + 1 + k;
-        if (len <= 32) {
-            const uint32_t t = __funnelshift_lc(0u, w, z + 1);      // w << (z+1), 0 when z+1 == 32
-            const uint32_t low = __funnelshift_lc(t, 0u, k);        // t >> (32-k), 0 when k == 0
-            consume(len);
-            return (z << k) | low;
-        }
-        const uint32_t q = unary();
-        const uint32_t low = get(k);
-        return (q << k) | low;
-    }
-    __device__ __forceinline__ void skip_rice(uint32_t k) {
-        const uint32_t len = __clz(window()) + 1 + k;
-        if (len <= 32) { consume(len); return; }
-        (void)unary();
-        consume(k);
-    }
-    __device__ __forceinline__ void seek(const uint8_t *base, uint64_t bits_forward, uint64_t byte_end) {
-        const uint64_t target = bitpos() + bits_forward;
-        cp_async_wait<0>();                                          // nothing may land in the ring after re-initialisation
-        init(sbase, base, target, byte_end);
-    }
-};
 
 __device__ __forceinline__ int32_t unzigzag(uint32_t u) { return (int32_t)(u >> 1) ^ -(int32_t)(u & 1u); }
 
@@ -155,7 +52,7 @@ __device__ __forceinline__ FrameLoc locate_frame(const DecStreamDev *__restrict_
 
 // status words: 0 frames_missing, 1 crc16_errors, 2 parse_errors, 3 frames_decoded, 4 order_overflow
 
-// ---- skim: subframe bit offsets for multi-channel frames ------------------------------------------
+// ---- bit reader + skim: subframe bit offsets for multi-channel frames ------------------------------
 // sub_bitoff[f*channels + c] = bit offset of subframe c from the frame start; 0 marks a bad frame.
 // One thread per frame walks subframes 0..C-2 (the last one only needs its start; its end is checked by
 // the decode kernel).
@@ -178,7 +75,7 @@ constexpr int kSkimBatch = 8;                                   // codes per bat
 // per code is clz -> add -> funnel shift (-> or, when a word is merged); everything else hangs off it.
 // Ring: the thread's 16 chunks are contiguous in shared memory, chunk index XOR-swizzled with the lane so that
 // lanes reading the same word offset spread over the banks.
-struct SkimReader {
+struct BitReader {
     const uint4 *gq;         // 16-byte view of the input buffer (16-byte aligned base)
     uint32_t sbase;          // shared-space address of this thread's 256-byte ring
     uint32_t swz;            // (lane & 15) << 4
@@ -264,6 +161,13 @@ struct SkimReader {
         consume(nb);
         return v;
     }
+    __device__ __forceinline__ int32_t get_signed(uint32_t nb) {    // nb in 0..33
+        if (nb == 0) return 0;
+        if (nb > 32) { consume(nb - 32); nb = 32; }                 // top bits are sign copies for in-range data
+        const uint32_t v = get(nb);
+        const uint32_t sh = 32 - nb;
+        return (int32_t)(v << sh) >> sh;
+    }
     __device__ __forceinline__ uint32_t unary() {
         uint32_t q = 0;
         for (;;) {
@@ -272,6 +176,12 @@ struct SkimReader {
             top_up();
             if (overrun()) return q;                                // ran past the frame: corrupt stream
         }
+    }
+    // zig-zag folded Rice value with parameter k (<= 30), any length (generic path)
+    __device__ __forceinline__ uint32_t rice_u(uint32_t k) {
+        const uint32_t q = unary();
+        const uint32_t low = get(k);
+        return (q << k) | low;
     }
     __device__ __forceinline__ void seek(const uint8_t *base, uint64_t bits_forward, uint64_t byte_end) {
         const uint64_t target = bitpos() + bits_forward;
@@ -301,7 +211,7 @@ k_skim_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__restri
     FrameHdr h; h.header_bytes = 0; h.ch_assign = 0;
     uint32_t *off_out = sub_bitoff + (size_t)(done ? 0 : f) * channels;
     uint64_t frame_bit0 = 0;
-    SkimReader br;
+    BitReader br;
     br.gq = (const uint4 *)bytes; br.sbase = (uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x * kSkimRing); br.swz = (lane & 15u) << 4;
     br.wnext = 2; br.cissue = 0; br.qlast = 0; br.hi = br.lo = br.nx = br.nx2raw = 0; br.vb = 64;
     if (lane < lanes_per_warp && f < total_frames) {
@@ -325,7 +235,7 @@ k_skim_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__restri
         if (left >= (uint32_t)kSkimBatch) {
             // ---- a full batch of Rice codes without data-dependent branches; a code longer than 32 bits (long unary
             // run or corrupt data) is detected once per batch and the batch is then redone one code at a time ----
-            const SkimReader snap = br;
+            const BitReader snap = br;
             const uint32_t k1 = k + 1;
             uint32_t maxlen = 0;
 #pragma unroll
@@ -452,73 +362,113 @@ struct SubCtx {
     bool err;
 };
 
+constexpr int kDecBatch = 8;      // samples decoded per branch-free batch
+
+// FIXED / LPC subframe body.  Called by ALL lanes of the warp (`active` false for lanes without a predictive
+// subframe): the sample loop re-converges the warp at every trip, and a trip is either one batch of kDecBatch
+// Rice codes parsed without data-dependent branches (predicated word merges, see BitReader) followed by the
+// predictor recursion from the register history, or a single sample through the generic path (escape-coded
+// partitions, partition tails, codes longer than 32 bits).
 template <int MAXORD, bool WIDE>
-__device__ __forceinline__ void decode_predictive(SubCtx &S, uint32_t *status) {
+__device__ __forceinline__ void decode_predictive(SubCtx &S, bool active) {
     BitReader &br = S.br;
     const uint32_t n = S.n, order = S.order, wasted = S.wasted;
     int32_t *dst = S.dst;
-    int32_t H[MAXORD + 4];
+    int32_t H[MAXORD + kDecBatch];
     int32_t cf[MAXORD];
 #pragma unroll
-    for (int q = 0; q < MAXORD + 4; q++) H[q] = 0;
+    for (int q = 0; q < MAXORD + kDecBatch; q++) H[q] = 0;
 #pragma unroll
     for (int q = 0; q < MAXORD; q++) cf[q] = 0;
-    // warm-up samples
-    for (uint32_t i = 0; i < order; i++) {
-        const int32_t v = br.get_signed(S.sbps);
-#pragma unroll
-        for (int q = 0; q < MAXORD - 1; q++) H[q] = H[q + 1];
-        H[MAXORD - 1] = v;
-        dst[i] = (int32_t)((uint32_t)v << wasted);
-    }
     int shift = 0;
-    if (S.type == 3) {
-        const uint32_t prec = br.get(4) + 1;
-        if (prec == 16) { S.err = true; return; }
-        const uint32_t sh = br.get(5);
-        if (sh & 16) { S.err = true; return; }
-        shift = (int)sh;
+    uint32_t k = 0, plen = 4, esc = 15, psize = 0, part_left = 0, raw_bits = 0, i = n;
+    bool escape = false;
+    if (active) {
+        // warm-up samples
+        for (uint32_t w = 0; w < order; w++) {
+            const int32_t v = br.get_signed(S.sbps);
 #pragma unroll
-        for (int q = 0; q < MAXORD; q++) if ((uint32_t)q < order) cf[q] = br.get_signed(prec);
-    } else {
-        if (order >= 1) cf[0] = order == 1 ? 1 : order == 2 ? 2 : order == 3 ? 3 : 4;
-        if (MAXORD > 1 && order >= 2) cf[1] = order == 2 ? -1 : order == 3 ? -3 : -6;
-        if (MAXORD > 2 && order >= 3) cf[2] = order == 3 ? 1 : 4;
-        if (MAXORD > 3 && order >= 4) cf[3] = -1;
-    }
-    const uint32_t m = br.get(2);
-    if (m > 1) { S.err = true; return; }
-    const uint32_t plen = m ? 5u : 4u, esc = m ? 31u : 15u;
-    const uint32_t po = br.get(4);
-    const uint32_t psize = n >> po;
-    if ((po > 0 && (n & ((1u << po) - 1))) || psize < order) { S.err = true; return; }
-    uint32_t k = br.get(plen);
-    bool escape = (k == esc);
-    uint32_t raw_bits = escape ? br.get(5) : 0;
-    uint32_t part_left = psize - order;
-    uint32_t i = order;
-    while (part_left == 0 && i < n) {
-        if (psize == 0) { S.err = true; return; }
-        k = br.get(plen); escape = (k == esc); raw_bits = escape ? br.get(5) : 0; part_left = psize;
-    }
-    while (i < n) {
-        if (!escape && part_left >= 4 && (i & 3u) == 0 && i + 4 <= n) {
+            for (int q = 0; q < MAXORD - 1; q++) H[q] = H[q + 1];
+            H[MAXORD - 1] = v;
+            dst[w] = (int32_t)((uint32_t)v << wasted);
+        }
+        br.top_up();
+        if (S.type == 3) {
+            const uint32_t prec = br.get(4) + 1;
+            const uint32_t sh = br.get(5);
+            if (prec == 16 || (sh & 16)) S.err = true;
+            shift = (int)sh;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int32_t r = unzigzag(br.rice_u(k));
-                H[MAXORD + j] = r + lpc_predict<MAXORD, WIDE>(cf, &H[MAXORD - 1 + j], shift);
-            }
-            if (S.aligned16) {
-                *reinterpret_cast<int4 *>(dst + i) = make_int4((int32_t)((uint32_t)H[MAXORD] << wasted), (int32_t)((uint32_t)H[MAXORD + 1] << wasted),
-                                                              (int32_t)((uint32_t)H[MAXORD + 2] << wasted), (int32_t)((uint32_t)H[MAXORD + 3] << wasted));
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; j++) dst[i + j] = (int32_t)((uint32_t)H[MAXORD + j] << wasted);
-            }
-#pragma unroll
-            for (int q = 0; q < MAXORD; q++) H[q] = H[q + 4];
-            part_left -= 4; i += 4;
+            for (int q = 0; q < MAXORD; q++) if ((uint32_t)q < order) cf[q] = br.get_signed(prec);
+            br.top_up();
         } else {
+            if (order >= 1) cf[0] = order == 1 ? 1 : order == 2 ? 2 : order == 3 ? 3 : 4;
+            if (MAXORD > 1 && order >= 2) cf[1] = order == 2 ? -1 : order == 3 ? -3 : -6;
+            if (MAXORD > 2 && order >= 3) cf[2] = order == 3 ? 1 : 4;
+            if (MAXORD > 3 && order >= 4) cf[3] = -1;
+        }
+        const uint32_t m = br.get(2);
+        const uint32_t po = br.get(4);
+        plen = m ? 5u : 4u; esc = m ? 31u : 15u;
+        psize = n >> po;
+        if (m > 1 || (po > 0 && (n & ((1u << po) - 1))) || psize < order) S.err = true;
+        if (!S.err) {
+            k = br.get(plen);
+            escape = (k == esc);
+            raw_bits = escape ? br.get(5) : 0;
+            part_left = psize - order;
+            i = order;
+            while (part_left == 0 && i < n) {
+                if (psize == 0) { S.err = true; break; }
+                k = br.get(plen); escape = (k == esc); raw_bits = escape ? br.get(5) : 0; part_left = psize;
+            }
+            if (S.err) i = n;
+        }
+    }
+    while (__any_sync(0xFFFFFFFFu, i < n)) {
+        if (i >= n) continue;
+        br.top_up();
+        bool did = false;
+        if (!escape && part_left >= (uint32_t)kDecBatch && (i & 3u) == 0) {       // (i & 3): keep the 16-byte stores aligned
+            // ---- batch: kDecBatch codes, no data-dependent branch; redone sample by sample if one is longer than 32 bits ----
+            const BitReader snap = br;
+            const uint32_t k1 = k + 1;
+            uint32_t maxlen = 0, u[kDecBatch];
+#pragma unroll
+            for (int j = 0; j < kDecBatch; j++) {
+                const uint32_t z = (uint32_t)__clz(br.hi);
+                const uint32_t len = z + k1;
+                maxlen = max(maxlen, len);
+                const uint32_t t = __funnelshift_lc(0u, br.hi, z + 1);      // hi << (z+1), 0 when z+1 == 32
+                u[j] = (z << k) | __funnelshift_lc(t, 0u, k);               // | t >> (32-k), 0 when k == 0
+                br.hi = __funnelshift_lc(br.lo, br.hi, len);
+                br.lo = __funnelshift_lc(0u, br.lo, len);
+                br.vb -= (int32_t)len;
+                br.merge_word_predicated();
+            }
+            if (maxlen <= 32) {
+#pragma unroll
+                for (int j = 0; j < kDecBatch; j++)
+                    H[MAXORD + j] = unzigzag(u[j]) + lpc_predict<MAXORD, WIDE>(cf, &H[MAXORD - 1 + j], shift);
+                if (S.aligned16) {
+#pragma unroll
+                    for (int q = 0; q < kDecBatch / 4; q++)
+                        *reinterpret_cast<int4 *>(dst + i + 4 * q) =
+                            make_int4((int32_t)((uint32_t)H[MAXORD + 4 * q] << wasted), (int32_t)((uint32_t)H[MAXORD + 4 * q + 1] << wasted),
+                                      (int32_t)((uint32_t)H[MAXORD + 4 * q + 2] << wasted), (int32_t)((uint32_t)H[MAXORD + 4 * q + 3] << wasted));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kDecBatch; j++) dst[i + j] = (int32_t)((uint32_t)H[MAXORD + j] << wasted);
+                }
+#pragma unroll
+                for (int q = 0; q < MAXORD; q++) H[q] = H[q + kDecBatch];
+                part_left -= kDecBatch; i += kDecBatch;
+                did = true;
+            } else {
+                br = snap;
+            }
+        }
+        if (!did) {
             const int32_t r = escape ? br.get_signed(raw_bits) : unzigzag(br.rice_u(k));
             const int32_t v = r + lpc_predict<MAXORD, WIDE>(cf, &H[MAXORD - 1], shift);
 #pragma unroll
@@ -526,6 +476,7 @@ __device__ __forceinline__ void decode_predictive(SubCtx &S, uint32_t *status) {
             H[MAXORD - 1] = v;
             dst[i] = (int32_t)((uint32_t)v << wasted);
             part_left--; i++;
+            if (br.overrun()) { S.err = true; i = n; }
         }
         if (part_left == 0 && i < n) {
             k = br.get(plen); escape = (k == esc); raw_bits = escape ? br.get(5) : 0; part_left = psize;
@@ -534,18 +485,21 @@ __device__ __forceinline__ void decode_predictive(SubCtx &S, uint32_t *status) {
 }
 
 template <bool BIGORDER>
-__global__ void __launch_bounds__(kDecThreads)
+__global__ void __launch_bounds__(kDecThreads, BIGORDER ? 1 : 6)
 k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__restrict__ streams, uint32_t n_streams,
                    uint32_t channels, uint32_t bps, uint32_t blocksize, uint32_t total_frames,
                    const unsigned long long *__restrict__ frame_pos, const uint32_t *__restrict__ sub_bitoff,
                    int32_t *__restrict__ audio, uint8_t *__restrict__ frame_chassign, uint32_t *__restrict__ status) {
-    __shared__ uint32_t s_ring[kRing * kDecThreads];
+    __shared__ __align__(256) uint4 s_ring[kSkimRing * kDecThreads];
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
     const uint32_t total_sub = total_frames * channels;
     bool alive = s < total_sub;
     const uint32_t f = alive ? s / channels : 0, c = alive ? s - f * channels : 0;
     SubCtx S;
     S.err = false; S.type = 0; S.order = 0; S.n = 0; S.wasted = 0; S.sbps = bps; S.dst = audio; S.aligned16 = false;
+    S.br.gq = (const uint4 *)bytes; S.br.sbase = (uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x * kSkimRing);
+    S.br.swz = (lane & 15u) << 4; S.br.wnext = 2; S.br.cissue = 0; S.br.qlast = 0; S.br.hi = S.br.lo = S.br.nx = S.br.nx2raw = 0; S.br.vb = 64;
     FrameLoc L; L.ok = false; L.start = L.end = 0; L.k = 0; L.n = 0;
     uint32_t hdr_bytes = 0;
     if (alive) {
@@ -567,7 +521,7 @@ k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__rest
                 bit0 = (L.start + hdr_bytes) * 8;
             }
             if (alive) {
-                S.br.init((uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x), bytes, bit0, L.end);
+                S.br.init(S.br.sbase, lane, bytes, bit0, L.end);
                 S.n = L.n;
                 const int64_t idx = st.audio_base + (int64_t)c * (int64_t)st.n_samples + (int64_t)L.k * blocksize;
                 S.dst = audio + idx;
@@ -604,19 +558,22 @@ k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__rest
             const int32_t v = (int32_t)((uint32_t)S.br.get_signed(S.sbps) << S.wasted);
             for (uint32_t i = 0; i < S.n; i++) S.dst[i] = v;
         } else if (S.type == 1) {
-            for (uint32_t i = 0; i < S.n; i++) S.dst[i] = (int32_t)((uint32_t)S.br.get_signed(S.sbps) << S.wasted);
+            for (uint32_t i = 0; i < S.n; i++) {
+                if ((i & 3u) == 0) S.br.top_up();
+                S.dst[i] = (int32_t)((uint32_t)S.br.get_signed(S.sbps) << S.wasted);
+            }
         } else if (!BIGORDER && S.order > 12) {
             S.err = true;
             atomicAdd(&status[4], 1u);
-        } else if (BIGORDER) {
-            decode_predictive<32, true>(S, status);
-        } else if (cls <= 4) {
-            if (wide) decode_predictive<4, true>(S, status); else decode_predictive<4, false>(S, status);
-        } else if (cls <= 8) {
-            if (wide) decode_predictive<8, true>(S, status); else decode_predictive<8, false>(S, status);
-        } else {
-            if (wide) decode_predictive<12, true>(S, status); else decode_predictive<12, false>(S, status);
         }
+    }
+    {
+        // every lane of the warp enters the same instantiation (the sample loop is warp-synchronous)
+        const bool act = run && S.type >= 2 && (BIGORDER || S.order <= 12);
+        if (BIGORDER) decode_predictive<32, true>(S, act);
+        else if (cls <= 4) { if (wide) decode_predictive<4, true>(S, act); else decode_predictive<4, false>(S, act); }
+        else if (cls <= 8) { if (wide) decode_predictive<8, true>(S, act); else decode_predictive<8, false>(S, act); }
+        else { if (wide) decode_predictive<12, true>(S, act); else decode_predictive<12, false>(S, act); }
     }
     if (alive) {
         if (!S.err && c + 1 == channels) {
