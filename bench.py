@@ -173,7 +173,26 @@ def run_cpu(workload: str, n_tiles: int, threads: int, device, repeats: int = 1)
     return best_e, best_d, desc, samples
 
 
+_REAL_STDOUT = None
+
+
+def emit_line(obj):
+    """The ONE JSON line of the contract, on the process's real stdout."""
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    # Libraries (NCCL's version banner, torch warnings) sometimes write to fd 1: route everything except the
+    # final JSON line to stderr so stdout carries exactly one line.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -218,7 +237,7 @@ def main():
             "e2e": {"value": e, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        emit_line(line)
         return 0
 
     # ------------------------------------------------------------------ our arm
@@ -273,15 +292,21 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = L.frb_launch_count()
-    k_ms = []
+    enc_prof, dec_prof = {}, {}
+
+    def prof(acc, slots):
+        """Device time of the library's bracketed kernels for the step that just ran (CUDA events on its stream)."""
+        for name, which in slots.items():
+            ms = nat.C.c_float(0)
+            if L.frb_profile_last_ms(which, nat.C.byref(ms)) == 0:
+                acc.setdefault(name, []).append(ms.value)
+
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
     for _ in range(args.steps):
         encode_step()
-        ms = nat.C.c_float(0)
-        if L.frb_profile_last_ms(0, nat.C.byref(ms)) == 0:
-            k_ms.append(ms.value)
+        prof(enc_prof, {"k_enc_code": 0, "k_enc_stats": 4, "k_emit_frames": 2, "subframe_analysis_total": 6})
     ev1.record()
     barrier()
     launches = L.frb_launch_count() - launches0
@@ -293,7 +318,6 @@ def main():
     payload = torch.cat([enc.payload, torch.zeros(64, dtype=torch.uint8, device=dev)])
     out = torch.zeros(raster.numel() * raster.element_size(), dtype=torch.uint8, device=dev).view(raster.dtype).reshape(raster.shape)
     scale = 32767.0 if enc.bits_per_sample == 16 else 8388607.0
-    dk_ms = []
 
     def decode_step():
         audio, base, status = eng.decode_streams(payload, enc.offsets, enc.sizes, enc.n_samples, enc.sample_rates,
@@ -311,9 +335,7 @@ def main():
     ev2.record()
     for _ in range(args.steps):
         decode_step()
-        ms = nat.C.c_float(0)
-        if L.frb_profile_last_ms(1, nat.C.byref(ms)) == 0:
-            dk_ms.append(ms.value)
+        prof(dec_prof, {"k_decode_subframes": 1, "k_skim_subframes": 5, "k_sync_scan": 3})
     ev3.record()
     barrier()
     dec_launches = L.frb_launch_count() - dlaunch0
@@ -364,13 +386,22 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
 
+    traffic = {}
+    tf = ROOT / "profiles" / "traffic.json"          # dram__bytes_read+write per launch from the committed ncu --set full captures
+    if tf.exists():
+        traffic = json.loads(tf.read_text()).get(args.workload, {})
+
     def roof(kernel_ms_list, alg_bytes, kernel, note):
         if not kernel_ms_list:
             return None
         kms = float(np.mean(kernel_ms_list))
         ach = alg_bytes / (kms * 1e-3) / 1e9
         return {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": None, "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "note": note}
+                "traffic": traffic.get(kernel) if args.scale_div == 1 else None, "kernel_ms": kms,
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "note": note}
+
+    def mean_ms(acc):
+        return {k: float(np.mean(v)) for k, v in acc.items()}
 
     enc_alg = samples_local * 4 + comp_bytes           # int32 audio read + compressed bytes produced
     dec_alg = comp_bytes + samples_local * 4           # compressed bytes consumed + int32 audio written
@@ -395,16 +426,20 @@ def main():
         "lossless_roundtrip_checked": lossless,
         "decode": {"value": total_samples / (dec_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": dec_ms,
                    "gpu_launches": int(dec_launches),
-                   "roofline": roof(dk_ms, dec_alg, "k_decode_frames", "compressed bytes read + int32 audio written")},
-        "roofline": roof(k_ms, enc_alg, "k_encode_subframes",
-                         "int32 audio read + compressed bytes written; the kernel is issue-bound, not HBM-bound (see DESIGN.md)"),
+                   "kernels_ms": mean_ms(dec_prof),
+                   "roofline": roof(dec_prof.get("k_decode_subframes"), dec_alg, "k_decode_subframes",
+                                    "compressed bytes read + int32 audio written; issue/latency-bound (Rice parse is a serial chain per subframe)")},
+        "kernels_ms": mean_ms(enc_prof),
+        "roofline": roof(enc_prof.get("k_enc_code") or enc_prof.get("subframe_analysis_total"), enc_alg, "k_enc_code",
+                         "int32 audio read + compressed bytes written by the dominant encode kernel (residual, Rice search, bit packing); "
+                         "issue-bound, not HBM-bound (see DESIGN.md)"),
         "cpu_baseline": cpu,
         "e2e": {"value": total_samples / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(raster.numel() * raster.element_size()), "d2h_bytes_per_step": int(nout)},
         "gpu_launches": int(tot[1]),
         "clocks": clocks,
     }
-    print(json.dumps(line))
+    emit_line(line)
     if world > 1:
         dist.barrier()
     return 0

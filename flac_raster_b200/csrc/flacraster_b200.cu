@@ -53,7 +53,7 @@ static int ensure_tables_impl() {
             T.k2032[256 + b] = (uint16_t)gf16_mul((uint32_t)b, K2);
         }
         for (int i = 0; i < 2048; i++) T.xp[i] = (uint16_t)gf16_xpow8((uint64_t)i);
-        FRB_CUDA(cudaMemcpyToSymbol(c_crct, &T, sizeof T));
+        FRB_CUDA(cudaMemcpyToSymbol(d_crct, &T, sizeof T));
     }
     if (dev >= 0 && dev < 64) done[dev] = true;
     return FRB_OK;
@@ -85,7 +85,7 @@ extern "C" uint64_t frb_launch_count(void) { return frb::g_launches.load(); }
 
 extern "C" int frb_profile_enable(int on) { frb::g_prof_on = on != 0; return FRB_OK; }
 extern "C" int frb_profile_last_ms(int which, float *ms) {
-    if (which < 0 || which > 3 || !ms) return FRB_ERR_INVALID_ARG;
+    if (which < 0 || which > 7 || !ms) return FRB_ERR_INVALID_ARG;
     frb::ProfSlot &p = frb::g_prof[which];
     if (!p.valid) return FRB_ERR_INVALID_ARG;
     FRB_CUDA(cudaEventSynchronize(p.b));

@@ -35,7 +35,7 @@ constexpr int kNumSMs = 148;   // B200
 // ---- optional kernel timing (bench roofline) ---------------------------------
 struct ProfSlot { cudaEvent_t a = nullptr, b = nullptr; bool valid = false; };
 static bool g_prof_on = false;
-static ProfSlot g_prof[4];
+static ProfSlot g_prof[8];
 inline void prof_begin(int which, cudaStream_t s) {
     if (!g_prof_on) return;
     ProfSlot &p = g_prof[which];

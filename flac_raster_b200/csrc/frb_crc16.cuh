@@ -11,7 +11,11 @@ struct CrcTables {
     uint16_t k2032[512];     // multiply by x^(8*2032) (128-thread CTAs: 128 chunks per row)
     uint16_t xp[2048];       // xp[i] = x^(8*i) mod P
 };
-__constant__ CrcTables c_crct;
+// The tables live in global memory: every CTA copies them to shared memory with coalesced 16-byte loads (L2
+// hits).  They used to sit in __constant__ memory, where the copy's per-thread addresses serialise in the
+// constant cache (32 passes per warp instruction): ~1 us per CTA, which dominated k_emit_frames for
+// single-channel frames (7.4 ms for 262 144 frames of C5, profiles/r01_bench_c5_v1.json).
+__device__ __align__(16) CrcTables d_crct;
 
 __device__ __forceinline__ uint32_t crc16_word(uint32_t crc, uint32_t w, const uint16_t *s4) {
     const uint32_t x = w ^ (crc << 16);
@@ -26,9 +30,10 @@ __device__ __forceinline__ uint32_t crc16_words4(uint32_t acc, const uint32_t (&
     return acc;
 }
 __device__ __forceinline__ void crc_tables_to_smem(CrcTables *dst) {
-    const uint32_t *s = reinterpret_cast<const uint32_t *>(&c_crct);
-    uint32_t *d = reinterpret_cast<uint32_t *>(dst);
-    for (uint32_t i = threadIdx.x; i < sizeof(CrcTables) / 4; i += blockDim.x) d[i] = s[i];
+    static_assert(sizeof(CrcTables) % 16 == 0, "vector copy");
+    const uint4 *s = reinterpret_cast<const uint4 *>(&d_crct);
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+    for (uint32_t i = threadIdx.x; i < sizeof(CrcTables) / 16; i += blockDim.x) d[i] = __ldg(s + i);
 }
 __device__ __forceinline__ void crc_mask_head(uint32_t (&w)[4], uint32_t head) {
 #pragma unroll
@@ -92,18 +97,19 @@ __global__ void __launch_bounds__(256)
 k_crc16_frames(const uint8_t *__restrict__ bytes, const DecStreamDev *__restrict__ streams, uint32_t n_streams,
                uint32_t blocksize, uint32_t total_frames, const unsigned long long *__restrict__ frame_pos,
                uint32_t *__restrict__ status) {
-    __shared__ CrcTables T;
+    __shared__ __align__(16) CrcTables T;
     crc_tables_to_smem(&T);
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const uint32_t f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (f >= total_frames) return;                        // warp-uniform
-    DecStreamDev st;
-    const FrameLoc L = locate_frame(streams, n_streams, blocksize, f, frame_pos, &st);
-    if (!L.ok) return;                                    // counted as missing by the decoder
-    const uint32_t crc = warp_crc16(bytes, L.start, L.end - 2, &T, lane);
-    if (lane == 0) {
-        const uint32_t want = ((uint32_t)bytes[L.end - 2] << 8) | bytes[L.end - 1];
-        if (crc != want) atomicAdd(&status[1], 1u);
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; f < total_frames; f += warps) {    // warp-uniform
+        DecStreamDev st;
+        const FrameLoc L = locate_frame(streams, n_streams, blocksize, f, frame_pos, &st);
+        if (!L.ok) continue;                              // counted as missing by the decoder
+        const uint32_t crc = warp_crc16(bytes, L.start, L.end - 2, &T, lane);
+        if (lane == 0) {
+            const uint32_t want = ((uint32_t)bytes[L.end - 2] << 8) | bytes[L.end - 1];
+            if (crc != want) atomicAdd(&status[1], 1u);
+        }
     }
 }

@@ -244,9 +244,11 @@ extern "C" int frb_decode_batch(const frb_decode_params *p, const frb_decode_str
             static uint32_t skim_lanes = 0;
             if (!skim_lanes) { const char *e = getenv("FRB_SKIM_LANES"); skim_lanes = e ? (uint32_t)atoi(e) : 32u; if (skim_lanes < 1 || skim_lanes > 32) skim_lanes = 32; }
             const uint32_t frames_per_cta = (kDecThreads / 32) * skim_lanes;
+            prof_begin(5, s);
             k_skim_subframes<<<(uint32_t)((total_frames + frames_per_cta - 1) / frames_per_cta), kDecThreads, 0, s>>>(
                 d_bytes, w.streams, p->n_streams, p->channels, p->bps, p->blocksize, (uint32_t)total_frames, w.frame_pos,
                 w.sub_bitoff, w.chassign, d_status, skim_lanes);
+            prof_end(5, s);
             FRB_LAUNCH_CHECK("k_skim_subframes");
             sub_bitoff = w.sub_bitoff;
         }
@@ -265,7 +267,9 @@ extern "C" int frb_decode_batch(const frb_decode_params *p, const frb_decode_str
     }
     if (p->verify_crc16) {
         const uint64_t threads = total_frames * 32;
-        k_crc16_frames<<<(uint32_t)((threads + 255) / 256), 256, 0, s>>>(d_bytes, w.streams, p->n_streams, p->blocksize,
+        uint32_t crc_grid = (uint32_t)((threads + 255) / 256);
+        if (crc_grid > (uint32_t)kNumSMs * 8) crc_grid = kNumSMs * 8;         // persistent: the tables are staged once per CTA
+        k_crc16_frames<<<crc_grid, 256, 0, s>>>(d_bytes, w.streams, p->n_streams, p->blocksize,
                                                                         (uint32_t)total_frames, w.frame_pos, d_status);
         FRB_LAUNCH_CHECK("k_crc16_frames");
     }

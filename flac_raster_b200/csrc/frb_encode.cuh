@@ -864,10 +864,12 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
               const uint32_t *__restrict__ slots, uint32_t slot_words, const uint32_t *__restrict__ frame_bytes,
               const unsigned long long *__restrict__ frame_off, uint8_t *__restrict__ out, uint64_t out_capacity,
               uint32_t *__restrict__ err_flag) {
-    __shared__ EmitShared S;
-    const uint32_t f = blockIdx.x;
+    __shared__ __align__(16) EmitShared S;
     const int tid = threadIdx.x;
     crc_tables_to_smem(&S.T);
+    // persistent CTAs: the CRC tables (8 KB) are staged once, then the CTA walks frames with stride gridDim.x
+    for (uint32_t f = blockIdx.x; f < total_frames; f += gridDim.x) {
+    __syncthreads();                                      // tables staged / previous frame's shared state consumed
     uint32_t lo = 0, hi = n_streams - 1;
     while (lo < hi) {
         uint32_t mid = (lo + hi + 1) >> 1;
@@ -913,7 +915,7 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
         if (((pos + 7) >> 3) + 2 != total || dst_off + total > out_capacity) atomicExch(err_flag, 1u);
     }
     __syncthreads();
-    if (dst_off + total > out_capacity) return;
+    if (dst_off + total > out_capacity) continue;
     const uint32_t payload = total - 2;                        // bytes covered by the CRC-16
     const uint32_t hdr_bits = S.seg_start[0], end_bits = S.seg_start[channels];
     const uint32_t *slots_f = slots + (size_t)f * channels * slot_words;
@@ -977,6 +979,7 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
         for (int w = 0; w < kEmitThreads / 32; w++) crc ^= S.red[w];
         dst[payload] = (uint8_t)(crc >> 8);
         dst[payload + 1] = (uint8_t)crc;
+    }
     }
 }
 
@@ -1108,7 +1111,7 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const int32_t *d_a
             FRB_CUDA(cudaStreamSynchronize(s));
         }
     }
-    prof_begin(0, s);
+    prof_begin(6, s);
     if (fast && slow.size() < total_tasks) {
         const uint32_t windows = (uint32_t)cfg.windows, max_lpc = (uint32_t)cfg.max_lpc_order;
         const uint32_t n_cands = max_lpc == 0 ? 0u : windows == 1 ? 1u : windows == 2 ? 3u : 9u;     // LPC candidates
@@ -1116,12 +1119,14 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const int32_t *d_a
         const dim3 grid((uint32_t)frames, p->channels);
         k_frame_table<<<(uint32_t)((frames + 255) / 256), 256, 0, s>>>(w.streams, p->n_streams, p->blocksize, (uint32_t)frames, w.frame_table);
         FRB_LAUNCH_CHECK("k_frame_table");
+        prof_begin(4, s);
 #define FRB_STATS(W, NL) k_enc_stats<W, NL><<<grid, kEncThreads, 0, s>>>(w.frame_table, p->channels, p->bps, windows, (uint32_t)cfg.max_po, d_audio, \
             w.window, w.stats, w.autoc, w.fx_fin)
         if (max_lpc == 0) { if (wide) FRB_STATS(true, 0); else FRB_STATS(false, 0); }
         else if (max_lpc <= 8) { if (wide) FRB_STATS(true, 9); else FRB_STATS(false, 9); }
         else { if (wide) FRB_STATS(true, 13); else FRB_STATS(false, 13); }
 #undef FRB_STATS
+        prof_end(4, s);
         FRB_LAUNCH_CHECK("k_enc_stats");
         k_enc_fixed<<<(total_tasks + 3) / 4, 128, 0, s>>>(w.frame_table, p->channels, p->bps, (uint32_t)cfg.max_po, total_tasks, d_audio,
                                                         w.stats, w.fx_fin);
@@ -1135,12 +1140,14 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const int32_t *d_a
 #undef FRB_MODEL
         FRB_LAUNCH_CHECK("k_enc_model");
         }
+        prof_begin(0, s);
         if (wide)
             k_enc_code<true><<<grid, kEncThreads, 0, s>>>(w.frame_table, p->channels, p->bps, (uint32_t)cfg.max_po, n_cands, d_audio,
                                                           w.stats, w.cands, slot_words, w.slots, w.sub_bits);
         else
             k_enc_code<false><<<grid, kEncThreads, 0, s>>>(w.frame_table, p->channels, p->bps, (uint32_t)cfg.max_po, n_cands, d_audio,
                                                            w.stats, w.cands, slot_words, w.slots, w.sub_bits);
+        prof_end(0, s);
         FRB_LAUNCH_CHECK("k_enc_code");
     }
     if (!fast || !slow.empty()) {
@@ -1150,7 +1157,7 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const int32_t *d_a
             fast ? w.slow_tasks : nullptr);
         FRB_LAUNCH_CHECK("k_encode_subframes");
     }
-    prof_end(0, s);
+    prof_end(6, s);
     k_frame_sizes<<<(uint32_t)((frames + 255) / 256), 256, 0, s>>>(w.streams, p->n_streams, p->channels, p->blocksize,
                                                                  (uint32_t)frames, w.sub_bits, w.frame_bytes);
     FRB_LAUNCH_CHECK("k_frame_sizes");
@@ -1184,7 +1191,7 @@ extern "C" int frb_encode_emit(const frb_encode_params *p, void *d_workspace, si
     k_set_out_offsets<<<(p->n_streams + 255) / 256, 256, 0, s>>>(w.streams, w.out_offs, p->n_streams);
     FRB_LAUNCH_CHECK("k_set_out_offsets");
     prof_begin(2, s);
-    k_emit_frames<<<(uint32_t)frames, kEmitThreads, 0, s>>>(w.streams, p->n_streams, p->channels, p->bps, p->blocksize,
+    k_emit_frames<<<(uint32_t)std::min<uint64_t>(frames, (uint64_t)kNumSMs * 16), kEmitThreads, 0, s>>>(w.streams, p->n_streams, p->channels, p->bps, p->blocksize,
                                                            (uint32_t)frames, w.sub_bits, w.slots, slot_words_for(p->blocksize, p->bps),
                                                            w.frame_bytes, w.frame_off, d_out, (uint64_t)out_capacity, w.err_flag);
     prof_end(2, s);

@@ -161,17 +161,24 @@ class Engine:
 
     # ------------------------------------------------------------------ encode, host buffers (pipelined)
     @staticmethod
-    def _row_groups(tiles: np.ndarray) -> List[Tuple[int, int, int, int]]:
-        """Consecutive runs of tiles that share a row band: [(first, last+1, row0, row1)].  A row-major tile grid
-        (cli.py:553-556) gives one group per tile row; any other ordering still works (more, smaller groups)."""
-        groups = []
+    def _row_groups(tiles: np.ndarray, row_bytes: int = 0, target_bytes: int = 0) -> List[Tuple[int, int, int, int]]:
+        """Consecutive runs of tiles that cover one band of rows: [(first, last+1, row0, row1)].  A row-major tile
+        grid (cli.py:553-556) gives one run per tile row; vertically adjacent runs are merged until a group holds
+        about `target_bytes` of raster (many small tiles would otherwise mean many tiny pipeline stages)."""
+        ro = tiles["row_off"].astype(np.int64)
+        re = ro + tiles["h"].astype(np.int64)
+        groups: List[Tuple[int, int, int, int]] = []
         i, n = 0, len(tiles)
         while i < n:
-            r0, r1 = int(tiles[i]["row_off"]), int(tiles[i]["row_off"]) + int(tiles[i]["h"])
             j = i + 1
-            while j < n and int(tiles[j]["row_off"]) == r0 and int(tiles[j]["row_off"]) + int(tiles[j]["h"]) == r1:
+            while j < n and ro[j] == ro[i] and re[j] == re[i]:
                 j += 1
-            groups.append((i, j, r0, r1))
+            g = (i, j, int(ro[i]), int(re[i]))
+            if groups and target_bytes and groups[-1][3] == g[2] and (groups[-1][3] - groups[-1][2]) * row_bytes < target_bytes:
+                p = groups[-1]
+                groups[-1] = (p[0], j, p[2], g[3])
+            else:
+                groups.append(g)
             i = j
         return groups
 
@@ -184,18 +191,20 @@ class Engine:
         return t
 
     def encode_tiles_host(self, host_raster: torch.Tensor, tiles: np.ndarray, level: int = 5, blocksize: int = 4096,
-                          host_out: Optional[torch.Tensor] = None) -> EncodedTiles:
+                          host_out: Optional[torch.Tensor] = None, group_bytes: Optional[int] = None) -> EncodedTiles:
         """Host (bands,H,W) raster in, host frames out: the end-to-end form of encode_tiles.
 
         The reference walks tiles serially (cli.py:553-622).  Here the tile rows are pipelined over three
         streams so PCIe and the GPU work concurrently: H2D of tile row g+1 (double-buffered slab) overlaps
         the encode of row g, which overlaps the D2H of row g-1's frames (double-buffered payload).
         `host_raster` and `host_out` should be pinned; the returned EncodedTiles.payload is a CPU tensor
-        (a view of host_out)."""
+        (a view of host_out, or of an engine-owned pinned buffer that the next call reuses).  `group_bytes`: raster
+        bytes per pipeline stage (default: a twelfth of the raster, at least 32 MiB; 0 = one stage per tile row)."""
         assert not host_raster.is_cuda and host_raster.is_contiguous() and host_raster.dim() == 3
         bands, H, W = host_raster.shape
         esize = host_raster.element_size()
-        groups = self._row_groups(tiles)
+        total_bytes = int(host_raster.numel()) * esize
+        groups = self._row_groups(tiles, bands * W * esize, group_bytes if group_bytes is not None else max(total_bytes // 12, 32 << 20))
         max_rows = max(r1 - r0 for _, _, r0, r1 in groups)
         if host_out is None:
             frames = int(sum((int(t["h"]) * int(t["w"]) + blocksize - 1) // blocksize for t in tiles))

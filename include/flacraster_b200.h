@@ -64,8 +64,10 @@ int frb_device_count(int *count);
 uint64_t frb_launch_count(void);
 
 /* Optional per-kernel timing: when enabled the library brackets its dominant kernels with
- * cudaEvents on the caller's stream.  which: 0 k_encode_subframes, 1 k_decode_frames,
- * 2 k_emit_frames, 3 k_sync_scan.  frb_profile_last_ms synchronises on the end event. */
+ * cudaEvents on the caller's stream.  which: 0 k_enc_code (Rice search + packing, the dominant
+ * encode kernel), 1 k_decode_subframes, 2 k_emit_frames, 3 k_sync_scan, 4 k_enc_stats,
+ * 5 k_skim_subframes, 6 whole subframe analysis (stats + fixed + model + code + tail frames).
+ * frb_profile_last_ms synchronises on the end event. */
 int frb_profile_enable(int on);
 int frb_profile_last_ms(int which, float *ms);
 

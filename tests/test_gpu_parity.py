@@ -396,8 +396,8 @@ def test_host_pipeline_equals_device_path(nat, torch_cuda):
     ref = eng.encode_tiles(raster, tiles, 5)
     ref_bytes = ref.payload.cpu().numpy().copy()
     host = raster.cpu().pin_memory()
-    for _ in range(2):                               # second pass reuses slabs/payload buffers
-        got = eng.encode_tiles_host(host, tiles, 5)
+    for gb in (0, 0, None):                          # 0: one stage per tile row (second pass reuses slabs/payload buffers)
+        got = eng.encode_tiles_host(host, tiles, 5, group_bytes=gb)
         assert not got.payload.is_cuda
         assert np.array_equal(got.sizes, ref.sizes) and np.array_equal(got.offsets, ref.offsets)
         assert np.array_equal(got.minmax, ref.minmax)
