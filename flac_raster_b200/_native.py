@@ -14,7 +14,7 @@ from pathlib import Path
 import numpy as np
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "lib" / "libflacraster_b200.so"
+LIB_PATH = Path(os.environ["FRB_LIB_PATH"]) if os.environ.get("FRB_LIB_PATH") else _PKG / "lib" / "libflacraster_b200.so"   # override: kernel variant experiments
 CSRC = _PKG / "csrc"
 
 FRB_OK = 0

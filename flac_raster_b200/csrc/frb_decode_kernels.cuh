@@ -484,8 +484,11 @@ __device__ __forceinline__ void decode_predictive(SubCtx &S, bool active) {
     }
 }
 
+#ifndef FRB_DEC_MINB
+#define FRB_DEC_MINB 4
+#endif
 template <bool BIGORDER>
-__global__ void __launch_bounds__(kDecThreads, BIGORDER ? 1 : 6)
+__global__ void __launch_bounds__(kDecThreads, BIGORDER ? 1 : FRB_DEC_MINB)
 k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__restrict__ streams, uint32_t n_streams,
                    uint32_t channels, uint32_t bps, uint32_t blocksize, uint32_t total_frames,
                    const unsigned long long *__restrict__ frame_pos, const uint32_t *__restrict__ sub_bitoff,

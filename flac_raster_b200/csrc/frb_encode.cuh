@@ -931,8 +931,21 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
     auto do_chunk = [&](uint32_t c, uint32_t (&w)[4], uint32_t nbytes /* valid bytes from the chunk start, 16 = full */) {
         const int32_t b0 = (int32_t)(16 * c) - (int32_t)a;    // frame byte of the chunk's first byte (negative in the head chunk)
         if (b0 >= 0 && nbytes == 16) {
+            const uint32_t P = 8u * (uint32_t)b0;
+            // common case: all 128 bits lie inside one subframe -> one segment lookup, five slot words, four funnel shifts
+            uint32_t ch = 0;
+            while (ch + 1 < channels && S.seg_start[ch + 1] <= P) ch++;
+            if (P >= hdr_bits && P + 128 <= S.seg_start[ch + 1]) {
+                const uint32_t o = P - S.seg_start[ch];
+                const uint32_t *sl = slots_f + (size_t)ch * slot_words + (o >> 5);
+                const uint32_t sh = o & 31;
+                uint32_t v0 = __ldg(sl), v1 = __ldg(sl + 1), v2 = __ldg(sl + 2), v3 = __ldg(sl + 3), v4 = __ldg(sl + 4);
+                w[0] = __funnelshift_l(v1, v0, sh); w[1] = __funnelshift_l(v2, v1, sh);
+                w[2] = __funnelshift_l(v3, v2, sh); w[3] = __funnelshift_l(v4, v3, sh);
+            } else {
 #pragma unroll
-            for (int q = 0; q < 4; q++) w[q] = emit_gather32(8u * (uint32_t)b0 + 32u * q, S, channels, hdr_bits, end_bits, slots_f, slot_words);
+                for (int q = 0; q < 4; q++) w[q] = emit_gather32(P + 32u * q, S, channels, hdr_bits, end_bits, slots_f, slot_words);
+            }
             *reinterpret_cast<uint4 *>(g0 + 16 * (size_t)c) = make_uint4(bswap32(w[0]), bswap32(w[1]), bswap32(w[2]), bswap32(w[3]));
         } else {
 #pragma unroll

@@ -249,8 +249,14 @@ struct StatsShared {
     double ac[8][kLags];
 };
 
+#ifndef FRB_STATS_MINB
+#define FRB_STATS_MINB 4
+#endif
+#ifndef FRB_CODE_MINB
+#define FRB_CODE_MINB 4
+#endif
 template <bool WIDE, int NLAGS>
-__global__ void __launch_bounds__(kEncThreads, (NLAGS > 9 || WIDE) ? 2 : 3)
+__global__ void __launch_bounds__(kEncThreads, (NLAGS > 9 || WIDE) ? 2 : FRB_STATS_MINB)
 k_enc_stats(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps_stream,
             uint32_t windows, uint32_t max_po_cfg, const int32_t *__restrict__ audio,
             const float *__restrict__ window, EncSubStats *__restrict__ stats, double *__restrict__ autoc_out,
@@ -741,7 +747,7 @@ __device__ __noinline__ bool residual_overflows(const int32_t *__restrict__ src,
 }
 
 template <bool WIDE>
-__global__ void __launch_bounds__(kEncThreads, WIDE ? 2 : 3)
+__global__ void __launch_bounds__(kEncThreads, WIDE ? 2 : FRB_CODE_MINB)
 k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps_stream,
            uint32_t max_po_cfg, uint32_t n_cands, const int32_t *__restrict__ audio,
            const EncSubStats *__restrict__ stats, const EncCand *__restrict__ cands, uint32_t slot_words,
