@@ -79,7 +79,7 @@ _EXPORTS = [
     "frb_version", "frb_error_string", "frb_last_cuda_error", "frb_device_count", "frb_launch_count",
     "frb_profile_enable", "frb_profile_last_ms",
     "frb_minmax_tiles", "frb_normalize_tiles", "frb_denormalize_tiles", "frb_sample_map_workspace_size",
-    "frb_minmax_flat", "frb_normalize_flat", "frb_denormalize_flat",
+    "frb_minmax_flat", "frb_normalize_flat", "frb_denormalize_flat", "frb_selftest_division",
     "frb_encode_workspace_size", "frb_encode_analyse", "frb_encode_emit",
     "frb_decode_workspace_size", "frb_decode_batch", "frb_probe_stream",
     "frb_host_encode", "frb_host_decode",
@@ -117,6 +117,7 @@ def lib():
     L.frb_normalize_tiles.argtypes = [vp, i32, u32, u32, u32, vp, u32, vp, i32, vp, vp, vp, sz, vp]
     L.frb_sample_map_workspace_size.argtypes = [u32, C.POINTER(sz)]
     L.frb_denormalize_tiles.argtypes = [vp, vp, vp, u32, vp, C.c_double, vp, i32, u32, u32, u32, vp, sz, vp]
+    L.frb_selftest_division.argtypes = [C.c_double, C.c_int64, C.c_int64, C.POINTER(C.c_uint64), vp]
     L.frb_minmax_flat.argtypes = [vp, i32, u64, vp, vp]
     L.frb_normalize_flat.argtypes = [vp, i32, u64, C.c_double, C.c_double, i32, vp, i32, vp]
     L.frb_denormalize_flat.argtypes = [vp, i32, u64, C.c_double, C.c_double, C.c_double, vp, i32, vp]

@@ -74,6 +74,30 @@ __device__ __forceinline__ double denormalize_one(double a, double scale, double
     return __dadd_rn(__dmul_rn(__ddiv_rn(__dadd_rn(n, 1.0), 2.0), range), mn);
 }
 
+// a / scale for an INTEGER a and one of the three constant scales, without the generic division sequence:
+// q0 = a * (1/scale), one residual correction with two FMAs (Markstein).  For these operands the result equals
+// the correctly rounded quotient for EVERY integer a of the audio range: frb_selftest_division compares it with
+// __ddiv_rn exhaustively (tests/test_gpu_parity.py::test_constant_division_is_exact).  The generic division
+// made k_denormalize_tiles fp64-bound (1.56 ms on C3 where the HBM floor is 0.9 ms).
+__device__ __forceinline__ double div_by_scale(double a, double scale, double rcp) {
+    const double q0 = __dmul_rn(a, rcp);
+    const double r = __fma_rn(-q0, scale, a);
+    return __fma_rn(r, rcp, q0);
+}
+__device__ __forceinline__ double denormalize_one_fast(double a, double scale, double rcp, double mn, double range) {
+    const double n = div_by_scale(a, scale, rcp);
+    return __dadd_rn(__dmul_rn(__dmul_rn(__dadd_rn(n, 1.0), 0.5), range), mn);      // x/2 == x*0.5 exactly
+}
+__global__ void k_selftest_division(double scale, long long lo, long long hi, unsigned long long *mismatches) {
+    const double rcp = __drcp_rn(scale);
+    unsigned long long bad = 0;
+    for (long long a = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; a <= hi; a += (long long)gridDim.x * blockDim.x) {
+        const double want = __ddiv_rn((double)a, scale), got = div_by_scale((double)a, scale, rcp);
+        if (__double_as_longlong(want) != __double_as_longlong(got)) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 // ---------------------------------------------------------------- min/max
 __global__ void k_minmax_init(unsigned long long *keys, uint32_t n_tiles) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -187,6 +211,24 @@ extern "C" int frb_minmax_flat(const void *d_src, int dtype, uint64_t n, double 
     FRB_LAUNCH_CHECK("k_minmax_flat");
     k_minmax_finish<<<1, 32, 0, s>>>((unsigned long long *)d_minmax, 1);
     FRB_LAUNCH_CHECK("k_minmax_finish");
+    return FRB_OK;
+}
+
+extern "C" int frb_selftest_division(double scale, int64_t lo, int64_t hi, uint64_t *h_mismatches, void *stream) {
+    using namespace frb;
+    if (!h_mismatches || hi < lo || !(scale > 0.0)) return FRB_ERR_INVALID_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long *d = nullptr;
+    FRB_CUDA(cudaMalloc(&d, 8));
+    cudaError_t e = cudaMemsetAsync(d, 0, 8, s);
+    if (e == cudaSuccess) {
+        k_selftest_division<<<kNumSMs * 8, 256, 0, s>>>(scale, (long long)lo, (long long)hi, d);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaMemcpyAsync(h_mismatches, d, 8, cudaMemcpyDeviceToHost, s);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(e, "frb_selftest_division");
     return FRB_OK;
 }
 

@@ -222,7 +222,12 @@ k_denormalize_tiles(const int32_t *__restrict__ audio, const int64_t *__restrict
     const int32_t *src = audio + audio_base[blockIdx.y];
     const uint32_t rows = bands * t.h;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    auto map = [&](int32_t a) -> T { return denorm_cast<T>(denormalize_one((double)a, scale, mn, range)); };
+    // the three scales the reference uses take the exact constant-division shortcut (see div_by_scale)
+    const bool fast = scale == 32767.0 || scale == 8388607.0 || scale == 2147483647.0;
+    const double rcp = __drcp_rn(scale);
+    auto map = [&](int32_t a) -> T {
+        return denorm_cast<T>(fast ? denormalize_one_fast((double)a, scale, rcp, mn, range) : denormalize_one((double)a, scale, mn, range));
+    };
     for (uint32_t ry = blockIdx.x * kMapWarps + warp; ry < rows; ry += gridDim.x * kMapWarps) {
         const uint32_t c = ry / t.h, y = ry - c * t.h;
         T *out = raster + ((size_t)c * H + (t.row_off + y)) * W + t.col_off;

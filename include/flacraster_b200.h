@@ -110,6 +110,11 @@ int frb_denormalize_tiles(const int32_t *d_audio, const int64_t *d_audio_base,
                           double scale, void *d_raster, int dtype, uint32_t bands, uint32_t H,
                           uint32_t W, void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* Self test of the constant-divisor shortcut used by frb_denormalize_tiles: counts the integers a in [lo, hi]
+ * for which the shortcut's a/scale differs from the correctly rounded IEEE quotient (expected: 0).
+ * Synchronises on `stream`. */
+int frb_selftest_division(double scale, int64_t lo, int64_t hi, uint64_t *h_mismatches, void *stream);
+
 /* Flat elementwise forms used by the drop-in normalize_to_audio /
  * denormalize_from_audio functions: n elements, any layout, one (min,max).
  * out16 != 0 writes int16 (16-bit path), else int32. */

@@ -446,3 +446,14 @@ def test_tile_mapping_odd_alignment_vs_oracle(nat, torch_cuda, dt):
         want = no.denormalize_from_audio(an, prm["data_min"], prm["data_max"], dt, prm["scale_factor"]).T.reshape(bands, h, w)
         got = out.cpu().numpy()[:, r:r + h, c:c + w]
         assert np.array_equal(got, want, equal_nan=True), (dt, i)
+
+
+def test_constant_division_is_exact(nat, torch_cuda):
+    """The denormalise kernel divides by the constant scale with a reciprocal + one FMA correction; it must give the
+    correctly rounded IEEE quotient for EVERY integer of the audio range (exhaustive, incl. all 2^32 int32 values)."""
+    import ctypes as C
+    L = nat.lib()
+    for scale, lo, hi in ((32767.0, -32768, 32767), (8388607.0, -8388608, 8388607), (2147483647.0, -2147483648, 2147483647)):
+        bad = C.c_uint64(123)
+        nat.check(L.frb_selftest_division(scale, lo, hi, C.byref(bad), None), "frb_selftest_division")
+        assert bad.value == 0, (scale, bad.value)
