@@ -237,6 +237,31 @@ extern "C" int frb_decode_batch(const frb_decode_params *p, const frb_decode_str
         prof_end(3, s);
         FRB_LAUNCH_CHECK("k_sync_scan");
     }
+    // CRC-16 only needs the frame positions: it runs on a side stream next to the skim pass (a latency-bound kernel
+    // that leaves most issue slots idle) and joins the caller's stream at the end.
+    static cudaStream_t side_of[64] = {nullptr};
+    static cudaEvent_t fork_of[64] = {nullptr}, join_of[64] = {nullptr};
+    int dev = 0;
+    FRB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return FRB_ERR_UNSUPPORTED;
+    cudaStream_t &side = side_of[dev];
+    cudaEvent_t &ev_fork = fork_of[dev], &ev_join = join_of[dev];
+    if (p->verify_crc16) {
+        if (!side) {
+            FRB_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+            FRB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+            FRB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        }
+        FRB_CUDA(cudaEventRecord(ev_fork, s));
+        FRB_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+        const uint64_t threads = total_frames * 32;
+        uint32_t crc_grid = (uint32_t)((threads + 255) / 256);
+        if (crc_grid > (uint32_t)kNumSMs * 8) crc_grid = kNumSMs * 8;         // persistent: the tables are staged once per CTA
+        k_crc16_frames<<<crc_grid, 256, 0, side>>>(d_bytes, w.streams, p->n_streams, p->blocksize,
+                                                  (uint32_t)total_frames, w.frame_pos, d_status);
+        FRB_LAUNCH_CHECK("k_crc16_frames");
+        FRB_CUDA(cudaEventRecord(ev_join, side));
+    }
     {
         const uint32_t *sub_bitoff = nullptr;
         if (p->channels > 1) {
@@ -265,14 +290,7 @@ extern "C" int frb_decode_batch(const frb_decode_params *p, const frb_decode_str
         prof_end(1, s);
         FRB_LAUNCH_CHECK("k_decode_subframes");
     }
-    if (p->verify_crc16) {
-        const uint64_t threads = total_frames * 32;
-        uint32_t crc_grid = (uint32_t)((threads + 255) / 256);
-        if (crc_grid > (uint32_t)kNumSMs * 8) crc_grid = kNumSMs * 8;         // persistent: the tables are staged once per CTA
-        k_crc16_frames<<<crc_grid, 256, 0, s>>>(d_bytes, w.streams, p->n_streams, p->blocksize,
-                                                                        (uint32_t)total_frames, w.frame_pos, d_status);
-        FRB_LAUNCH_CHECK("k_crc16_frames");
-    }
+    if (p->verify_crc16) FRB_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
     if (p->channels == 2) {
         k_stereo_fix<<<(uint32_t)total_frames, 128, 0, s>>>(w.streams, p->n_streams, p->blocksize, (uint32_t)total_frames,
                                                            w.chassign, w.frame_pos, d_audio);
