@@ -32,6 +32,15 @@ inline int cuda_fail(cudaError_t e, const char *what) {
 
 constexpr int kNumSMs = 148;   // B200
 
+// cudaFuncSetAttribute is per device: returns true the first time it is called for the current device
+inline bool first_call_on_device(bool (&done)[64]) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+}
+
 // ---- optional kernel timing (bench roofline) ---------------------------------
 struct ProfSlot { cudaEvent_t a = nullptr, b = nullptr; bool valid = false; };
 static bool g_prof_on = false;

@@ -1096,11 +1096,9 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const int32_t *d_a
     FRB_CUDA(cudaMemsetAsync(w.err_flag, 0, 256, s));
     FRB_CUDA(cudaStreamSynchronize(s));       // staging vectors are locals
     const uint32_t slot_words = slot_words_for(p->blocksize, p->bps);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};
+    if (first_call_on_device(attr_set))
         FRB_CUDA(cudaFuncSetAttribute(k_encode_subframes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncShared)));
-        attr_set = true;
-    }
     // Full, 16-byte aligned 4096-sample blocks go through the three-kernel fast path; everything else (the short
     // last frame of a stream, channels that start at an unaligned sample) is listed for the one-kernel encoder.
     const LevelCfg cfg = level_cfg(p->level);

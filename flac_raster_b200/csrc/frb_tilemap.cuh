@@ -157,8 +157,9 @@ k_normalize_tiles(const T *__restrict__ raster, uint32_t bands, uint32_t H, uint
     const uint32_t rows = bands * t.h;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool use_lut = is_small_int<T>::value && lut_all != nullptr && (mx - mn < (double)kNormLutCap);
-    const int32_t *lut = lut_all ? lut_all + (size_t)blockIdx.y * kNormLutCap : nullptr;
     const int32_t vmin = use_lut ? (int32_t)mn : 0;
+    // (staging the table in shared memory was tried: 64 KB per CTA costs more occupancy than the L1 gathers cost)
+    const int32_t *lut = lut_all ? lut_all + (size_t)blockIdx.y * kNormLutCap : nullptr;
     auto map = [&](T v) -> int32_t {
         if (is_small_int<T>::value && use_lut) return __ldg(lut + ((int32_t)v - vmin));
         return normalize_one((double)v, mn, range, scale);
@@ -333,7 +334,7 @@ extern "C" int frb_normalize_tiles(const void *d_raster, int dtype, uint32_t ban
     }
     const dim3 grid = tile_grid_dims(n_tiles, bands * H);
     FRB_DISPATCH_DTYPE(dtype, (k_normalize_tiles<T><<<grid, kMapThreads, 0, s>>>((const T *)d_raster, bands, H, W, d_tiles, d_minmax,
-                                                                                bits_per_sample, d_audio, d_audio_base, lut)));
+                                                                                       bits_per_sample, d_audio, d_audio_base, lut)));
     FRB_LAUNCH_CHECK("k_normalize_tiles");
     return FRB_OK;
 }
