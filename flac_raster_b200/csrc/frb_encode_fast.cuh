@@ -306,7 +306,8 @@ k_enc_stats(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bp
     if (!WIDE) {
         // successive differences in 32 bits: |4th difference| <= 16 * 2^15, 16 samples per thread, 32 per warp
         uint32_t e32[5] = {0, 0, 0, 0, 0}, x32[4] = {0, 0, 0, 0};
-        int32_t d1[kSPT + 3], d2[kSPT + 2], d3[kSPT + 1], d4[kSPT];
+        // |d| accumulates with one VABSDIFF (|a - b| + c); the 4th difference is never materialised
+        int32_t d1[kSPT + 3], d2[kSPT + 2], d3[kSPT + 1];
 #pragma unroll
         for (int j = 0; j < kSPT + 3; j++) d1[j] = xs[9 + j] - xs[8 + j];
 #pragma unroll
@@ -314,17 +315,16 @@ k_enc_stats(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bp
 #pragma unroll
         for (int j = 0; j < kSPT + 1; j++) d3[j] = d2[j + 1] - d2[j];
 #pragma unroll
-        for (int j = 0; j < kSPT; j++) d4[j] = d3[j + 1] - d3[j];
-#pragma unroll
         for (int s = 0; s < kSPT; s++) {
             if (s >= 4 || tid > 0) {
-                e32[0] += (uint32_t)abs(xs[12 + s]); e32[1] += (uint32_t)abs(d1[s + 3]); e32[2] += (uint32_t)abs(d2[s + 2]);
-                e32[3] += (uint32_t)abs(d3[s + 1]); e32[4] += (uint32_t)abs(d4[s]);
+                e32[0] = __sad(xs[12 + s], 0, e32[0]); e32[1] = __sad(xs[12 + s], xs[11 + s], e32[1]);
+                e32[2] = __sad(d1[s + 3], d1[s + 2], e32[2]); e32[3] = __sad(d2[s + 2], d2[s + 1], e32[3]);
+                e32[4] = __sad(d3[s + 1], d3[s], e32[4]);
             } else {
-                x32[0] += (uint32_t)abs(xs[12 + s]);
-                if (s >= 1) x32[1] += (uint32_t)abs(d1[s + 3]);
-                if (s >= 2) x32[2] += (uint32_t)abs(d2[s + 2]);
-                if (s >= 3) x32[3] += (uint32_t)abs(d3[s + 1]);
+                x32[0] = __sad(xs[12 + s], 0, x32[0]);
+                if (s >= 1) x32[1] = __sad(xs[12 + s], xs[11 + s], x32[1]);
+                if (s >= 2) x32[2] = __sad(d1[s + 3], d1[s + 2], x32[2]);
+                if (s >= 3) x32[3] = __sad(d2[s + 2], d2[s + 1], x32[3]);
             }
         }
 #pragma unroll
@@ -676,29 +676,38 @@ __device__ __forceinline__ void put_bits_atomic(uint32_t *buf, uint32_t pos, uin
     if (lo) atomicOr(&buf[(pos >> 5) + 1], lo);
 }
 
-// Per-thread bit accumulator over the zeroed shared word buffer (MSB first): 64-bit window, completed words
-// are OR-ed in (a thread's first and last word can be shared with its neighbours).
+// Per-thread bit accumulator over the zeroed shared word buffer (MSB first).  `hi` holds the pending bits of
+// the current word (top `fill` < 32 bits); a code of len <= 32 bits is split into the part that still fits and
+// the spill-over, and a completed word is OR-ed in with a predicated reduction (a thread's first and last
+// word can be shared with its neighbours, and a data-dependent branch would diverge in almost every step).
+// v1 kept a 64-bit window and branched on the flush: ~26 instructions per code (profiles/r01_ncu_enc_v5_lines_code.txt).
 struct PackWriter {
-    uint32_t *buf;
-    uint32_t widx, fill;
-    unsigned long long acc;
-    __device__ __forceinline__ void init(uint32_t *b, uint32_t bitpos) { buf = b; widx = bitpos >> 5; fill = bitpos & 31u; acc = 0; }
-    __device__ __forceinline__ void flush_hi() {
-        atomicOr(&buf[widx], (uint32_t)(acc >> 32));
-        widx++; acc <<= 32; fill -= 32;
+    uint32_t addr, fill, hi;     // shared-space byte address of the current word
+    __device__ __forceinline__ void init(uint32_t *b, uint32_t bitpos) {
+        addr = (uint32_t)__cvta_generic_to_shared(b) + ((bitpos >> 5) << 2); fill = bitpos & 31u; hi = 0;
     }
     __device__ __forceinline__ void put(uint32_t v, uint32_t len) {        // 1 <= len <= 32, v < 2^len
-        acc |= (unsigned long long)v << (64u - fill - len);
+        const uint32_t vh = v << (32u - len);                              // left-aligned code
+        hi |= vh >> fill;
+        const uint32_t lo = __funnelshift_lc(0u, vh, 32u - fill);          // spill-over: vh << (32 - fill), 0 when fill == 0
         fill += len;
-        if (fill >= 32) flush_hi();
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "setp.ge.u32 p, %1, 32;\n\t"
+                     "@p red.shared.or.b32 [%2], %0;\n\t"
+                     "@p mov.b32 %0, %3;\n\t"
+                     "@p add.u32 %2, %2, 4;\n\t"
+                     "@p sub.u32 %1, %1, 32;\n\t"
+                     "}\n" : "+r"(hi), "+r"(fill), "+r"(addr) : "r"(lo) : "memory");
     }
     __device__ __forceinline__ void zeros(uint32_t q) {
         fill += q;
-        while (fill >= 32) flush_hi();
+        while (fill >= 32) {
+            if (hi) asm volatile("red.shared.or.b32 [%0], %1;\n" ::"r"(addr), "r"(hi) : "memory");
+            hi = 0; addr += 4; fill -= 32;
+        }
     }
     __device__ __forceinline__ void finish() {
-        const uint32_t w = (uint32_t)(acc >> 32);
-        if (w) atomicOr(&buf[widx], w);
+        if (hi) asm volatile("red.shared.or.b32 [%0], %1;\n" ::"r"(addr), "r"(hi) : "memory");
     }
 };
 
@@ -822,7 +831,7 @@ k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps
             if (ora < 0x08000000u) {
                 uint32_t s32 = 0;
 #pragma unroll
-                for (int s = 0; s < kSPT; s++) s32 += (uint32_t)abs(r[s]);
+                for (int s = 0; s < kSPT; s++) s32 = __sad(r[s], 0, s32);
                 s64 = s32;
             } else {
                 s64 = 0;
