@@ -122,7 +122,9 @@ k_sync_scan(const uint8_t *__restrict__ bytes, const DecStreamDev *__restrict__ 
     const uint32_t *words = (const uint32_t *)bytes;
     for (uint64_t q = q0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < q1; q += (uint64_t)gridDim.x * blockDim.x) {
         const uint4 c = __ldg(chunks + q);
-        const uint32_t nxt = __ldg(words + 4 * q + 4);               // first word of the next chunk (little-endian bytes)
+        // first word of the next chunk (little-endian bytes); a sync code straddling out of the stream's last chunk
+        // would fail the length check anyway, so nothing is read past the 16-byte slack
+        const uint32_t nxt = (q + 1 < q1) ? __ldg(words + 4 * q + 4) : 0u;
         const uint32_t w[5] = {c.x, c.y, c.z, c.w, nxt};
 #pragma unroll
         for (int j = 0; j < 4; j++) {
