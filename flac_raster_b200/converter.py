@@ -217,9 +217,9 @@ def decode_tile_blobs(blobs, headers, metadatas, mosaic=None):
     tiles = np.zeros(n, dtype=nat.TILE_DTYPE)
     minmax = np.zeros((n, 2), dtype=np.float64)
     pos = 0
-    parts = []
     row = 0
     maxw = 0
+    bodies = []
     for i, (b, h, md) in enumerate(zip(blobs, headers, metadatas)):
         si = h.streaminfo
         if (si.channels, si.bits_per_sample, si.max_blocksize) != (channels, bps, blocksize):
@@ -228,20 +228,26 @@ def decode_tile_blobs(blobs, headers, metadatas, mosaic=None):
             raise ValueError("band count in tags does not match the FLAC channel count")
         body = memoryview(b)[h.first_frame_offset:]
         offs[i], lens[i] = pos, len(body)
-        parts.append(body)
-        pad = (-len(body)) % 4
-        if pad:
-            parts.append(b"\0" * pad)
-        pos += len(body) + pad
+        bodies.append(body)
+        pos += (len(body) + 3) & ~3
         nsamp[i] = md["width"] * md["height"]
         rates[i] = si.sample_rate
         tiles[i] = (row, 0, md["height"], md["width"])
         row += md["height"]
         maxw = max(maxw, md["width"])
         minmax[i] = (md["data_min"], md["data_max"])
-    parts.append(b"\0" * 32)
-    host = np.frombuffer(b"".join(parts), dtype=np.uint8)
-    data = torch.from_numpy(host).to(eng.device)
+    # frames of all tiles -> one pinned staging buffer (no intermediate bytes objects) -> one H2D copy
+    stage = eng._pinned("dec_stage", pos + 64)
+    stage_np = stage.numpy()
+    for i, body in enumerate(bodies):
+        o = int(offs[i])
+        stage_np[o:o + len(body)] = np.frombuffer(body, dtype=np.uint8)
+        pad = (-len(body)) % 4
+        if pad:
+            stage_np[o + len(body):o + len(body) + pad] = 0
+    stage_np[pos:pos + 64] = 0
+    data = eng._buf("dec_data", pos + 64)[:pos + 64]
+    data.copy_(stage[:pos + 64], non_blocking=True)
     audio, base, status = eng.decode_streams(data, offs, lens, nsamp, rates, channels, bps, blocksize)
     if status[0] or status[2]:
         raise ValueError(f"malformed FLAC stream (missing frames={status[0]}, parse errors={status[2]})")
@@ -255,9 +261,23 @@ def decode_tile_blobs(blobs, headers, metadatas, mosaic=None):
     out = torch.zeros(channels * row * maxw * dtype.itemsize, dtype=torch.uint8, device=eng.device)
     out = out.view(TORCH_DTYPES[str(dtype)]).reshape(channels, row, maxw)
     eng.denormalize_tiles(audio, base, tiles, minmax, scale, out)
-    host_out = out.reshape(-1).view(torch.uint8).cpu().numpy().view(dtype).reshape(channels, row, maxw)
-    res = []
-    for i in range(n):
+    # D2H through a pinned buffer, then every tile becomes its own array (the buffer is reused by the next call);
+    # the per-tile copies run on a few threads (numpy releases the GIL while copying)
+    nbytes = out.numel() * dtype.itemsize
+    pinned = eng._pinned("dec_out", nbytes)
+    pinned[:nbytes].copy_(out.reshape(-1).view(torch.uint8), non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    host_out = pinned[:nbytes].numpy().view(dtype).reshape(channels, row, maxw)
+
+    def take(i):
         r0, h_, w_ = int(tiles[i]["row_off"]), int(tiles[i]["h"]), int(tiles[i]["w"])
-        res.append(np.ascontiguousarray(host_out[:, r0:r0 + h_, :w_]))
+        return np.ascontiguousarray(host_out[:, r0:r0 + h_, :w_])
+
+    if n >= 64:
+        from concurrent.futures import ThreadPoolExecutor
+        jobs = [range(a, min(n, a + (n + 31) // 32)) for a in range(0, n, (n + 31) // 32)]
+        with ThreadPoolExecutor(8) as ex:
+            res = [a for part in ex.map(lambda rg: [take(i) for i in rg], jobs) for a in part]
+    else:
+        res = [take(i) for i in range(n)]
     return res

@@ -355,11 +355,11 @@ class SpatialFLACStreamer:
             while j + 1 < len(order) and frames[order[j + 1]].byte_offset == end:
                 j += 1
                 end += frames[order[j]].byte_size
-            chunk = self._read_range(self.header_size + start, self.header_size + end - 1)
+            chunk = memoryview(self._read_range(self.header_size + start, self.header_size + end - 1))
             for k in range(i, j + 1):
                 f = frames[order[k]]
                 o = f.byte_offset - start
-                blobs[order[k]] = chunk[o:o + f.byte_size]
+                blobs[order[k]] = chunk[o:o + f.byte_size]          # views: no per-tile copy of the range just read
             i = j + 1
         return blobs   # type: ignore[return-value]
 
