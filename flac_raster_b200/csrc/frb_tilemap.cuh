@@ -131,14 +131,18 @@ k_minmax_tiles(const T *__restrict__ raster, uint32_t bands, uint32_t H, uint32_
 // ---------------------------------------------------------------- normalise
 __global__ void __launch_bounds__(256)
 k_build_norm_lut(const double *__restrict__ minmax, int bits, int32_t *__restrict__ lut) {
+    // 16-bit audio: entries are stored as int16 in the same buffer (half the cache sectors per warp-wide gather)
+    int16_t *lut16 = reinterpret_cast<int16_t *>(lut);
     const double mn = minmax[2 * blockIdx.y], mx = minmax[2 * blockIdx.y + 1];
     if (!(mx - mn < (double)kNormLutCap)) return;          // also false for NaN: those tiles use the direct path
     const double range = (mx <= mn) ? 1.0 : __dsub_rn(mx, mn);
     const double scale = scale_for_bits(bits);
     const uint32_t cnt = (uint32_t)(mx - mn) + 1;
-    int32_t *dst = lut + (size_t)blockIdx.y * kNormLutCap;
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += gridDim.x * blockDim.x)
-        dst[j] = normalize_one(__dadd_rn(mn, (double)j), mn, range, scale);     // mn + j is exact (small integers)
+    const size_t base = (size_t)blockIdx.y * kNormLutCap;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += gridDim.x * blockDim.x) {
+        const int32_t v = normalize_one(__dadd_rn(mn, (double)j), mn, range, scale);     // mn + j is exact (small integers)
+        if (bits == 16) lut16[base + j] = (int16_t)v; else lut[base + j] = v;
+    }
 }
 
 template <typename T>
@@ -161,7 +165,9 @@ k_normalize_tiles(const T *__restrict__ raster, uint32_t bands, uint32_t H, uint
     // (staging the table in shared memory was tried: 64 KB per CTA costs more occupancy than the L1 gathers cost)
     const int32_t *lut = lut_all ? lut_all + (size_t)blockIdx.y * kNormLutCap : nullptr;
     auto map = [&](T v) -> int32_t {
-        if (is_small_int<T>::value && use_lut) return __ldg(lut + ((int32_t)v - vmin));
+        if (is_small_int<T>::value && use_lut)
+            return bits == 16 ? (int32_t)__ldg(reinterpret_cast<const int16_t *>(lut_all) + (size_t)blockIdx.y * kNormLutCap + ((int32_t)v - vmin))
+                              : __ldg(lut + ((int32_t)v - vmin));
         return normalize_one((double)v, mn, range, scale);
     };
     for (uint32_t ry = blockIdx.x * kMapWarps + warp; ry < rows; ry += gridDim.x * kMapWarps) {
