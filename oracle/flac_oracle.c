@@ -904,30 +904,63 @@ size_t fo_encode_stream(const int32_t *samples, uint64_t n_samples, uint32_t cha
     if (!W) { free(E.window); return 0; }
     int64_t (*ch)[FO_MAX_BLOCK + 1] = W->ch; int32_t (*res)[FO_MAX_BLOCK + 1] = W->chres; sf_choice *choice = W->choice;
     uint64_t pos = 0, frame_no = 0; size_t nd = 0;
+    /* loose mid/side state (FLAC__stream_encoder: loose_mid_side_stereo_frames = sample_rate * 0.4 / blocksize) */
+    uint32_t loose_frames = (uint32_t)((double)sample_rate * 0.4 / (double)blocksize + 0.5), loose_count = 0, last_assign = 1;
+    if (loose_frames == 0) loose_frames = 1;
     uint32_t minf = 0xFFFFFFFFu, maxf = 0;
     while (pos < n_samples) {
         uint32_t n = (n_samples - pos) < blocksize ? (uint32_t)(n_samples - pos) : blocksize;
         for (uint32_t c = 0; c < channels; c++)
             for (uint32_t i = 0; i < n; i++) ch[c][i] = samples[(pos + i) * channels + c];
-        /* NOTE: stereo decorrelation (exactly-2-channel input, levels 1,2,4-8) is not
-         * restated yet; channels are coded independently (always a valid stream). */
-        size_t need = 16 + (size_t)channels * ((size_t)n * (bps + 1) / 8 + 16) + 2;
+        /* Stereo decorrelation for exactly two channels (libFLAC process_subframes_ / process_frame_, presets with
+         * do_mid_side): mid = (L+R)>>1, side = L-R (one more bit per sample); all four subframes are evaluated
+         * and the cheapest of independent / left-side / right-side / mid-side by the estimated bits wins, ties
+         * going to the earlier one.  "Loose" presets (levels 1 and 4) take that decision only every
+         * loose_frames frames and otherwise keep independent or switch to mid-side.  [upstream, unverified:
+         * restated from libFLAC 1.4.3; the reference holds no 2-channel golden]  finalize bit 1 disables it. */
+        const int do_ms = (channels == 2) && E.ps->do_mid_side && !(finalize & 2);
+        uint32_t ch_assign = channels - 1;
+        uint32_t order_ch[2] = {0, 1};       /* which of L,R,M,S go into the frame */
+        uint32_t nsub = channels;
+        if (do_ms) {
+            for (uint32_t i = 0; i < n; i++) { ch[2][i] = (ch[0][i] + ch[1][i]) >> 1; ch[3][i] = ch[0][i] - ch[1][i]; }
+            int eval_indep = 1, eval_ms = 1;
+            if (E.ps->loose_mid_side && loose_count > 0) { eval_indep = (last_assign == 1); eval_ms = !eval_indep; }
+            if (eval_indep) { choose_subframe(W, &E, ch[0], n, bps, &choice[0], res[0]); choose_subframe(W, &E, ch[1], n, bps, &choice[1], res[1]); }
+            if (eval_ms) { choose_subframe(W, &E, ch[2], n, bps, &choice[2], res[2]); choose_subframe(W, &E, ch[3], n, bps + 1, &choice[3], res[3]); }
+            if (E.ps->loose_mid_side && loose_count > 0) ch_assign = eval_indep ? 1 : 10;
+            else {
+                uint64_t b[4] = { (uint64_t)choice[0].bits + choice[1].bits, (uint64_t)choice[0].bits + choice[3].bits,
+                                  (uint64_t)choice[1].bits + choice[3].bits, (uint64_t)choice[2].bits + choice[3].bits };
+                uint32_t best = 0;
+                for (uint32_t a = 1; a < 4; a++) if (b[a] < b[best]) best = a;
+                ch_assign = best == 0 ? 1 : 7 + best;          /* 8 left/side, 9 side/right, 10 mid/side */
+            }
+            if (E.ps->loose_mid_side) { loose_count++; if (loose_count >= loose_frames) loose_count = 0; }
+            last_assign = ch_assign;
+            if (ch_assign == 8) { order_ch[0] = 0; order_ch[1] = 3; }
+            else if (ch_assign == 9) { order_ch[0] = 3; order_ch[1] = 1; }
+            else if (ch_assign == 10) { order_ch[0] = 2; order_ch[1] = 3; }
+        }
+        size_t need = 16 + (size_t)channels * ((size_t)n * (bps + 2) / 8 + 16) + 2;
         if ((size_t)(p - out) + need > cap) { free(E.window); free(W); return 0; }
         uint8_t *f0 = p;
-        size_t hb = write_frame_header(p, n, sample_rate, channels - 1, bps, frame_no);
+        size_t hb = write_frame_header(p, n, sample_rate, ch_assign, bps, frame_no);
         bw_t w = { f0, need, hb * 8, 0 };
-        for (uint32_t c = 0; c < channels; c++) {
-            choose_subframe(W, &E, ch[c], n, bps, &choice[c], res[c]);
+        for (uint32_t k = 0; k < nsub; k++) {
+            const uint32_t c = do_ms ? order_ch[k] : k;
+            const uint32_t sbps = bps + ((do_ms && c == 3) ? 1u : 0u);
+            if (!do_ms) choose_subframe(W, &E, ch[c], n, bps, &choice[c], res[c]);
             size_t b0 = w.bitpos;
-            write_subframe(&w, &choice[c], ch[c], res[c], n, bps);
+            write_subframe(&w, &choice[c], ch[c], res[c], n, sbps);
             if (descs && nd < desc_cap) {
                 fo_subframe_desc *d = &descs[nd++];
                 memset(d, 0, sizeof *d);
-                d->frame = (uint32_t)frame_no; d->channel = c; d->type = (uint32_t)choice[c].type; d->order = (uint32_t)choice[c].order;
+                d->frame = (uint32_t)frame_no; d->channel = k; d->type = (uint32_t)choice[c].type; d->order = (uint32_t)choice[c].order;
                 d->wasted = (uint32_t)choice[c].wasted; d->precision = (uint32_t)choice[c].precision; d->shift = choice[c].shift;
                 memcpy(d->coefs, choice[c].coefs, sizeof d->coefs); d->method = (uint32_t)choice[c].method; d->partition_order = (uint32_t)choice[c].part_order;
-                for (uint32_t k = 0; k < FO_DESC_PARAMS && k < (1u << choice[c].part_order); k++) d->params[k] = choice[c].params[k];
-                d->nbits = (uint32_t)(w.bitpos - b0); d->blocksize = n; d->ch_assign = channels - 1; d->frame_offset = (uint32_t)(f0 - out);
+                for (uint32_t q = 0; q < FO_DESC_PARAMS && q < (1u << choice[c].part_order); q++) d->params[q] = choice[c].params[q];
+                d->nbits = (uint32_t)(w.bitpos - b0); d->blocksize = n; d->ch_assign = ch_assign; d->frame_offset = (uint32_t)(f0 - out);
                 (void)exact_subframe_bits;
             }
         }
@@ -942,7 +975,7 @@ size_t fo_encode_stream(const int32_t *samples, uint64_t n_samples, uint32_t cha
         p += fb; pos += n; frame_no++;
     }
     free(E.window); free(W);
-    if (finalize && frame_no) {
+    if ((finalize & 1) && frame_no) {
         s[4] = (uint8_t)(minf >> 16); s[5] = (uint8_t)(minf >> 8); s[6] = (uint8_t)minf;
         s[7] = (uint8_t)(maxf >> 16); s[8] = (uint8_t)(maxf >> 8); s[9] = (uint8_t)maxf;
         s[13] = (uint8_t)((s[13] & 0xF0) | ((n_samples >> 32) & 15));

@@ -120,8 +120,9 @@ def decode(data: bytes, want_descs: bool = False, max_samples: int | None = None
 
 
 def encode(samples: np.ndarray, bps: int, sample_rate: int, level: int = 5, blocksize: int = 4096,
-           finalize: bool = False, vendor: bytes | None = None, want_descs: bool = False):
-    """Encode (N,C) int samples into a full FLAC stream (bytes)."""
+           finalize: bool = False, vendor: bytes | None = None, want_descs: bool = False, mid_side: bool = True):
+    """Encode (N,C) int samples into a full FLAC stream (bytes).  mid_side=False codes two-channel input as
+    independent channels (what the GPU encoder emits today); True follows libFLAC's presets."""
     L = lib()
     a = np.ascontiguousarray(samples).astype(np.int32)
     if a.ndim == 1:
@@ -133,7 +134,7 @@ def encode(samples: np.ndarray, bps: int, sample_rate: int, level: int = 5, bloc
     fs = np.zeros(max(nframes, 1), dtype=np.uint32)
     ndesc = nframes * ch if want_descs else 0
     descs = (SubframeDesc * max(ndesc, 1))()
-    sz = L.fo_encode_stream(a.ctypes.data, n, ch, bps, sample_rate, level, blocksize, int(finalize),
+    sz = L.fo_encode_stream(a.ctypes.data, n, ch, bps, sample_rate, level, blocksize, int(bool(finalize)) | (0 if mid_side else 2),
                             vendor, out.ctypes.data, cap, fs.ctypes.data, fs.size,
                             C.cast(descs, C.c_void_p) if want_descs else None, ndesc)
     if sz == 0:
