@@ -277,30 +277,31 @@ extern "C" int frb_decode_batch(const frb_decode_params *p, const frb_decode_str
         FRB_CUDA(cudaEventRecord(ev_join, side));
     }
     {
-        const uint32_t *sub_bitoff = nullptr;
+        uint32_t *sub_bitoff = nullptr;
+        uint32_t n_skim_ctas = 0, skim_lanes = 32;
         if (p->channels > 1) {
-            // subframes of a frame are bit-packed back to back: find their starts first
-            static uint32_t skim_lanes = 0;
-            if (!skim_lanes) { const char *e = getenv("FRB_SKIM_LANES"); skim_lanes = e ? (uint32_t)atoi(e) : 32u; if (skim_lanes < 1 || skim_lanes > 32) skim_lanes = 32; }
+            // subframes of a frame are bit-packed back to back: their starts are found by the skim CTAs of the SAME
+            // launch and handed to the decode threads through sub_bitoff (kNotReady until published)
+            static uint32_t skim_lanes_cfg = 0;
+            if (!skim_lanes_cfg) { const char *e = getenv("FRB_SKIM_LANES"); skim_lanes_cfg = e ? (uint32_t)atoi(e) : 32u; if (skim_lanes_cfg < 1 || skim_lanes_cfg > 32) skim_lanes_cfg = 32; }
+            skim_lanes = skim_lanes_cfg;
             const uint32_t frames_per_cta = (kDecThreads / 32) * skim_lanes;
-            prof_begin(5, s);
-            k_skim_subframes<<<(uint32_t)((total_frames + frames_per_cta - 1) / frames_per_cta), kDecThreads, 0, s>>>(
-                d_bytes, w.streams, p->n_streams, p->channels, p->bps, p->blocksize, (uint32_t)total_frames, w.frame_pos,
-                w.sub_bitoff, w.chassign, d_status, skim_lanes);
-            prof_end(5, s);
-            FRB_LAUNCH_CHECK("k_skim_subframes");
+            n_skim_ctas = (uint32_t)((total_frames + frames_per_cta - 1) / frames_per_cta);
             sub_bitoff = w.sub_bitoff;
+            FRB_CUDA(cudaMemsetAsync(sub_bitoff, 0xFF, 4 * (size_t)(total_frames * p->channels), s));
         }
         const uint64_t total_sub = total_frames * p->channels;
-        const uint32_t grid = (uint32_t)((total_sub + 127) / 128);
+        const uint32_t grid = n_skim_ctas + (uint32_t)((total_sub + kDecThreads - 1) / kDecThreads);
         const bool big = p->reserved > 12;
         prof_begin(1, s);
         if (!big)
-            k_decode_subframes<false><<<grid, 128, 0, s>>>(d_bytes, w.streams, p->n_streams, p->channels, p->bps, p->blocksize,
-                                                          (uint32_t)total_frames, w.frame_pos, sub_bitoff, d_audio, w.chassign, d_status);
+            k_decode_subframes<false><<<grid, kDecThreads, 0, s>>>(d_bytes, w.streams, p->n_streams, p->channels, p->bps, p->blocksize,
+                                                          (uint32_t)total_frames, w.frame_pos, sub_bitoff, d_audio, w.chassign, d_status,
+                                                          n_skim_ctas, skim_lanes);
         else
-            k_decode_subframes<true><<<grid, 128, 0, s>>>(d_bytes, w.streams, p->n_streams, p->channels, p->bps, p->blocksize,
-                                                         (uint32_t)total_frames, w.frame_pos, sub_bitoff, d_audio, w.chassign, d_status);
+            k_decode_subframes<true><<<grid, kDecThreads, 0, s>>>(d_bytes, w.streams, p->n_streams, p->channels, p->bps, p->blocksize,
+                                                         (uint32_t)total_frames, w.frame_pos, sub_bitoff, d_audio, w.chassign, d_status,
+                                                         n_skim_ctas, skim_lanes);
         prof_end(1, s);
         FRB_LAUNCH_CHECK("k_decode_subframes");
     }
@@ -312,6 +313,20 @@ extern "C" int frb_decode_batch(const frb_decode_params *p, const frb_decode_str
     }
     return FRB_OK;
 }
+
+#ifdef FRB_DEC_TIMING
+extern "C" int frb_debug_decode_timing(unsigned long long *out16, int reset) {
+    using namespace frb;
+    if (out16) FRB_CUDA(cudaMemcpyFromSymbol(out16, g_dec_dbg, sizeof(unsigned long long) * 16));
+    if (reset) {
+        unsigned long long z[16];
+        for (int i = 0; i < 16; i++) z[i] = 0;
+        z[0] = z[11] = ~0ull;
+        FRB_CUDA(cudaMemcpyToSymbol(g_dec_dbg, z, sizeof z));
+    }
+    return FRB_OK;
+}
+#endif
 
 extern "C" int frb_probe_stream(const uint8_t *d_bytes, uint64_t byte_offset, uint64_t byte_length,
                                 uint32_t channels, uint32_t bps, uint32_t blocksize, uint32_t sample_rate,

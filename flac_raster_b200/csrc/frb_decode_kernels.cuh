@@ -71,29 +71,33 @@ __device__ __forceinline__ FrameLoc locate_frame(const DecStreamDev *__restrict_
 constexpr int kSkimRing = 16;                                   // 16-byte chunks per thread (256 contiguous bytes)
 constexpr int kSkimBatch = 8;                                   // codes per batch: <= 8 words = 2 chunks
 
-// 64-bit left-aligned window (hi:lo, the top vb >= 32 bits valid) + two pre-loaded words.  The dependent chain
-// per code is clz -> add -> funnel shift (-> or, when a word is merged); everything else hangs off it.
-// Ring: the thread's 16 chunks are contiguous in shared memory, chunk index XOR-swizzled with the lane so that
-// lanes reading the same word offset spread over the banks.
+// 96-bit left-aligned shifting window H:M:L (the top vb >= 64 bits valid before every code) + two pre-loaded words.
+// H always holds 32 valid bits, so the dependent chain per Rice code is clz(H) -> add -> ONE funnel shift of H:M;
+// everything else (shifting M:L, the valid-bit count, merging the next word below the valid bits -- it only ever
+// touches M and L) hangs off that chain.  The earlier 64-bit window merged into the word the next clz reads, which
+// put compare -> predicated shift -> or on the chain of every code (the skim walk, one warp or two per scheduler,
+// ran at 130 cycles per code).
+// Ring: the thread's 16 chunks are contiguous in shared memory (256-byte aligned), chunk index XOR-swizzled with the
+// lane so that lanes reading the same word offset spread over the banks.
 struct BitReader {
     const uint4 *gq;         // 16-byte view of the input buffer (16-byte aligned base)
     uint32_t sbase;          // shared-space address of this thread's 256-byte ring
     uint32_t swz;            // (lane & 15) << 4
-    uint32_t wnext;          // word index (32-bit words from the buffer base) of the next word to load; nx = wnext-2, nx2 = wnext-1
+    uint32_t sx;             // sbase ^ swz: ring word at byte offset o (0..252) lives at sx ^ o
+    uint32_t woff;           // 4 * (index of the next word to load, in 32-bit words from the buffer base); nx2raw is word woff/4-1, nx woff/4-2
     uint32_t cissue;         // next chunk to copy into the ring
     uint32_t qlast;          // copies are clamped to this chunk (16 readable bytes follow the frame end)
-    uint32_t hi, lo, nx, nx2raw;   // nx2raw: word wnext-1 as loaded (little-endian), byte-swapped when it becomes nx
-    int32_t vb;              // valid bits in hi:lo
-    __device__ __forceinline__ uint32_t load_raw(uint32_t a) const { return lds_u32(sbase + ((((a << 2) & 252u)) ^ swz)); }
-    __device__ __forceinline__ uint32_t load_word(uint32_t a) const { return bswap32(load_raw(a)); }
+    uint32_t H, M, L, nx, nx2raw;   // nx2raw: as loaded (little-endian), byte-swapped when it becomes nx
+    int32_t vb;              // valid bits in H:M:L
+    __device__ __forceinline__ uint32_t load_raw4(uint32_t byte_off) const { return lds_u32(sx ^ (byte_off & 252u)); }
     __device__ __forceinline__ void copy_chunk(uint32_t c) const {
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sbase + (((c & (kSkimRing - 1)) << 4) ^ swz)),
                      "l"(gq + min(c, qlast)) : "memory");
     }
     // Copy ahead without overwriting anything still needed: chunk c may replace chunk c - kSkimRing once that one
-    // lies before the chunk of the oldest pre-loaded word.  At most two chunks per call (a batch consumes at most two).
+    // lies before the chunk of the next word to load.  At most two chunks per call (a batch consumes at most two).
     __device__ __forceinline__ void top_up() {
-        const uint32_t lim = ((wnext - 2) >> 2) + kSkimRing - 1;
+        const uint32_t lim = (woff >> 4) + kSkimRing - 1;
 #pragma unroll
         for (int r = 0; r < 2; r++)
             if (cissue < lim) { copy_chunk(cissue); cissue++; }
@@ -105,59 +109,65 @@ struct BitReader {
         gq = (const uint4 *)base;
         sbase = ring_saddr;
         swz = (lane & 15u) << 4;
+        sx = sbase ^ swz;
         const uint32_t w = (uint32_t)(bitpos >> 5);
         qlast = (uint32_t)(byte_end >> 4);
         cissue = w >> 2;
         for (int j = 0; j < kSkimRing - 1; j++) { copy_chunk(cissue); cissue++; }
         cp_async_commit();
         cp_async_wait<0>();
-        hi = load_word(w); lo = load_word(w + 1); nx = load_word(w + 2); nx2raw = load_raw(w + 3);
-        wnext = w + 4;
-        vb = 64;
+        H = bswap32(load_raw4(w << 2)); M = bswap32(load_raw4((w + 1) << 2)); L = bswap32(load_raw4((w + 2) << 2));
+        nx = bswap32(load_raw4((w + 3) << 2)); nx2raw = load_raw4((w + 4) << 2);
+        woff = (w + 5) << 2;
+        vb = 96;
         consume((uint32_t)bitpos & 31u);
     }
-    __device__ __forceinline__ uint64_t bitpos() const { return (uint64_t)(wnext - 2) * 32u - (uint32_t)vb; }
-    __device__ __forceinline__ bool overrun() const { return (wnext >> 2) > qlast + 2; }
-    __device__ __forceinline__ uint32_t window() const { return hi; }
-    __device__ __forceinline__ void merge_word() {                 // vb < 32: append nx below the valid bits
-        hi |= __funnelshift_rc(nx, 0u, (uint32_t)vb);
-        lo = __funnelshift_lc(0u, nx, 32u - (uint32_t)vb);
+    __device__ __forceinline__ uint64_t bitpos() const { return (uint64_t)((woff >> 2) - 2u) * 32u - (uint32_t)vb; }
+    __device__ __forceinline__ bool overrun() const { return (woff >> 4) > qlast + 2; }
+    __device__ __forceinline__ uint32_t window() const { return H; }
+    __device__ __forceinline__ void merge_word() {                 // 32 <= vb <= 64: append nx below the valid bits (M and L only)
+        const uint32_t v = (uint32_t)vb - 32u;
+        M |= __funnelshift_rc(nx, 0u, v);                          // nx >> v, 0 when v == 32
+        L = __funnelshift_rc(0u, nx, v);                           // low word of (nx:0) >> v
         vb += 32;
-        nx = bswap32(nx2raw); nx2raw = load_raw(wnext); wnext++;
+        nx = bswap32(nx2raw); nx2raw = load_raw4(woff); woff += 4;
     }
-    // The same as `if (vb < 32) merge_word();` as straight-line predicated code: with 32 independent streams per warp
-    // some lane merges in almost every step, so a branch would cost every lane the divergent path plus its
+    // Drop nb <= 32 bits, then `if (vb <= 64) merge_word();` as straight-line predicated code: with 32 independent streams
+    // per warp some lane merges in almost every step, so a branch would cost every lane the divergent path plus its
     // reconvergence; the freshly loaded word is not touched before the next merge (no wait on the LDS).
-    __device__ __forceinline__ void merge_word_predicated() {
+    __device__ __forceinline__ void advance_predicated(uint32_t nb) {
+        H = __funnelshift_lc(M, H, nb);
+        M = __funnelshift_lc(L, M, nb);
+        L = __funnelshift_lc(0u, L, nb);
+        vb -= (int32_t)nb;
         asm volatile(
-            "{\n\t.reg .pred p;\n\t.reg .b32 t, a;\n\t"
-            "setp.lt.s32 p, %4, 32;\n\t"
-            "@p shf.r.clamp.b32 t, %2, 0, %4;\n\t"
+            "{\n\t.reg .pred p;\n\t.reg .b32 t, a, v;\n\t"
+            "setp.le.s32 p, %4, 64;\n\t"
+            "sub.s32 v, %4, 32;\n\t"
+            "@p shf.r.clamp.b32 t, %2, 0, v;\n\t"
             "@p or.b32 %0, %0, t;\n\t"
-            "@p sub.s32 t, 32, %4;\n\t"
-            "@p shf.l.clamp.b32 %1, 0, %2, t;\n\t"
+            "@p shf.r.clamp.b32 %1, 0, %2, v;\n\t"
             "@p add.s32 %4, %4, 32;\n\t"
             "@p prmt.b32 %2, %3, 0, 0x0123;\n\t"
-            "@p shl.b32 a, %5, 2;\n\t"
-            "@p and.b32 a, a, 252;\n\t"
+            "@p and.b32 a, %5, 252;\n\t"
             "@p xor.b32 a, a, %6;\n\t"
-            "@p add.u32 a, a, %7;\n\t"
             "@p ld.shared.u32 %3, [a];\n\t"
-            "@p add.u32 %5, %5, 1;\n\t"
+            "@p add.u32 %5, %5, 4;\n\t"
             "}\n"
-            : "+r"(hi), "+r"(lo), "+r"(nx), "+r"(nx2raw), "+r"(vb), "+r"(wnext)
-            : "r"(swz), "r"(sbase)
+            : "+r"(M), "+r"(L), "+r"(nx), "+r"(nx2raw), "+r"(vb), "+r"(woff)
+            : "r"(sx)
             : "memory");
     }
     __device__ __forceinline__ void consume(uint32_t nb) {         // nb <= 32
-        hi = __funnelshift_lc(lo, hi, nb);
-        lo = __funnelshift_lc(0u, lo, nb);
+        H = __funnelshift_lc(M, H, nb);
+        M = __funnelshift_lc(L, M, nb);
+        L = __funnelshift_lc(0u, L, nb);
         vb -= (int32_t)nb;
-        if (vb < 32) merge_word();
+        if (vb <= 64) merge_word();
     }
     // generic (rare) operations for headers, escapes and over-long codes; callers top up between them
     __device__ __forceinline__ uint32_t get(uint32_t nb) {          // nb in 0..32
-        const uint32_t v = __funnelshift_lc(hi, 0u, nb);            // hi >> (32 - nb), 0 for nb == 0
+        const uint32_t v = __funnelshift_lc(H, 0u, nb);             // H >> (32 - nb), 0 for nb == 0
         consume(nb);
         return v;
     }
@@ -171,7 +181,7 @@ struct BitReader {
     __device__ __forceinline__ uint32_t unary() {
         uint32_t q = 0;
         for (;;) {
-            if (hi) { const uint32_t z = __clz(hi); consume(z + 1); return q + z; }
+            if (H) { const uint32_t z = __clz(H); consume(z + 1); return q + z; }
             q += 32; consume(32);
             top_up();
             if (overrun()) return q;                                // ran past the frame: corrupt stream
@@ -190,17 +200,29 @@ struct BitReader {
     }
 };
 
-__global__ void __launch_bounds__(kDecThreads)
-k_skim_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__restrict__ streams, uint32_t n_streams,
-                 uint32_t channels, uint32_t bps, uint32_t blocksize, uint32_t total_frames,
-                 const unsigned long long *__restrict__ frame_pos, uint32_t *__restrict__ sub_bitoff,
-                 uint8_t *__restrict__ frame_chassign, uint32_t *__restrict__ status, uint32_t lanes_per_warp) {
-    __shared__ __align__(256) uint4 s_ring[kSkimRing * kDecThreads];
+// Publication protocol (fused skim + decode, see k_decode_subframes): sub_bitoff[] starts as kNotReady (host memset);
+// the skim thread of a frame stores each subframe's bit offset with release semantics as soon as the walk reaches it
+// (0 = bad frame, nothing to decode), the decode thread of that subframe polls it with acquire loads.
+constexpr uint32_t kNotReady = 0xFFFFFFFFu;
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void
+skim_role(uint4 *s_ring, uint32_t cta, const uint8_t *__restrict__ bytes, const DecStreamDev *__restrict__ streams, uint32_t n_streams,
+          uint32_t channels, uint32_t bps, uint32_t blocksize, uint32_t total_frames,
+          const unsigned long long *__restrict__ frame_pos, uint32_t *__restrict__ sub_bitoff,
+          uint8_t *__restrict__ frame_chassign, uint32_t *__restrict__ status, uint32_t lanes_per_warp) {
     // Only `lanes_per_warp` lanes of every warp take a frame: the walk is a long dependent chain, and there are far
     // fewer frames than the machine has thread slots, so spreading them over more warps buys latency hiding (and
     // less divergence per warp) for issue slots that would otherwise idle.
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t f = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * lanes_per_warp + lane;
+    const uint32_t f = (cta * (blockDim.x >> 5) + (threadIdx.x >> 5)) * lanes_per_warp + lane;
     // No lane leaves before the walk is over: the loop below re-converges the whole warp at every trip
     // (__any_sync).  Without that, lanes in different phases (batch / partition change / subframe header) ran
     // their phases one after the other and a warp executed 3.3x the batches a single lane needs
@@ -211,20 +233,22 @@ k_skim_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__restri
     FrameHdr h; h.header_bytes = 0; h.ch_assign = 0;
     uint32_t *off_out = sub_bitoff + (size_t)(done ? 0 : f) * channels;
     uint64_t frame_bit0 = 0;
+    uint32_t published = 0;                                   // entries [0, published) of off_out have been stored
     BitReader br;
     br.gq = (const uint4 *)bytes; br.sbase = (uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x * kSkimRing); br.swz = (lane & 15u) << 4;
-    br.wnext = 2; br.cissue = 0; br.qlast = 0; br.hi = br.lo = br.nx = br.nx2raw = 0; br.vb = 64;
-    if (lane < lanes_per_warp && f < total_frames) {
+    br.sx = br.sbase ^ br.swz; br.woff = 8; br.cissue = 0; br.qlast = 0; br.H = br.M = br.L = br.nx = br.nx2raw = 0; br.vb = 96;
+    if (lane < lanes_per_warp && f < total_frames && channels > 1) {
         L = locate_frame(streams, n_streams, blocksize, f, frame_pos, &st);
-        for (uint32_t c = 0; c < channels; c++) off_out[c] = 0;
         if (!L.ok) { atomicAdd(&status[0], 1u); done = true; }
         else if (!parse_frame_header(bytes + L.start, L.end - L.start, 0, bps, &h)) { atomicAdd(&status[2], 1u); done = true; }
         else {
             frame_chassign[f] = (uint8_t)h.ch_assign;
             frame_bit0 = L.start * 8;
-            off_out[0] = h.header_bytes * 8;
-            if (!done) br.init(br.sbase, lane, bytes, frame_bit0 + (uint64_t)h.header_bytes * 8, L.end);
+            st_release_u32(off_out, h.header_bytes * 8);
+            published = 1;
+            br.init(br.sbase, lane, bytes, frame_bit0 + (uint64_t)h.header_bytes * 8, L.end);
         }
+        if (done) { for (uint32_t q = 0; q < channels; q++) st_release_u32(off_out + q, 0u); published = channels; }
     }
     const uint32_t n = L.n;
     bool err = false, in_res = false;
@@ -240,12 +264,9 @@ k_skim_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__restri
             uint32_t maxlen = 0;
 #pragma unroll
             for (int i = 0; i < kSkimBatch; i++) {
-                const uint32_t len = (uint32_t)__clz(br.hi) + k1;
+                const uint32_t len = (uint32_t)__clz(br.window()) + k1;
                 maxlen = max(maxlen, len);
-                br.hi = __funnelshift_lc(br.lo, br.hi, len);
-                br.lo = __funnelshift_lc(0u, br.lo, len);
-                br.vb -= (int32_t)len;
-                br.merge_word_predicated();
+                br.advance_predicated(len);
             }
             if (maxlen <= 32) { left -= kSkimBatch; continue; }
             br = snap;
@@ -279,7 +300,7 @@ k_skim_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__restri
                 if (k == esc) { const uint32_t raw = br.get(5); br.seek(bytes, (uint64_t)raw * left, L.end); left = 0; }
                 if (left) break;
             }
-            if (!in_res) { c++; off_out[c] = (uint32_t)(br.bitpos() - frame_bit0); }
+            if (!in_res) { c++; st_release_u32(off_out + c, (uint32_t)(br.bitpos() - frame_bit0)); published = c + 1; }
             continue;
         }
         if (err || c + 1 >= channels) { done = true; continue; }
@@ -325,15 +346,17 @@ k_skim_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__restri
                     if (psize == 0) { err = true; break; }
                 }
             }
-            if (!in_res) { c++; off_out[c] = (uint32_t)(br.bitpos() - frame_bit0); }
+            if (!in_res) { c++; st_release_u32(off_out + c, (uint32_t)(br.bitpos() - frame_bit0)); published = c + 1; }
         }
         if (err) done = true;
     }
     const bool mine = lane < lanes_per_warp && f < total_frames && channels > 1 && L.ok && h.header_bytes != 0;
     if (mine && !err && br.bitpos() > L.end * 8) err = true;
-    if (mine && err) {
-        atomicAdd(&status[2], 1u);
-        for (uint32_t q = 0; q < channels; q++) off_out[q] = 0;
+    if (mine) {
+        if (err) atomicAdd(&status[2], 1u);
+        // whatever the walk did not reach is published as "bad" so that no decode thread waits for ever; subframes
+        // already handed out are decoded (their threads notice the damage themselves) and the call reports the error
+        for (uint32_t q = published; q < channels; q++) st_release_u32(off_out + q, 0u);
     }
 }
 
@@ -364,67 +387,91 @@ struct SubCtx {
 
 constexpr int kDecBatch = 8;      // samples decoded per branch-free batch
 
-// FIXED / LPC subframe body.  Called by ALL lanes of the warp (`active` false for lanes without a predictive
-// subframe): the sample loop re-converges the warp at every trip, and a trip is either one batch of kDecBatch
-// Rice codes parsed without data-dependent branches (predicated word merges, see BitReader) followed by the
-// predictor recursion from the register history, or a single sample through the generic path (escape-coded
-// partitions, partition tails, codes longer than 32 bits).
-template <int MAXORD, bool WIDE>
-__device__ __forceinline__ void decode_predictive(SubCtx &S, bool active) {
+// FIXED / LPC subframe, part 1 (per lane, divergent): warm-up samples, predictor, residual coding header and the
+// first partition's parameter.  Run BEFORE the warp picks its sample loop, so that the loop can use libFLAC's
+// 32-bit rule with the subframe's ACTUAL coefficient precision (16-bit audio coded by libFLAC has precision <= 12
+// and never needs 64-bit accumulation; assuming the maximum of 15 sent every LPC subframe down the 64-bit path).
+template <int PMAX>
+struct PredState {
+    int32_t hist[PMAX];      // hist[PMAX-1] = newest warm-up sample
+    int32_t cf[PMAX];        // cf[q] multiplies the sample q+1 back; 0 beyond the order
+    int shift;
+    uint32_t k, plen, esc, psize, part_left, raw_bits, i;
+    bool escape, wide;
+};
+template <int PMAX>
+__device__ __forceinline__ void decode_prologue(SubCtx &S, bool active, PredState<PMAX> &P) {
     BitReader &br = S.br;
     const uint32_t n = S.n, order = S.order, wasted = S.wasted;
+#pragma unroll
+    for (int q = 0; q < PMAX; q++) { P.hist[q] = 0; P.cf[q] = 0; }
+    P.shift = 0; P.k = 0; P.plen = 4; P.esc = 15; P.psize = 0; P.part_left = 0; P.raw_bits = 0; P.i = n;
+    P.escape = false; P.wide = false;
+    if (!active) return;
+    for (uint32_t w = 0; w < order; w++) {
+        const int32_t v = br.get_signed(S.sbps);
+#pragma unroll
+        for (int q = 0; q < PMAX - 1; q++) P.hist[q] = P.hist[q + 1];
+        P.hist[PMAX - 1] = v;
+        S.dst[w] = (int32_t)((uint32_t)v << wasted);
+    }
+    br.top_up();
+    if (S.type == 3) {
+        const uint32_t prec = br.get(4) + 1;
+        const uint32_t sh = br.get(5);
+        if (prec == 16 || (sh & 16)) S.err = true;
+        P.shift = (int)sh;
+#pragma unroll
+        for (int q = 0; q < PMAX; q++) if ((uint32_t)q < order) { P.cf[q] = br.get_signed(prec); if ((q & 7) == 7) br.top_up(); }
+        br.top_up();
+        // libFLAC's rule: 32-bit arithmetic is exact when bps + precision + ilog2(order) <= 32
+        P.wide = S.sbps + prec + (uint32_t)(31 - __clz(order | 1u)) > 32u;
+    } else {
+        if (order >= 1) P.cf[0] = order == 1 ? 1 : order == 2 ? 2 : order == 3 ? 3 : 4;
+        if (order >= 2) P.cf[1] = order == 2 ? -1 : order == 3 ? -3 : -6;
+        if (order >= 3) P.cf[2] = order == 3 ? 1 : 4;
+        if (order >= 4) P.cf[3] = -1;
+        P.wide = S.sbps + order > 32u;
+    }
+    const uint32_t m = br.get(2);
+    const uint32_t po = br.get(4);
+    P.plen = m ? 5u : 4u; P.esc = m ? 31u : 15u;
+    P.psize = n >> po;
+    if (m > 1 || (po > 0 && (n & ((1u << po) - 1))) || P.psize < order) S.err = true;
+    if (!S.err) {
+        P.k = br.get(P.plen);
+        P.escape = (P.k == P.esc);
+        P.raw_bits = P.escape ? br.get(5) : 0;
+        P.part_left = P.psize - order;
+        P.i = order;
+        while (P.part_left == 0 && P.i < n) {
+            if (P.psize == 0) { S.err = true; break; }
+            P.k = br.get(P.plen); P.escape = (P.k == P.esc); P.raw_bits = P.escape ? br.get(5) : 0; P.part_left = P.psize;
+        }
+        if (S.err) P.i = n;
+    }
+}
+
+// Part 2.  Called by ALL lanes of the warp (lanes without a predictive subframe arrive with i == n): the sample loop
+// re-converges the warp at every trip, and a trip is either one batch of kDecBatch Rice codes parsed without
+// data-dependent branches (predicated word merges, see BitReader) followed by the predictor recursion from the
+// register history, or a single sample through the generic path (escape-coded partitions, partition tails, codes
+// longer than 32 bits).
+template <int MAXORD, bool WIDE, int PMAX>
+__device__ __forceinline__ void decode_predictive(SubCtx &S, const PredState<PMAX> &P) {
+    BitReader &br = S.br;
+    const uint32_t n = S.n, wasted = S.wasted;
     int32_t *dst = S.dst;
     int32_t H[MAXORD + kDecBatch];
     int32_t cf[MAXORD];
 #pragma unroll
-    for (int q = 0; q < MAXORD + kDecBatch; q++) H[q] = 0;
+    for (int q = 0; q < MAXORD; q++) { H[q] = P.hist[PMAX - MAXORD + q]; cf[q] = P.cf[q]; }
 #pragma unroll
-    for (int q = 0; q < MAXORD; q++) cf[q] = 0;
-    int shift = 0;
-    uint32_t k = 0, plen = 4, esc = 15, psize = 0, part_left = 0, raw_bits = 0, i = n;
-    bool escape = false;
-    if (active) {
-        // warm-up samples
-        for (uint32_t w = 0; w < order; w++) {
-            const int32_t v = br.get_signed(S.sbps);
-#pragma unroll
-            for (int q = 0; q < MAXORD - 1; q++) H[q] = H[q + 1];
-            H[MAXORD - 1] = v;
-            dst[w] = (int32_t)((uint32_t)v << wasted);
-        }
-        br.top_up();
-        if (S.type == 3) {
-            const uint32_t prec = br.get(4) + 1;
-            const uint32_t sh = br.get(5);
-            if (prec == 16 || (sh & 16)) S.err = true;
-            shift = (int)sh;
-#pragma unroll
-            for (int q = 0; q < MAXORD; q++) if ((uint32_t)q < order) cf[q] = br.get_signed(prec);
-            br.top_up();
-        } else {
-            if (order >= 1) cf[0] = order == 1 ? 1 : order == 2 ? 2 : order == 3 ? 3 : 4;
-            if (MAXORD > 1 && order >= 2) cf[1] = order == 2 ? -1 : order == 3 ? -3 : -6;
-            if (MAXORD > 2 && order >= 3) cf[2] = order == 3 ? 1 : 4;
-            if (MAXORD > 3 && order >= 4) cf[3] = -1;
-        }
-        const uint32_t m = br.get(2);
-        const uint32_t po = br.get(4);
-        plen = m ? 5u : 4u; esc = m ? 31u : 15u;
-        psize = n >> po;
-        if (m > 1 || (po > 0 && (n & ((1u << po) - 1))) || psize < order) S.err = true;
-        if (!S.err) {
-            k = br.get(plen);
-            escape = (k == esc);
-            raw_bits = escape ? br.get(5) : 0;
-            part_left = psize - order;
-            i = order;
-            while (part_left == 0 && i < n) {
-                if (psize == 0) { S.err = true; break; }
-                k = br.get(plen); escape = (k == esc); raw_bits = escape ? br.get(5) : 0; part_left = psize;
-            }
-            if (S.err) i = n;
-        }
-    }
+    for (int q = MAXORD; q < MAXORD + kDecBatch; q++) H[q] = 0;
+    const int shift = P.shift;
+    uint32_t k = P.k, part_left = P.part_left, raw_bits = P.raw_bits, i = P.i;
+    const uint32_t plen = P.plen, esc = P.esc, psize = P.psize;
+    bool escape = P.escape;
     while (__any_sync(0xFFFFFFFFu, i < n)) {
         if (i >= n) continue;
         br.top_up();
@@ -436,15 +483,13 @@ __device__ __forceinline__ void decode_predictive(SubCtx &S, bool active) {
             uint32_t maxlen = 0, u[kDecBatch];
 #pragma unroll
             for (int j = 0; j < kDecBatch; j++) {
-                const uint32_t z = (uint32_t)__clz(br.hi);
+                const uint32_t win = br.window();
+                const uint32_t z = (uint32_t)__clz(win);
                 const uint32_t len = z + k1;
                 maxlen = max(maxlen, len);
-                const uint32_t t = __funnelshift_lc(0u, br.hi, z + 1);      // hi << (z+1), 0 when z+1 == 32
+                const uint32_t t = __funnelshift_lc(0u, win, z + 1);        // win << (z+1), 0 when z+1 == 32
                 u[j] = (z << k) | __funnelshift_lc(t, 0u, k);               // | t >> (32-k), 0 when k == 0
-                br.hi = __funnelshift_lc(br.lo, br.hi, len);
-                br.lo = __funnelshift_lc(0u, br.lo, len);
-                br.vb -= (int32_t)len;
-                br.merge_word_predicated();
+                br.advance_predicated(len);
             }
             if (maxlen <= 32) {
 #pragma unroll
@@ -487,22 +532,49 @@ __device__ __forceinline__ void decode_predictive(SubCtx &S, bool active) {
 #ifndef FRB_DEC_MINB
 #define FRB_DEC_MINB 4
 #endif
+// Fused skim + decode.  The first `n_skim_ctas` CTAs (lowest block indices, dispatched first) walk the frames and
+// publish subframe offsets as they go; the remaining CTAs decode one subframe per thread in CHANNEL-MAJOR order
+// (all subframes 0, then all subframes 1, ...), each waiting for its offset.  The walk of a frame reaches channel c
+// after c/(C-1) of its run time, so the decode of channel c overlaps the walk of channels c+1.. instead of
+// starting when the whole skim kernel has drained (5.0 -> see DESIGN.md section 4 for the measured step).  Forward
+// progress: skim CTAs never wait, and they are resident before any waiting CTA is dispatched (the same in-order
+// dispatch assumption as a decoupled look-back scan); a waiting thread gives up after kSpinLimit polls (status[5]).
+constexpr uint32_t kSpinLimit = 1u << 22;
+#ifdef FRB_DEC_TIMING
+__device__ unsigned long long g_dec_dbg[16];
+#endif
 template <bool BIGORDER>
 __global__ void __launch_bounds__(kDecThreads, BIGORDER ? 1 : FRB_DEC_MINB)
 k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__restrict__ streams, uint32_t n_streams,
                    uint32_t channels, uint32_t bps, uint32_t blocksize, uint32_t total_frames,
-                   const unsigned long long *__restrict__ frame_pos, const uint32_t *__restrict__ sub_bitoff,
-                   int32_t *__restrict__ audio, uint8_t *__restrict__ frame_chassign, uint32_t *__restrict__ status) {
+                   const unsigned long long *__restrict__ frame_pos, uint32_t *__restrict__ sub_bitoff,
+                   int32_t *__restrict__ audio, uint8_t *__restrict__ frame_chassign, uint32_t *__restrict__ status,
+                   uint32_t n_skim_ctas, uint32_t skim_lanes) {
     __shared__ __align__(256) uint4 s_ring[kSkimRing * kDecThreads];
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+#ifdef FRB_DEC_TIMING
+    unsigned long long t_start; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+    if (threadIdx.x == 0) atomicMin(&g_dec_dbg[0], t_start);
+#endif
+    if (blockIdx.x < n_skim_ctas) {
+        skim_role(s_ring, blockIdx.x, bytes, streams, n_streams, channels, bps, blocksize, total_frames, frame_pos, sub_bitoff,
+                  frame_chassign, status, skim_lanes);
+#ifdef FRB_DEC_TIMING
+        unsigned long long t_end; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        if (threadIdx.x == 0) atomicMax(&g_dec_dbg[1], t_end);
+#endif
+        return;
+    }
+    const uint32_t s = (blockIdx.x - n_skim_ctas) * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t total_sub = total_frames * channels;
     bool alive = s < total_sub;
-    const uint32_t f = alive ? s / channels : 0, c = alive ? s - f * channels : 0;
+    // channel-major: a warp holds 32 consecutive frames of ONE channel (similar predictor orders, and their offsets
+    // are published by one skim warp at about the same time)
+    const uint32_t c = alive ? s / total_frames : 0, f = alive ? s - c * total_frames : 0;
     SubCtx S;
     S.err = false; S.type = 0; S.order = 0; S.n = 0; S.wasted = 0; S.sbps = bps; S.dst = audio; S.aligned16 = false;
     S.br.gq = (const uint4 *)bytes; S.br.sbase = (uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x * kSkimRing);
-    S.br.swz = (lane & 15u) << 4; S.br.wnext = 2; S.br.cissue = 0; S.br.qlast = 0; S.br.hi = S.br.lo = S.br.nx = S.br.nx2raw = 0; S.br.vb = 64;
+    S.br.swz = (lane & 15u) << 4; S.br.sx = S.br.sbase ^ S.br.swz; S.br.woff = 8; S.br.cissue = 0; S.br.qlast = 0; S.br.H = S.br.M = S.br.L = S.br.nx = S.br.nx2raw = 0; S.br.vb = 96;
     FrameLoc L; L.ok = false; L.start = L.end = 0; L.k = 0; L.n = 0;
     uint32_t hdr_bytes = 0;
     if (alive) {
@@ -513,7 +585,13 @@ k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__rest
             uint32_t ch_assign = 0;
             uint64_t bit0;
             if (sub_bitoff) {
-                const uint32_t off = sub_bitoff[s];
+                const uint32_t *slot = sub_bitoff + (size_t)f * channels + c;
+                uint32_t off = ld_acquire_u32(slot), spins = 0;
+                while (off == kNotReady) {
+                    __nanosleep(200);
+                    off = ld_acquire_u32(slot);
+                    if (++spins > kSpinLimit) { atomicAdd(&status[5], 1u); off = 0; }
+                }
                 if (off == 0) alive = false;               // the skim pass already counted the error
                 bit0 = L.start * 8 + off;
                 ch_assign = frame_chassign[f];
@@ -546,16 +624,6 @@ k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__rest
         }
     }
     const bool run = alive && !S.err;
-    // warp-uniform code path: taps padded to the largest order in the warp, 64-bit MACs if any lane needs them
-    uint32_t my_ord = (run && S.type >= 2) ? S.order : 0;
-    if (!BIGORDER && my_ord > 12) { my_ord = 0; }
-    const uint32_t cls = __reduce_max_sync(0xFFFFFFFFu, my_ord);
-    bool wide_lane = false;
-    if (run && S.type >= 2) {
-        // libFLAC's rule: 32-bit arithmetic is exact when bps + precision + ilog2(order) <= 32 (fixed: bps + order)
-        wide_lane = S.sbps + (S.type == 3 ? 15u + (uint32_t)(31 - __clz(S.order | 1u)) : S.order) > 32u;
-    }
-    const bool wide = __any_sync(0xFFFFFFFFu, wide_lane);
     if (run) {
         if (S.type == 0) {
             const int32_t v = (int32_t)((uint32_t)S.br.get_signed(S.sbps) << S.wasted);
@@ -571,13 +639,25 @@ k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__rest
         }
     }
     {
-        // every lane of the warp enters the same instantiation (the sample loop is warp-synchronous)
+        constexpr int PMAX = BIGORDER ? 32 : 12;
         const bool act = run && S.type >= 2 && (BIGORDER || S.order <= 12);
-        if (BIGORDER) decode_predictive<32, true>(S, act);
-        else if (cls <= 4) { if (wide) decode_predictive<4, true>(S, act); else decode_predictive<4, false>(S, act); }
-        else if (cls <= 8) { if (wide) decode_predictive<8, true>(S, act); else decode_predictive<8, false>(S, act); }
-        else { if (wide) decode_predictive<12, true>(S, act); else decode_predictive<12, false>(S, act); }
+        PredState<PMAX> P;
+        decode_prologue<PMAX>(S, act, P);
+        // warp-uniform sample loop (it is warp-synchronous): taps padded to the largest order in the warp, 64-bit MACs
+        // only if a lane needs them
+        const uint32_t cls = __reduce_max_sync(0xFFFFFFFFu, act ? S.order : 0u);
+        const bool wide = __any_sync(0xFFFFFFFFu, act && P.wide);
+        if (BIGORDER) decode_predictive<32, true, PMAX>(S, P);
+        else if (cls <= 4) { if (wide) decode_predictive<4, true, PMAX>(S, P); else decode_predictive<4, false, PMAX>(S, P); }
+        else if (cls <= 8) { if (wide) decode_predictive<8, true, PMAX>(S, P); else decode_predictive<8, false, PMAX>(S, P); }
+        else { if (wide) decode_predictive<12, true, PMAX>(S, P); else decode_predictive<12, false, PMAX>(S, P); }
     }
+#ifdef FRB_DEC_TIMING
+    {
+        unsigned long long t_end; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        if (threadIdx.x == 0) { atomicMax(&g_dec_dbg[2], t_end); atomicMax(&g_dec_dbg[3 + (c & 7)], t_end); atomicMin(&g_dec_dbg[11], t_start); }
+    }
+#endif
     if (alive) {
         if (!S.err && c + 1 == channels) {
             // the last subframe must end (after byte padding) exactly 2 bytes before the next frame

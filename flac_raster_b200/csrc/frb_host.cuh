@@ -142,6 +142,7 @@ extern "C" int frb_host_decode(const uint8_t *frames, size_t n_bytes, uint32_t c
         if (h_status[4] && attempt == 0) { p.reserved = 32; continue; }   // LPC order > 12: rerun the wide kernel
         break;
     }
+    if (h_status[5]) return FRB_ERR_CUDA;                       // a decode thread gave up waiting for its subframe offset
     if (h_status[0] || h_status[2]) return FRB_ERR_BAD_STREAM;
     if (h_status[1]) return FRB_ERR_CRC;
     if (channels == 1) {

@@ -276,10 +276,13 @@ class Engine:
 
     # ------------------------------------------------------------------ decode
     def decode_streams(self, data: torch.Tensor, byte_offsets: np.ndarray, byte_lengths: np.ndarray, n_samples: np.ndarray,
-                       sample_rates: np.ndarray, channels: int, bps: int, blocksize: int = 4096, verify_crc: bool = True):
+                       sample_rates: np.ndarray, channels: int, bps: int, blocksize: int = 4096, verify_crc: bool = True,
+                       sync: bool = True, name: str = "dec"):
         """Frames of many streams (device bytes) -> int32 planar audio on the device.
 
-        data must be readable 16 bytes past the last stream.  Returns (audio, audio_base, status[8])."""
+        data must be readable 16 bytes past the last stream.  Returns (audio, audio_base, status[8]).
+        sync=False leaves everything queued on the current stream and returns the status words as a device tensor
+        (the caller checks them, and status[4] != 0 means the stream needs the wide-order kernel: rerun with sync)."""
         n_streams = len(n_samples)
         n_samples = np.asarray(n_samples, dtype=np.int64)
         frames_per = (n_samples + blocksize - 1) // blocksize
@@ -298,23 +301,25 @@ class Engine:
         total = int((n_samples * channels).sum())
         with torch.cuda.device(self.device):
             s = _stream_ptr()
-            audio = self._buf("dec_audio", total * 4)
+            audio = self._buf(name + "_audio", total * 4)
             d_status = torch.zeros(8, dtype=torch.int32, device=self.device)
             status = None
             for max_order in (12, 32):
                 p = nat.DecodeParams(n_streams, channels, bps, blocksize, 1 if verify_crc else 0, max_order)
                 ws_bytes = C.c_size_t(0)
                 nat.check(self.L.frb_decode_workspace_size(C.byref(p), total_frames, C.byref(ws_bytes)), "frb_decode_workspace_size")
-                ws = self._buf("dec_ws", ws_bytes.value)
+                ws = self._buf(name + "_ws", ws_bytes.value)
                 nat.check(self.L.frb_decode_batch(C.byref(p), st.ctypes.data, data.data_ptr(), total_frames, audio.data_ptr(),
                                                   ws.data_ptr(), ws.numel(), d_status.data_ptr(), s), "frb_decode_batch")
+                if not sync:
+                    return audio, base, d_status
                 status = d_status.cpu().numpy().astype(np.int64)
                 if status[4] == 0:
                     break
         return audio, base, status
 
     def denormalize_tiles(self, audio: torch.Tensor, audio_base: np.ndarray, tiles: np.ndarray, minmax: np.ndarray,
-                          scale: float, out: torch.Tensor):
+                          scale: float, out: torch.Tensor, sync: bool = True):
         """int32 planar audio -> windows of the (bands,H,W) device raster `out` (denormalize_from_audio, int path)."""
         bands, H, W = out.shape
         dt = str(out.dtype).replace("torch.", "")
@@ -328,7 +333,11 @@ class Engine:
                                                    d_mm.data_ptr(), float(scale), out.data_ptr(), nat.DTYPE_CODES[dt],
                                                    bands, H, W, mws.data_ptr(), mws.numel(), s), "frb_denormalize_tiles")
             # keep the staging tensors alive until the kernel has consumed them
-            torch.cuda.current_stream().synchronize()
+            if sync:
+                torch.cuda.current_stream().synchronize()
+            else:
+                for t in (d_tiles, d_base, d_mm):
+                    t.record_stream(torch.cuda.current_stream())
         return out
 
 

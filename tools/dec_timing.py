@@ -1,0 +1,24 @@
+#!/usr/bin/env python
+"""Debug: role timeline of the fused skim+decode kernel (needs a -DFRB_DEC_TIMING build at /tmp/libfrb_timing.so)."""
+import ctypes as C, os, sys
+from pathlib import Path
+import numpy as np, torch
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from flac_raster_b200 import _native as nat, synth
+from flac_raster_b200.engine import Engine, tile_grid
+dev = torch.device("cuda", 0)
+eng = Engine(dev)
+L = nat.lib()
+raster = synth.sentinel2_like(10980, 10980, 8, device=dev)
+tiles = tile_grid(10980, 10980, 1024)
+enc = eng.encode_tiles(raster, tiles, 5)
+payload = torch.cat([enc.payload, torch.zeros(64, dtype=torch.uint8, device=dev)])
+dbg = (C.c_ulonglong * 16)()
+for it in range(3):
+    L.frb_debug_decode_timing(None, 1)
+    audio, base, st = eng.decode_streams(payload, enc.offsets, enc.sizes, enc.n_samples, enc.sample_rates, 8, 16, 4096)
+    torch.cuda.synchronize()
+    L.frb_debug_decode_timing(dbg, 0)
+    t0 = dbg[0]
+    print("skim end %.3f ms, decode end %.3f ms, first decode CTA start %.3f; per-channel decode end:" % ((dbg[1]-t0)/1e6, (dbg[2]-t0)/1e6, (dbg[11]-t0)/1e6),
+          " ".join("%.2f" % ((dbg[3+c]-t0)/1e6) for c in range(8)), "status", st[:6])
