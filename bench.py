@@ -320,10 +320,9 @@ def main():
     scale = 32767.0 if enc.bits_per_sample == 16 else 8388607.0
 
     def decode_step():
-        audio, base, status = eng.decode_streams(payload, enc.offsets, enc.sizes, enc.n_samples, enc.sample_rates,
-                                                 nb, enc.bps, enc.blocksize)
-        eng.denormalize_tiles(audio, base, tiles, enc.minmax, scale, out)
-        return status
+        # frames -> raster in one fused launch (sync scan, then skim + Rice decode + predictor restore + denormalise; CRC-16
+        # beside it); the status read-back is part of the step
+        return eng.decode_tiles(payload, enc.offsets, enc.sizes, tiles, enc.sample_rates, enc.minmax, scale, out, enc.bps, enc.blocksize)
 
     for _ in range(args.warmup):
         st = decode_step()

@@ -81,7 +81,7 @@ _EXPORTS = [
     "frb_minmax_tiles", "frb_normalize_tiles", "frb_denormalize_tiles", "frb_sample_map_workspace_size",
     "frb_minmax_flat", "frb_normalize_flat", "frb_denormalize_flat", "frb_selftest_division",
     "frb_encode_workspace_size", "frb_encode_analyse", "frb_encode_emit",
-    "frb_decode_workspace_size", "frb_decode_batch", "frb_probe_stream",
+    "frb_decode_workspace_size", "frb_decode_batch", "frb_decode_tiles", "frb_probe_stream",
     "frb_host_encode", "frb_host_decode",
     "frb_stream_encoder_new", "frb_stream_encoder_delete", "frb_stream_encoder_set_channels",
     "frb_stream_encoder_set_bits_per_sample", "frb_stream_encoder_set_sample_rate",
@@ -126,6 +126,7 @@ def lib():
     L.frb_encode_emit.argtypes = [C.POINTER(EncodeParams), vp, sz, vp, vp, sz, vp, vp]
     L.frb_decode_workspace_size.argtypes = [C.POINTER(DecodeParams), u64, C.POINTER(sz)]
     L.frb_decode_batch.argtypes = [C.POINTER(DecodeParams), vp, vp, u64, vp, vp, sz, vp, vp]
+    L.frb_decode_tiles.argtypes = [C.POINTER(DecodeParams), vp, vp, u64, vp, vp, C.c_double, vp, C.c_int, u32, u32, u32, vp, sz, vp, vp]
     L.frb_probe_stream.argtypes = [vp, u64, u64, u32, u32, u32, u32, C.POINTER(u64), C.POINTER(u64), vp]
     L.frb_host_encode.argtypes = [vp, u64, u32, u32, u32, u32, u32, u64, vp, sz, C.POINTER(sz), vp, sz, C.POINTER(sz)]
     L.frb_host_decode.argtypes = [vp, sz, u32, u32, u32, u32, u64, vp, sz, C.POINTER(u64)]

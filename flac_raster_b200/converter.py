@@ -248,11 +248,6 @@ def decode_tile_blobs(blobs, headers, metadatas, mosaic=None):
     stage_np[pos:pos + 64] = 0
     data = eng._buf("dec_data", pos + 64)[:pos + 64]
     data.copy_(stage[:pos + 64], non_blocking=True)
-    audio, base, status = eng.decode_streams(data, offs, lens, nsamp, rates, channels, bps, blocksize)
-    if status[0] or status[2]:
-        raise ValueError(f"malformed FLAC stream (missing frames={status[0]}, parse errors={status[2]})")
-    if status[1]:
-        raise ValueError(f"FLAC frame CRC-16 mismatch in {status[1]} frame(s)")
     dtype = np.dtype(metadatas[0]["dtype"])
     # decode default scale by audio width (converter.py:220-229)
     scale = float(metadatas[0].get("scale_factor") or (32767 if bps == 16 else 8388607))
@@ -260,7 +255,14 @@ def decode_tile_blobs(blobs, headers, metadatas, mosaic=None):
         scale = 32767.0
     out = torch.zeros(channels * row * maxw * dtype.itemsize, dtype=torch.uint8, device=eng.device)
     out = out.view(TORCH_DTYPES[str(dtype)]).reshape(channels, row, maxw)
-    eng.denormalize_tiles(audio, base, tiles, minmax, scale, out)
+    # one fused launch: Rice decode + predictor restore + denormalise straight into the tile windows
+    status = eng.decode_tiles(data, offs, lens, tiles, rates, minmax, scale, out, bps, blocksize)
+    if status[5]:
+        raise RuntimeError("decode kernel timed out waiting for a subframe offset")
+    if status[0] or status[2]:
+        raise ValueError(f"malformed FLAC stream (missing frames={status[0]}, parse errors={status[2]})")
+    if status[1]:
+        raise ValueError(f"FLAC frame CRC-16 mismatch in {status[1]} frame(s)")
     # D2H through a pinned buffer, then every tile becomes its own array (the buffer is reused by the next call);
     # the per-tile copies run on a few threads (numpy releases the GIL while copying)
     nbytes = out.numel() * dtype.itemsize

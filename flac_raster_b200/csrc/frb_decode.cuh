@@ -204,11 +204,11 @@ extern "C" int frb_decode_workspace_size(const frb_decode_params *p, uint64_t to
     return FRB_OK;
 }
 
-extern "C" int frb_decode_batch(const frb_decode_params *p, const frb_decode_stream *h_streams,
-                                const uint8_t *d_bytes, uint64_t total_frames, int32_t *d_audio,
-                                void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream) {
-    using namespace frb;
-    if (!p || !h_streams || !d_bytes || !d_audio || !d_workspace || !d_status) return FRB_ERR_INVALID_ARG;
+namespace frb {
+static int decode_batch_impl(const frb_decode_params *p, const frb_decode_stream *h_streams,
+                             const uint8_t *d_bytes, uint64_t total_frames, int32_t *d_audio,
+                             void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream, const SinkCfg &sink) {
+    if (!p || !h_streams || !d_bytes || (!d_audio && sink.dtype < 0) || !d_workspace || !d_status) return FRB_ERR_INVALID_ARG;
     if (p->n_streams == 0 || p->channels < 1 || p->channels > FRB_MAX_CHANNELS || p->blocksize < 16 ||
         p->blocksize > 65535 || p->bps < 4 || p->bps > 32) return FRB_ERR_INVALID_ARG;
     if (total_frames == 0 || total_frames > 0x7FFFFFFFull) return FRB_ERR_INVALID_ARG;
@@ -294,24 +294,51 @@ extern "C" int frb_decode_batch(const frb_decode_params *p, const frb_decode_str
         const uint32_t grid = n_skim_ctas + (uint32_t)((total_sub + kDecThreads - 1) / kDecThreads);
         const bool big = p->reserved > 12;
         prof_begin(1, s);
-        if (!big)
-            k_decode_subframes<false><<<grid, kDecThreads, 0, s>>>(d_bytes, w.streams, p->n_streams, p->channels, p->bps, p->blocksize,
-                                                          (uint32_t)total_frames, w.frame_pos, sub_bitoff, d_audio, w.chassign, d_status,
-                                                          n_skim_ctas, skim_lanes);
-        else
-            k_decode_subframes<true><<<grid, kDecThreads, 0, s>>>(d_bytes, w.streams, p->n_streams, p->channels, p->bps, p->blocksize,
-                                                         (uint32_t)total_frames, w.frame_pos, sub_bitoff, d_audio, w.chassign, d_status,
-                                                         n_skim_ctas, skim_lanes);
+#define FRB_DECODE(BIG, RAS) k_decode_subframes<BIG, RAS><<<grid, kDecThreads, 0, s>>>(d_bytes, w.streams, p->n_streams, p->channels, p->bps, \
+            p->blocksize, (uint32_t)total_frames, w.frame_pos, sub_bitoff, d_audio, w.chassign, d_status, n_skim_ctas, skim_lanes, sink)
+        if (sink.dtype < 0) { if (big) FRB_DECODE(true, false); else FRB_DECODE(false, false); }
+        else { if (big) FRB_DECODE(true, true); else FRB_DECODE(false, true); }
+#undef FRB_DECODE
         prof_end(1, s);
         FRB_LAUNCH_CHECK("k_decode_subframes");
     }
     if (p->verify_crc16) FRB_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
-    if (p->channels == 2) {
+    if (p->channels == 2 && sink.dtype < 0) {
         k_stereo_fix<<<(uint32_t)total_frames, 128, 0, s>>>(w.streams, p->n_streams, p->blocksize, (uint32_t)total_frames,
                                                            w.chassign, w.frame_pos, d_audio);
         FRB_LAUNCH_CHECK("k_stereo_fix");
     }
     return FRB_OK;
+}
+}  // namespace frb
+
+extern "C" int frb_decode_batch(const frb_decode_params *p, const frb_decode_stream *h_streams,
+                                const uint8_t *d_bytes, uint64_t total_frames, int32_t *d_audio,
+                                void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream) {
+    frb::SinkCfg sink;
+    memset(&sink, 0, sizeof sink);
+    sink.dtype = -1;
+    return frb::decode_batch_impl(p, h_streams, d_bytes, total_frames, d_audio, d_workspace, workspace_bytes, d_status, stream, sink);
+}
+
+extern "C" int frb_decode_tiles(const frb_decode_params *p, const frb_decode_stream *h_streams,
+                                const uint8_t *d_bytes, uint64_t total_frames,
+                                const frb_tile *d_tiles, const double *d_minmax, double scale,
+                                void *d_raster, int dtype, uint32_t bands, uint32_t H, uint32_t W,
+                                void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream) {
+    using namespace frb;
+    if (!p || !d_tiles || !d_minmax || !d_raster || dtype < 0 || dtype > FRB_F64 || !(scale > 0.0)) return FRB_ERR_INVALID_ARG;
+    if (bands != p->channels) return FRB_ERR_INVALID_ARG;
+    // two-channel streams may carry left/side, side/right or mid/side frames, whose samples only exist after both
+    // subframes have been decoded: those go through frb_decode_batch + frb_denormalize_tiles
+    if (p->channels == 2) return FRB_ERR_UNSUPPORTED;
+    static const uint32_t esz[8] = {1, 1, 2, 2, 4, 4, 4, 8};
+    SinkCfg sink;
+    sink.dtype = dtype; sink.esize = esz[dtype]; sink.H = H; sink.W = W; sink.tiles = d_tiles; sink.minmax = d_minmax;
+    sink.raster = (uint8_t *)d_raster; sink.scale = scale; sink.rcp = 1.0 / scale;
+    sink.fast = (scale == 32767.0 || scale == 8388607.0 || scale == 2147483647.0) ? 1 : 0;
+    sink.intpath = (dtype <= FRB_I16 && scale == 32767.0) ? 1 : 0;      // integer min/max, range < 2^16, |audio| <= 32767
+    return decode_batch_impl(p, h_streams, d_bytes, total_frames, nullptr, d_workspace, workspace_bytes, d_status, stream, sink);
 }
 
 #ifdef FRB_DEC_TIMING

@@ -377,8 +377,32 @@ __device__ __forceinline__ int32_t lpc_predict(const int32_t (&cf)[MAXORD], cons
     }
 }
 
+// Optional fused denormalise: instead of the planar int32 audio buffer, a decode thread can write its samples straight
+// into the window of the (bands,H,W) raster that its tile covers (denormalize_from_audio, normalization.py:222-249,
+// same fp64 operation order as k_denormalize_tiles).  This removes the audio round trip through HBM (4 B written +
+// 4 B read per sample) and the separate mapping kernel.  Uniform per launch:
+struct SinkCfg {
+    int dtype;               // FRB_U8..FRB_F64, or -1: plain audio output
+    uint32_t esize;          // bytes per raster element
+    uint32_t H, W;           // raster height / width
+    const frb_tile *tiles;   // one per stream (stream i carries tile i, bands == channels)
+    const double *minmax;    // {min,max} per tile
+    uint8_t *raster;
+    double scale, rcp;
+    int fast;                // scale is one of the three reference constants (exact reciprocal division)
+    int intpath;             // 8/16-bit integer raster + scale 32767: exact integer evaluation of the fp64 formula (sink_px)
+};
+struct RasterPos {           // per thread
+    uint8_t *rowp;           // first pixel of the current row of this tile/band window
+    uint32_t x, w, pitch;    // position inside the row, row length (pixels), raster row pitch in bytes
+    double mn, range;        // fp64 path
+    int32_t imn;             // integer path: data_min - 1, data_max - data_min (integers for integer rasters, range < 2^16)
+    uint32_t irange, kround; // kround = 32767*range + 32767 + 65534 (see sink_px)
+};
+
 struct SubCtx {
     BitReader br;
+    RasterPos rp;
     int32_t *dst;            // first sample of this subframe in the planar audio buffer
     uint32_t n, order, sbps, wasted, type;
     bool aligned16;
@@ -386,6 +410,121 @@ struct SubCtx {
 };
 
 constexpr int kDecBatch = 8;      // samples decoded per branch-free batch
+
+__device__ __forceinline__ double sink_map(const SinkCfg &G, const RasterPos &R, int32_t a) {
+    return G.fast ? denormalize_one_fast((double)a, G.scale, G.rcp, R.mn, R.range) : denormalize_one((double)a, G.scale, R.mn, R.range);
+}
+// Integer rasters behind 16-bit audio: the reference's value is v = ((a/32767 + 1)/2)*range + min in fp64, then
+// np.round.  In exact arithmetic v = min + N/65534 with N = (a + 32767)*range, so its fraction is a multiple of
+// 1/65534: either an exact tie or at least 1.5e-5 away from one, far more than the fp64 evaluation can drift (a few
+// ulp of 2^17 ~ 1e-11).  Away from ties round(v) = min + floor((N + 32767)/65534).  With one more 65534 added to
+// keep the numerator non-negative for a = -32768 (a foreign stream may hold it):
+//     px = (min - 1) + (a*range + K) / 65534,  K = 32767*range + 32767 + 65534,   numerator in [0, 2^32)
+// -- one multiply-add, a constant division and an add instead of ten fp64 / conversion instructions (the fused kernel
+// is issue-bound).  A zero remainder marks an exact tie, where fp64 rounding decides: the caller redoes that sample
+// with the fp64 formula (sink_px_tie).
+__device__ __forceinline__ uint32_t sink_px(const RasterPos &R, int32_t a, bool &tie) {
+    const uint32_t N = (uint32_t)a * R.irange + R.kround;
+    const uint32_t q = N / 65534u;
+    tie |= (N - q * 65534u) == 0u;
+    return (uint32_t)R.imn + q;                               // imn holds min - 1
+}
+__device__ __noinline__ uint32_t sink_px_tie(double scale, double rcp, int32_t imn_minus_1, uint32_t irange, int32_t a) {
+    return (uint32_t)(int32_t)__double2ll_rn(denormalize_one_fast((double)a, scale, rcp, (double)(imn_minus_1 + 1), (double)irange));
+}
+__device__ __forceinline__ void sink_put1(const SinkCfg &G, RasterPos &R, int32_t a) {
+    if (G.intpath) {
+        bool tie = false;
+        uint32_t v = sink_px(R, a, tie);
+        if (tie) v = sink_px_tie(G.scale, G.rcp, R.imn, R.irange, a);
+        if (G.esize == 2) reinterpret_cast<uint16_t *>(R.rowp)[R.x] = (uint16_t)v; else R.rowp[R.x] = (uint8_t)v;
+    } else store_denorm(R.rowp, G.dtype, R.x, sink_map(G, R, a));
+    if (++R.x == R.w) { R.x = 0; R.rowp += R.pitch; }
+}
+// rare slow path of sink_put_batch (a sample on an exact rounding tie, or a batch that straddles a row end): kept out of
+// line so the hot loop stays small (the fused kernel showed instruction-cache stalls with everything inlined)
+// (everything by value: a reference to the thread's RasterPos would force that struct into local memory)
+__device__ __noinline__ void sink_put_batch_slow(uint8_t *rowp, uint32_t x, uint32_t w, uint32_t pitch, int dtype, int intpath, uint32_t esize,
+                                                 int fast, double scale, double rcp, double mn, double range, int32_t imn, uint32_t irange,
+                                                 uint32_t kround, int32_t a0, int32_t a1, int32_t a2, int32_t a3,
+                                                 int32_t a4, int32_t a5, int32_t a6, int32_t a7) {
+    const int32_t a[8] = {a0, a1, a2, a3, a4, a5, a6, a7};
+    SinkCfg G;
+    G.dtype = dtype; G.intpath = intpath; G.esize = esize; G.fast = fast; G.scale = scale; G.rcp = rcp;
+    G.H = G.W = 0; G.tiles = nullptr; G.minmax = nullptr; G.raster = nullptr;
+    RasterPos R;
+    R.rowp = rowp; R.x = x; R.w = w; R.pitch = pitch; R.mn = mn; R.range = range; R.imn = imn; R.irange = irange; R.kround = kround;
+#pragma unroll 1
+    for (int j = 0; j < 8; j++) sink_put1(G, R, a[j]);
+}
+__device__ __forceinline__ void sink_advance(RasterPos &R, uint32_t n) {
+    R.x += n;
+    while (R.x >= R.w) { R.x -= R.w; R.rowp += R.pitch; }
+}
+#define FRB_SINK_SLOW(G, R, a)                                                                                                   \
+    do {                                                                                                                         \
+        sink_put_batch_slow((R).rowp, (R).x, (R).w, (R).pitch, (G).dtype, (G).intpath, (G).esize, (G).fast, (G).scale, (G).rcp,    \
+                            (R).mn, (R).range, (R).imn, (R).irange, (R).kround, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);   \
+        sink_advance(R, kDecBatch);                                                                                              \
+    } while (0)
+// kDecBatch consecutive samples; one or two vector stores when they stay inside the row and the address allows it
+__device__ __forceinline__ void sink_put_batch(const SinkCfg &G, RasterPos &R, const int32_t (&a)[kDecBatch]) {
+    static_assert(kDecBatch == 8, "packing below assumes 8 samples");
+    if (R.x + kDecBatch <= R.w) {
+        if (G.dtype == FRB_U16 || G.dtype == FRB_I16) {
+            uint16_t *p = reinterpret_cast<uint16_t *>(R.rowp) + R.x;
+            uint32_t pk[4];
+            if (G.intpath) {
+                bool tie = false;
+#pragma unroll
+                for (int j = 0; j < 4; j++) pk[j] = __byte_perm(sink_px(R, a[2 * j], tie), sink_px(R, a[2 * j + 1], tie), 0x5410);
+                if (tie) {                                     // rare: some sample sits on an exact .5; redo the batch sample by sample
+                    FRB_SINK_SLOW(G, R, a);
+                    return;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t lo = (uint32_t)(uint16_t)(int32_t)__double2ll_rn(sink_map(G, R, a[2 * j]));
+                    const uint32_t hi = (uint32_t)(int32_t)__double2ll_rn(sink_map(G, R, a[2 * j + 1]));
+                    pk[j] = lo | (hi << 16);
+                }
+            }
+            const uintptr_t ad = reinterpret_cast<uintptr_t>(p);
+            if ((ad & 15u) == 0) *reinterpret_cast<uint4 *>(p) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            else if ((ad & 7u) == 0) { reinterpret_cast<uint2 *>(p)[0] = make_uint2(pk[0], pk[1]); reinterpret_cast<uint2 *>(p)[1] = make_uint2(pk[2], pk[3]); }
+            else if ((ad & 3u) == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) reinterpret_cast<uint32_t *>(p)[j] = pk[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) { p[2 * j] = (uint16_t)pk[j]; p[2 * j + 1] = (uint16_t)(pk[j] >> 16); }
+            }
+        } else if (G.dtype == FRB_U8 || G.dtype == FRB_I8) {
+            uint8_t *p = R.rowp + R.x;
+            uint32_t pk[2] = {0, 0};
+            bool tie = false;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t b = (G.intpath ? sink_px(R, a[j], tie) : (uint32_t)(int32_t)__double2ll_rn(sink_map(G, R, a[j]))) & 0xFFu;
+                pk[j >> 2] |= b << (8 * (j & 3));
+            }
+            if (tie) { FRB_SINK_SLOW(G, R, a); return; }
+            if ((reinterpret_cast<uintptr_t>(p) & 7u) == 0) *reinterpret_cast<uint2 *>(p) = make_uint2(pk[0], pk[1]);
+            else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) p[j] = (uint8_t)(pk[j >> 2] >> (8 * (j & 3)));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kDecBatch; j++) store_denorm(R.rowp, G.dtype, R.x + j, sink_map(G, R, a[j]));
+        }
+        R.x += kDecBatch;
+        if (R.x == R.w) { R.x = 0; R.rowp += R.pitch; }
+    } else {
+        FRB_SINK_SLOW(G, R, a);
+    }
+}
 
 // FIXED / LPC subframe, part 1 (per lane, divergent): warm-up samples, predictor, residual coding header and the
 // first partition's parameter.  Run BEFORE the warp picks its sample loop, so that the loop can use libFLAC's
@@ -399,8 +538,8 @@ struct PredState {
     uint32_t k, plen, esc, psize, part_left, raw_bits, i;
     bool escape, wide;
 };
-template <int PMAX>
-__device__ __forceinline__ void decode_prologue(SubCtx &S, bool active, PredState<PMAX> &P) {
+template <int PMAX, bool RASTER>
+__device__ __forceinline__ void decode_prologue(SubCtx &S, bool active, PredState<PMAX> &P, const SinkCfg &G) {
     BitReader &br = S.br;
     const uint32_t n = S.n, order = S.order, wasted = S.wasted;
 #pragma unroll
@@ -413,7 +552,7 @@ __device__ __forceinline__ void decode_prologue(SubCtx &S, bool active, PredStat
 #pragma unroll
         for (int q = 0; q < PMAX - 1; q++) P.hist[q] = P.hist[q + 1];
         P.hist[PMAX - 1] = v;
-        S.dst[w] = (int32_t)((uint32_t)v << wasted);
+        if (!RASTER) S.dst[w] = (int32_t)((uint32_t)v << wasted); else sink_put1(G, S.rp, (int32_t)((uint32_t)v << wasted));
     }
     br.top_up();
     if (S.type == 3) {
@@ -457,8 +596,8 @@ __device__ __forceinline__ void decode_prologue(SubCtx &S, bool active, PredStat
 // data-dependent branches (predicated word merges, see BitReader) followed by the predictor recursion from the
 // register history, or a single sample through the generic path (escape-coded partitions, partition tails, codes
 // longer than 32 bits).
-template <int MAXORD, bool WIDE, int PMAX>
-__device__ __forceinline__ void decode_predictive(SubCtx &S, const PredState<PMAX> &P) {
+template <int MAXORD, bool WIDE, int PMAX, bool RASTER>
+__device__ __forceinline__ void decode_predictive(SubCtx &S, const PredState<PMAX> &P, const SinkCfg &G) {
     BitReader &br = S.br;
     const uint32_t n = S.n, wasted = S.wasted;
     int32_t *dst = S.dst;
@@ -495,7 +634,12 @@ __device__ __forceinline__ void decode_predictive(SubCtx &S, const PredState<PMA
 #pragma unroll
                 for (int j = 0; j < kDecBatch; j++)
                     H[MAXORD + j] = unzigzag(u[j]) + lpc_predict<MAXORD, WIDE>(cf, &H[MAXORD - 1 + j], shift);
-                if (S.aligned16) {
+                if (RASTER) {
+                    int32_t o[kDecBatch];
+#pragma unroll
+                    for (int j = 0; j < kDecBatch; j++) o[j] = (int32_t)((uint32_t)H[MAXORD + j] << wasted);
+                    sink_put_batch(G, S.rp, o);
+                } else if (S.aligned16) {
 #pragma unroll
                     for (int q = 0; q < kDecBatch / 4; q++)
                         *reinterpret_cast<int4 *>(dst + i + 4 * q) =
@@ -519,7 +663,7 @@ __device__ __forceinline__ void decode_predictive(SubCtx &S, const PredState<PMA
 #pragma unroll
             for (int q = 0; q < MAXORD - 1; q++) H[q] = H[q + 1];
             H[MAXORD - 1] = v;
-            dst[i] = (int32_t)((uint32_t)v << wasted);
+            if (!RASTER) dst[i] = (int32_t)((uint32_t)v << wasted); else sink_put1(G, S.rp, (int32_t)((uint32_t)v << wasted));
             part_left--; i++;
             if (br.overrun()) { S.err = true; i = n; }
         }
@@ -543,13 +687,13 @@ constexpr uint32_t kSpinLimit = 1u << 22;
 #ifdef FRB_DEC_TIMING
 __device__ unsigned long long g_dec_dbg[16];
 #endif
-template <bool BIGORDER>
+template <bool BIGORDER, bool RASTER>
 __global__ void __launch_bounds__(kDecThreads, BIGORDER ? 1 : FRB_DEC_MINB)
 k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__restrict__ streams, uint32_t n_streams,
                    uint32_t channels, uint32_t bps, uint32_t blocksize, uint32_t total_frames,
                    const unsigned long long *__restrict__ frame_pos, uint32_t *__restrict__ sub_bitoff,
                    int32_t *__restrict__ audio, uint8_t *__restrict__ frame_chassign, uint32_t *__restrict__ status,
-                   uint32_t n_skim_ctas, uint32_t skim_lanes) {
+                   uint32_t n_skim_ctas, uint32_t skim_lanes, const SinkCfg sink) {
     __shared__ __align__(256) uint4 s_ring[kSkimRing * kDecThreads];
 #ifdef FRB_DEC_TIMING
     unsigned long long t_start; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
@@ -573,6 +717,7 @@ k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__rest
     const uint32_t c = alive ? s / total_frames : 0, f = alive ? s - c * total_frames : 0;
     SubCtx S;
     S.err = false; S.type = 0; S.order = 0; S.n = 0; S.wasted = 0; S.sbps = bps; S.dst = audio; S.aligned16 = false;
+    S.rp.rowp = sink.raster; S.rp.x = 0; S.rp.w = 1; S.rp.pitch = 0; S.rp.mn = 0.0; S.rp.range = 0.0; S.rp.imn = 0; S.rp.irange = 0; S.rp.kround = 0;
     S.br.gq = (const uint4 *)bytes; S.br.sbase = (uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x * kSkimRing);
     S.br.swz = (lane & 15u) << 4; S.br.sx = S.br.sbase ^ S.br.swz; S.br.woff = 8; S.br.cissue = 0; S.br.qlast = 0; S.br.H = S.br.M = S.br.L = S.br.nx = S.br.nx2raw = 0; S.br.vb = 96;
     FrameLoc L; L.ok = false; L.start = L.end = 0; L.k = 0; L.n = 0;
@@ -607,6 +752,16 @@ k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__rest
                 const int64_t idx = st.audio_base + (int64_t)c * (int64_t)st.n_samples + (int64_t)L.k * blocksize;
                 S.dst = audio + idx;
                 S.aligned16 = ((reinterpret_cast<uintptr_t>(S.dst) & 15u) == 0);
+                if (RASTER) {
+                    const frb_tile t = sink.tiles[L.stream];
+                    const uint32_t i0 = L.k * blocksize, y = i0 / t.w;
+                    S.rp.x = i0 - y * t.w; S.rp.w = t.w; S.rp.pitch = sink.W * sink.esize;
+                    S.rp.rowp = sink.raster + (((size_t)c * sink.H + t.row_off + y) * sink.W + t.col_off) * sink.esize;
+                    const double mn = sink.minmax[2 * L.stream];
+                    const double range = __dsub_rn(sink.minmax[2 * L.stream + 1], mn);    // max-min unconditionally (:239)
+                    if (sink.intpath) { S.rp.imn = (int32_t)mn - 1; S.rp.irange = (uint32_t)range; S.rp.kround = 32767u * S.rp.irange + 32767u + 65534u; }
+                    else { S.rp.mn = mn; S.rp.range = range; }
+                }
                 if ((ch_assign == 8 && c == 1) || (ch_assign == 9 && c == 0) || (ch_assign == 10 && c == 1)) S.sbps++;
                 const uint32_t hd = S.br.get(8);
                 if (hd & 0x80) S.err = true;
@@ -627,11 +782,13 @@ k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__rest
     if (run) {
         if (S.type == 0) {
             const int32_t v = (int32_t)((uint32_t)S.br.get_signed(S.sbps) << S.wasted);
-            for (uint32_t i = 0; i < S.n; i++) S.dst[i] = v;
+            if (!RASTER) { for (uint32_t i = 0; i < S.n; i++) S.dst[i] = v; }
+            else { for (uint32_t i = 0; i < S.n; i++) sink_put1(sink, S.rp, v); }
         } else if (S.type == 1) {
             for (uint32_t i = 0; i < S.n; i++) {
                 if ((i & 3u) == 0) S.br.top_up();
-                S.dst[i] = (int32_t)((uint32_t)S.br.get_signed(S.sbps) << S.wasted);
+                const int32_t v = (int32_t)((uint32_t)S.br.get_signed(S.sbps) << S.wasted);
+                if (!RASTER) S.dst[i] = v; else sink_put1(sink, S.rp, v);
             }
         } else if (!BIGORDER && S.order > 12) {
             S.err = true;
@@ -642,15 +799,15 @@ k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__rest
         constexpr int PMAX = BIGORDER ? 32 : 12;
         const bool act = run && S.type >= 2 && (BIGORDER || S.order <= 12);
         PredState<PMAX> P;
-        decode_prologue<PMAX>(S, act, P);
+        decode_prologue<PMAX, RASTER>(S, act, P, sink);
         // warp-uniform sample loop (it is warp-synchronous): taps padded to the largest order in the warp, 64-bit MACs
         // only if a lane needs them
         const uint32_t cls = __reduce_max_sync(0xFFFFFFFFu, act ? S.order : 0u);
         const bool wide = __any_sync(0xFFFFFFFFu, act && P.wide);
-        if (BIGORDER) decode_predictive<32, true, PMAX>(S, P);
-        else if (cls <= 4) { if (wide) decode_predictive<4, true, PMAX>(S, P); else decode_predictive<4, false, PMAX>(S, P); }
-        else if (cls <= 8) { if (wide) decode_predictive<8, true, PMAX>(S, P); else decode_predictive<8, false, PMAX>(S, P); }
-        else { if (wide) decode_predictive<12, true, PMAX>(S, P); else decode_predictive<12, false, PMAX>(S, P); }
+        if (BIGORDER) decode_predictive<32, true, PMAX, RASTER>(S, P, sink);
+        else if (cls <= 4) { if (wide) decode_predictive<4, true, PMAX, RASTER>(S, P, sink); else decode_predictive<4, false, PMAX, RASTER>(S, P, sink); }
+        else if (cls <= 8) { if (wide) decode_predictive<8, true, PMAX, RASTER>(S, P, sink); else decode_predictive<8, false, PMAX, RASTER>(S, P, sink); }
+        else { if (wide) decode_predictive<12, true, PMAX, RASTER>(S, P, sink); else decode_predictive<12, false, PMAX, RASTER>(S, P, sink); }
     }
 #ifdef FRB_DEC_TIMING
     {

@@ -318,6 +318,55 @@ class Engine:
                     break
         return audio, base, status
 
+    def decode_tiles(self, data: torch.Tensor, byte_offsets: np.ndarray, byte_lengths: np.ndarray, tiles: np.ndarray,
+                     sample_rates: np.ndarray, minmax: np.ndarray, scale: float, out: torch.Tensor, bps: int,
+                     blocksize: int = 4096, verify_crc: bool = True) -> np.ndarray:
+        """Frames of a batch of tiles (device bytes) -> windows of the (bands,H,W) device raster `out`, decoded and
+        denormalised in one launch (frb_decode_tiles); what `extract` + flac_to_tiff do per tile (cli.py:297-315,
+        converter.py:181-253).  Returns the status words.  Two-band rasters go through decode_streams +
+        denormalize_tiles (their frames may be mid/side coded)."""
+        bands, H, W = out.shape
+        n_tiles = len(tiles)
+        n_samples = tiles["h"].astype(np.int64) * tiles["w"].astype(np.int64)
+        if bands == 2:
+            audio, base, status = self.decode_streams(data, byte_offsets, byte_lengths, n_samples, sample_rates, bands, bps, blocksize,
+                                                      verify_crc)
+            self.denormalize_tiles(audio, base, tiles, minmax, scale, out)
+            return status
+        frames_per = (n_samples + blocksize - 1) // blocksize
+        st = np.zeros(n_tiles, dtype=nat.DECODE_STREAM_DTYPE)
+        st["byte_offset"] = byte_offsets
+        st["byte_length"] = byte_lengths
+        st["n_samples"] = n_samples
+        st["sample_rate"] = sample_rates
+        fb = np.zeros(n_tiles, dtype=np.int64)
+        np.cumsum(frames_per[:-1], out=fb[1:])
+        st["frame_base"] = fb
+        total_frames = int(frames_per.sum())
+        dt = str(out.dtype).replace("torch.", "")
+        with torch.cuda.device(self.device):
+            s = _stream_ptr()
+            # one staging buffer, one copy: tile table followed by the min/max pairs
+            stage = np.zeros(n_tiles * 16 + n_tiles * 16, dtype=np.uint8)
+            stage[: n_tiles * 16] = np.ascontiguousarray(tiles).view(np.uint8)
+            stage[n_tiles * 16:] = np.ascontiguousarray(minmax, dtype=np.float64).reshape(-1).view(np.uint8)
+            d_stage = torch.from_numpy(stage).to(self.device, non_blocking=True)
+            d_status = torch.zeros(8, dtype=torch.int32, device=self.device)
+            status = None
+            for max_order in (12, 32):
+                p = nat.DecodeParams(n_tiles, bands, bps, blocksize, 1 if verify_crc else 0, max_order)
+                ws_bytes = C.c_size_t(0)
+                nat.check(self.L.frb_decode_workspace_size(C.byref(p), total_frames, C.byref(ws_bytes)), "frb_decode_workspace_size")
+                ws = self._buf("dec_ws", ws_bytes.value)
+                nat.check(self.L.frb_decode_tiles(C.byref(p), st.ctypes.data, data.data_ptr(), total_frames,
+                                                  d_stage.data_ptr(), d_stage.data_ptr() + n_tiles * 16, float(scale),
+                                                  out.data_ptr(), nat.DTYPE_CODES[dt], bands, H, W,
+                                                  ws.data_ptr(), ws.numel(), d_status.data_ptr(), s), "frb_decode_tiles")
+                status = d_status.cpu().numpy().astype(np.int64)      # also keeps d_stage alive until the kernels are done
+                if status[4] == 0:
+                    break
+        return status
+
     def denormalize_tiles(self, audio: torch.Tensor, audio_base: np.ndarray, tiles: np.ndarray, minmax: np.ndarray,
                           scale: float, out: torch.Tensor, sync: bool = True):
         """int32 planar audio -> windows of the (bands,H,W) device raster `out` (denormalize_from_audio, int path)."""

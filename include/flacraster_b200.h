@@ -195,10 +195,25 @@ typedef struct frb_decode_params {
 int frb_decode_workspace_size(const frb_decode_params *p, uint64_t total_frames, size_t *bytes);
 
 /* d_bytes must be readable 16 bytes past the last stream's end.
- * d_audio: int32 planar, same layout as section 2.  d_status: 4 uint32
- * {frames_missing, crc16_errors, parse_errors, frames_decoded}. */
+ * d_audio: int32 planar, same layout as section 2.  d_status: 8 uint32
+ * {frames_missing, crc16_errors, parse_errors, frames_decoded, lpc_order_above_12 (rerun with
+ * reserved = 32), offset_wait_timeouts, 0, 0}.  Multi-channel streams: the subframe offsets of a frame
+ * are found and consumed inside ONE launch (skim CTAs publish, decode threads acquire). */
 int frb_decode_batch(const frb_decode_params *p, const frb_decode_stream *h_streams,
                      const uint8_t *d_bytes, uint64_t total_frames, int32_t *d_audio,
+                     void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream);
+
+/* Fused decode + denormalise (the tile fetch of cli.py:297-315 followed by denormalize_from_audio,
+ * normalization.py:222-249, in one launch): stream i holds tile d_tiles[i] of a (bands,H,W) raster of
+ * `dtype` (frb_dtype), bands == p->channels, n_samples == h*w; every decode thread writes its samples
+ * straight into the tile's window of d_raster, so the int32 audio never goes through HBM.  d_minmax:
+ * {data_min,data_max} per tile; scale: 32767 / 8388607 / 2147483647 (normalization.py:222-232).
+ * Two-channel streams (possible mid/side frames) return FRB_ERR_UNSUPPORTED: use frb_decode_batch +
+ * frb_denormalize_tiles.  Same workspace, status words and slack rule as frb_decode_batch. */
+int frb_decode_tiles(const frb_decode_params *p, const frb_decode_stream *h_streams,
+                     const uint8_t *d_bytes, uint64_t total_frames,
+                     const frb_tile *d_tiles, const double *d_minmax, double scale,
+                     void *d_raster, int dtype, uint32_t bands, uint32_t H, uint32_t W,
                      void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream);
 
 /* Frame discovery for a stream of unknown length (FileDecoder on a file

@@ -339,6 +339,11 @@ def _roundtrip_on_device(torch, raster, tile_size, level):
     out = torch.zeros_like(raster)
     scale = 32767.0 if enc.bits_per_sample == 16 else 8388607.0
     eng.denormalize_tiles(audio, base, tiles, enc.minmax, scale, out)
+    # the fused decode + denormalise launch must write exactly the same raster
+    fused = torch.zeros_like(raster)
+    st2 = eng.decode_tiles(payload, enc.offsets, enc.sizes, tiles, enc.sample_rates, enc.minmax, scale, fused, enc.bps, enc.blocksize)
+    assert list(st2[:3]) == [0, 0, 0] and st2[3] == status[3] and st2[5] == 0, st2
+    assert torch.equal(fused.reshape(-1).view(torch.uint8), out.reshape(-1).view(torch.uint8))
     return enc, out
 
 
@@ -448,6 +453,80 @@ def test_tile_mapping_odd_alignment_vs_oracle(nat, torch_cuda, dt):
         want = no.denormalize_from_audio(an, prm["data_min"], prm["data_max"], dt, prm["scale_factor"]).T.reshape(bands, h, w)
         got = out.cpu().numpy()[:, r:r + h, c:c + w]
         assert np.array_equal(got, want, equal_nan=True), (dt, i)
+
+
+@pytest.mark.parametrize("dt", ["uint8", "int8", "uint16", "int16", "uint32", "int32", "float32", "float64"])
+@pytest.mark.parametrize("bands", [1, 3])
+def test_fused_decode_to_raster_equals_two_step_path(nat, torch_cuda, dt, bands):
+    """frb_decode_tiles (decode threads write denormalised pixels straight into the tile windows) against
+    frb_decode_batch + frb_denormalize_tiles on ragged tiles: odd widths (batches straddle rows), a raster width that
+    leaves rows at every store alignment, tail frames, constant and wasted-bits bands."""
+    torch = torch_cuda
+    from flac_raster_b200.engine import default_engine, tile_grid
+    rng = np.random.default_rng(11)
+    H, W = 301, 1037
+    yy, xx = np.mgrid[0:H, 0:W]
+    planes = []
+    for b in range(bands):
+        base_sig = 900 * np.sin(xx / (13.0 + b)) * np.cos(yy / 17.0) + rng.integers(-40, 40, size=(H, W))
+        if dt.startswith("float"):
+            planes.append((base_sig * 1.37 + 0.25).astype(dt))
+        elif dt in ("uint8", "int8"):
+            info = np.iinfo(dt)
+            planes.append(np.clip(base_sig / 9 + (info.max + info.min) // 2, info.min, info.max).astype(dt))
+        else:
+            info = np.iinfo(dt)
+            planes.append(np.clip(base_sig * 8 + 20000, max(info.min, -32000), min(info.max, 32000)).astype(dt))
+    x = np.stack(planes)
+    if bands == 3:
+        x[2, :, :] = x[2, 0, 0]                              # a constant band: CONSTANT subframes
+    raster = torch.from_numpy(x.view(np.uint8).reshape(-1)).cuda().view(getattr(torch, dt)).reshape(bands, H, W)
+    eng = default_engine()
+    for tile in (128, 97):
+        tiles = tile_grid(H, W, tile)
+        enc = eng.encode_tiles(raster, tiles, 5)
+        payload = torch.cat([enc.payload, torch.zeros(64, dtype=torch.uint8, device=raster.device)])
+        scale = 32767.0 if enc.bits_per_sample == 16 else 8388607.0
+        audio, base, status = eng.decode_streams(payload, enc.offsets, enc.sizes, enc.n_samples, enc.sample_rates, bands, enc.bps, 4096)
+        assert list(status[:3]) == [0, 0, 0]
+        two = torch.zeros_like(raster)
+        eng.denormalize_tiles(audio, base, tiles, enc.minmax, scale, two)
+        one = torch.zeros_like(raster)
+        st = eng.decode_tiles(payload, enc.offsets, enc.sizes, tiles, enc.sample_rates, enc.minmax, scale, one, enc.bps, 4096)
+        assert list(st[:3]) == [0, 0, 0] and st[5] == 0, st
+        assert torch.equal(one.reshape(-1).view(torch.uint8), two.reshape(-1).view(torch.uint8)), (dt, bands, tile)
+        if enc.bits_per_sample == 16:
+            assert torch.equal(one.reshape(-1).view(torch.uint8), raster.reshape(-1).view(torch.uint8))
+
+
+@pytest.mark.parametrize("dt", ["uint16", "int16", "uint8", "int8"])
+def test_fused_integer_denormalise_is_exact_for_every_audio_value(nat, torch_cuda, dt):
+    """The fused kernel maps 16-bit audio to integer pixels with exact integer arithmetic and only evaluates the fp64
+    formula on exact ties.  Every audio value -32768..32767 (a foreign stream may hold any) under min/max pairs chosen to
+    produce ties, zero range, full range and negative minima must equal the reference's fp64 formula + np.round."""
+    torch = torch_cuda
+    from flac_raster_b200.engine import default_engine
+    from flac_raster_b200 import _native as natmod
+    from oracle import normalization_oracle as no
+    rng = np.random.default_rng(3)
+    a = rng.permutation(np.arange(-32768, 32768, dtype=np.int32)).reshape(-1, 1)
+    payload, _ = nat.host_encode(a, 16, 44100, 5)
+    eng = default_engine()
+    data = torch.cat([torch.from_numpy(np.frombuffer(bytes(payload), dtype=np.uint8).copy()), torch.zeros(64, dtype=torch.uint8)]).cuda()
+    tiles = np.zeros(1, dtype=natmod.TILE_DTYPE)
+    tiles[0] = (0, 0, 256, 256)
+    info = np.iinfo(dt)
+    pairs = [(info.min, info.max), (info.min, info.min + 1), (info.min + 3, info.min + 6), (info.max - 2, info.max),
+             (info.min + 5, info.min + 5), (info.min, info.min + min(info.max - info.min, 32767)), (info.min + 1, info.max - 1),
+             (info.min, info.min + 2), (info.min + 10, info.min + 10 + min(info.max - info.min - 10, 65533))]
+    for mn, mx in pairs:
+        out = torch.zeros(1, 256, 256, dtype=getattr(torch, dt), device="cuda")
+        st = eng.decode_tiles(data, np.array([0]), np.array([len(payload)]), tiles, np.array([44100], dtype=np.uint32),
+                              np.array([[mn, mx]], dtype=np.float64), 32767.0, out, 16, 4096)
+        assert list(st[:3]) == [0, 0, 0], st
+        want = no.denormalize_from_audio(a.astype(np.int16), float(mn), float(mx), dt, 32767.0).reshape(256, 256)
+        got = out.cpu().numpy()[0]
+        assert np.array_equal(got, want), (dt, mn, mx, int((got != want).sum()))
 
 
 def test_constant_division_is_exact(nat, torch_cuda):
