@@ -1,14 +1,17 @@
 // frb_decode_kernels.cuh -- included inside namespace frb by frb_decode.cuh.
 //
-// v2 decode pipeline (justified by profiles/r01_ncu_dec_v1_raw_subset.csv: the v1 thread-per-frame
-// kernel ran at 9.7 % occupancy on 8-band tiles and spent 228 instructions per sample):
-//   k_skim_subframes    (channels > 1 only) one thread per frame walks the Rice codes without
-//                       reconstructing anything and records each subframe's bit offset
-//   k_decode_subframes  one thread per SUBFRAME; 32-bit funnel-shift bit window with a prefetched
-//                       third word; LPC history in registers (sliding window, 4 samples per group,
-//                       taps padded to the warp's order class 4/8/12); 128-bit stores
+// Decode pipeline after k_sync_scan (history: the v1 thread-per-frame kernel ran at 9.7 % occupancy on 8-band tiles and
+// spent 228 instructions per sample, profiles/r01_ncu_dec_v1_raw_subset.csv; v2 split it into a skim kernel and a
+// thread-per-subframe decode kernel; v3 fuses the two launches and optionally the denormalisation):
+//   k_decode_subframes  ONE launch with two roles.  Skim CTAs (lowest block indices; channels > 1 only): one thread per
+//                       frame walks the Rice codes without reconstructing anything and publishes each subframe's bit
+//                       offset as soon as it is known.  Decode CTAs: one thread per SUBFRAME in channel-major order
+//                       waits for its offset, then Rice decode + predictor restore from a register history (taps padded
+//                       to the warp's order class 4/8/12, 64-bit MACs only when libFLAC's rule demands them); output is
+//                       either the planar int32 audio (128-bit stores) or, fused, the denormalised pixels written
+//                       straight into the tile's window of the raster
 //   k_crc16_frames      one warp per frame, 16-byte chunks per lane, slice-by-4 tables in shared
-//                       memory, Horner combination with x^(8*512) and a final x^(8*n) weight
+//                       memory, Horner combination with x^(8*512) and a final x^(8*n) weight (side stream)
 
 // ---- cp.async / shared-memory helpers ------------------------------------------------------------------
 constexpr int kDecThreads = 128;
@@ -71,142 +74,18 @@ __device__ __forceinline__ FrameLoc locate_frame(const DecStreamDev *__restrict_
 constexpr int kSkimRing = 16;                                   // 16-byte chunks per thread (256 contiguous bytes)
 constexpr int kSkimBatch = 8;                                   // codes per batch: <= 8 words = 2 chunks
 
-// 96-bit left-aligned shifting window H:M:L (the top vb >= 64 bits valid before every code) + two pre-loaded words.
-// H always holds 32 valid bits, so the dependent chain per Rice code is clz(H) -> add -> ONE funnel shift of H:M;
-// everything else (shifting M:L, the valid-bit count, merging the next word below the valid bits -- it only ever
-// touches M and L) hangs off that chain.  The earlier 64-bit window merged into the word the next clz reads, which
-// put compare -> predicated shift -> or on the chain of every code (the skim walk, one warp or two per scheduler,
-// ran at 130 cycles per code).
+// Bit reader (skim and decode roles): three consecutive big-endian words of the stream in registers -- A (holds the
+// next unread bit), B, and C still as loaded (raw little-endian) -- plus a running bit position bp.  Only bits 0..4 of
+// bp address A; bit 5 flipping means the position moved into B and the words shift up (A=B, B=bswap(C), C=next ring
+// word).  The window of the next 32 bits is ONE wrap-mode funnel shift of A:B and the bookkeeping for a Rice code is
+// 9 predicated instructions.  Two shifting-window readers came before it: a 64-bit window (2 funnel shifts + a
+// 13-instruction predicated merge per code: 27 % of the decode kernel's instructions,
+// profiles/r01_ncu_dec_v5_lines_decode.txt) and a 96-bit one whose merge stayed off the clz chain (17 per code).  They
+// had shorter dependent chains, which mattered while the kernels were latency-bound; the fused skim+decode kernel is
+// issue-bound (ALU pipe 55-59 %, profiles/r01_ncu_dec_v6_fused.txt) and the instruction count decides: 4.04 -> 3.84 ms.
 // Ring: the thread's 16 chunks are contiguous in shared memory (256-byte aligned), chunk index XOR-swizzled with the
 // lane so that lanes reading the same word offset spread over the banks.
 struct BitReader {
-    const uint4 *gq;         // 16-byte view of the input buffer (16-byte aligned base)
-    uint32_t sbase;          // shared-space address of this thread's 256-byte ring
-    uint32_t swz;            // (lane & 15) << 4
-    uint32_t sx;             // sbase ^ swz: ring word at byte offset o (0..252) lives at sx ^ o
-    uint32_t woff;           // 4 * (index of the next word to load, in 32-bit words from the buffer base); nx2raw is word woff/4-1, nx woff/4-2
-    uint32_t cissue;         // next chunk to copy into the ring
-    uint32_t qlast;          // copies are clamped to this chunk (16 readable bytes follow the frame end)
-    uint32_t H, M, L, nx, nx2raw;   // nx2raw: as loaded (little-endian), byte-swapped when it becomes nx
-    int32_t vb;              // valid bits in H:M:L
-    __device__ __forceinline__ uint32_t load_raw4(uint32_t byte_off) const { return lds_u32(sx ^ (byte_off & 252u)); }
-    __device__ __forceinline__ void copy_chunk(uint32_t c) const {
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sbase + (((c & (kSkimRing - 1)) << 4) ^ swz)),
-                     "l"(gq + min(c, qlast)) : "memory");
-    }
-    // Copy ahead without overwriting anything still needed: chunk c may replace chunk c - kSkimRing once that one
-    // lies before the chunk of the next word to load.  At most two chunks per call (a batch consumes at most two).
-    __device__ __forceinline__ void top_up() {
-        const uint32_t lim = (woff >> 4) + kSkimRing - 1;
-#pragma unroll
-        for (int r = 0; r < 2; r++)
-            if (cissue < lim) { copy_chunk(cissue); cissue++; }
-        cp_async_commit();
-        // a chunk is read at least (kSkimRing - 3) / 2 batches after it was requested
-        cp_async_wait<(kSkimRing - 3) / 2 - 1>();
-    }
-    __device__ __forceinline__ void init(uint32_t ring_saddr, uint32_t lane, const uint8_t *base, uint64_t bitpos, uint64_t byte_end) {
-        gq = (const uint4 *)base;
-        sbase = ring_saddr;
-        swz = (lane & 15u) << 4;
-        sx = sbase ^ swz;
-        const uint32_t w = (uint32_t)(bitpos >> 5);
-        qlast = (uint32_t)(byte_end >> 4);
-        cissue = w >> 2;
-        for (int j = 0; j < kSkimRing - 1; j++) { copy_chunk(cissue); cissue++; }
-        cp_async_commit();
-        cp_async_wait<0>();
-        H = bswap32(load_raw4(w << 2)); M = bswap32(load_raw4((w + 1) << 2)); L = bswap32(load_raw4((w + 2) << 2));
-        nx = bswap32(load_raw4((w + 3) << 2)); nx2raw = load_raw4((w + 4) << 2);
-        woff = (w + 5) << 2;
-        vb = 96;
-        consume((uint32_t)bitpos & 31u);
-    }
-    __device__ __forceinline__ uint64_t bitpos() const { return (uint64_t)((woff >> 2) - 2u) * 32u - (uint32_t)vb; }
-    __device__ __forceinline__ bool overrun() const { return (woff >> 4) > qlast + 2; }
-    __device__ __forceinline__ uint32_t window() const { return H; }
-    __device__ __forceinline__ void merge_word() {                 // 32 <= vb <= 64: append nx below the valid bits (M and L only)
-        const uint32_t v = (uint32_t)vb - 32u;
-        M |= __funnelshift_rc(nx, 0u, v);                          // nx >> v, 0 when v == 32
-        L = __funnelshift_rc(0u, nx, v);                           // low word of (nx:0) >> v
-        vb += 32;
-        nx = bswap32(nx2raw); nx2raw = load_raw4(woff); woff += 4;
-    }
-    // Drop nb <= 32 bits, then `if (vb <= 64) merge_word();` as straight-line predicated code: with 32 independent streams
-    // per warp some lane merges in almost every step, so a branch would cost every lane the divergent path plus its
-    // reconvergence; the freshly loaded word is not touched before the next merge (no wait on the LDS).
-    __device__ __forceinline__ void advance_predicated(uint32_t nb) {
-        H = __funnelshift_lc(M, H, nb);
-        M = __funnelshift_lc(L, M, nb);
-        L = __funnelshift_lc(0u, L, nb);
-        vb -= (int32_t)nb;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t.reg .b32 t, a, v;\n\t"
-            "setp.le.s32 p, %4, 64;\n\t"
-            "sub.s32 v, %4, 32;\n\t"
-            "@p shf.r.clamp.b32 t, %2, 0, v;\n\t"
-            "@p or.b32 %0, %0, t;\n\t"
-            "@p shf.r.clamp.b32 %1, 0, %2, v;\n\t"
-            "@p add.s32 %4, %4, 32;\n\t"
-            "@p prmt.b32 %2, %3, 0, 0x0123;\n\t"
-            "@p and.b32 a, %5, 252;\n\t"
-            "@p xor.b32 a, a, %6;\n\t"
-            "@p ld.shared.u32 %3, [a];\n\t"
-            "@p add.u32 %5, %5, 4;\n\t"
-            "}\n"
-            : "+r"(M), "+r"(L), "+r"(nx), "+r"(nx2raw), "+r"(vb), "+r"(woff)
-            : "r"(sx)
-            : "memory");
-    }
-    __device__ __forceinline__ void consume(uint32_t nb) {         // nb <= 32
-        H = __funnelshift_lc(M, H, nb);
-        M = __funnelshift_lc(L, M, nb);
-        L = __funnelshift_lc(0u, L, nb);
-        vb -= (int32_t)nb;
-        if (vb <= 64) merge_word();
-    }
-    // generic (rare) operations for headers, escapes and over-long codes; callers top up between them
-    __device__ __forceinline__ uint32_t get(uint32_t nb) {          // nb in 0..32
-        const uint32_t v = __funnelshift_lc(H, 0u, nb);             // H >> (32 - nb), 0 for nb == 0
-        consume(nb);
-        return v;
-    }
-    __device__ __forceinline__ int32_t get_signed(uint32_t nb) {    // nb in 0..33
-        if (nb == 0) return 0;
-        if (nb > 32) { consume(nb - 32); nb = 32; }                 // top bits are sign copies for in-range data
-        const uint32_t v = get(nb);
-        const uint32_t sh = 32 - nb;
-        return (int32_t)(v << sh) >> sh;
-    }
-    __device__ __forceinline__ uint32_t unary() {
-        uint32_t q = 0;
-        for (;;) {
-            if (H) { const uint32_t z = __clz(H); consume(z + 1); return q + z; }
-            q += 32; consume(32);
-            top_up();
-            if (overrun()) return q;                                // ran past the frame: corrupt stream
-        }
-    }
-    // zig-zag folded Rice value with parameter k (<= 30), any length (generic path)
-    __device__ __forceinline__ uint32_t rice_u(uint32_t k) {
-        const uint32_t q = unary();
-        const uint32_t low = get(k);
-        return (q << k) | low;
-    }
-    __device__ __forceinline__ void seek(const uint8_t *base, uint64_t bits_forward, uint64_t byte_end) {
-        const uint64_t target = bitpos() + bits_forward;
-        cp_async_wait<0>();                                          // nothing may land in the ring after re-initialisation
-        init(sbase, swz >> 4, base, target, byte_end);
-    }
-};
-
-// Position-based reader for the SKIM role (which never needs the sample bits, only code lengths): three consecutive
-// big-endian words in registers -- A (holds the next unread bit), B, and C still as loaded -- plus a running bit
-// position bp; bit 5 of bp flipping means the position moved into B and the words shift up.  The window is one
-// wrap-mode funnel shift of A:B and a code costs 12 instructions instead of the shifting window's 17; its longer
-// dependent chain does not matter for the walk inside the fused kernel, where skim warps wait for issue slots, not for
-// their own results (they finish 3.0 ms into the kernel against 1.9 ms when running alone).
-struct SkimReader {
     const uint4 *gq;
     uint32_t sbase, swz, sx;
     uint32_t woff;           // 4 * (index of the next word to load); A is word woff/4 - 3
@@ -273,6 +152,13 @@ struct SkimReader {
         consume(nb);
         return v;
     }
+    __device__ __forceinline__ int32_t get_signed(uint32_t nb) {    // nb in 0..33
+        if (nb == 0) return 0;
+        if (nb > 32) { consume(nb - 32); nb = 32; }
+        const uint32_t v = get(nb);
+        const uint32_t sh = 32 - nb;
+        return (int32_t)(v << sh) >> sh;
+    }
     __device__ __forceinline__ uint32_t unary() {
         uint32_t q = 0;
         for (;;) {
@@ -282,6 +168,11 @@ struct SkimReader {
             top_up();
             if (overrun()) return q;
         }
+    }
+    __device__ __forceinline__ uint32_t rice_u(uint32_t k) {
+        const uint32_t q = unary();
+        const uint32_t low = get(k);
+        return (q << k) | low;
     }
     __device__ __forceinline__ void seek(const uint8_t *base, uint64_t bits_forward, uint64_t byte_end) {
         const uint64_t target = bitpos() + bits_forward;
@@ -324,7 +215,7 @@ skim_role(uint4 *s_ring, uint32_t cta, const uint8_t *__restrict__ bytes, const 
     uint32_t *off_out = sub_bitoff + (size_t)(done ? 0 : f) * channels;
     uint64_t frame_bit0 = 0;
     uint32_t published = 0;                                   // entries [0, published) of off_out have been stored
-    SkimReader br;
+    BitReader br;
     br.gq = (const uint4 *)bytes; br.sbase = (uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x * kSkimRing); br.swz = (lane & 15u) << 4;
     br.sx = br.sbase ^ br.swz; br.woff = 12; br.cissue = 0; br.qlast = 0; br.A = br.B = br.Craw = 0; br.bp = 0;
     if (lane < lanes_per_warp && f < total_frames && channels > 1) {
@@ -349,7 +240,7 @@ skim_role(uint4 *s_ring, uint32_t cta, const uint8_t *__restrict__ bytes, const 
         if (left >= (uint32_t)kSkimBatch) {
             // ---- a full batch of Rice codes without data-dependent branches; a code longer than 32 bits (long unary
             // run or corrupt data) is detected once per batch and the batch is then redone one code at a time ----
-            const SkimReader snap = br;
+            const BitReader snap = br;
             const uint32_t k1 = k + 1;
             uint32_t maxlen = 0;
 #pragma unroll
@@ -490,8 +381,9 @@ struct RasterPos {           // per thread
     uint32_t irange, kround; // kround = 32767*range + 32767 + 65534 (see sink_px)
 };
 
+typedef BitReader DecReader;
 struct SubCtx {
-    BitReader br;
+    DecReader br;
     RasterPos rp;
     int32_t *dst;            // first sample of this subframe in the planar audio buffer
     uint32_t n, order, sbps, wasted, type;
@@ -630,7 +522,7 @@ struct PredState {
 };
 template <int PMAX, bool RASTER>
 __device__ __forceinline__ void decode_prologue(SubCtx &S, bool active, PredState<PMAX> &P, const SinkCfg &G) {
-    BitReader &br = S.br;
+    DecReader &br = S.br;
     const uint32_t n = S.n, order = S.order, wasted = S.wasted;
 #pragma unroll
     for (int q = 0; q < PMAX; q++) { P.hist[q] = 0; P.cf[q] = 0; }
@@ -688,7 +580,7 @@ __device__ __forceinline__ void decode_prologue(SubCtx &S, bool active, PredStat
 // longer than 32 bits).
 template <int MAXORD, bool WIDE, int PMAX, bool RASTER>
 __device__ __forceinline__ void decode_predictive(SubCtx &S, const PredState<PMAX> &P, const SinkCfg &G) {
-    BitReader &br = S.br;
+    DecReader &br = S.br;
     const uint32_t n = S.n, wasted = S.wasted;
     int32_t *dst = S.dst;
     int32_t H[MAXORD + kDecBatch];
@@ -707,7 +599,7 @@ __device__ __forceinline__ void decode_predictive(SubCtx &S, const PredState<PMA
         bool did = false;
         if (!escape && part_left >= (uint32_t)kDecBatch && (i & 3u) == 0) {       // (i & 3): keep the 16-byte stores aligned
             // ---- batch: kDecBatch codes, no data-dependent branch; redone sample by sample if one is longer than 32 bits ----
-            const BitReader snap = br;
+            const DecReader snap = br;
             const uint32_t k1 = k + 1;
             uint32_t maxlen = 0, u[kDecBatch];
 #pragma unroll
@@ -809,7 +701,8 @@ k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__rest
     S.err = false; S.type = 0; S.order = 0; S.n = 0; S.wasted = 0; S.sbps = bps; S.dst = audio; S.aligned16 = false;
     S.rp.rowp = sink.raster; S.rp.x = 0; S.rp.w = 1; S.rp.pitch = 0; S.rp.mn = 0.0; S.rp.range = 0.0; S.rp.imn = 0; S.rp.irange = 0; S.rp.kround = 0;
     S.br.gq = (const uint4 *)bytes; S.br.sbase = (uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x * kSkimRing);
-    S.br.swz = (lane & 15u) << 4; S.br.sx = S.br.sbase ^ S.br.swz; S.br.woff = 8; S.br.cissue = 0; S.br.qlast = 0; S.br.H = S.br.M = S.br.L = S.br.nx = S.br.nx2raw = 0; S.br.vb = 96;
+    S.br.swz = (lane & 15u) << 4; S.br.sx = S.br.sbase ^ S.br.swz; S.br.cissue = 0; S.br.qlast = 0;
+    S.br.woff = 12; S.br.A = S.br.B = S.br.Craw = 0; S.br.bp = 0;
     FrameLoc L; L.ok = false; L.start = L.end = 0; L.k = 0; L.n = 0;
     uint32_t hdr_bytes = 0;
     if (alive) {

@@ -14,9 +14,13 @@ tiles = tile_grid(10980, 10980, 1024)
 enc = eng.encode_tiles(raster, tiles, 5)
 payload = torch.cat([enc.payload, torch.zeros(64, dtype=torch.uint8, device=dev)])
 dbg = (C.c_ulonglong * 16)()
+out = torch.zeros_like(raster)
 for it in range(3):
     L.frb_debug_decode_timing(None, 1)
-    audio, base, st = eng.decode_streams(payload, enc.offsets, enc.sizes, enc.n_samples, enc.sample_rates, 8, 16, 4096)
+    if len(sys.argv) > 1 and sys.argv[1] == "audio":
+        audio, base, st = eng.decode_streams(payload, enc.offsets, enc.sizes, enc.n_samples, enc.sample_rates, 8, 16, 4096)
+    else:
+        st = eng.decode_tiles(payload, enc.offsets, enc.sizes, tiles, enc.sample_rates, enc.minmax, 32767.0, out, 16, 4096)
     torch.cuda.synchronize()
     L.frb_debug_decode_timing(dbg, 0)
     t0 = dbg[0]
