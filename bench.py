@@ -395,15 +395,18 @@ def main():
             return None
         kms = float(np.mean(kernel_ms_list))
         ach = alg_bytes / (kms * 1e-3) / 1e9
+        extra = {k[len(kernel) + 1:]: v for k, v in traffic.items() if k.startswith(kernel + ":")} if args.scale_div == 1 else {}
         return {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": traffic.get(kernel) if args.scale_div == 1 else None, "kernel_ms": kms,
+                "traffic": traffic.get(kernel) if args.scale_div == 1 else None, "kernel_ms": kms, **extra,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "note": note}
 
     def mean_ms(acc):
         return {k: float(np.mean(v)) for k, v in acc.items()}
 
     enc_alg = samples_local * 4 + comp_bytes           # int32 audio read + compressed bytes produced
-    dec_alg = comp_bytes + samples_local * 4           # compressed bytes consumed + int32 audio written
+    fused_dec = enc.bps == 16 and raster.element_size() <= 2 and nb != 2
+    # compressed bytes consumed + output written: pixels of the raster (fused launch) or int32 audio (two-step path)
+    dec_alg = comp_bytes + samples_local * (raster.element_size() if fused_dec else 4)
     cpu = None
     if not args.no_cpu_baseline:
         try:
@@ -427,7 +430,9 @@ def main():
                    "gpu_launches": int(dec_launches),
                    "kernels_ms": mean_ms(dec_prof),
                    "roofline": roof(dec_prof.get("k_decode_subframes"), dec_alg, "k_decode_subframes",
-                                    "compressed bytes read + int32 audio written; issue/latency-bound (Rice parse is a serial chain per subframe)")},
+                                    ("compressed bytes read + raster pixels written by the fused skim + Rice decode + predictor restore + "
+                                     "denormalise launch" if fused_dec else "compressed bytes read + int32 audio written") +
+                                    "; issue-bound (ALU pipe), not HBM-bound: see roofline.issue_* (ncu) and DESIGN.md section 4")},
         "kernels_ms": mean_ms(enc_prof),
         "roofline": roof(enc_prof.get("k_enc_code") or enc_prof.get("subframe_analysis_total"), enc_alg, "k_enc_code",
                          "int32 audio read + compressed bytes written by the dominant encode kernel (residual, Rice search, bit packing); "

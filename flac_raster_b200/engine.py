@@ -320,15 +320,22 @@ class Engine:
 
     def decode_tiles(self, data: torch.Tensor, byte_offsets: np.ndarray, byte_lengths: np.ndarray, tiles: np.ndarray,
                      sample_rates: np.ndarray, minmax: np.ndarray, scale: float, out: torch.Tensor, bps: int,
-                     blocksize: int = 4096, verify_crc: bool = True) -> np.ndarray:
+                     blocksize: int = 4096, verify_crc: bool = True, fused: Optional[bool] = None) -> np.ndarray:
         """Frames of a batch of tiles (device bytes) -> windows of the (bands,H,W) device raster `out`, decoded and
         denormalised in one launch (frb_decode_tiles); what `extract` + flac_to_tiff do per tile (cli.py:297-315,
         converter.py:181-253).  Returns the status words.  Two-band rasters go through decode_streams +
-        denormalize_tiles (their frames may be mid/side coded)."""
+        denormalize_tiles (their frames may be mid/side coded); `fused` forces (True) or forbids (False) the one-launch
+        form, None picks it where it is the faster one."""
         bands, H, W = out.shape
         n_tiles = len(tiles)
         n_samples = tiles["h"].astype(np.int64) * tiles["w"].astype(np.int64)
-        if bands == 2:
+        dt = str(out.dtype).replace("torch.", "")
+        # The fused launch pays off where the pixel mapping is the exact integer form (8/16-bit rasters behind 16-bit
+        # audio).  Wider dtypes need the fp64 formula per sample, which is cheaper in the bandwidth-bound mapping kernel
+        # than inside the issue-bound decode kernel (C4 float32: 129 vs 97 GSamples/s), so they stay two-step.
+        if fused is None:
+            fused = bps == 16 and dt in ("uint8", "int8", "uint16", "int16") and float(scale) == 32767.0
+        if bands == 2 or not fused:
             audio, base, status = self.decode_streams(data, byte_offsets, byte_lengths, n_samples, sample_rates, bands, bps, blocksize,
                                                       verify_crc)
             self.denormalize_tiles(audio, base, tiles, minmax, scale, out)
@@ -343,7 +350,6 @@ class Engine:
         np.cumsum(frames_per[:-1], out=fb[1:])
         st["frame_base"] = fb
         total_frames = int(frames_per.sum())
-        dt = str(out.dtype).replace("torch.", "")
         with torch.cuda.device(self.device):
             s = _stream_ptr()
             # one staging buffer, one copy: tile table followed by the min/max pairs

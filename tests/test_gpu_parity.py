@@ -341,7 +341,7 @@ def _roundtrip_on_device(torch, raster, tile_size, level):
     eng.denormalize_tiles(audio, base, tiles, enc.minmax, scale, out)
     # the fused decode + denormalise launch must write exactly the same raster
     fused = torch.zeros_like(raster)
-    st2 = eng.decode_tiles(payload, enc.offsets, enc.sizes, tiles, enc.sample_rates, enc.minmax, scale, fused, enc.bps, enc.blocksize)
+    st2 = eng.decode_tiles(payload, enc.offsets, enc.sizes, tiles, enc.sample_rates, enc.minmax, scale, fused, enc.bps, enc.blocksize, fused=True)
     assert list(st2[:3]) == [0, 0, 0] and st2[3] == status[3] and st2[5] == 0, st2
     assert torch.equal(fused.reshape(-1).view(torch.uint8), out.reshape(-1).view(torch.uint8))
     return enc, out
@@ -492,7 +492,7 @@ def test_fused_decode_to_raster_equals_two_step_path(nat, torch_cuda, dt, bands)
         two = torch.zeros_like(raster)
         eng.denormalize_tiles(audio, base, tiles, enc.minmax, scale, two)
         one = torch.zeros_like(raster)
-        st = eng.decode_tiles(payload, enc.offsets, enc.sizes, tiles, enc.sample_rates, enc.minmax, scale, one, enc.bps, 4096)
+        st = eng.decode_tiles(payload, enc.offsets, enc.sizes, tiles, enc.sample_rates, enc.minmax, scale, one, enc.bps, 4096, fused=True)
         assert list(st[:3]) == [0, 0, 0] and st[5] == 0, st
         assert torch.equal(one.reshape(-1).view(torch.uint8), two.reshape(-1).view(torch.uint8)), (dt, bands, tile)
         if enc.bits_per_sample == 16:
