@@ -737,6 +737,11 @@ k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__rest
                 S.aligned16 = ((reinterpret_cast<uintptr_t>(S.dst) & 15u) == 0);
                 if (RASTER) {
                     const frb_tile t = sink.tiles[L.stream];
+                    // the stream must be exactly this tile's pixels and the window must lie inside the raster (status[6])
+                    if ((uint64_t)t.h * t.w != st.n_samples || t.w == 0 || (uint64_t)t.row_off + t.h > sink.H || (uint64_t)t.col_off + t.w > sink.W) {
+                        if (c == 0 && L.k == 0) atomicAdd(&status[6], 1u);
+                        alive = false;
+                    }
                     const uint32_t i0 = L.k * blocksize, y = i0 / t.w;
                     S.rp.x = i0 - y * t.w; S.rp.w = t.w; S.rp.pitch = sink.W * sink.esize;
                     S.rp.rowp = sink.raster + (((size_t)c * sink.H + t.row_off + y) * sink.W + t.col_off) * sink.esize;

@@ -41,17 +41,19 @@ struct EncStreamDev {
     uint32_t sample_rate, frame_base, n_frames, pad;
 };
 
-struct LevelCfg { int max_lpc_order, max_po, windows; };
+struct LevelCfg { int max_lpc_order, max_po, windows, mid_side, loose; };   // mid_side/loose: exactly-two-channel streams only
 __host__ __device__ __forceinline__ LevelCfg level_cfg(uint32_t level) {
     // docs/sonos-pyflac.txt:6926-6934
     switch (level) {
-        case 0: case 1: case 2: return {0, 3, 1};
-        case 3: return {6, 4, 1};
-        case 4: return {8, 4, 1};
-        case 5: return {8, 5, 1};
-        case 6: return {8, 6, 2};
-        case 7: return {12, 6, 2};
-        default: return {12, 6, 3};
+        case 0: return {0, 3, 1, 0, 0};
+        case 1: return {0, 3, 1, 1, 1};
+        case 2: return {0, 3, 1, 1, 0};
+        case 3: return {6, 4, 1, 0, 0};
+        case 4: return {8, 4, 1, 1, 1};
+        case 5: return {8, 5, 1, 1, 0};
+        case 6: return {8, 6, 2, 1, 0};
+        case 7: return {12, 6, 2, 1, 0};
+        default: return {12, 6, 3, 1, 0};
     }
 }
 __host__ __device__ __forceinline__ uint32_t qlp_precision_for(uint32_t bps, uint32_t blocksize) {
@@ -334,7 +336,8 @@ __global__ void __launch_bounds__(kEncThreads, 3)
 k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint32_t channels, uint32_t bps_stream,
                    uint32_t blocksize, uint32_t level, const int32_t *__restrict__ audio,
                    const float *__restrict__ window, uint32_t slot_words, uint32_t *__restrict__ slots,
-                   uint32_t *__restrict__ sub_bits, const uint32_t *__restrict__ task_list) {
+                   uint32_t *__restrict__ sub_bits, const uint32_t *__restrict__ task_list, uint32_t side_ch,
+                   uint32_t *__restrict__ sub_est) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EncShared &S = *reinterpret_cast<EncShared *>(smem_raw);
     const uint32_t task = task_list ? task_list[blockIdx.x] : blockIdx.x;
@@ -353,7 +356,8 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
     const int32_t *src = audio + st.audio_base + (int64_t)c * (int64_t)st.n_samples + (int64_t)kf * blocksize;
     int32_t *X = S.buf[1];
     const LevelCfg cfg = level_cfg(level);
-    const uint32_t k_limit = bps_stream > 16 ? 31u : 15u;
+    const uint32_t k_limit = bps_stream > 16 ? 31u : 15u;      // by the STREAM's bps, also for a 17-bit side channel
+    const uint32_t sbps = bps_stream + (c == side_ch ? 1u : 0u);
     const uint32_t i0 = tid * kSPT;
 
     // ---- load, wasted bits, constant check -----------------------------------
@@ -367,8 +371,8 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
     orv = block_or(orv, S);
     diff = block_or(diff, S);
     uint32_t wasted = orv ? (uint32_t)(__ffs((int)orv) - 1) : 0;
-    if (wasted > bps_stream) wasted = bps_stream;
-    const uint32_t bps = bps_stream - wasted;
+    if (wasted > sbps) wasted = sbps;
+    const uint32_t bps = sbps - wasted;
     if (wasted) {
 #pragma unroll
         for (int s = 0; s < kSPT; s++) { const uint32_t i = i0 + s; if (i < n) X[PX(i)] >>= wasted; }
@@ -392,7 +396,7 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
                 int32_t xv[kSPT + 4];
 #pragma unroll
                 for (int j = 0; j < kSPT + 4; j++) { int idx = (int)i0 - 4 + j; xv[j] = (idx >= 0 && (uint32_t)idx < n) ? X[PX(idx)] : 0; }
-                if (bps_stream <= 16) {
+                if (sbps <= 16) {
                     // successive differences in 32-bit: |4th difference| <= 16 * 2^15, 16 samples per thread
                     uint32_t e32[5] = {0, 0, 0, 0, 0};
                     int32_t d1[kSPT + 3], d2[kSPT + 2], d3[kSPT + 1], d4[kSPT];
@@ -452,7 +456,7 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
                 }
                 __syncthreads();
                 int32_t *R = S.buf[cand_buf];
-                bool ok = bps_stream <= 16 ? compute_residual<false>(X, R, n, (int)guess, 0, S.cand.coefs)
+                bool ok = sbps <= 16 ? compute_residual<false>(X, R, n, (int)guess, 0, S.cand.coefs)
                                             : compute_residual<true>(X, R, n, (int)guess, 0, S.cand.coefs);
                 int bad = __syncthreads_or(ok ? 0 : 1);
                 if (!bad) {
@@ -618,7 +622,7 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
                             cand_buf = (S.best_buf == 0 && (S.best.type >= 2)) ? 2 : 0;
                             const int order = S.cand.order, sh = S.cand.shift;
                             int32_t *R = S.buf[cand_buf];
-                            bool ok = bps_stream <= 16 ? compute_residual<false>(X, R, n, order, sh, S.cand.coefs)
+                            bool ok = sbps <= 16 ? compute_residual<false>(X, R, n, order, sh, S.cand.coefs)
                                                         : compute_residual<true>(X, R, n, order, sh, S.cand.coefs);
                             int bad = __syncthreads_or(ok ? 0 : 1);
                             if (!bad) {
@@ -750,7 +754,7 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
     const uint4 *b4 = reinterpret_cast<const uint4 *>(bitbuf);
     uint4 *s4 = reinterpret_cast<uint4 *>(slot);
     for (uint32_t q = tid; q < nq && q * 4 < slot_words; q += kEncThreads) s4[q] = b4[q];
-    if (tid == 0) sub_bits[task] = total_bits;
+    if (tid == 0) { sub_bits[task] = total_bits; if (sub_est) sub_est[task] = S.best.bits; }
 }
 
 #include "frb_encode_fast.cuh"
@@ -763,9 +767,70 @@ __device__ __forceinline__ uint32_t frame_header_bytes(uint32_t n, uint32_t samp
     return 4 + (uint32_t)utf8_len(number) + (uint32_t)bh + (sh == 0 ? 0u : sh == 1 ? 1u : 2u) + 1;
 }
 
+// ---- two-channel streams: libFLAC's stereo decorrelation --------------------------------------------------------
+// The four candidate subframes of a frame -- left, right, mid = (L+R)>>1, side = L-R (one more bit per sample) -- are
+// encoded as four VIRTUAL channels (k_ms_expand builds their planar audio, every analysis kernel runs unchanged on
+// them); k_ms_choose then picks the channel assignment per frame from libFLAC's ESTIMATED subframe bits, exactly as
+// process_subframes_ does: independent, left/side, right/side, mid/side in that order, strict improvement only; the
+// "loose" presets (levels 1 and 4) decide once every loose_frames frames and keep independent or switch to
+// mid/side in between.  frame_sel[f]: 0 independent, 1 left/side, 2 right/side, 3 mid/side; the frame is assembled
+// from two of the four slots.
+__host__ __device__ __forceinline__ uint32_t ms_slot(uint32_t sel, uint32_t c) {
+    // virtual channels: 0 L, 1 R, 2 M, 3 S
+    return sel == 0 ? c : sel == 1 ? (c == 0 ? 0u : 3u) : sel == 2 ? (c == 0 ? 3u : 1u) : (c == 0 ? 2u : 3u);
+}
+__host__ __device__ __forceinline__ uint32_t ms_channel_code(uint32_t sel) { return sel == 0 ? 1u : 7u + sel; }   // 1, 8, 9, 10
+
+__global__ void __launch_bounds__(256)
+k_ms_expand(const EncStreamDev *__restrict__ streams, const EncStreamDev *__restrict__ vstreams,
+            const int32_t *__restrict__ audio, int32_t *__restrict__ vaudio) {
+    const EncStreamDev st = streams[blockIdx.y], vs = vstreams[blockIdx.y];
+    const int32_t *l = audio + st.audio_base, *r = l + st.n_samples;
+    int32_t *o = vaudio + vs.audio_base;
+    const uint64_t n = st.n_samples;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int32_t a = l[i], b = r[i];
+        o[i] = a; o[n + i] = b; o[2 * n + i] = (a + b) >> 1; o[3 * n + i] = a - b;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_ms_choose(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint32_t blocksize, uint32_t total_frames, uint32_t loose,
+            const uint32_t *__restrict__ sub_est, uint8_t *__restrict__ frame_sel) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= total_frames) return;
+    uint32_t lo = 0, hi = n_streams - 1;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (streams[mid].frame_base <= f) lo = mid; else hi = mid - 1;
+    }
+    const EncStreamDev st = streams[lo];
+    const uint32_t k = f - st.frame_base;
+    auto decide = [&](uint32_t fr) -> uint32_t {
+        const uint32_t *e = sub_est + (size_t)fr * 4;
+        const unsigned long long b[4] = {(unsigned long long)e[0] + e[1], (unsigned long long)e[0] + e[3],
+                                         (unsigned long long)e[1] + e[3], (unsigned long long)e[2] + e[3]};
+        uint32_t best = 0;
+        for (uint32_t a = 1; a < 4; a++) if (b[a] < b[best]) best = a;
+        return best;
+    };
+    uint32_t sel;
+    if (!loose) sel = decide(f);
+    else {
+        // FLAC__stream_encoder: loose_mid_side_stereo_frames = (uint32_t)(sample_rate * 0.4 / blocksize + 0.5), at least 1
+        uint32_t lf = (uint32_t)((double)st.sample_rate * 0.4 / (double)blocksize + 0.5);
+        if (lf == 0) lf = 1;
+        const uint32_t r = k % lf;
+        if (r == 0) sel = decide(f);
+        else sel = decide(f - r) == 0 ? 0u : 3u;
+    }
+    frame_sel[f] = (uint8_t)sel;
+}
+
 __global__ void __launch_bounds__(256)
 k_frame_sizes(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint32_t channels, uint32_t blocksize,
-              uint32_t total_frames, const uint32_t *__restrict__ sub_bits, uint32_t *__restrict__ frame_bytes) {
+              uint32_t total_frames, const uint32_t *__restrict__ sub_bits, uint32_t *__restrict__ frame_bytes,
+              uint32_t vch, const uint8_t *__restrict__ frame_sel) {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= total_frames) return;
     uint32_t lo = 0, hi = n_streams - 1;
@@ -777,7 +842,7 @@ k_frame_sizes(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
     const uint32_t k = f - st.frame_base;
     const uint32_t n = (k + 1 < st.n_frames) ? blocksize : (uint32_t)(st.n_samples - (uint64_t)k * blocksize);
     uint64_t bits = 0;
-    for (uint32_t c = 0; c < channels; c++) bits += sub_bits[(size_t)f * channels + c];
+    for (uint32_t c = 0; c < channels; c++) bits += sub_bits[(size_t)f * vch + (frame_sel ? ms_slot(frame_sel[f], c) : c)];
     frame_bytes[f] = frame_header_bytes(n, st.sample_rate, k) + (uint32_t)((bits + 7) >> 3) + 2;
 }
 
@@ -828,6 +893,7 @@ struct EmitShared {
     CrcTables T;
     uint32_t hdr[6];
     uint32_t seg_start[FRB_MAX_CHANNELS + 2];
+    uint32_t slot_of[FRB_MAX_CHANNELS];      // slot (virtual channel) that holds subframe c of this frame
     uint32_t red[kEmitThreads / 32];
 };
 
@@ -847,7 +913,7 @@ __device__ __forceinline__ uint32_t emit_gather32(uint32_t P, const EmitShared &
             while (S.seg_start[c + 1] <= P) c++;
             const uint32_t o = P - S.seg_start[c];
             take = min(need, S.seg_start[c + 1] - P);
-            const uint32_t *sl = slots_f + (size_t)c * slot_words;
+            const uint32_t *sl = slots_f + (size_t)S.slot_of[c] * slot_words;
             const uint32_t wi = o >> 5, sh = o & 31;
             const uint32_t v = __funnelshift_l(__ldg(sl + wi + 1), __ldg(sl + wi), sh);
             bits = take == 32 ? v : (v >> (32 - take));
@@ -863,7 +929,7 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
               uint32_t blocksize, uint32_t total_frames, const uint32_t *__restrict__ sub_bits,
               const uint32_t *__restrict__ slots, uint32_t slot_words, const uint32_t *__restrict__ frame_bytes,
               const unsigned long long *__restrict__ frame_off, uint8_t *__restrict__ out, uint64_t out_capacity,
-              uint32_t *__restrict__ err_flag) {
+              uint32_t *__restrict__ err_flag, uint32_t vch, const uint8_t *__restrict__ frame_sel) {
     __shared__ __align__(16) EmitShared S;
     const int tid = threadIdx.x;
     crc_tables_to_smem(&S.T);
@@ -887,7 +953,8 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
         uint32_t i = 0;
         hb[i++] = 0xFF; hb[i++] = 0xF8;
         hb[i++] = (uint8_t)((bsc << 4) | src);
-        hb[i++] = (uint8_t)(((channels - 1) << 4) | (bps_code(bps_stream) << 1));
+        const uint32_t sel = frame_sel ? frame_sel[f] : 0u;
+        hb[i++] = (uint8_t)(((frame_sel ? ms_channel_code(sel) : channels - 1) << 4) | (bps_code(bps_stream) << 1));
         {
             uint64_t v = k; int len = utf8_len(v);
             if (len == 1) hb[i++] = (uint8_t)v;
@@ -911,14 +978,18 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
         S.hdr[4] = 0; S.hdr[5] = 0;
         uint32_t pos = i * 8;
         S.seg_start[0] = pos;
-        for (uint32_t c = 0; c < channels; c++) { pos += sub_bits[(size_t)f * channels + c]; S.seg_start[c + 1] = pos; }
+        for (uint32_t c = 0; c < channels; c++) {
+            const uint32_t sl = frame_sel ? ms_slot(sel, c) : c;
+            S.slot_of[c] = sl;
+            pos += sub_bits[(size_t)f * vch + sl]; S.seg_start[c + 1] = pos;
+        }
         if (((pos + 7) >> 3) + 2 != total || dst_off + total > out_capacity) atomicExch(err_flag, 1u);
     }
     __syncthreads();
     if (dst_off + total > out_capacity) continue;
     const uint32_t payload = total - 2;                        // bytes covered by the CRC-16
     const uint32_t hdr_bits = S.seg_start[0], end_bits = S.seg_start[channels];
-    const uint32_t *slots_f = slots + (size_t)f * channels * slot_words;
+    const uint32_t *slots_f = slots + (size_t)f * vch * slot_words;
     uint8_t *dst = out + dst_off;
     const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);   // bytes of the first chunk that are not ours
     uint8_t *g0 = dst - a;
@@ -937,7 +1008,7 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
             while (ch + 1 < channels && S.seg_start[ch + 1] <= P) ch++;
             if (P >= hdr_bits && P + 128 <= S.seg_start[ch + 1]) {
                 const uint32_t o = P - S.seg_start[ch];
-                const uint32_t *sl = slots_f + (size_t)ch * slot_words + (o >> 5);
+                const uint32_t *sl = slots_f + (size_t)S.slot_of[ch] * slot_words + (o >> 5);
                 const uint32_t sh = o & 31;
                 uint32_t v0 = __ldg(sl), v1 = __ldg(sl + 1), v2 = __ldg(sl + 2), v3 = __ldg(sl + 3), v4 = __ldg(sl + 4);
                 w[0] = __funnelshift_l(v1, v0, sh); w[1] = __funnelshift_l(v2, v1, sh);
@@ -1013,11 +1084,19 @@ struct EncWorkspace {
     FrameDesc *frame_table;
     unsigned long long *fx_fin;
     uint32_t *slots;
+    EncStreamDev *vstreams;      // two-channel streams: stream table of the four virtual channels (L, R, M, S)
+    uint32_t *sub_est;           //   estimated bits per virtual subframe (libFLAC's decision metric)
+    uint8_t *frame_sel;          //   chosen channel assignment per frame
+    int32_t *vaudio;             //   planar audio of the virtual channels
 };
+// Two-channel streams are analysed as four virtual channels (see k_ms_choose); the workspace is laid out for that
+// whenever channels == 2, whether or not the level / bit depth ends up using it.
+static inline uint32_t enc_virtual_channels(const frb_encode_params *p) { return p->channels == 2 ? 4u : p->channels; }
+static inline uint32_t enc_slot_bps(const frb_encode_params *p) { return p->bps + (p->channels == 2 ? 1u : 0u); }
 static inline size_t enc_ws_layout(const frb_encode_params *p, uint64_t total_frames, void *base, EncWorkspace *w) {
     size_t off = 0;
     uint8_t *b = (uint8_t *)base;
-    const uint64_t subs = total_frames * p->channels;
+    const uint64_t subs = total_frames * enc_virtual_channels(p);
 #define FRB_TAKE(field, type, count)                                         \
     if (w) w->field = (type *)(b + off);                                      \
     off += align256(sizeof(type) * (size_t)(count));
@@ -1035,7 +1114,11 @@ static inline size_t enc_ws_layout(const frb_encode_params *p, uint64_t total_fr
     FRB_TAKE(slow_tasks, uint32_t, subs)
     FRB_TAKE(frame_table, FrameDesc, total_frames)
     FRB_TAKE(fx_fin, unsigned long long, subs * 64)
-    FRB_TAKE(slots, uint32_t, subs * slot_words_for(p->blocksize, p->bps))
+    FRB_TAKE(slots, uint32_t, subs * slot_words_for(p->blocksize, enc_slot_bps(p)))
+    FRB_TAKE(vstreams, EncStreamDev, p->n_streams)
+    FRB_TAKE(sub_est, uint32_t, subs)
+    FRB_TAKE(frame_sel, uint8_t, total_frames)
+    FRB_TAKE(vaudio, int32_t, p->channels == 2 ? total_frames * (uint64_t)p->blocksize * 4u : 0u)
 #undef FRB_TAKE
     return off;
 }
@@ -1052,6 +1135,10 @@ static inline void make_tukey(float *w, int L, float p) {
         }
     }
 }
+
+// libFLAC's stereo decorrelation applies to exactly two channels at the presets with do_mid_side; the GPU path covers
+// 16-bit streams (a 32-bit stream would need a 33-bit side channel: those stay independent)
+static inline bool enc_mid_side(const frb_encode_params *p) { return p->channels == 2 && p->bps == 16 && level_cfg(p->level).mid_side; }
 
 static inline bool enc_params_ok(const frb_encode_params *p) {
     return p && p->n_streams >= 1 && p->channels >= 1 && p->channels <= FRB_MAX_CHANNELS &&
@@ -1091,11 +1178,35 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const int32_t *d_a
     cudaStream_t s = (cudaStream_t)stream;
     std::vector<float> win(FRB_MAX_BLOCKSIZE, 1.0f);
     make_tukey(win.data(), (int)p->blocksize, 0.5f / (float)level_cfg(p->level).windows);
+    // two-channel streams at a mid/side preset: analyse the four virtual channels L, R, M, S (an_* below)
+    const bool ms = enc_mid_side(p);
+    const uint32_t an_ch = ms ? 4u : p->channels;
+    std::vector<EncStreamDev> vhs;
+    if (ms) {
+        vhs = hs;
+        uint64_t cum = 0;
+        for (uint32_t i = 0; i < p->n_streams; i++) { vhs[i].audio_base = (int64_t)(4 * cum); cum += hs[i].n_samples; }
+        if (cum > frames * (uint64_t)p->blocksize) return FRB_ERR_INVALID_ARG;
+        FRB_CUDA(cudaMemcpyAsync(w.vstreams, vhs.data(), sizeof(EncStreamDev) * vhs.size(), cudaMemcpyHostToDevice, s));
+    }
     FRB_CUDA(cudaMemcpyAsync(w.streams, hs.data(), sizeof(EncStreamDev) * hs.size(), cudaMemcpyHostToDevice, s));
     FRB_CUDA(cudaMemcpyAsync(w.window, win.data(), sizeof(float) * FRB_MAX_BLOCKSIZE, cudaMemcpyHostToDevice, s));
     FRB_CUDA(cudaMemsetAsync(w.err_flag, 0, 256, s));
     FRB_CUDA(cudaStreamSynchronize(s));       // staging vectors are locals
-    const uint32_t slot_words = slot_words_for(p->blocksize, p->bps);
+    const std::vector<EncStreamDev> &ahs = ms ? vhs : hs;
+    const EncStreamDev *an_streams = ms ? w.vstreams : w.streams;
+    const int32_t *an_audio = ms ? w.vaudio : d_audio;
+    const uint32_t side_ch = ms ? 3u : 0xFFFFFFFFu;
+    uint32_t *sub_est = ms ? w.sub_est : nullptr;
+    if (ms) {
+        uint64_t max_n = 0;
+        for (uint32_t i = 0; i < p->n_streams; i++) max_n = std::max<uint64_t>(max_n, hs[i].n_samples);
+        uint32_t gx = (uint32_t)std::min<uint64_t>((max_n + 256 * 8 - 1) / (256 * 8), std::max<uint32_t>(1u, (uint32_t)kNumSMs * 16 / p->n_streams));
+        if (gx < 1) gx = 1;
+        k_ms_expand<<<dim3(gx, p->n_streams), 256, 0, s>>>(w.streams, w.vstreams, d_audio, w.vaudio);
+        FRB_LAUNCH_CHECK("k_ms_expand");
+    }
+    const uint32_t slot_words = slot_words_for(p->blocksize, enc_slot_bps(p));
     static bool attr_set[64] = {false};
     if (first_call_on_device(attr_set))
         FRB_CUDA(cudaFuncSetAttribute(k_encode_subframes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncShared)));
@@ -1104,17 +1215,17 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const int32_t *d_a
     const LevelCfg cfg = level_cfg(p->level);
     const bool fast = p->blocksize == (uint32_t)kMaxBlock && cfg.max_po >= 3 && cfg.max_po <= 6;
     std::vector<uint32_t> slow;
-    const uint32_t total_tasks = (uint32_t)(frames * p->channels);
+    const uint32_t total_tasks = (uint32_t)(frames * an_ch);
     if (fast) {
-        const uint64_t base_words = (uint64_t)(reinterpret_cast<uintptr_t>(d_audio) >> 2);
-        if (reinterpret_cast<uintptr_t>(d_audio) & 3u) return FRB_ERR_INVALID_ARG;
+        const uint64_t base_words = (uint64_t)(reinterpret_cast<uintptr_t>(an_audio) >> 2);
+        if (reinterpret_cast<uintptr_t>(an_audio) & 3u) return FRB_ERR_INVALID_ARG;
         for (uint32_t i = 0; i < p->n_streams; i++) {
-            const EncStreamDev &d = hs[i];
+            const EncStreamDev &d = ahs[i];
             const bool tail = (d.n_samples % p->blocksize) != 0;
-            for (uint32_t c = 0; c < p->channels; c++) {
+            for (uint32_t c = 0; c < an_ch; c++) {
                 const bool aligned = ((base_words + (uint64_t)d.audio_base + (uint64_t)c * d.n_samples) & 3u) == 0;
                 for (uint32_t k = aligned ? (tail ? d.n_frames - 1 : d.n_frames) : 0; k < d.n_frames; k++)
-                    slow.push_back((d.frame_base + k) * p->channels + c);
+                    slow.push_back((d.frame_base + k) * an_ch + c);
             }
         }
         if (!slow.empty()) {
@@ -1127,50 +1238,58 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const int32_t *d_a
         const uint32_t windows = (uint32_t)cfg.windows, max_lpc = (uint32_t)cfg.max_lpc_order;
         const uint32_t n_cands = max_lpc == 0 ? 0u : windows == 1 ? 1u : windows == 2 ? 3u : 9u;     // LPC candidates
         const bool wide = p->bps > 16;
-        const dim3 grid((uint32_t)frames, p->channels);
-        k_frame_table<<<(uint32_t)((frames + 255) / 256), 256, 0, s>>>(w.streams, p->n_streams, p->blocksize, (uint32_t)frames, w.frame_table);
+        // one CTA per subframe; with mid/side the 17-bit side channel (virtual channel 3) runs in the 64-bit kernels
+        const dim3 grid((uint32_t)frames, ms ? 3u : p->channels), grid_side((uint32_t)frames, 1);
+        k_frame_table<<<(uint32_t)((frames + 255) / 256), 256, 0, s>>>(an_streams, p->n_streams, p->blocksize, (uint32_t)frames, w.frame_table);
         FRB_LAUNCH_CHECK("k_frame_table");
         prof_begin(4, s);
-#define FRB_STATS(W, NL) k_enc_stats<W, NL><<<grid, kEncThreads, 0, s>>>(w.frame_table, p->channels, p->bps, windows, (uint32_t)cfg.max_po, d_audio, \
-            w.window, w.stats, w.autoc, w.fx_fin)
-        if (max_lpc == 0) { if (wide) FRB_STATS(true, 0); else FRB_STATS(false, 0); }
-        else if (max_lpc <= 8) { if (wide) FRB_STATS(true, 9); else FRB_STATS(false, 9); }
-        else { if (wide) FRB_STATS(true, 13); else FRB_STATS(false, 13); }
+#define FRB_STATS(W, NL, G, C0, EX) k_enc_stats<W, NL><<<G, kEncThreads, 0, s>>>(w.frame_table, an_ch, p->bps, windows, (uint32_t)cfg.max_po, an_audio, \
+            w.window, w.stats, w.autoc, w.fx_fin, C0, EX)
+#define FRB_STATS_L(NL) do { if (wide) FRB_STATS(true, NL, grid, 0u, 0u); else FRB_STATS(false, NL, grid, 0u, 0u); \
+                             if (ms) FRB_STATS(true, NL, grid_side, 3u, 1u); } while (0)
+        if (max_lpc == 0) FRB_STATS_L(0);
+        else if (max_lpc <= 8) FRB_STATS_L(9);
+        else FRB_STATS_L(13);
+#undef FRB_STATS_L
 #undef FRB_STATS
         prof_end(4, s);
         FRB_LAUNCH_CHECK("k_enc_stats");
-        k_enc_fixed<<<(total_tasks + 3) / 4, 128, 0, s>>>(w.frame_table, p->channels, p->bps, (uint32_t)cfg.max_po, total_tasks, d_audio,
-                                                        w.stats, w.fx_fin);
+        k_enc_fixed<<<(total_tasks + 3) / 4, 128, 0, s>>>(w.frame_table, an_ch, p->bps, (uint32_t)cfg.max_po, total_tasks, an_audio,
+                                                        w.stats, w.fx_fin, side_ch);
         FRB_LAUNCH_CHECK("k_enc_fixed");
         const uint32_t n_slots = n_cands;
         const uint32_t model_threads = total_tasks * n_slots;
         if (n_cands) {
-#define FRB_MODEL(MO) k_enc_model<MO><<<(model_threads + 127) / 128, 128, 0, s>>>(w.frame_table, p->channels, p->bps, \
-            p->blocksize, windows, max_lpc, n_slots, total_tasks, d_audio, w.stats, w.autoc, w.cands)
+#define FRB_MODEL(MO) k_enc_model<MO><<<(model_threads + 127) / 128, 128, 0, s>>>(w.frame_table, an_ch, p->bps, \
+            p->blocksize, windows, max_lpc, n_slots, total_tasks, an_audio, w.stats, w.autoc, w.cands, side_ch)
         if (max_lpc <= 8) FRB_MODEL(8); else FRB_MODEL(12);
 #undef FRB_MODEL
         FRB_LAUNCH_CHECK("k_enc_model");
         }
         prof_begin(0, s);
-        if (wide)
-            k_enc_code<true><<<grid, kEncThreads, 0, s>>>(w.frame_table, p->channels, p->bps, (uint32_t)cfg.max_po, n_cands, d_audio,
-                                                          w.stats, w.cands, slot_words, w.slots, w.sub_bits);
-        else
-            k_enc_code<false><<<grid, kEncThreads, 0, s>>>(w.frame_table, p->channels, p->bps, (uint32_t)cfg.max_po, n_cands, d_audio,
-                                                           w.stats, w.cands, slot_words, w.slots, w.sub_bits);
+#define FRB_CODE(W, G, C0, EX) k_enc_code<W><<<G, kEncThreads, 0, s>>>(w.frame_table, an_ch, p->bps, (uint32_t)cfg.max_po, n_cands, an_audio, \
+            w.stats, w.cands, slot_words, w.slots, w.sub_bits, C0, EX, sub_est)
+        if (wide) FRB_CODE(true, grid, 0u, 0u); else FRB_CODE(false, grid, 0u, 0u);
+        if (ms) FRB_CODE(true, grid_side, 3u, 1u);
+#undef FRB_CODE
         prof_end(0, s);
         FRB_LAUNCH_CHECK("k_enc_code");
     }
     if (!fast || !slow.empty()) {
         const uint32_t grid = fast ? (uint32_t)slow.size() : total_tasks;
         k_encode_subframes<<<grid, kEncThreads, sizeof(EncShared), s>>>(
-            w.streams, p->n_streams, p->channels, p->bps, p->blocksize, p->level, d_audio, w.window, slot_words, w.slots, w.sub_bits,
-            fast ? w.slow_tasks : nullptr);
+            an_streams, p->n_streams, an_ch, p->bps, p->blocksize, p->level, an_audio, w.window, slot_words, w.slots, w.sub_bits,
+            fast ? w.slow_tasks : nullptr, side_ch, sub_est);
         FRB_LAUNCH_CHECK("k_encode_subframes");
     }
     prof_end(6, s);
+    if (ms) {
+        k_ms_choose<<<(uint32_t)((frames + 255) / 256), 256, 0, s>>>(w.streams, p->n_streams, p->blocksize, (uint32_t)frames,
+                                                                   (uint32_t)cfg.loose, w.sub_est, w.frame_sel);
+        FRB_LAUNCH_CHECK("k_ms_choose");
+    }
     k_frame_sizes<<<(uint32_t)((frames + 255) / 256), 256, 0, s>>>(w.streams, p->n_streams, p->channels, p->blocksize,
-                                                                 (uint32_t)frames, w.sub_bits, w.frame_bytes);
+                                                                 (uint32_t)frames, w.sub_bits, w.frame_bytes, an_ch, ms ? w.frame_sel : nullptr);
     FRB_LAUNCH_CHECK("k_frame_sizes");
     k_stream_scan<<<p->n_streams, 1024, 0, s>>>(w.streams, w.frame_bytes, w.frame_off, w.stream_bytes);
     FRB_LAUNCH_CHECK("k_stream_scan");
@@ -1203,8 +1322,9 @@ extern "C" int frb_encode_emit(const frb_encode_params *p, void *d_workspace, si
     FRB_LAUNCH_CHECK("k_set_out_offsets");
     prof_begin(2, s);
     k_emit_frames<<<(uint32_t)std::min<uint64_t>(frames, (uint64_t)kNumSMs * 16), kEmitThreads, 0, s>>>(w.streams, p->n_streams, p->channels, p->bps, p->blocksize,
-                                                           (uint32_t)frames, w.sub_bits, w.slots, slot_words_for(p->blocksize, p->bps),
-                                                           w.frame_bytes, w.frame_off, d_out, (uint64_t)out_capacity, w.err_flag);
+                                                           (uint32_t)frames, w.sub_bits, w.slots, slot_words_for(p->blocksize, enc_slot_bps(p)),
+                                                           w.frame_bytes, w.frame_off, d_out, (uint64_t)out_capacity, w.err_flag,
+                                                           enc_mid_side(p) ? 4u : p->channels, enc_mid_side(p) ? w.frame_sel : nullptr);
     prof_end(2, s);
     FRB_LAUNCH_CHECK("k_emit_frames");
     if (d_frame_bytes)

@@ -260,10 +260,13 @@ __global__ void __launch_bounds__(kEncThreads, (NLAGS > 9 || WIDE) ? 2 : FRB_STA
 k_enc_stats(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps_stream,
             uint32_t windows, uint32_t max_po_cfg, const int32_t *__restrict__ audio,
             const float *__restrict__ window, EncSubStats *__restrict__ stats, double *__restrict__ autoc_out,
-            unsigned long long *__restrict__ fx_fin) {
+            unsigned long long *__restrict__ fx_fin, uint32_t c0, uint32_t side_extra) {
+    // c0 / side_extra: channel offset of this launch and 1 when its subframes carry one more bit than the stream (the
+    // side channel of a two-channel stream, see frb_encode_analyse); bps_stream stays the STREAM's value
     __shared__ StatsShared S;
-    const uint32_t task = blockIdx.x * channels + blockIdx.y;
-    const TaskLoc L = locate_task(frames, audio, blockIdx.x, blockIdx.y);
+    const uint32_t cch = blockIdx.y + c0, sbps = bps_stream + side_extra;
+    const uint32_t task = blockIdx.x * channels + cch;
+    const TaskLoc L = locate_task(frames, audio, blockIdx.x, cch);
     if (!fast_eligible(L)) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr uint32_t n = kMaxBlock;
@@ -294,7 +297,7 @@ k_enc_stats(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bp
 #pragma unroll
     for (int w = 0; w < 8; w++) { orv |= S.orv[w]; diff |= S.diff[w]; }
     uint32_t wasted = orv ? (uint32_t)(__ffs((int)orv) - 1) : 0;
-    if (wasted > bps_stream) wasted = bps_stream;
+    if (wasted > sbps) wasted = sbps;
     if (wasted) {
 #pragma unroll
         for (int j = 0; j < 28; j++) xs[j] >>= wasted;
@@ -376,7 +379,7 @@ k_enc_stats(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bp
 #pragma unroll
     for (int q = 0; q < 5; q++) e[q] = __shfl_sync(0xFFFFFFFFu, et, q);
     if (tid < 5) stats[task].e[tid] = et;
-    const uint32_t bps = bps_stream - wasted;
+    const uint32_t bps = sbps - wasted;
     uint32_t flags = diff == 0 ? 1u : 0u;
     if (diff != 0) {
         // ---- FIXED candidate: libFLAC's order guess; the per-thread |residual| sums of that order are already in
@@ -479,7 +482,8 @@ k_enc_stats(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bp
 // from the finest partition sums k_enc_stats stored.
 __global__ void __launch_bounds__(128)
 k_enc_fixed(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps_stream, uint32_t max_po_cfg, uint32_t total_tasks,
-            const int32_t *__restrict__ audio, EncSubStats *__restrict__ stats, const unsigned long long *__restrict__ fx_fin) {
+            const int32_t *__restrict__ audio, EncSubStats *__restrict__ stats, const unsigned long long *__restrict__ fx_fin,
+            uint32_t side_ch) {
     const int lane = threadIdx.x & 31;
     const uint32_t task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (task >= total_tasks) return;
@@ -491,7 +495,7 @@ k_enc_fixed(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bp
     if (!(flags & 2u)) return;
     constexpr uint32_t n = kMaxBlock;
     const uint32_t wasted = st->wasted, guess = st->fx_order;
-    const uint32_t bps = bps_stream - wasted;
+    const uint32_t bps = bps_stream + (task - f * channels == side_ch ? 1u : 0u) - wasted;
     // FLAC__fixed_compute_best_predictor's estimate for the guessed order; >= bps means "do not even try"
     const unsigned long long eg = st->e[guess];
     const float fbits_guess = (float)(eg > 0 ? log(0.69314718055994530942 * (double)eg / (double)(n - 4)) / 0.69314718055994530942 : 0.0);
@@ -618,7 +622,7 @@ __global__ void __launch_bounds__(128)
 k_enc_model(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps_stream,
             uint32_t blocksize, uint32_t windows, uint32_t max_lpc_cfg, uint32_t n_cands, uint32_t total_tasks,
             const int32_t *__restrict__ audio, EncSubStats *__restrict__ stats, const double *__restrict__ autoc_in,
-            EncCand *__restrict__ cands) {
+            EncCand *__restrict__ cands, uint32_t side_ch) {
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t task = gid / n_cands, slot = gid - task * n_cands;
     if (task >= total_tasks) return;
@@ -632,7 +636,7 @@ k_enc_model(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bp
     for (int j = 0; j < kMaxOrd; j++) C.coefs[j] = 0;
     const EncSubStats *stp = stats + task;
     const uint32_t st_flags = stp->flags;
-    const uint32_t bps = bps_stream - stp->wasted;
+    const uint32_t bps = bps_stream + (task - f * channels == side_ch ? 1u : 0u) - stp->wasted;
     if (!(st_flags & 1u)) {
         if constexpr (MAXO > 0) {
             // map the slot to (set, punch-out?)
@@ -760,17 +764,19 @@ __global__ void __launch_bounds__(kEncThreads, WIDE ? 2 : FRB_CODE_MINB)
 k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps_stream,
            uint32_t max_po_cfg, uint32_t n_cands, const int32_t *__restrict__ audio,
            const EncSubStats *__restrict__ stats, const EncCand *__restrict__ cands, uint32_t slot_words,
-           uint32_t *__restrict__ slots, uint32_t *__restrict__ sub_bits) {
+           uint32_t *__restrict__ slots, uint32_t *__restrict__ sub_bits, uint32_t c0, uint32_t side_extra,
+           uint32_t *__restrict__ sub_est) {
     __shared__ __align__(16) CodeShared<WIDE> S;
-    const uint32_t task = blockIdx.x * channels + blockIdx.y;
-    const TaskLoc L = locate_task(frames, audio, blockIdx.x, blockIdx.y);
+    const uint32_t cch = blockIdx.y + c0;
+    const uint32_t task = blockIdx.x * channels + cch;
+    const TaskLoc L = locate_task(frames, audio, blockIdx.x, cch);
     if (!fast_eligible(L)) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr uint32_t n = kMaxBlock;
     const uint32_t k_limit = bps_stream > 16 ? 31u : 15u;
     const EncSubStats *stp = stats + task;
     const uint32_t wasted = stp->wasted, st_flags = stp->flags;
-    const uint32_t bps = bps_stream - wasted;
+    const uint32_t bps = bps_stream + side_extra - wasted;
     int32_t xs[28];
     load_samples28(L.src, tid, xs);
     if (wasted) {
@@ -972,5 +978,5 @@ k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps
     const uint4 *b4 = reinterpret_cast<const uint4 *>(S.bitbuf);
     uint4 *s4 = reinterpret_cast<uint4 *>(slot);
     for (uint32_t q = tid; q < nq && q * 4 < slot_words; q += kEncThreads) s4[q] = b4[q];
-    if (tid == 0) sub_bits[task] = total_bits;
+    if (tid == 0) { sub_bits[task] = total_bits; if (sub_est) sub_est[task] = best_bits; }      // estimate = libFLAC's decision metric
 }

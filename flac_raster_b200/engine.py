@@ -369,6 +369,9 @@ class Engine:
                                                   out.data_ptr(), nat.DTYPE_CODES[dt], bands, H, W,
                                                   ws.data_ptr(), ws.numel(), d_status.data_ptr(), s), "frb_decode_tiles")
                 status = d_status.cpu().numpy().astype(np.int64)      # also keeps d_stage alive until the kernels are done
+                if status[6]:
+                    raise nat.NativeError(nat.ERR_INVALID_ARG, "frb_decode_tiles",
+                                          f"{int(status[6])} tile(s) do not match their stream length or lie outside the raster")
                 if status[4] == 0:
                     break
         return status

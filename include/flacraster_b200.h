@@ -197,7 +197,8 @@ int frb_decode_workspace_size(const frb_decode_params *p, uint64_t total_frames,
 /* d_bytes must be readable 16 bytes past the last stream's end.
  * d_audio: int32 planar, same layout as section 2.  d_status: 8 uint32
  * {frames_missing, crc16_errors, parse_errors, frames_decoded, lpc_order_above_12 (rerun with
- * reserved = 32), offset_wait_timeouts, 0, 0}.  Multi-channel streams: the subframe offsets of a frame
+ * reserved = 32), offset_wait_timeouts, tiles_rejected (frb_decode_tiles: h*w != n_samples or window
+ * outside the raster; nothing is written for them), 0}.  Multi-channel streams: the subframe offsets of a frame
  * are found and consumed inside ONE launch (skim CTAs publish, decode threads acquire). */
 int frb_decode_batch(const frb_decode_params *p, const frb_decode_stream *h_streams,
                      const uint8_t *d_bytes, uint64_t total_frames, int32_t *d_audio,

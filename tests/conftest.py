@@ -51,4 +51,16 @@ def signal_cases(seed=7):
     c["exact8192"] = ((1000 * np.sin(np.arange(8192) / 9.0)).astype(np.int32).reshape(-1, 1), 16)
     c["extremes16"] = (np.where(rng.random((6000, 1)) < 0.5, -32767, 32767).astype(np.int32), 16)
     c["ramp24"] = ((np.arange(20000) * 397 - 4000000).astype(np.int32).reshape(-1, 1), 32)
+    # two correlated channels: libFLAC's mid/side search (left/side, right/side and mid/side all win somewhere)
+    left = np.cumsum(rng.integers(-60, 61, size=40000)).astype(np.int64)
+    st = np.stack([left, left + rng.integers(-6, 7, size=left.size)], axis=1)
+    st[12000:20000, 1] = rng.integers(-3000, 3000, size=8000)          # right turns into noise: independent / left-side
+    st[26000:33000, 0] = -st[26000:33000, 1] + rng.integers(-4, 5, size=7000)   # anti-correlated: mid is small
+    st[33000:, 0] = st[33000:, 1] + rng.integers(-40, 41, size=7000)                # left = smooth right + noise: right/side
+    st[33000:, 1] = np.cumsum(rng.integers(-3, 4, size=7000)) + st[32999, 1]
+    st[33000:, 0] = st[33000:, 1] + rng.integers(-40, 41, size=7000)
+    c["stereo16_corr"] = (np.clip(st, -32767, 32767).astype(np.int32), 16)
+    alt = np.where(np.arange(9000) % 2 == 0, 32000, -32000)
+    c["stereo16_extreme"] = (np.stack([alt + rng.integers(-700, 700, size=9000), -alt + rng.integers(-700, 700, size=9000)],
+                                      axis=1).astype(np.int32), 16)          # side = L-R swings over the full 17 bits
     return c

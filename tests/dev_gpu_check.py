@@ -83,7 +83,7 @@ def check_encode():
                 stream = full_stream(payload, x.shape[0], x.shape[1], bps, rate)
                 dec, info = fo.decode(stream)
                 ok = np.array_equal(dec, x)
-                oenc, ofs = fo.encode(x, bps, rate, level, mid_side=False)
+                oenc, ofs = fo.encode(x, bps, rate, level, mid_side=(bps == 16))
                 osz = int(ofs.sum())
                 ratio = len(payload) / max(osz, 1)
                 same = bytes(payload) == oenc[len(oenc) - osz:]
