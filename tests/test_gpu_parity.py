@@ -391,6 +391,40 @@ def test_fullsize_c4_float32_level8_roundtrip(nat, torch_cuda):
     assert int(enc.sizes.sum()) < side * side * 4 * 0.75
 
 
+def test_two_band_raster_mid_side_tiles(nat, oracle, torch_cuda):
+    """A 2-band raster through the tile engine: frames equal the oracle's libFLAC procedure WITH its stereo decorrelation
+    (correlated bands make left/side or mid/side win), and the mid/side frames decode back to the raster."""
+    torch = torch_cuda
+    from flac_raster_b200 import flacfmt
+    from flac_raster_b200.engine import default_engine, tile_grid
+    from oracle import normalization_oracle as no
+    rng = np.random.default_rng(21)
+    H, W = 300, 420
+    yy, xx = np.mgrid[0:H, 0:W]
+    b0 = (3000 + 1500 * np.sin(xx / 31.0) * np.cos(yy / 19.0) + rng.integers(-20, 20, size=(H, W))).astype(np.uint16)
+    b1 = (b0.astype(np.int32) + 40 + rng.integers(-5, 5, size=(H, W))).astype(np.uint16)
+    x = np.stack([b0, b1])
+    raster = torch.from_numpy(x.view(np.int16)).cuda().view(torch.uint16)
+    eng = default_engine()
+    tiles = tile_grid(H, W, 160)
+    enc = eng.encode_tiles(raster, tiles, 5)
+    payload = enc.payload.cpu().numpy()
+    assigns = set()
+    for i, t in enumerate(tiles):
+        r, c, h, w = (int(t[k]) for k in ("row_off", "col_off", "h", "w"))
+        want, prm = no.normalize_to_audio(x[:, r:r + h, c:c + w].transpose(1, 2, 0).reshape(-1, 2), 16)
+        oenc, ofs, descs = oracle.encode(want, 16, int(enc.sample_rates[i]), 5, want_descs=True)
+        assigns.update(d["ch_assign"] for d in descs)
+        frames = payload[enc.offsets[i]:enc.offsets[i] + enc.sizes[i]].tobytes()
+        assert frames == oenc[len(oenc) - int(ofs.sum()):], i
+    assert assigns & {8, 9, 10}, assigns                      # the decorrelated forms were actually chosen
+    dev_payload = torch.cat([enc.payload, torch.zeros(64, dtype=torch.uint8, device=raster.device)])
+    out = torch.zeros_like(raster)
+    st = eng.decode_tiles(dev_payload, enc.offsets, enc.sizes, tiles, enc.sample_rates, enc.minmax, 32767.0, out, 16, 4096)
+    assert list(st[:3]) == [0, 0, 0], st
+    assert torch.equal(out.view(torch.int16), raster.view(torch.int16))
+
+
 def test_host_pipeline_equals_device_path(nat, torch_cuda):
     """encode_tiles_host (tile rows pipelined over copy/compute/copy streams, host buffers) produces exactly the
     bytes, offsets and min/max of the one-shot device path, including ragged edge tiles."""
