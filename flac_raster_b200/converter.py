@@ -195,12 +195,14 @@ class RasterFLACConverter:
         return None
 
 
-def decode_tile_blobs(blobs, headers, metadatas, mosaic=None):
+def decode_tile_blobs(blobs, headers, metadatas, mosaic=None, staged=None):
     """Batch-decode complete per-tile FLAC files on the GPU.
 
     blobs: list of bytes (each a standalone FLAC file as the streaming container holds them,
     cli.py:594-598); headers/metadatas: parsed per tile.  Returns a list of (bands,h,w) arrays
     in the original dtype (denormalize_from_audio integer path, normalization.py:222-249).
+    staged=(pinned uint8 tensor, nbytes, tile_starts): the tiles already sit in one pinned buffer (read straight
+    from the file, see SpatialFLACStreamer._decode); blobs are then views into it and nothing is copied on the host.
     """
     import torch
     from . import _native as nat
@@ -226,25 +228,32 @@ def decode_tile_blobs(blobs, headers, metadatas, mosaic=None):
             raise ValueError("tiles of one batch must share channels, bits per sample and blocksize")
         if md["count"] != si.channels:
             raise ValueError("band count in tags does not match the FLAC channel count")
-        body = memoryview(b)[h.first_frame_offset:]
-        offs[i], lens[i] = pos, len(body)
-        bodies.append(body)
-        pos += (len(body) + 3) & ~3
+        if staged is None:
+            body = memoryview(b)[h.first_frame_offset:]
+            offs[i], lens[i] = pos, len(body)
+            bodies.append(body)
+            pos += (len(body) + 3) & ~3
+        else:
+            offs[i], lens[i] = int(staged[2][i]) + h.first_frame_offset, len(b) - h.first_frame_offset
         nsamp[i] = md["width"] * md["height"]
         rates[i] = si.sample_rate
         tiles[i] = (row, 0, md["height"], md["width"])
         row += md["height"]
         maxw = max(maxw, md["width"])
         minmax[i] = (md["data_min"], md["data_max"])
-    # frames of all tiles -> one pinned staging buffer (no intermediate bytes objects) -> one H2D copy
-    stage = eng._pinned("dec_stage", pos + 64)
-    stage_np = stage.numpy()
-    for i, body in enumerate(bodies):
-        o = int(offs[i])
-        stage_np[o:o + len(body)] = np.frombuffer(body, dtype=np.uint8)
-        pad = (-len(body)) % 4
-        if pad:
-            stage_np[o + len(body):o + len(body) + pad] = 0
+    if staged is None:
+        # frames of all tiles -> one pinned staging buffer (no intermediate bytes objects) -> one H2D copy
+        stage = eng._pinned("dec_stage", pos + 64)
+        stage_np = stage.numpy()
+        for i, body in enumerate(bodies):
+            o = int(offs[i])
+            stage_np[o:o + len(body)] = np.frombuffer(body, dtype=np.uint8)
+            pad = (-len(body)) % 4
+            if pad:
+                stage_np[o + len(body):o + len(body) + pad] = 0
+    else:
+        stage, pos = staged[0], int(staged[1])
+        stage_np = stage.numpy()
     stage_np[pos:pos + 64] = 0
     data = eng._buf("dec_data", pos + 64)[:pos + 64]
     data.copy_(stage[:pos + 64], non_blocking=True)

@@ -363,8 +363,50 @@ class SpatialFLACStreamer:
             i = j + 1
         return blobs   # type: ignore[return-value]
 
+    def _fetch_tiles_pinned(self, frames: List[SpatialFrame]):
+        """Local file: read the (merged) byte ranges of the tiles straight into ONE pinned staging buffer -- no bytes
+        object per range and no second host copy before the H2D transfer.  Returns (views per tile, staged tuple)."""
+        from .engine import default_engine
+
+        eng = default_engine()
+        order = sorted(range(len(frames)), key=lambda i: frames[i].byte_offset)
+        total = sum(f.byte_size for f in frames)
+        stage = eng._pinned("dec_stage", total + 64)
+        stage_np = stage.numpy()
+        view = memoryview(stage_np)
+        starts = [0] * len(frames)
+        pos = 0
+        with open(self.flac_path, "rb", buffering=0) as fh:
+            i = 0
+            while i < len(order):
+                j = i
+                start = frames[order[i]].byte_offset
+                end = start + frames[order[i]].byte_size
+                while j + 1 < len(order) and frames[order[j + 1]].byte_offset == end:
+                    j += 1
+                    end += frames[order[j]].byte_size
+                fh.seek(self.header_size + start)
+                want = end - start
+                got = 0
+                while got < want:                                   # readinto may return short counts on large reads
+                    r = fh.readinto(view[pos + got:pos + want])
+                    if not r:
+                        raise ValueError("streaming container is shorter than its index says")
+                    got += r
+                for k in range(i, j + 1):
+                    f = frames[order[k]]
+                    starts[order[k]] = pos + (f.byte_offset - start)
+                pos += want
+                i = j + 1
+        blobs = [view[starts[i]:starts[i] + frames[i].byte_size] for i in range(len(frames))]
+        return blobs, (stage, pos, starts)
+
     def _decode(self, frames: List[SpatialFrame]):
-        blobs = self._fetch_tiles(frames)
+        staged = None
+        if self.is_url:
+            blobs = self._fetch_tiles(frames)
+        else:
+            blobs, staged = self._fetch_tiles_pinned(frames)
         headers = [flacfmt.parse_header(b) for b in blobs]
         metas = []
         for h in headers:
@@ -372,7 +414,7 @@ class SpatialFLACStreamer:
             if not md:
                 raise ValueError("No metadata found in FLAC file or sidecar file")
             metas.append(md)
-        arrays = decode_tile_blobs(blobs, headers, metas)
+        arrays = decode_tile_blobs(blobs, headers, metas, staged=staged)
         out = []
         for f, a, md in zip(frames, arrays, metas):
             meta = dict(md)
