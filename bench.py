@@ -376,6 +376,7 @@ def main():
     if rank != 0:
         if world > 1:
             dist.barrier()
+            dist.destroy_process_group()
         return 0
 
     peaks = {}
@@ -408,7 +409,7 @@ def main():
     # compressed bytes consumed + output written: pixels of the raster (fused launch) or int32 audio (two-step path)
     dec_alg = comp_bytes + samples_local * (raster.element_size() if fused_dec else 4)
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported by the single-GPU run only
         try:
             n_cpu = args.cpu_tiles or (8 if args.workload == "c3" else 64 if args.workload == "c5" else 4)
             ce, cd, sdesc, _ = run_cpu(args.workload, n_cpu, 1, dev)
@@ -446,6 +447,7 @@ def main():
     emit_line(line)
     if world > 1:
         dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 
