@@ -67,6 +67,29 @@ class ClockSampler(threading.Thread):
         self._halt = threading.Event()
 
     def run(self):
+        # NVML in-process (a query takes well under a millisecond, so even a 50 ms timed region gets several samples);
+        # nvidia-smi subprocesses (~0.2 s per sample) only if the binding is missing
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": pynvml.nvmlClocksEventReasonHwSlowdown if hasattr(pynvml, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                    "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._halt.is_set():
+                try:
+                    self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    r = int(get_reasons(h))
+                    for n, b in bits.items():
+                        if r & int(b):
+                            self.reasons.add(n)
+                except Exception:  # noqa: BLE001
+                    pass
+                self._halt.wait(0.004)
+            return
+        except Exception:  # noqa: BLE001
+            pass
         import subprocess
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -85,6 +108,17 @@ class ClockSampler(threading.Thread):
             except Exception:  # noqa: BLE001
                 pass
             self._halt.wait(0.2)
+
+    def _nvml_index(self) -> int:
+        # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it lists plain indices
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        try:
+            ids = [int(v) for v in vis.split(",") if v.strip() != ""]
+            if ids and self.index < len(ids):
+                return ids[self.index]
+        except ValueError:
+            pass
+        return self.index
 
     def stop(self):
         self._halt.set()
