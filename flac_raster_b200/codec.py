@@ -122,6 +122,16 @@ class StreamEncoder:
                                                       self._compression_level, self._blocksize)
                 except nat.NativeError as e:
                     raise EncoderProcessException(str(e)) from e
+                if self._verify:
+                    # libFLAC's verify mode (FLAC__stream_encoder_set_verify, docs/sonos-pyflac.txt:6810-6824): decode the
+                    # frames just produced -- on the GPU decoder -- and compare them with the input samples
+                    try:
+                        back = nat.host_decode(payload, self._channels, self._bits_per_sample, self._blocksize,
+                                               self._sample_rate, x.shape[0])
+                    except nat.NativeError as e:
+                        raise EncoderProcessException("FLAC__STREAM_ENCODER_VERIFY_DECODER_ERROR: " + str(e)) from e
+                    if not np.array_equal(back, x):
+                        raise EncoderProcessException("FLAC__STREAM_ENCODER_VERIFY_MISMATCH_IN_AUDIO_DATA")
                 mv = memoryview(payload)
                 off = 0
                 n = x.shape[0]

@@ -122,6 +122,40 @@ def test_decode_detects_corruption(nat, oracle):
         nat.host_decode(bytes(enc[off:off + 3000]), 1, 16, 4096, 44100, x.shape[0])
 
 
+def test_decode_fuzzed_multichannel_streams_fail_cleanly(nat, oracle):
+    """Random single-byte damage anywhere in an 8-channel stream (frame headers, subframe headers, Rice data, CRC bytes):
+    the fused skim + decode launch must come back promptly with CRC / malformed-stream status -- never hang on an offset
+    that is no longer published, never return damaged samples as good."""
+    x, bps = signal_cases()["smooth16_8ch"]
+    enc, _ = oracle.encode(x, bps, 44100, 5)
+    from flac_raster_b200 import flacfmt
+    off = flacfmt.parse_header(enc).first_frame_offset
+    good = bytearray(enc[off:])
+    assert np.array_equal(nat.host_decode(bytes(good), 8, 16, 4096, 44100, x.shape[0]), x)
+    rng = np.random.default_rng(99)
+    for trial in range(24):
+        bad = bytearray(good)
+        pos = int(rng.integers(0, len(bad)))
+        bad[pos] ^= int(rng.integers(1, 256))
+        if trial % 6 == 5:                                   # also a burst: a run of zero bytes (long unary runs)
+            bad[pos:pos + 64] = bytes(min(64, len(bad) - pos))
+        with pytest.raises(nat.NativeError) as ei:
+            nat.host_decode(bytes(bad), 8, 16, 4096, 44100, x.shape[0])
+        assert ei.value.status in (nat.ERR_CRC, nat.ERR_BAD_STREAM), (trial, pos, ei.value.status)
+    assert np.array_equal(nat.host_decode(bytes(good), 8, 16, 4096, 44100, x.shape[0]), x)   # and the engine is still healthy
+
+
+def test_stream_encoder_verify_mode(nat):
+    """pyflac's verify=True (libFLAC set_verify): the shim decodes its own frames on the GPU and compares."""
+    from flac_raster_b200 import codec
+    x = signal_cases()["stereo16_corr"][0].astype(np.int16)
+    chunks = []
+    enc = codec.StreamEncoder(44100, lambda b, n, s, f: chunks.append(bytes(b)), compression_level=5, blocksize=4096, verify=True)
+    enc.process(x)
+    assert enc.finish() is True
+    assert len(chunks) == 3 + (x.shape[0] + 4095) // 4096
+
+
 # ------------------------------------------------------------------ encode
 @pytest.mark.parametrize("level", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 def test_encode_matches_oracle_and_roundtrips(nat, oracle, level):
