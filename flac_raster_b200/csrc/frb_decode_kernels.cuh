@@ -25,6 +25,18 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t smem_addr) {
 }
 
 __device__ __forceinline__ int32_t unzigzag(uint32_t u) { return (int32_t)(u >> 1) ^ -(int32_t)(u & 1u); }
+// position of the most significant set bit (0xFFFFFFFF for 0): clz(w) = 31 - bfind(w), so the length of a Rice code with
+// parameter k is (k + 32) - bfind(window) in one subtraction, and 33 + k (> 32, "too long") for an all-zero window
+__device__ __forceinline__ uint32_t bfind_u32(uint32_t w) {
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(w));
+    return r;
+}
+__device__ __forceinline__ uint32_t shr_clamped(uint32_t v, uint32_t s) {      // v >> s with s >= 32 giving 0 (PTX semantics)
+    uint32_t r;
+    asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(s));
+    return r;
+}
 
 struct FrameLoc {
     uint64_t start, end;      // byte range [start, end) of the frame incl. CRC-16
@@ -241,11 +253,11 @@ skim_role(uint4 *s_ring, uint32_t cta, const uint8_t *__restrict__ bytes, const 
             // ---- a full batch of Rice codes without data-dependent branches; a code longer than 32 bits (long unary
             // run or corrupt data) is detected once per batch and the batch is then redone one code at a time ----
             const BitReader snap = br;
-            const uint32_t k1 = k + 1;
+            const uint32_t kb = k + 32;
             uint32_t maxlen = 0;
 #pragma unroll
             for (int i = 0; i < kSkimBatch; i++) {
-                const uint32_t len = (uint32_t)__clz(br.window()) + k1;
+                const uint32_t len = kb - bfind_u32(br.window());
                 maxlen = max(maxlen, len);
                 br.advance_predicated(len);
             }
@@ -600,16 +612,17 @@ __device__ __forceinline__ void decode_predictive(SubCtx &S, const PredState<PMA
         if (!escape && part_left >= (uint32_t)kDecBatch && (i & 3u) == 0) {       // (i & 3): keep the 16-byte stores aligned
             // ---- batch: kDecBatch codes, no data-dependent branch; redone sample by sample if one is longer than 32 bits ----
             const DecReader snap = br;
-            const uint32_t k1 = k + 1;
+            // code = z zeros, a one, k low bits.  With f = bfind(window) = 31 - z: length (k + 32) - f, the low bits sit at
+            // window >> (f - k), and z << k = (31 << k) - (f << k) is one multiply-add
+            const uint32_t kb = k + 32, kmask = (1u << k) - 1u, pow2k = 1u << k, c31k = 31u << k;
             uint32_t maxlen = 0, u[kDecBatch];
 #pragma unroll
             for (int j = 0; j < kDecBatch; j++) {
                 const uint32_t win = br.window();
-                const uint32_t z = (uint32_t)__clz(win);
-                const uint32_t len = z + k1;
+                const uint32_t f = bfind_u32(win);
+                const uint32_t len = kb - f;
                 maxlen = max(maxlen, len);
-                const uint32_t t = __funnelshift_lc(0u, win, z + 1);        // win << (z+1), 0 when z+1 == 32
-                u[j] = (z << k) | __funnelshift_lc(t, 0u, k);               // | t >> (32-k), 0 when k == 0
+                u[j] = (c31k - f * pow2k) | (shr_clamped(win, f - k) & kmask);   // garbage when len > 32: the batch is redone then
                 br.advance_predicated(len);
             }
             if (maxlen <= 32) {
