@@ -998,13 +998,16 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
     const uint32_t rows = nfull / kEmitThreads, rem = nfull % kEmitThreads;
     const CrcTables &T = S.T;
 
+    // A thread visits its chunks in increasing order, so the subframe that holds a chunk only moves forward: the
+    // segment search resumes where the previous chunk left it (it restarted from 0 for every chunk: 19 % of the kernel's
+    // instructions, profiles/r01_ncu_emit_v7.txt).  seg_start[] entries and the chunk's register state: per frame.
+    uint32_t ch = 0;
     // produce chunk c: returns its four big-endian words (head-masked), stores its bytes
     auto do_chunk = [&](uint32_t c, uint32_t (&w)[4], uint32_t nbytes /* valid bytes from the chunk start, 16 = full */) {
         const int32_t b0 = (int32_t)(16 * c) - (int32_t)a;    // frame byte of the chunk's first byte (negative in the head chunk)
         if (b0 >= 0 && nbytes == 16) {
             const uint32_t P = 8u * (uint32_t)b0;
             // common case: all 128 bits lie inside one subframe -> one segment lookup, five slot words, four funnel shifts
-            uint32_t ch = 0;
             while (ch + 1 < channels && S.seg_start[ch + 1] <= P) ch++;
             if (P >= hdr_bits && P + 128 <= S.seg_start[ch + 1]) {
                 const uint32_t o = P - S.seg_start[ch];
