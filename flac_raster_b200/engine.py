@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _native as nat
-from .normalization import audio_params_for
+from .normalization import audio_params_for, sample_rates_for_pixel_counts
 
 TORCH_DTYPES = {
     "uint8": torch.uint8, "int8": torch.int8, "uint16": torch.uint16, "int16": torch.int16,
@@ -153,8 +153,7 @@ class Engine:
             raise ValueError("FLAC carries at most 8 channels (bands)")
         audio, base, npx, d_minmax, bits = self.normalize_tiles(raster, tiles)
         bps = 16 if bits == 16 else 32            # pyflac derives bps from the array dtype (docs/sonos-pyflac.txt:1988-1991)
-        rates = np.array([audio_params_for((int(t["h"]), int(t["w"])), str(raster.dtype).replace("torch.", ""))[0] for t in tiles],
-                         dtype=np.uint32)
+        rates = sample_rates_for_pixel_counts(npx)                # one vector expression (4096 tiles: 5 ms of Python before)
         payload, offsets, sizes = self.encode_audio(audio, npx, base, rates, bands, bps, level, blocksize, payload_name)
         minmax = d_minmax.cpu().numpy().reshape(-1, 2)
         return EncodedTiles(payload, offsets, sizes, minmax, npx, rates, bands, bps, bits, blocksize)

@@ -86,6 +86,12 @@ def audio_params_for(shape, dtype) -> Tuple[int, int]:
     return rate, bits
 
 
+def sample_rates_for_pixel_counts(npx: np.ndarray) -> np.ndarray:
+    """Vectorised sample-rate rule of audio_params_for (normalization.py:113-120) for an array of pixel counts."""
+    npx = np.asarray(npx, dtype=np.int64)
+    return np.select([npx < 1_000_000, npx < 10_000_000, npx < 100_000_000], [44100, 48000, 96000], 192000).astype(np.uint32)
+
+
 def calculate_audio_params(data, dtype) -> Tuple[int, int]:
     """Same as the reference: sample rate by pixel count, bit depth by dtype."""
     return audio_params_for(tuple(data.shape), dtype)
