@@ -281,7 +281,11 @@ def main():
     import torch.distributed as dist
 
     nat.require_cuda()
+    numa_node = None
     if world > 1:
+        from flac_raster_b200.distributed import bind_to_gpu_numa_node
+        numa_node = bind_to_gpu_numa_node(local)            # before any pinned allocation (first touch)
+        print(f"[bench] rank {rank}: bound to NUMA node {numa_node}", file=sys.stderr)
         init_from_env("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -458,7 +462,8 @@ def main():
         "config": {"workload": desc if args.scale_div == 1 else desc + f" [DEBUG scale-div {args.scale_div}]", "level": level,
                    "tile_size": ts, "blocksize": 4096, "tiles_per_gpu": n_tiles_local, "samples_per_gpu": samples_local,
                    "l2": "inputs (>= 1.9 GB per step) are far larger than the 126 MB L2; no flush needed",
-                   "parallelism": f"tiles sharded over {world} GPU(s), one process per GPU; all-gather of per-tile sizes only"},
+                   "parallelism": f"tiles sharded over {world} GPU(s), one process per GPU; all-gather of per-tile sizes only",
+                   "numa_bound_rank0": numa_node},
         "compressed_bytes_per_gpu": comp_bytes, "bits_per_sample_out": comp_bytes * 8 / samples_local,
         "lossless_roundtrip_checked": lossless,
         "decode": {"value": total_samples / (dec_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": dec_ms,

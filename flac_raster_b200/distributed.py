@@ -40,6 +40,40 @@ def init_from_env(backend: Optional[str] = None):
     return rank, world, local
 
 
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """Pin this process (and therefore its first-touch pinned host buffers) to the CPUs of the NUMA node its GPU hangs
+    off.  With one process per GPU on a two-socket box the host side of the tile pipeline -- pinned staging, H2D of the
+    raster, D2H of the frames -- otherwise crosses the socket interconnect for half the ranks.  Best effort: returns the
+    node, or None when sysfs / NVML do not say."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip() != ""]
+        idx = int(vis[device_index]) if vis and all(v.strip().isdigit() for v in vis) and device_index < len(vis) else device_index
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:                      # NVML prints an 8-digit domain, sysfs uses 4
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def allgather_tile_sizes(local_sizes: np.ndarray, n_tiles: int, rank: int, world: int, device=None) -> np.ndarray:
     """All ranks obtain the byte size of every tile (int64[n_tiles]) -- the one collective of the path."""
     if world == 1:
