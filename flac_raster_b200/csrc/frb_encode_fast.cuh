@@ -379,7 +379,6 @@ k_enc_stats(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bp
 #pragma unroll
     for (int q = 0; q < 5; q++) e[q] = __shfl_sync(0xFFFFFFFFu, et, q);
     if (tid < 5) stats[task].e[tid] = et;
-    const uint32_t bps = sbps - wasted;
     uint32_t flags = diff == 0 ? 1u : 0u;
     if (diff != 0) {
         // ---- FIXED candidate: libFLAC's order guess; the per-thread |residual| sums of that order are already in

@@ -179,3 +179,24 @@ def test_pyflac_shim_signatures():
     with pytest.raises(codec.DecoderInitException):
         codec.FileDecoder("/nonexistent/file.flac")
     assert enc.finish() is False
+
+
+def test_sample_rates_vector_rule_equals_reference_rule():
+    """Engine.encode_tiles derives every tile's sample rate with one vector expression; it must be the reference's
+    threshold rule (normalization.py:113-120) at and around every boundary."""
+    from flac_raster_b200.normalization import audio_params_for, sample_rates_for_pixel_counts
+    counts = [1, 999_999, 1_000_000, 1_000_001, 9_999_999, 10_000_000, 99_999_999, 100_000_000, 3_000_000_000]
+    got = sample_rates_for_pixel_counts(np.array(counts))
+    assert got.dtype == np.uint32
+    assert [int(v) for v in got] == [audio_params_for((1, c), "uint16")[0] for c in counts]
+
+
+def test_numa_binding_is_best_effort():
+    """bind_to_gpu_numa_node never raises: without NVML / sysfs information it returns None and leaves the affinity."""
+    import os
+    from flac_raster_b200.distributed import bind_to_gpu_numa_node
+    before = os.sched_getaffinity(0)
+    node = bind_to_gpu_numa_node(0)
+    assert node is None or isinstance(node, int)
+    if node is None:
+        assert os.sched_getaffinity(0) == before

@@ -108,3 +108,27 @@ def test_oracle_rejects_corruption(oracle):
     data[5000] ^= 0x10
     with pytest.raises(ValueError):
         oracle.decode(bytes(data))
+
+
+def test_oracle_mid_side_presets(oracle):
+    """The restated stereo decorrelation of libFLAC's presets: none at levels 0 and 3; levels 1 and 4 ("loose") decide
+    every sample_rate*0.4/blocksize frames and keep independent or mid/side in between; the others choose among all four
+    assignments per frame; turning the search off can only make the stream larger."""
+    x, bps = signal_cases()["stereo16_corr"]
+    for level in range(9):
+        enc, fs, descs = oracle.encode(x, bps, 44100, level, want_descs=True)
+        dec, _ = oracle.decode(enc)
+        assert np.array_equal(dec, x)
+        assign = [d["ch_assign"] for d in descs[::2]]
+        if level in (0, 3):
+            assert set(assign) == {1}, (level, assign)
+            continue
+        plain, _ = oracle.encode(x, bps, 44100, level, mid_side=False)
+        assert len(enc) < len(plain), level
+        if level in (1, 4):
+            lf = int(44100 * 0.4 / 4096 + 0.5)                        # 4 frames per decision
+            for k, a in enumerate(assign):
+                if k % lf:
+                    assert a in (1, 10) and a == (1 if assign[k - k % lf] == 1 else 10), (level, k, assign)
+        else:
+            assert {8, 9, 10} <= set(assign), (level, assign)           # left/side, right/side and mid/side all occur
