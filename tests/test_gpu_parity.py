@@ -122,6 +122,72 @@ def test_decode_detects_corruption(nat, oracle):
         nat.host_decode(bytes(enc[off:off + 3000]), 1, 16, 4096, 44100, x.shape[0])
 
 
+def test_decode_handcrafted_stream_big_orders_rice2_escapes(nat, oracle, torch_cuda):
+    """Syntax no libFLAC preset emits, written by tests/flac_handcraft.py and checked against the oracle decoder first:
+    LPC orders 20, 32 and 13 (the > 12 kernel instantiation and the automatic rerun), Rice2 parameters, an escape-coded
+    partition, partition orders 3/0/2, a short last frame with a 16-bit blocksize field.  Decoded through the host API and
+    through the fused decode-to-raster launch."""
+    torch = torch_cuda
+    import flac_handcraft as hc
+    from flac_raster_b200 import flacfmt, _native as natmod
+    from flac_raster_b200.engine import default_engine
+    from oracle import normalization_oracle as no
+    rng = np.random.default_rng(4)
+    n_total, bs = 4096 * 2 + 1000, 4096
+    t = np.arange(n_total)
+    x = (9000 * np.sin(t / 40.0) + 3000 * np.sin(t / 7.3) + rng.integers(-40, 40, size=n_total)).astype(np.int64)
+    frames = b""
+    for f, a in enumerate(range(0, n_total, bs)):
+        order = [20, 32, 13][f]
+        coefs = rng.integers(-300, 300, size=order); coefs[0] = 1900; coefs[1] = -900
+        frames += hc.frame(x[a:a + bs], 16, 9, f, bs, oracle.crc8, oracle.crc16, order=order, coefs=coefs, shift=10, precision=12,
+                           partition_order=[3, 0, 2][f], rice2=(f == 1), escape_partitions=((2,) if f == 0 else ()))
+    si = flacfmt.StreamInfo(bs, bs, 0, 0, 44100, 1, 16, n_total)
+    ref, _ = oracle.decode(flacfmt.build_header(si) + frames)
+    assert np.array_equal(ref[:, 0], x)
+    got = nat.host_decode(frames, 1, 16, bs, 44100, n_total)
+    assert np.array_equal(got[:, 0], x)
+    # the same frames as one "tile" of 8 x 1149 pixels, straight into an int16 raster
+    eng = default_engine()
+    data = torch.cat([torch.from_numpy(np.frombuffer(frames, dtype=np.uint8).copy()), torch.zeros(64, dtype=torch.uint8)]).cuda()
+    tiles = np.zeros(1, dtype=natmod.TILE_DTYPE)
+    tiles[0] = (0, 0, 8, 1149)
+    mn, mx = -12345.0, 20000.0
+    out = torch.zeros(1, 8, 1149, dtype=torch.int16, device="cuda")
+    st = eng.decode_tiles(data, np.array([0]), np.array([len(frames)]), tiles, np.array([44100], dtype=np.uint32),
+                          np.array([[mn, mx]]), 32767.0, out, 16, bs, fused=True)
+    assert list(st[:3]) == [0, 0, 0] and st[4] == 0, st
+    want = no.denormalize_from_audio(x.astype(np.int16), mn, mx, "int16", 32767.0).reshape(8, 1149)
+    assert np.array_equal(out.cpu().numpy()[0], want)
+
+
+def test_decode_handcrafted_multichannel_skim_paths(nat, oracle):
+    """Three-channel frames whose FIRST subframes hold what the skim walk has to step over without decoding it: escape-coded
+    partitions (raw words), Rice2 parameters, LPC order 32 warm-up and coefficient blocks, partition order 5."""
+    import flac_handcraft as hc
+    from flac_raster_b200 import flacfmt
+    rng = np.random.default_rng(8)
+    n_total, bs = 4096 * 3, 4096
+    t = np.arange(n_total)
+    x = np.stack([(7000 * np.sin(t / (23.0 + 9 * c)) + rng.integers(-60, 60, size=n_total)).astype(np.int64) for c in range(3)], axis=1)
+    x[5000:5200, 1] = rng.integers(-30000, 30000, size=200)          # a burst: long codes in one partition
+    frames = b""
+    for f, a in enumerate(range(0, n_total, bs)):
+        subs = []
+        for c in range(3):
+            order = [[32, 4, 8], [13, 20, 2], [8, 8, 31]][f][c]
+            coefs = rng.integers(-200, 200, size=order); coefs[0] = 1800; 
+            if order > 1: coefs[1] = -800
+            subs.append(dict(order=order, coefs=coefs, shift=10, precision=12, partition_order=[5, 2, 0][c],
+                             rice2=(c == 1), escape_partitions=((0, 3) if (c + f) % 2 == 0 and c < 2 else ())))
+        frames += hc.frame(x[a:a + bs], 16, 9, f, bs, oracle.crc8, oracle.crc16, subs=subs)
+    si = flacfmt.StreamInfo(bs, bs, 0, 0, 44100, 3, 16, n_total)
+    ref, _ = oracle.decode(flacfmt.build_header(si) + frames)
+    assert np.array_equal(ref, x)
+    got = nat.host_decode(frames, 3, 16, bs, 44100, n_total)
+    assert np.array_equal(got, x)
+
+
 def test_decode_fuzzed_multichannel_streams_fail_cleanly(nat, oracle):
     """Random single-byte damage anywhere in an 8-channel stream (frame headers, subframe headers, Rice data, CRC bytes):
     the fused skim + decode launch must come back promptly with CRC / malformed-stream status -- never hang on an offset
