@@ -889,16 +889,19 @@ __global__ void k_set_out_offsets(EncStreamDev *streams, const unsigned long lon
 // v1 stored single bytes and ran a byte-serial CRC per thread: 13.8 ms on C3 (profiles/r01_launches_c3_v1.csv).
 constexpr int kEmitThreads = 128;
 
-struct EmitShared {
-    CrcTables T;
+struct EmitGroup {                           // state of the frame a thread group (a CTA or a warp) is assembling
     uint32_t hdr[6];
     uint32_t seg_start[FRB_MAX_CHANNELS + 2];
     uint32_t slot_of[FRB_MAX_CHANNELS];      // slot (virtual channel) that holds subframe c of this frame
+};
+struct EmitShared {
+    CrcTables T;
+    EmitGroup g[kEmitThreads / 32];
     uint32_t red[kEmitThreads / 32];
 };
 
 // 32 bits of the frame bitstream starting at bit position P (P + 32 may run past the end: zero padded)
-__device__ __forceinline__ uint32_t emit_gather32(uint32_t P, const EmitShared &S, uint32_t channels, uint32_t hdr_bits,
+__device__ __forceinline__ uint32_t emit_gather32(uint32_t P, const EmitGroup &S, uint32_t channels, uint32_t hdr_bits,
                                                   uint32_t end_bits, const uint32_t *__restrict__ slots_f, uint32_t slot_words) {
     uint32_t need = 32, val = 0;
     while (need) {
@@ -924,18 +927,25 @@ __device__ __forceinline__ uint32_t emit_gather32(uint32_t P, const EmitShared &
     return val;
 }
 
+// TPF = threads per frame: 128 (the whole CTA; large multi-channel frames) or 32 (a warp per frame, no CTA barriers:
+// small frames, where the per-frame barriers and the serial header dominated -- C5's 6 KB frames took 2.16 ms).
+template <int TPF>
 __global__ void __launch_bounds__(kEmitThreads)
 k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint32_t channels, uint32_t bps_stream,
               uint32_t blocksize, uint32_t total_frames, const uint32_t *__restrict__ sub_bits,
               const uint32_t *__restrict__ slots, uint32_t slot_words, const uint32_t *__restrict__ frame_bytes,
               const unsigned long long *__restrict__ frame_off, uint8_t *__restrict__ out, uint64_t out_capacity,
               uint32_t *__restrict__ err_flag, uint32_t vch, const uint8_t *__restrict__ frame_sel) {
-    __shared__ __align__(16) EmitShared S;
-    const int tid = threadIdx.x;
-    crc_tables_to_smem(&S.T);
-    // persistent CTAs: the CRC tables (8 KB) are staged once, then the CTA walks frames with stride gridDim.x
-    for (uint32_t f = blockIdx.x; f < total_frames; f += gridDim.x) {
-    __syncthreads();                                      // tables staged / previous frame's shared state consumed
+    __shared__ __align__(16) EmitShared SS;
+    constexpr int kGroups = kEmitThreads / TPF;
+    const int tid = threadIdx.x % TPF, grp = threadIdx.x / TPF;
+    EmitGroup &S = SS.g[grp];
+    auto group_sync = [&]() { if (TPF == kEmitThreads) __syncthreads(); else __syncwarp(); };
+    crc_tables_to_smem(&SS.T);
+    __syncthreads();                                      // tables staged
+    // persistent CTAs: the CRC tables (8 KB) are staged once, then every group walks frames with stride gridDim.x * kGroups
+    for (uint32_t f = blockIdx.x * kGroups + grp; f < total_frames; f += gridDim.x * kGroups) {
+    group_sync();                                         // previous frame's shared state consumed
     uint32_t lo = 0, hi = n_streams - 1;
     while (lo < hi) {
         uint32_t mid = (lo + hi + 1) >> 1;
@@ -985,7 +995,7 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
         }
         if (((pos + 7) >> 3) + 2 != total || dst_off + total > out_capacity) atomicExch(err_flag, 1u);
     }
-    __syncthreads();
+    group_sync();
     if (dst_off + total > out_capacity) continue;
     const uint32_t payload = total - 2;                        // bytes covered by the CRC-16
     const uint32_t hdr_bits = S.seg_start[0], end_bits = S.seg_start[channels];
@@ -995,8 +1005,9 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
     uint8_t *g0 = dst - a;
     const uint32_t span = a + payload;
     const uint32_t nfull = span >> 4, tl = span & 15;
-    const uint32_t rows = nfull / kEmitThreads, rem = nfull % kEmitThreads;
-    const CrcTables &T = S.T;
+    const uint32_t rows = nfull / TPF, rem = nfull % TPF;
+    const CrcTables &T = SS.T;
+    const uint16_t *kskip = TPF == kEmitThreads ? T.k2032 : T.k496;      // x^(8 * 16 * (TPF - 1)): skip the other threads' chunks
 
     // A thread visits its chunks in increasing order, so the subframe that holds a chunk only moves forward: the
     // segment search resumes where the previous chunk left it (it restarted from 0 for every chunk: 19 % of the kernel's
@@ -1037,17 +1048,17 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
     uint32_t acc = 0;
     for (uint32_t m = 0; m < rows; m++) {
         uint32_t w[4];
-        do_chunk(m * kEmitThreads + tid, w, 16);
-        acc = (uint32_t)T.k2032[acc >> 8] ^ T.k2032[256 + (acc & 0xFF)];
+        do_chunk(m * TPF + tid, w, 16);
+        acc = (uint32_t)kskip[acc >> 8] ^ kskip[256 + (acc & 0xFF)];
         acc = crc16_words4(acc, w, T.s4);
     }
-    uint32_t v = gf16_mul(gf16_mul(acc, T.xp[16 * (kEmitThreads - 1 - tid)]), T.xp[16 * rem + tl]);
+    uint32_t v = gf16_mul(gf16_mul(acc, T.xp[16 * (TPF - 1 - tid)]), T.xp[16 * rem + tl]);
     if ((uint32_t)tid < rem) {
         uint32_t w[4];
-        do_chunk(rows * kEmitThreads + tid, w, 16);
+        do_chunk(rows * TPF + tid, w, 16);
         v ^= gf16_mul(crc16_words4(0, w, T.s4), T.xp[16 * (rem - 1 - tid) + tl]);
     }
-    if (tid == kEmitThreads - 1 && tl) {
+    if (tid == TPF - 1 && tl) {
         uint32_t w[4];
         do_chunk(nfull, w, tl);
         uint32_t c = 0;
@@ -1059,13 +1070,18 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    if ((tid & 31) == 0) S.red[tid >> 5] = v;
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t crc = 0;
-        for (int w = 0; w < kEmitThreads / 32; w++) crc ^= S.red[w];
-        dst[payload] = (uint8_t)(crc >> 8);
-        dst[payload + 1] = (uint8_t)crc;
+    if (TPF == kEmitThreads) {
+        if ((tid & 31) == 0) SS.red[tid >> 5] = v;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t crc = 0;
+            for (int w = 0; w < kEmitThreads / 32; w++) crc ^= SS.red[w];
+            dst[payload] = (uint8_t)(crc >> 8);
+            dst[payload + 1] = (uint8_t)crc;
+        }
+    } else if (tid == 0) {
+        dst[payload] = (uint8_t)(v >> 8);
+        dst[payload + 1] = (uint8_t)v;
     }
     }
 }
@@ -1324,10 +1340,24 @@ extern "C" int frb_encode_emit(const frb_encode_params *p, void *d_workspace, si
     k_set_out_offsets<<<(p->n_streams + 255) / 256, 256, 0, s>>>(w.streams, w.out_offs, p->n_streams);
     FRB_LAUNCH_CHECK("k_set_out_offsets");
     prof_begin(2, s);
-    k_emit_frames<<<(uint32_t)std::min<uint64_t>(frames, (uint64_t)kNumSMs * 16), kEmitThreads, 0, s>>>(w.streams, p->n_streams, p->channels, p->bps, p->blocksize,
-                                                           (uint32_t)frames, w.sub_bits, w.slots, slot_words_for(p->blocksize, enc_slot_bps(p)),
-                                                           w.frame_bytes, w.frame_off, d_out, (uint64_t)out_capacity, w.err_flag,
-                                                           enc_mid_side(p) ? 4u : p->channels, enc_mid_side(p) ? w.frame_sel : nullptr);
+    {
+        // a warp per frame when frames are small (their raw size bounds the coded size), the whole CTA otherwise
+        static int tpf_cfg = -1;
+        if (tpf_cfg < 0) { const char *e = getenv("FRB_EMIT_TPF"); tpf_cfg = e ? atoi(e) : 0; }
+        const uint64_t raw_frame_bytes = (uint64_t)p->channels * p->blocksize * p->bps / 8;
+        const bool warp_per_frame = tpf_cfg == 32 || (tpf_cfg != 128 && raw_frame_bytes <= 16384);
+        const uint32_t vch = enc_mid_side(p) ? 4u : p->channels;
+        const uint8_t *sel = enc_mid_side(p) ? w.frame_sel : nullptr;
+        const uint32_t sw = slot_words_for(p->blocksize, enc_slot_bps(p));
+        if (warp_per_frame)
+            k_emit_frames<32><<<(uint32_t)std::min<uint64_t>((frames + 3) / 4, (uint64_t)kNumSMs * 16), kEmitThreads, 0, s>>>(
+                w.streams, p->n_streams, p->channels, p->bps, p->blocksize, (uint32_t)frames, w.sub_bits, w.slots, sw,
+                w.frame_bytes, w.frame_off, d_out, (uint64_t)out_capacity, w.err_flag, vch, sel);
+        else
+            k_emit_frames<kEmitThreads><<<(uint32_t)std::min<uint64_t>(frames, (uint64_t)kNumSMs * 16), kEmitThreads, 0, s>>>(
+                w.streams, p->n_streams, p->channels, p->bps, p->blocksize, (uint32_t)frames, w.sub_bits, w.slots, sw,
+                w.frame_bytes, w.frame_off, d_out, (uint64_t)out_capacity, w.err_flag, vch, sel);
+    }
     prof_end(2, s);
     FRB_LAUNCH_CHECK("k_emit_frames");
     if (d_frame_bytes)
