@@ -403,13 +403,35 @@ def main():
     barrier()
     e2e_ms = max(ev4.elapsed_time(ev5), (time.perf_counter() - t0) * 1e3) / e2e_steps
 
+    # ---- decode e2e: host (pinned) frames in, host raster out ---------------------------------------
+    host_payload = torch.empty(comp_bytes, dtype=torch.uint8).pin_memory()
+    host_payload.copy_(enc.payload[:comp_bytes])
+    host_back = torch.empty(raster.numel() * raster.element_size(), dtype=torch.uint8).pin_memory().view(raster.dtype).reshape(raster.shape)
+
+    def dec_e2e_step():
+        return eng.decode_tiles_host(host_payload, enc.offsets, enc.sizes, tiles, enc.sample_rates, enc.minmax, scale, host_back,
+                                     enc.bps, enc.blocksize)
+
+    dec_e2e_ms = None
+    if nb != 2:
+        for _ in range(min(args.warmup, 2)):
+            dec_e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            dst_ = dec_e2e_step()
+        torch.cuda.synchronize()
+        dec_e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        assert list(dst_[:3]) == [0, 0, 0], dst_
+        barrier()
+
     # ---- reduce over ranks (max time) -------------------------------------------------------------
-    t = torch.tensor([enc_ms, dec_ms, e2e_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([enc_ms, dec_ms, e2e_ms, dec_e2e_ms or 0.0], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(samples_local), float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    enc_ms, dec_ms, e2e_ms = (float(v) for v in t.cpu())
+    enc_ms, dec_ms, e2e_ms, dec_e2e_ms = (float(v) for v in t.cpu())
     total_samples = float(tot[0])
     if rank != 0:
         if world > 1:
@@ -468,6 +490,9 @@ def main():
         "lossless_roundtrip_checked": lossless,
         "decode": {"value": total_samples / (dec_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": dec_ms,
                    "gpu_launches": int(dec_launches),
+                   "e2e": ({"value": total_samples / (dec_e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": dec_e2e_ms,
+                            "h2d_bytes_per_step": comp_bytes, "d2h_bytes_per_step": int(raster.numel() * raster.element_size())}
+                           if dec_e2e_ms else None),
                    "kernels_ms": mean_ms(dec_prof),
                    "roofline": roof(dec_prof.get("k_decode_subframes"), dec_alg, "k_decode_subframes",
                                     ("compressed bytes read + raster pixels written by the fused skim + Rice decode + predictor restore + "

@@ -375,6 +375,79 @@ class Engine:
                     break
         return status
 
+    def decode_tiles_host(self, host_payload: torch.Tensor, byte_offsets: np.ndarray, byte_lengths: np.ndarray, tiles: np.ndarray,
+                          sample_rates: np.ndarray, minmax: np.ndarray, scale: float, host_out: torch.Tensor, bps: int,
+                          blocksize: int = 4096, group_bytes: Optional[int] = None) -> np.ndarray:
+        """Host frames in, host (bands,H,W) raster out: the end-to-end form of decode_tiles and the mirror of
+        encode_tiles_host.  Tile rows are pipelined over three streams: H2D of the frames of rows g+1 (double-buffered),
+        the fused decode of rows g into a device slab, D2H of the pixels of rows g-1.  `host_payload` (uint8, the tiles'
+        frames in row-major tile order) and `host_out` should be pinned.  Returns the summed status words."""
+        assert not host_out.is_cuda and host_out.is_contiguous() and host_out.dim() == 3 and not host_payload.is_cuda
+        bands, H, W = host_out.shape
+        esize = host_out.element_size()
+        total_bytes = int(host_out.numel()) * esize
+        groups = self._row_groups(tiles, bands * W * esize, group_bytes if group_bytes is not None else max(total_bytes // 12, 32 << 20))
+        max_rows = max(r1 - r0 for _, _, r0, r1 in groups)
+        byte_offsets = np.asarray(byte_offsets, dtype=np.int64)
+        byte_lengths = np.asarray(byte_lengths, dtype=np.int64)
+        spans = [(int(byte_offsets[i0]), int(byte_offsets[i1 - 1] + byte_lengths[i1 - 1])) for i0, i1, _, _ in groups]
+        max_span = max(b - a for a, b in spans)
+        status = np.zeros(8, dtype=np.int64)
+        with torch.cuda.device(self.device):
+            if not hasattr(self, "_streams"):
+                self._streams = (torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream())
+            s_h2d, s_comp, s_d2h = self._streams
+            entry = torch.cuda.current_stream()
+            for st in self._streams:
+                st.wait_stream(entry)
+            frames_dev = [self._buf(f"dec_frames{k}", max_span + 64 + 16) for k in range(2)]
+            slabs = [self._buf(f"dec_slab{k}", bands * max_rows * W * esize) for k in range(2)]
+            ev_h2d: List[torch.cuda.Event] = []
+            ev_comp: List[torch.cuda.Event] = []
+            ev_d2h: List[torch.cuda.Event] = []
+
+            def enqueue_h2d(g):
+                a, b = spans[g]
+                with torch.cuda.stream(s_h2d):
+                    if g >= 2:
+                        s_h2d.wait_event(ev_comp[g - 2])          # frames buffer g%2 has been decoded
+                    buf = frames_dev[g % 2]
+                    buf[:b - a].copy_(host_payload[a:b], non_blocking=True)
+                    buf[b - a:b - a + 64].zero_()                  # readable slack behind the last frame
+                    e = torch.cuda.Event()
+                    e.record(s_h2d)
+                    ev_h2d.append(e)
+
+            enqueue_h2d(0)
+            for g, (i0, i1, r0, r1) in enumerate(groups):
+                if g + 1 < len(groups):
+                    enqueue_h2d(g + 1)
+                local = tiles[i0:i1].copy()
+                local["row_off"] -= r0
+                slab = slabs[g % 2][: bands * (r1 - r0) * W * esize].view(host_out.dtype).reshape(bands, r1 - r0, W)
+                with torch.cuda.stream(s_comp):
+                    s_comp.wait_event(ev_h2d[g])
+                    if g >= 2:
+                        s_comp.wait_event(ev_d2h[g - 2])          # slab g%2 has left the device
+                    a, b = spans[g]
+                    st = self.decode_tiles(frames_dev[g % 2][:b - a + 64], byte_offsets[i0:i1] - a, byte_lengths[i0:i1], local,
+                                           sample_rates[i0:i1], minmax[i0:i1], scale, slab, bps, blocksize)
+                    status += st
+                    e = torch.cuda.Event()
+                    e.record(s_comp)
+                    ev_comp.append(e)
+                with torch.cuda.stream(s_d2h):
+                    s_d2h.wait_event(ev_comp[g])
+                    for b_ in range(bands):
+                        host_out[b_, r0:r1].copy_(slab[b_], non_blocking=True)
+                    e = torch.cuda.Event()
+                    e.record(s_d2h)
+                    ev_d2h.append(e)
+            for st_ in self._streams:
+                entry.wait_stream(st_)
+            s_d2h.synchronize()
+        return status
+
     def denormalize_tiles(self, audio: torch.Tensor, audio_base: np.ndarray, tiles: np.ndarray, minmax: np.ndarray,
                           scale: float, out: torch.Tensor, sync: bool = True):
         """int32 planar audio -> windows of the (bands,H,W) device raster `out` (denormalize_from_audio, int path)."""

@@ -608,6 +608,26 @@ def test_host_pipeline_equals_device_path(nat, torch_cuda):
         assert np.array_equal(got.payload.numpy(), ref_bytes)
 
 
+def test_host_decode_pipeline_equals_raster(nat, torch_cuda):
+    """decode_tiles_host (frames of tile rows pipelined over copy/decode/copy streams, host buffers) reproduces the raster,
+    ragged edge tiles included, whatever the stage size."""
+    torch = torch_cuda
+    from flac_raster_b200.engine import default_engine, tile_grid
+    from flac_raster_b200.synth import sentinel2_like
+    raster = sentinel2_like(1500, 1300, 3)
+    eng = default_engine()
+    tiles = tile_grid(1500, 1300, 512)
+    enc = eng.encode_tiles(raster, tiles, 5)
+    host_payload = enc.payload.cpu().pin_memory()
+    want = raster.cpu()
+    for gb in (0, 0, None):
+        out = torch.zeros(raster.shape, dtype=raster.dtype).pin_memory()
+        st = eng.decode_tiles_host(host_payload, enc.offsets, enc.sizes, tiles, enc.sample_rates, enc.minmax, 32767.0, out, enc.bps,
+                                   group_bytes=gb)
+        assert list(st[:3]) == [0, 0, 0] and st[3] == int(((enc.n_samples + 4095) // 4096).sum()), st
+        assert torch.equal(out.view(torch.int16), want.view(torch.int16))
+
+
 @pytest.mark.parametrize("dt", ["uint8", "int16", "uint16", "float32", "float64", "int32"])
 def test_tile_mapping_odd_alignment_vs_oracle(nat, torch_cuda, dt):
     """Per-tile min/max, normalise and denormalise on windows whose rows start at odd element offsets and
