@@ -77,7 +77,7 @@ _lib = None
 
 _EXPORTS = [
     "frb_version", "frb_error_string", "frb_last_cuda_error", "frb_device_count", "frb_launch_count",
-    "frb_profile_enable", "frb_profile_last_ms",
+    "frb_profile_enable", "frb_profile_last_ms", "frb_small_upload", "frb_small_download",
     "frb_minmax_tiles", "frb_normalize_tiles", "frb_denormalize_tiles", "frb_sample_map_workspace_size",
     "frb_minmax_flat", "frb_normalize_flat", "frb_denormalize_flat", "frb_selftest_division",
     "frb_encode_workspace_size", "frb_encode_analyse", "frb_encode_emit",
@@ -127,6 +127,8 @@ def lib():
     L.frb_decode_workspace_size.argtypes = [C.POINTER(DecodeParams), u64, C.POINTER(sz)]
     L.frb_decode_batch.argtypes = [C.POINTER(DecodeParams), vp, vp, u64, vp, vp, sz, vp, vp]
     L.frb_decode_tiles.argtypes = [C.POINTER(DecodeParams), vp, vp, u64, vp, vp, C.c_double, vp, C.c_int, u32, u32, u32, vp, sz, vp, vp]
+    L.frb_small_upload.argtypes = [vp, vp, sz, vp]
+    L.frb_small_download.argtypes = [vp, vp, sz, vp]
     L.frb_probe_stream.argtypes = [vp, u64, u64, u32, u32, u32, u32, C.POINTER(u64), C.POINTER(u64), vp]
     L.frb_host_encode.argtypes = [vp, u64, u32, u32, u32, u32, u32, u64, vp, sz, C.POINTER(sz), vp, sz, C.POINTER(sz)]
     L.frb_host_decode.argtypes = [vp, sz, u32, u32, u32, u32, u64, vp, sz, C.POINTER(u64)]

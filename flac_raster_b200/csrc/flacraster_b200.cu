@@ -83,6 +83,16 @@ extern "C" int frb_device_count(int *count) {
 }
 extern "C" uint64_t frb_launch_count(void) { return frb::g_launches.load(); }
 
+// Small transfers through pinned staging + a copy kernel (see frb_common.cuh: they must not queue behind bulk DMA).
+extern "C" int frb_small_upload(void *d_dst, const void *h_src, size_t bytes, void *stream) {
+    if (!d_dst || !h_src) return FRB_ERR_INVALID_ARG;
+    return frb::small_upload(d_dst, h_src, bytes, (cudaStream_t)stream);
+}
+extern "C" int frb_small_download(void *h_dst, const void *d_src, size_t bytes, void *stream) {
+    if (!h_dst || !d_src) return FRB_ERR_INVALID_ARG;
+    return frb::small_download(h_dst, d_src, bytes, (cudaStream_t)stream);
+}
+
 extern "C" int frb_profile_enable(int on) { frb::g_prof_on = on != 0; return FRB_OK; }
 extern "C" int frb_profile_last_ms(int which, float *ms) {
     if (which < 0 || which > 7 || !ms) return FRB_ERR_INVALID_ARG;

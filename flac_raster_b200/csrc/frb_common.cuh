@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <atomic>
+#include <string.h>
 #include "../../include/flacraster_b200.h"
 
 namespace frb {
@@ -40,6 +41,82 @@ inline bool first_call_on_device(bool (&done)[64]) {
     done[dev] = true;
     return true;
 }
+
+// ---- small host <-> device transfers that stay off the copy engines -----------------------------------------------
+// A bulk cudaMemcpyAsync in flight (the tile pipeline moves ~100-200 MB per stage and direction) occupies a DMA engine
+// for milliseconds, and every small copy enqueued after it -- a 2 KB stream table, an 8-byte size read-back -- queues
+// behind it: tools/e2e_timeline.py showed each stage's encode starting exactly when the previous stage's 130 MB
+// device-to-host copy ended, i.e. copy and compute serialised (49 ms per C3 step against a 42 ms PCIe bound).  Small
+// transfers therefore go through pinned (UVA-mapped) host memory and a copy KERNEL: SM loads/stores over PCIe, no DMA
+// queue.  Memsets of small device ranges use a fill kernel for the same reason.
+__global__ void k_copy_small(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, size_t bytes) {
+    const size_t words = bytes >> 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+    if (blockIdx.x == 0 && threadIdx.x < (bytes & 3)) ((uint8_t *)dst)[(words << 2) + threadIdx.x] = ((const uint8_t *)src)[(words << 2) + threadIdx.x];
+}
+__global__ void k_fill_small(uint32_t *__restrict__ dst, uint32_t v, size_t words) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) dst[i] = v;
+}
+struct Mailbox {                       // per host thread: a ring of pinned memory; a slot lives until the ring wraps (8 MiB later)
+    uint8_t *base = nullptr;
+    size_t cap = 0, pos = 0;
+    uint8_t *take(size_t bytes) {
+        if (!base) {
+            if (cudaMallocHost((void **)&base, kCap) != cudaSuccess) { base = nullptr; cudaGetLastError(); return nullptr; }
+            cap = kCap;
+        }
+        bytes = (bytes + 63) & ~(size_t)63;
+        if (bytes > cap / 4) return nullptr;               // not "small": the caller uses the DMA path
+        if (pos + bytes > cap) pos = 0;
+        uint8_t *p = base + pos;
+        pos += bytes;
+        return p;
+    }
+    static constexpr size_t kCap = 8u << 20;
+};
+static thread_local Mailbox t_mailbox;
+static inline uint32_t small_grid(size_t bytes) { size_t g = (bytes / 4 + 255) / 256; return (uint32_t)(g < 1 ? 1 : g > 256 ? 256 : g); }
+
+// host -> device, asynchronous on `s` (the source may be reused as soon as the call returns)
+inline int small_upload(void *d_dst, const void *h_src, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) return FRB_OK;
+    uint8_t *slot = ((reinterpret_cast<uintptr_t>(d_dst) & 3u) == 0) ? t_mailbox.take(bytes) : nullptr;
+    if (!slot) {
+        cudaError_t e = cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, s);
+        return e == cudaSuccess ? FRB_OK : cuda_fail(e, "cudaMemcpyAsync(H2D)");
+    }
+    memcpy(slot, h_src, bytes);
+    k_copy_small<<<small_grid(bytes), 256, 0, s>>>((uint32_t *)d_dst, (const uint32_t *)slot, bytes);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? FRB_OK : cuda_fail(e, "k_copy_small");
+}
+// device -> host; returns after the stream has been synchronised and h_dst holds the data
+inline int small_download(void *h_dst, const void *d_src, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) return FRB_OK;
+    uint8_t *slot = ((reinterpret_cast<uintptr_t>(d_src) & 3u) == 0) ? t_mailbox.take(bytes) : nullptr;
+    cudaError_t e;
+    if (!slot) {
+        e = cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        return e == cudaSuccess ? FRB_OK : cuda_fail(e, "cudaMemcpyAsync(D2H)");
+    }
+    k_copy_small<<<small_grid(bytes), 256, 0, s>>>((uint32_t *)slot, (const uint32_t *)d_src, bytes);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return cuda_fail(e, "k_copy_small");
+    memcpy(h_dst, slot, bytes);
+    return FRB_OK;
+}
+inline int small_fill(void *d_dst, uint32_t word, size_t bytes, cudaStream_t s) {        // bytes and d_dst: multiples of 4
+    if (bytes == 0) return FRB_OK;
+    k_fill_small<<<small_grid(bytes), 256, 0, s>>>((uint32_t *)d_dst, word, bytes >> 2);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? FRB_OK : cuda_fail(e, "k_fill_small");
+}
+#define FRB_TRY(call) do { int rc__ = (call); if (rc__ != FRB_OK) return rc__; } while (0)
 
 // ---- optional kernel timing (bench roofline) ---------------------------------
 struct ProfSlot { cudaEvent_t a = nullptr, b = nullptr; bool valid = false; };

@@ -233,10 +233,9 @@ static int decode_batch_impl(const frb_decode_params *p, const frb_decode_stream
         hs[i] = d;
     }
     if (frames != total_frames) return FRB_ERR_INVALID_ARG;
-    FRB_CUDA(cudaMemcpyAsync(w.streams, hs.data(), sizeof(DecStreamDev) * hs.size(), cudaMemcpyHostToDevice, s));
-    FRB_CUDA(cudaStreamSynchronize(s));   // hs is a stack-local staging vector
-    FRB_CUDA(cudaMemsetAsync(d_status, 0, 8 * sizeof(uint32_t), s));
-    FRB_CUDA(cudaMemsetAsync(w.chassign, 0, (size_t)total_frames + 1, s));
+    FRB_TRY(small_upload(w.streams, hs.data(), sizeof(DecStreamDev) * hs.size(), s));   // staged in pinned memory before returning
+    FRB_TRY(small_fill(d_status, 0u, 8 * sizeof(uint32_t), s));
+    FRB_TRY(small_fill(w.chassign, 0u, ((size_t)total_frames + 1 + 3) & ~(size_t)3, s));
     k_fill_u64<<<grid_for(total_frames + 1, 256 * 4, kNumSMs * 4), 256, 0, s>>>(w.frame_pos, total_frames + 1, kNoPos);
     FRB_LAUNCH_CHECK("k_fill_u64");
     {
@@ -288,7 +287,7 @@ static int decode_batch_impl(const frb_decode_params *p, const frb_decode_stream
             const uint32_t frames_per_cta = (kDecThreads / 32) * skim_lanes;
             n_skim_ctas = (uint32_t)((total_frames + frames_per_cta - 1) / frames_per_cta);
             sub_bitoff = w.sub_bitoff;
-            FRB_CUDA(cudaMemsetAsync(sub_bitoff, 0xFF, 4 * (size_t)(total_frames * p->channels), s));
+            FRB_TRY(small_fill(sub_bitoff, 0xFFFFFFFFu, 4 * (size_t)(total_frames * p->channels), s));
         }
         const uint64_t total_sub = total_frames * p->channels;
         const uint32_t grid = n_skim_ctas + (uint32_t)((total_sub + kDecThreads - 1) / kDecThreads);

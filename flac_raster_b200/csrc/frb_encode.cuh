@@ -1206,12 +1206,12 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const int32_t *d_a
         uint64_t cum = 0;
         for (uint32_t i = 0; i < p->n_streams; i++) { vhs[i].audio_base = (int64_t)(4 * cum); cum += hs[i].n_samples; }
         if (cum > frames * (uint64_t)p->blocksize) return FRB_ERR_INVALID_ARG;
-        FRB_CUDA(cudaMemcpyAsync(w.vstreams, vhs.data(), sizeof(EncStreamDev) * vhs.size(), cudaMemcpyHostToDevice, s));
+        FRB_TRY(small_upload(w.vstreams, vhs.data(), sizeof(EncStreamDev) * vhs.size(), s));
     }
-    FRB_CUDA(cudaMemcpyAsync(w.streams, hs.data(), sizeof(EncStreamDev) * hs.size(), cudaMemcpyHostToDevice, s));
-    FRB_CUDA(cudaMemcpyAsync(w.window, win.data(), sizeof(float) * FRB_MAX_BLOCKSIZE, cudaMemcpyHostToDevice, s));
-    FRB_CUDA(cudaMemsetAsync(w.err_flag, 0, 256, s));
-    FRB_CUDA(cudaStreamSynchronize(s));       // staging vectors are locals
+    FRB_TRY(small_upload(w.streams, hs.data(), sizeof(EncStreamDev) * hs.size(), s));
+    FRB_TRY(small_upload(w.window, win.data(), sizeof(float) * FRB_MAX_BLOCKSIZE, s));
+    FRB_TRY(small_fill(w.err_flag, 0u, 256, s));
+    // (small_upload copies its source into pinned staging before it returns: no synchronisation needed here)
     const std::vector<EncStreamDev> &ahs = ms ? vhs : hs;
     const EncStreamDev *an_streams = ms ? w.vstreams : w.streams;
     const int32_t *an_audio = ms ? w.vaudio : d_audio;
@@ -1248,8 +1248,11 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const int32_t *d_a
             }
         }
         if (!slow.empty()) {
-            FRB_CUDA(cudaMemcpyAsync(w.slow_tasks, slow.data(), 4 * slow.size(), cudaMemcpyHostToDevice, s));
-            FRB_CUDA(cudaStreamSynchronize(s));
+            if (4 * slow.size() <= (1u << 20)) FRB_TRY(small_upload(w.slow_tasks, slow.data(), 4 * slow.size(), s));
+            else {
+                FRB_CUDA(cudaMemcpyAsync(w.slow_tasks, slow.data(), 4 * slow.size(), cudaMemcpyHostToDevice, s));
+                FRB_CUDA(cudaStreamSynchronize(s));
+            }
         }
     }
     prof_begin(6, s);
@@ -1315,8 +1318,7 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const int32_t *d_a
     if (d_stream_bytes)
         FRB_CUDA(cudaMemcpyAsync(d_stream_bytes, w.stream_bytes, 8 * (size_t)p->n_streams, cudaMemcpyDeviceToDevice, s));
     if (h_stream_bytes) {
-        FRB_CUDA(cudaMemcpyAsync(h_stream_bytes, w.stream_bytes, 8 * (size_t)p->n_streams, cudaMemcpyDeviceToHost, s));
-        FRB_CUDA(cudaStreamSynchronize(s));
+        FRB_TRY(small_download(h_stream_bytes, w.stream_bytes, 8 * (size_t)p->n_streams, s));
     }
     return FRB_OK;
 }
@@ -1331,12 +1333,11 @@ extern "C" int frb_encode_emit(const frb_encode_params *p, void *d_workspace, si
     EncWorkspace w0;
     (void)enc_ws_layout(p, 0, d_workspace, &w0);
     EncStreamDev last;
-    FRB_CUDA(cudaMemcpyAsync(&last, w0.streams + (p->n_streams - 1), sizeof last, cudaMemcpyDeviceToHost, s));
-    FRB_CUDA(cudaStreamSynchronize(s));
+    FRB_TRY(small_download(&last, w0.streams + (p->n_streams - 1), sizeof last, s));
     const uint64_t frames = (uint64_t)last.frame_base + last.n_frames;
     EncWorkspace w;
     if (enc_ws_layout(p, frames, d_workspace, &w) > workspace_bytes) return FRB_ERR_OVERFLOW;
-    FRB_CUDA(cudaMemcpyAsync(w.out_offs, h_out_offset, 8 * (size_t)p->n_streams, cudaMemcpyHostToDevice, s));
+    FRB_TRY(small_upload(w.out_offs, h_out_offset, 8 * (size_t)p->n_streams, s));
     k_set_out_offsets<<<(p->n_streams + 255) / 256, 256, 0, s>>>(w.streams, w.out_offs, p->n_streams);
     FRB_LAUNCH_CHECK("k_set_out_offsets");
     prof_begin(2, s);
@@ -1363,8 +1364,7 @@ extern "C" int frb_encode_emit(const frb_encode_params *p, void *d_workspace, si
     if (d_frame_bytes)
         FRB_CUDA(cudaMemcpyAsync(d_frame_bytes, w.frame_bytes, 4 * (size_t)frames, cudaMemcpyDeviceToDevice, s));
     uint32_t h_err = 0;
-    FRB_CUDA(cudaMemcpyAsync(&h_err, w.err_flag, 4, cudaMemcpyDeviceToHost, s));
-    FRB_CUDA(cudaStreamSynchronize(s));
+    FRB_TRY(small_download(&h_err, w.err_flag, 4, s));
     if (h_err) return FRB_ERR_OVERFLOW;
     return FRB_OK;
 }

@@ -92,6 +92,22 @@ class Engine:
     def release(self):
         self._ws.clear()
 
+    def _upload(self, arr: np.ndarray) -> torch.Tensor:
+        """A small host array -> a fresh device tensor (uint8 view) on the current stream, through the library's pinned
+        staging + copy kernel: torch's .to(device) is a DMA transfer and would queue behind the bulk copies of the host
+        pipelines (see frb_small_upload)."""
+        a = np.ascontiguousarray(arr)
+        nbytes = a.nbytes
+        t = torch.empty((nbytes + 15) & ~15, dtype=torch.uint8, device=self.device)
+        nat.check(self.L.frb_small_upload(t.data_ptr(), a.ctypes.data, nbytes, _stream_ptr()), "frb_small_upload")
+        return t
+
+    def _download(self, t: torch.Tensor, dtype, count: int) -> np.ndarray:
+        """A small device tensor -> numpy (synchronises the current stream), off the copy engines as well."""
+        out = np.empty(count, dtype=dtype)
+        nat.check(self.L.frb_small_download(out.ctypes.data, t.data_ptr(), out.nbytes, _stream_ptr()), "frb_small_download")
+        return out
+
     # ------------------------------------------------------------------ encode
     def normalize_tiles(self, raster: torch.Tensor, tiles: np.ndarray, bits_per_sample: Optional[int] = None):
         """(bands,H,W) device raster -> (audio int32 planar per tile, audio_base, minmax_dev)."""
@@ -108,8 +124,8 @@ class Engine:
         total = int((npx * bands).sum())
         with torch.cuda.device(self.device):
             s = _stream_ptr()
-            d_tiles = torch.from_numpy(tiles.view(np.uint8).copy()).to(self.device, non_blocking=True)
-            d_base = torch.from_numpy(base).to(self.device, non_blocking=True)
+            d_tiles = self._upload(tiles.view(np.uint8))
+            d_base = self._upload(base)
             d_minmax = torch.empty(2 * n_tiles, dtype=torch.float64, device=self.device)
             audio = self._buf("audio", total * 4)
             nat.check(self.L.frb_minmax_tiles(raster.data_ptr(), code, bands, H, W, d_tiles.data_ptr(), n_tiles,
@@ -155,7 +171,8 @@ class Engine:
         bps = 16 if bits == 16 else 32            # pyflac derives bps from the array dtype (docs/sonos-pyflac.txt:1988-1991)
         rates = sample_rates_for_pixel_counts(npx)                # one vector expression (4096 tiles: 5 ms of Python before)
         payload, offsets, sizes = self.encode_audio(audio, npx, base, rates, bands, bps, level, blocksize, payload_name)
-        minmax = d_minmax.cpu().numpy().reshape(-1, 2)
+        with torch.cuda.device(self.device):
+            minmax = self._download(d_minmax, np.float64, 2 * len(tiles)).reshape(-1, 2)
         return EncodedTiles(payload, offsets, sizes, minmax, npx, rates, bands, bps, bits, blocksize)
 
     # ------------------------------------------------------------------ encode, host buffers (pipelined)
@@ -190,7 +207,8 @@ class Engine:
         return t
 
     def encode_tiles_host(self, host_raster: torch.Tensor, tiles: np.ndarray, level: int = 5, blocksize: int = 4096,
-                          host_out: Optional[torch.Tensor] = None, group_bytes: Optional[int] = None) -> EncodedTiles:
+                          host_out: Optional[torch.Tensor] = None, group_bytes: Optional[int] = None,
+                          timeline: Optional[list] = None) -> EncodedTiles:
         """Host (bands,H,W) raster in, host frames out: the end-to-end form of encode_tiles.
 
         The reference walks tiles serially (cli.py:553-622).  Here the tile rows are pipelined over three
@@ -220,6 +238,20 @@ class Engine:
             ev_h2d: List[torch.cuda.Event] = []
             ev_comp: List[torch.cuda.Event] = []
             ev_d2h: List[torch.cuda.Event] = []
+            timed = timeline is not None          # debug: per-stage device timestamps (tools/e2e_timeline.py)
+            if timed:
+                t_origin = torch.cuda.Event(enable_timing=True)
+                t_origin.record(entry)
+                marks = []
+                host_marks = []
+                import time
+
+            def mark(stream, name, g):
+                if timed:
+                    e = torch.cuda.Event(enable_timing=True)
+                    e.record(stream)
+                    marks.append((name, g, e))
+                    host_marks.append((name, g, time.perf_counter()))
 
             def slab_view(g):
                 _, _, r0, r1 = groups[g]
@@ -231,11 +263,13 @@ class Engine:
                     if g >= 2:
                         s_h2d.wait_event(ev_comp[g - 2])          # slab g%2 is free once row g-2 has been encoded
                     dst = slab_view(g)
+                    mark(s_h2d, "h2d_begin", g)
                     for b in range(bands):                          # each band's rows are one contiguous block
                         dst[b].copy_(host_raster[b, r0:r1], non_blocking=True)
                     e = torch.cuda.Event()
                     e.record(s_h2d)
                     ev_h2d.append(e)
+                    mark(s_h2d, "h2d_end", g)
 
             parts: List[EncodedTiles] = []
             total = 0
@@ -249,25 +283,34 @@ class Engine:
                     s_comp.wait_event(ev_h2d[g])
                     if g >= 2:
                         s_comp.wait_event(ev_d2h[g - 2])          # payload g%2 has left the device
+                    mark(s_comp, "enc_begin", g)
                     enc = self.encode_tiles(slab_view(g), local, level, blocksize, payload_name=f"payload{g % 2}")
                     e = torch.cuda.Event()
                     e.record(s_comp)
                     ev_comp.append(e)
+                    mark(s_comp, "enc_end", g)
                 n = int(enc.payload.numel())
                 if total + n > host_out.numel():
                     raise nat.NativeError(nat.ERR_OVERFLOW, "encode_tiles_host", "host_out too small")
                 with torch.cuda.stream(s_d2h):
                     s_d2h.wait_event(ev_comp[g])
+                    mark(s_d2h, "d2h_begin", g)
                     host_out[total:total + n].copy_(enc.payload, non_blocking=True)
                     e = torch.cuda.Event()
                     e.record(s_d2h)
                     ev_d2h.append(e)
+                    mark(s_d2h, "d2h_end", g)
                 enc.offsets = enc.offsets + total
                 parts.append(enc)
                 total += n
             for st in self._streams:
                 entry.wait_stream(st)
             s_d2h.synchronize()
+            if timed:
+                torch.cuda.synchronize()
+                timeline.extend((name, g, t_origin.elapsed_time(e)) for name, g, e in marks)
+                h0 = host_marks[0][2]
+                timeline.extend(("host_" + name, g, (t - h0) * 1e3) for name, g, t in host_marks)
         p0 = parts[0]
         return EncodedTiles(host_out[:total], np.concatenate([p.offsets for p in parts]), np.concatenate([p.sizes for p in parts]),
                             np.concatenate([p.minmax for p in parts]), np.concatenate([p.n_samples for p in parts]),
@@ -312,7 +355,7 @@ class Engine:
                                                   ws.data_ptr(), ws.numel(), d_status.data_ptr(), s), "frb_decode_batch")
                 if not sync:
                     return audio, base, d_status
-                status = d_status.cpu().numpy().astype(np.int64)
+                status = self._download(d_status, np.int32, 8).astype(np.int64)
                 if status[4] == 0:
                     break
         return audio, base, status
@@ -355,7 +398,7 @@ class Engine:
             stage = np.zeros(n_tiles * 16 + n_tiles * 16, dtype=np.uint8)
             stage[: n_tiles * 16] = np.ascontiguousarray(tiles).view(np.uint8)
             stage[n_tiles * 16:] = np.ascontiguousarray(minmax, dtype=np.float64).reshape(-1).view(np.uint8)
-            d_stage = torch.from_numpy(stage).to(self.device, non_blocking=True)
+            d_stage = self._upload(stage)
             d_status = torch.zeros(8, dtype=torch.int32, device=self.device)
             status = None
             for max_order in (12, 32):
@@ -367,7 +410,7 @@ class Engine:
                                                   d_stage.data_ptr(), d_stage.data_ptr() + n_tiles * 16, float(scale),
                                                   out.data_ptr(), nat.DTYPE_CODES[dt], bands, H, W,
                                                   ws.data_ptr(), ws.numel(), d_status.data_ptr(), s), "frb_decode_tiles")
-                status = d_status.cpu().numpy().astype(np.int64)      # also keeps d_stage alive until the kernels are done
+                status = self._download(d_status, np.int32, 8).astype(np.int64)      # (synchronises: d_stage stays alive until the kernels are done)
                 if status[6]:
                     raise nat.NativeError(nat.ERR_INVALID_ARG, "frb_decode_tiles",
                                           f"{int(status[6])} tile(s) do not match their stream length or lie outside the raster")
@@ -455,9 +498,9 @@ class Engine:
         dt = str(out.dtype).replace("torch.", "")
         with torch.cuda.device(self.device):
             s = _stream_ptr()
-            d_tiles = torch.from_numpy(tiles.view(np.uint8).copy()).to(self.device, non_blocking=True)
-            d_base = torch.from_numpy(np.ascontiguousarray(audio_base, dtype=np.int64)).to(self.device, non_blocking=True)
-            d_mm = torch.from_numpy(np.ascontiguousarray(minmax, dtype=np.float64).reshape(-1)).to(self.device, non_blocking=True)
+            d_tiles = self._upload(tiles.view(np.uint8))
+            d_base = self._upload(np.ascontiguousarray(audio_base, dtype=np.int64))
+            d_mm = self._upload(np.ascontiguousarray(minmax, dtype=np.float64).reshape(-1))
             mws = self._map_ws(len(tiles))
             nat.check(self.L.frb_denormalize_tiles(audio.data_ptr(), d_base.data_ptr(), d_tiles.data_ptr(), len(tiles),
                                                    d_mm.data_ptr(), float(scale), out.data_ptr(), nat.DTYPE_CODES[dt],

@@ -224,6 +224,14 @@ int frb_probe_stream(const uint8_t *d_bytes, uint64_t byte_offset, uint64_t byte
                      uint32_t channels, uint32_t bps, uint32_t blocksize, uint32_t sample_rate,
                      uint64_t *n_frames, uint64_t *n_samples, void *stream);
 
+/* Small host <-> device transfers for the tables and read-backs around the batch calls (tile tables, min/max,
+ * status words).  They go through pinned staging and a copy kernel instead of cudaMemcpyAsync, so that they do not
+ * queue behind the bulk H2D/D2H transfers of a host pipeline on the copy engines.  frb_small_upload is asynchronous
+ * on `stream` (h_src may be reused on return); frb_small_download returns once h_dst holds the data (it
+ * synchronises `stream`).  Device pointers must be 4-byte aligned; above 2 MiB both fall back to cudaMemcpyAsync. */
+int frb_small_upload(void *d_dst, const void *h_src, size_t bytes, void *stream);
+int frb_small_download(void *h_dst, const void *d_src, size_t bytes, void *stream);
+
 /* ------------------------------------------------------ 5. host API
  * One-shot calls on HOST buffers (the e2e path: H2D, kernels, D2H inside).
  * frb_host_encode takes the interleaved int32 buffer pyflac passes to
