@@ -57,7 +57,7 @@ __global__ void k_copy_small(uint32_t *__restrict__ dst, const uint32_t *__restr
 __global__ void k_fill_small(uint32_t *__restrict__ dst, uint32_t v, size_t words) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) dst[i] = v;
 }
-struct Mailbox {                       // per host thread: a ring of pinned memory; a slot lives until the ring wraps (8 MiB later)
+struct Mailbox {                       // per host thread: a ring of pinned memory; a slot lives until the ring wraps (32 MiB later)
     uint8_t *base = nullptr;
     size_t cap = 0, pos = 0;
     uint8_t *take(size_t bytes) {
@@ -67,12 +67,17 @@ struct Mailbox {                       // per host thread: a ring of pinned memo
         }
         bytes = (bytes + 63) & ~(size_t)63;
         if (bytes > cap / 4) return nullptr;               // not "small": the caller uses the DMA path
-        if (pos + bytes > cap) pos = 0;
+        if (pos + bytes > cap) {
+            // wrapping onto slots whose copy kernels may, in principle, still be queued (a caller that never synchronises):
+            // drain the device once per 32 MiB of small transfers
+            cudaDeviceSynchronize();
+            pos = 0;
+        }
         uint8_t *p = base + pos;
         pos += bytes;
         return p;
     }
-    static constexpr size_t kCap = 8u << 20;
+    static constexpr size_t kCap = 32u << 20;
 };
 static thread_local Mailbox t_mailbox;
 static inline uint32_t small_grid(size_t bytes) { size_t g = (bytes / 4 + 255) / 256; return (uint32_t)(g < 1 ? 1 : g > 256 ? 256 : g); }
