@@ -1159,6 +1159,11 @@ static inline void make_tukey(float *w, int L, float p) {
 // 16-bit streams (a 32-bit stream would need a 33-bit side channel: those stay independent)
 static inline bool enc_mid_side(const frb_encode_params *p) { return p->channels == 2 && p->bps == 16 && level_cfg(p->level).mid_side; }
 
+// frb_encode_emit needs the frame count frb_encode_analyse computed; it is remembered per host thread for the usual
+// analyse -> emit sequence on one workspace (otherwise emit reads it back from the stream table: one more round trip)
+struct LastAnalyse { const void *ws = nullptr; uint64_t frames = 0; uint32_t n_streams = 0; };
+static thread_local LastAnalyse t_last_analyse;
+
 static inline bool enc_params_ok(const frb_encode_params *p) {
     return p && p->n_streams >= 1 && p->channels >= 1 && p->channels <= FRB_MAX_CHANNELS &&
            (p->bps == 16 || p->bps == 32) && p->blocksize >= 16 && p->blocksize <= FRB_MAX_BLOCKSIZE && p->level <= 8;
@@ -1321,6 +1326,7 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const int32_t *d_a
     k_frame_sizes<<<(uint32_t)((frames + 255) / 256), 256, 0, s>>>(w.streams, p->n_streams, p->channels, p->blocksize,
                                                                  (uint32_t)frames, w.sub_bits, w.frame_bytes, an_ch, ms ? w.frame_sel : nullptr);
     FRB_LAUNCH_CHECK("k_frame_sizes");
+    t_last_analyse.ws = d_workspace; t_last_analyse.frames = frames; t_last_analyse.n_streams = p->n_streams;
     k_stream_scan<<<p->n_streams, 1024, 0, s>>>(w.streams, w.frame_bytes, w.frame_off, w.stream_bytes);
     FRB_LAUNCH_CHECK("k_stream_scan");
     if (d_stream_bytes)
@@ -1340,9 +1346,13 @@ extern "C" int frb_encode_emit(const frb_encode_params *p, void *d_workspace, si
     // recover the frame count from the stream table written by analyse
     EncWorkspace w0;
     (void)enc_ws_layout(p, 0, d_workspace, &w0);
-    EncStreamDev last;
-    FRB_TRY(small_download(&last, w0.streams + (p->n_streams - 1), sizeof last, s));
-    const uint64_t frames = (uint64_t)last.frame_base + last.n_frames;
+    uint64_t frames;
+    if (t_last_analyse.ws == d_workspace && t_last_analyse.n_streams == p->n_streams && t_last_analyse.frames) frames = t_last_analyse.frames;
+    else {
+        EncStreamDev last;
+        FRB_TRY(small_download(&last, w0.streams + (p->n_streams - 1), sizeof last, s));
+        frames = (uint64_t)last.frame_base + last.n_frames;
+    }
     EncWorkspace w;
     if (enc_ws_layout(p, frames, d_workspace, &w) > workspace_bytes) return FRB_ERR_OVERFLOW;
     FRB_TRY(small_upload(w.out_offs, h_out_offset, 8 * (size_t)p->n_streams, s));
