@@ -736,6 +736,15 @@ def test_fused_integer_denormalise_is_exact_for_every_audio_value(nat, torch_cud
     pairs = [(info.min, info.max), (info.min, info.min + 1), (info.min + 3, info.min + 6), (info.max - 2, info.max),
              (info.min + 5, info.min + 5), (info.min, info.min + min(info.max - info.min, 32767)), (info.min + 1, info.max - 1),
              (info.min, info.min + 2), (info.min + 10, info.min + 10 + min(info.max - info.min - 10, 65533))]
+    prng = np.random.default_rng(17)
+    span = int(info.max) - int(info.min)
+    for _ in range(24):                                   # seeded random windows, odd ranges (exact ties) over-represented
+        r = int(prng.integers(0, min(span, 65535) + 1))
+        if prng.random() < 0.5:
+            r |= 1
+        r = min(r, span)
+        lo = int(prng.integers(int(info.min), int(info.max) - r + 1))
+        pairs.append((lo, lo + r))
     for mn, mx in pairs:
         out = torch.zeros(1, 256, 256, dtype=getattr(torch, dt), device="cuda")
         st = eng.decode_tiles(data, np.array([0]), np.array([len(payload)]), tiles, np.array([44100], dtype=np.uint32),
