@@ -87,11 +87,50 @@ _EXPORTS = [
     "frb_stream_encoder_set_bits_per_sample", "frb_stream_encoder_set_sample_rate",
     "frb_stream_encoder_set_compression_level", "frb_stream_encoder_set_blocksize",
     "frb_stream_encoder_set_total_samples_estimate", "frb_stream_encoder_init_stream",
-    "frb_stream_encoder_process_interleaved", "frb_stream_encoder_finish",
-    "frb_stream_encoder_get_state",
+    "frb_stream_encoder_process_interleaved", "frb_stream_encoder_process", "frb_stream_encoder_finish",
+    "frb_stream_encoder_get_state", "frb_stream_encoder_set_verify", "frb_stream_encoder_set_streamable_subset",
+    "frb_stream_encoder_set_limit_min_bitrate", "frb_stream_encoder_get_verify",
+    "frb_stream_decoder_new", "frb_stream_decoder_delete", "frb_stream_decoder_init_stream", "frb_stream_decoder_init_file",
+    "frb_stream_decoder_process_until_end_of_metadata", "frb_stream_decoder_process_until_end_of_stream",
+    "frb_stream_decoder_finish", "frb_stream_decoder_get_state", "frb_stream_decoder_get_channels",
+    "frb_stream_decoder_get_bits_per_sample", "frb_stream_decoder_get_sample_rate", "frb_stream_decoder_get_blocksize",
+    "frb_stream_decoder_get_total_samples",
 ]
 
+
+class StreamInfoC(C.Structure):
+    _fields_ = [("min_blocksize", C.c_uint32), ("max_blocksize", C.c_uint32), ("min_framesize", C.c_uint32),
+                ("max_framesize", C.c_uint32), ("sample_rate", C.c_uint32), ("channels", C.c_uint32),
+                ("bits_per_sample", C.c_uint32), ("total_samples", C.c_uint64), ("md5sum", C.c_uint8 * 16)]
+
+
+class StreamMetadataC(C.Structure):
+    _fields_ = [("type", C.c_int), ("is_last", C.c_int), ("length", C.c_uint32), ("stream_info", StreamInfoC)]
+
+
+class _FrameNumber(C.Union):
+    _fields_ = [("frame_number", C.c_uint32), ("sample_number", C.c_uint64)]
+
+
+class FrameHeaderC(C.Structure):
+    _fields_ = [("blocksize", C.c_uint32), ("sample_rate", C.c_uint32), ("channels", C.c_uint32),
+                ("channel_assignment", C.c_int), ("bits_per_sample", C.c_uint32), ("number_type", C.c_int),
+                ("number", _FrameNumber), ("crc", C.c_uint8)]
+
+
+class FrameC(C.Structure):
+    _fields_ = [("header", FrameHeaderC)]
+
+
+# callback types of the handle API (include/flacraster_b200.h section 6)
 WRITE_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint8), C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p)
+ENC_SEEK_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_void_p)
+ENC_TELL_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p)
+ENC_METADATA_CB = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(StreamMetadataC), C.c_void_p)
+DEC_WRITE_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(FrameC), C.POINTER(C.POINTER(C.c_int32)), C.c_void_p)
+DEC_METADATA_CB = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(StreamMetadataC), C.c_void_p)
+DEC_ERROR_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_void_p)
+DEC_READ_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_size_t), C.c_void_p)
 
 
 def lib():
@@ -138,10 +177,26 @@ def lib():
     for name in ("channels", "bits_per_sample", "sample_rate", "compression_level", "blocksize"):
         getattr(L, f"frb_stream_encoder_set_{name}").argtypes = [vp, u32]
     L.frb_stream_encoder_set_total_samples_estimate.argtypes = [vp, u64]
-    L.frb_stream_encoder_init_stream.argtypes = [vp, WRITE_CB, vp]
+    for name in ("verify", "streamable_subset", "limit_min_bitrate"):
+        getattr(L, f"frb_stream_encoder_set_{name}").argtypes = [vp, i32]
+    L.frb_stream_encoder_init_stream.argtypes = [vp, WRITE_CB, ENC_SEEK_CB, ENC_TELL_CB, ENC_METADATA_CB, vp]
     L.frb_stream_encoder_process_interleaved.argtypes = [vp, vp, u32]
+    L.frb_stream_encoder_process.argtypes = [vp, vp, u32]
     L.frb_stream_encoder_finish.argtypes = [vp]
     L.frb_stream_encoder_get_state.argtypes = [vp]
+    L.frb_stream_encoder_get_verify.argtypes = [vp]
+    L.frb_stream_decoder_new.restype = vp
+    L.frb_stream_decoder_delete.argtypes = [vp]
+    L.frb_stream_decoder_delete.restype = None
+    L.frb_stream_decoder_init_stream.argtypes = [vp, DEC_READ_CB, vp, vp, vp, vp, DEC_WRITE_CB, DEC_METADATA_CB, DEC_ERROR_CB, vp]
+    L.frb_stream_decoder_init_file.argtypes = [vp, C.c_char_p, DEC_WRITE_CB, DEC_METADATA_CB, DEC_ERROR_CB, vp]
+    for name in ("process_until_end_of_metadata", "process_until_end_of_stream", "finish", "get_state"):
+        getattr(L, f"frb_stream_decoder_{name}").argtypes = [vp]
+    for name in ("get_channels", "get_bits_per_sample", "get_sample_rate", "get_blocksize"):
+        getattr(L, f"frb_stream_decoder_{name}").argtypes = [vp]
+        getattr(L, f"frb_stream_decoder_{name}").restype = u32
+    L.frb_stream_decoder_get_total_samples.argtypes = [vp]
+    L.frb_stream_decoder_get_total_samples.restype = u64
     for name in _EXPORTS:
         getattr(L, name)          # AttributeError if a declared symbol is not exported
     _lib = L

@@ -282,7 +282,10 @@ def decode_tile_blobs(blobs, headers, metadatas, mosaic=None, staged=None):
 
     def take(i):
         r0, h_, w_ = int(tiles[i]["row_off"]), int(tiles[i]["h"]), int(tiles[i]["w"])
-        return np.ascontiguousarray(host_out[:, r0:r0 + h_, :w_])
+        # a real copy, always: host_out is a view of the engine's reusable pinned buffer, and ascontiguousarray would hand
+        # an already contiguous slice (single tile, full-width single-band tiles) straight back to the caller, to be
+        # overwritten by the next decode (the reference returns independent arrays)
+        return np.array(host_out[:, r0:r0 + h_, :w_], copy=True, order="C")
 
     if n >= 64:
         from concurrent.futures import ThreadPoolExecutor

@@ -88,7 +88,7 @@ __global__ void k_fill_u64(unsigned long long *p, uint64_t n, unsigned long long
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
-// grid (chunks, n_streams); every thread tests the 16 byte positions of one aligned 16-byte chunk per step
+// flattened grid of `parts` CTAs per stream; every thread tests the 16 byte positions of one aligned 16-byte chunk per step
 // (the sync code may straddle into the next chunk: one extra word).  SIMD byte compares reject a word without a
 // 0xFF 0xF8 pair in ~6 instructions; v1 tested 4 positions per two 4-byte loads (0.85 ms on C3).
 __device__ __forceinline__ void sync_candidate(const uint8_t *__restrict__ bytes, const DecStreamDev &st, uint64_t pos, uint64_t start,
@@ -114,13 +114,15 @@ __device__ __forceinline__ void sync_candidate(const uint8_t *__restrict__ bytes
 __global__ void __launch_bounds__(256)
 k_sync_scan(const uint8_t *__restrict__ bytes, const DecStreamDev *__restrict__ streams, uint32_t channels,
             uint32_t bps, uint32_t blocksize, unsigned long long *__restrict__ frame_pos,
-            unsigned long long *__restrict__ probe /* optional: [0]=max key, [1]=count */) {
-    const DecStreamDev st = streams[blockIdx.y];
+            unsigned long long *__restrict__ probe /* optional: [0]=max key, [1]=count */, uint32_t parts) {
+    // flattened grid, `parts` CTAs per stream (gridDim.y stops at 65535 streams)
+    const uint32_t si = blockIdx.x / parts, part = blockIdx.x - si * parts;
+    const DecStreamDev st = streams[si];
     const uint64_t start = st.byte_offset, end = st.byte_offset + st.byte_length;
     const uint64_t q0 = start >> 4, q1 = (end + 15) >> 4;            // 16-byte chunks touching the stream
     const uint4 *chunks = (const uint4 *)bytes;                      // 16-byte aligned base, 16 readable bytes past the end
     const uint32_t *words = (const uint32_t *)bytes;
-    for (uint64_t q = q0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < q1; q += (uint64_t)gridDim.x * blockDim.x) {
+    for (uint64_t q = q0 + (uint64_t)part * blockDim.x + threadIdx.x; q < q1; q += (uint64_t)parts * blockDim.x) {
         const uint4 c = __ldg(chunks + q);
         // first word of the next chunk (little-endian bytes); a sync code straddling out of the stream's last chunk
         // would fail the length check anyway, so nothing is read past the 16-byte slack
@@ -244,9 +246,8 @@ static int decode_batch_impl(const frb_decode_params *p, const frb_decode_stream
         uint32_t cap = (kNumSMs * 16 + p->n_streams - 1) / p->n_streams;
         if (gx > cap) gx = cap;
         if (gx < 1) gx = 1;
-        dim3 grid(gx, p->n_streams);
         prof_begin(3, s);
-        k_sync_scan<<<grid, 256, 0, s>>>(d_bytes, w.streams, p->channels, p->bps, p->blocksize, w.frame_pos, nullptr);
+        k_sync_scan<<<gx * p->n_streams, 256, 0, s>>>(d_bytes, w.streams, p->channels, p->bps, p->blocksize, w.frame_pos, nullptr, gx);
         prof_end(3, s);
         FRB_LAUNCH_CHECK("k_sync_scan");
     }
@@ -375,7 +376,7 @@ extern "C" int frb_probe_stream(const uint8_t *d_bytes, uint64_t byte_offset, ui
     uint64_t chunks = byte_length / 16 + 2;
     uint32_t gx = (uint32_t)((chunks + 256 * 4 - 1) / (256 * 4));
     if (gx > (uint32_t)kNumSMs * 16) gx = kNumSMs * 16;
-    k_sync_scan<<<dim3(gx, 1), 256, 0, s>>>(d_bytes, d_st, channels, bps, blocksize, nullptr, d_probe);
+    k_sync_scan<<<gx, 256, 0, s>>>(d_bytes, d_st, channels, bps, blocksize, nullptr, d_probe, gx);
     g_launches.fetch_add(1);
     unsigned long long h_probe[2] = {0, 0};
     e = cudaMemcpyAsync(h_probe, d_probe, 16, cudaMemcpyDeviceToHost, s);

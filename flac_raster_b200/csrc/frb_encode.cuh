@@ -783,12 +783,14 @@ __host__ __device__ __forceinline__ uint32_t ms_channel_code(uint32_t sel) { ret
 
 __global__ void __launch_bounds__(256)
 k_ms_expand(const EncStreamDev *__restrict__ streams, const EncStreamDev *__restrict__ vstreams,
-            const int32_t *__restrict__ audio, int32_t *__restrict__ vaudio) {
-    const EncStreamDev st = streams[blockIdx.y], vs = vstreams[blockIdx.y];
+            const int32_t *__restrict__ audio, int32_t *__restrict__ vaudio, uint32_t parts) {
+    // flattened grid, `parts` CTAs per stream (gridDim.y stops at 65535 streams)
+    const uint32_t si = blockIdx.x / parts, part = blockIdx.x - si * parts;
+    const EncStreamDev st = streams[si], vs = vstreams[si];
     const int32_t *l = audio + st.audio_base, *r = l + st.n_samples;
     int32_t *o = vaudio + vs.audio_base;
     const uint64_t n = st.n_samples;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    for (uint64_t i = (uint64_t)part * blockDim.x + threadIdx.x; i < n; i += (uint64_t)parts * blockDim.x) {
         const int32_t a = l[i], b = r[i];
         o[i] = a; o[n + i] = b; o[2 * n + i] = (a + b) >> 1; o[3 * n + i] = a - b;
     }
@@ -1227,7 +1229,7 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const int32_t *d_a
         for (uint32_t i = 0; i < p->n_streams; i++) max_n = std::max<uint64_t>(max_n, hs[i].n_samples);
         uint32_t gx = (uint32_t)std::min<uint64_t>((max_n + 256 * 8 - 1) / (256 * 8), std::max<uint32_t>(1u, (uint32_t)kNumSMs * 16 / p->n_streams));
         if (gx < 1) gx = 1;
-        k_ms_expand<<<dim3(gx, p->n_streams), 256, 0, s>>>(w.streams, w.vstreams, d_audio, w.vaudio);
+        k_ms_expand<<<gx * p->n_streams, 256, 0, s>>>(w.streams, w.vstreams, d_audio, w.vaudio, gx);
         FRB_LAUNCH_CHECK("k_ms_expand");
     }
     const uint32_t slot_words = slot_words_for(p->blocksize, enc_slot_bps(p));

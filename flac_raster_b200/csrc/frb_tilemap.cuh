@@ -89,9 +89,11 @@ struct RowSplit {
 template <typename T>
 __global__ void __launch_bounds__(kMapThreads)
 k_minmax_tiles(const T *__restrict__ raster, uint32_t bands, uint32_t H, uint32_t W,
-               const frb_tile *__restrict__ tiles, unsigned long long *keys) {
+               const frb_tile *__restrict__ tiles, unsigned long long *keys, uint32_t parts) {
     constexpr int G = MapGroup<T>::G;
-    const frb_tile t = tiles[blockIdx.y];
+    // flattened grid: `parts` CTAs per tile (the tile index must not sit in gridDim.y, which stops at 65535)
+    const uint32_t tile_i = blockIdx.x / parts, part = blockIdx.x - tile_i * parts;
+    const frb_tile t = tiles[tile_i];
     const uint32_t rows = bands * t.h;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     bool any = false;
@@ -101,7 +103,7 @@ k_minmax_tiles(const T *__restrict__ raster, uint32_t bands, uint32_t H, uint32_
         if (!any) { mn = mx = v; any = true; }
         else { mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
     };
-    for (uint32_t ry = blockIdx.x * kMapWarps + warp; ry < rows; ry += gridDim.x * kMapWarps) {
+    for (uint32_t ry = part * kMapWarps + warp; ry < rows; ry += parts * kMapWarps) {
         const uint32_t c = ry / t.h, y = ry - c * t.h;
         const T *src = raster + ((size_t)c * H + (t.row_off + y)) * W + t.col_off;
         const RowSplit<T> rs(src, t.w);
@@ -125,21 +127,22 @@ k_minmax_tiles(const T *__restrict__ raster, uint32_t bands, uint32_t H, uint32_
             for (int j = 0; j < G; j++) take(e0[j]);
         }
     }
-    block_minmax_commit(any ? dkey((double)mn) : kKeyMinInit, any ? dkey((double)mx) : kKeyMaxInit, keys + 2 * (size_t)blockIdx.y);
+    block_minmax_commit(any ? dkey((double)mn) : kKeyMinInit, any ? dkey((double)mx) : kKeyMaxInit, keys + 2 * (size_t)tile_i);
 }
 
 // ---------------------------------------------------------------- normalise
 __global__ void __launch_bounds__(256)
-k_build_norm_lut(const double *__restrict__ minmax, int bits, int32_t *__restrict__ lut) {
+k_build_norm_lut(const double *__restrict__ minmax, int bits, int32_t *__restrict__ lut, uint32_t parts) {
+    const uint32_t tile_i = blockIdx.x / parts, part = blockIdx.x - tile_i * parts;
     // 16-bit audio: entries are stored as int16 in the same buffer (half the cache sectors per warp-wide gather)
     int16_t *lut16 = reinterpret_cast<int16_t *>(lut);
-    const double mn = minmax[2 * blockIdx.y], mx = minmax[2 * blockIdx.y + 1];
+    const double mn = minmax[2 * tile_i], mx = minmax[2 * tile_i + 1];
     if (!(mx - mn < (double)kNormLutCap)) return;          // also false for NaN: those tiles use the direct path
     const double range = (mx <= mn) ? 1.0 : __dsub_rn(mx, mn);
     const double scale = scale_for_bits(bits);
     const uint32_t cnt = (uint32_t)(mx - mn) + 1;
-    const size_t base = (size_t)blockIdx.y * kNormLutCap;
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += gridDim.x * blockDim.x) {
+    const size_t base = (size_t)tile_i * kNormLutCap;
+    for (uint32_t j = part * blockDim.x + threadIdx.x; j < cnt; j += parts * blockDim.x) {
         const int32_t v = normalize_one(__dadd_rn(mn, (double)j), mn, range, scale);     // mn + j is exact (small integers)
         if (bits == 16) lut16[base + j] = (int16_t)v; else lut[base + j] = v;
     }
@@ -150,27 +153,28 @@ __global__ void __launch_bounds__(kMapThreads)
 k_normalize_tiles(const T *__restrict__ raster, uint32_t bands, uint32_t H, uint32_t W,
                   const frb_tile *__restrict__ tiles, const double *__restrict__ minmax, int bits,
                   int32_t *__restrict__ audio, const int64_t *__restrict__ audio_base,
-                  const int32_t *__restrict__ lut_all) {
+                  const int32_t *__restrict__ lut_all, uint32_t parts) {
     constexpr int G = MapGroup<T>::G, AV = MapGroup<T>::AV;
-    const frb_tile t = tiles[blockIdx.y];
+    const uint32_t tile_i = blockIdx.x / parts, part = blockIdx.x - tile_i * parts;
+    const frb_tile t = tiles[tile_i];
     const uint32_t n = t.h * t.w;
-    const double mn = minmax[2 * blockIdx.y], mx = minmax[2 * blockIdx.y + 1];
+    const double mn = minmax[2 * tile_i], mx = minmax[2 * tile_i + 1];
     const double range = (mx <= mn) ? 1.0 : __dsub_rn(mx, mn);
     const double scale = scale_for_bits(bits);
-    int32_t *dst = audio + audio_base[blockIdx.y];
+    int32_t *dst = audio + audio_base[tile_i];
     const uint32_t rows = bands * t.h;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool use_lut = is_small_int<T>::value && lut_all != nullptr && (mx - mn < (double)kNormLutCap);
     const int32_t vmin = use_lut ? (int32_t)mn : 0;
     // (staging the table in shared memory was tried: 64 KB per CTA costs more occupancy than the L1 gathers cost)
-    const int32_t *lut = lut_all ? lut_all + (size_t)blockIdx.y * kNormLutCap : nullptr;
+    const int32_t *lut = lut_all ? lut_all + (size_t)tile_i * kNormLutCap : nullptr;
     auto map = [&](T v) -> int32_t {
         if (is_small_int<T>::value && use_lut)
-            return bits == 16 ? (int32_t)__ldg(reinterpret_cast<const int16_t *>(lut_all) + (size_t)blockIdx.y * kNormLutCap + ((int32_t)v - vmin))
+            return bits == 16 ? (int32_t)__ldg(reinterpret_cast<const int16_t *>(lut_all) + (size_t)tile_i * kNormLutCap + ((int32_t)v - vmin))
                               : __ldg(lut + ((int32_t)v - vmin));
         return normalize_one((double)v, mn, range, scale);
     };
-    for (uint32_t ry = blockIdx.x * kMapWarps + warp; ry < rows; ry += gridDim.x * kMapWarps) {
+    for (uint32_t ry = part * kMapWarps + warp; ry < rows; ry += parts * kMapWarps) {
         const uint32_t c = ry / t.h, y = ry - c * t.h;
         const T *src = raster + ((size_t)c * H + (t.row_off + y)) * W + t.col_off;
         int32_t *out = dst + (size_t)c * n + (size_t)y * t.w;
@@ -220,13 +224,14 @@ template <typename T>
 __global__ void __launch_bounds__(kMapThreads)
 k_denormalize_tiles(const int32_t *__restrict__ audio, const int64_t *__restrict__ audio_base,
                     const frb_tile *__restrict__ tiles, const double *__restrict__ minmax, double scale,
-                    T *__restrict__ raster, uint32_t bands, uint32_t H, uint32_t W) {
+                    T *__restrict__ raster, uint32_t bands, uint32_t H, uint32_t W, uint32_t parts) {
     constexpr int G = MapGroup<T>::G, AV = MapGroup<T>::AV;
-    const frb_tile t = tiles[blockIdx.y];
+    const uint32_t tile_i = blockIdx.x / parts, part = blockIdx.x - tile_i * parts;
+    const frb_tile t = tiles[tile_i];
     const uint32_t n = t.h * t.w;
-    const double mn = minmax[2 * blockIdx.y], mx = minmax[2 * blockIdx.y + 1];
+    const double mn = minmax[2 * tile_i], mx = minmax[2 * tile_i + 1];
     const double range = __dsub_rn(mx, mn);                 // denormalize uses max-min unconditionally (:239)
-    const int32_t *src = audio + audio_base[blockIdx.y];
+    const int32_t *src = audio + audio_base[tile_i];
     const uint32_t rows = bands * t.h;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // the three scales the reference uses take the exact constant-division shortcut (see div_by_scale)
@@ -235,7 +240,7 @@ k_denormalize_tiles(const int32_t *__restrict__ audio, const int64_t *__restrict
     auto map = [&](int32_t a) -> T {
         return denorm_cast<T>(fast ? denormalize_one_fast((double)a, scale, rcp, mn, range) : denormalize_one((double)a, scale, mn, range));
     };
-    for (uint32_t ry = blockIdx.x * kMapWarps + warp; ry < rows; ry += gridDim.x * kMapWarps) {
+    for (uint32_t ry = part * kMapWarps + warp; ry < rows; ry += parts * kMapWarps) {
         const uint32_t c = ry / t.h, y = ry - c * t.h;
         T *out = raster + ((size_t)c * H + (t.row_off + y)) * W + t.col_off;
         const int32_t *in = src + (size_t)c * n + (size_t)y * t.w;
@@ -278,13 +283,13 @@ k_denormalize_tiles(const int32_t *__restrict__ audio, const int64_t *__restrict
     }
 }
 
-static inline dim3 tile_grid_dims(uint32_t n_tiles, uint32_t max_rows) {
+static inline uint32_t tile_grid_parts(uint32_t n_tiles, uint32_t max_rows) {
     // ~16 CTAs per SM in total, but never more CTAs per tile than it has (band,row) groups of kMapWarps
     uint32_t per_tile = (kNumSMs * 16 + n_tiles - 1) / n_tiles;
     const uint32_t cap = (max_rows + kMapWarps - 1) / kMapWarps;
     if (per_tile > cap) per_tile = cap;
     if (per_tile < 1) per_tile = 1;
-    return dim3(per_tile, n_tiles);
+    return per_tile;
 }
 
 #define FRB_DISPATCH_DTYPE(dtype, CALL)                                   \
@@ -314,8 +319,8 @@ extern "C" int frb_minmax_tiles(const void *d_raster, int dtype, uint32_t bands,
     cudaStream_t s = (cudaStream_t)stream;
     k_minmax_init<<<(n_tiles + 255) / 256, 256, 0, s>>>((unsigned long long *)d_minmax, n_tiles);
     FRB_LAUNCH_CHECK("k_minmax_init");
-    const dim3 grid = tile_grid_dims(n_tiles, bands * H);
-    FRB_DISPATCH_DTYPE(dtype, (k_minmax_tiles<T><<<grid, kMapThreads, 0, s>>>((const T *)d_raster, bands, H, W, d_tiles, (unsigned long long *)d_minmax)));
+    const uint32_t parts = tile_grid_parts(n_tiles, bands * H), grid = parts * n_tiles;
+    FRB_DISPATCH_DTYPE(dtype, (k_minmax_tiles<T><<<grid, kMapThreads, 0, s>>>((const T *)d_raster, bands, H, W, d_tiles, (unsigned long long *)d_minmax, parts)));
     FRB_LAUNCH_CHECK("k_minmax_tiles");
     k_minmax_finish<<<(n_tiles + 255) / 256, 256, 0, s>>>((unsigned long long *)d_minmax, n_tiles);
     FRB_LAUNCH_CHECK("k_minmax_finish");
@@ -334,13 +339,13 @@ extern "C" int frb_normalize_tiles(const void *d_raster, int dtype, uint32_t ban
     if (d_workspace && dtype <= FRB_I16) {
         MapWorkspace w;
         if (map_ws_layout(n_tiles, d_workspace, &w) > workspace_bytes) return FRB_ERR_OVERFLOW;
-        k_build_norm_lut<<<dim3(8, n_tiles), 256, 0, s>>>(d_minmax, bits_per_sample, w.norm_lut);
+        k_build_norm_lut<<<8 * n_tiles, 256, 0, s>>>(d_minmax, bits_per_sample, w.norm_lut, 8);
         FRB_LAUNCH_CHECK("k_build_norm_lut");
         lut = w.norm_lut;
     }
-    const dim3 grid = tile_grid_dims(n_tiles, bands * H);
+    const uint32_t parts = tile_grid_parts(n_tiles, bands * H), grid = parts * n_tiles;
     FRB_DISPATCH_DTYPE(dtype, (k_normalize_tiles<T><<<grid, kMapThreads, 0, s>>>((const T *)d_raster, bands, H, W, d_tiles, d_minmax,
-                                                                                       bits_per_sample, d_audio, d_audio_base, lut)));
+                                                                                       bits_per_sample, d_audio, d_audio_base, lut, parts)));
     FRB_LAUNCH_CHECK("k_normalize_tiles");
     return FRB_OK;
 }
@@ -354,9 +359,9 @@ extern "C" int frb_denormalize_tiles(const int32_t *d_audio, const int64_t *d_au
     if (!d_raster || !d_tiles || !d_minmax || !d_audio || !d_audio_base || dtype < 0 || dtype > FRB_F64 || !bands || !n_tiles)
         return FRB_ERR_INVALID_ARG;
     cudaStream_t s = (cudaStream_t)stream;
-    const dim3 grid = tile_grid_dims(n_tiles, bands * H);
+    const uint32_t parts = tile_grid_parts(n_tiles, bands * H), grid = parts * n_tiles;
     FRB_DISPATCH_DTYPE(dtype, (k_denormalize_tiles<T><<<grid, kMapThreads, 0, s>>>(d_audio, d_audio_base, d_tiles, d_minmax, scale,
-                                                                                  (T *)d_raster, bands, H, W)));
+                                                                                  (T *)d_raster, bands, H, W, parts)));
     FRB_LAUNCH_CHECK("k_denormalize_tiles");
     return FRB_OK;
 }

@@ -117,59 +117,134 @@ def build_index(template: Dict, tiles: np.ndarray, bboxes: List[List[float]], si
 
 
 def write_sharded_container(path: str, index: Dict, rank: int, first_tile: int, headers: List[bytes],
-                            payload: np.ndarray, offsets: np.ndarray, sizes: np.ndarray):
-    """Rank 0 writes [u32][JSON]; every rank pwrite()s its tiles at header + byte_offset."""
+                            payload, offsets: np.ndarray, sizes: np.ndarray, world: int = 1):
+    """Rank 0 writes [u32][JSON]; every rank pwrite()s its tiles at header + byte_offset (cli.py:625-630).
+
+    Rank 0 first creates the file and sets its length to header + sum(byte_size) -- re-encoding onto an existing,
+    longer file must not leave stale bytes behind -- and only then (barrier) do the other ranks open and write it.
+    A rank's tiles are contiguous in the file, so they go out as gathered writes (pwritev, <= 1024 buffers a call).
+    `payload`: anything with the buffer protocol (numpy array, pinned tensor's .numpy())."""
     index_json = json.dumps(index, separators=(",", ":")).encode("utf-8")
     header_size = 4 + len(index_json)
-    flags = os.O_WRONLY | os.O_CREAT
-    fd = os.open(path, flags, 0o644)
-    try:
-        if rank == 0:
+    total = header_size + sum(int(f["byte_size"]) for f in index["frames"])
+    multi = world > 1 and dist.is_available() and dist.is_initialized()
+    if rank == 0:
+        fd = os.open(path, os.O_WRONLY | os.O_CREAT, 0o644)
+        try:
+            os.ftruncate(fd, total)
             os.pwrite(fd, len(index_json).to_bytes(4, "big") + index_json, 0)
+        except BaseException:
+            os.close(fd)
+            raise
+    if multi:
+        dist.barrier()
+    if rank != 0:
+        fd = os.open(path, os.O_WRONLY)
+    try:
         mv = memoryview(payload)
+        bufs: List = []
+        pos0 = None
+        expect = None
         for j, (h, o, s) in enumerate(zip(headers, offsets, sizes)):
-            pos = header_size + index["frames"][first_tile + j]["byte_offset"]
-            os.pwrite(fd, h, pos)
-            os.pwrite(fd, mv[int(o):int(o) + int(s)], pos + len(h))
+            pos = header_size + int(index["frames"][first_tile + j]["byte_offset"])
+            if pos0 is None:
+                pos0 = expect = pos
+            if pos != expect or len(bufs) >= 1022:       # not contiguous with the previous tile, or IOV_MAX reached
+                _pwritev_all(fd, bufs, pos0)
+                bufs, pos0 = [], pos
+            bufs.append(h)
+            bufs.append(mv[int(o):int(o) + int(s)])
+            expect = pos + len(h) + int(s)
+        if bufs:
+            _pwritev_all(fd, bufs, pos0)
     finally:
         os.close(fd)
+    if multi:
+        dist.barrier()          # the container is complete on return, on every rank
     return header_size
 
 
-def encode_streaming_sharded(raster_dev, row_origin: int, full_shape: Tuple[int, int, int], transform, crs, nodata,
+def _pwritev_all(fd: int, bufs: List, pos: int):
+    """os.pwritev until every byte is out (a gathered write may be short)."""
+    bufs = [memoryview(b).cast("B") for b in bufs if len(b)]
+    while bufs:
+        n = os.pwritev(fd, bufs, pos)
+        pos += n
+        while bufs and n >= len(bufs[0]):
+            n -= len(bufs[0])
+            bufs.pop(0)
+        if bufs and n:
+            bufs[0] = bufs[0][n:]
+
+
+def rows_of_shard(tiles_all: np.ndarray, a: int, b: int) -> Tuple[int, int]:
+    """Raster rows [row0, row1) touched by tiles a..b-1 (a contiguous row-major block: at most a few tile rows)."""
+    if b <= a:
+        return 0, 0
+    t = tiles_all[a:b]
+    return int(t["row_off"].min()), int((t["row_off"].astype(np.int64) + t["h"]).max())
+
+
+def shard_plan(height: int, width: int, tile_size: int, rank: int, world: int):
+    """(all tiles, (first, last+1) tile of this rank, (row0, row1) raster rows this rank needs)."""
+    from .engine import tile_grid
+
+    tiles_all = tile_grid(height, width, tile_size)
+    a, b = shard_range(len(tiles_all), rank, world)
+    return tiles_all, (a, b), rows_of_shard(tiles_all, a, b)
+
+
+def encode_streaming_sharded(raster, row_origin: int, full_shape: Tuple[int, int, int], transform, crs, nodata,
                              dtype_name: str, tile_size: int, compression_level: int, output_path: Optional[str],
                              rank: int, world: int, engine=None):
-    """Each rank encodes its contiguous block of tiles of a (bands,H,W) raster.
+    """The streaming-tile loop of cli.py:553-630 with the tiles of ONE raster split over the ranks.
 
-    raster_dev holds (at least) the rows this rank's tiles touch, starting at global row
-    `row_origin`.  Returns (index, local EncodedTiles, (first_tile, last_tile)).
+    Each rank encodes its contiguous row-major block of tiles (one batched GPU call), the per-tile file sizes are
+    all-gathered (the one collective; its exclusive scan is every tile's byte_offset, cli.py:615-621), rank 0
+    writes [u32 BE][JSON index] and every rank pwrite()s its own tiles.  The file is byte-identical to the one
+    SpatialFLACEncoder.encode writes on one GPU.
+
+    raster: (bands, rows, W) device tensor, or host (ideally pinned) tensor, holding at least the rows this rank's
+    tiles touch, starting at global row `row_origin` (see shard_plan).  Returns (index, local EncodedTiles,
+    (first_tile, last_tile+1)).
     """
-    from .engine import default_engine, tile_grid
+    from .engine import default_engine
     from .spatial_encoder import build_streaming_container, _tile_bbox
-
     eng = engine or default_engine()
     bands, H, W = full_shape
-    tiles_all = tile_grid(H, W, tile_size)
-    a, b = shard_range(len(tiles_all), rank, world)
-    local = tiles_all[a:b].copy()
-    local["row_off"] -= row_origin
-    # per-tile transforms/bboxes are computed against the global grid
-    gtrans = transform
-    shifted = None
-    if transform is not None:
-        from .tiffio import window_transform
-        shifted = window_transform(transform, 0, row_origin)
-    index_local, headers, enc = build_streaming_container(raster_dev, shifted, crs, nodata, dtype_name, tile_size,
-                                                          compression_level, tiles=local, engine=eng)
-    file_sizes = np.array([f["byte_size"] for f in index_local["frames"]], dtype=np.int64)
+    tiles_all, (a, b), _ = shard_plan(H, W, tile_size, rank, world)
+    if b > a:
+        # tiles stay in global coordinates (their transform/bounds tags must equal the one-GPU file's bit for bit);
+        # row_origin tells the engine where the local slab starts
+        index_local, headers, enc = build_streaming_container(raster, transform, crs, nodata, dtype_name, tile_size,
+                                                              compression_level, tiles=tiles_all[a:b], engine=eng,
+                                                              row_origin=row_origin, full_shape=full_shape)
+        file_sizes = np.array([f["byte_size"] for f in index_local["frames"]], dtype=np.int64)
+    else:                                    # more ranks than tiles
+        index_local, headers, enc, file_sizes = {}, [], None, np.zeros(0, dtype=np.int64)
     sizes_all = allgather_tile_sizes(file_sizes, len(tiles_all), rank, world)
-    bboxes = [_tile_bbox(gtrans, int(t["col_off"]), int(t["row_off"]), int(t["w"]), int(t["h"]))[0] for t in tiles_all]
-    template = {k: v for k, v in index_local.items() if k != "frames"}
-    template.update({"width": W, "height": H})
-    if transform is not None:
-        template["transform"] = list(transform[:6]) + [0.0, 0.0, 1.0]
+    bboxes = [_tile_bbox(transform, int(t["col_off"]), int(t["row_off"]), int(t["w"]), int(t["h"]))[0] for t in tiles_all]
+    template = {"crs": str(crs), "transform": (list(transform[:6]) + [0.0, 0.0, 1.0]) if transform else [],
+                "width": W, "height": H, "bands": bands, "dtype": dtype_name, "tile_size": tile_size}
     index = build_index(template, tiles_all, bboxes, sizes_all)
     if output_path:
-        payload = enc.payload.cpu().numpy()
-        write_sharded_container(output_path, index, rank, a, headers, payload, enc.offsets, enc.sizes)
+        if enc is None:
+            payload, offs, szs = np.zeros(0, dtype=np.uint8), [], []
+        elif enc.payload.is_cuda:
+            # frames -> pinned staging (no pageable bounce buffer) -> pwritev
+            n = int(enc.payload.numel())
+            stage = eng._pinned("shard_out", n)
+            stage[:n].copy_(enc.payload, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            payload, offs, szs = stage[:n].numpy(), enc.offsets, enc.sizes
+        else:
+            payload, offs, szs = enc.payload.numpy(), enc.offsets, enc.sizes
+        write_sharded_container(output_path, index, rank, a, headers, payload, offs, szs, world)
     return index, enc, (a, b)
+
+
+def current_rank_world() -> Tuple[int, int]:
+    """(rank, world) of the initialised process group, (0, 1) without one."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1

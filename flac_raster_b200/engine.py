@@ -92,6 +92,11 @@ class Engine:
     def release(self):
         self._ws.clear()
 
+    @staticmethod
+    def audio_elem_bytes(bps: int) -> int:
+        """Bytes per sample of the planar audio buffer between the mapping kernels and the codec kernels."""
+        return 4
+
     def _upload(self, arr: np.ndarray) -> torch.Tensor:
         """A small host array -> a fresh device tensor (uint8 view) on the current stream, through the library's pinned
         staging + copy kernel: torch's .to(device) is a DMA transfer and would queue behind the bulk copies of the host

@@ -97,23 +97,31 @@ def _tile_bbox(transform, col, row, w, h):
 
 
 def build_streaming_container(raster_dev, transform, crs, nodata, dtype_name: str, tile_size: int,
-                              compression_level: int = 5, tiles: Optional[np.ndarray] = None, engine=None):
+                              compression_level: int = 5, tiles: Optional[np.ndarray] = None, engine=None,
+                              row_origin: int = 0, full_shape: Optional[Tuple[int, int, int]] = None):
     """Encode every tile of a device-resident (bands,H,W) raster and lay out the container.
 
     Returns (index dict, list of per-tile header bytes, EncodedTiles).  Tile t's complete FLAC
     file is headers[t] + payload[offsets[t]:offsets[t]+sizes[t]]; index byte_offset/byte_size are
     the exclusive scan of the file sizes (cli.py:615-621).
+    `tiles` are in the coordinates of the FULL raster (`full_shape`, default: raster_dev's own); `row_origin` is the
+    global row raster_dev[:, 0] holds (a rank of the sharded path passes only the rows its tiles touch), so every
+    tile's transform/bounds tags are computed exactly as the one-GPU path computes them.
     """
     from .engine import default_engine, tile_grid
 
     eng = engine or default_engine()
-    bands, H, W = raster_dev.shape
+    bands, H, W = full_shape if full_shape is not None else raster_dev.shape
     if tiles is None:
         tiles = tile_grid(H, W, tile_size)
+    local = tiles
+    if row_origin:
+        local = tiles.copy()
+        local["row_off"] -= row_origin
     if raster_dev.is_cuda:
-        enc = eng.encode_tiles(raster_dev, tiles, compression_level)
+        enc = eng.encode_tiles(raster_dev, local, compression_level)
     else:       # host raster: tile rows pipelined over copy / compute / copy streams (Engine.encode_tiles_host)
-        enc = eng.encode_tiles_host(raster_dev, tiles, compression_level)
+        enc = eng.encode_tiles_host(raster_dev, local, compression_level)
     scale = 32767 if enc.bits_per_sample == 16 else 8388607
     headers, frames = [], []
     total = 0
@@ -196,6 +204,22 @@ class SpatialFLACEncoder:
         if arr.shape[0] > 8:
             raise ValueError("FLAC supports at most 8 channels (bands)")
         eng = default_engine()
+        from .distributed import current_rank_world, encode_streaming_sharded, shard_plan
+        rank, world = current_rank_world()
+        if world > 1:
+            # one process per GPU (torch.distributed initialised by the caller): the tiles of this raster are split
+            # over the ranks, every rank writes its own part of ONE container (distributed.encode_streaming_sharded)
+            bands, H, W = arr.shape
+            _, _, (r0, r1) = shard_plan(H, W, self.tile_size, rank, world)
+            sl = np.ascontiguousarray(arr[:, r0:r1])
+            host = torch.from_numpy(sl.view(np.uint8).reshape(-1)).view(TORCH_DTYPES[str(arr.dtype)]).reshape(sl.shape)
+            index, _, _ = encode_streaming_sharded(host, r0, (bands, H, W), raster.transform, raster.crs, raster.nodata,
+                                                   str(arr.dtype), self.tile_size, compression_level, str(output_path),
+                                                   rank, world, engine=eng)
+            self.frames = [SpatialFrame(f["frame_id"], tuple(f["bbox"]),
+                                        _Window(f["window"]["col_off"], f["window"]["row_off"], f["window"]["width"], f["window"]["height"]),
+                                        f["byte_offset"], f["byte_size"]) for f in index["frames"]]
+            return SpatialIndex(self.frames, raster.crs, raster.transform)
         host = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).view(TORCH_DTYPES[str(arr.dtype)]).reshape(arr.shape)
         index, headers, enc = build_streaming_container(host, raster.transform, raster.crs, raster.nodata, str(arr.dtype),
                                                         self.tile_size, compression_level, engine=eng)
@@ -282,6 +306,7 @@ class SpatialFLACStreamer:
         self.metadata: Optional[Dict] = None      # streaming container index
         self.header_size = 0
         self.spatial_index: Optional[SpatialIndex] = None
+        self.legacy_tags: Dict[str, List[str]] = {}
         self._load_spatial_index()
 
     # ---- byte access ---------------------------------------------------------------------
@@ -311,21 +336,102 @@ class SpatialFLACStreamer:
         self.spatial_index = SpatialIndex(frames, self.metadata.get("crs"), self.metadata.get("transform"))
 
     def _load_legacy_index(self):
-        """Index from the first stream's VORBIS tags (spatial_encoder.py:434-515)."""
+        """Index from the first stream's VORBIS tags (spatial_encoder.py:434-515).
+
+        The reference ALWAYS stores GEOSPATIAL_SPATIAL_INDEX as base64(gzip(json)) and writes no marker tag
+        (spatial_encoder.py:366-375, read back at :464-474), so that is tried first; plain JSON is accepted too.
+        Reference-written files carry STALE byte offsets: they are recorded while the tile streams are appended
+        (:238-241) and mutagen then grows stream 0 by its tags and padding (:251), moving every later stream
+        (SURVEY Q6).  An entry that does not point at a "fLaC" marker triggers a rescan for the real stream starts."""
         blob = self._read_range(0, (1 << 20) - 1)           # same first-MiB probe as the reference
         hdr = flacfmt.parse_header(blob)
         tag = hdr.tags.get("GEOSPATIAL_SPATIAL_INDEX")
         if not tag:
             raise ValueError("No spatial index found in FLAC metadata")
         raw = tag[0]
-        if hdr.tags.get("GEOSPATIAL_SPATIAL_INDEX_COMPRESSED", [""])[0] == "gzip+base64":
-            raw = gzip.decompress(base64.b64decode(raw)).decode("utf-8")
+        try:
+            raw = gzip.decompress(base64.b64decode(raw.encode("ascii"), validate=True)).decode("utf-8")
+        except (ValueError, OSError, EOFError, UnicodeError):
+            pass                                            # not base64+gzip: plain JSON text
         d = json.loads(raw)
         frames = [SpatialFrame(f["frame_id"], tuple(f["bbox"]),
                                _Window(f["window"]["col_off"], f["window"]["row_off"], f["window"]["width"], f["window"]["height"]),
                                f["byte_offset"], f["byte_size"]) for f in d["frames"]]
         self.spatial_index = SpatialIndex(frames, d.get("crs"), d.get("transform"))
         self.header_size = 0
+        self.legacy_tags = hdr.tags                         # global metadata: the tile streams carry none
+        self._fix_stale_legacy_offsets(blob)
+
+    @staticmethod
+    def _stream_starts(data) -> List[int]:
+        """Positions of 'fLaC' markers that are followed by a STREAMINFO block header (type 0, length 34): eight
+        fixed bytes, so a chance hit inside compressed audio is a 2^-64 event per position."""
+        out, pos, mv = [], 0, bytes(data) if not isinstance(data, (bytes, bytearray)) else data
+        while True:
+            pos = mv.find(b"fLaC", pos)
+            if pos < 0:
+                return out
+            if mv[pos + 4:pos + 8] in (b"\x00\x00\x00\x22", b"\x80\x00\x00\x22"):
+                out.append(pos)
+            pos += 4
+
+    def _fix_stale_legacy_offsets(self, first_mib: bytes):
+        frames = self.spatial_index.frames
+        if not frames:
+            return
+
+        def marker_at(off: int) -> bool:
+            if off + 4 <= len(first_mib):
+                return first_mib[off:off + 4] == b"fLaC"
+            try:
+                return self._read_range(off, off + 3) == b"fLaC"
+            except Exception:  # noqa: BLE001  (offset beyond the end of the file)
+                return False
+
+        if all(marker_at(f.byte_offset) for f in frames):
+            return
+        # stale: locate the real stream starts (whole file: legacy files are small, one stream per tile)
+        if self.is_url:
+            from .remote import RemoteFile
+            data = RemoteFile(self.source).read_all()
+        else:
+            data = self.flac_path.read_bytes()
+        starts = self._stream_starts(data)
+        order = sorted(range(len(frames)), key=lambda i: frames[i].byte_offset)
+        if len(starts) == len(frames):
+            ends = starts[1:] + [len(data)]
+            for rank_, i in enumerate(order):
+                frames[i].byte_offset, frames[i].byte_size = starts[rank_], ends[rank_] - starts[rank_]
+        elif len(starts) >= 2:
+            # the only thing that moved is stream 0's length: shift every later stream by that growth
+            delta = starts[1] - frames[order[0]].byte_size - frames[order[0]].byte_offset
+            for rank_, i in enumerate(order):
+                if rank_ == 0:
+                    frames[i].byte_size += delta
+                else:
+                    frames[i].byte_offset += delta
+            if not all(data[f.byte_offset:f.byte_offset + 4] == b"fLaC" for f in frames):
+                raise ValueError("legacy spatial FLAC: byte offsets do not point at FLAC streams and cannot be repaired")
+        else:
+            raise ValueError("legacy spatial FLAC: byte offsets do not point at FLAC streams and cannot be repaired")
+        self.logger.info("legacy spatial FLAC: stale byte offsets corrected from the stream markers")
+        self.spatial_index.total_bytes = sum(f.byte_size for f in frames)
+
+    def _legacy_tile_metadata(self, frame: SpatialFrame, streaminfo) -> Dict:
+        """Per-tile metadata of a legacy file: the tile streams have no tags of their own, only stream 0 carries the
+        GLOBAL ones (spatial_encoder.py:338-356; the per-tile normalisation parameters were discarded at :222,
+        SURVEY Q6), so a tile is denormalised with the global min/max -- all the information the file holds."""
+        g = parse_metadata_tags(self.legacy_tags) or {}
+        w, h = int(frame.window.width), int(frame.window.height)
+        tr = g.get("transform") or None
+        md = {
+            "crs": g.get("crs", ""), "width": w, "height": h, "count": int(g.get("count", streaminfo.channels)),
+            "dtype": g.get("dtype", "int16" if streaminfo.bits_per_sample == 16 else "int32"),
+            "nodata": g.get("nodata"), "data_min": float(g.get("data_min", 0.0)), "data_max": float(g.get("data_max", 0.0)),
+            "transform": (list(window_transform(tuple(tr[:6]), int(frame.window.col_off), int(frame.window.row_off))) + [0.0, 0.0, 1.0]) if tr else [],
+            "bounds": list(frame.bbox), "spatial_tiling": True,
+        }
+        return md
 
     # ---- reference methods (byte ranges only, spatial_encoder.py:517-567) ----------------------
     def get_byte_ranges_for_bbox(self, bbox) -> List[Tuple[int, int]]:
@@ -409,8 +515,12 @@ class SpatialFLACStreamer:
             blobs, staged = self._fetch_tiles_pinned(frames)
         headers = [flacfmt.parse_header(b) for b in blobs]
         metas = []
-        for h in headers:
+        legacy = self.metadata is None
+        for f, h in zip(frames, headers):
             md = parse_metadata_tags(h.tags)
+            if legacy and not (md and int(md.get("width", 0)) * int(md.get("height", 0)) == int(f.window.width) * int(f.window.height)):
+                # reference-written legacy file: no per-tile tags (stream 0 holds the GLOBAL ones)
+                md = self._legacy_tile_metadata(f, h.streaminfo)
             if not md:
                 raise ValueError("No metadata found in FLAC file or sidecar file")
             metas.append(md)
@@ -432,9 +542,21 @@ class SpatialFLACStreamer:
             raise KeyError(f"Tile ID {tile_id} not found")
         return self._decode([frame])[0]
 
-    def get_tiles_by_bbox(self, xmin, ymin, xmax, ymax):
-        """README.md:202 -> list of (tile_data, metadata) for ALL intersecting tiles (one batched decode)."""
+    def get_tiles_by_bbox(self, xmin, ymin, xmax, ymax, shard=None):
+        """README.md:202 -> list of (tile_data, metadata) for ALL intersecting tiles (one batched decode).
+
+        Multi-GPU (one process per GPU): the intersecting tiles are split over the ranks in contiguous blocks and each
+        rank fetches and decodes only its own block -- no collective; the call returns this rank's tiles.
+        `shard`: (rank, world) to split explicitly, None = the initialised torch.distributed group (or no split),
+        False = never split."""
         frames = [f for f in self.spatial_index.frames if _intersects((xmin, ymin, xmax, ymax), f.bbox)]
+        if shard is None:
+            from .distributed import current_rank_world
+            shard = current_rank_world()
+        if shard and shard[1] > 1:
+            from .distributed import shard_range
+            a, b = shard_range(len(frames), int(shard[0]), int(shard[1]))
+            frames = frames[a:b]
         if not frames:
             return []
         return self._decode(frames)

@@ -252,32 +252,131 @@ int frb_host_decode(const uint8_t *frames, size_t n_bytes, uint32_t channels, ui
                     int32_t *interleaved_out, size_t out_capacity_samples,
                     uint64_t *n_samples_out);
 
-/* libFLAC-shaped handle API: the exact calls pyflac's cffi layer makes
- * (docs/sonos-pyflac.txt:2200-2212, :1994-1997, :2003-2014), so a binding
- * written against FLAC__stream_encoder_* can be retargeted by renaming. */
+/* ------------------------------------------ 6. libFLAC-shaped handle API
+ * The exact calls pyflac's cffi layer makes, so a binding written against FLAC__stream_encoder_* /
+ * FLAC__stream_decoder_* (cdef at docs/sonos-pyflac.txt:3206-3263 and :2826-2935) can be retargeted by renaming
+ * FLAC__ -> frb_.  Same argument order and meaning, FLAC__bool-style returns (1 = success) for the
+ * set/process/finish calls, FLAC__Stream{En,De}coderInitStatus numbers for the init calls and
+ * FLAC__Stream{En,De}coderState numbers for get_state.  Handles are not thread-safe; callbacks run on
+ * the calling thread; callback buffers are borrowed for the duration of the callback (pyflac copies them,
+ * docs/sonos-pyflac.txt:2325, :1840-1841).
+ *
+ * Difference in timing, not in content: the engine codes a stream as ONE GPU batch, so the encoder
+ * buffers every process*() call and delivers all frame callbacks inside finish() (peak host memory:
+ * the stream twice), and the decoder pulls the whole stream before the first write callback.  The
+ * reference makes one process() call followed by finish() (converter.py:153-154) and decodes whole
+ * files (converter.py:181-182), so it cannot observe the difference. */
+
+/* ---- metadata / frame views handed to callbacks: the leading members of FLAC__StreamMetadata (with its
+ * stream_info arm, docs/sonos-pyflac.txt:2698-2708, :2799-2813) and of FLAC__Frame (:2598-2610, :2679-2683) */
+typedef struct frb_stream_info {
+    uint32_t min_blocksize, max_blocksize;
+    uint32_t min_framesize, max_framesize;
+    uint32_t sample_rate, channels, bits_per_sample;
+    uint64_t total_samples;
+    uint8_t md5sum[16];
+} frb_stream_info;
+typedef struct frb_stream_metadata {
+    int type;                   /* 0 = STREAMINFO (the only block the callbacks report, libFLAC's default) */
+    int is_last;
+    uint32_t length;
+    frb_stream_info stream_info;
+} frb_stream_metadata;
+
+typedef struct frb_frame_header {
+    uint32_t blocksize;
+    uint32_t sample_rate;
+    uint32_t channels;
+    int channel_assignment;     /* always 0 (independent): buffer[] holds the restored channels */
+    uint32_t bits_per_sample;
+    int number_type;            /* 0 = frame number (fixed-blocksize streams) */
+    union { uint32_t frame_number; uint64_t sample_number; } number;
+    uint8_t crc;
+} frb_frame_header;
+typedef struct frb_frame {
+    frb_frame_header header;    /* FLAC__Frame continues with subframes[8] and the footer; pyflac reads the header only
+                                   (docs/sonos-pyflac.txt:1823-1846) */
+} frb_frame;
+
+/* ---- encoder (FLAC__stream_encoder_*, docs/sonos-pyflac.txt:3206-3263; used at :2186-2212, :1994-1997, :2003-2014) */
 typedef struct frb_stream_encoder frb_stream_encoder;
-/* same shape as FLAC__StreamEncoderWriteCallback (docs/sonos-pyflac.txt:3192):
- * returns 0 on success */
+/* FLAC__StreamEncoderWriteCallback (:3192): returns 0 on success.  samples == 0 marks a metadata chunk */
 typedef int (*frb_encoder_write_cb)(const frb_stream_encoder *enc, const uint8_t *buffer,
                                     size_t bytes, uint32_t samples, uint32_t current_frame,
                                     void *client_data);
+/* FLAC__StreamEncoderSeekCallback / TellCallback / MetadataCallback (:3193-3195): 0 = OK */
+typedef int (*frb_encoder_seek_cb)(const frb_stream_encoder *enc, uint64_t absolute_byte_offset, void *client_data);
+typedef int (*frb_encoder_tell_cb)(const frb_stream_encoder *enc, uint64_t *absolute_byte_offset, void *client_data);
+typedef void (*frb_encoder_metadata_cb)(const frb_stream_encoder *enc, const frb_stream_metadata *metadata, void *client_data);
 
 frb_stream_encoder *frb_stream_encoder_new(void);
 void frb_stream_encoder_delete(frb_stream_encoder *enc);
+int frb_stream_encoder_set_verify(frb_stream_encoder *enc, int value);       /* finish() decodes its own frames on the GPU and compares */
 int frb_stream_encoder_set_channels(frb_stream_encoder *enc, uint32_t v);
 int frb_stream_encoder_set_bits_per_sample(frb_stream_encoder *enc, uint32_t v);
 int frb_stream_encoder_set_sample_rate(frb_stream_encoder *enc, uint32_t v);
 int frb_stream_encoder_set_compression_level(frb_stream_encoder *enc, uint32_t v);
 int frb_stream_encoder_set_blocksize(frb_stream_encoder *enc, uint32_t v);
 int frb_stream_encoder_set_total_samples_estimate(frb_stream_encoder *enc, uint64_t v);
-/* emits "fLaC" + STREAMINFO + VORBIS_COMMENT(vendor) through the callback (samples == 0) */
+int frb_stream_encoder_set_streamable_subset(frb_stream_encoder *enc, int value);   /* every preset is subset-conformant: accepted */
+int frb_stream_encoder_set_limit_min_bitrate(frb_stream_encoder *enc, int value);   /* 1 is refused by init_stream (not implemented) */
+int frb_stream_encoder_get_verify(const frb_stream_encoder *enc);
+/* FLAC__StreamEncoderState: 0 OK, 1 UNINITIALIZED, 3 VERIFY_DECODER_ERROR, 4 VERIFY_MISMATCH_IN_AUDIO_DATA, 5 CLIENT_ERROR,
+ * 7 FRAMING_ERROR, 8 MEMORY_ALLOCATION_ERROR */
+int frb_stream_encoder_get_state(const frb_stream_encoder *enc);
+/* Emits "fLaC" + STREAMINFO + VORBIS_COMMENT(vendor) through write_cb (samples == 0).  seek_cb, tell_cb and
+ * metadata_cb may be NULL (the reference passes none, converter.py:139-144: STREAMINFO then stays unfinalised,
+ * SURVEY Q7); with seek_cb + tell_cb finish() seeks to byte 8 and rewrites the STREAMINFO body with the total samples
+ * and min/max frame sizes (MD5 stays zero).  Returns a FLAC__StreamEncoderInitStatus (0 = OK). */
 int frb_stream_encoder_init_stream(frb_stream_encoder *enc, frb_encoder_write_cb write_cb,
-                                   void *client_data);
-/* returns 1 (true) on success like FLAC__bool */
+                                   frb_encoder_seek_cb seek_cb, frb_encoder_tell_cb tell_cb,
+                                   frb_encoder_metadata_cb metadata_cb, void *client_data);
+/* return 1 (true) on success like FLAC__bool */
 int frb_stream_encoder_process_interleaved(frb_stream_encoder *enc, const int32_t *buffer,
                                            uint32_t samples);
+int frb_stream_encoder_process(frb_stream_encoder *enc, const int32_t *const buffer[], uint32_t samples);
 int frb_stream_encoder_finish(frb_stream_encoder *enc);
-int frb_stream_encoder_get_state(const frb_stream_encoder *enc);
+
+/* ---- decoder (FLAC__stream_decoder_*, cdef docs/sonos-pyflac.txt:2826-2935; used by pyflac.FileDecoder at :1584-1629
+ * and by its write callback at :1809-1854) */
+typedef struct frb_stream_decoder frb_stream_decoder;
+/* FLAC__StreamDecoderWriteCallback (:2825): one call per frame, buffer[c] = header.blocksize samples of channel c
+ * (16-bit samples sign-extended in int32, like libFLAC).  Return 0 to continue, non-zero to abort. */
+typedef int (*frb_decoder_write_cb)(const frb_stream_decoder *dec, const frb_frame *frame,
+                                    const int32_t *const buffer[], void *client_data);
+typedef void (*frb_decoder_metadata_cb)(const frb_stream_decoder *dec, const frb_stream_metadata *metadata, void *client_data);
+/* status: FLAC__StreamDecoderErrorStatus (0 LOST_SYNC, 1 BAD_HEADER, 2 FRAME_CRC_MISMATCH, 3 UNPARSEABLE_STREAM) */
+typedef void (*frb_decoder_error_cb)(const frb_stream_decoder *dec, int status, void *client_data);
+/* FLAC__StreamDecoderReadCallback (:2820): fill buffer[0..*bytes), set *bytes; return 0 continue, 1 end of stream, 2 abort */
+typedef int (*frb_decoder_read_cb)(const frb_stream_decoder *dec, uint8_t buffer[], size_t *bytes, void *client_data);
+typedef int (*frb_decoder_seek_cb)(const frb_stream_decoder *dec, uint64_t absolute_byte_offset, void *client_data);
+typedef int (*frb_decoder_tell_cb)(const frb_stream_decoder *dec, uint64_t *absolute_byte_offset, void *client_data);
+typedef int (*frb_decoder_length_cb)(const frb_stream_decoder *dec, uint64_t *stream_length, void *client_data);
+typedef int (*frb_decoder_eof_cb)(const frb_stream_decoder *dec, void *client_data);
+
+frb_stream_decoder *frb_stream_decoder_new(void);
+void frb_stream_decoder_delete(frb_stream_decoder *dec);
+/* FLAC__StreamDecoderInitStatus: 0 OK, 2 INVALID_CALLBACKS, 3 MEMORY_ALLOCATION_ERROR, 4 ERROR_OPENING_FILE,
+ * 5 ALREADY_INITIALIZED.  seek/tell/length/eof callbacks may be NULL (the engine never seeks). */
+int frb_stream_decoder_init_stream(frb_stream_decoder *dec, frb_decoder_read_cb read_cb, frb_decoder_seek_cb seek_cb,
+                                   frb_decoder_tell_cb tell_cb, frb_decoder_length_cb length_cb, frb_decoder_eof_cb eof_cb,
+                                   frb_decoder_write_cb write_cb, frb_decoder_metadata_cb metadata_cb,
+                                   frb_decoder_error_cb error_cb, void *client_data);
+int frb_stream_decoder_init_file(frb_stream_decoder *dec, const char *filename, frb_decoder_write_cb write_cb,
+                                 frb_decoder_metadata_cb metadata_cb, frb_decoder_error_cb error_cb, void *client_data);
+int frb_stream_decoder_process_until_end_of_metadata(frb_stream_decoder *dec);
+/* whole stream: metadata callback (STREAMINFO), GPU decode, one write callback per frame.  A file holding several
+ * concatenated streams (legacy --spatial layout) yields the first one.  Returns 1 on success. */
+int frb_stream_decoder_process_until_end_of_stream(frb_stream_decoder *dec);
+int frb_stream_decoder_finish(frb_stream_decoder *dec);
+/* FLAC__StreamDecoderState: 0 SEARCH_FOR_METADATA, 2 SEARCH_FOR_FRAME_SYNC, 3 READ_FRAME, 4 END_OF_STREAM, 7 ABORTED,
+ * 8 MEMORY_ALLOCATION_ERROR, 9 UNINITIALIZED */
+int frb_stream_decoder_get_state(const frb_stream_decoder *dec);
+uint32_t frb_stream_decoder_get_channels(const frb_stream_decoder *dec);
+uint32_t frb_stream_decoder_get_bits_per_sample(const frb_stream_decoder *dec);
+uint32_t frb_stream_decoder_get_sample_rate(const frb_stream_decoder *dec);
+uint32_t frb_stream_decoder_get_blocksize(const frb_stream_decoder *dec);
+uint64_t frb_stream_decoder_get_total_samples(const frb_stream_decoder *dec);   /* samples handed to the write callback so far */
 
 #ifdef __cplusplus
 }

@@ -38,7 +38,7 @@ def _worker(rank, world, port, path, n_tiles):
     tiles["col_off"] = np.arange(n_tiles)
     index = build_index({"crs": "None", "transform": [], "width": n_tiles, "height": 1, "bands": 1, "dtype": "uint8", "tile_size": 1},
                         tiles, [[float(t), 0.0, float(t + 1), 1.0] for t in range(n_tiles)], sizes)
-    write_sharded_container(path, index, rank, a, headers, payload, poffs, psizes)
+    write_sharded_container(path, index, rank, a, headers, payload, poffs, psizes, world)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -46,6 +46,8 @@ def _worker(rank, world, port, path, n_tiles):
 def test_two_rank_sharded_container(tmp_path):
     n_tiles, world = 11, 2
     path = str(tmp_path / "sharded.flac")
+    with open(path, "wb") as fh:                          # a stale, longer file from an earlier run must not leave bytes behind
+        fh.write(b"\xEE" * 4096)
     mp.spawn(_worker, args=(world, _free_port(), path, n_tiles), nprocs=world, join=True)
     blob = open(path, "rb").read()
     (n,) = struct.unpack(">I", blob[:4])

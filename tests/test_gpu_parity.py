@@ -534,12 +534,14 @@ def test_fullsize_c3_sentinel_like_roundtrip(nat, torch_cuda):
 
 
 def test_fullsize_c4_float32_level8_roundtrip(nat, torch_cuda):
-    """Config 4 shape family (float32 DEM, level 8, 32-bps stream): decode(encode(x)) == normalise(x)
-    sample-for-sample, and reconstruction equals the reference's 24-bit quantisation."""
+    """Config 4 at its BASELINE size (float32 DEM 32768^2, level 8, one 32-bps stream of 2^30 samples; FRB_TEST_C4_SIDE
+    shrinks it for debugging): decode(encode(x)) == normalise(x) sample-for-sample, and the reconstruction equals the
+    reference's 24-bit quantisation (normalize_to_audio -> denormalize_from_audio in numpy) on sampled rows."""
     torch = torch_cuda
     from flac_raster_b200.engine import default_engine, tile_grid
     from flac_raster_b200.synth import dem_float32
-    side = int(os.environ.get("FRB_TEST_C4_SIDE", "8192"))
+    from oracle import normalization_oracle as no
+    side = int(os.environ.get("FRB_TEST_C4_SIDE", "32768"))
     raster = dem_float32(side, side)
     eng = default_engine()
     tiles = tile_grid(side, side, side)
@@ -550,8 +552,19 @@ def test_fullsize_c4_float32_level8_roundtrip(nat, torch_cuda):
     payload = torch.cat([enc.payload, torch.zeros(64, dtype=torch.uint8, device=raster.device)])
     audio, base, status = eng.decode_streams(payload, enc.offsets, enc.sizes, enc.n_samples, enc.sample_rates, 1, 32, 4096)
     assert list(status[:3]) == [0, 0, 0]
+    assert status[3] == (side * side + 4095) // 4096
     assert torch.equal(audio[:side * side * 4].view(torch.int32), ref)
     assert int(enc.sizes.sum()) < side * side * 4 * 0.75
+    # reconstruction: the GPU denormalise of the decoded samples against the reference formula on a few row bands
+    out = torch.zeros_like(raster)
+    eng.denormalize_tiles(audio, base, tiles, enc.minmax, 8388607.0, out)
+    dmin, dmax = float(enc.minmax[0, 0]), float(enc.minmax[0, 1])
+    for r0 in (0, side // 2 - 3, side - 8):
+        rows = raster[0, r0:r0 + 8].cpu().numpy()
+        a, prm = no.normalize_to_audio(rows.reshape(-1, 1), 24, dmin, dmax)
+        back = no.denormalize_from_audio(a, dmin, dmax, "float32", 8388607)
+        assert np.array_equal(out[0, r0:r0 + 8].cpu().numpy().reshape(-1, 1), back)
+        assert np.abs(back.reshape(rows.shape).astype(np.float64) - rows).max() <= (dmax - dmin) / 8388607.0
 
 
 def test_two_band_raster_mid_side_tiles(nat, oracle, torch_cuda):
@@ -764,3 +777,99 @@ def test_constant_division_is_exact(nat, torch_cuda):
         bad = C.c_uint64(123)
         nat.check(L.frb_selftest_division(scale, lo, hi, C.byref(bad), None), "frb_selftest_division")
         assert bad.value == 0, (scale, bad.value)
+
+
+# ------------------------------------------------------------------ round 2: legacy reader, aliasing, big batches, C5 via the public API
+def test_legacy_spatial_reader_on_reference_golden(nat, oracle):
+    """the reference's own legacy --spatial file (gzip+base64 index without a marker tag, STALE byte offsets
+    because mutagen grew stream 0 afterwards) opens, and every tile equals oracle decode + reference denormalise
+    with the file's global min/max (all the information a legacy file keeps)."""
+    from flac_raster_b200 import SpatialFLACStreamer, flacfmt
+    from oracle import normalization_oracle as no
+    path = GOLDEN / "sample_dem.flac"
+    blob = path.read_bytes()
+    s = SpatialFLACStreamer(path)
+    assert [(f.byte_offset, f.byte_size) for f in s.spatial_index.frames] == [(0, 10426), (10426, 8454), (18880, 8454), (27334, 8454)]
+    for i, f in enumerate(s.spatial_index.frames):
+        tile, meta = s.get_tile_by_id(i)
+        pcm, info = oracle.decode(blob[f.byte_offset:f.byte_offset + f.byte_size])
+        want = no.denormalize_from_audio(pcm.reshape(1, 256, 256), 577.0, 1493.0, "int16", 8388607)
+        assert tile.dtype == np.int16 and tile.shape == (1, 256, 256) and np.array_equal(tile, want)
+        assert meta["frame_id"] == i and meta["width"] == 256 and meta["data_min"] == 577.0
+    allt = s.get_tiles_by_bbox(-200.0, -90.0, 200.0, 90.0)
+    assert [m["frame_id"] for _, m in allt] == [0, 1, 2, 3]
+
+
+def test_decoded_tiles_do_not_alias_the_staging_buffer(nat, tmp_path):
+    """arrays handed to the caller must survive the next decode call."""
+    from flac_raster_b200 import SpatialFLACEncoder, SpatialFLACStreamer
+    from flac_raster_b200.tiffio import read_geotiff
+    src = read_geotiff(GOLDEN / "sample_dem.tif").data
+    out = tmp_path / "s.flac"
+    SpatialFLACEncoder(tile_size=256).encode(GOLDEN / "sample_dem.tif", out, streaming=True)
+    s = SpatialFLACStreamer(out)
+    a, _ = s.get_tile_by_id(1)
+    a_copy = a.copy()
+    b, _ = s.get_tile_by_id(2)
+    assert not np.shares_memory(a, b)
+    assert np.array_equal(a, a_copy) and np.array_equal(a, src[:, :256, 256:]) and np.array_equal(b, src[:, 256:, :256])
+    res = s.get_tiles_by_bbox(-1e9, -1e9, 1e9, 1e9)
+    keep = [t.copy() for t, _ in res]
+    s.get_tile_by_id(3)
+    assert all(np.array_equal(t, k) for (t, _), k in zip(res, keep))
+
+
+def test_more_than_65535_tiles_in_one_batch(nat, torch_cuda):
+    """the tile / stream index must not live in gridDim.y.  70 000 tiles of 16x16 in one batched call."""
+    torch = torch_cuda
+    from flac_raster_b200.engine import default_engine, tile_grid
+    eng = default_engine()
+    H, W = 16 * 280, 16 * 250
+    g = torch.Generator(device="cuda").manual_seed(5)
+    raster = (torch.randint(0, 4000, (1, H, W), generator=g, device="cuda", dtype=torch.int32)
+              + (torch.arange(W, device="cuda", dtype=torch.int32) // 7)[None, None, :]).to(torch.int16)
+    tiles = tile_grid(H, W, 16)
+    assert len(tiles) == 70000
+    enc = eng.encode_tiles(raster, tiles, 5)
+    payload = torch.cat([enc.payload, torch.zeros(64, dtype=torch.uint8, device="cuda")])
+    out = torch.zeros_like(raster)
+    st = eng.decode_tiles(payload, enc.offsets, enc.sizes, tiles, enc.sample_rates, enc.minmax, 32767.0, out, 16, 4096)
+    assert list(st[:3]) == [0, 0, 0] and st[3] == 70000
+    assert torch.equal(out, raster)
+
+
+def test_config5_bbox_over_4096_tiles_through_the_public_api(nat, torch_cuda, tmp_path):
+    """BASELINE.json configs[4] through the product path: a 4096-tile container of 512x512 int16 written by the sharded
+    writer, SpatialFLACStreamer.get_tiles_by_bbox over all of it (FRB_TEST_TILES shrinks it), every tile compared with the
+    source, and the rank-split form (shard=(r, 4)) returning disjoint contiguous shares."""
+    torch = torch_cuda
+    import shutil
+    import tempfile
+    from flac_raster_b200 import SpatialFLACStreamer
+    from flac_raster_b200.distributed import encode_streaming_sharded
+    from flac_raster_b200.engine import default_engine
+    from flac_raster_b200.synth import dem_int16_tiles
+    n = int(os.environ.get("FRB_TEST_TILES", "4096"))
+    T = 512
+    raster = dem_int16_tiles(n, T)
+    d = tempfile.mkdtemp(prefix="frb_c5_", dir="/dev/shm" if os.path.isdir("/dev/shm") else str(tmp_path))
+    try:
+        path = os.path.join(d, "c5.flac")
+        H = n * T
+        index, enc, _ = encode_streaming_sharded(raster, 0, (1, H, T), (1.0, 0.0, 0.0, 0.0, -1.0, float(H)), "EPSG:32633", None, "int16",
+                                                 T, 5, path, 0, 1, engine=default_engine())
+        s = SpatialFLACStreamer(path)
+        res = s.get_tiles_by_bbox(-1.0, -1.0, T + 1.0, H + 1.0)
+        assert [m["frame_id"] for _, m in res] == list(range(n))
+        host = raster.cpu().numpy()
+        for k, (tile, m) in enumerate(res):
+            assert tile.shape == (1, T, T) and np.array_equal(tile, host[:, k * T:(k + 1) * T])
+        del res
+        shares = [s.get_tiles_by_bbox(-1.0, -1.0, T + 1.0, H + 1.0, shard=(r, 4)) for r in range(4)]
+        ids = [m["frame_id"] for sh in shares for _, m in sh]
+        assert ids == list(range(n)) and max(len(sh) for sh in shares) - min(len(sh) for sh in shares) <= 1
+        # a bbox over part of the column: tiles 10..19 (strict intersection, cli.py:273-278)
+        part = s.get_tiles_by_bbox(0.0, H - 20 * T + 0.5, T, H - 10 * T - 0.5)
+        assert [m["frame_id"] for _, m in part] == list(range(10, 20))
+    finally:
+        shutil.rmtree(d, ignore_errors=True)

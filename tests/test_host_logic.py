@@ -18,7 +18,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     hdr = (ROOT / "include" / "flacraster_b200.h").read_text()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     declared = set(re.findall(r"\b(frb_[a-z0-9_]+)\s*\(", hdr))
-    declared -= {"frb_encoder_write_cb"}
+    declared = {d for d in declared if not d.endswith("_cb")}          # callback typedefs
     assert len(declared) >= 30
     lib = ctypes.CDLL(str(nat.LIB_PATH))
     missing = [n for n in sorted(declared) if not hasattr(lib, n)]
@@ -200,3 +200,68 @@ def test_numa_binding_is_best_effort():
     assert node is None or isinstance(node, int)
     if node is None:
         assert os.sched_getaffinity(0) == before
+
+
+def test_legacy_index_of_reference_golden_loads_and_offsets_are_repaired():
+    """SURVEY Q6 / 8(f)4 (index part, no decode): the reference's legacy golden stores its index as base64(gzip(json)) with
+    no marker tag and with byte offsets that went stale when mutagen grew stream 0; the streamer repairs them."""
+    from flac_raster_b200 import flacfmt
+    from flac_raster_b200.spatial_encoder import SpatialFLACStreamer
+    path = GOLDEN / "sample_dem.flac"
+    blob = path.read_bytes()
+    s = SpatialFLACStreamer(path)
+    fr = s.spatial_index.frames
+    assert [(f.frame_id, f.byte_offset, f.byte_size) for f in fr] == [(0, 0, 10426), (1, 10426, 8454), (2, 18880, 8454), (3, 27334, 8454)]
+    assert sum(f.byte_size for f in fr) == len(blob) == s.spatial_index.total_bytes
+    for f in fr:
+        h = flacfmt.parse_header(blob[f.byte_offset:f.byte_offset + f.byte_size])
+        md = s._legacy_tile_metadata(f, h.streaminfo)
+        assert (md["width"], md["height"], md["count"], md["dtype"], md["data_min"], md["data_max"]) == (256, 256, 1, "int16", 577.0, 1493.0)
+        assert md["transform"][2] == -105.5 + f.window.col_off * 0.001 and md["transform"][5] == 40.5 - f.window.row_off * 0.001
+    assert s.get_byte_ranges_for_bbox((-200, -90, 200, 90)) == [(0, len(blob) - 1)]
+
+
+def test_legacy_index_plain_json_and_delta_repair(tmp_path):
+    """Plain-JSON index text is accepted as well, and when the marker count does not match the index (a tile stream that
+    happens to be missing) the growth of stream 0 alone repairs the later offsets."""
+    from flac_raster_b200 import flacfmt
+    from flac_raster_b200.spatial_encoder import SpatialFLACStreamer
+    si = flacfmt.StreamInfo(4096, 4096, 0, 0, 44100, 1, 16, 0)
+    body = [bytes([0xFF, 0xF8, i]) * (40 + i) for i in range(3)]
+    plain = [flacfmt.build_header(si) + b for b in body]                     # what was appended while offsets were recorded
+    offs, frames = 0, []
+    for i, p in enumerate(plain):
+        frames.append({"frame_id": i, "bbox": [i, 0.0, i + 1.0, 1.0], "window": {"row_off": 0, "col_off": i, "height": 1, "width": 1},
+                       "byte_offset": offs, "byte_size": len(p)})
+        offs += len(p)
+    index = json.dumps({"crs": "EPSG:4326", "transform": [1, 0, 0, 0, -1, 1, 0, 0, 1], "frames": frames})
+    tagged0 = flacfmt.build_header(si, {"GEOSPATIAL_CRS": "EPSG:4326", "GEOSPATIAL_SPATIAL_INDEX": index}, padding=333) + body[0]
+    f = tmp_path / "legacy.flac"
+    f.write_bytes(tagged0 + plain[1] + plain[2])
+    s = SpatialFLACStreamer(f)
+    blob = f.read_bytes()
+    got = [(fr.byte_offset, fr.byte_size) for fr in s.spatial_index.frames]
+    assert got == [(0, len(tagged0)), (len(tagged0), len(plain[1])), (len(tagged0) + len(plain[1]), len(plain[2]))]
+    assert all(blob[o:o + 4] == b"fLaC" for o, _ in got)
+    # index lists only two of the three streams: shift by the growth of stream 0
+    index2 = json.dumps({"crs": "EPSG:4326", "transform": [1, 0, 0, 0, -1, 1, 0, 0, 1], "frames": frames[:2]})
+    tagged0 = flacfmt.build_header(si, {"GEOSPATIAL_CRS": "EPSG:4326", "GEOSPATIAL_SPATIAL_INDEX": index2}) + body[0]
+    f.write_bytes(tagged0 + plain[1] + plain[2])
+    s = SpatialFLACStreamer(f)
+    assert [(fr.byte_offset, fr.byte_size) for fr in s.spatial_index.frames] == [(0, len(tagged0)), (len(tagged0), len(plain[1]))]
+
+
+def test_shard_plan_covers_every_tile_once():
+    from flac_raster_b200.distributed import rows_of_shard, shard_plan, shard_range
+    for world in (1, 2, 3, 8, 130):
+        seen = []
+        for r in range(world):
+            tiles, (a, b), (r0, r1) = shard_plan(10980, 10980, 1024, r, world)
+            seen += list(range(a, b))
+            if b > a:
+                assert r0 == int(tiles[a]["row_off"]) and r1 == int(tiles[b - 1]["row_off"]) + int(tiles[b - 1]["h"])
+                assert (r1 - r0) <= 1024 * (2 + (b - a) // 11)
+            else:
+                assert (r0, r1) == (0, 0)
+        assert seen == list(range(121))
+    assert [shard_range(121, r, 8) for r in (0, 7)] == [(0, 16), (106, 121)]
