@@ -179,7 +179,7 @@ def lib():
     L.frb_stream_encoder_set_total_samples_estimate.argtypes = [vp, u64]
     for name in ("verify", "streamable_subset", "limit_min_bitrate"):
         getattr(L, f"frb_stream_encoder_set_{name}").argtypes = [vp, i32]
-    L.frb_stream_encoder_init_stream.argtypes = [vp, WRITE_CB, ENC_SEEK_CB, ENC_TELL_CB, ENC_METADATA_CB, vp]
+    L.frb_stream_encoder_init_stream.argtypes = [vp, vp, vp, vp, vp, vp]      # callbacks may be NULL: pass cb_ptr(cb)
     L.frb_stream_encoder_process_interleaved.argtypes = [vp, vp, u32]
     L.frb_stream_encoder_process.argtypes = [vp, vp, u32]
     L.frb_stream_encoder_finish.argtypes = [vp]
@@ -188,8 +188,8 @@ def lib():
     L.frb_stream_decoder_new.restype = vp
     L.frb_stream_decoder_delete.argtypes = [vp]
     L.frb_stream_decoder_delete.restype = None
-    L.frb_stream_decoder_init_stream.argtypes = [vp, DEC_READ_CB, vp, vp, vp, vp, DEC_WRITE_CB, DEC_METADATA_CB, DEC_ERROR_CB, vp]
-    L.frb_stream_decoder_init_file.argtypes = [vp, C.c_char_p, DEC_WRITE_CB, DEC_METADATA_CB, DEC_ERROR_CB, vp]
+    L.frb_stream_decoder_init_stream.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.frb_stream_decoder_init_file.argtypes = [vp, C.c_char_p, vp, vp, vp, vp]
     for name in ("process_until_end_of_metadata", "process_until_end_of_stream", "finish", "get_state"):
         getattr(L, f"frb_stream_decoder_{name}").argtypes = [vp]
     for name in ("get_channels", "get_bits_per_sample", "get_sample_rate", "get_blocksize"):
@@ -201,6 +201,11 @@ def lib():
         getattr(L, name)          # AttributeError if a declared symbol is not exported
     _lib = L
     return L
+
+
+def cb_ptr(cb):
+    """A ctypes callback object (or None) as the void* the handle API takes (NULL = callback not given)."""
+    return None if cb is None else C.cast(cb, C.c_void_p)
 
 
 def check(status: int, where: str):

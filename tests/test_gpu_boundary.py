@@ -62,7 +62,8 @@ def _encode_with_handle(nat, pcm, bps, rate, level, seekable=False, verify=False
         assert L.frb_stream_encoder_set_blocksize(e, 4096) == 1
         assert L.frb_stream_encoder_set_streamable_subset(e, 1) == 1
         assert L.frb_stream_encoder_set_limit_min_bitrate(e, 0) == 1
-        rc = L.frb_stream_encoder_init_stream(e, w, s_ if seekable else None, t_ if seekable else None, m_ if seekable else None, None)
+        P = nat.cb_ptr
+        rc = L.frb_stream_encoder_init_stream(e, P(w), P(s_) if seekable else None, P(t_) if seekable else None, P(m_) if seekable else None, None)
         assert rc == 0 and L.frb_stream_encoder_get_state(e) == 0
         assert L.frb_stream_encoder_set_channels(e, 2) == 0               # setters are refused once initialised (libFLAC)
         x = np.ascontiguousarray(pcm, dtype=np.int32)
@@ -119,13 +120,13 @@ def test_encoder_handle_rejects_bad_settings(nat):
                                 ("limit_min_bitrate", 1, 1)):
         e = L.frb_stream_encoder_new()
         getattr(L, f"frb_stream_encoder_set_{setter}")(e, value)
-        assert L.frb_stream_encoder_init_stream(e, w, None, None, None, None) == want, setter
+        assert L.frb_stream_encoder_init_stream(e, nat.cb_ptr(w), None, None, None, None) == want, setter
         assert L.frb_stream_encoder_process_interleaved(e, None, 0) == 0     # not initialised
         L.frb_stream_encoder_delete(e)
     e = L.frb_stream_encoder_new()
     assert L.frb_stream_encoder_init_stream(e, None, None, None, None, None) == 3    # INVALID_CALLBACKS
-    assert L.frb_stream_encoder_init_stream(e, w, None, None, None, None) == 0
-    assert L.frb_stream_encoder_init_stream(e, w, None, None, None, None) == 13      # ALREADY_INITIALIZED
+    assert L.frb_stream_encoder_init_stream(e, nat.cb_ptr(w), None, None, None, None) == 0
+    assert L.frb_stream_encoder_init_stream(e, nat.cb_ptr(w), None, None, None, None) == 13      # ALREADY_INITIALIZED
     assert L.frb_stream_encoder_finish(e) == 1                                        # no samples: header only
     L.frb_stream_encoder_delete(e)
 
@@ -161,9 +162,9 @@ def _decode_with_handle(nat, path=None, data=None, abort_after=None):
     try:
         assert L.frb_stream_decoder_get_state(d) == 9                         # UNINITIALIZED
         if path is not None:
-            rc = L.frb_stream_decoder_init_file(d, str(path).encode(), w, m, er, None)
+            rc = L.frb_stream_decoder_init_file(d, str(path).encode(), nat.cb_ptr(w), nat.cb_ptr(m), nat.cb_ptr(er), None)
         else:
-            rc = L.frb_stream_decoder_init_stream(d, r, None, None, None, None, w, m, er, None)
+            rc = L.frb_stream_decoder_init_stream(d, nat.cb_ptr(r), None, None, None, None, nat.cb_ptr(w), nat.cb_ptr(m), nat.cb_ptr(er), None)
         if rc != 0:
             return rc, None, None, frames, metas, errors, None
         ok = L.frb_stream_decoder_process_until_end_of_stream(d)
