@@ -473,16 +473,38 @@ def run_ours(args, rank, world, local):
     out = torch.zeros(raster.numel() * raster.element_size(), dtype=torch.uint8, device=dev).view(raster.dtype).reshape(raster.shape)
     scale = 32767.0 if enc.bits_per_sample == 16 else 8388607.0
 
-    def decode_step():
-        # frames -> raster in one fused launch (sync scan, then skim + Rice decode + predictor restore + denormalise; CRC-16
-        # beside it); the status read-back is part of the step
-        return eng.decode_tiles(payload, enc.offsets, enc.sizes, tiles, enc.sample_rates, enc.minmax, scale, out, enc.bps, enc.blocksize)
+    def decode_step(index=enc.index()):
+        # frames -> raster in one fused launch (Rice decode + predictor restore + denormalise, CRC-16 beside it); the status
+        # read-back is part of the step.  Streams written by this engine carry their seek index (frame sizes + subframe bit
+        # offsets, the "frbI" block of the container): no sync scan, no walk for subframe starts.  index=None is the path
+        # for foreign streams (reference / libFLAC files): sync scan + skim CTAs inside the launch.
+        return eng.decode_tiles(payload, enc.offsets, enc.sizes, tiles, enc.sample_rates, enc.minmax, scale, out, enc.bps, enc.blocksize,
+                                index=index)
 
+    for _ in range(args.warmup):
+        st = decode_step(None)
+    assert list(st[:3]) == [0, 0, 0], f"decode status {st}"
+    foreign_ok = all(bool(torch.equal(out[:, int(t["row_off"]):int(t["row_off"] + t["h"]), int(t["col_off"]):int(t["col_off"] + t["w"])],
+                                      raster[:, int(t["row_off"]):int(t["row_off"] + t["h"]), int(t["col_off"]):int(t["col_off"] + t["w"])]))
+                     for t in tiles) if enc.bits_per_sample == 16 else None
+    barrier()
+    evf0, evf1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evf0.record()
+    for _ in range(args.steps):
+        decode_step(None)
+        prof(dec_prof, {"k_decode_subframes_scan_path": 1, "k_sync_scan": 3})
+    evf1.record()
+    barrier()
+    dec_foreign_ms = evf0.elapsed_time(evf1) / args.steps
+    out.zero_()
     for _ in range(args.warmup):
         st = decode_step()
     assert list(st[:3]) == [0, 0, 0], f"decode status {st}"
     if enc.bits_per_sample == 16:
-        lossless = bool(torch.equal(out.reshape(-1).view(torch.uint8), raster.reshape(-1).view(torch.uint8)))
+        # pixel for pixel inside this rank's tiles (its slab also holds rows of neighbouring ranks' tiles, which stay zero in `out`)
+        lossless = all(bool(torch.equal(out[:, int(t["row_off"]):int(t["row_off"] + t["h"]), int(t["col_off"]):int(t["col_off"] + t["w"])].view(torch.int16),
+                                        raster[:, int(t["row_off"]):int(t["row_off"] + t["h"]), int(t["col_off"]):int(t["col_off"] + t["w"])].view(torch.int16)))
+                       for t in tiles)
     else:
         # 32-bps streams (float32 / int32 rasters quantised to 24 bits): lossless means the decoded samples equal
         # the normalised samples that went into the encoder, compared on the device
@@ -498,7 +520,7 @@ def run_ours(args, rank, world, local):
     ev2.record()
     for _ in range(args.steps):
         decode_step()
-        prof(dec_prof, {"k_decode_subframes": 1, "k_skim_subframes": 5, "k_sync_scan": 3})
+        prof(dec_prof, {"k_decode_subframes": 1})
     ev3.record()
     barrier()
     dec_launches = L.frb_launch_count() - dlaunch0
@@ -539,7 +561,7 @@ def run_ours(args, rank, world, local):
 
     def dec_e2e_step():
         return eng.decode_tiles_host(host_payload, enc.offsets, enc.sizes, tiles, enc.sample_rates, enc.minmax, scale, host_back,
-                                     enc.bps, enc.blocksize)
+                                     enc.bps, enc.blocksize, index=enc.index())
 
     dec_e2e_ms = None
     if nb != 2:
@@ -595,14 +617,15 @@ def run_ours(args, rank, world, local):
 
     # ---- reduce over ranks (max time) -------------------------------------------------------------
     t = torch.tensor([enc_ms, dec_ms, e2e_ms, dec_e2e_ms or 0.0, weak or 0.0, enc_wall_ms,
-                      (c5 or {}).get("ms", 0.0) or 0.0], dtype=torch.float64, device=dev)
+                      (c5 or {}).get("ms", 0.0) or 0.0, dec_foreign_ms], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(samples_local), float(launches), float(comp_bytes), float(nout)], dtype=torch.float64, device=dev)
-    tmin = t.clone()
+    tmin = torch.cat([t, torch.tensor([1.0 if lossless else 0.0], dtype=torch.float64, device=dev)])
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    enc_ms, dec_ms, e2e_ms, dec_e2e_ms, weak_ms, enc_wall_ms, c5_ms = (float(v) for v in t.cpu())
+    lossless = bool(float(tmin[-1]) == 1.0)                 # every rank's tiles
+    enc_ms, dec_ms, e2e_ms, dec_e2e_ms, weak_ms, enc_wall_ms, c5_ms, dec_foreign_ms = (float(v) for v in t.cpu())
     enc_ms_min = float(tmin[0])
     total_samples = float(tot[0])
     comp_total, nout_total = int(tot[2]), int(tot[3])
@@ -679,6 +702,10 @@ def run_ours(args, rank, world, local):
         "rank_ms": {"encode_max": enc_ms, "encode_min": enc_ms_min, "encode_wall_max": enc_wall_ms},
         "decode": {"value": total_samples / (dec_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": dec_ms,
                    "gpu_launches": int(dec_launches),
+                   "path": "streams of this engine: seek index from the container (frame sizes + subframe bit offsets), no sync scan, no skim",
+                   "foreign_streams": {"value": total_samples / (dec_foreign_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": dec_foreign_ms,
+                                       "lossless": foreign_ok,
+                                       "path": "no index (reference / libFLAC-made files): sync scan + skim CTAs that walk the Rice codes for the subframe starts"},
                    "e2e": ({"value": total_samples / (dec_e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": dec_e2e_ms,
                             "h2d_bytes_per_step": comp_total, "d2h_bytes_per_step": int(total_samples) * raster_elem_size(args.workload)}
                            if dec_e2e_ms else None),

@@ -80,8 +80,9 @@ _EXPORTS = [
     "frb_profile_enable", "frb_profile_last_ms", "frb_small_upload", "frb_small_download",
     "frb_minmax_tiles", "frb_normalize_tiles", "frb_denormalize_tiles", "frb_sample_map_workspace_size",
     "frb_minmax_flat", "frb_normalize_flat", "frb_denormalize_flat", "frb_selftest_division",
-    "frb_encode_workspace_size", "frb_encode_analyse", "frb_encode_emit",
-    "frb_decode_workspace_size", "frb_decode_batch", "frb_decode_tiles", "frb_probe_stream",
+    "frb_encode_workspace_size", "frb_encode_analyse", "frb_encode_emit", "frb_encode_index",
+    "frb_decode_workspace_size", "frb_decode_batch", "frb_decode_tiles", "frb_decode_batch_indexed", "frb_decode_tiles_indexed",
+    "frb_probe_stream",
     "frb_host_encode", "frb_host_decode",
     "frb_stream_encoder_new", "frb_stream_encoder_delete", "frb_stream_encoder_set_channels",
     "frb_stream_encoder_set_bits_per_sample", "frb_stream_encoder_set_sample_rate",
@@ -143,6 +144,20 @@ def lib():
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(flac_raster_b200 has no CPU fallback)")
     L = C.CDLL(str(LIB_PATH))
+    if os.environ.get("FRB_LIB_PATH"):
+        # kernel-variant experiments (tools/var_sweep.sh) may load an older build: symbols it lacks resolve to a stub that raises
+        class _Tolerant:
+            def __init__(self, lib):
+                object.__setattr__(self, "_l", lib)
+
+            def __getattr__(self, name):
+                try:
+                    return getattr(self._l, name)
+                except AttributeError:
+                    def missing(*a, **k):
+                        raise NativeError(ERR_UNSUPPORTED, name, "not exported by the FRB_LIB_PATH variant build")
+                    return missing
+        L = _Tolerant(L)
     vp, u32, u64, i32, sz = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_size_t
     L.frb_version.restype = i32
     L.frb_error_string.restype = C.c_char_p
@@ -163,6 +178,9 @@ def lib():
     L.frb_encode_workspace_size.argtypes = [C.POINTER(EncodeParams), u64, C.POINTER(sz)]
     L.frb_encode_analyse.argtypes = [C.POINTER(EncodeParams), vp, vp, vp, vp, vp, sz, vp, vp, vp]
     L.frb_encode_emit.argtypes = [C.POINTER(EncodeParams), vp, sz, vp, vp, sz, vp, vp]
+    L.frb_encode_index.argtypes = [C.POINTER(EncodeParams), vp, sz, vp, vp, vp]
+    L.frb_decode_batch_indexed.argtypes = [C.POINTER(DecodeParams), vp, vp, u64, vp, vp, vp, vp, sz, vp, vp]
+    L.frb_decode_tiles_indexed.argtypes = [C.POINTER(DecodeParams), vp, vp, u64, vp, vp, vp, vp, C.c_double, vp, C.c_int, u32, u32, u32, vp, sz, vp, vp]
     L.frb_decode_workspace_size.argtypes = [C.POINTER(DecodeParams), u64, C.POINTER(sz)]
     L.frb_decode_batch.argtypes = [C.POINTER(DecodeParams), vp, vp, u64, vp, vp, sz, vp, vp]
     L.frb_decode_tiles.argtypes = [C.POINTER(DecodeParams), vp, vp, u64, vp, vp, C.c_double, vp, C.c_int, u32, u32, u32, vp, sz, vp, vp]

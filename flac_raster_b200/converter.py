@@ -92,11 +92,11 @@ def tile_metadata(width, height, count, dtype, crs, transform, data_min, data_ma
 
 
 def build_flac_file(frames: bytes, n_samples: int, channels: int, bps: int, sample_rate: int, blocksize: int,
-                    metadata: Optional[Dict], padding: int = 0) -> bytes:
-    """STREAMINFO + VORBIS tags (+ padding) + frames: one standalone FLAC file."""
+                    metadata: Optional[Dict], padding: int = 0, seek_index: Optional[bytes] = None) -> bytes:
+    """STREAMINFO + VORBIS tags (+ seek index) (+ padding) + frames: one standalone FLAC file."""
     si = flacfmt.StreamInfo(blocksize, blocksize, 0, 0, sample_rate, channels, bps, n_samples)
     tags = metadata_tags(metadata) if metadata else {}
-    return flacfmt.build_header(si, tags, padding=padding) + bytes(frames)
+    return flacfmt.build_header(si, tags, padding=padding, seek_index=seek_index) + bytes(frames)
 
 
 class RasterFLACConverter:
@@ -145,8 +145,12 @@ class RasterFLACConverter:
         scale = 32767 if enc.bits_per_sample == 16 else 8388607
         md = tile_metadata(W, H, bands, arr.dtype, crs, transform, float(enc.minmax[0, 0]), float(enc.minmax[0, 1]),
                            nodata, scale)
+        sidx = None
+        if enc.frame_bytes is not None:
+            sidx = flacfmt.pack_seek_index(bands, enc.blocksize, enc.frame_bytes.cpu().numpy().view(np.uint32),
+                                           enc.sub_bitoff.cpu().numpy().view(np.uint32))
         blob = build_flac_file(frames, int(enc.n_samples[0]), bands, enc.bps, int(enc.sample_rates[0]), enc.blocksize,
-                               md, padding=1024)
+                               md, padding=1024, seek_index=sidx)
         Path(flac_path).write_bytes(blob)
         return None
 
@@ -222,6 +226,7 @@ def decode_tile_blobs(blobs, headers, metadatas, mosaic=None, staged=None):
     row = 0
     maxw = 0
     bodies = []
+    idx_fb, idx_sb = [], []          # seek index of every tile ("frbI" block); None as soon as one tile has none
     for i, (b, h, md) in enumerate(zip(blobs, headers, metadatas)):
         si = h.streaminfo
         if (si.channels, si.bits_per_sample, si.max_blocksize) != (channels, bps, blocksize):
@@ -236,6 +241,14 @@ def decode_tile_blobs(blobs, headers, metadatas, mosaic=None, staged=None):
         else:
             offs[i], lens[i] = int(staged[2][i]) + h.first_frame_offset, len(b) - h.first_frame_offset
         nsamp[i] = md["width"] * md["height"]
+        if idx_fb is not None:
+            blk = h.applications.get(flacfmt.SEEK_INDEX_ID) if getattr(h, "applications", None) else None
+            got = flacfmt.unpack_seek_index(blk, channels, blocksize, (int(nsamp[i]) + blocksize - 1) // blocksize) if blk else None
+            if got is None:
+                idx_fb = idx_sb = None
+            else:
+                idx_fb.append(got[0])
+                idx_sb.append(got[1])
         rates[i] = si.sample_rate
         tiles[i] = (row, 0, md["height"], md["width"])
         row += md["height"]
@@ -265,7 +278,10 @@ def decode_tile_blobs(blobs, headers, metadatas, mosaic=None, staged=None):
     out = torch.zeros(channels * row * maxw * dtype.itemsize, dtype=torch.uint8, device=eng.device)
     out = out.view(TORCH_DTYPES[str(dtype)]).reshape(channels, row, maxw)
     # one fused launch: Rice decode + predictor restore + denormalise straight into the tile windows
-    status = eng.decode_tiles(data, offs, lens, tiles, rates, minmax, scale, out, bps, blocksize)
+    index = None
+    if idx_fb:
+        index = (np.concatenate(idx_fb), np.concatenate(idx_sb) if channels > 1 else None)
+    status = eng.decode_tiles(data, offs, lens, tiles, rates, minmax, scale, out, bps, blocksize, index=index)
     if status[5]:
         raise RuntimeError("decode kernel timed out waiting for a subframe offset")
     if status[0] or status[2]:

@@ -146,6 +146,40 @@ k_sync_scan(const uint8_t *__restrict__ bytes, const DecStreamDev *__restrict__ 
 #include "frb_decode_kernels.cuh"   // bit reader, skim, subframe decode, CRC-16 (inside namespace frb)
 
 
+// Indexed streams: frame positions from the frame sizes of the seek index.  One CTA per stream, chunked block scan.  A
+// stream whose sizes do not add up to its byte length is reported as "frames missing" (status[0]) and left unlocated.
+__global__ void __launch_bounds__(256)
+k_index_frame_pos(const DecStreamDev *__restrict__ streams, const uint32_t *__restrict__ frame_bytes,
+                  unsigned long long *__restrict__ frame_pos, uint32_t *__restrict__ status) {
+    __shared__ unsigned long long s_warp[8];
+    __shared__ unsigned long long s_carry;
+    const DecStreamDev st = streams[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < st.n_frames; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const unsigned long long v = i < st.n_frames ? frame_bytes[st.frame_base + i] : 0ull;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        unsigned long long wbase = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { const unsigned long long x = s_warp[w]; if (w < warp) wbase += x; tot += x; }
+        const unsigned long long carry = s_carry;
+        if (i < st.n_frames) frame_pos[st.frame_base + i] = st.byte_offset + carry + wbase + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && s_carry != st.byte_length) {
+        atomicAdd(&status[0], st.n_frames);
+        for (uint32_t i = 0; i < st.n_frames; i++) frame_pos[st.frame_base + i] = kNoPos;
+    }
+}
+
 // one CTA per frame; only frames with ch_assign 8/9/10 do work
 __global__ void __launch_bounds__(128)
 k_stereo_fix(const DecStreamDev *__restrict__ streams, uint32_t n_streams, uint32_t blocksize, uint32_t total_frames,
@@ -209,7 +243,9 @@ extern "C" int frb_decode_workspace_size(const frb_decode_params *p, uint64_t to
 namespace frb {
 static int decode_batch_impl(const frb_decode_params *p, const frb_decode_stream *h_streams,
                              const uint8_t *d_bytes, uint64_t total_frames, int32_t *d_audio,
-                             void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream, const SinkCfg &sink) {
+                             void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream, const SinkCfg &sink,
+                             const uint32_t *d_frame_bytes = nullptr, const uint32_t *d_index_bitoff = nullptr) {
+    if ((d_frame_bytes == nullptr) != (d_index_bitoff == nullptr) && p && p->channels > 1) return FRB_ERR_INVALID_ARG;
     if (!p || !h_streams || !d_bytes || (!d_audio && sink.dtype < 0) || !d_workspace || !d_status) return FRB_ERR_INVALID_ARG;
     if (p->n_streams == 0 || p->channels < 1 || p->channels > FRB_MAX_CHANNELS || p->blocksize < 16 ||
         p->blocksize > 65535 || p->bps < 4 || p->bps > 32) return FRB_ERR_INVALID_ARG;
@@ -238,9 +274,15 @@ static int decode_batch_impl(const frb_decode_params *p, const frb_decode_stream
     FRB_TRY(small_upload(w.streams, hs.data(), sizeof(DecStreamDev) * hs.size(), s));   // staged in pinned memory before returning
     FRB_TRY(small_fill(d_status, 0u, 8 * sizeof(uint32_t), s));
     FRB_TRY(small_fill(w.chassign, 0u, ((size_t)total_frames + 1 + 3) & ~(size_t)3, s));
+    const bool indexed = d_frame_bytes != nullptr;
+    if (indexed) {
+        // seek index supplied (frb_encode_index / the container's index block): frame positions are a scan of the frame sizes,
+        // no byte of the streams is inspected to find them
+        k_index_frame_pos<<<p->n_streams, 256, 0, s>>>(w.streams, d_frame_bytes, w.frame_pos, d_status);
+        FRB_LAUNCH_CHECK("k_index_frame_pos");
+    } else {
     k_fill_u64<<<grid_for(total_frames + 1, 256 * 4, kNumSMs * 4), 256, 0, s>>>(w.frame_pos, total_frames + 1, kNoPos);
     FRB_LAUNCH_CHECK("k_fill_u64");
-    {
         uint64_t chunks = max_len / 16 + 2;
         uint32_t gx = (uint32_t)((chunks + 256 * 4 - 1) / (256 * 4));
         uint32_t cap = (kNumSMs * 16 + p->n_streams - 1) / p->n_streams;
@@ -288,14 +330,16 @@ static int decode_batch_impl(const frb_decode_params *p, const frb_decode_stream
             const uint32_t frames_per_cta = (kDecThreads / 32) * skim_lanes;
             n_skim_ctas = (uint32_t)((total_frames + frames_per_cta - 1) / frames_per_cta);
             sub_bitoff = w.sub_bitoff;
-            FRB_TRY(small_fill(sub_bitoff, 0xFFFFFFFFu, 4 * (size_t)(total_frames * p->channels), s));
+            if (indexed) { n_skim_ctas = 0; sub_bitoff = const_cast<uint32_t *>(d_index_bitoff); }
+            else FRB_TRY(small_fill(sub_bitoff, 0xFFFFFFFFu, 4 * (size_t)(total_frames * p->channels), s));
         }
         const uint64_t total_sub = total_frames * p->channels;
         const uint32_t grid = n_skim_ctas + (uint32_t)((total_sub + kDecThreads - 1) / kDecThreads);
         const bool big = p->reserved > 12;
         prof_begin(1, s);
 #define FRB_DECODE(BIG, RAS) k_decode_subframes<BIG, RAS><<<grid, kDecThreads, 0, s>>>(d_bytes, w.streams, p->n_streams, p->channels, p->bps, \
-            p->blocksize, (uint32_t)total_frames, w.frame_pos, sub_bitoff, d_audio, w.chassign, d_status, n_skim_ctas, skim_lanes, sink)
+            p->blocksize, (uint32_t)total_frames, w.frame_pos, sub_bitoff, d_audio, w.chassign, d_status, n_skim_ctas, skim_lanes, sink, \
+            indexed ? 1u : 0u)
         if (sink.dtype < 0) { if (big) FRB_DECODE(true, false); else FRB_DECODE(false, false); }
         else { if (big) FRB_DECODE(true, true); else FRB_DECODE(false, true); }
 #undef FRB_DECODE
@@ -321,11 +365,12 @@ extern "C" int frb_decode_batch(const frb_decode_params *p, const frb_decode_str
     return frb::decode_batch_impl(p, h_streams, d_bytes, total_frames, d_audio, d_workspace, workspace_bytes, d_status, stream, sink);
 }
 
-extern "C" int frb_decode_tiles(const frb_decode_params *p, const frb_decode_stream *h_streams,
-                                const uint8_t *d_bytes, uint64_t total_frames,
-                                const frb_tile *d_tiles, const double *d_minmax, double scale,
-                                void *d_raster, int dtype, uint32_t bands, uint32_t H, uint32_t W,
-                                void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream) {
+static int frb_decode_tiles_impl(const frb_decode_params *p, const frb_decode_stream *h_streams,
+                                 const uint8_t *d_bytes, uint64_t total_frames,
+                                 const frb_tile *d_tiles, const double *d_minmax, double scale,
+                                 void *d_raster, int dtype, uint32_t bands, uint32_t H, uint32_t W,
+                                 void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream,
+                                 const uint32_t *d_frame_bytes, const uint32_t *d_sub_bitoff) {
     using namespace frb;
     if (!p || !d_tiles || !d_minmax || !d_raster || dtype < 0 || dtype > FRB_F64 || !(scale > 0.0)) return FRB_ERR_INVALID_ARG;
     if (bands != p->channels) return FRB_ERR_INVALID_ARG;
@@ -338,7 +383,40 @@ extern "C" int frb_decode_tiles(const frb_decode_params *p, const frb_decode_str
     sink.raster = (uint8_t *)d_raster; sink.scale = scale; sink.rcp = 1.0 / scale;
     sink.fast = (scale == 32767.0 || scale == 8388607.0 || scale == 2147483647.0) ? 1 : 0;
     sink.intpath = (dtype <= FRB_I16 && scale == 32767.0) ? 1 : 0;      // integer min/max, range < 2^16, |audio| <= 32767
-    return decode_batch_impl(p, h_streams, d_bytes, total_frames, nullptr, d_workspace, workspace_bytes, d_status, stream, sink);
+    return decode_batch_impl(p, h_streams, d_bytes, total_frames, nullptr, d_workspace, workspace_bytes, d_status, stream, sink,
+                             d_frame_bytes, d_sub_bitoff);
+}
+
+extern "C" int frb_decode_tiles(const frb_decode_params *p, const frb_decode_stream *h_streams,
+                                const uint8_t *d_bytes, uint64_t total_frames,
+                                const frb_tile *d_tiles, const double *d_minmax, double scale,
+                                void *d_raster, int dtype, uint32_t bands, uint32_t H, uint32_t W,
+                                void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream) {
+    return frb_decode_tiles_impl(p, h_streams, d_bytes, total_frames, d_tiles, d_minmax, scale, d_raster, dtype, bands, H, W,
+                                 d_workspace, workspace_bytes, d_status, stream, nullptr, nullptr);
+}
+
+extern "C" int frb_decode_tiles_indexed(const frb_decode_params *p, const frb_decode_stream *h_streams,
+                                        const uint8_t *d_bytes, uint64_t total_frames,
+                                        const uint32_t *d_frame_bytes, const uint32_t *d_sub_bitoff,
+                                        const frb_tile *d_tiles, const double *d_minmax, double scale,
+                                        void *d_raster, int dtype, uint32_t bands, uint32_t H, uint32_t W,
+                                        void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream) {
+    if (!d_frame_bytes || !d_sub_bitoff) return FRB_ERR_INVALID_ARG;
+    return frb_decode_tiles_impl(p, h_streams, d_bytes, total_frames, d_tiles, d_minmax, scale, d_raster, dtype, bands, H, W,
+                                 d_workspace, workspace_bytes, d_status, stream, d_frame_bytes, d_sub_bitoff);
+}
+
+extern "C" int frb_decode_batch_indexed(const frb_decode_params *p, const frb_decode_stream *h_streams,
+                                        const uint8_t *d_bytes, uint64_t total_frames,
+                                        const uint32_t *d_frame_bytes, const uint32_t *d_sub_bitoff, int32_t *d_audio,
+                                        void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream) {
+    if (!d_frame_bytes || !d_sub_bitoff) return FRB_ERR_INVALID_ARG;
+    frb::SinkCfg sink;
+    memset(&sink, 0, sizeof sink);
+    sink.dtype = -1;
+    return frb::decode_batch_impl(p, h_streams, d_bytes, total_frames, d_audio, d_workspace, workspace_bytes, d_status, stream, sink,
+                                  d_frame_bytes, d_sub_bitoff);
 }
 
 #ifdef FRB_DEC_TIMING

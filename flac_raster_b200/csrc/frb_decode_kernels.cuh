@@ -24,13 +24,27 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t smem_addr) {
     return v;
 }
 
-__device__ __forceinline__ int32_t unzigzag(uint32_t u) { return (int32_t)(u >> 1) ^ -(int32_t)(u & 1u); }
+__device__ __forceinline__ int32_t unzigzag(uint32_t u) {
+    int32_t sgn;                                              // -(u & 1): a one-bit signed field extract instead of AND + negate
+    asm("bfe.s32 %0, %1, 0, 1;" : "=r"(sgn) : "r"(u));
+    return (int32_t)(u >> 1) ^ sgn;
+}
 // position of the most significant set bit (0xFFFFFFFF for 0): clz(w) = 31 - bfind(w), so the length of a Rice code with
 // parameter k is (k + 32) - bfind(window) in one subtraction, and 33 + k (> 32, "too long") for an all-zero window
+// Measured on B200 (tools/microbench/lat.cu, dependent chains): bfind/clz/popc ~20 cycles, an integer -> float conversion
+// ~6 cycles, shifts / multiply-adds 4.5, adds 3.  The Rice walk is ONE chain of bfind -> length -> shift per code, so the
+// position of the leading one is taken from the exponent of cvt.rz.f32.u32 (round toward zero: exactly floor(log2 w));
+// w == 0 gives a huge value (0 - 127), like bfind's 0xFFFFFFFF, which the callers read as "code longer than 32 bits".
 __device__ __forceinline__ uint32_t bfind_u32(uint32_t w) {
+#if FRB_BFIND_I2F
+    float f;
+    asm("cvt.rz.f32.u32 %0, %1;" : "=f"(f) : "r"(w));
+    return (__float_as_uint(f) >> 23) - 127u;
+#else
     uint32_t r;
     asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(w));
     return r;
+#endif
 }
 __device__ __forceinline__ uint32_t shr_clamped(uint32_t v, uint32_t s) {      // v >> s with s >= 32 giving 0 (PTX semantics)
     uint32_t r;
@@ -83,8 +97,21 @@ __device__ __forceinline__ FrameLoc locate_frame(const DecStreamDev *__restrict_
 //     predicated 4-byte LDS from the thread's ring, never a wait;
 //   * the ring (16-byte chunks, cp.async) is topped up ONCE per batch at a warp-uniform point with
 //     predicated copies, and one wait_group per batch covers every word the batch can touch.
+#ifndef FRB_SKIM_BATCH
+#define FRB_SKIM_BATCH 8
+#endif
+#ifndef FRB_BFIND_I2F
+#define FRB_BFIND_I2F 1
+#endif
+#ifndef FRB_LPC_NEWEST_LAST
+#define FRB_LPC_NEWEST_LAST 1
+#endif
+#ifndef FRB_DEC_SHIFTWIN
+#define FRB_DEC_SHIFTWIN 0
+#endif
 constexpr int kSkimRing = 16;                                   // 16-byte chunks per thread (256 contiguous bytes)
-constexpr int kSkimBatch = 8;                                   // codes per batch: <= 8 words = 2 chunks
+constexpr int kSkimBatch = FRB_SKIM_BATCH;                      // codes per skim batch: <= kSkimBatch words = kSkimBatch / 4 chunks
+static_assert(kSkimBatch == 8 || kSkimBatch == 16, "the 16-chunk ring feeds batches of 8 or 16 codes");
 
 // Bit reader (skim and decode roles): three consecutive big-endian words of the stream in registers -- A (holds the
 // next unread bit), B, and C still as loaded (raw little-endian) -- plus a running bit position bp.  Only bits 0..4 of
@@ -109,14 +136,24 @@ struct BitReader {
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sbase + (((c & (kSkimRing - 1)) << 4) ^ swz)),
                      "l"(gq + min(c, qlast)) : "memory");
     }
-    __device__ __forceinline__ void top_up() {
+    // Tops the ring up by at most R chunks (R = what a batch of 4 R codes can consume at 32 bits each) without a branch:
+    // predicated copies, so that the compiler can schedule them into the shadow of the Rice chain.  Afterwards at most
+    // N copy groups stay in flight, N chosen so that the R + 1 chunks a batch (plus the skim's look-ahead) can touch are
+    // complete: 15 - N R >= R + 1.
+    template <int R>
+    __device__ __forceinline__ void top_up_n() {
         const uint32_t lim = (woff >> 4) + kSkimRing - 1;
 #pragma unroll
-        for (int r = 0; r < 2; r++)
-            if (cissue < lim) { copy_chunk(cissue); cissue++; }
+        for (int r = 0; r < R; r++) {
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %0, %1;\n\t@p cp.async.cg.shared.global [%2], [%3], 16;\n\t}\n"
+                         ::"r"(cissue), "r"(lim), "r"(sbase + (((cissue & (kSkimRing - 1)) << 4) ^ swz)), "l"(gq + min(cissue, qlast)) : "memory");
+            cissue += cissue < lim ? 1u : 0u;
+        }
         cp_async_commit();
-        cp_async_wait<(kSkimRing - 3) / 2 - 1>();
+        static_assert(R == 2 || R == 4, "ring depth table");
+        cp_async_wait<R == 2 ? 5 : 2>();                         // 15 - N R >= R + 1
     }
+    __device__ __forceinline__ void top_up() { top_up_n<2>(); }
     __device__ __forceinline__ void init(uint32_t ring_saddr, uint32_t lane, const uint8_t *base, uint64_t bitpos, uint64_t byte_end) {
         gq = (const uint4 *)base;
         sbase = ring_saddr;
@@ -193,6 +230,59 @@ struct BitReader {
     }
 };
 
+// Reader of the skim role.  The walk over a frame's Rice codes is ONE dependent chain of ~28 000 codes, and it gates
+// every decode thread of that frame: with few frames in flight (a rank's share of a scene at N = 8, a single tile) the
+// kernel's run time IS this chain (round 2, N = 2: 3.0 ms for half the frames against 3.8 ms for all of them).  The
+// position-based BitReader above minimises instructions, but its chain per code is window -> bfind -> length ->
+// position -> word-crossing test -> select -> window (8 dependent instructions, ~130 cycles per code measured).  Here
+// the next 64 bits live in a shifting register pair (hi, lo) and a BitReader runs 64 bits AHEAD to supply the word that
+// enters at the bottom: the chain per code is bfind -> subtract -> funnel shift; the look-ahead bookkeeping is off it.
+struct SkimReader {
+    BitReader br;            // positioned 64 bits ahead of the read position
+    uint32_t hi, lo;         // bits [pos, pos + 32) and [pos + 32, pos + 64)
+    __device__ __forceinline__ void prime() { hi = br.get(32); lo = br.get(32); }
+    __device__ __forceinline__ void init(uint32_t ring_saddr, uint32_t lane, const uint8_t *base, uint64_t bitpos, uint64_t byte_end) {
+        br.init(ring_saddr, lane, base, bitpos, byte_end);
+        prime();
+    }
+    __device__ __forceinline__ uint64_t bitpos() const { return br.bitpos() - 64u; }
+    __device__ __forceinline__ bool overrun() const { return br.overrun(); }
+    __device__ __forceinline__ void top_up() { br.top_up_n<kSkimBatch / 4>(); }
+    __device__ __forceinline__ uint32_t window() const { return hi; }
+    __device__ __forceinline__ void skip_predicated(uint32_t nb) {     // nb <= 32; branch-free
+        const uint32_t in = br.window();
+        hi = __funnelshift_lc(lo, hi, nb);
+        lo = __funnelshift_lc(in, lo, nb);
+        br.advance_predicated(nb);
+    }
+    __device__ __forceinline__ void skip(uint32_t nb) {               // nb <= 32
+        const uint32_t in = br.window();
+        hi = __funnelshift_lc(lo, hi, nb);
+        lo = __funnelshift_lc(in, lo, nb);
+        br.consume(nb);
+    }
+    __device__ __forceinline__ uint32_t get(uint32_t nb) {            // nb in 0..32
+        const uint32_t v = __funnelshift_lc(hi, 0u, nb);
+        skip(nb);
+        return v;
+    }
+    __device__ __forceinline__ uint32_t unary() {
+        uint32_t q = 0;
+        for (;;) {
+            if (hi) { const uint32_t z = __clz(hi); skip(z + 1); return q + z; }
+            q += 32; skip(32);
+            top_up();
+            if (overrun()) return q;
+        }
+    }
+    __device__ __forceinline__ void seek(const uint8_t *base, uint64_t bits_forward, uint64_t byte_end) {
+        const uint64_t target = bitpos() + bits_forward;
+        cp_async_wait<0>();
+        br.init(br.sbase, br.swz >> 4, base, target, byte_end);
+        prime();
+    }
+};
+
 // Publication protocol (fused skim + decode, see k_decode_subframes): sub_bitoff[] starts as kNotReady (host memset);
 // the skim thread of a frame stores each subframe's bit offset with release semantics as soon as the walk reaches it
 // (0 = bad frame, nothing to decode), the decode thread of that subframe polls it with acquire loads.
@@ -227,9 +317,10 @@ skim_role(uint4 *s_ring, uint32_t cta, const uint8_t *__restrict__ bytes, const 
     uint32_t *off_out = sub_bitoff + (size_t)(done ? 0 : f) * channels;
     uint64_t frame_bit0 = 0;
     uint32_t published = 0;                                   // entries [0, published) of off_out have been stored
-    BitReader br;
-    br.gq = (const uint4 *)bytes; br.sbase = (uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x * kSkimRing); br.swz = (lane & 15u) << 4;
-    br.sx = br.sbase ^ br.swz; br.woff = 12; br.cissue = 0; br.qlast = 0; br.A = br.B = br.Craw = 0; br.bp = 0;
+    SkimReader br;
+    br.br.gq = (const uint4 *)bytes; br.br.sbase = (uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x * kSkimRing); br.br.swz = (lane & 15u) << 4;
+    br.br.sx = br.br.sbase ^ br.br.swz; br.br.woff = 12; br.br.cissue = 0; br.br.qlast = 0; br.br.A = br.br.B = br.br.Craw = 0; br.br.bp = 0;
+    br.hi = br.lo = 0;
     if (lane < lanes_per_warp && f < total_frames && channels > 1) {
         L = locate_frame(streams, n_streams, blocksize, f, frame_pos, &st);
         if (!L.ok) { atomicAdd(&status[0], 1u); done = true; }
@@ -239,7 +330,7 @@ skim_role(uint4 *s_ring, uint32_t cta, const uint8_t *__restrict__ bytes, const 
             frame_bit0 = L.start * 8;
             st_release_u32(off_out, h.header_bytes * 8);
             published = 1;
-            br.init(br.sbase, lane, bytes, frame_bit0 + (uint64_t)h.header_bytes * 8, L.end);
+            br.init(br.br.sbase, lane, bytes, frame_bit0 + (uint64_t)h.header_bytes * 8, L.end);
         }
         if (done) { for (uint32_t q = 0; q < channels; q++) st_release_u32(off_out + q, 0u); published = channels; }
     }
@@ -252,14 +343,14 @@ skim_role(uint4 *s_ring, uint32_t cta, const uint8_t *__restrict__ bytes, const 
         if (left >= (uint32_t)kSkimBatch) {
             // ---- a full batch of Rice codes without data-dependent branches; a code longer than 32 bits (long unary
             // run or corrupt data) is detected once per batch and the batch is then redone one code at a time ----
-            const BitReader snap = br;
+            const SkimReader snap = br;
             const uint32_t kb = k + 32;
             uint32_t maxlen = 0;
 #pragma unroll
             for (int i = 0; i < kSkimBatch; i++) {
                 const uint32_t len = kb - bfind_u32(br.window());
                 maxlen = max(maxlen, len);
-                br.advance_predicated(len);
+                br.skip_predicated(len);
             }
             if (maxlen <= 32) { left -= kSkimBatch; continue; }
             br = snap;
@@ -278,7 +369,7 @@ skim_role(uint4 *s_ring, uint32_t cta, const uint8_t *__restrict__ bytes, const 
                     len = k;
                     if (br.overrun()) { err = true; len = 0; }
                 }
-                br.consume(active ? len : 0u);
+                br.skip(active ? len : 0u);
             }
             left -= m;
             if (err) done = true;
@@ -357,6 +448,21 @@ skim_role(uint4 *s_ring, uint32_t cta, const uint8_t *__restrict__ bytes, const 
 template <int MAXORD, bool WIDE>
 __device__ __forceinline__ int32_t lpc_predict(const int32_t (&cf)[MAXORD], const int32_t *Hj, int shift) {
     // Hj points at the newest history sample; taps walk backwards (static indices after unrolling)
+#if FRB_LPC_NEWEST_LAST
+    // oldest tap first: inside a batch the newest sample is the one just reconstructed, and with it last only one
+    // multiply-add of the next sample waits for it
+    if (WIDE) {
+        long long acc = 0;
+#pragma unroll
+        for (int q = MAXORD - 1; q >= 0; q--) acc += (long long)cf[q] * (long long)Hj[-q];
+        return (int32_t)(acc >> shift);
+    } else {
+        int32_t acc = 0;
+#pragma unroll
+        for (int q = MAXORD - 1; q >= 0; q--) acc += cf[q] * Hj[-q];
+        return acc >> shift;
+    }
+#else
     if (WIDE) {
         long long acc = 0;
 #pragma unroll
@@ -368,6 +474,7 @@ __device__ __forceinline__ int32_t lpc_predict(const int32_t (&cf)[MAXORD], cons
         for (int q = 0; q < MAXORD; q++) acc += cf[q] * Hj[-q];
         return acc >> shift;
     }
+#endif
 }
 
 // Optional fused denormalise: instead of the planar int32 audio buffer, a decode thread can write its samples straight
@@ -461,29 +568,50 @@ __device__ __forceinline__ void sink_advance(RasterPos &R, uint32_t n) {
                             (R).mn, (R).range, (R).imn, (R).irange, (R).kround, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);   \
         sink_advance(R, kDecBatch);                                                                                              \
     } while (0)
+// Rare paths of the 8/16-bit integer sink, out of line (one call site each) so that the hot loop stays small:
+//  * a sample sits on an exact rounding tie: the whole batch is redone with the tied samples through the fp64 formula;
+//  * the batch straddles the end of a tile row (edge tiles whose width is not a multiple of 8: their 32 frames per warp
+//    reach row ends in different trips, so SOME lane is here in a quarter of the trips): element stores with the row
+//    step in between -- ~50 instructions instead of the generic sample-by-sample path (~300).
+__device__ __noinline__ uint4 sink_fix_ties(double scale, double rcp, int32_t imn, uint32_t irange, uint32_t kround, int shift16,
+                                            int32_t a0, int32_t a1, int32_t a2, int32_t a3, int32_t a4, int32_t a5, int32_t a6, int32_t a7) {
+    const int32_t a[8] = {a0, a1, a2, a3, a4, a5, a6, a7};
+    uint32_t v[8];
+#pragma unroll 1
+    for (int j = 0; j < 8; j++) {
+        const uint32_t N = (uint32_t)a[j] * irange + kround;
+        const uint32_t q = N / 65534u;
+        v[j] = (N - q * 65534u) == 0u ? sink_px_tie(scale, rcp, imn, irange, a[j]) : (uint32_t)imn + q;
+    }
+    if (shift16) return make_uint4(__byte_perm(v[0], v[1], 0x5410), __byte_perm(v[2], v[3], 0x5410), __byte_perm(v[4], v[5], 0x5410), __byte_perm(v[6], v[7], 0x5410));
+    return make_uint4((v[0] & 0xFFu) | ((v[1] & 0xFFu) << 8) | ((v[2] & 0xFFu) << 16) | (v[3] << 24),
+                      (v[4] & 0xFFu) | ((v[5] & 0xFFu) << 8) | ((v[6] & 0xFFu) << 16) | (v[7] << 24), 0u, 0u);
+}
+__device__ __noinline__ void sink_store_straddle(uint8_t *rowp, uint32_t x, uint32_t w, uint32_t pitch, int esize2,
+                                                 uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3) {
+    const uint32_t pk[4] = {p0, p1, p2, p3};
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        if (esize2) reinterpret_cast<uint16_t *>(rowp)[x] = (uint16_t)(pk[j >> 1] >> (16 * (j & 1)));
+        else rowp[x] = (uint8_t)(pk[j >> 2] >> (8 * (j & 3)));
+        if (++x == w) { x = 0; rowp += pitch; }
+    }
+}
 // kDecBatch consecutive samples; one or two vector stores when they stay inside the row and the address allows it
 __device__ __forceinline__ void sink_put_batch(const SinkCfg &G, RasterPos &R, const int32_t (&a)[kDecBatch]) {
     static_assert(kDecBatch == 8, "packing below assumes 8 samples");
-    if (R.x + kDecBatch <= R.w) {
-        if (G.dtype == FRB_U16 || G.dtype == FRB_I16) {
+    const bool inside = R.x + kDecBatch <= R.w;
+    if (G.intpath && (G.dtype == FRB_U16 || G.dtype == FRB_I16)) {
+        uint32_t pk[4];
+        bool tie = false;
+#pragma unroll
+        for (int j = 0; j < 4; j++) pk[j] = __byte_perm(sink_px(R, a[2 * j], tie), sink_px(R, a[2 * j + 1], tie), 0x5410);
+        if (tie) {
+            const uint4 r = sink_fix_ties(G.scale, G.rcp, R.imn, R.irange, R.kround, 1, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+            pk[0] = r.x; pk[1] = r.y; pk[2] = r.z; pk[3] = r.w;
+        }
+        if (inside) {
             uint16_t *p = reinterpret_cast<uint16_t *>(R.rowp) + R.x;
-            uint32_t pk[4];
-            if (G.intpath) {
-                bool tie = false;
-#pragma unroll
-                for (int j = 0; j < 4; j++) pk[j] = __byte_perm(sink_px(R, a[2 * j], tie), sink_px(R, a[2 * j + 1], tie), 0x5410);
-                if (tie) {                                     // rare: some sample sits on an exact .5; redo the batch sample by sample
-                    FRB_SINK_SLOW(G, R, a);
-                    return;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t lo = (uint32_t)(uint16_t)(int32_t)__double2ll_rn(sink_map(G, R, a[2 * j]));
-                    const uint32_t hi = (uint32_t)(int32_t)__double2ll_rn(sink_map(G, R, a[2 * j + 1]));
-                    pk[j] = lo | (hi << 16);
-                }
-            }
             const uintptr_t ad = reinterpret_cast<uintptr_t>(p);
             if ((ad & 15u) == 0) *reinterpret_cast<uint4 *>(p) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             else if ((ad & 7u) == 0) { reinterpret_cast<uint2 *>(p)[0] = make_uint2(pk[0], pk[1]); reinterpret_cast<uint2 *>(p)[1] = make_uint2(pk[2], pk[3]); }
@@ -494,21 +622,47 @@ __device__ __forceinline__ void sink_put_batch(const SinkCfg &G, RasterPos &R, c
 #pragma unroll
                 for (int j = 0; j < 4; j++) { p[2 * j] = (uint16_t)pk[j]; p[2 * j + 1] = (uint16_t)(pk[j] >> 16); }
             }
-        } else if (G.dtype == FRB_U8 || G.dtype == FRB_I8) {
-            uint8_t *p = R.rowp + R.x;
-            uint32_t pk[2] = {0, 0};
-            bool tie = false;
+            R.x += kDecBatch;
+            if (R.x == R.w) { R.x = 0; R.rowp += R.pitch; }
+        } else {
+            sink_store_straddle(R.rowp, R.x, R.w, R.pitch, 1, pk[0], pk[1], pk[2], pk[3]);
+            sink_advance(R, kDecBatch);
+        }
+        return;
+    }
+    if (G.intpath && (G.dtype == FRB_U8 || G.dtype == FRB_I8)) {
+        uint32_t pk[2] = {0, 0};
+        bool tie = false;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const uint32_t b = (G.intpath ? sink_px(R, a[j], tie) : (uint32_t)(int32_t)__double2ll_rn(sink_map(G, R, a[j]))) & 0xFFu;
-                pk[j >> 2] |= b << (8 * (j & 3));
-            }
-            if (tie) { FRB_SINK_SLOW(G, R, a); return; }
+        for (int j = 0; j < 8; j++) pk[j >> 2] |= (sink_px(R, a[j], tie) & 0xFFu) << (8 * (j & 3));
+        if (tie) {
+            const uint4 r = sink_fix_ties(G.scale, G.rcp, R.imn, R.irange, R.kround, 0, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+            pk[0] = r.x; pk[1] = r.y;
+        }
+        if (inside) {
+            uint8_t *p = R.rowp + R.x;
             if ((reinterpret_cast<uintptr_t>(p) & 7u) == 0) *reinterpret_cast<uint2 *>(p) = make_uint2(pk[0], pk[1]);
             else {
 #pragma unroll
                 for (int j = 0; j < 8; j++) p[j] = (uint8_t)(pk[j >> 2] >> (8 * (j & 3)));
             }
+            R.x += kDecBatch;
+            if (R.x == R.w) { R.x = 0; R.rowp += R.pitch; }
+        } else {
+            sink_store_straddle(R.rowp, R.x, R.w, R.pitch, 0, pk[0], pk[1], 0u, 0u);
+            sink_advance(R, kDecBatch);
+        }
+        return;
+    }
+    if (inside) {
+        if (G.dtype == FRB_U16 || G.dtype == FRB_I16) {
+            uint16_t *p = reinterpret_cast<uint16_t *>(R.rowp) + R.x;
+#pragma unroll
+            for (int j = 0; j < kDecBatch; j++) p[j] = (uint16_t)(int32_t)__double2ll_rn(sink_map(G, R, a[j]));
+        } else if (G.dtype == FRB_U8 || G.dtype == FRB_I8) {
+            uint8_t *p = R.rowp + R.x;
+#pragma unroll
+            for (int j = 0; j < kDecBatch; j++) p[j] = (uint8_t)(int32_t)__double2ll_rn(sink_map(G, R, a[j]));
         } else {
 #pragma unroll
             for (int j = 0; j < kDecBatch; j++) store_denorm(R.rowp, G.dtype, R.x + j, sink_map(G, R, a[j]));
@@ -614,7 +768,9 @@ __device__ __forceinline__ void decode_predictive(SubCtx &S, const PredState<PMA
             const DecReader snap = br;
             // code = z zeros, a one, k low bits.  With f = bfind(window) = 31 - z: length (k + 32) - f, the low bits sit at
             // window >> (f - k), and z << k = (31 << k) - (f << k) is one multiply-add
-            const uint32_t kb = k + 32, kmask = (1u << k) - 1u, pow2k = 1u << k, c31k = 31u << k;
+            // ... and window >> (f - k) holds the stop bit at position k with nothing above it, i.e. 2^k + low bits, so
+            // u = (z << k) + low = ((30 - f) << k) + (window >> (f - k)): shift, multiply-add, add
+            const uint32_t kb = k + 32, npow2k = 0u - (1u << k), c30k = 30u << k;
             uint32_t maxlen = 0, u[kDecBatch];
 #pragma unroll
             for (int j = 0; j < kDecBatch; j++) {
@@ -622,7 +778,7 @@ __device__ __forceinline__ void decode_predictive(SubCtx &S, const PredState<PMA
                 const uint32_t f = bfind_u32(win);
                 const uint32_t len = kb - f;
                 maxlen = max(maxlen, len);
-                u[j] = (c31k - f * pow2k) | (shr_clamped(win, f - k) & kmask);   // garbage when len > 32: the batch is redone then
+                u[j] = f * npow2k + shr_clamped(win, f - k) + c30k;              // garbage when len > 32: the batch is redone then
                 br.advance_predicated(len);
             }
             if (maxlen <= 32) {
@@ -688,7 +844,9 @@ k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__rest
                    uint32_t channels, uint32_t bps, uint32_t blocksize, uint32_t total_frames,
                    const unsigned long long *__restrict__ frame_pos, uint32_t *__restrict__ sub_bitoff,
                    int32_t *__restrict__ audio, uint8_t *__restrict__ frame_chassign, uint32_t *__restrict__ status,
-                   uint32_t n_skim_ctas, uint32_t skim_lanes, const SinkCfg sink) {
+                   uint32_t n_skim_ctas, uint32_t skim_lanes, const SinkCfg sink, uint32_t indexed) {
+    // indexed != 0: sub_bitoff is a READ-ONLY table the caller supplied (the stream's seek index, frb_encode_index): there is
+    // no skim role and nothing to wait for; every decode thread checks the frame header itself
     __shared__ __align__(256) uint4 s_ring[kSkimRing * kDecThreads];
 #ifdef FRB_DEC_TIMING
     unsigned long long t_start; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
@@ -725,7 +883,7 @@ k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__rest
         else {
             uint32_t ch_assign = 0;
             uint64_t bit0;
-            if (sub_bitoff) {
+            if (sub_bitoff && !indexed) {
                 const uint32_t *slot = sub_bitoff + (size_t)f * channels + c;
                 uint32_t off = ld_acquire_u32(slot), spins = 0;
                 while (off == kNotReady) {
@@ -738,9 +896,15 @@ k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__rest
                 ch_assign = frame_chassign[f];
             } else {
                 FrameHdr h;
-                if (!parse_frame_header(bytes + L.start, L.end - L.start, 0, bps, &h)) { alive = false; atomicAdd(&status[2], 1u); }
-                else { hdr_bytes = h.header_bytes; ch_assign = h.ch_assign; frame_chassign[f] = (uint8_t)h.ch_assign; }
+                if (!parse_frame_header(bytes + L.start, L.end - L.start, 0, bps, &h)) { alive = false; if (c == 0) atomicAdd(&status[2], 1u); }
+                else { hdr_bytes = h.header_bytes; ch_assign = h.ch_assign; if (c == 0) frame_chassign[f] = (uint8_t)h.ch_assign; }
                 bit0 = (L.start + hdr_bytes) * 8;
+                if (indexed && alive && sub_bitoff) {
+                    const uint32_t off = sub_bitoff[(size_t)f * channels + c];
+                    // the index must agree with the stream: subframe 0 starts right behind the header, the others inside the frame
+                    if (c == 0 ? off != hdr_bytes * 8 : (off <= hdr_bytes * 8 || (uint64_t)off >= (L.end - L.start) * 8)) { alive = false; atomicAdd(&status[2], 1u); }
+                    bit0 = L.start * 8 + off;
+                }
             }
             if (alive) {
                 S.br.init(S.br.sbase, lane, bytes, bit0, L.end);
@@ -821,6 +985,9 @@ k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__rest
             // the last subframe must end (after byte padding) exactly 2 bytes before the next frame
             const uint64_t bits = S.br.bitpos() - L.start * 8;
             if (L.start + ((bits + 7) >> 3) + 2 != L.end) S.err = true;
+        } else if (!S.err && indexed && sub_bitoff) {
+            // indexed streams: a subframe must end exactly where the index says the next one starts
+            if (S.br.bitpos() - L.start * 8 != (uint64_t)sub_bitoff[(size_t)f * channels + c + 1]) S.err = true;
         }
         if (S.err) atomicAdd(&status[2], 1u);
         else if (c + 1 == channels) atomicAdd(&status[3], 1u);

@@ -848,6 +848,29 @@ k_frame_sizes(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
     frame_bytes[f] = frame_header_bytes(n, st.sample_rate, k) + (uint32_t)((bits + 7) >> 3) + 2;
 }
 
+// Seek index of the coded streams (frb_encode_index): for every frame the bit offset of each of its subframes from the
+// frame's first byte (entry 0 = the frame header's length).  Thread per frame; same sums as k_frame_sizes.
+__global__ void __launch_bounds__(256)
+k_export_index(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint32_t channels, uint32_t blocksize,
+               uint32_t total_frames, const uint32_t *__restrict__ sub_bits, uint32_t vch, const uint8_t *__restrict__ frame_sel,
+               uint32_t *__restrict__ sub_bitoff) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= total_frames) return;
+    uint32_t lo = 0, hi = n_streams - 1;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (streams[mid].frame_base <= f) lo = mid; else hi = mid - 1;
+    }
+    const EncStreamDev st = streams[lo];
+    const uint32_t k = f - st.frame_base;
+    const uint32_t n = (k + 1 < st.n_frames) ? blocksize : (uint32_t)(st.n_samples - (uint64_t)k * blocksize);
+    uint32_t bits = 8u * frame_header_bytes(n, st.sample_rate, k);
+    for (uint32_t c = 0; c < channels; c++) {
+        sub_bitoff[(size_t)f * channels + c] = bits;
+        bits += sub_bits[(size_t)f * vch + (frame_sel ? ms_slot(frame_sel[f], c) : c)];
+    }
+}
+
 // one CTA per stream: exclusive scan of its frame sizes -> frame_off, total -> stream_bytes
 __global__ void __launch_bounds__(1024)
 k_stream_scan(const EncStreamDev *__restrict__ streams, const uint32_t *__restrict__ frame_bytes,
@@ -1386,6 +1409,24 @@ extern "C" int frb_encode_emit(const frb_encode_params *p, void *d_workspace, si
     uint32_t h_err = 0;
     FRB_TRY(small_download(&h_err, w.err_flag, 4, s));
     if (h_err) return FRB_ERR_OVERFLOW;
+    return FRB_OK;
+}
+extern "C" int frb_encode_index(const frb_encode_params *p, void *d_workspace, size_t workspace_bytes,
+                                uint32_t *d_frame_bytes, uint32_t *d_sub_bitoff, void *stream) {
+    using namespace frb;
+    if (!enc_params_ok(p) || !d_workspace || (!d_frame_bytes && !d_sub_bitoff)) return FRB_ERR_INVALID_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!(t_last_analyse.ws == d_workspace && t_last_analyse.n_streams == p->n_streams && t_last_analyse.frames)) return FRB_ERR_INVALID_ARG;
+    const uint64_t frames = t_last_analyse.frames;           // the index describes the analyse that just ran on this workspace
+    EncWorkspace w;
+    if (enc_ws_layout(p, frames, d_workspace, &w) > workspace_bytes) return FRB_ERR_OVERFLOW;
+    if (d_frame_bytes) FRB_CUDA(cudaMemcpyAsync(d_frame_bytes, w.frame_bytes, 4 * (size_t)frames, cudaMemcpyDeviceToDevice, s));
+    if (d_sub_bitoff) {
+        const bool ms = enc_mid_side(p);
+        k_export_index<<<(uint32_t)((frames + 255) / 256), 256, 0, s>>>(w.streams, p->n_streams, p->channels, p->blocksize, (uint32_t)frames,
+                                                                       w.sub_bits, ms ? 4u : p->channels, ms ? w.frame_sel : nullptr, d_sub_bitoff);
+        FRB_LAUNCH_CHECK("k_export_index");
+    }
     return FRB_OK;
 }
 static_assert(sizeof(frb::EncShared) <= 100 * 1024, "EncShared must allow >= 2 CTAs per SM");

@@ -61,6 +61,17 @@ class EncodedTiles:
     bps: int                       # FLAC bits per sample (16 or 32)
     bits_per_sample: int           # the reference's notion (16 or 24)
     blocksize: int
+    # seek index of the frames (frb_encode_index): byte size of every frame and bit offset of every subframe inside its
+    # frame, tiles and frames in payload order; int32 views of uint32 data, on the payload's device (CPU for the host path)
+    frame_bytes: Optional[torch.Tensor] = None
+    sub_bitoff: Optional[torch.Tensor] = None
+
+    def frames_per_tile(self) -> np.ndarray:
+        return (np.asarray(self.n_samples, dtype=np.int64) + self.blocksize - 1) // self.blocksize
+
+    def index(self):
+        """(frame_bytes, sub_bitoff) for Engine.decode_tiles / decode_streams, or None."""
+        return None if self.frame_bytes is None else (self.frame_bytes, self.sub_bitoff)
 
 
 class Engine:
@@ -164,7 +175,11 @@ class Engine:
             payload = self._buf(payload_name, total + 16)
             nat.check(self.L.frb_encode_emit(C.byref(p), ws.data_ptr(), ws.numel(), offsets.ctypes.data,
                                              payload.data_ptr(), payload.numel(), None, s), "frb_encode_emit")
-        return payload[:total], offsets.astype(np.int64), sizes.astype(np.int64)
+            # seek index (frame sizes + subframe bit offsets): what lets a decoder skip the sync scan and the subframe walk
+            fb = torch.empty(frames, dtype=torch.int32, device=self.device)
+            sb = torch.empty(frames * channels, dtype=torch.int32, device=self.device)
+            nat.check(self.L.frb_encode_index(C.byref(p), ws.data_ptr(), ws.numel(), fb.data_ptr(), sb.data_ptr(), s), "frb_encode_index")
+        return payload[:total], offsets.astype(np.int64), sizes.astype(np.int64), fb, sb
 
     def encode_tiles(self, raster: torch.Tensor, tiles: np.ndarray, level: int = 5, blocksize: int = 4096,
                      payload_name: str = "payload") -> EncodedTiles:
@@ -175,10 +190,10 @@ class Engine:
         audio, base, npx, d_minmax, bits = self.normalize_tiles(raster, tiles)
         bps = 16 if bits == 16 else 32            # pyflac derives bps from the array dtype (docs/sonos-pyflac.txt:1988-1991)
         rates = sample_rates_for_pixel_counts(npx)                # one vector expression (4096 tiles: 5 ms of Python before)
-        payload, offsets, sizes = self.encode_audio(audio, npx, base, rates, bands, bps, level, blocksize, payload_name)
+        payload, offsets, sizes, fb, sb = self.encode_audio(audio, npx, base, rates, bands, bps, level, blocksize, payload_name)
         with torch.cuda.device(self.device):
             minmax = self._download(d_minmax, np.float64, 2 * len(tiles)).reshape(-1, 2)
-        return EncodedTiles(payload, offsets, sizes, minmax, npx, rates, bands, bps, bits, blocksize)
+        return EncodedTiles(payload, offsets, sizes, minmax, npx, rates, bands, bps, bits, blocksize, fb, sb)
 
     # ------------------------------------------------------------------ encode, host buffers (pipelined)
     @staticmethod
@@ -317,19 +332,24 @@ class Engine:
                 h0 = host_marks[0][2]
                 timeline.extend(("host_" + name, g, (t - h0) * 1e3) for name, g, t in host_marks)
         p0 = parts[0]
+        fb = torch.cat([p.frame_bytes for p in parts]).cpu() if all(p.frame_bytes is not None for p in parts) else None
+        sb = torch.cat([p.sub_bitoff for p in parts]).cpu() if fb is not None else None
         return EncodedTiles(host_out[:total], np.concatenate([p.offsets for p in parts]), np.concatenate([p.sizes for p in parts]),
                             np.concatenate([p.minmax for p in parts]), np.concatenate([p.n_samples for p in parts]),
-                            np.concatenate([p.sample_rates for p in parts]), p0.channels, p0.bps, p0.bits_per_sample, p0.blocksize)
+                            np.concatenate([p.sample_rates for p in parts]), p0.channels, p0.bps, p0.bits_per_sample, p0.blocksize, fb, sb)
 
     # ------------------------------------------------------------------ decode
     def decode_streams(self, data: torch.Tensor, byte_offsets: np.ndarray, byte_lengths: np.ndarray, n_samples: np.ndarray,
                        sample_rates: np.ndarray, channels: int, bps: int, blocksize: int = 4096, verify_crc: bool = True,
-                       sync: bool = True, name: str = "dec"):
+                       sync: bool = True, name: str = "dec", index=None):
         """Frames of many streams (device bytes) -> int32 planar audio on the device.
 
         data must be readable 16 bytes past the last stream.  Returns (audio, audio_base, status[8]).
         sync=False leaves everything queued on the current stream and returns the status words as a device tensor
-        (the caller checks them, and status[4] != 0 means the stream needs the wide-order kernel: rerun with sync)."""
+        (the caller checks them, and status[4] != 0 means the stream needs the wide-order kernel: rerun with sync).
+        index = (frame_bytes, sub_bitoff) of these streams (EncodedTiles.index(), or the container's "frbI" blocks): the
+        sync scan and the subframe walk are skipped; an index that does not fit the streams is detected while decoding and
+        the call falls back to the scanning path."""
         n_streams = len(n_samples)
         n_samples = np.asarray(n_samples, dtype=np.int64)
         frames_per = (n_samples + blocksize - 1) // blocksize
@@ -351,23 +371,57 @@ class Engine:
             audio = self._buf(name + "_audio", total * 4)
             d_status = torch.zeros(8, dtype=torch.int32, device=self.device)
             status = None
-            for max_order in (12, 32):
+            idx = self._index_on_device(index, total_frames, channels)
+            for max_order, use_idx in ((12, True), (32, True), (12, False), (32, False)):
+                if use_idx and idx is None:
+                    continue
                 p = nat.DecodeParams(n_streams, channels, bps, blocksize, 1 if verify_crc else 0, max_order)
                 ws_bytes = C.c_size_t(0)
                 nat.check(self.L.frb_decode_workspace_size(C.byref(p), total_frames, C.byref(ws_bytes)), "frb_decode_workspace_size")
                 ws = self._buf(name + "_ws", ws_bytes.value)
-                nat.check(self.L.frb_decode_batch(C.byref(p), st.ctypes.data, data.data_ptr(), total_frames, audio.data_ptr(),
-                                                  ws.data_ptr(), ws.numel(), d_status.data_ptr(), s), "frb_decode_batch")
+                if use_idx:
+                    nat.check(self.L.frb_decode_batch_indexed(C.byref(p), st.ctypes.data, data.data_ptr(), total_frames, idx[0].data_ptr(),
+                                                              idx[1].data_ptr(), audio.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                              d_status.data_ptr(), s), "frb_decode_batch_indexed")
+                else:
+                    nat.check(self.L.frb_decode_batch(C.byref(p), st.ctypes.data, data.data_ptr(), total_frames, audio.data_ptr(),
+                                                      ws.data_ptr(), ws.numel(), d_status.data_ptr(), s), "frb_decode_batch")
                 if not sync:
                     return audio, base, d_status
                 status = self._download(d_status, np.int32, 8).astype(np.int64)
+                if use_idx and (status[0] or status[1] or status[2]):
+                    idx = None                       # the index does not describe these bytes: decode again by scanning
+                    continue
                 if status[4] == 0:
                     break
         return audio, base, status
 
+    def _index_on_device(self, index, total_frames: int, channels: int):
+        """(frame_bytes, sub_bitoff) as int32 device tensors of the right length, or None."""
+        if index is None:
+            return None
+        fb, sb = index
+        if fb is None or (sb is None and channels > 1):
+            return None
+
+        def dev(x, n):
+            if isinstance(x, np.ndarray):
+                if x.size != n:
+                    return None
+                return self._upload(np.ascontiguousarray(x, dtype=np.uint32).view(np.uint8))[:4 * n].view(torch.int32)
+            if x.numel() != n:
+                return None
+            return x.contiguous() if x.is_cuda else self._upload(x.contiguous().numpy().view(np.uint8))[:4 * n].view(torch.int32)
+
+        d_fb = dev(fb, total_frames)
+        d_sb = dev(sb, total_frames * channels) if channels > 1 else d_fb
+        if d_fb is None or d_sb is None:
+            return None
+        return d_fb, d_sb
+
     def decode_tiles(self, data: torch.Tensor, byte_offsets: np.ndarray, byte_lengths: np.ndarray, tiles: np.ndarray,
                      sample_rates: np.ndarray, minmax: np.ndarray, scale: float, out: torch.Tensor, bps: int,
-                     blocksize: int = 4096, verify_crc: bool = True, fused: Optional[bool] = None) -> np.ndarray:
+                     blocksize: int = 4096, verify_crc: bool = True, fused: Optional[bool] = None, index=None) -> np.ndarray:
         """Frames of a batch of tiles (device bytes) -> windows of the (bands,H,W) device raster `out`, decoded and
         denormalised in one launch (frb_decode_tiles); what `extract` + flac_to_tiff do per tile (cli.py:297-315,
         converter.py:181-253).  Returns the status words.  Two-band rasters go through decode_streams +
@@ -384,7 +438,7 @@ class Engine:
             fused = bps == 16 and dt in ("uint8", "int8", "uint16", "int16") and float(scale) == 32767.0
         if bands == 2 or not fused:
             audio, base, status = self.decode_streams(data, byte_offsets, byte_lengths, n_samples, sample_rates, bands, bps, blocksize,
-                                                      verify_crc)
+                                                      verify_crc, index=index)
             self.denormalize_tiles(audio, base, tiles, minmax, scale, out)
             return status
         frames_per = (n_samples + blocksize - 1) // blocksize
@@ -406,26 +460,39 @@ class Engine:
             d_stage = self._upload(stage)
             d_status = torch.zeros(8, dtype=torch.int32, device=self.device)
             status = None
-            for max_order in (12, 32):
+            idx = self._index_on_device(index, total_frames, bands)
+            for max_order, use_idx in ((12, True), (32, True), (12, False), (32, False)):
+                if use_idx and idx is None:
+                    continue
                 p = nat.DecodeParams(n_tiles, bands, bps, blocksize, 1 if verify_crc else 0, max_order)
                 ws_bytes = C.c_size_t(0)
                 nat.check(self.L.frb_decode_workspace_size(C.byref(p), total_frames, C.byref(ws_bytes)), "frb_decode_workspace_size")
                 ws = self._buf("dec_ws", ws_bytes.value)
-                nat.check(self.L.frb_decode_tiles(C.byref(p), st.ctypes.data, data.data_ptr(), total_frames,
-                                                  d_stage.data_ptr(), d_stage.data_ptr() + n_tiles * 16, float(scale),
-                                                  out.data_ptr(), nat.DTYPE_CODES[dt], bands, H, W,
-                                                  ws.data_ptr(), ws.numel(), d_status.data_ptr(), s), "frb_decode_tiles")
+                if use_idx:
+                    nat.check(self.L.frb_decode_tiles_indexed(C.byref(p), st.ctypes.data, data.data_ptr(), total_frames,
+                                                              idx[0].data_ptr(), idx[1].data_ptr(),
+                                                              d_stage.data_ptr(), d_stage.data_ptr() + n_tiles * 16, float(scale),
+                                                              out.data_ptr(), nat.DTYPE_CODES[dt], bands, H, W,
+                                                              ws.data_ptr(), ws.numel(), d_status.data_ptr(), s), "frb_decode_tiles_indexed")
+                else:
+                    nat.check(self.L.frb_decode_tiles(C.byref(p), st.ctypes.data, data.data_ptr(), total_frames,
+                                                      d_stage.data_ptr(), d_stage.data_ptr() + n_tiles * 16, float(scale),
+                                                      out.data_ptr(), nat.DTYPE_CODES[dt], bands, H, W,
+                                                      ws.data_ptr(), ws.numel(), d_status.data_ptr(), s), "frb_decode_tiles")
                 status = self._download(d_status, np.int32, 8).astype(np.int64)      # (synchronises: d_stage stays alive until the kernels are done)
                 if status[6]:
                     raise nat.NativeError(nat.ERR_INVALID_ARG, "frb_decode_tiles",
                                           f"{int(status[6])} tile(s) do not match their stream length or lie outside the raster")
+                if use_idx and (status[0] or status[1] or status[2]):
+                    idx = None                       # the index does not describe these bytes: decode again by scanning
+                    continue
                 if status[4] == 0:
                     break
         return status
 
     def decode_tiles_host(self, host_payload: torch.Tensor, byte_offsets: np.ndarray, byte_lengths: np.ndarray, tiles: np.ndarray,
                           sample_rates: np.ndarray, minmax: np.ndarray, scale: float, host_out: torch.Tensor, bps: int,
-                          blocksize: int = 4096, group_bytes: Optional[int] = None) -> np.ndarray:
+                          blocksize: int = 4096, group_bytes: Optional[int] = None, index=None) -> np.ndarray:
         """Host frames in, host (bands,H,W) raster out: the end-to-end form of decode_tiles and the mirror of
         encode_tiles_host.  Tile rows are pipelined over three streams: H2D of the frames of rows g+1 (double-buffered),
         the fused decode of rows g into a device slab, D2H of the pixels of rows g-1.  `host_payload` (uint8, the tiles'
@@ -438,6 +505,11 @@ class Engine:
         max_rows = max(r1 - r0 for _, _, r0, r1 in groups)
         byte_offsets = np.asarray(byte_offsets, dtype=np.int64)
         byte_lengths = np.asarray(byte_lengths, dtype=np.int64)
+        # seek index: uploaded once, sliced per stage by frame range (tiles and frames are in payload order)
+        frames_per = (tiles["h"].astype(np.int64) * tiles["w"].astype(np.int64) + blocksize - 1) // blocksize
+        frame_start = np.concatenate([[0], np.cumsum(frames_per)])
+        with torch.cuda.device(self.device):
+            d_index = self._index_on_device(index, int(frame_start[-1]), bands)
         spans = [(int(byte_offsets[i0]), int(byte_offsets[i1 - 1] + byte_lengths[i1 - 1])) for i0, i1, _, _ in groups]
         max_span = max(b - a for a, b in spans)
         status = np.zeros(8, dtype=np.int64)
@@ -478,8 +550,10 @@ class Engine:
                     if g >= 2:
                         s_comp.wait_event(ev_d2h[g - 2])          # slab g%2 has left the device
                     a, b = spans[g]
+                    f0, f1 = int(frame_start[i0]), int(frame_start[i1])
+                    gidx = None if d_index is None else (d_index[0][f0:f1], d_index[1][f0 * bands:f1 * bands] if bands > 1 else d_index[0][f0:f1])
                     st = self.decode_tiles(frames_dev[g % 2][:b - a + 64], byte_offsets[i0:i1] - a, byte_lengths[i0:i1], local,
-                                           sample_rates[i0:i1], minmax[i0:i1], scale, slab, bps, blocksize)
+                                           sample_rates[i0:i1], minmax[i0:i1], scale, slab, bps, blocksize, index=gidx)
                     status += st
                     e = torch.cuda.Event()
                     e.record(s_comp)

@@ -98,7 +98,7 @@ def _tile_bbox(transform, col, row, w, h):
 
 def build_streaming_container(raster_dev, transform, crs, nodata, dtype_name: str, tile_size: int,
                               compression_level: int = 5, tiles: Optional[np.ndarray] = None, engine=None,
-                              row_origin: int = 0, full_shape: Optional[Tuple[int, int, int]] = None):
+                              row_origin: int = 0, full_shape: Optional[Tuple[int, int, int]] = None, seek_index: bool = True):
     """Encode every tile of a device-resident (bands,H,W) raster and lay out the container.
 
     Returns (index dict, list of per-tile header bytes, EncodedTiles).  Tile t's complete FLAC
@@ -126,6 +126,13 @@ def build_streaming_container(raster_dev, transform, crs, nodata, dtype_name: st
     headers, frames = [], []
     total = 0
     a9 = (list(transform[:6]) + [0.0, 0.0, 1.0]) if transform else []
+    # seek index per tile ("frbI" APPLICATION block): frame sizes + subframe bit offsets, so that a tile fetched later is
+    # decoded without the sync scan and the walk for subframe starts
+    fb_all = sb_all = None
+    if seek_index and enc.frame_bytes is not None:
+        fb_all = enc.frame_bytes.cpu().numpy().view(np.uint32)
+        sb_all = enc.sub_bitoff.cpu().numpy().view(np.uint32)
+        fstart = np.concatenate([[0], np.cumsum(enc.frames_per_tile())])
     for i, t in enumerate(tiles):
         r, c, h, w = int(t["row_off"]), int(t["col_off"]), int(t["h"]), int(t["w"])
         bbox, ttrans = _tile_bbox(transform, c, r, w, h)
@@ -133,7 +140,11 @@ def build_streaming_container(raster_dev, transform, crs, nodata, dtype_name: st
                            float(enc.minmax[i, 0]), float(enc.minmax[i, 1]), nodata, scale)
         si = flacfmt.StreamInfo(enc.blocksize, enc.blocksize, 0, 0, int(enc.sample_rates[i]), bands, enc.bps, int(enc.n_samples[i]))
         from .converter import metadata_tags
-        hdr = flacfmt.build_header(si, metadata_tags(md))
+        sidx = None
+        if fb_all is not None:
+            f0, f1 = int(fstart[i]), int(fstart[i + 1])
+            sidx = flacfmt.pack_seek_index(bands, enc.blocksize, fb_all[f0:f1], sb_all[f0 * bands:f1 * bands])
+        hdr = flacfmt.build_header(si, metadata_tags(md), seek_index=sidx)
         headers.append(hdr)
         size = len(hdr) + int(enc.sizes[i])
         frames.append({

@@ -166,6 +166,16 @@ int frb_encode_emit(const frb_encode_params *p, void *d_workspace, size_t worksp
                     const uint64_t *h_out_offset, uint8_t *d_out, size_t out_capacity,
                     uint32_t *d_frame_bytes, void *stream);
 
+/* Seek index of the streams the last frb_encode_analyse on this workspace coded (optional, any time after it):
+ * d_frame_bytes[total_frames] = byte size of every frame in stream order, d_sub_bitoff[total_frames * channels] = bit
+ * offset of every subframe from the first byte of its frame (entry 0 of a frame = its header's length in bits).
+ * Subframes of a FLAC frame are bit-packed back to back, so without this a decoder has to walk every Rice code of
+ * subframes 0..C-2 just to find where the next one starts; a decoder that is handed the index (frb_decode_*_indexed)
+ * skips that walk and the sync-code scan.  The Python layer stores it per tile in a FLAC APPLICATION block ("frbI"),
+ * which other decoders ignore.  Either pointer may be NULL. */
+int frb_encode_index(const frb_encode_params *p, void *d_workspace, size_t workspace_bytes,
+                     uint32_t *d_frame_bytes, uint32_t *d_sub_bitoff, void *stream);
+
 /* --------------------------------------------------- 4. decode (device)
  * Batch of FLAC streams whose bytes are resident on the device.  The host
  * has parsed the metadata blocks (STREAMINFO) and passes, per stream, the
@@ -216,6 +226,22 @@ int frb_decode_tiles(const frb_decode_params *p, const frb_decode_stream *h_stre
                      const frb_tile *d_tiles, const double *d_minmax, double scale,
                      void *d_raster, int dtype, uint32_t bands, uint32_t H, uint32_t W,
                      void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream);
+
+/* The same two calls for streams that come with a seek index (frb_encode_index): no sync scan, no walk for subframe
+ * starts -- every subframe of the batch is decoded independently from the first instruction.  The index is verified
+ * against the streams while decoding (frame sizes must add up to byte_length, every header must parse, every subframe
+ * must end where the next one is said to begin, CRC-16): a wrong index shows up in the status words like a damaged
+ * stream, and the caller then repeats the call without it. */
+int frb_decode_batch_indexed(const frb_decode_params *p, const frb_decode_stream *h_streams,
+                             const uint8_t *d_bytes, uint64_t total_frames,
+                             const uint32_t *d_frame_bytes, const uint32_t *d_sub_bitoff, int32_t *d_audio,
+                             void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream);
+int frb_decode_tiles_indexed(const frb_decode_params *p, const frb_decode_stream *h_streams,
+                             const uint8_t *d_bytes, uint64_t total_frames,
+                             const uint32_t *d_frame_bytes, const uint32_t *d_sub_bitoff,
+                             const frb_tile *d_tiles, const double *d_minmax, double scale,
+                             void *d_raster, int dtype, uint32_t bands, uint32_t H, uint32_t W,
+                             void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream);
 
 /* Frame discovery for a stream of unknown length (FileDecoder on a file
  * whose STREAMINFO total_samples is 0 and no tags are known).  Synchronous.

@@ -873,3 +873,54 @@ def test_config5_bbox_over_4096_tiles_through_the_public_api(nat, torch_cuda, tm
         assert [m["frame_id"] for _, m in part] == list(range(10, 20))
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+def test_seek_index_decode_equals_scan_path_and_bad_index_falls_back(nat, torch_cuda, tmp_path):
+    """The encoder's seek index (frb_encode_index: frame sizes + subframe bit offsets) lets the decoder skip the sync scan and
+    the subframe walk; results must be identical to the scanning path, an index that does not fit the bytes must be noticed and
+    replaced by the scan, and containers must carry it in an APPLICATION block other decoders ignore."""
+    torch = torch_cuda
+    from flac_raster_b200 import SpatialFLACEncoder, SpatialFLACStreamer, flacfmt
+    from flac_raster_b200.engine import default_engine, tile_grid
+    from flac_raster_b200.synth import sentinel2_like
+    eng = default_engine()
+    for bands, side, ts in ((8, 1500, 512), (1, 1300, 512), (2, 700, 256)):
+        raster = sentinel2_like(side, side, bands)
+        tiles = tile_grid(side, side, ts)
+        enc = eng.encode_tiles(raster, tiles, 5)
+        assert enc.frame_bytes is not None and int(enc.frame_bytes.sum()) == int(enc.sizes.sum())
+        fpt = enc.frames_per_tile()
+        assert enc.frame_bytes.numel() == int(fpt.sum()) and enc.sub_bitoff.numel() == int(fpt.sum()) * bands
+        payload = torch.cat([enc.payload, torch.zeros(64, dtype=torch.uint8, device="cuda")])
+        outs = []
+        for index in (None, enc.index(), (enc.frame_bytes.cpu().numpy().view(np.uint32), enc.sub_bitoff.cpu().numpy().view(np.uint32))):
+            out = torch.zeros_like(raster)
+            st = eng.decode_tiles(payload, enc.offsets, enc.sizes, tiles, enc.sample_rates, enc.minmax, 32767.0, out, 16, 4096, index=index)
+            assert list(st[:3]) == [0, 0, 0] and st[3] == int(fpt.sum()), st
+            outs.append(out)
+        assert torch.equal(outs[0].view(torch.int16), raster.view(torch.int16))
+        assert torch.equal(outs[1], outs[0]) and torch.equal(outs[2], outs[0])
+        a0, b0, s0 = eng.decode_streams(payload, enc.offsets, enc.sizes, enc.n_samples, enc.sample_rates, bands, 16, 4096)
+        ref_audio = a0[:int(enc.n_samples.sum()) * bands * 4].clone()
+        a1, b1, s1 = eng.decode_streams(payload, enc.offsets, enc.sizes, enc.n_samples, enc.sample_rates, bands, 16, 4096, index=enc.index())
+        assert list(s1[:3]) == [0, 0, 0] and torch.equal(a1[:ref_audio.numel()], ref_audio)
+        # wrong index: one subframe offset moved, one frame size changed -> noticed, decoded by scanning, same pixels
+        for which in ("sub", "frame"):
+            fb, sb = enc.frame_bytes.clone(), enc.sub_bitoff.clone()
+            if which == "sub" and bands > 1:
+                sb[bands * 3 + 1] += 8
+            else:
+                fb[2] += 1
+                fb[3] -= 1
+            out = torch.zeros_like(raster)
+            st = eng.decode_tiles(payload, enc.offsets, enc.sizes, tiles, enc.sample_rates, enc.minmax, 32767.0, out, 16, 4096, index=(fb, sb))
+            assert list(st[:3]) == [0, 0, 0] and torch.equal(out, outs[0])
+    # container: the block is there, is found again, and tiles decode through it
+    out = tmp_path / "idx.flac"
+    SpatialFLACEncoder(tile_size=256).encode(GOLDEN / "sample_rgb.tif", out, streaming=True)
+    s = SpatialFLACStreamer(out)
+    blob = out.read_bytes()
+    f = s.spatial_index.frames[0]
+    h = flacfmt.parse_header(blob[s.header_size + f.byte_offset: s.header_size + f.byte_offset + f.byte_size])
+    got = flacfmt.unpack_seek_index(h.applications[flacfmt.SEEK_INDEX_ID], 3, 4096, 16)
+    assert got is not None and int(got[0].sum()) == f.byte_size - h.first_frame_offset and got[1].size == 48
