@@ -49,6 +49,13 @@ class DecodeParams(C.Structure):
                 ("blocksize", C.c_uint32), ("verify_crc16", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+TILE_HEADER_DTYPE = np.dtype([
+    ("first_frame_offset", "<u4"), ("sample_rate", "<u4"), ("channels", "<u4"), ("bps", "<u4"), ("min_blocksize", "<u4"),
+    ("max_blocksize", "<u4"), ("width", "<u4"), ("height", "<u4"), ("count", "<u4"), ("dtype", "<i4"), ("flags", "<u4"),
+    ("index_offset", "<u4"), ("index_len", "<u4"), ("_pad", "<u4"), ("total_samples", "<u8"),
+    ("data_min", "<f8"), ("data_max", "<f8"), ("nodata", "<f8"),
+])
+
 DECODE_STREAM_DTYPE = np.dtype([
     ("byte_offset", "<u8"), ("byte_length", "<u8"), ("n_samples", "<u8"), ("audio_base", "<i8"),
     ("sample_rate", "<u4"), ("frame_base", "<u4"),
@@ -82,7 +89,7 @@ _EXPORTS = [
     "frb_minmax_flat", "frb_normalize_flat", "frb_denormalize_flat", "frb_selftest_division",
     "frb_encode_workspace_size", "frb_encode_analyse", "frb_encode_emit", "frb_encode_index",
     "frb_decode_workspace_size", "frb_decode_batch", "frb_decode_tiles", "frb_decode_batch_indexed", "frb_decode_tiles_indexed",
-    "frb_probe_stream",
+    "frb_probe_stream", "frb_debug_spin", "frb_parse_tile_headers", "frb_gather_seek_index",
     "frb_host_encode", "frb_host_decode",
     "frb_stream_encoder_new", "frb_stream_encoder_delete", "frb_stream_encoder_set_channels",
     "frb_stream_encoder_set_bits_per_sample", "frb_stream_encoder_set_sample_rate",
@@ -181,6 +188,9 @@ def lib():
     L.frb_encode_index.argtypes = [C.POINTER(EncodeParams), vp, sz, vp, vp, vp]
     L.frb_decode_batch_indexed.argtypes = [C.POINTER(DecodeParams), vp, vp, u64, vp, vp, vp, vp, sz, vp, vp]
     L.frb_decode_tiles_indexed.argtypes = [C.POINTER(DecodeParams), vp, vp, u64, vp, vp, vp, vp, C.c_double, vp, C.c_int, u32, u32, u32, vp, sz, vp, vp]
+    L.frb_debug_spin.argtypes = [u32, u32, u64, vp]
+    L.frb_parse_tile_headers.argtypes = [vp, vp, vp, u32, vp]
+    L.frb_gather_seek_index.argtypes = [vp, vp, vp, u32, u32, u32, vp, vp, vp]
     L.frb_decode_workspace_size.argtypes = [C.POINTER(DecodeParams), u64, C.POINTER(sz)]
     L.frb_decode_batch.argtypes = [C.POINTER(DecodeParams), vp, vp, u64, vp, vp, sz, vp, vp]
     L.frb_decode_tiles.argtypes = [C.POINTER(DecodeParams), vp, vp, u64, vp, vp, C.c_double, vp, C.c_int, u32, u32, u32, vp, sz, vp, vp]

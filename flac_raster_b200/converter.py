@@ -282,12 +282,7 @@ def decode_tile_blobs(blobs, headers, metadatas, mosaic=None, staged=None):
     if idx_fb:
         index = (np.concatenate(idx_fb), np.concatenate(idx_sb) if channels > 1 else None)
     status = eng.decode_tiles(data, offs, lens, tiles, rates, minmax, scale, out, bps, blocksize, index=index)
-    if status[5]:
-        raise RuntimeError("decode kernel timed out waiting for a subframe offset")
-    if status[0] or status[2]:
-        raise ValueError(f"malformed FLAC stream (missing frames={status[0]}, parse errors={status[2]})")
-    if status[1]:
-        raise ValueError(f"FLAC frame CRC-16 mismatch in {status[1]} frame(s)")
+    _raise_for_status(status)
     # D2H through a pinned buffer, then every tile becomes its own array (the buffer is reused by the next call);
     # the per-tile copies run on a few threads (numpy releases the GIL while copying)
     nbytes = out.numel() * dtype.itemsize
@@ -311,3 +306,110 @@ def decode_tile_blobs(blobs, headers, metadatas, mosaic=None, staged=None):
     else:
         res = [take(i) for i in range(n)]
     return res
+
+
+_DTYPE_NAMES = ["uint8", "int8", "uint16", "int16", "uint32", "int32", "float32", "float64"]
+
+
+def decode_staged_tiles(stage, nbytes: int, starts: np.ndarray, sizes: np.ndarray):
+    """Fast form of decode_tile_blobs for tiles that already sit in ONE pinned staging buffer (SpatialFLACStreamer reads the
+    byte ranges of a bbox query straight into it): the per-tile metadata walk runs in C (frb_parse_tile_headers) instead of
+    4096 Python header parses, the seek indices are gathered in C, and single-band tiles of equal width come back as views
+    of a pinned result buffer that belongs to the returned arrays (no second host copy; torch's pinned allocator recycles the
+    block once the arrays are dropped).  Returns (arrays, header records) or None when a tile does not qualify (no
+    GEOSPATIAL tags, mixed geometry): the caller then takes the general path."""
+    import ctypes as C
+
+    import torch
+    from . import _native as nat
+    from .engine import TORCH_DTYPES, default_engine
+
+    eng = default_engine()
+    L = nat.lib()
+    n = len(starts)
+    stage_np = stage.numpy()
+    offs64 = np.ascontiguousarray(starts, dtype=np.uint64)
+    size64 = np.ascontiguousarray(sizes, dtype=np.uint64)
+    hdr = np.zeros(n, dtype=nat.TILE_HEADER_DTYPE)
+    rc = L.frb_parse_tile_headers(stage_np.ctypes.data, offs64.ctypes.data, size64.ctypes.data, n, hdr.ctypes.data)
+    if rc != nat.FRB_OK:
+        raise ValueError("not a FLAC stream (missing fLaC marker)")
+    h0 = hdr[0]
+    channels, bps, blocksize = int(h0["channels"]), int(h0["bps"]), int(h0["max_blocksize"])
+    same = (hdr["channels"] == channels) & (hdr["bps"] == bps) & (hdr["max_blocksize"] == blocksize) & (hdr["dtype"] == h0["dtype"])
+    if not same.all():
+        raise ValueError("tiles of one batch must share channels, bits per sample and blocksize")
+    if not ((hdr["flags"] & 1) != 0).all() or h0["dtype"] < 0 or (hdr["width"] == 0).any() or (hdr["height"] == 0).any():
+        return None
+    if not (hdr["count"] == channels).all():
+        raise ValueError("band count in tags does not match the FLAC channel count")
+    dtype = np.dtype(_DTYPE_NAMES[int(h0["dtype"])])
+    widths = hdr["width"].astype(np.int64)
+    heights = hdr["height"].astype(np.int64)
+    nsamp = widths * heights
+    tiles = np.zeros(n, dtype=nat.TILE_DTYPE)
+    rows0 = np.zeros(n, dtype=np.int64)
+    np.cumsum(heights[:-1], out=rows0[1:])
+    tiles["row_off"] = rows0
+    tiles["h"] = heights
+    tiles["w"] = widths
+    row, maxw = int(heights.sum()), int(widths.max())
+    offs = offs64.astype(np.int64) + hdr["first_frame_offset"].astype(np.int64)
+    lens = size64.astype(np.int64) - hdr["first_frame_offset"].astype(np.int64)
+    minmax = np.stack([hdr["data_min"], hdr["data_max"]], axis=1)
+    scale = 32767.0 if bps == 16 else 8388607.0                  # decode default by audio width (converter.py:220-229)
+    # seek indices of all tiles, concatenated in C
+    index = None
+    fpt = ((nsamp + blocksize - 1) // blocksize).astype(np.uint32)
+    if ((hdr["flags"] & 4) != 0).all():
+        nf = int(fpt.sum())
+        fb = np.empty(nf, dtype=np.uint32)
+        sb = np.empty(nf * channels, dtype=np.uint32) if channels > 1 else None
+        rc = L.frb_gather_seek_index(stage_np.ctypes.data, offs64.ctypes.data, hdr.ctypes.data, n, channels, blocksize, fpt.ctypes.data,
+                                     fb.ctypes.data, sb.ctypes.data if sb is not None else None)
+        if rc == nat.FRB_OK:
+            index = (fb, sb)
+    stage_np[nbytes:nbytes + 64] = 0
+    data = eng._buf("dec_data", nbytes + 64)[:nbytes + 64]
+    data.copy_(stage[:nbytes + 64], non_blocking=True)
+    out = torch.zeros(channels * row * maxw * dtype.itemsize, dtype=torch.uint8, device=eng.device)
+    out = out.view(TORCH_DTYPES[str(dtype)]).reshape(channels, row, maxw)
+    status = eng.decode_tiles(data, offs, lens, tiles, hdr["sample_rate"].astype(np.uint32), minmax, scale, out, bps, blocksize, index=index)
+    _raise_for_status(status)
+    nb = out.numel() * dtype.itemsize
+    # result buffer: a fresh pinned block per call (cached by torch's host allocator), owned by the arrays handed out
+    host = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+    host.copy_(out.reshape(-1).view(torch.uint8), non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    host_out = host.numpy().view(dtype).reshape(channels, row, maxw)
+    if channels == 1 and (widths == maxw).all():
+        arrays = [host_out[:, int(r0):int(r0 + h_)] for r0, h_ in zip(rows0, heights)]     # C-contiguous views, one owner
+    else:
+        arrays = _copy_tiles_out(host_out, rows0, heights, widths)
+    return arrays, hdr
+
+
+def _raise_for_status(status):
+    if status[5]:
+        raise RuntimeError("decode kernel timed out waiting for a subframe offset")
+    if status[0] or status[2]:
+        raise ValueError(f"malformed FLAC stream (missing frames={status[0]}, parse errors={status[2]})")
+    if status[1]:
+        raise ValueError(f"FLAC frame CRC-16 mismatch in {status[1]} frame(s)")
+
+
+def _copy_tiles_out(host_out, rows0, heights, widths):
+    """Every tile becomes its own C-contiguous array (multi-band or ragged tiles are strided inside the stacked buffer); the
+    copies run on a few threads (numpy releases the GIL while copying)."""
+    n = len(rows0)
+
+    def take(i):
+        return np.array(host_out[:, int(rows0[i]):int(rows0[i] + heights[i]), :int(widths[i])], copy=True, order="C")
+
+    if n >= 64:
+        from concurrent.futures import ThreadPoolExecutor
+        step = (n + 31) // 32
+        jobs = [range(a, min(n, a + step)) for a in range(0, n, step)]
+        with ThreadPoolExecutor(8) as ex:
+            return [a for part in ex.map(lambda rg: [take(i) for i in rg], jobs) for a in part]
+    return [take(i) for i in range(n)]

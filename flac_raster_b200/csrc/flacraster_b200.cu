@@ -14,6 +14,7 @@ static int ensure_tables_impl();
 #include "frb_decode.cuh"
 #include "frb_encode.cuh"
 #include "frb_host.cuh"
+#include "frb_hostparse.cuh"
 
 namespace frb {
 // CRC tables are uploaded once per device.
@@ -100,5 +101,23 @@ extern "C" int frb_profile_last_ms(int which, float *ms) {
     if (!p.valid) return FRB_ERR_INVALID_ARG;
     FRB_CUDA(cudaEventSynchronize(p.b));
     FRB_CUDA(cudaEventElapsedTime(ms, p.a, p.b));
+    return FRB_OK;
+}
+
+namespace frb {
+__global__ void __launch_bounds__(128) k_debug_spin(unsigned long long ns) {
+    extern __shared__ uint8_t spin_smem[];
+    if (threadIdx.x == 0) spin_smem[0] = 0;
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do { __nanosleep(1000); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); } while (t - t0 < ns);
+}
+}  // namespace frb
+extern "C" int frb_debug_spin(uint32_t ctas, uint32_t smem_bytes, uint64_t ns, void *stream) {
+    using namespace frb;
+    if (!ctas || smem_bytes > 200 * 1024 || ns > 2000000000ull) return FRB_ERR_INVALID_ARG;
+    FRB_CUDA(cudaFuncSetAttribute(k_debug_spin, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    k_debug_spin<<<ctas, 128, smem_bytes, (cudaStream_t)stream>>>(ns);
+    FRB_LAUNCH_CHECK("k_debug_spin");
     return FRB_OK;
 }

@@ -302,7 +302,7 @@ static int decode_batch_impl(const frb_decode_params *p, const frb_decode_stream
     if (dev < 0 || dev >= 64) return FRB_ERR_UNSUPPORTED;
     cudaStream_t &side = side_of[dev];
     cudaEvent_t &ev_fork = fork_of[dev], &ev_join = join_of[dev];
-    if (p->verify_crc16) {
+    if (p->verify_crc16 & 1u) {
         if (!side) {
             FRB_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
             FRB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
@@ -334,19 +334,34 @@ static int decode_batch_impl(const frb_decode_params *p, const frb_decode_stream
             else FRB_TRY(small_fill(sub_bitoff, 0xFFFFFFFFu, 4 * (size_t)(total_frames * p->channels), s));
         }
         const uint64_t total_sub = total_frames * p->channels;
-        const uint32_t grid = n_skim_ctas + (uint32_t)((total_sub + kDecThreads - 1) / kDecThreads);
+        const uint32_t dec_ctas = (uint32_t)((total_sub + kDecThreads - 1) / kDecThreads);
         const bool big = p->reserved > 12;
+        // The fused launch relies on in-order dispatch of CTAs (skim CTAs, the lowest block indices, are resident or done
+        // before any decode CTA that waits for them).  verify_crc16 bit 1 (or FRB_DECODE_TWO_LAUNCH=1) takes the assumption
+        // away: the skim CTAs run as a launch of their own and the decode launch finds every offset already published.
+        static int two_env = -1;
+        if (two_env < 0) { const char *e = getenv("FRB_DECODE_TWO_LAUNCH"); two_env = e ? atoi(e) : 0; }
+        const bool two_launch = n_skim_ctas > 0 && ((p->verify_crc16 & 2u) || two_env);
         prof_begin(1, s);
-#define FRB_DECODE(BIG, RAS) k_decode_subframes<BIG, RAS><<<grid, kDecThreads, 0, s>>>(d_bytes, w.streams, p->n_streams, p->channels, p->bps, \
-            p->blocksize, (uint32_t)total_frames, w.frame_pos, sub_bitoff, d_audio, w.chassign, d_status, n_skim_ctas, skim_lanes, sink, \
+#define FRB_DECODE(BIG, RAS, GRID, NSKIM) k_decode_subframes<BIG, RAS><<<GRID, kDecThreads, 0, s>>>(d_bytes, w.streams, p->n_streams, p->channels, p->bps, \
+            p->blocksize, (uint32_t)total_frames, w.frame_pos, sub_bitoff, d_audio, w.chassign, d_status, NSKIM, skim_lanes, sink, \
             indexed ? 1u : 0u)
-        if (sink.dtype < 0) { if (big) FRB_DECODE(true, false); else FRB_DECODE(false, false); }
-        else { if (big) FRB_DECODE(true, true); else FRB_DECODE(false, true); }
+#define FRB_DECODE_ANY(GRID, NSKIM) do { \
+        if (sink.dtype < 0) { if (big) FRB_DECODE(true, false, GRID, NSKIM); else FRB_DECODE(false, false, GRID, NSKIM); } \
+        else { if (big) FRB_DECODE(true, true, GRID, NSKIM); else FRB_DECODE(false, true, GRID, NSKIM); } } while (0)
+        if (two_launch) {
+            FRB_DECODE_ANY(n_skim_ctas, n_skim_ctas);          // a grid of skim CTAs only
+            FRB_LAUNCH_CHECK("k_decode_subframes(skim)");
+            FRB_DECODE_ANY(dec_ctas, 0u);                      // decode CTAs: offsets are all there (0 = bad frame)
+        } else {
+            FRB_DECODE_ANY(n_skim_ctas + dec_ctas, n_skim_ctas);
+        }
+#undef FRB_DECODE_ANY
 #undef FRB_DECODE
         prof_end(1, s);
         FRB_LAUNCH_CHECK("k_decode_subframes");
     }
-    if (p->verify_crc16) FRB_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
+    if (p->verify_crc16 & 1u) FRB_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
     if (p->channels == 2 && sink.dtype < 0) {
         k_stereo_fix<<<(uint32_t)total_frames, 128, 0, s>>>(w.streams, p->n_streams, p->blocksize, (uint32_t)total_frames,
                                                            w.chassign, w.frame_pos, d_audio);

@@ -84,6 +84,10 @@ class Engine:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.L = nat.lib()
         self._ws: dict[str, torch.Tensor] = {}
+        # scan-path decode of multi-channel streams: False = skim CTAs inside the decode launch (in-order CTA dispatch assumed),
+        # True = skim as its own launch.  Switched on for good the first time a decode thread reports that it gave up waiting
+        # for a subframe offset (status[5]): the device is shared or does not dispatch in order.
+        self._two_launch = False
 
     # ---------------------------------------------------------------- helpers
     def _buf(self, name: str, nbytes: int) -> torch.Tensor:
@@ -222,7 +226,7 @@ class Engine:
         t = self._ws.get(name)
         if t is None or t.numel() < nbytes:
             self._ws.pop(name, None)
-            t = torch.empty(int(nbytes) + 4096, dtype=torch.uint8).pin_memory()
+            t = torch.empty(int(nbytes) + 4096, dtype=torch.uint8, pin_memory=True)     # straight from the pinned allocator (no pageable detour)
             self._ws[name] = t
         return t
 
@@ -375,7 +379,7 @@ class Engine:
             for max_order, use_idx in ((12, True), (32, True), (12, False), (32, False)):
                 if use_idx and idx is None:
                     continue
-                p = nat.DecodeParams(n_streams, channels, bps, blocksize, 1 if verify_crc else 0, max_order)
+                p = nat.DecodeParams(n_streams, channels, bps, blocksize, (1 if verify_crc else 0) | (2 if self._two_launch else 0), max_order)
                 ws_bytes = C.c_size_t(0)
                 nat.check(self.L.frb_decode_workspace_size(C.byref(p), total_frames, C.byref(ws_bytes)), "frb_decode_workspace_size")
                 ws = self._buf(name + "_ws", ws_bytes.value)
@@ -394,6 +398,10 @@ class Engine:
                     continue
                 if status[4] == 0:
                     break
+        if status is not None and status[5] and not self._two_launch:
+            self._two_launch = True                  # offsets did not arrive inside the fused launch: separate skim launch from now on
+            return self.decode_streams(data, byte_offsets, byte_lengths, n_samples, sample_rates, channels, bps, blocksize, verify_crc,
+                                       sync, name, index)
         return audio, base, status
 
     def _index_on_device(self, index, total_frames: int, channels: int):
@@ -464,7 +472,7 @@ class Engine:
             for max_order, use_idx in ((12, True), (32, True), (12, False), (32, False)):
                 if use_idx and idx is None:
                     continue
-                p = nat.DecodeParams(n_tiles, bands, bps, blocksize, 1 if verify_crc else 0, max_order)
+                p = nat.DecodeParams(n_tiles, bands, bps, blocksize, (1 if verify_crc else 0) | (2 if self._two_launch else 0), max_order)
                 ws_bytes = C.c_size_t(0)
                 nat.check(self.L.frb_decode_workspace_size(C.byref(p), total_frames, C.byref(ws_bytes)), "frb_decode_workspace_size")
                 ws = self._buf("dec_ws", ws_bytes.value)
@@ -488,6 +496,10 @@ class Engine:
                     continue
                 if status[4] == 0:
                     break
+        if status[5] and not self._two_launch:
+            self._two_launch = True                  # offsets did not arrive inside the fused launch: separate skim launch from now on
+            return self.decode_tiles(data, byte_offsets, byte_lengths, tiles, sample_rates, minmax, scale, out, bps, blocksize, verify_crc,
+                                     fused, index)
         return status
 
     def decode_tiles_host(self, host_payload: torch.Tensor, byte_offsets: np.ndarray, byte_lengths: np.ndarray, tiles: np.ndarray,

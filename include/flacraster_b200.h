@@ -198,7 +198,9 @@ typedef struct frb_decode_params {
     uint32_t channels;
     uint32_t bps;
     uint32_t blocksize;         /* STREAMINFO max blocksize */
-    uint32_t verify_crc16;      /* 1: check every frame's CRC-16 (libFLAC always does) */
+    uint32_t verify_crc16;      /* bit 0: check every frame's CRC-16 (libFLAC always does); bit 1: run the subframe-offset
+                                   walk of multi-channel streams as a launch of its own instead of inside the decode launch
+                                   (no assumption about the order in which CTAs become resident; slower) */
     uint32_t reserved;
 } frb_decode_params;
 
@@ -250,6 +252,10 @@ int frb_probe_stream(const uint8_t *d_bytes, uint64_t byte_offset, uint64_t byte
                      uint32_t channels, uint32_t bps, uint32_t blocksize, uint32_t sample_rate,
                      uint64_t *n_frames, uint64_t *n_samples, void *stream);
 
+/* Test aid: occupies the device with `ctas` thread blocks of 128 threads that each hold `smem_bytes` of shared memory and
+ * spin for `ns` nanoseconds (asynchronous on `stream`).  Used to run the decode launch under SM contention. */
+int frb_debug_spin(uint32_t ctas, uint32_t smem_bytes, uint64_t ns, void *stream);
+
 /* Small host <-> device transfers for the tables and read-backs around the batch calls (tile tables, min/max,
  * status words).  They go through pinned staging and a copy kernel instead of cudaMemcpyAsync, so that they do not
  * queue behind the bulk H2D/D2H transfers of a host pipeline on the copy engines.  frb_small_upload is asynchronous
@@ -277,6 +283,30 @@ int frb_host_decode(const uint8_t *frames, size_t n_bytes, uint32_t channels, ui
                     uint32_t blocksize, uint32_t sample_rate, uint64_t n_samples_hint,
                     int32_t *interleaved_out, size_t out_capacity_samples,
                     uint64_t *n_samples_out);
+
+/* --------------------------------------------- 5b. tile files (host, no GPU work)
+ * Metadata walk over n standalone tile FLAC files that sit in one host buffer (file i = base[offsets[i] .. +sizes[i])):
+ * what SpatialFLACStreamer needs per tile before the batched GPU decode -- where the frames start, STREAMINFO, the
+ * GEOSPATIAL_* numbers the reference parses from the VORBIS tags (converter.py:356-377) and the seek index block.
+ * Returns FRB_ERR_BAD_STREAM if any file is not a FLAC stream (its entry has first_frame_offset == 0). */
+typedef struct frb_tile_header {
+    uint32_t first_frame_offset;        /* 0: not a parseable FLAC file */
+    uint32_t sample_rate, channels, bps, min_blocksize, max_blocksize;
+    uint32_t width, height, count;      /* GEOSPATIAL_WIDTH / HEIGHT / COUNT (0 when absent) */
+    int32_t dtype;                      /* FRB_U8..FRB_F64 from GEOSPATIAL_DTYPE, -1 when absent / unknown */
+    uint32_t flags;                     /* bit 0: GEOSPATIAL_CRS present, bit 1: nodata is a number, bit 2: seek index block present */
+    uint32_t index_offset, index_len;   /* "frbI" APPLICATION data (behind the 4-byte id), offset from the start of the file */
+    uint64_t total_samples;
+    double data_min, data_max, nodata;  /* NaN when absent */
+} frb_tile_header;
+int frb_parse_tile_headers(const uint8_t *base, const uint64_t *offsets, const uint64_t *sizes, uint32_t n,
+                           frb_tile_header *out);
+/* Concatenates the tiles' seek indices in payload order for frb_decode_*_indexed (frame_bytes_out: sum(frames_per_tile)
+ * entries, sub_bitoff_out: that times channels; NULL allowed for one channel).  FRB_ERR_BAD_STREAM if a tile has no
+ * index or one that does not match (channels, blocksize, frame count): decode without an index then. */
+int frb_gather_seek_index(const uint8_t *base, const uint64_t *offsets, const frb_tile_header *hdrs, uint32_t n,
+                          uint32_t channels, uint32_t blocksize, const uint32_t *frames_per_tile,
+                          uint32_t *frame_bytes_out, uint32_t *sub_bitoff_out);
 
 /* ------------------------------------------ 6. libFLAC-shaped handle API
  * The exact calls pyflac's cffi layer makes, so a binding written against FLAC__stream_encoder_* /

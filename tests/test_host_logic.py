@@ -265,3 +265,74 @@ def test_shard_plan_covers_every_tile_once():
                 assert (r0, r1) == (0, 0)
         assert seen == list(range(121))
     assert [shard_range(121, r, 8) for r in (0, 7)] == [(0, 16), (106, 121)]
+
+
+def test_c_tile_header_parser_equals_python_parser():
+    """frb_parse_tile_headers / frb_gather_seek_index (host C, no GPU) against flacfmt.parse_header + parse_metadata_tags on
+    tile files as the container holds them, on the reference goldens, and on damaged input."""
+    from flac_raster_b200 import _native as nat, flacfmt
+    from flac_raster_b200.converter import _DTYPE_NAMES, metadata_tags, parse_metadata_tags, tile_metadata
+    L = nat.lib()
+    rng = np.random.default_rng(3)
+    files, want_idx = [], []
+    cases = [("uint16", 3, 512, 300, 0.0, 11672.0, None), ("int16", 1, 512, 512, -3050.0, 3049.0, -9999.0),
+             ("float32", 1, 77, 5, 0.1 + 0.2, 1e-300, float("nan")), ("uint8", 8, 1024, 1024, 7.0, 7.0, 255.0),
+             ("float64", 2, 9, 4097, -1.5e300, 2.5e300, None)]
+    for k, (dt, bands, w, h, mn, mx, nod) in enumerate(cases):
+        md = tile_metadata(w, h, bands, dt, "EPSG:32633", (10.0, 0.0, 5e5 + k, 0.0, -10.0, 4e6), mn, mx, nod, 32767)
+        bps = 16 if dt in ("uint8", "int8", "uint16", "int16") else 32
+        nf = (w * h + 4095) // 4096
+        fb = rng.integers(20, 9000, nf).astype(np.uint32)
+        sb = rng.integers(40, 70000, nf * bands).astype(np.uint32)
+        sidx = flacfmt.pack_seek_index(bands, 4096, fb, sb) if k != 2 else None
+        si = flacfmt.StreamInfo(4096, 4096, 0, 0, 48000, bands, bps, w * h)
+        files.append(flacfmt.build_header(si, metadata_tags(md), padding=33 if k == 1 else 0, seek_index=sidx) + b"\xff\xf8" + bytes(50 + k))
+        want_idx.append((fb, sb if bands > 1 else None) if sidx is not None else None)
+    files.append((GOLDEN / "sample_rgb.flac").read_bytes())          # reference file: mutagen-free vendor header, no GEOSPATIAL tags
+    files.append((GOLDEN / "sample_dem.flac").read_bytes()[:10426])  # reference legacy stream 0: tags + padding written by mutagen
+    blob = b"".join(files)
+    offs = np.cumsum([0] + [len(f) for f in files[:-1]]).astype(np.uint64)
+    sizes = np.array([len(f) for f in files], dtype=np.uint64)
+    buf = np.frombuffer(blob, dtype=np.uint8)
+    hdr = np.zeros(len(files), dtype=nat.TILE_HEADER_DTYPE)
+    assert L.frb_parse_tile_headers(buf.ctypes.data, offs.ctypes.data, sizes.ctypes.data, len(files), hdr.ctypes.data) == 0
+    for f, rec in zip(files, hdr):
+        h = flacfmt.parse_header(f)
+        si = h.streaminfo
+        assert (rec["first_frame_offset"], rec["sample_rate"], rec["channels"], rec["bps"], rec["max_blocksize"], rec["total_samples"]) == \
+               (h.first_frame_offset, si.sample_rate, si.channels, si.bits_per_sample, si.max_blocksize, si.total_samples)
+        md = parse_metadata_tags(h.tags)
+        assert bool(rec["flags"] & 1) == (md is not None)
+        if md and "dtype" in md and md["dtype"] in _DTYPE_NAMES:
+            assert (rec["width"], rec["height"], rec["count"], _DTYPE_NAMES[rec["dtype"]]) == (md["width"], md["height"], md["count"], md["dtype"])
+            assert rec["data_min"] == md["data_min"] and rec["data_max"] == md["data_max"]
+            nod = md.get("nodata")
+            if nod is None:
+                assert not rec["flags"] & 2
+            else:
+                assert rec["flags"] & 2 and (rec["nodata"] == nod or (np.isnan(nod) and np.isnan(rec["nodata"])))
+        assert bool(rec["flags"] & 4) == (flacfmt.SEEK_INDEX_ID in h.applications)
+        if rec["flags"] & 4:
+            assert f[rec["index_offset"]:rec["index_offset"] + rec["index_len"]] == h.applications[flacfmt.SEEK_INDEX_ID]
+    assert hdr[5]["dtype"] == -1 and hdr[6]["dtype"] == 3 and hdr[6]["data_min"] == 577.0      # the goldens
+    # seek index gather: tiles 0 and 3 (3 and 8 channels differ -> one at a time), then a tile without a block
+    for t in (0, 1, 3, 4):
+        bands = int(hdr[t]["channels"])
+        nf = np.array([want_idx[t][0].size], dtype=np.uint32)
+        fb = np.zeros(int(nf[0]), dtype=np.uint32)
+        sb = np.zeros(int(nf[0]) * bands, dtype=np.uint32)
+        rc = L.frb_gather_seek_index(buf.ctypes.data, offs[t:].ctypes.data, hdr[t:].ctypes.data, 1, bands, 4096, nf.ctypes.data,
+                                     fb.ctypes.data, sb.ctypes.data if bands > 1 else None)
+        assert rc == 0 and np.array_equal(fb, want_idx[t][0]) and (bands == 1 or np.array_equal(sb, want_idx[t][1]))
+        assert L.frb_gather_seek_index(buf.ctypes.data, offs[t:].ctypes.data, hdr[t:].ctypes.data, 1, bands, 1024, nf.ctypes.data,
+                                       fb.ctypes.data, sb.ctypes.data) == nat.ERR_BAD_STREAM     # wrong blocksize
+    one = np.array([1], dtype=np.uint32)
+    assert L.frb_gather_seek_index(buf.ctypes.data, offs[2:].ctypes.data, hdr[2:].ctypes.data, 1, 1, 4096, one.ctypes.data,
+                                   np.zeros(1, np.uint32).ctypes.data, None) == nat.ERR_BAD_STREAM
+    # damaged: not a FLAC file, truncated metadata
+    bad = np.frombuffer(b"RIFF" + bytes(60) + files[0][:40], dtype=np.uint8)
+    boffs = np.array([0, 64], dtype=np.uint64)
+    bsz = np.array([64, 40], dtype=np.uint64)
+    bh = np.zeros(2, dtype=nat.TILE_HEADER_DTYPE)
+    assert L.frb_parse_tile_headers(bad.ctypes.data, boffs.ctypes.data, bsz.ctypes.data, 2, bh.ctypes.data) == nat.ERR_BAD_STREAM
+    assert bh[0]["first_frame_offset"] == 0 and bh[1]["first_frame_offset"] == 0

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Debug: role timeline of the fused skim+decode kernel (needs a -DFRB_DEC_TIMING build: tools/build_variants.py
-timing=-DFRB_DEC_TIMING, run with FRB_LIB_PATH=flac_raster_b200/lib/var_timing.so).  argv: [audio] [n_tiles]"""
+timing=-DFRB_DEC_TIMING, run with FRB_LIB_PATH=flac_raster_b200/lib/var_timing.so).  argv: [audio] [idx] [n_tiles]"""
 import ctypes as C, os, sys
 from pathlib import Path
 import numpy as np, torch
@@ -26,7 +26,8 @@ for it in range(3):
     if len(sys.argv) > 1 and sys.argv[1] == "audio":
         audio, base, st = eng.decode_streams(payload, enc.offsets, enc.sizes, enc.n_samples, enc.sample_rates, 8, 16, 4096)
     else:
-        st = eng.decode_tiles(payload, enc.offsets, enc.sizes, tiles, enc.sample_rates, enc.minmax, 32767.0, out, 16, 4096)
+        st = eng.decode_tiles(payload, enc.offsets, enc.sizes, tiles, enc.sample_rates, enc.minmax, 32767.0, out, 16, 4096,
+                              index=enc.index() if "idx" in sys.argv else None)
     ev1.record()
     torch.cuda.synchronize()
     L.frb_debug_decode_timing(dbg, 0)
