@@ -311,13 +311,15 @@ def decode_tile_blobs(blobs, headers, metadatas, mosaic=None, staged=None):
 _DTYPE_NAMES = ["uint8", "int8", "uint16", "int16", "uint32", "int32", "float32", "float64"]
 
 
-def decode_staged_tiles(stage, nbytes: int, starts: np.ndarray, sizes: np.ndarray):
+def decode_staged_tiles(stage, nbytes: int, starts: np.ndarray, sizes: np.ndarray, data=None, while_copying=None):
     """Fast form of decode_tile_blobs for tiles that already sit in ONE pinned staging buffer (SpatialFLACStreamer reads the
     byte ranges of a bbox query straight into it): the per-tile metadata walk runs in C (frb_parse_tile_headers) instead of
     4096 Python header parses, the seek indices are gathered in C, and single-band tiles of equal width come back as views
     of a pinned result buffer that belongs to the returned arrays (no second host copy; torch's pinned allocator recycles the
     block once the arrays are dropped).  Returns (arrays, header records) or None when a tile does not qualify (no
-    GEOSPATIAL tags, mixed geometry): the caller then takes the general path."""
+    GEOSPATIAL tags, mixed geometry): the caller then takes the general path.
+    data: the staging buffer's bytes already on the device (the reader sent them piece by piece), else they are copied here.
+    while_copying(header records): called while the device-to-host copy of the pixels is in flight."""
     import ctypes as C
 
     import torch
@@ -369,9 +371,10 @@ def decode_staged_tiles(stage, nbytes: int, starts: np.ndarray, sizes: np.ndarra
                                      fb.ctypes.data, sb.ctypes.data if sb is not None else None)
         if rc == nat.FRB_OK:
             index = (fb, sb)
-    stage_np[nbytes:nbytes + 64] = 0
-    data = eng._buf("dec_data", nbytes + 64)[:nbytes + 64]
-    data.copy_(stage[:nbytes + 64], non_blocking=True)
+    if data is None:
+        stage_np[nbytes:nbytes + 64] = 0
+        data = eng._buf("dec_data", nbytes + 64)[:nbytes + 64]
+        data.copy_(stage[:nbytes + 64], non_blocking=True)
     out = torch.zeros(channels * row * maxw * dtype.itemsize, dtype=torch.uint8, device=eng.device)
     out = out.view(TORCH_DTYPES[str(dtype)]).reshape(channels, row, maxw)
     status = eng.decode_tiles(data, offs, lens, tiles, hdr["sample_rate"].astype(np.uint32), minmax, scale, out, bps, blocksize, index=index)
@@ -380,6 +383,8 @@ def decode_staged_tiles(stage, nbytes: int, starts: np.ndarray, sizes: np.ndarra
     # result buffer: a fresh pinned block per call (cached by torch's host allocator), owned by the arrays handed out
     host = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
     host.copy_(out.reshape(-1).view(torch.uint8), non_blocking=True)
+    if while_copying is not None:
+        while_copying(hdr)
     torch.cuda.current_stream().synchronize()
     host_out = host.numpy().view(dtype).reshape(channels, row, maxw)
     if channels == 1 and (widths == maxw).all():

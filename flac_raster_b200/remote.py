@@ -1,12 +1,20 @@
-"""Remote byte-range access (out of the accelerated path; reference src/flac_raster/remote.py).
+"""Remote byte-range access (reference src/flac_raster/remote.py).
 
-Only the names the package surface exports are kept: is_remote_url, RemoteFile.read_range,
-open_remote, read_remote_range, download_remote.  HTTP(S) uses urllib Range requests
+The names the package surface exports are kept: is_remote_url, RemoteFile.read_range,
+open_remote, read_remote_range, download_remote.  HTTP(S) uses Range requests
 (remote.py:153-168); cloud schemes need obstore, as in the reference.
+
+Added for the tile path: read_range_into writes a range straight into a caller
+buffer -- SpatialFLACStreamer hands it slices of its pinned staging buffer, several ranges in
+flight on a thread pool (one keep-alive connection per thread), and sends every piece to the
+GPU as soon as it has arrived, so the fetches overlap the host-to-device copies.
 """
 from __future__ import annotations
 
+import http.client
 import tempfile
+import threading
+import urllib.parse
 import urllib.request
 from pathlib import Path
 from typing import Optional, Union
@@ -52,6 +60,52 @@ class RemoteFile:
             data = data[start:end + 1]
         return data
 
+    def read_range_into(self, start: int, end: int, out) -> int:
+        """Inclusive byte range written into the writable buffer `out` (len >= end - start + 1); returns the byte count.
+        HTTP(S): one keep-alive connection per calling thread, the body is received straight into `out`."""
+        want = end - start + 1
+        mv = memoryview(out).cast("B")
+        if self._store is not None or self.scheme not in ("http", "https"):
+            data = self.read_range(start, end)
+            mv[:len(data)] = data
+            return len(data)
+        u = urllib.parse.urlsplit(self.url)
+        path = (u.path or "/") + ("?" + u.query if u.query else "")
+        local = _conn_cache.__dict__.setdefault("conns", {})
+        key = (u.scheme, u.netloc)
+        for attempt in (0, 1):
+            conn = local.get(key)
+            if conn is None:
+                cls = http.client.HTTPSConnection if u.scheme == "https" else http.client.HTTPConnection
+                conn = local[key] = cls(u.netloc, timeout=30)
+            try:
+                conn.request("GET", path, headers={"Range": f"bytes={start}-{end}", "Connection": "keep-alive"})
+                r = conn.getresponse()
+                if r.status == 206:
+                    got = 0
+                    while got < want:
+                        n = r.readinto(mv[got:want])
+                        if not n:
+                            break
+                        got += n
+                    r.read()                       # drain (nothing left on a conforming server) so the connection can be reused
+                    return got
+                body = r.read()                    # 200: the server ignored the Range header (remote.py:166-168)
+                if r.status != 200:
+                    raise OSError(f"HTTP {r.status} for {self.url}")
+                data = body[start:end + 1]
+                mv[:len(data)] = data
+                return len(data)
+            except (http.client.HTTPException, ConnectionError, OSError):
+                local.pop(key, None)
+                try:
+                    conn.close()
+                except Exception:  # noqa: BLE001
+                    pass
+                if attempt:
+                    raise
+        return 0
+
     def read_all(self) -> bytes:
         if self._store is not None:
             import obstore  # type: ignore
@@ -65,6 +119,9 @@ class RemoteFile:
         with tempfile.NamedTemporaryFile(suffix=suffix, delete=False) as tmp:
             tmp.write(self.read_all())
             return Path(tmp.name)
+
+
+_conn_cache = threading.local()
 
 
 def open_remote(url: str) -> RemoteFile:

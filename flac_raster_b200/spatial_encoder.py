@@ -461,31 +461,13 @@ class SpatialFLACStreamer:
         return b"".join(self._read_range(s, e) for s, e in self.get_byte_ranges_for_bbox(bbox))
 
     # ---- README API: decode on the GPU ----------------------------------------------------------
-    def _fetch_tiles(self, frames: List[SpatialFrame]) -> List[bytes]:
-        # merge adjacent ranges so a bbox of neighbouring tiles is one read / one HTTP request
-        order = sorted(range(len(frames)), key=lambda i: frames[i].byte_offset)
-        blobs: List[Optional[bytes]] = [None] * len(frames)
-        i = 0
-        while i < len(order):
-            j = i
-            start = frames[order[i]].byte_offset
-            end = start + frames[order[i]].byte_size
-            while j + 1 < len(order) and frames[order[j + 1]].byte_offset == end:
-                j += 1
-                end += frames[order[j]].byte_size
-            chunk = memoryview(self._read_range(self.header_size + start, self.header_size + end - 1))
-            for k in range(i, j + 1):
-                f = frames[order[k]]
-                o = f.byte_offset - start
-                blobs[order[k]] = chunk[o:o + f.byte_size]          # views: no per-tile copy of the range just read
-            i = j + 1
-        return blobs   # type: ignore[return-value]
-
-    def _read_tiles_pinned(self, frames: List[SpatialFrame]):
+    def _read_tiles_pinned(self, frames: List[SpatialFrame], to_device: bool = False):
         """Local file: read the (merged) byte ranges of the tiles straight into ONE pinned staging buffer -- no bytes object
         per range and no second host copy before the H2D transfer.  Big queries are read by several threads (pread releases
         the GIL; one thread moves ~8 GB/s out of the page cache).  Returns (pinned uint8 tensor, bytes used, start of
-        every tile in it)."""
+        every tile in it).  to_device: every piece is also sent to the engine's "dec_data" device buffer as soon as it has
+        been read (H2D overlaps the reads of the following pieces); the 4th result is then that device tensor."""
+        import torch
         from .engine import default_engine
 
         eng = default_engine()
@@ -508,32 +490,58 @@ class SpatialFLACStreamer:
                 f = frames[order[k]]
                 starts[order[k]] = pos + (f.byte_offset - start)
             want = end - start
-            piece = 32 << 20
+            piece = (8 << 20) if self.is_url else (32 << 20)
             for o in range(0, want, piece):
                 jobs.append((self.header_size + start + o, pos + o, min(piece, want - o)))
             pos += want
             i = j + 1
-        fd = os.open(self.flac_path, os.O_RDONLY)
+        fd = None if self.is_url else os.open(self.flac_path, os.O_RDONLY)
         try:
-            def read(job):
-                off, p, n = job
-                got = 0
-                while got < n:
-                    r = os.preadv(fd, [view[p + got:p + n]], off + got)
-                    if r <= 0:
+            if self.is_url:
+                # remote container: the same pieces as HTTP / object-store range requests (remote.py:137-177), several in
+                # flight; each lands in its slice of the pinned buffer and goes on to the GPU while the others are fetched
+                from .remote import RemoteFile
+                rf = RemoteFile(self.source)
+
+                def read(job):
+                    off, p, n = job
+                    if rf.read_range_into(off, off + n - 1, view[p:p + n]) != n:
                         raise ValueError("streaming container is shorter than its index says")
-                    got += r
+            else:
+                def read(job):
+                    off, p, n = job
+                    got = 0
+                    while got < n:
+                        r = os.preadv(fd, [view[p + got:p + n]], off + got)
+                        if r <= 0:
+                            raise ValueError("streaming container is shorter than its index says")
+                        got += r
+
+            data = None
+            if to_device:
+                data = eng._buf("dec_data", pos + 64)[:pos + 64]
+
+            def send(job):
+                if data is not None:
+                    _, p, n = job
+                    data[p:p + n].copy_(stage[p:p + n], non_blocking=True)
 
             if len(jobs) > 2:
                 from concurrent.futures import ThreadPoolExecutor
                 with ThreadPoolExecutor(min(8, len(jobs))) as ex:
-                    list(ex.map(read, jobs))
+                    for job, _ in zip(jobs, ex.map(read, jobs)):       # results come back in submission order
+                        send(job)
             else:
                 for job in jobs:
                     read(job)
+                    send(job)
+            if data is not None:
+                stage[pos:pos + 64].zero_()
+                data[pos:pos + 64].copy_(stage[pos:pos + 64], non_blocking=True)
         finally:
-            os.close(fd)
-        return stage, pos, starts
+            if fd is not None:
+                os.close(fd)
+        return (stage, pos, starts, data) if to_device else (stage, pos, starts)
 
     def _tile_meta_from_index(self, f: SpatialFrame, rec) -> Dict:
         """A tile's metadata dict without parsing its tags in Python: the numbers come from frb_parse_tile_headers, the
@@ -558,29 +566,31 @@ class SpatialFLACStreamer:
         }
 
     def _decode(self, frames: List[SpatialFrame]):
-        staged = None
-        if self.is_url:
-            blobs = self._fetch_tiles(frames)
+        fast = self.metadata is not None and os.environ.get("FRB_SLOW_TILE_PARSE") != "1"
+        if fast:
+            # streaming container written with per-tile tags: the pieces go to the GPU as they arrive, metadata walk and index
+            # gather in C, one batched decode; the metadata dicts are put together while the pixels travel back to the host
+            stage, nbytes, starts, data = self._read_tiles_pinned(frames, to_device=True)
+            sizes = np.fromiter((f.byte_size for f in frames), dtype=np.int64, count=len(frames))
+            metas: List[Dict] = []
+
+            def build_metas(recs):
+                for f, rec in zip(frames, recs):
+                    meta = self._tile_meta_from_index(f, rec)
+                    meta.update({"frame_id": f.frame_id, "bbox": list(f.bbox),
+                                 "window": {"col_off": f.window.col_off, "row_off": f.window.row_off,
+                                            "width": f.window.width, "height": f.window.height},
+                                 "byte_offset": f.byte_offset, "byte_size": f.byte_size})
+                    metas.append(meta)
+
+            res = decode_staged_tiles(stage, nbytes, starts, sizes, data=data, while_copying=build_metas)
+            if res is not None:
+                return list(zip(res[0], metas))
         else:
             stage, nbytes, starts = self._read_tiles_pinned(frames)
-            if self.metadata is not None and os.environ.get("FRB_SLOW_TILE_PARSE") != "1":
-                # streaming container written with per-tile tags: metadata walk and index gather in C, one batched decode
-                sizes = np.fromiter((f.byte_size for f in frames), dtype=np.int64, count=len(frames))
-                res = decode_staged_tiles(stage, nbytes, starts, sizes)
-                if res is not None:
-                    arrays, recs = res
-                    out = []
-                    for f, a, rec in zip(frames, arrays, recs):
-                        meta = self._tile_meta_from_index(f, rec)
-                        meta.update({"frame_id": f.frame_id, "bbox": list(f.bbox),
-                                     "window": {"col_off": f.window.col_off, "row_off": f.window.row_off,
-                                                "width": f.window.width, "height": f.window.height},
-                                     "byte_offset": f.byte_offset, "byte_size": f.byte_size})
-                        out.append((a, meta))
-                    return out
-            view = memoryview(stage.numpy())
-            blobs = [view[int(starts[i]):int(starts[i]) + frames[i].byte_size] for i in range(len(frames))]
-            staged = (stage, nbytes, starts)
+        view = memoryview(stage.numpy())
+        blobs = [view[int(starts[i]):int(starts[i]) + frames[i].byte_size] for i in range(len(frames))]
+        staged = (stage, nbytes, starts)
         headers = [flacfmt.parse_header(b) for b in blobs]
         metas = []
         legacy = self.metadata is None

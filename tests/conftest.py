@@ -64,3 +64,50 @@ def signal_cases(seed=7):
     c["stereo16_extreme"] = (np.stack([alt + rng.integers(-700, 700, size=9000), -alt + rng.integers(-700, 700, size=9000)],
                                       axis=1).astype(np.int32), 16)          # side = L-R swings over the full 17 bits
     return c
+
+
+@pytest.fixture()
+def range_http_server(tmp_path):
+    """http://127.0.0.1:<port>/<name> serving files of tmp_path with Range support (206) -- or, for names starting with
+    'norange_', ignoring the Range header (200 + whole body), the case the reference handles at remote.py:166-168.
+    Yields (base_url, directory, log) where log collects the Range headers seen."""
+    import http.server
+    import threading
+
+    log = []
+
+    class H(http.server.BaseHTTPRequestHandler):
+        protocol_version = "HTTP/1.1"
+
+        def do_GET(self):
+            p = tmp_path / self.path.lstrip("/").split("?")[0]
+            if not p.is_file():
+                self.send_response(404); self.send_header("Content-Length", "0"); self.end_headers()
+                return
+            data = p.read_bytes()
+            rng = self.headers.get("Range")
+            log.append(rng)
+            if rng and not p.name.startswith("norange_"):
+                a, b = rng.split("=")[1].split("-")
+                a, b = int(a), min(int(b), len(data) - 1)
+                body = data[a:b + 1]
+                self.send_response(206)
+                self.send_header("Content-Range", f"bytes {a}-{b}/{len(data)}")
+            else:
+                body = data
+                self.send_response(200)
+            self.send_header("Content-Length", str(len(body)))
+            self.end_headers()
+            self.wfile.write(body)
+
+        def log_message(self, *a):
+            pass
+
+    srv = http.server.ThreadingHTTPServer(("127.0.0.1", 0), H)
+    th = threading.Thread(target=srv.serve_forever, daemon=True)
+    th.start()
+    try:
+        yield f"http://127.0.0.1:{srv.server_address[1]}", tmp_path, log
+    finally:
+        srv.shutdown()
+        srv.server_close()

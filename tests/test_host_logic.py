@@ -336,3 +336,35 @@ def test_c_tile_header_parser_equals_python_parser():
     bh = np.zeros(2, dtype=nat.TILE_HEADER_DTYPE)
     assert L.frb_parse_tile_headers(bad.ctypes.data, boffs.ctypes.data, bsz.ctypes.data, 2, bh.ctypes.data) == nat.ERR_BAD_STREAM
     assert bh[0]["first_frame_offset"] == 0 and bh[1]["first_frame_offset"] == 0
+
+
+def test_remote_range_reads_into_a_buffer(range_http_server):
+    """remote.RemoteFile against a local HTTP server (reference remote.py:137-177): inclusive ranges, keep-alive reuse,
+    a server that ignores Range, and the streamer's index load + merged byte ranges over a URL (no decode here)."""
+    from flac_raster_b200.remote import RemoteFile
+    from flac_raster_b200.spatial_encoder import SpatialFLACStreamer
+    base, d, log = range_http_server
+    rng = np.random.default_rng(1)
+    blob = rng.integers(0, 256, 300_000, dtype=np.uint8).tobytes()
+    (d / "f.bin").write_bytes(blob)
+    (d / "norange_f.bin").write_bytes(blob)
+    for name in ("f.bin", "norange_f.bin"):
+        rf = RemoteFile(f"{base}/{name}")
+        assert rf.read_range(10, 19) == blob[10:20]
+        buf = bytearray(70_000)
+        assert rf.read_range_into(1234, 1234 + 69_999, buf) == 70_000 and bytes(buf) == blob[1234:71_234]
+        assert rf.read_range_into(299_990, 299_999, memoryview(buf)[:10]) == 10 and bytes(buf[:10]) == blob[-10:]
+    assert "bytes=1234-71233" in log
+    # a container index over HTTP
+    frames, off = [], 0
+    for i in range(3):
+        frames.append({"frame_id": i, "bbox": [i, 0.0, i + 1.0, 1.0], "window": {"col_off": i, "row_off": 0, "width": 1, "height": 1},
+                       "byte_offset": off, "byte_size": 1000 + i})
+        off += 1000 + i
+    js = json.dumps({"crs": "EPSG:4326", "transform": [1, 0, 0, 0, -1, 1, 0, 0, 1], "width": 3, "height": 1, "bands": 1, "dtype": "uint8",
+                     "tile_size": 1, "frames": frames}, separators=(",", ":")).encode()
+    (d / "c.flac").write_bytes(len(js).to_bytes(4, "big") + js + bytes(off))
+    s = SpatialFLACStreamer(f"{base}/c.flac")
+    assert s.is_url and s.header_size == 4 + len(js) and len(s.spatial_index.frames) == 3
+    assert s.get_byte_ranges_for_bbox((0.5, 0.1, 2.5, 0.9)) == [(s.header_size, s.header_size + off - 1)]
+    assert len(s.stream_bbox_data((1.1, 0.1, 1.9, 0.9))) == 1001
