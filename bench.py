@@ -388,7 +388,7 @@ def run_ours(args, rank, world, local):
     import torch.distributed as dist
 
     from flac_raster_b200 import _native as nat
-    from flac_raster_b200.distributed import (allgather_tile_sizes, bind_to_gpu_numa_node, exclusive_scan, init_from_env,
+    from flac_raster_b200.distributed import (SizeExchange, allgather_tile_sizes, bind_to_gpu_numa_node, exclusive_scan, init_from_env,
                                               shard_plan, shard_range)
     from flac_raster_b200.engine import Engine, tile_grid
 
@@ -429,11 +429,14 @@ def run_ours(args, rank, world, local):
 
     state = {}
 
+    # the one collective of the path: every tile's frame bytes -> global byte offsets of the container (cli.py:615-621); it is
+    # enqueued on the stream inside the step and its result comes back with the step's own size download
+    xchg = SizeExchange(len(tiles_all), rank, world, dev) if world > 1 and shardable else None
+
     def encode_step():
-        enc = eng.encode_tiles(raster, tiles, level)
-        if world > 1 and shardable:        # the one collective of the path: every tile's size -> global byte offsets (cli.py:615-621)
-            sizes_all = allgather_tile_sizes(enc.sizes, len(tiles_all), rank, world, device=dev)
-            state["offsets_all"] = exclusive_scan(sizes_all)
+        enc = eng.encode_tiles(raster, tiles, level, size_exchange=xchg)
+        if xchg is not None:
+            state["offsets_all"] = exclusive_scan(enc.sizes_all)
         state["enc"] = enc
         return enc
 

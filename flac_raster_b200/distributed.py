@@ -93,6 +93,30 @@ def allgather_tile_sizes(local_sizes: np.ndarray, n_tiles: int, rank: int, world
     return out
 
 
+class SizeExchange:
+    """The path's one collective as a stream-ordered step of Engine.encode_tiles: all-gather of the per-tile frame sizes
+    (int64, device to device over NCCL/NVLink) between the analysis kernels and the size download, so that the other
+    ranks' sizes arrive in the transfer the step needs anyway.  Ranks hold contiguous blocks of shard_range(n_tiles)."""
+
+    def __init__(self, n_tiles: int, rank: int, world: int, device):
+        self.n_tiles, self.rank, self.world, self.device = n_tiles, rank, world, device
+        self.ranges = [shard_range(n_tiles, r, world) for r in range(world)]
+        self.per = max(b - a for a, b in self.ranges)
+        self.recv_count = self.per * world
+        self._send = torch.zeros(self.per, dtype=torch.int64, device=device)
+
+    def enqueue(self, d_sizes: torch.Tensor, d_recv: torch.Tensor):
+        self._send[:d_sizes.numel()].copy_(d_sizes, non_blocking=True)
+        dist.all_gather_into_tensor(d_recv, self._send)
+
+    def unpack(self, recv_host: np.ndarray) -> np.ndarray:
+        recv = np.asarray(recv_host, dtype=np.int64).reshape(self.world, self.per)
+        out = np.zeros(self.n_tiles, dtype=np.int64)
+        for r, (a, b) in enumerate(self.ranges):
+            out[a:b] = recv[r, :b - a]
+        return out
+
+
 def exclusive_scan(sizes: np.ndarray) -> np.ndarray:
     off = np.zeros(len(sizes), dtype=np.int64)
     np.cumsum(sizes[:-1], out=off[1:])

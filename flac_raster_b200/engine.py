@@ -65,6 +65,7 @@ class EncodedTiles:
     # frame, tiles and frames in payload order; int32 views of uint32 data, on the payload's device (CPU for the host path)
     frame_bytes: Optional[torch.Tensor] = None
     sub_bitoff: Optional[torch.Tensor] = None
+    sizes_all: Optional[np.ndarray] = None   # sharded path: frame bytes of EVERY tile of the scene (all ranks), see encode_tiles
 
     def frames_per_tile(self) -> np.ndarray:
         return (np.asarray(self.n_samples, dtype=np.int64) + self.blocksize - 1) // self.blocksize
@@ -129,7 +130,8 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ encode
-    def normalize_tiles(self, raster: torch.Tensor, tiles: np.ndarray, bits_per_sample: Optional[int] = None):
+    def normalize_tiles(self, raster: torch.Tensor, tiles: np.ndarray, bits_per_sample: Optional[int] = None,
+                        d_minmax: Optional[torch.Tensor] = None):
         """(bands,H,W) device raster -> (audio int32 planar per tile, audio_base, minmax_dev)."""
         assert raster.is_cuda and raster.is_contiguous() and raster.dim() == 3
         bands, H, W = raster.shape
@@ -146,7 +148,8 @@ class Engine:
             s = _stream_ptr()
             d_tiles = self._upload(tiles.view(np.uint8))
             d_base = self._upload(base)
-            d_minmax = torch.empty(2 * n_tiles, dtype=torch.float64, device=self.device)
+            if d_minmax is None:
+                d_minmax = torch.empty(2 * n_tiles, dtype=torch.float64, device=self.device)
             audio = self._buf("audio", total * 4)
             nat.check(self.L.frb_minmax_tiles(raster.data_ptr(), code, bands, H, W, d_tiles.data_ptr(), n_tiles,
                                               d_minmax.data_ptr(), s), "frb_minmax_tiles")
@@ -157,8 +160,13 @@ class Engine:
         return audio, base, npx, d_minmax, bits_per_sample
 
     def encode_audio(self, audio: torch.Tensor, n_samples: np.ndarray, audio_base: np.ndarray, sample_rates: np.ndarray,
-                     channels: int, bps: int, level: int = 5, blocksize: int = 4096, payload_name: str = "payload"):
-        """int32 planar audio on the device -> (payload uint8 tensor, offsets, sizes). One sync (sizes)."""
+                     channels: int, bps: int, level: int = 5, blocksize: int = 4096, payload_name: str = "payload",
+                     fetch=None):
+        """int32 planar audio on the device -> (payload uint8 tensor, offsets, sizes, frame sizes, subframe offsets).
+        One host synchronisation: the per-stream sizes, which fix where every stream's frames go.  `fetch(d_sizes)`
+        (optional) replaces the plain size download: it gets the device tensor of the sizes (int64[n_streams], filled by the
+        analysis, stream-ordered) and returns them on the host -- encode_tiles uses it to bring the min/max pairs and the
+        other ranks' sizes back in the SAME transfer."""
         n_streams = len(n_samples)
         p = nat.EncodeParams(n_streams, channels, bps, blocksize, level, 0)
         frames = int(((n_samples + blocksize - 1) // blocksize).sum())
@@ -171,8 +179,14 @@ class Engine:
         sizes = np.zeros(n_streams, dtype=np.uint64)
         with torch.cuda.device(self.device):
             s = _stream_ptr()
-            nat.check(self.L.frb_encode_analyse(C.byref(p), audio.data_ptr(), hn.ctypes.data, hr.ctypes.data, hb.ctypes.data,
-                                                ws.data_ptr(), ws.numel(), None, sizes.ctypes.data, s), "frb_encode_analyse")
+            if fetch is None:
+                nat.check(self.L.frb_encode_analyse(C.byref(p), audio.data_ptr(), hn.ctypes.data, hr.ctypes.data, hb.ctypes.data,
+                                                    ws.data_ptr(), ws.numel(), None, sizes.ctypes.data, s), "frb_encode_analyse")
+            else:
+                d_sizes = fetch.d_sizes
+                nat.check(self.L.frb_encode_analyse(C.byref(p), audio.data_ptr(), hn.ctypes.data, hr.ctypes.data, hb.ctypes.data,
+                                                    ws.data_ptr(), ws.numel(), d_sizes.data_ptr(), None, s), "frb_encode_analyse")
+                sizes = np.ascontiguousarray(fetch(), dtype=np.uint64)
             offsets = np.zeros(n_streams, dtype=np.uint64)
             np.cumsum(sizes[:-1], out=offsets[1:])
             total = int(sizes.sum())
@@ -186,18 +200,42 @@ class Engine:
         return payload[:total], offsets.astype(np.int64), sizes.astype(np.int64), fb, sb
 
     def encode_tiles(self, raster: torch.Tensor, tiles: np.ndarray, level: int = 5, blocksize: int = 4096,
-                     payload_name: str = "payload") -> EncodedTiles:
-        """Whole pipeline for a batch of tiles of one device-resident raster."""
+                     payload_name: str = "payload", size_exchange=None) -> EncodedTiles:
+        """Whole pipeline for a batch of tiles of one device-resident raster.
+
+        The step has ONE host round trip in the middle (frame assembly needs every stream's byte size for the output
+        offsets): the tiles' min/max pairs ride along in that transfer, and with `size_exchange`
+        (distributed.SizeExchange: the all-gather of per-tile sizes of the sharded path, cli.py:615-621) the other ranks'
+        sizes do as well -- the collective is enqueued on the stream between analysis and download, so the multi-GPU
+        path costs no extra synchronisation.  The gathered sizes come back as EncodedTiles.sizes_all."""
         bands = raster.shape[0]
         if not (1 <= bands <= 8):
             raise ValueError("FLAC carries at most 8 channels (bands)")
-        audio, base, npx, d_minmax, bits = self.normalize_tiles(raster, tiles)
+        n = len(tiles)
+        extra = size_exchange.recv_count if size_exchange is not None else 0
+        with torch.cuda.device(self.device):
+            combo = torch.empty(3 * n + extra, dtype=torch.float64, device=self.device)     # [sizes int64 n | min/max 2n | gathered sizes]
+        d_sizes = combo[:n].view(torch.int64)
+        d_minmax = combo[n:3 * n]
+        audio, base, npx, d_minmax, bits = self.normalize_tiles(raster, tiles, d_minmax=d_minmax)
         bps = 16 if bits == 16 else 32            # pyflac derives bps from the array dtype (docs/sonos-pyflac.txt:1988-1991)
         rates = sample_rates_for_pixel_counts(npx)                # one vector expression (4096 tiles: 5 ms of Python before)
-        payload, offsets, sizes, fb, sb = self.encode_audio(audio, npx, base, rates, bands, bps, level, blocksize, payload_name)
-        with torch.cuda.device(self.device):
-            minmax = self._download(d_minmax, np.float64, 2 * len(tiles)).reshape(-1, 2)
-        return EncodedTiles(payload, offsets, sizes, minmax, npx, rates, bands, bps, bits, blocksize, fb, sb)
+        got = {}
+
+        def fetch():
+            if size_exchange is not None:
+                size_exchange.enqueue(d_sizes, combo[3 * n:].view(torch.int64))
+            host = self._download(combo.view(torch.uint8), np.uint8, combo.numel() * 8)
+            got["minmax"] = host[8 * n:24 * n].view(np.float64).reshape(-1, 2).copy()
+            if size_exchange is not None:
+                got["sizes_all"] = size_exchange.unpack(host[24 * n:].view(np.int64))
+            return host[:8 * n].view(np.int64)
+
+        fetch.d_sizes = d_sizes
+        payload, offsets, sizes, fb, sb = self.encode_audio(audio, npx, base, rates, bands, bps, level, blocksize, payload_name, fetch=fetch)
+        enc = EncodedTiles(payload, offsets, sizes, got["minmax"], npx, rates, bands, bps, bits, blocksize, fb, sb)
+        enc.sizes_all = got.get("sizes_all")
+        return enc
 
     # ------------------------------------------------------------------ encode, host buffers (pipelined)
     @staticmethod
