@@ -670,7 +670,7 @@ def run_ours(args, rank, world, local):
     def mean_ms(acc):
         return {k: float(np.mean(v)) for k, v in acc.items()}
 
-    audio_bytes = eng.audio_elem_bytes(enc.bps)         # planar audio element the encode kernels read
+    audio_bytes = 2 if (enc.bps == 16 and raster_elem_size(args.workload) <= 2) else 4    # planar audio element the encode kernels read (Engine.audio_elem_bytes)
     enc_alg = samples_local * audio_bytes + comp_bytes           # audio read + compressed bytes produced
     fused_dec = enc.bps == 16 and raster_elem_size(args.workload) <= 2 and nb != 2
     # compressed bytes consumed + output written: pixels of the raster (fused launch) or int32 audio (two-step path)

@@ -44,6 +44,9 @@ class EncodeParams(C.Structure):
                 ("blocksize", C.c_uint32), ("level", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+ENC_AUDIO_I16 = 1          # frb_encode_params.reserved flag (FRB_ENC_AUDIO_I16): d_audio holds int16 elements
+
+
 class DecodeParams(C.Structure):
     _fields_ = [("n_streams", C.c_uint32), ("channels", C.c_uint32), ("bps", C.c_uint32),
                 ("blocksize", C.c_uint32), ("verify_crc16", C.c_uint32), ("reserved", C.c_uint32)]
@@ -85,7 +88,7 @@ _lib = None
 _EXPORTS = [
     "frb_version", "frb_error_string", "frb_last_cuda_error", "frb_device_count", "frb_launch_count",
     "frb_profile_enable", "frb_profile_last_ms", "frb_small_upload", "frb_small_download",
-    "frb_minmax_tiles", "frb_normalize_tiles", "frb_denormalize_tiles", "frb_sample_map_workspace_size",
+    "frb_minmax_tiles", "frb_normalize_tiles", "frb_normalize_tiles_i16", "frb_denormalize_tiles", "frb_sample_map_workspace_size",
     "frb_minmax_flat", "frb_normalize_flat", "frb_denormalize_flat", "frb_selftest_division",
     "frb_encode_workspace_size", "frb_encode_analyse", "frb_encode_emit", "frb_encode_index",
     "frb_decode_workspace_size", "frb_decode_batch", "frb_decode_tiles", "frb_decode_batch_indexed", "frb_decode_tiles_indexed",
@@ -176,6 +179,7 @@ def lib():
     L.frb_profile_last_ms.argtypes = [i32, C.POINTER(C.c_float)]
     L.frb_minmax_tiles.argtypes = [vp, i32, u32, u32, u32, vp, u32, vp, vp]
     L.frb_normalize_tiles.argtypes = [vp, i32, u32, u32, u32, vp, u32, vp, i32, vp, vp, vp, sz, vp]
+    L.frb_normalize_tiles_i16.argtypes = [vp, i32, u32, u32, u32, vp, u32, vp, vp, vp, vp, sz, vp]
     L.frb_sample_map_workspace_size.argtypes = [u32, C.POINTER(sz)]
     L.frb_denormalize_tiles.argtypes = [vp, vp, vp, u32, vp, C.c_double, vp, i32, u32, u32, u32, vp, sz, vp]
     L.frb_selftest_division.argtypes = [C.c_double, C.c_int64, C.c_int64, C.POINTER(C.c_uint64), vp]

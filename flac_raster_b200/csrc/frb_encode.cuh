@@ -34,6 +34,23 @@ constexpr int kMaxPO = 8;
 #define PX(i) ((i) + ((uint32_t)(i) >> 4))
 constexpr int kBufWords = kMaxBlock + kMaxBlock / 16;
 
+// Where the samples come from: planar audio with int32 elements, or -- 16-bps streams of the tile path -- int16 elements
+// (round 1 moved every sample as int32: the mapping kernel wrote 4 bytes per sample and both analysis kernels read them
+// again, 3.8 GB + 2 x 3.9 GB per C3 scene where 16-bit samples need half).  Sample indices are the same in both cases.
+struct EncSrc {
+    const void *audio;
+    uint32_t a16;            // elements are int16
+};
+__device__ __forceinline__ const void *audio_at(const EncSrc &S, int64_t idx) {
+    return reinterpret_cast<const uint8_t *>(S.audio) + idx * (S.a16 ? 2 : 4);
+}
+struct TaskLoc {
+    uint32_t n, a16;
+    const void *src;
+};
+__device__ __forceinline__ int32_t sample_at(const TaskLoc &L, uint32_t i) {
+    return L.a16 ? (int32_t)__ldg(reinterpret_cast<const int16_t *>(L.src) + i) : __ldg(reinterpret_cast<const int32_t *>(L.src) + i);
+}
 struct EncStreamDev {
     uint64_t n_samples;
     int64_t audio_base;
@@ -334,7 +351,7 @@ __device__ __forceinline__ void consider_candidate(uint32_t cand_bits, int cand_
 
 __global__ void __launch_bounds__(kEncThreads, 3)
 k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint32_t channels, uint32_t bps_stream,
-                   uint32_t blocksize, uint32_t level, const int32_t *__restrict__ audio,
+                   uint32_t blocksize, uint32_t level, const EncSrc audio,
                    const float *__restrict__ window, uint32_t slot_words, uint32_t *__restrict__ slots,
                    uint32_t *__restrict__ sub_bits, const uint32_t *__restrict__ task_list, uint32_t side_ch,
                    uint32_t *__restrict__ sub_est) {
@@ -353,7 +370,9 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
     const EncStreamDev st = streams[lo];
     const uint32_t kf = f - st.frame_base;
     const uint32_t n = (kf + 1 < st.n_frames) ? blocksize : (uint32_t)(st.n_samples - (uint64_t)kf * blocksize);
-    const int32_t *src = audio + st.audio_base + (int64_t)c * (int64_t)st.n_samples + (int64_t)kf * blocksize;
+    TaskLoc src;
+    src.n = n; src.a16 = audio.a16;
+    src.src = audio_at(audio, st.audio_base + (int64_t)c * (int64_t)st.n_samples + (int64_t)kf * blocksize);
     int32_t *X = S.buf[1];
     const LevelCfg cfg = level_cfg(level);
     const uint32_t k_limit = bps_stream > 16 ? 31u : 15u;      // by the STREAM's bps, also for a 17-bit side channel
@@ -362,11 +381,11 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
 
     // ---- load, wasted bits, constant check -----------------------------------
     uint32_t orv = 0, diff = 0;
-    const int32_t x_first = n ? __ldg(src) : 0;
+    const int32_t x_first = n ? sample_at(src, 0) : 0;
 #pragma unroll
     for (int s = 0; s < kSPT; s++) {
         const uint32_t i = i0 + s;
-        if (i < n) { int32_t v = __ldg(src + i); X[PX(i)] = v; orv |= (uint32_t)v; diff |= (uint32_t)(v ^ x_first); }
+        if (i < n) { int32_t v = sample_at(src, i); X[PX(i)] = v; orv |= (uint32_t)v; diff |= (uint32_t)(v ^ x_first); }
     }
     orv = block_or(orv, S);
     diff = block_or(diff, S);
@@ -783,15 +802,17 @@ __host__ __device__ __forceinline__ uint32_t ms_channel_code(uint32_t sel) { ret
 
 __global__ void __launch_bounds__(256)
 k_ms_expand(const EncStreamDev *__restrict__ streams, const EncStreamDev *__restrict__ vstreams,
-            const int32_t *__restrict__ audio, int32_t *__restrict__ vaudio, uint32_t parts) {
+            const EncSrc audio, int32_t *__restrict__ vaudio, uint32_t parts) {
     // flattened grid, `parts` CTAs per stream (gridDim.y stops at 65535 streams)
     const uint32_t si = blockIdx.x / parts, part = blockIdx.x - si * parts;
     const EncStreamDev st = streams[si], vs = vstreams[si];
-    const int32_t *l = audio + st.audio_base, *r = l + st.n_samples;
+    TaskLoc l, r;
+    l.n = r.n = 0; l.a16 = r.a16 = audio.a16;
+    l.src = audio_at(audio, st.audio_base); r.src = audio_at(audio, st.audio_base + (int64_t)st.n_samples);
     int32_t *o = vaudio + vs.audio_base;
     const uint64_t n = st.n_samples;
     for (uint64_t i = (uint64_t)part * blockDim.x + threadIdx.x; i < n; i += (uint64_t)parts * blockDim.x) {
-        const int32_t a = l[i], b = r[i];
+        const int32_t a = sample_at(l, (uint32_t)i), b = sample_at(r, (uint32_t)i);
         o[i] = a; o[n + i] = b; o[2 * n + i] = (a + b) >> 1; o[3 * n + i] = a - b;
     }
 }
@@ -1202,7 +1223,7 @@ extern "C" int frb_encode_workspace_size(const frb_encode_params *p, uint64_t to
     return FRB_OK;
 }
 
-extern "C" int frb_encode_analyse(const frb_encode_params *p, const int32_t *d_audio,
+extern "C" int frb_encode_analyse(const frb_encode_params *p, const void *d_audio,
                                   const uint64_t *h_n_samples, const uint32_t *h_sample_rate,
                                   const int64_t *h_audio_base, void *d_workspace, size_t workspace_bytes,
                                   uint64_t *d_stream_bytes, uint64_t *h_stream_bytes, void *stream) {
@@ -1244,7 +1265,12 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const int32_t *d_a
     // (small_upload copies its source into pinned staging before it returns: no synchronisation needed here)
     const std::vector<EncStreamDev> &ahs = ms ? vhs : hs;
     const EncStreamDev *an_streams = ms ? w.vstreams : w.streams;
-    const int32_t *an_audio = ms ? w.vaudio : d_audio;
+    // reserved bit 0: d_audio holds int16 elements (16-bps streams only); the mid/side expansion always writes int32
+    const bool a16 = (p->reserved & 1u) != 0;
+    if (a16 && p->bps != 16) return FRB_ERR_INVALID_ARG;
+    const EncSrc in_audio = {d_audio, a16 ? 1u : 0u};
+    const EncSrc an_audio = ms ? EncSrc{w.vaudio, 0u} : in_audio;
+    const uint32_t an_esz = an_audio.a16 ? 2u : 4u;
     const uint32_t side_ch = ms ? 3u : 0xFFFFFFFFu;
     uint32_t *sub_est = ms ? w.sub_est : nullptr;
     if (ms) {
@@ -1252,7 +1278,7 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const int32_t *d_a
         for (uint32_t i = 0; i < p->n_streams; i++) max_n = std::max<uint64_t>(max_n, hs[i].n_samples);
         uint32_t gx = (uint32_t)std::min<uint64_t>((max_n + 256 * 8 - 1) / (256 * 8), std::max<uint32_t>(1u, (uint32_t)kNumSMs * 16 / p->n_streams));
         if (gx < 1) gx = 1;
-        k_ms_expand<<<gx * p->n_streams, 256, 0, s>>>(w.streams, w.vstreams, d_audio, w.vaudio, gx);
+        k_ms_expand<<<gx * p->n_streams, 256, 0, s>>>(w.streams, w.vstreams, in_audio, w.vaudio, gx);
         FRB_LAUNCH_CHECK("k_ms_expand");
     }
     const uint32_t slot_words = slot_words_for(p->blocksize, enc_slot_bps(p));
@@ -1274,13 +1300,13 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const int32_t *d_a
     std::vector<uint32_t> slow;
     const uint32_t total_tasks = (uint32_t)(frames * an_ch);
     if (fast) {
-        const uint64_t base_words = (uint64_t)(reinterpret_cast<uintptr_t>(an_audio) >> 2);
-        if (reinterpret_cast<uintptr_t>(an_audio) & 3u) return FRB_ERR_INVALID_ARG;
+        const uint64_t base_addr = (uint64_t)reinterpret_cast<uintptr_t>(an_audio.audio);
+        if (base_addr & (an_esz - 1)) return FRB_ERR_INVALID_ARG;
         for (uint32_t i = 0; i < p->n_streams; i++) {
             const EncStreamDev &d = ahs[i];
             const bool tail = (d.n_samples % p->blocksize) != 0;
             for (uint32_t c = 0; c < an_ch; c++) {
-                const bool aligned = ((base_words + (uint64_t)d.audio_base + (uint64_t)c * d.n_samples) & 3u) == 0;
+                const bool aligned = ((base_addr + ((uint64_t)d.audio_base + (uint64_t)c * d.n_samples) * an_esz) & 15u) == 0;
                 for (uint32_t k = aligned ? (tail ? d.n_frames - 1 : d.n_frames) : 0; k < d.n_frames; k++)
                     slow.push_back((d.frame_base + k) * an_ch + c);
             }

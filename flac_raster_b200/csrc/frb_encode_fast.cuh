@@ -65,16 +65,12 @@ k_frame_table(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
     out[f] = d;
 }
 
-struct TaskLoc {
-    uint32_t n;
-    const int32_t *src;
-};
-__device__ __forceinline__ TaskLoc locate_task(const FrameDesc *__restrict__ frames, const int32_t *__restrict__ audio,
-                                               uint32_t f, uint32_t c) {
+__device__ __forceinline__ TaskLoc locate_task(const FrameDesc *__restrict__ frames, const EncSrc &S, uint32_t f, uint32_t c) {
     const FrameDesc d = frames[f];
     TaskLoc L;
     L.n = d.n;
-    L.src = audio + d.src0 + (int64_t)c * (int64_t)d.ns;
+    L.a16 = S.a16;
+    L.src = audio_at(S, d.src0 + (int64_t)c * (int64_t)d.ns);
     return L;
 }
 // The fast path handles full 4096-sample blocks whose first sample is 16-byte aligned (the host lists every
@@ -83,9 +79,36 @@ __device__ __forceinline__ bool fast_eligible(const TaskLoc &L) {
     return L.n == (uint32_t)kMaxBlock && (reinterpret_cast<uintptr_t>(L.src) & 15u) == 0;
 }
 
+// two sign-extended int16 samples of a 32-bit word, one instruction each (the compiler emits PRMT with sign replication /
+// an arithmetic shift; __byte_perm cannot express it: it masks the selector nibbles to 3 bits)
+__device__ __forceinline__ int32_t s16_lo(uint32_t w) { return (int32_t)(int16_t)(uint16_t)w; }
+__device__ __forceinline__ int32_t s16_hi(uint32_t w) { return (int32_t)w >> 16; }
+
 // 16 own samples at xs[12..27], 12 halo samples (previous thread's tail, zeros for thread 0) at xs[0..11]
-__device__ __forceinline__ void load_samples28(const int32_t *__restrict__ src, int tid, int32_t (&xs)[28]) {
-    const int4 *p = reinterpret_cast<const int4 *>(src + tid * kSPT);
+__device__ __forceinline__ void load_samples28(const TaskLoc &L, int tid, int32_t (&xs)[28]) {
+    if (L.a16) {
+        // int16 audio: the thread's 16 samples are 32 bytes (two 16-byte loads), the halo 24 bytes (three 8-byte loads)
+        const uint4 *p = reinterpret_cast<const uint4 *>(reinterpret_cast<const int16_t *>(L.src) + tid * kSPT);
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const uint4 v = __ldg(p + q);
+            xs[12 + 8 * q] = s16_lo(v.x); xs[13 + 8 * q] = s16_hi(v.x); xs[14 + 8 * q] = s16_lo(v.y); xs[15 + 8 * q] = s16_hi(v.y);
+            xs[16 + 8 * q] = s16_lo(v.z); xs[17 + 8 * q] = s16_hi(v.z); xs[18 + 8 * q] = s16_lo(v.w); xs[19 + 8 * q] = s16_hi(v.w);
+        }
+        if (tid > 0) {
+            const uint2 *h = reinterpret_cast<const uint2 *>(p) - 3;
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const uint2 v = __ldg(h + q);
+                xs[4 * q] = s16_lo(v.x); xs[4 * q + 1] = s16_hi(v.x); xs[4 * q + 2] = s16_lo(v.y); xs[4 * q + 3] = s16_hi(v.y);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 12; q++) xs[q] = 0;
+        }
+        return;
+    }
+    const int4 *p = reinterpret_cast<const int4 *>(reinterpret_cast<const int32_t *>(L.src) + tid * kSPT);
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const int4 v = __ldg(p + q);
@@ -258,7 +281,7 @@ struct StatsShared {
 template <bool WIDE, int NLAGS>
 __global__ void __launch_bounds__(kEncThreads, (NLAGS > 9 || WIDE) ? 2 : FRB_STATS_MINB)
 k_enc_stats(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps_stream,
-            uint32_t windows, uint32_t max_po_cfg, const int32_t *__restrict__ audio,
+            uint32_t windows, uint32_t max_po_cfg, const EncSrc audio,
             const float *__restrict__ window, EncSubStats *__restrict__ stats, double *__restrict__ autoc_out,
             unsigned long long *__restrict__ fx_fin, uint32_t c0, uint32_t side_extra) {
     // c0 / side_extra: channel offset of this launch and 1 when its subframes carry one more bit than the stream (the
@@ -272,7 +295,7 @@ k_enc_stats(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bp
     constexpr uint32_t n = kMaxBlock;
     constexpr int HALO = NLAGS > 0 ? NLAGS - 1 : 0;         // 8 or 12: multiples of 4, so the window reads stay 16-byte aligned
     int32_t xs[28];
-    load_samples28(L.src, tid, xs);
+    load_samples28(L, tid, xs);
     // full-length window for this thread's samples and halo, fetched together with the samples
     float wv[kSPT + HALO + 1];
     if (NLAGS > 0) {
@@ -286,7 +309,7 @@ k_enc_stats(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bp
     }
     // ---- wasted bits / constant ----
     uint32_t orv = 0, diff = 0;
-    const int32_t x_first = __ldg(L.src);
+    const int32_t x_first = sample_at(L, 0);
 #pragma unroll
     for (int s = 0; s < kSPT; s++) { orv |= (uint32_t)xs[12 + s]; diff |= (uint32_t)(xs[12 + s] ^ x_first); }
     orv = __reduce_or_sync(0xFFFFFFFFu, orv);
@@ -481,7 +504,7 @@ k_enc_stats(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bp
 // from the finest partition sums k_enc_stats stored.
 __global__ void __launch_bounds__(128)
 k_enc_fixed(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps_stream, uint32_t max_po_cfg, uint32_t total_tasks,
-            const int32_t *__restrict__ audio, EncSubStats *__restrict__ stats, const unsigned long long *__restrict__ fx_fin,
+            const EncSrc audio, EncSubStats *__restrict__ stats, const unsigned long long *__restrict__ fx_fin,
             uint32_t side_ch) {
     const int lane = threadIdx.x & 31;
     const uint32_t task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -620,7 +643,7 @@ template <int MAXO>
 __global__ void __launch_bounds__(128)
 k_enc_model(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps_stream,
             uint32_t blocksize, uint32_t windows, uint32_t max_lpc_cfg, uint32_t n_cands, uint32_t total_tasks,
-            const int32_t *__restrict__ audio, EncSubStats *__restrict__ stats, const double *__restrict__ autoc_in,
+            const EncSrc audio, EncSubStats *__restrict__ stats, const double *__restrict__ autoc_in,
             EncCand *__restrict__ cands, uint32_t side_ch) {
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t task = gid / n_cands, slot = gid - task * n_cands;
@@ -744,15 +767,17 @@ __device__ __forceinline__ uint32_t residual16(const int32_t (&xs)[28], const in
 
 // Rare path (a residual magnitude reached 2^30): the oracle's exact test r > INT32_MAX || r <= INT32_MIN in 64-bit
 // arithmetic for this thread's samples, read back from global memory so the hot path keeps its arrays in registers.
-__device__ __noinline__ bool residual_overflows(const int32_t *__restrict__ src, uint32_t wasted, const EncCand *__restrict__ C, int tid) {
+__device__ __noinline__ bool residual_overflows(const void *src, uint32_t a16, uint32_t wasted, const EncCand *__restrict__ C, int tid) {
     const int order = C->order, shift = C->shift;
+    TaskLoc L;
+    L.src = src; L.a16 = a16; L.n = kMaxBlock;
     bool bad = false;
     for (int s = 0; s < kSPT; s++) {
         const int i = tid * kSPT + s;
         if (i < order) continue;
         long long acc = 0;
-        for (int j = 0; j < order; j++) acc += (long long)C->coefs[j] * (long long)(src[i - 1 - j] >> wasted);
-        const long long v = (long long)(src[i] >> wasted) - (acc >> shift);
+        for (int j = 0; j < order; j++) acc += (long long)C->coefs[j] * (long long)(sample_at(L, (uint32_t)(i - 1 - j)) >> wasted);
+        const long long v = (long long)(sample_at(L, (uint32_t)i) >> wasted) - (acc >> shift);
         if (v > 2147483647ll || v <= -2147483648ll) bad = true;
     }
     return bad;
@@ -761,7 +786,7 @@ __device__ __noinline__ bool residual_overflows(const int32_t *__restrict__ src,
 template <bool WIDE>
 __global__ void __launch_bounds__(kEncThreads, WIDE ? 2 : FRB_CODE_MINB)
 k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps_stream,
-           uint32_t max_po_cfg, uint32_t n_cands, const int32_t *__restrict__ audio,
+           uint32_t max_po_cfg, uint32_t n_cands, const EncSrc audio,
            const EncSubStats *__restrict__ stats, const EncCand *__restrict__ cands, uint32_t slot_words,
            uint32_t *__restrict__ slots, uint32_t *__restrict__ sub_bits, uint32_t c0, uint32_t side_extra,
            uint32_t *__restrict__ sub_est) {
@@ -777,7 +802,7 @@ k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps
     const uint32_t wasted = stp->wasted, st_flags = stp->flags;
     const uint32_t bps = bps_stream + side_extra - wasted;
     int32_t xs[28];
-    load_samples28(L.src, tid, xs);
+    load_samples28(L, tid, xs);
     if (wasted) {
 #pragma unroll
         for (int j = 0; j < 28; j++) xs[j] >>= wasted;
@@ -809,7 +834,7 @@ k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps
             for (int s = 0; s < kSPT; s++) { if (s < C.order) r[s] = 0; ora |= (uint32_t)abs(r[s]); }   // order <= 12 < 16
         }
         bool bad = false;
-        if (Cg != nullptr && ((WIDE && him) || ora >= 0x40000000u)) bad = residual_overflows(L.src, wasted, Cg, tid);
+        if (Cg != nullptr && ((WIDE && him) || ora >= 0x40000000u)) bad = residual_overflows(L.src, L.a16, wasted, Cg, tid);
         *bad_out = bad;
         return ora;
     };
@@ -934,7 +959,7 @@ k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps
     }
     if (type >= 2) {
         if (tid >= 32 && tid < 32 + order)                   // warm-up sample j = tid - 32
-            put_bits_atomic(S.bitbuf, pos0 + (uint32_t)(tid - 32) * bps, (uint32_t)(__ldg(L.src + (tid - 32)) >> wasted) & mask_bps, bps);
+            put_bits_atomic(S.bitbuf, pos0 + (uint32_t)(tid - 32) * bps, (uint32_t)(sample_at(L, (uint32_t)(tid - 32)) >> wasted) & mask_bps, bps);
         const uint32_t pos1 = pos0 + (uint32_t)order * bps;
         if (type == 3) {
             const uint32_t prec = (uint32_t)best_prec;

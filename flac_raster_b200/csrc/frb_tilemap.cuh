@@ -148,20 +148,23 @@ k_build_norm_lut(const double *__restrict__ minmax, int bits, int32_t *__restric
     }
 }
 
-template <typename T>
+// A: element type of the planar audio (int32_t, or int16_t for 16-bit audio of 8/16-bit rasters: half the bytes written
+// here and half the bytes both analysis kernels read back; G * sizeof(A) stays a multiple of 16 for those types)
+template <typename T, typename A>
 __global__ void __launch_bounds__(kMapThreads)
 k_normalize_tiles(const T *__restrict__ raster, uint32_t bands, uint32_t H, uint32_t W,
                   const frb_tile *__restrict__ tiles, const double *__restrict__ minmax, int bits,
-                  int32_t *__restrict__ audio, const int64_t *__restrict__ audio_base,
+                  A *__restrict__ audio, const int64_t *__restrict__ audio_base,
                   const int32_t *__restrict__ lut_all, uint32_t parts) {
-    constexpr int G = MapGroup<T>::G, AV = MapGroup<T>::AV;
+    constexpr int G = MapGroup<T>::G, AV = G * (int)sizeof(A) / 16;
+    static_assert(sizeof(A) == 4 || (G * sizeof(A)) % 16 == 0, "int16 audio needs 8 or 16 elements per group");
     const uint32_t tile_i = blockIdx.x / parts, part = blockIdx.x - tile_i * parts;
     const frb_tile t = tiles[tile_i];
     const uint32_t n = t.h * t.w;
     const double mn = minmax[2 * tile_i], mx = minmax[2 * tile_i + 1];
     const double range = (mx <= mn) ? 1.0 : __dsub_rn(mx, mn);
     const double scale = scale_for_bits(bits);
-    int32_t *dst = audio + audio_base[tile_i];
+    A *dst = audio + audio_base[tile_i];
     const uint32_t rows = bands * t.h;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool use_lut = is_small_int<T>::value && lut_all != nullptr && (mx - mn < (double)kNormLutCap);
@@ -177,25 +180,32 @@ k_normalize_tiles(const T *__restrict__ raster, uint32_t bands, uint32_t H, uint
     for (uint32_t ry = part * kMapWarps + warp; ry < rows; ry += parts * kMapWarps) {
         const uint32_t c = ry / t.h, y = ry - c * t.h;
         const T *src = raster + ((size_t)c * H + (t.row_off + y)) * W + t.col_off;
-        int32_t *out = dst + (size_t)c * n + (size_t)y * t.w;
+        A *out = dst + (size_t)c * n + (size_t)y * t.w;
         const RowSplit<T> rs(src, t.w);
-        if ((uint32_t)lane < rs.head) out[lane] = map(src[lane]);
-        if (rs.tail0 + lane < t.w) out[rs.tail0 + lane] = map(src[rs.tail0 + lane]);
+        if ((uint32_t)lane < rs.head) out[lane] = (A)map(src[lane]);
+        if (rs.tail0 + lane < t.w) out[rs.tail0 + lane] = (A)map(src[rs.tail0 + lane]);
         const T *body = src + rs.head;
-        int32_t *obody = out + rs.head;
+        A *obody = out + rs.head;
         const bool ovec = (reinterpret_cast<uintptr_t>(obody) & 15u) == 0;
         auto emit = [&](uint32_t g, const T (&e)[G]) {
             int32_t r[G];
 #pragma unroll
             for (int j = 0; j < G; j++) r[j] = map(e[j]);
-            int32_t *o = obody + (size_t)g * G;
+            A *o = obody + (size_t)g * G;
             if (ovec) {
+                if (sizeof(A) == 4) {
 #pragma unroll
-                for (int q = 0; q < AV; q++)
-                    st_stream16(o + 4 * q, make_uint4((uint32_t)r[4 * q], (uint32_t)r[4 * q + 1], (uint32_t)r[4 * q + 2], (uint32_t)r[4 * q + 3]));
+                    for (int q = 0; q < AV; q++)
+                        st_stream16(o + 4 * q, make_uint4((uint32_t)r[4 * q], (uint32_t)r[4 * q + 1], (uint32_t)r[4 * q + 2], (uint32_t)r[4 * q + 3]));
+                } else {
+                    auto pk = [&](int j) { return __byte_perm((uint32_t)r[j], (uint32_t)r[j + 1], 0x5410); };   // two int16 per word
+#pragma unroll
+                    for (int q = 0; q < AV; q++)
+                        st_stream16(o + 8 * q, make_uint4(pk(8 * q), pk(8 * q + 2), pk(8 * q + 4), pk(8 * q + 6)));
+                }
             } else {
 #pragma unroll
-                for (int j = 0; j < G; j++) o[j] = r[j];
+                for (int j = 0; j < G; j++) o[j] = (A)r[j];
             }
         };
         uint32_t g = lane;
@@ -344,8 +354,39 @@ extern "C" int frb_normalize_tiles(const void *d_raster, int dtype, uint32_t ban
         lut = w.norm_lut;
     }
     const uint32_t parts = tile_grid_parts(n_tiles, bands * H), grid = parts * n_tiles;
-    FRB_DISPATCH_DTYPE(dtype, (k_normalize_tiles<T><<<grid, kMapThreads, 0, s>>>((const T *)d_raster, bands, H, W, d_tiles, d_minmax,
-                                                                                       bits_per_sample, d_audio, d_audio_base, lut, parts)));
+    FRB_DISPATCH_DTYPE(dtype, (k_normalize_tiles<T, int32_t><<<grid, kMapThreads, 0, s>>>((const T *)d_raster, bands, H, W, d_tiles, d_minmax,
+                                                                                                bits_per_sample, d_audio, d_audio_base, lut, parts)));
+    FRB_LAUNCH_CHECK("k_normalize_tiles");
+    return FRB_OK;
+}
+
+// The same mapping with int16 audio elements: 8/16-bit rasters at 16 bits per sample only (the tile path of the
+// BASELINE configs C2, C3 and C5).  Consumed by frb_encode_analyse with FRB_ENC_AUDIO_I16 set in params.reserved.
+extern "C" int frb_normalize_tiles_i16(const void *d_raster, int dtype, uint32_t bands, uint32_t H, uint32_t W,
+                                       const frb_tile *d_tiles, uint32_t n_tiles, const double *d_minmax,
+                                       int16_t *d_audio, const int64_t *d_audio_base,
+                                       void *d_workspace, size_t workspace_bytes, void *stream) {
+    using namespace frb;
+    if (!d_raster || !d_tiles || !d_minmax || !d_audio || !d_audio_base || dtype < 0 || dtype > FRB_I16 || !bands || !n_tiles)
+        return FRB_ERR_INVALID_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int32_t *lut = nullptr;
+    if (d_workspace) {
+        MapWorkspace w;
+        if (map_ws_layout(n_tiles, d_workspace, &w) > workspace_bytes) return FRB_ERR_OVERFLOW;
+        k_build_norm_lut<<<8 * n_tiles, 256, 0, s>>>(d_minmax, 16, w.norm_lut, 8);
+        FRB_LAUNCH_CHECK("k_build_norm_lut");
+        lut = w.norm_lut;
+    }
+    const uint32_t parts = tile_grid_parts(n_tiles, bands * H), grid = parts * n_tiles;
+#define FRB_NORM16(T) k_normalize_tiles<T, int16_t><<<grid, kMapThreads, 0, s>>>((const T *)d_raster, bands, H, W, d_tiles, d_minmax, 16, d_audio, d_audio_base, lut, parts)
+    switch (dtype) {
+        case FRB_U8: FRB_NORM16(uint8_t); break;
+        case FRB_I8: FRB_NORM16(int8_t); break;
+        case FRB_U16: FRB_NORM16(uint16_t); break;
+        default: FRB_NORM16(int16_t); break;
+    }
+#undef FRB_NORM16
     FRB_LAUNCH_CHECK("k_normalize_tiles");
     return FRB_OK;
 }

@@ -109,9 +109,10 @@ class Engine:
         self._ws.clear()
 
     @staticmethod
-    def audio_elem_bytes(bps: int) -> int:
-        """Bytes per sample of the planar audio buffer between the mapping kernels and the codec kernels."""
-        return 4
+    def audio_elem_bytes(bits_per_sample: int, dtype_code: int) -> int:
+        """Bytes per sample of the planar audio buffer between the mapping kernels and the codec kernels: int16 for
+        16-bit audio of 8/16-bit rasters (the tile path of C2/C3/C5), int32 otherwise."""
+        return 2 if (bits_per_sample == 16 and dtype_code <= nat.DTYPE_CODES["int16"]) else 4
 
     def _upload(self, arr: np.ndarray) -> torch.Tensor:
         """A small host array -> a fresh device tensor (uint8 view) on the current stream, through the library's pinned
@@ -131,8 +132,10 @@ class Engine:
 
     # ------------------------------------------------------------------ encode
     def normalize_tiles(self, raster: torch.Tensor, tiles: np.ndarray, bits_per_sample: Optional[int] = None,
-                        d_minmax: Optional[torch.Tensor] = None):
-        """(bands,H,W) device raster -> (audio int32 planar per tile, audio_base, minmax_dev)."""
+                        d_minmax: Optional[torch.Tensor] = None, audio_i16: bool = False):
+        """(bands,H,W) device raster -> (planar audio per tile, audio_base, n_px, minmax_dev, bits).  The audio is int32
+        in a uint8 workspace buffer; with `audio_i16` (encode_tiles asks for it) it is an int16 tensor whenever
+        audio_elem_bytes allows (encode_audio takes either; denormalize_tiles takes int32 only)."""
         assert raster.is_cuda and raster.is_contiguous() and raster.dim() == 3
         bands, H, W = raster.shape
         dt = str(raster.dtype).replace("torch.", "")
@@ -150,25 +153,37 @@ class Engine:
             d_base = self._upload(base)
             if d_minmax is None:
                 d_minmax = torch.empty(2 * n_tiles, dtype=torch.float64, device=self.device)
-            audio = self._buf("audio", total * 4)
+            esz = self.audio_elem_bytes(bits_per_sample, code) if audio_i16 else 4
+            audio = self._buf("audio", total * esz)
+            if esz == 2:
+                audio = audio[: total * 2].view(torch.int16)
             nat.check(self.L.frb_minmax_tiles(raster.data_ptr(), code, bands, H, W, d_tiles.data_ptr(), n_tiles,
                                               d_minmax.data_ptr(), s), "frb_minmax_tiles")
             mws = self._map_ws(n_tiles)
-            nat.check(self.L.frb_normalize_tiles(raster.data_ptr(), code, bands, H, W, d_tiles.data_ptr(), n_tiles,
-                                                 d_minmax.data_ptr(), bits_per_sample, audio.data_ptr(),
-                                                 d_base.data_ptr(), mws.data_ptr(), mws.numel(), s), "frb_normalize_tiles")
+            if esz == 2:
+                nat.check(self.L.frb_normalize_tiles_i16(raster.data_ptr(), code, bands, H, W, d_tiles.data_ptr(), n_tiles,
+                                                         d_minmax.data_ptr(), audio.data_ptr(),
+                                                         d_base.data_ptr(), mws.data_ptr(), mws.numel(), s), "frb_normalize_tiles_i16")
+            else:
+                nat.check(self.L.frb_normalize_tiles(raster.data_ptr(), code, bands, H, W, d_tiles.data_ptr(), n_tiles,
+                                                     d_minmax.data_ptr(), bits_per_sample, audio.data_ptr(),
+                                                     d_base.data_ptr(), mws.data_ptr(), mws.numel(), s), "frb_normalize_tiles")
         return audio, base, npx, d_minmax, bits_per_sample
 
     def encode_audio(self, audio: torch.Tensor, n_samples: np.ndarray, audio_base: np.ndarray, sample_rates: np.ndarray,
                      channels: int, bps: int, level: int = 5, blocksize: int = 4096, payload_name: str = "payload",
                      fetch=None):
-        """int32 planar audio on the device -> (payload uint8 tensor, offsets, sizes, frame sizes, subframe offsets).
+        """planar audio on the device (int32, or int16 for 16-bps streams: the element type is taken from the tensor) ->
+        (payload uint8 tensor, offsets, sizes, frame sizes, subframe offsets).
         One host synchronisation: the per-stream sizes, which fix where every stream's frames go.  `fetch(d_sizes)`
         (optional) replaces the plain size download: it gets the device tensor of the sizes (int64[n_streams], filled by the
         analysis, stream-ordered) and returns them on the host -- encode_tiles uses it to bring the min/max pairs and the
         other ranks' sizes back in the SAME transfer."""
         n_streams = len(n_samples)
-        p = nat.EncodeParams(n_streams, channels, bps, blocksize, level, 0)
+        a16 = audio.dtype == torch.int16
+        if a16 and bps != 16:
+            raise ValueError("int16 audio is for 16-bps streams")
+        p = nat.EncodeParams(n_streams, channels, bps, blocksize, level, nat.ENC_AUDIO_I16 if a16 else 0)
         frames = int(((n_samples + blocksize - 1) // blocksize).sum())
         ws_bytes = C.c_size_t(0)
         nat.check(self.L.frb_encode_workspace_size(C.byref(p), frames, C.byref(ws_bytes)), "frb_encode_workspace_size")
@@ -217,7 +232,7 @@ class Engine:
             combo = torch.empty(3 * n + extra, dtype=torch.float64, device=self.device)     # [sizes int64 n | min/max 2n | gathered sizes]
         d_sizes = combo[:n].view(torch.int64)
         d_minmax = combo[n:3 * n]
-        audio, base, npx, d_minmax, bits = self.normalize_tiles(raster, tiles, d_minmax=d_minmax)
+        audio, base, npx, d_minmax, bits = self.normalize_tiles(raster, tiles, d_minmax=d_minmax, audio_i16=True)
         bps = 16 if bits == 16 else 32            # pyflac derives bps from the array dtype (docs/sonos-pyflac.txt:1988-1991)
         rates = sample_rates_for_pixel_counts(npx)                # one vector expression (4096 tiles: 5 ms of Python before)
         got = {}

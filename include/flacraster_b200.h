@@ -77,8 +77,8 @@ int frb_profile_last_ms(int which, float *ms);
  * Its audio is `bands` planar channels of n = h*w samples (row-major), the
  * planar equivalent of the reference's interleaved (H*W, bands) array
  * (converter.py:99-110): channel c, sample i == pixel i of band c.
- * Audio is always int32 on the device: tile t, channel c, sample i lives at
- * audio[audio_base[t] + c*n_t + i].
+ * Audio is int32 on the device (int16 on the 16-bit tile path, see frb_normalize_tiles_i16): tile t, channel c,
+ * sample i lives at audio[audio_base[t] + c*n_t + i].
  */
 typedef struct frb_tile {
     uint32_t row_off, col_off, h, w;
@@ -96,6 +96,14 @@ int frb_normalize_tiles(const void *d_raster, int dtype, uint32_t bands, uint32_
                         const frb_tile *d_tiles, uint32_t n_tiles, const double *d_minmax,
                         int bits_per_sample, int32_t *d_audio, const int64_t *d_audio_base,
                         void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* The same mapping with int16 audio elements (same indices, half the bytes): 8/16-bit rasters at 16 bits per
+ * sample only.  frb_encode_analyse reads such a buffer when FRB_ENC_AUDIO_I16 is set in frb_encode_params.reserved.
+ * Round 1 moved every sample as int32 (3.8 GB written + 2 x 3.9 GB read back per C3 scene). */
+int frb_normalize_tiles_i16(const void *d_raster, int dtype, uint32_t bands, uint32_t H, uint32_t W,
+                            const frb_tile *d_tiles, uint32_t n_tiles, const double *d_minmax,
+                            int16_t *d_audio, const int64_t *d_audio_base,
+                            void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* Optional device workspace for frb_normalize_tiles / frb_denormalize_tiles: exact lookup tables that
  * replace the per-sample fp64 divisions (entries are computed with the same operations, so results
@@ -138,8 +146,10 @@ typedef struct frb_encode_params {
     uint32_t bps;               /* 16 or 32 (what pyflac derives, docs/sonos-pyflac.txt:1988-1991) */
     uint32_t blocksize;         /* 16..4096 */
     uint32_t level;             /* 0..8 */
-    uint32_t reserved;
+    uint32_t reserved;          /* flags: FRB_ENC_AUDIO_I16 */
 } frb_encode_params;
+/* d_audio of frb_encode_analyse holds int16 elements (bps must be 16; written by frb_normalize_tiles_i16) */
+#define FRB_ENC_AUDIO_I16 1u
 
 /* Bytes of device workspace needed by frb_encode_analyse/emit for
  * `total_frames` frames (sum over streams of ceil(n/blocksize)). */
@@ -152,7 +162,7 @@ int frb_encode_workspace_size(const frb_encode_params *p, uint64_t total_frames,
  * d_stream_bytes (device, n_streams uint64, optional) receives each stream's
  * frame payload size; h_stream_bytes (host, n_streams uint64, optional) is
  * filled after an internal stream synchronise when non-NULL. */
-int frb_encode_analyse(const frb_encode_params *p, const int32_t *d_audio,
+int frb_encode_analyse(const frb_encode_params *p, const void *d_audio /* int32, or int16 with FRB_ENC_AUDIO_I16 */,
                        const uint64_t *h_n_samples, const uint32_t *h_sample_rate,
                        const int64_t *h_audio_base, void *d_workspace, size_t workspace_bytes,
                        uint64_t *d_stream_bytes, uint64_t *h_stream_bytes, void *stream);

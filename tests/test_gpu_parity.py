@@ -641,6 +641,41 @@ def test_host_decode_pipeline_equals_raster(nat, torch_cuda):
         assert torch.equal(out.view(torch.int16), want.view(torch.int16))
 
 
+@pytest.mark.parametrize("dt", ["uint8", "int8", "uint16", "int16"])
+def test_int16_audio_equals_int32_audio(nat, oracle, torch_cuda, dt):
+    """The tile path keeps 16-bit audio as int16 between the mapping kernel and the analysis kernels
+    (frb_normalize_tiles_i16 + FRB_ENC_AUDIO_I16): same samples as the int32 buffer on aligned and ragged windows, and
+    the frames coded from either buffer are the same bytes (fast kernels on aligned full blocks, the one-kernel
+    encoder on unaligned channels and tail frames)."""
+    torch = torch_cuda
+    from flac_raster_b200.engine import Engine
+    from flac_raster_b200 import _native as natmod
+    from flac_raster_b200.normalization import sample_rates_for_pixel_counts
+    rng = np.random.default_rng(11)
+    bands, H, W = 3, 300, 523
+    info = np.iinfo(dt)
+    yy, xx = np.mgrid[0:H, 0:W]
+    x = np.stack([np.clip(info.min // 2 + (info.max - info.min) // 3 * (1 + np.sin(xx / 19.0 + b) * np.cos(yy / 13.0)) / 2
+                          + rng.integers(-3, 4, xx.shape), info.min, info.max).astype(dt) for b in range(bands)])
+    tiles = np.zeros(5, dtype=natmod.TILE_DTYPE)
+    tiles[0] = (0, 0, 128, 128); tiles[1] = (1, 3, 67, 211); tiles[2] = (7, 13, 33, 37); tiles[3] = (44, 1, 256, 512); tiles[4] = (2, 5, 5, 1)
+    eng = Engine()
+    dev = torch.from_numpy(x.view(np.uint8).reshape(-1)).cuda().view(getattr(torch, dt)).reshape(bands, H, W)
+    a32, base, npx, d_mm, bits = eng.normalize_tiles(dev, tiles)
+    total = int((npx * bands).sum())
+    a32 = a32[: total * 4].view(torch.int32).clone()
+    a16, base16, _, _, _ = eng.normalize_tiles(dev, tiles, audio_i16=True)
+    assert a16.dtype == torch.int16 and a16.numel() == total and np.array_equal(base, base16)
+    assert torch.equal(a16.to(torch.int32), a32)
+    rates = sample_rates_for_pixel_counts(npx)
+    for level in (0, 5, 8):
+        p16, o16, s16, fb16, sb16 = eng.encode_audio(a16, npx, base, rates, bands, 16, level, 4096, payload_name="p16")
+        p32, o32, s32, fb32, sb32 = eng.encode_audio(a32, npx, base, rates, bands, 16, level, 4096, payload_name="p32")
+        assert np.array_equal(s16, s32) and torch.equal(p16, p32) and torch.equal(fb16, fb32) and torch.equal(sb16, sb32), level
+    with pytest.raises(ValueError):
+        eng.encode_audio(a16, npx, base, rates, bands, 32, 5, 4096)
+
+
 @pytest.mark.parametrize("dt", ["uint8", "int16", "uint16", "float32", "float64", "int32"])
 def test_tile_mapping_odd_alignment_vs_oracle(nat, torch_cuda, dt):
     """Per-tile min/max, normalise and denormalise on windows whose rows start at odd element offsets and
