@@ -273,7 +273,7 @@ struct StatsShared {
 };
 
 #ifndef FRB_STATS_MINB
-#define FRB_STATS_MINB 4
+#define FRB_STATS_MINB 3
 #endif
 #ifndef FRB_CODE_MINB
 #define FRB_CODE_MINB 4

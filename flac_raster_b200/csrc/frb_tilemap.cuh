@@ -62,6 +62,21 @@ __device__ __forceinline__ void load_group(const T *p, T (&e)[MapGroup<T>::G]) {
 #pragma unroll
     for (int j = 0; j < MapGroup<T>::G; j++) e[j] = u.e[j];
 }
+// the same in two steps: the vectors as loaded (what a look-ahead buffer should hold: 4 registers per 16 bytes, whatever
+// the element size), unpacked when they are used
+template <typename T>
+__device__ __forceinline__ void load_group_raw(const T *p, uint4 (&v)[MapGroup<T>::TV]) {
+#pragma unroll
+    for (int q = 0; q < MapGroup<T>::TV; q++) v[q] = ld_stream16(reinterpret_cast<const uint8_t *>(p) + 16 * q);
+}
+template <typename T>
+__device__ __forceinline__ void unpack_group(const uint4 (&v)[MapGroup<T>::TV], T (&e)[MapGroup<T>::G]) {
+    union { uint4 v[MapGroup<T>::TV]; T e[MapGroup<T>::G]; } u;
+#pragma unroll
+    for (int q = 0; q < MapGroup<T>::TV; q++) u.v[q] = v[q];
+#pragma unroll
+    for (int j = 0; j < MapGroup<T>::G; j++) e[j] = u.e[j];
+}
 template <typename T>
 __device__ __forceinline__ void store_group(T *p, const T (&e)[MapGroup<T>::G]) {
     union { uint4 v[MapGroup<T>::TV]; T e[MapGroup<T>::G]; } u;
@@ -150,14 +165,23 @@ k_build_norm_lut(const double *__restrict__ minmax, int bits, int32_t *__restric
 
 // A: element type of the planar audio (int32_t, or int16_t for 16-bit audio of 8/16-bit rasters: half the bytes written
 // here and half the bytes both analysis kernels read back; G * sizeof(A) stays a multiple of 16 for those types)
-template <typename T, typename A>
-__global__ void __launch_bounds__(kMapThreads)
+// SLUT (int16 audio only): the CTA copies its tile's table into shared memory first (at most 32 KB) and gathers from
+// there.  Round 2 measured the global-memory gathers at 1.40 ms per C3 scene for 3.9 GB of traffic (2.8 TB/s, 24
+// instructions per sample, 64-bit address arithmetic and an L1 tag lookup per distinct line of every gather); round 1
+// had rejected a shared-memory table because the int32 table of the time took 64 KB per CTA.
+#ifndef FRB_NORM_MINB
+#define FRB_NORM_MINB 4
+#endif
+template <typename T, typename A, bool SLUT = false>
+__global__ void __launch_bounds__(kMapThreads, (sizeof(T) <= 2 && sizeof(A) == 2) ? FRB_NORM_MINB : 1)
 k_normalize_tiles(const T *__restrict__ raster, uint32_t bands, uint32_t H, uint32_t W,
                   const frb_tile *__restrict__ tiles, const double *__restrict__ minmax, int bits,
                   A *__restrict__ audio, const int64_t *__restrict__ audio_base,
                   const int32_t *__restrict__ lut_all, uint32_t parts) {
     constexpr int G = MapGroup<T>::G, AV = G * (int)sizeof(A) / 16;
     static_assert(sizeof(A) == 4 || (G * sizeof(A)) % 16 == 0, "int16 audio needs 8 or 16 elements per group");
+    static_assert(!SLUT || (sizeof(A) == 2 && is_small_int<T>::value), "shared-memory table: 8/16-bit rasters, int16 audio");
+    extern __shared__ __align__(16) int16_t s_lut[];
     const uint32_t tile_i = blockIdx.x / parts, part = blockIdx.x - tile_i * parts;
     const frb_tile t = tiles[tile_i];
     const uint32_t n = t.h * t.w;
@@ -171,57 +195,98 @@ k_normalize_tiles(const T *__restrict__ raster, uint32_t bands, uint32_t H, uint
     const int32_t vmin = use_lut ? (int32_t)mn : 0;
     // (staging the table in shared memory was tried: 64 KB per CTA costs more occupancy than the L1 gathers cost)
     const int32_t *lut = lut_all ? lut_all + (size_t)tile_i * kNormLutCap : nullptr;
-    auto map = [&](T v) -> int32_t {
-        if (is_small_int<T>::value && use_lut)
-            return bits == 16 ? (int32_t)__ldg(reinterpret_cast<const int16_t *>(lut_all) + (size_t)tile_i * kNormLutCap + ((int32_t)v - vmin))
-                              : __ldg(lut + ((int32_t)v - vmin));
-        return normalize_one((double)v, mn, range, scale);
-    };
-    for (uint32_t ry = part * kMapWarps + warp; ry < rows; ry += parts * kMapWarps) {
-        const uint32_t c = ry / t.h, y = ry - c * t.h;
-        const T *src = raster + ((size_t)c * H + (t.row_off + y)) * W + t.col_off;
-        A *out = dst + (size_t)c * n + (size_t)y * t.w;
-        const RowSplit<T> rs(src, t.w);
-        if ((uint32_t)lane < rs.head) out[lane] = (A)map(src[lane]);
-        if (rs.tail0 + lane < t.w) out[rs.tail0 + lane] = (A)map(src[rs.tail0 + lane]);
-        const T *body = src + rs.head;
-        A *obody = out + rs.head;
-        const bool ovec = (reinterpret_cast<uintptr_t>(obody) & 15u) == 0;
-        auto emit = [&](uint32_t g, const T (&e)[G]) {
-            int32_t r[G];
-#pragma unroll
-            for (int j = 0; j < G; j++) r[j] = map(e[j]);
-            A *o = obody + (size_t)g * G;
-            if (ovec) {
-                if (sizeof(A) == 4) {
-#pragma unroll
-                    for (int q = 0; q < AV; q++)
-                        st_stream16(o + 4 * q, make_uint4((uint32_t)r[4 * q], (uint32_t)r[4 * q + 1], (uint32_t)r[4 * q + 2], (uint32_t)r[4 * q + 3]));
-                } else {
-                    auto pk = [&](int j) { return __byte_perm((uint32_t)r[j], (uint32_t)r[j + 1], 0x5410); };   // two int16 per word
-#pragma unroll
-                    for (int q = 0; q < AV; q++)
-                        st_stream16(o + 8 * q, make_uint4(pk(8 * q), pk(8 * q + 2), pk(8 * q + 4), pk(8 * q + 6)));
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < G; j++) o[j] = (A)r[j];
-            }
+    if (SLUT) {
+        if (use_lut) {        // uniform over the CTA; whole 16-byte chunks (the tile's table region is kNormLutCap entries long)
+            const uint32_t chunks = ((uint32_t)(mx - mn) + 1 + 7) / 8;
+            const uint4 *g = reinterpret_cast<const uint4 *>(reinterpret_cast<const int16_t *>(lut_all) + (size_t)tile_i * kNormLutCap);
+            for (uint32_t q = threadIdx.x; q < chunks; q += kMapThreads) reinterpret_cast<uint4 *>(s_lut)[q] = __ldg(g + q);
+        }
+        __syncthreads();
+    }
+    const int16_t *s_tab = s_lut - vmin;         // table indexed by the pixel value itself
+    // the row walk is instantiated once per mapping, so the table path carries no per-sample test of `use_lut`
+    // (with the test inside the mapping, every gather was followed by a branch around the inlined fp64 formula)
+    auto walk = [&](auto map) {
+        const uint32_t stride = parts * kMapWarps;
+        auto row_src = [&](uint32_t ry) -> const T * {
+            const uint32_t c = ry / t.h, y = ry - c * t.h;
+            return raster + ((size_t)c * H + (t.row_off + y)) * W + t.col_off;
         };
-        uint32_t g = lane;
-        for (; g + 96 < rs.ngroups; g += 128) {
-            T e0[G], e1[G], e2[G], e3[G];
-            load_group(body + (size_t)g * G, e0);
-            load_group(body + (size_t)(g + 32) * G, e1);
-            load_group(body + (size_t)(g + 64) * G, e2);
-            load_group(body + (size_t)(g + 96) * G, e3);
-            emit(g, e0); emit(g + 32, e1); emit(g + 64, e2); emit(g + 96, e3);
+        // The first 128 groups of a row (the whole row for tiles up to 1024 16-bit / 2048 8-bit pixels wide) are loaded one
+        // row AHEAD: a warp alternated between waiting for its four loads and mapping them, so little was in flight while it
+        // mapped (1.06 ms per C3 scene for 3.9 GB with the table already in shared memory).
+        constexpr int TV = MapGroup<T>::TV;
+        uint4 E[4][TV], En[4][TV];
+        auto prefetch = [&](uint32_t ry, uint4 (&B)[4][TV]) {
+            const T *src = row_src(ry);
+            const RowSplit<T> rs(src, t.w);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (lane + 32u * k < rs.ngroups) load_group_raw<T>(src + rs.head + (size_t)(lane + 32u * k) * G, B[k]);
+        };
+        uint32_t ry = part * kMapWarps + warp;
+        if (ry < rows) prefetch(ry, E);
+        for (; ry < rows; ry += stride) {
+            if (ry + stride < rows) prefetch(ry + stride, En);
+            const uint32_t c = ry / t.h, y = ry - c * t.h;
+            const T *src = row_src(ry);
+            A *out = dst + (size_t)c * n + (size_t)y * t.w;
+            const RowSplit<T> rs(src, t.w);
+            if ((uint32_t)lane < rs.head) out[lane] = (A)map(src[lane]);
+            if (rs.tail0 + lane < t.w) out[rs.tail0 + lane] = (A)map(src[rs.tail0 + lane]);
+            const T *body = src + rs.head;
+            A *obody = out + rs.head;
+            const bool ovec = (reinterpret_cast<uintptr_t>(obody) & 15u) == 0;
+            auto emit = [&](uint32_t g, const T (&e)[G]) {
+                int32_t r[G];
+#pragma unroll
+                for (int j = 0; j < G; j++) r[j] = map(e[j]);
+                A *o = obody + (size_t)g * G;
+                if (ovec) {
+                    if (sizeof(A) == 4) {
+#pragma unroll
+                        for (int q = 0; q < AV; q++)
+                            st_stream16(o + 4 * q, make_uint4((uint32_t)r[4 * q], (uint32_t)r[4 * q + 1], (uint32_t)r[4 * q + 2], (uint32_t)r[4 * q + 3]));
+                    } else {
+                        auto pk = [&](int j) { return __byte_perm((uint32_t)r[j], (uint32_t)r[j + 1], 0x5410); };   // two int16 per word
+#pragma unroll
+                        for (int q = 0; q < AV; q++)
+                            st_stream16(o + 8 * q, make_uint4(pk(8 * q), pk(8 * q + 2), pk(8 * q + 4), pk(8 * q + 6)));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < G; j++) o[j] = (A)r[j];
+                }
+            };
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (lane + 32u * k < rs.ngroups) {
+                    T e[G];
+                    unpack_group<T>(E[k], e);
+                    emit(lane + 32u * k, e);
+                }
+            for (uint32_t g = lane + 128u; g < rs.ngroups; g += 32) {      // wider rows: the rest without look-ahead
+                T e0[G];
+                load_group(body + (size_t)g * G, e0);
+                emit(g, e0);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+#pragma unroll
+                for (int q = 0; q < TV; q++) E[k][q] = En[k][q];
         }
-        for (; g < rs.ngroups; g += 32) {
-            T e0[G];
-            load_group(body + (size_t)g * G, e0);
-            emit(g, e0);
+    };
+    if (is_small_int<T>::value && use_lut) {
+        if (SLUT) walk([&](T v) -> int32_t { return (int32_t)s_tab[(int32_t)v]; });
+        else if (bits == 16) {
+            const int16_t *tab = reinterpret_cast<const int16_t *>(lut_all) + (size_t)tile_i * kNormLutCap - vmin;
+            walk([&](T v) -> int32_t { return (int32_t)__ldg(tab + (int32_t)v); });
+        } else {
+            const int32_t *tab = lut - vmin;
+            walk([&](T v) -> int32_t { return __ldg(tab + (int32_t)v); });
         }
+    } else {
+        walk([&](T v) -> int32_t { return normalize_one((double)v, mn, range, scale); });
     }
 }
 
@@ -379,7 +444,8 @@ extern "C" int frb_normalize_tiles_i16(const void *d_raster, int dtype, uint32_t
         lut = w.norm_lut;
     }
     const uint32_t parts = tile_grid_parts(n_tiles, bands * H), grid = parts * n_tiles;
-#define FRB_NORM16(T) k_normalize_tiles<T, int16_t><<<grid, kMapThreads, 0, s>>>((const T *)d_raster, bands, H, W, d_tiles, d_minmax, 16, d_audio, d_audio_base, lut, parts)
+#define FRB_NORM16(T) do { if (lut) k_normalize_tiles<T, int16_t, true><<<grid, kMapThreads, kNormLutCap * 2, s>>>((const T *)d_raster, bands, H, W, d_tiles, d_minmax, 16, d_audio, d_audio_base, lut, parts); \
+                           else k_normalize_tiles<T, int16_t, false><<<grid, kMapThreads, 0, s>>>((const T *)d_raster, bands, H, W, d_tiles, d_minmax, 16, d_audio, d_audio_base, lut, parts); } while (0)
     switch (dtype) {
         case FRB_U8: FRB_NORM16(uint8_t); break;
         case FRB_I8: FRB_NORM16(int8_t); break;
