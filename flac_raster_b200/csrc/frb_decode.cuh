@@ -93,7 +93,8 @@ __global__ void k_fill_u64(unsigned long long *p, uint64_t n, unsigned long long
 // 0xFF 0xF8 pair in ~6 instructions; v1 tested 4 positions per two 4-byte loads (0.85 ms on C3).
 __device__ __forceinline__ void sync_candidate(const uint8_t *__restrict__ bytes, const DecStreamDev &st, uint64_t pos, uint64_t start,
                                                uint64_t end, uint32_t channels, uint32_t bps, uint32_t blocksize,
-                                               unsigned long long *__restrict__ frame_pos, unsigned long long *__restrict__ probe) {
+                                               unsigned long long *__restrict__ frame_pos, unsigned long long *__restrict__ frame_pos2,
+                                               unsigned long long *__restrict__ probe) {
     if (pos < start || pos + 8 > end) return;
     FrameHdr h;
     if (!parse_frame_header(bytes + pos, end - pos, st.sample_rate, bps, &h)) return;
@@ -108,12 +109,42 @@ __device__ __forceinline__ void sync_candidate(const uint8_t *__restrict__ bytes
     if (h.number >= st.n_frames) return;
     const uint64_t expect = (h.number + 1 < st.n_frames) ? blocksize : (st.n_samples - h.number * blocksize);
     if (h.blocksize != expect) return;
-    atomicMin(&frame_pos[st.frame_base + h.number], (unsigned long long)pos);
+    // the two smallest candidate positions per frame number: cand[f] and cand2[f] (k_sync_resolve picks between them).
+    // Every position other than the final minimum is at some point the larger side of an atomicMin exchange, so the
+    // minimum of those larger sides is the second smallest.
+    const unsigned long long old = atomicMin(&frame_pos[st.frame_base + h.number], (unsigned long long)pos);
+    if (frame_pos2 && old != kNoPos && old != pos) atomicMin(&frame_pos2[st.frame_base + h.number], old > pos ? old : (unsigned long long)pos);
+}
+
+// A byte sequence inside some frame's payload can look like a frame header (sync code, plausible fields, CRC-8: about
+// 2^-39 per byte position, ~1e-3 per 1.5 GB container).  libFLAC decodes sequentially and never looks there; a parallel
+// scan that keeps the FIRST candidate per frame number is shadowed by it whenever it lies before the real frame.  Frame
+// starts grow with the frame number, so a first candidate at or before the previous frame's first candidate cannot be
+// the frame: the second candidate takes its place.  (A false header inside the immediately preceding frame is still
+// not told apart -- 1/n_frames of the cases; the decode then reports a parse / CRC-16 error, never wrong samples.)
+__global__ void __launch_bounds__(256)
+k_sync_resolve(const DecStreamDev *__restrict__ streams, uint32_t n_streams, uint32_t total_frames,
+               const unsigned long long *__restrict__ cand, const unsigned long long *__restrict__ cand2,
+               unsigned long long *__restrict__ frame_pos) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= total_frames) return;
+    uint32_t lo = 0, hi = n_streams - 1;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (streams[mid].frame_base <= f) lo = mid; else hi = mid - 1;
+    }
+    unsigned long long c = cand[f];
+    if (f > streams[lo].frame_base && c != kNoPos) {
+        const unsigned long long prev = cand[f - 1], c2 = cand2[f];
+        if (prev != kNoPos && c <= prev && c2 != kNoPos) c = c2;
+    }
+    frame_pos[f] = c;
 }
 
 __global__ void __launch_bounds__(256)
 k_sync_scan(const uint8_t *__restrict__ bytes, const DecStreamDev *__restrict__ streams, uint32_t channels,
             uint32_t bps, uint32_t blocksize, unsigned long long *__restrict__ frame_pos,
+            unsigned long long *__restrict__ frame_pos2 /* optional: second smallest candidate per frame */,
             unsigned long long *__restrict__ probe /* optional: [0]=max key, [1]=count */, uint32_t parts) {
     // flattened grid, `parts` CTAs per stream (gridDim.y stops at 65535 streams)
     const uint32_t si = blockIdx.x / parts, part = blockIdx.x - si * parts;
@@ -137,7 +168,7 @@ k_sync_scan(const uint8_t *__restrict__ bytes, const DecStreamDev *__restrict__ 
 #pragma unroll
             for (int k = 0; k < 4; k++)
                 if (hit & (0xFFu << (8 * k)))
-                    sync_candidate(bytes, st, 16 * q + 4 * j + k, start, end, channels, bps, blocksize, frame_pos, probe);
+                    sync_candidate(bytes, st, 16 * q + 4 * j + k, start, end, channels, bps, blocksize, frame_pos, frame_pos2, probe);
         }
     }
 }
@@ -214,6 +245,7 @@ k_stereo_fix(const DecStreamDev *__restrict__ streams, uint32_t n_streams, uint3
 struct DecWorkspace {
     DecStreamDev *streams;
     unsigned long long *frame_pos;
+    unsigned long long *frame_cand;     // scan path: smallest and second smallest candidate per frame, 2 x (total_frames + 1)
     uint8_t *chassign;
     uint32_t *sub_bitoff;      // only used when channels > 1
 };
@@ -225,6 +257,8 @@ static inline size_t dec_ws_layout(uint32_t n_streams, uint32_t channels, uint64
     off += align256(sizeof(DecStreamDev) * (size_t)n_streams);
     if (w) w->frame_pos = (unsigned long long *)(b + off);
     off += align256(8 * (size_t)(total_frames + 1));
+    if (w) w->frame_cand = (unsigned long long *)(b + off);
+    off += align256(16 * (size_t)(total_frames + 1));
     if (w) w->chassign = b + off;
     off += align256((size_t)total_frames + 1);
     if (w) w->sub_bitoff = (uint32_t *)(b + off);
@@ -281,17 +315,21 @@ static int decode_batch_impl(const frb_decode_params *p, const frb_decode_stream
         k_index_frame_pos<<<p->n_streams, 256, 0, s>>>(w.streams, d_frame_bytes, w.frame_pos, d_status);
         FRB_LAUNCH_CHECK("k_index_frame_pos");
     } else {
-    k_fill_u64<<<grid_for(total_frames + 1, 256 * 4, kNumSMs * 4), 256, 0, s>>>(w.frame_pos, total_frames + 1, kNoPos);
-    FRB_LAUNCH_CHECK("k_fill_u64");
+        k_fill_u64<<<grid_for(2 * (total_frames + 1), 256 * 4, kNumSMs * 4), 256, 0, s>>>(w.frame_cand, 2 * (total_frames + 1), kNoPos);
+        FRB_LAUNCH_CHECK("k_fill_u64");
         uint64_t chunks = max_len / 16 + 2;
         uint32_t gx = (uint32_t)((chunks + 256 * 4 - 1) / (256 * 4));
         uint32_t cap = (kNumSMs * 16 + p->n_streams - 1) / p->n_streams;
         if (gx > cap) gx = cap;
         if (gx < 1) gx = 1;
         prof_begin(3, s);
-        k_sync_scan<<<gx * p->n_streams, 256, 0, s>>>(d_bytes, w.streams, p->channels, p->bps, p->blocksize, w.frame_pos, nullptr, gx);
+        k_sync_scan<<<gx * p->n_streams, 256, 0, s>>>(d_bytes, w.streams, p->channels, p->bps, p->blocksize, w.frame_cand,
+                                                      w.frame_cand + total_frames + 1, nullptr, gx);
         prof_end(3, s);
         FRB_LAUNCH_CHECK("k_sync_scan");
+        k_sync_resolve<<<(uint32_t)((total_frames + 255) / 256), 256, 0, s>>>(w.streams, p->n_streams, (uint32_t)total_frames, w.frame_cand,
+                                                                            w.frame_cand + total_frames + 1, w.frame_pos);
+        FRB_LAUNCH_CHECK("k_sync_resolve");
     }
     // CRC-16 only needs the frame positions: it runs on a side stream next to the skim pass (a latency-bound kernel
     // that leaves most issue slots idle) and joins the caller's stream at the end.
@@ -469,7 +507,7 @@ extern "C" int frb_probe_stream(const uint8_t *d_bytes, uint64_t byte_offset, ui
     uint64_t chunks = byte_length / 16 + 2;
     uint32_t gx = (uint32_t)((chunks + 256 * 4 - 1) / (256 * 4));
     if (gx > (uint32_t)kNumSMs * 16) gx = kNumSMs * 16;
-    k_sync_scan<<<gx, 256, 0, s>>>(d_bytes, d_st, channels, bps, blocksize, nullptr, d_probe, gx);
+    k_sync_scan<<<gx, 256, 0, s>>>(d_bytes, d_st, channels, bps, blocksize, nullptr, nullptr, d_probe, gx);
     g_launches.fetch_add(1);
     unsigned long long h_probe[2] = {0, 0};
     e = cudaMemcpyAsync(h_probe, d_probe, 16, cudaMemcpyDeviceToHost, s);

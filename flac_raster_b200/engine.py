@@ -40,6 +40,13 @@ def tile_grid(height: int, width: int, tile_size: int) -> np.ndarray:
     return t
 
 
+def _check_tile_sizes(npx: np.ndarray) -> None:
+    """The mapping kernels index a tile's pixels with 32 bits (h * w, k * blocksize): reject what would wrap instead of
+    coding garbage.  The reference has no such limit (numpy), but pyflac's 32-bit frame counters end well below it."""
+    if len(npx) and int(npx.max()) >= 1 << 32:
+        raise ValueError(f"a tile of {int(npx.max())} pixels exceeds the 2^32 - 1 pixels one tile may hold; use a smaller tile_size")
+
+
 def _stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -144,6 +151,7 @@ class Engine:
             bits_per_sample = 16 if dt in ("uint8", "int8", "uint16", "int16") else 24
         n_tiles = len(tiles)
         npx = tiles["h"].astype(np.int64) * tiles["w"].astype(np.int64)
+        _check_tile_sizes(npx)
         base = np.zeros(n_tiles, dtype=np.int64)
         np.cumsum(npx[:-1] * bands, out=base[1:])
         total = int((npx * bands).sum())
@@ -491,6 +499,7 @@ class Engine:
         bands, H, W = out.shape
         n_tiles = len(tiles)
         n_samples = tiles["h"].astype(np.int64) * tiles["w"].astype(np.int64)
+        _check_tile_sizes(n_samples)
         dt = str(out.dtype).replace("torch.", "")
         # The fused launch pays off where the pixel mapping is the exact integer form (8/16-bit rasters behind 16-bit
         # audio).  Wider dtypes need the fp64 formula per sample, which is cheaper in the bandwidth-bound mapping kernel
@@ -640,6 +649,7 @@ class Engine:
         """int32 planar audio -> windows of the (bands,H,W) device raster `out` (denormalize_from_audio, int path)."""
         bands, H, W = out.shape
         dt = str(out.dtype).replace("torch.", "")
+        _check_tile_sizes(tiles["h"].astype(np.int64) * tiles["w"].astype(np.int64))
         with torch.cuda.device(self.device):
             s = _stream_ptr()
             d_tiles = self._upload(tiles.view(np.uint8))

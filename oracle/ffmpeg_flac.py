@@ -1,4 +1,5 @@
-"""Independent production FLAC decoder (FFmpeg libavcodec via ctypes) -- TEST INFRASTRUCTURE ONLY.
+"""Independent production FLAC codec (FFmpeg libavcodec via ctypes: decoder as a checker, encoder + decoder as labelled
+CPU baseline rows of bench.py) -- TEST INFRASTRUCTURE ONLY.
 
 pyflac/libFLAC cannot be installed offline, but opencv-python-headless bundles FFmpeg 8
 (libavformat 62 / libavcodec 62.11 / libavutil 60).  Decoding our streams with a second,
@@ -145,3 +146,90 @@ def decode_bytes(data: bytes, channels: int) -> np.ndarray:
         return decode_file(name, channels)
     finally:
         os.unlink(name)
+
+
+def encode_timing(path: str, level: int = 5, blocksize: int = 4096, repeat: int = 1):
+    """CPU-baseline helper (bench.py cpu_baseline.ffmpeg): decode `path` with libavcodec, keep the decoded AVFrames, then
+    TIME libavcodec's FLAC ENCODER (SIMD LPC / residual code, the only production FLAC encoder on the box) over them at
+    `level`.  The frames the decoder produced carry format, channel layout, rate and sample count, so no AVFrame field is
+    written by offset; the encoder context is filled from the file's codec parameters and three AVOptions.
+    Returns (seconds, samples_per_channel, encoded_bytes)."""
+    import time
+    avutil, avcodec, avformat = _load()
+    vp = C.c_void_p
+    avcodec.avcodec_find_encoder_by_name.restype = vp
+    avcodec.avcodec_find_encoder_by_name.argtypes = [C.c_char_p]
+    avcodec.avcodec_send_frame.argtypes = [vp, vp]
+    avcodec.avcodec_receive_packet.argtypes = [vp, vp]
+    avutil.av_frame_clone.restype = vp
+    avutil.av_frame_clone.argtypes = [vp]
+    avutil.av_opt_set_int.argtypes = [vp, C.c_char_p, C.c_int64, C.c_int]
+    avutil.av_opt_set.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int]
+    fmt = vp(None)
+    if avformat.avformat_open_input(C.byref(fmt), path.encode(), None, None) < 0:
+        raise ValueError("avformat_open_input failed")
+    frames = []
+    try:
+        if avformat.avformat_find_stream_info(fmt, None) < 0:
+            raise ValueError("find_stream_info failed")
+        streams = _rd(fmt.value + 48, vp)
+        st0 = _rd(streams, vp)
+        codecpar = _rd(st0 + 16, vp)
+        dec = avcodec.avcodec_find_decoder_by_name(b"flac")
+        dctx = vp(avcodec.avcodec_alloc_context3(dec))
+        avcodec.avcodec_parameters_to_context(dctx, codecpar)
+        if avcodec.avcodec_open2(dctx, dec, None) < 0:
+            raise ValueError("avcodec_open2(decoder) failed")
+        pkt = vp(avcodec.av_packet_alloc())
+        frm = vp(avutil.av_frame_alloc())
+        n_samples = 0
+
+        def drain():
+            nonlocal n_samples
+            while avcodec.avcodec_receive_frame(dctx, frm) == 0:
+                n_samples += _rd(frm.value + 112, C.c_int)
+                frames.append(vp(avutil.av_frame_clone(frm)))
+                avutil.av_frame_unref(frm)
+
+        while avformat.av_read_frame(fmt, pkt) >= 0:
+            rc = avcodec.avcodec_send_packet(dctx, pkt)
+            avcodec.av_packet_unref(pkt)
+            if rc < 0:
+                raise ValueError("send_packet failed")
+            drain()
+        avcodec.avcodec_send_packet(dctx, None)
+        drain()
+        enc = avcodec.avcodec_find_encoder_by_name(b"flac")
+        if not enc:
+            raise ValueError("this libavcodec has no FLAC encoder")
+        total_s, out_bytes = 0.0, 0
+        for _ in range(repeat):
+            ectx = vp(avcodec.avcodec_alloc_context3(enc))
+            avcodec.avcodec_parameters_to_context(ectx, codecpar)        # rate, channel layout, sample format, bits per raw sample
+            avutil.av_opt_set_int(ectx, b"compression_level", level, 0)
+            avutil.av_opt_set_int(ectx, b"frame_size", blocksize, 0)
+            avutil.av_opt_set(ectx, b"time_base", b"1/%d" % 44100, 0)
+            if avcodec.avcodec_open2(ectx, enc, None) < 0:
+                raise ValueError("avcodec_open2(encoder) failed")
+            out_bytes = 0
+            t0 = time.perf_counter()
+            for f in frames:
+                if avcodec.avcodec_send_frame(ectx, f) < 0:
+                    raise ValueError("send_frame failed")
+                while avcodec.avcodec_receive_packet(ectx, pkt) == 0:
+                    out_bytes += _rd(pkt.value + 32, C.c_int)
+                    avcodec.av_packet_unref(pkt)
+            avcodec.avcodec_send_frame(ectx, None)
+            while avcodec.avcodec_receive_packet(ectx, pkt) == 0:
+                out_bytes += _rd(pkt.value + 32, C.c_int)
+                avcodec.av_packet_unref(pkt)
+            total_s += time.perf_counter() - t0
+            avcodec.avcodec_free_context(C.byref(ectx))
+        avutil.av_frame_free(C.byref(frm))
+        avcodec.av_packet_free(C.byref(pkt))
+        avcodec.avcodec_free_context(C.byref(dctx))
+    finally:
+        for f in frames:
+            avutil.av_frame_free(C.byref(f))
+        avformat.avformat_close_input(C.byref(fmt))
+    return total_s / repeat, n_samples, out_bytes

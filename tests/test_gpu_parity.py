@@ -108,6 +108,25 @@ def test_decode_oracle_encoded_streams(nat, oracle, level):
         assert np.array_equal(out, x), (name, level)
 
 
+def test_decode_survives_a_false_frame_header_before_the_real_one(nat, oracle):
+    """The scan path keeps the two earliest header candidates per frame number and drops a first candidate that lies at or
+    before the previous frame's (frb_decode.cuh k_sync_resolve): bytes that look like frame k's header (sync code, matching
+    fields, correct CRC-8) placed ahead of the real frame must not shadow it.  libFLAC never sees such bytes (it walks the
+    frames in order); the keep-the-first scan of round 1 reported a malformed stream here."""
+    from flac_raster_b200 import flacfmt
+    for case, ch in (("sine16_1ch", 1), ("smooth16_8ch", 8)):
+        x, bps = signal_cases()[case]
+        enc, fsz = oracle.encode(x, bps, 44100, 5)
+        off = flacfmt.parse_header(enc).first_frame_offset
+        frames = enc[off:]
+        starts = np.concatenate([[0], np.cumsum(fsz)]).astype(np.int64)
+        assert len(fsz) >= 3
+        for k in (1, len(fsz) - 2):
+            fake = frames[starts[k]:starts[k] + 16]                 # frame k's own header (CRC-8 included) + a few payload bytes
+            got = nat.host_decode(fake + frames, ch, bps, 4096, 44100, x.shape[0])
+            assert np.array_equal(got, x), (case, k)
+
+
 def test_decode_detects_corruption(nat, oracle):
     x, bps = signal_cases()["sine16_1ch"]
     enc, _ = oracle.encode(x, bps, 44100, 5)

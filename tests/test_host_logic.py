@@ -368,3 +368,11 @@ def test_remote_range_reads_into_a_buffer(range_http_server):
     assert s.is_url and s.header_size == 4 + len(js) and len(s.spatial_index.frames) == 3
     assert s.get_byte_ranges_for_bbox((0.5, 0.1, 2.5, 0.9)) == [(s.header_size, s.header_size + off - 1)]
     assert len(s.stream_bbox_data((1.1, 0.1, 1.9, 0.9))) == 1001
+
+
+def test_oversized_tile_is_rejected():
+    """A tile of 2^32 pixels or more would wrap the kernels' 32-bit pixel index: the engine refuses it up front."""
+    from flac_raster_b200 import engine
+    engine._check_tile_sizes(np.array([1 << 20, (1 << 32) - 1], dtype=np.int64))
+    with pytest.raises(ValueError, match="pixels"):
+        engine._check_tile_sizes(np.array([70000 * 70000], dtype=np.int64))
