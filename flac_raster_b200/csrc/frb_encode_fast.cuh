@@ -273,10 +273,19 @@ struct StatsShared {
 };
 
 #ifndef FRB_STATS_MINB
-#define FRB_STATS_MINB 3
+#define FRB_STATS_MINB 4
 #endif
 #ifndef FRB_CODE_MINB
 #define FRB_CODE_MINB 4
+#endif
+#ifndef FRB_CODE_RELOAD
+#define FRB_CODE_RELOAD 1
+#endif
+#ifndef FRB_STATS_LATEWIN
+#define FRB_STATS_LATEWIN 0
+#endif
+#ifndef FRB_STATS_RELOAD
+#define FRB_STATS_RELOAD 1
 #endif
 template <bool WIDE, int NLAGS>
 __global__ void __launch_bounds__(kEncThreads, (NLAGS > 9 || WIDE) ? 2 : FRB_STATS_MINB)
@@ -296,17 +305,22 @@ k_enc_stats(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bp
     constexpr int HALO = NLAGS > 0 ? NLAGS - 1 : 0;         // 8 or 12: multiples of 4, so the window reads stay 16-byte aligned
     int32_t xs[28];
     load_samples28(L, tid, xs);
-    // full-length window for this thread's samples and halo, fetched together with the samples
+    // full-length window for this thread's samples and halo
     float wv[kSPT + HALO + 1];
-    if (NLAGS > 0) {
-        const float4 *wp = reinterpret_cast<const float4 *>(window + tid * kSPT) - HALO / 4;
+    auto load_window = [&]() {
+        if (NLAGS > 0) {
+            const float4 *wp = reinterpret_cast<const float4 *>(window + tid * kSPT) - HALO / 4;
 #pragma unroll
-        for (int q = 0; q < (kSPT + HALO) / 4; q++) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (tid > 0 || q >= HALO / 4) v = __ldg(wp + q);
-            wv[4 * q] = v.x; wv[4 * q + 1] = v.y; wv[4 * q + 2] = v.z; wv[4 * q + 3] = v.w;
+            for (int q = 0; q < (kSPT + HALO) / 4; q++) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tid > 0 || q >= HALO / 4) v = __ldg(wp + q);
+                wv[4 * q] = v.x; wv[4 * q + 1] = v.y; wv[4 * q + 2] = v.z; wv[4 * q + 3] = v.w;
+            }
         }
-    }
+    };
+#if !FRB_STATS_LATEWIN
+    load_window();          // fetched together with the samples
+#endif
     // ---- wasted bits / constant ----
     uint32_t orv = 0, diff = 0;
     const int32_t x_first = sample_at(L, 0);
@@ -421,6 +435,11 @@ k_enc_stats(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bp
     if (tid == 5) { stats[task].wasted = wasted; stats[task].flags = flags; }
     if (NLAGS == 0 || diff == 0) return;
     // ---- windowed autocorrelation, one set per apodization (root, halves, thirds) ----
+#if FRB_STATS_LATEWIN
+    // the window (16 KB, shared by every CTA: L1 hits) and, with FRB_STATS_RELOAD, the samples are fetched only now: the
+    // fixed-predictor phase above and this one no longer hold each other's registers
+    load_window();
+#endif
     const uint32_t i0 = tid * kSPT;
     int set = 0;
     for (uint32_t b = 1; b <= windows; b++) {
@@ -434,6 +453,16 @@ k_enc_stats(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bp
             // threads whose 16 samples lie outside the window contribute nothing
             if (i0 + kSPT > wshift && i0 < wshift + wlen) {
                 float df[kSPT + HALO];                   // windowed samples (libFLAC windows in single precision)
+#if FRB_STATS_RELOAD
+                // the samples are fetched again per window set (L1 hits) so that they are dead once df[] is formed,
+                // instead of staying in 28 registers next to the fp64 window and accumulators for the next set
+                int32_t xs[28];
+                load_samples28(L, tid, xs);
+                if (wasted) {
+#pragma unroll
+                    for (int j = 0; j < 28; j++) xs[j] >>= wasted;
+                }
+#endif
                 if (b == 1) {
                     // full window: thread 0's halo samples are zero, so no range checks are needed
 #pragma unroll
@@ -725,6 +754,22 @@ struct PackWriter {
                      "@p sub.u32 %1, %1, 32;\n\t"
                      "}\n" : "+r"(hi), "+r"(fill), "+r"(addr) : "r"(lo) : "memory");
     }
+    // the same for 0 <= len <= 32 (len == 0 with v == 0 writes nothing): the left-aligning shift is a PTX shift, whose
+    // count clamps at 32 (the C++ operator is undefined there)
+    __device__ __forceinline__ void put0(uint32_t v, uint32_t len) {
+        uint32_t vh;
+        asm("shl.b32 %0, %1, %2;" : "=r"(vh) : "r"(v), "r"(32u - len));
+        hi |= vh >> fill;
+        const uint32_t lo = __funnelshift_lc(0u, vh, 32u - fill);
+        fill += len;
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "setp.ge.u32 p, %1, 32;\n\t"
+                     "@p red.shared.or.b32 [%2], %0;\n\t"
+                     "@p mov.b32 %0, %3;\n\t"
+                     "@p add.u32 %2, %2, 4;\n\t"
+                     "@p sub.u32 %1, %1, 32;\n\t"
+                     "}\n" : "+r"(hi), "+r"(fill), "+r"(addr) : "r"(lo) : "memory");
+    }
     __device__ __forceinline__ void zeros(uint32_t q) {
         fill += q;
         while (fill >= 32) {
@@ -736,6 +781,26 @@ struct PackWriter {
         if (hi) asm volatile("red.shared.or.b32 [%0], %1;\n" ::"r"(addr), "r"(hi) : "memory");
     }
 };
+
+// Rare path of the packing loop (a thread that holds a code longer than 32 bits: long unary runs), out of line and
+// rolled up so that it costs no instruction-cache space in the hot kernel.
+__device__ __noinline__ void pack_codes_long(uint32_t addr, uint32_t fill, uint32_t hi, uint32_t kcur, uint32_t skip,
+                                             int32_t r0, int32_t r1, int32_t r2, int32_t r3, int32_t r4, int32_t r5, int32_t r6, int32_t r7,
+                                             int32_t r8, int32_t r9, int32_t r10, int32_t r11, int32_t r12, int32_t r13, int32_t r14, int32_t r15) {
+    const int32_t r[kSPT] = {r0, r1, r2, r3, r4, r5, r6, r7, r8, r9, r10, r11, r12, r13, r14, r15};
+    PackWriter bw;
+    bw.addr = addr; bw.fill = fill; bw.hi = hi;
+    const uint32_t kbit = 1u << kcur, kmask = kbit - 1u, k1 = kcur + 1;
+#pragma unroll 1
+    for (uint32_t s = skip; s < (uint32_t)kSPT; s++) {
+        const uint32_t u = (uint32_t)r[s];
+        const uint32_t q = u >> kcur;
+        const uint32_t tailv = kbit | (u & kmask);
+        if (q + k1 <= 32) bw.put(tailv, q + k1);
+        else { bw.zeros(q); bw.put(tailv, k1); }
+    }
+    bw.finish();
+}
 
 // Residual of this thread's 16 samples.  Returns the OR of |r| (>= 2^30 means an exact overflow check is needed).
 template <bool WIDE, int TAPS>
@@ -801,12 +866,14 @@ k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps
     const EncSubStats *stp = stats + task;
     const uint32_t wasted = stp->wasted, st_flags = stp->flags;
     const uint32_t bps = bps_stream + side_extra - wasted;
+#if !FRB_CODE_RELOAD
     int32_t xs[28];
     load_samples28(L, tid, xs);
     if (wasted) {
 #pragma unroll
         for (int j = 0; j < 28; j++) xs[j] >>= wasted;
     }
+#endif
     {   // zero the bit buffer
         constexpr int nq = (int)(sizeof(S.bitbuf) / 16);
         uint4 *b4 = reinterpret_cast<uint4 *>(S.bitbuf);
@@ -821,6 +888,16 @@ k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps
 
     // residual of candidate C into r[] (warm-up positions of thread 0 zeroed).  Returns OR |r|, sets *bad.
     auto eval_residual = [&](const EncCand &C, const EncCand *Cg, bool *bad_out) -> uint32_t {
+#if FRB_CODE_RELOAD
+        // the samples are fetched again for every evaluation (L1 / L2 hits) instead of living in 28 registers across the
+        // Rice search and the packing phase, where nothing reads them
+        int32_t xs[28];
+        load_samples28(L, tid, xs);
+        if (wasted) {
+#pragma unroll
+            for (int j = 0; j < 28; j++) xs[j] >>= wasted;
+        }
+#endif
         int32_t cf[kMaxOrd];
 #pragma unroll
         for (int j = 0; j < kMaxOrd; j++) cf[j] = C.coefs[j];
@@ -848,12 +925,37 @@ k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps
             best_bits = stp->fx_bits; best_type = 2; best_order = (int)stp->fx_order; best_po = (int)stp->fx_po; best_slot = -2;
             if (tid < 64) S.best_params[tid] = stp->fx_params[tid];
         }
-        for (uint32_t slot = 0; slot < n_cands; slot++) {
-            const EncCand *Cg = cands + (size_t)task * kMaxCands + slot;
-            const EncCand C = *Cg;
-            if (C.type == 0) continue;                       // uniform over the CTA
+        // Passes 0 .. n_cands-1 evaluate the LPC candidates; the last pass makes sure r[] holds the residual of the winner
+        // (the FIXED candidate was searched by k_enc_stats without a residual pass; with several candidates the winner may
+        // not be the one evaluated last).  ONE loop so that the residual code (three tap counts, 16 samples unrolled)
+        // exists once: as three inlined copies the kernel was 96 KB of instructions, and four CTAs per SM in different
+        // phases miss the instruction cache (stall "no_instruction").
+        for (uint32_t slot = 0; slot <= n_cands; slot++) {
+            const bool final_pass = slot == n_cands;
+            const EncCand *Cg = nullptr;
+            EncCand C;
+            if (!final_pass) {
+                Cg = cands + (size_t)task * kMaxCands + slot;
+                C = *Cg;
+                if (C.type == 0) continue;                   // uniform over the CTA
+            } else {
+                if (best_type < 2 || best_slot == cur_slot) break;
+                if (best_slot == -2) {                       // its overflow check was done by k_enc_stats: no Cg
+                    C.type = 2; C.order = best_order; C.precision = 0; C.shift = 0;
+#pragma unroll
+                    for (int j = 0; j < kMaxOrd; j++) C.coefs[j] = 0;
+                    if (best_order == 1) { C.coefs[0] = 1; }
+                    else if (best_order == 2) { C.coefs[0] = 2; C.coefs[1] = -1; }
+                    else if (best_order == 3) { C.coefs[0] = 3; C.coefs[1] = -3; C.coefs[2] = 1; }
+                    else if (best_order == 4) { C.coefs[0] = 4; C.coefs[1] = -6; C.coefs[2] = 4; C.coefs[3] = -1; }
+                } else {
+                    Cg = cands + (size_t)task * kMaxCands + best_slot;
+                    C = *Cg;
+                }
+            }
             bool bad_lane;
             const uint32_t ora = eval_residual(C, Cg, &bad_lane);
+            if (final_pass) break;
             cur_slot = (int)slot;
             const uint32_t order = (uint32_t)C.order;
             // ---- per-thread abs sum (32-bit unless a residual is huge) ----
@@ -891,26 +993,9 @@ k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps
     // ---- exact bit lengths, fallback to VERBATIM, pack -------------------------------------------
     int type = best_type;
     const int order = best_order;
-    uint32_t my_bits = 0, kcur = 0, plen = 4, method = 0;
+    uint32_t my_bits = 0, kcur = 0, plen = 4, method = 0, qmax = 0;
     bool pstart = false;
     if (type >= 2) {
-        if (best_slot == -2) {
-            EncCand C;
-            C.type = 2; C.order = order; C.precision = 0; C.shift = 0;
-#pragma unroll
-            for (int j = 0; j < kMaxOrd; j++) C.coefs[j] = 0;
-            if (order == 1) { C.coefs[0] = 1; }
-            else if (order == 2) { C.coefs[0] = 2; C.coefs[1] = -1; }
-            else if (order == 3) { C.coefs[0] = 3; C.coefs[1] = -3; C.coefs[2] = 1; }
-            else if (order == 4) { C.coefs[0] = 4; C.coefs[1] = -6; C.coefs[2] = 4; C.coefs[3] = -1; }
-            bool dummy;
-            (void)eval_residual(C, nullptr, &dummy);        // its overflow check was done by k_enc_stats
-        } else if (cur_slot != best_slot) {
-            const EncCand *Cg = cands + (size_t)task * kMaxCands + best_slot;
-            const EncCand C = *Cg;
-            bool dummy;
-            (void)eval_residual(C, Cg, &dummy);
-        }
         const uint32_t tl = 8 - (uint32_t)best_po;           // log2 threads per partition (psize = 4096 >> po >= 16)
         kcur = S.best_params[(uint32_t)tid >> tl];
         if (WIDE) {
@@ -922,7 +1007,7 @@ k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps
         pstart = ((uint32_t)tid & ((1u << tl) - 1u)) == 0;
         uint32_t qsum = 0;
 #pragma unroll
-        for (int s = 0; s < kSPT; s++) { r[s] = (int32_t)zigzag(r[s]); qsum += (uint32_t)r[s] >> kcur; }
+        for (int s = 0; s < kSPT; s++) { r[s] = (int32_t)zigzag(r[s]); const uint32_t q = (uint32_t)r[s] >> kcur; qsum += q; qmax = max(qmax, q); }
         const uint32_t cnt = tid == 0 ? kSPT - (uint32_t)order : (uint32_t)kSPT;    // warm-up slots hold 0 and add nothing to qsum
         my_bits = qsum + cnt * (1 + kcur) + (pstart ? plen : 0u);
     }
@@ -955,7 +1040,7 @@ k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps
         const uint32_t typecode = type == 0 ? 0u : type == 1 ? 1u : type == 2 ? (8u | (uint32_t)order) : (32u | (uint32_t)(order - 1));
         put_bits_atomic(S.bitbuf, 0, (typecode << 1) | (wasted ? 1u : 0u), 8);
         if (wasted) put_bits_atomic(S.bitbuf, 8 + wasted - 1, 1, 1);
-        if (type == 0 && bps) put_bits_atomic(S.bitbuf, pos0, (uint32_t)xs[12] & mask_bps, bps);
+        if (type == 0 && bps) put_bits_atomic(S.bitbuf, pos0, (uint32_t)(sample_at(L, 0) >> wasted) & mask_bps, bps);
     }
     if (type >= 2) {
         if (tid >= 32 && tid < 32 + order)                   // warm-up sample j = tid - 32
@@ -974,25 +1059,41 @@ k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps
     if (type == 1) {
         bw.init(S.bitbuf, hdr_bits + (uint32_t)tid * kSPT * bps);
         if (bps) {
+#if FRB_CODE_RELOAD
+            int32_t xs[28];
+            load_samples28(L, tid, xs);
+#pragma unroll
+            for (int s = 0; s < kSPT; s++) bw.put((uint32_t)(xs[12 + s] >> wasted) & mask_bps, bps);
+#else
 #pragma unroll
             for (int s = 0; s < kSPT; s++) bw.put((uint32_t)xs[12 + s] & mask_bps, bps);
+#endif
         }
         bw.finish();
     } else if (type >= 2) {
         bw.init(S.bitbuf, hdr_bits + my_off);
         if (pstart) bw.put(kcur, plen);
         const uint32_t kbit = 1u << kcur, kmask = kbit - 1u, k1 = kcur + 1;
+        const uint32_t skip = tid == 0 ? (uint32_t)order : 0u;          // thread 0: its first `order` slots are warm-up samples, not codes
+        // Per code the writer used to test "is this a warm-up slot" (re-reading %tid) and "does the code fit one 32-bit
+        // write", each a branch around the writer's inline assembly: 26 instructions per code
+        // (profiles/r02_ncu_lines_v1.txt).  Whether ANY of the thread's codes is longer than 32 bits is known from the
+        // length pass (qmax), so the common loop has no length test, and a warm-up slot is a zero-length write of zero
+        // (two selects) instead of a branch.
+        if (qmax + k1 <= 32) {
 #pragma unroll
-        for (int s = 0; s < kSPT; s++) {
-            if (tid != 0 || s >= order) {
+            for (int s = 0; s < kSPT; s++) {
                 const uint32_t u = (uint32_t)r[s];
                 const uint32_t q = u >> kcur;
                 const uint32_t tailv = kbit | (u & kmask);
-                if (q + k1 <= 32) bw.put(tailv, q + k1);     // zeros, stop bit and LSBs in one write
-                else { bw.zeros(q); bw.put(tailv, k1); }
+                if (s < kMaxOrd) { const bool on = (uint32_t)s >= skip; bw.put0(on ? tailv : 0u, on ? q + k1 : 0u); }
+                else bw.put(tailv, q + k1);                  // zeros, stop bit and LSBs in one write
             }
+            bw.finish();
+        } else {
+            pack_codes_long(bw.addr, bw.fill, bw.hi, kcur, skip, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8], r[9], r[10], r[11],
+                            r[12], r[13], r[14], r[15]);
         }
-        bw.finish();
     }
     __syncthreads();
     // ---- slot store (128-bit, coalesced) ----
