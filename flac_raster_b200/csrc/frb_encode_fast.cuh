@@ -79,6 +79,10 @@ __device__ __forceinline__ bool fast_eligible(const TaskLoc &L) {
     return L.n == (uint32_t)kMaxBlock && (reinterpret_cast<uintptr_t>(L.src) & 15u) == 0;
 }
 
+// compile-time choice between two arrays of the same type (a reference, so that the unused one stays dead)
+template <bool FIRST, typename T>
+__device__ __forceinline__ const T &pick_ref(const T &a, const T &b) { if constexpr (FIRST) return a; else return b; }
+
 // two sign-extended int16 samples of a 32-bit word, one instruction each (the compiler emits PRMT with sign replication /
 // an arithmetic shift; __byte_perm cannot express it: it masks the selector nibbles to 3 bits)
 __device__ __forceinline__ int32_t s16_lo(uint32_t w) { return (int32_t)(int16_t)(uint16_t)w; }
@@ -441,6 +445,7 @@ k_enc_stats(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bp
     load_window();
 #endif
     const uint32_t i0 = tid * kSPT;
+    const int32_t (&xs0)[28] = xs;
     int set = 0;
     for (uint32_t b = 1; b <= windows; b++) {
         const uint32_t nsub = (b == 1) ? 1u : b;
@@ -453,16 +458,20 @@ k_enc_stats(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bp
             // threads whose 16 samples lie outside the window contribute nothing
             if (i0 + kSPT > wshift && i0 < wshift + wlen) {
                 float df[kSPT + HALO];                   // windowed samples (libFLAC windows in single precision)
-#if FRB_STATS_RELOAD
-                // the samples are fetched again per window set (L1 hits) so that they are dead once df[] is formed,
-                // instead of staying in 28 registers next to the fp64 window and accumulators for the next set
-                int32_t xs[28];
-                load_samples28(L, tid, xs);
-                if (wasted) {
+                // 16-bit kernels at the 64-register cap: the samples are fetched again per window set (L1 hits) so that they
+                // are dead once df[] is formed, instead of staying in 28 registers next to the fp64 window and accumulators
+                // for the next set.  (The 64-bit / 13-lag instantiations run at 128 registers and keep them: reloading
+                // there only adds work, C4 24.7 against 23.5 ms.)
+                constexpr bool RELOAD = FRB_STATS_RELOAD != 0 && !WIDE && NLAGS <= 9;
+                int32_t xr[28];
+                if constexpr (RELOAD) {
+                    load_samples28(L, tid, xr);
+                    if (wasted) {
 #pragma unroll
-                    for (int j = 0; j < 28; j++) xs[j] >>= wasted;
+                        for (int j = 0; j < 28; j++) xr[j] >>= wasted;
+                    }
                 }
-#endif
+                const int32_t (&xs)[28] = pick_ref<RELOAD>(xr, xs0);
                 if (b == 1) {
                     // full window: thread 0's halo samples are zero, so no range checks are needed
 #pragma unroll
@@ -866,14 +875,18 @@ k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps
     const EncSubStats *stp = stats + task;
     const uint32_t wasted = stp->wasted, st_flags = stp->flags;
     const uint32_t bps = bps_stream + side_extra - wasted;
-#if !FRB_CODE_RELOAD
-    int32_t xs[28];
-    load_samples28(L, tid, xs);
-    if (wasted) {
+    // 16-bit kernel (64-register cap): the samples are fetched again for every evaluation (L1 / L2 hits) instead of living in
+    // 28 registers across the Rice search and the packing phase, where nothing reads them.  The 64-bit kernel runs at 128
+    // registers and keeps them (with nine candidates per subframe at level 8 the reloads only add work: C4 38.3 against 34.7 ms).
+    constexpr bool RELOAD = FRB_CODE_RELOAD != 0 && !WIDE;
+    int32_t xs0[28];
+    if constexpr (!RELOAD) {
+        load_samples28(L, tid, xs0);
+        if (wasted) {
 #pragma unroll
-        for (int j = 0; j < 28; j++) xs[j] >>= wasted;
+            for (int j = 0; j < 28; j++) xs0[j] >>= wasted;
+        }
     }
-#endif
     {   // zero the bit buffer
         constexpr int nq = (int)(sizeof(S.bitbuf) / 16);
         uint4 *b4 = reinterpret_cast<uint4 *>(S.bitbuf);
@@ -888,16 +901,15 @@ k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps
 
     // residual of candidate C into r[] (warm-up positions of thread 0 zeroed).  Returns OR |r|, sets *bad.
     auto eval_residual = [&](const EncCand &C, const EncCand *Cg, bool *bad_out) -> uint32_t {
-#if FRB_CODE_RELOAD
-        // the samples are fetched again for every evaluation (L1 / L2 hits) instead of living in 28 registers across the
-        // Rice search and the packing phase, where nothing reads them
-        int32_t xs[28];
-        load_samples28(L, tid, xs);
-        if (wasted) {
+        int32_t xr[28];
+        if constexpr (RELOAD) {
+            load_samples28(L, tid, xr);
+            if (wasted) {
 #pragma unroll
-            for (int j = 0; j < 28; j++) xs[j] >>= wasted;
+                for (int j = 0; j < 28; j++) xr[j] >>= wasted;
+            }
         }
-#endif
+        const int32_t (&xs)[28] = pick_ref<RELOAD>(xr, xs0);
         int32_t cf[kMaxOrd];
 #pragma unroll
         for (int j = 0; j < kMaxOrd; j++) cf[j] = C.coefs[j];
@@ -1059,15 +1071,15 @@ k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps
     if (type == 1) {
         bw.init(S.bitbuf, hdr_bits + (uint32_t)tid * kSPT * bps);
         if (bps) {
-#if FRB_CODE_RELOAD
-            int32_t xs[28];
-            load_samples28(L, tid, xs);
+            int32_t xr[28];
+            if constexpr (RELOAD) {
+                load_samples28(L, tid, xr);
 #pragma unroll
-            for (int s = 0; s < kSPT; s++) bw.put((uint32_t)(xs[12 + s] >> wasted) & mask_bps, bps);
-#else
+                for (int j = 12; j < 28; j++) xr[j] >>= wasted;
+            }
+            const int32_t (&xs)[28] = pick_ref<RELOAD>(xr, xs0);
 #pragma unroll
             for (int s = 0; s < kSPT; s++) bw.put((uint32_t)xs[12 + s] & mask_bps, bps);
-#endif
         }
         bw.finish();
     } else if (type >= 2) {

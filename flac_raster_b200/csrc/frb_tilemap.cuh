@@ -199,7 +199,7 @@ k_build_norm_lut(const double *__restrict__ minmax, int bits, int32_t *__restric
 #define FRB_NORM_MINB 4
 #endif
 template <typename T, typename A, bool SLUT = false>
-__global__ void __launch_bounds__(kMapThreads, (sizeof(T) <= 2 && sizeof(A) == 2) ? FRB_NORM_MINB : 1)
+__global__ void __launch_bounds__(kMapThreads, (sizeof(T) <= 2 && sizeof(A) == 2) ? FRB_NORM_MINB : 3)
 k_normalize_tiles(const T *__restrict__ raster, uint32_t bands, uint32_t H, uint32_t W,
                   const frb_tile *__restrict__ tiles, const double *__restrict__ minmax, int bits,
                   A *__restrict__ audio, const int64_t *__restrict__ audio_base,
@@ -251,10 +251,13 @@ k_normalize_tiles(const T *__restrict__ raster, uint32_t bands, uint32_t H, uint
             for (int k = 0; k < 4; k++)
                 if (lane + 32u * k < rs.ngroups) load_group_raw<T>(src + rs.head + (size_t)(lane + 32u * k) * G, B[k]);
         };
+        // (only the int16-audio instantiations look ahead: the others are bound by their fp64 formula or by 4-byte audio
+        // stores, and the two vector buffers cost them occupancy -- float32 74 -> 100 registers, C4's mapping 3.0 -> 5.0 ms)
+        constexpr bool AHEAD = sizeof(A) == 2;
         uint32_t ry = part * kMapWarps + warp;
-        if (ry < rows) prefetch(cc, cy, E);
+        if (AHEAD && ry < rows) prefetch(cc, cy, E);
         for (; ry < rows; ry += stride, cc = nc, cy = ny, step(nc, ny)) {
-            if (ry + stride < rows) prefetch(nc, ny, En);
+            if (AHEAD && ry + stride < rows) prefetch(nc, ny, En);
             const uint32_t c = cc, y = cy;
             const T *src = row_src(c, y);
             A *out = dst + (size_t)c * n + (size_t)y * t.w;
@@ -285,22 +288,35 @@ k_normalize_tiles(const T *__restrict__ raster, uint32_t bands, uint32_t H, uint
                     for (int j = 0; j < G; j++) o[j] = (A)r[j];
                 }
             };
+            if (AHEAD) {
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (lane + 32u * k < rs.ngroups) {
-                    T e[G];
-                    unpack_group<T>(E[k], e);
-                    emit(lane + 32u * k, e);
-                }
-            for (uint32_t g = lane + 128u; g < rs.ngroups; g += 32) {      // wider rows: the rest without look-ahead
+                for (int k = 0; k < 4; k++)
+                    if (lane + 32u * k < rs.ngroups) {
+                        T e[G];
+                        unpack_group<T>(E[k], e);
+                        emit(lane + 32u * k, e);
+                    }
+            }
+            uint32_t g = lane + (AHEAD ? 128u : 0u);                                      // wider rows: the rest without look-ahead, four loads in flight
+            for (; g + 96 < rs.ngroups; g += 128) {
+                T e0[G], e1[G], e2[G], e3[G];
+                load_group(body + (size_t)g * G, e0);
+                load_group(body + (size_t)(g + 32) * G, e1);
+                load_group(body + (size_t)(g + 64) * G, e2);
+                load_group(body + (size_t)(g + 96) * G, e3);
+                emit(g, e0); emit(g + 32, e1); emit(g + 64, e2); emit(g + 96, e3);
+            }
+            for (; g < rs.ngroups; g += 32) {
                 T e0[G];
                 load_group(body + (size_t)g * G, e0);
                 emit(g, e0);
             }
+            if (AHEAD) {
 #pragma unroll
-            for (int k = 0; k < 4; k++)
+                for (int k = 0; k < 4; k++)
 #pragma unroll
-                for (int q = 0; q < TV; q++) E[k][q] = En[k][q];
+                    for (int q = 0; q < TV; q++) E[k][q] = En[k][q];
+            }
         }
     };
     if (is_small_int<T>::value && use_lut) {
