@@ -934,6 +934,9 @@ __global__ void k_set_out_offsets(EncStreamDev *streams, const unsigned long lon
 // weights x^(128*(127-t)) and small tail powers, XOR-reduced over the CTA (see frb_crc16.cuh).
 // v1 stored single bytes and ran a byte-serial CRC per thread: 13.8 ms on C3 (profiles/r01_launches_c3_v1.csv).
 constexpr int kEmitThreads = 128;
+#ifndef FRB_EMIT_VLOAD
+#define FRB_EMIT_VLOAD 1
+#endif
 
 struct EmitGroup {                           // state of the frame a thread group (a CTA or a warp) is assembling
     uint32_t hdr[6];
@@ -1070,7 +1073,24 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
                 const uint32_t o = P - S.seg_start[ch];
                 const uint32_t *sl = slots_f + (size_t)S.slot_of[ch] * slot_words + (o >> 5);
                 const uint32_t sh = o & 31;
+#if FRB_EMIT_VLOAD
+                // the five words as TWO aligned 16-byte loads (slots are 16-byte aligned and over-allocated by a vector): five
+                // 4-byte loads at a 16-byte lane stride cost 20 L1 wavefronts per warp against 8, and the kernel is bound by
+                // its L1 / shared-memory data path (CRC table lookups with 92 M bank conflicts).  The word offset inside the
+                // vector is the same for every lane of a warp inside one subframe, so the switch does not diverge.
+                const uint32_t k = (uint32_t)((reinterpret_cast<uintptr_t>(sl) >> 2) & 3u);
+                const uint4 *al = reinterpret_cast<const uint4 *>(sl - k);
+                const uint4 a4 = __ldg(al), b4 = __ldg(al + 1);
+                uint32_t v0, v1, v2, v3, v4;
+                switch (k) {
+                    case 0: v0 = a4.x; v1 = a4.y; v2 = a4.z; v3 = a4.w; v4 = b4.x; break;
+                    case 1: v0 = a4.y; v1 = a4.z; v2 = a4.w; v3 = b4.x; v4 = b4.y; break;
+                    case 2: v0 = a4.z; v1 = a4.w; v2 = b4.x; v3 = b4.y; v4 = b4.z; break;
+                    default: v0 = a4.w; v1 = b4.x; v2 = b4.y; v3 = b4.z; v4 = b4.w; break;
+                }
+#else
                 uint32_t v0 = __ldg(sl), v1 = __ldg(sl + 1), v2 = __ldg(sl + 2), v3 = __ldg(sl + 3), v4 = __ldg(sl + 4);
+#endif
                 w[0] = __funnelshift_l(v1, v0, sh); w[1] = __funnelshift_l(v2, v1, sh);
                 w[2] = __funnelshift_l(v3, v2, sh); w[3] = __funnelshift_l(v4, v3, sh);
             } else {
@@ -1246,8 +1266,14 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const void *d_audi
     EncWorkspace w;
     if (enc_ws_layout(p, frames, d_workspace, &w) > workspace_bytes) return FRB_ERR_OVERFLOW;
     cudaStream_t s = (cudaStream_t)stream;
-    std::vector<float> win(FRB_MAX_BLOCKSIZE, 1.0f);
-    make_tukey(win.data(), (int)p->blocksize, 0.5f / (float)level_cfg(p->level).windows);
+    // analysis window of this (blocksize, apodization count): computed once per host thread and kept
+    static thread_local std::vector<float> win;
+    static thread_local uint32_t win_bs = 0, win_n = 0;
+    if (win_bs != p->blocksize || win_n != (uint32_t)level_cfg(p->level).windows) {
+        win.assign(FRB_MAX_BLOCKSIZE, 1.0f);
+        make_tukey(win.data(), (int)p->blocksize, 0.5f / (float)level_cfg(p->level).windows);
+        win_bs = p->blocksize; win_n = (uint32_t)level_cfg(p->level).windows;
+    }
     // two-channel streams at a mid/side preset: analyse the four virtual channels L, R, M, S (an_* below)
     const bool ms = enc_mid_side(p);
     const uint32_t an_ch = ms ? 4u : p->channels;
