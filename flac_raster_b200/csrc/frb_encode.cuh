@@ -921,6 +921,34 @@ k_stream_scan(const EncStreamDev *__restrict__ streams, const uint32_t *__restri
     if (threadIdx.x == 0) stream_bytes[blockIdx.x] = s_carry;
 }
 
+// out_offset of every stream = exclusive scan of the stream sizes (streams packed back to back in stream order): what the
+// caller of frb_encode_emit would compute on the host from the downloaded sizes -- done here so that the step has no
+// host round trip between analysis and frame assembly.  One CTA walks the streams in chunks of its size.
+__global__ void __launch_bounds__(1024)
+k_pack_out_offsets(EncStreamDev *__restrict__ streams, const unsigned long long *__restrict__ stream_bytes, uint32_t n) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const unsigned long long v = i < n ? stream_bytes[i] : 0ull;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        unsigned long long wbase = 0, tot = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { const unsigned long long x = s_warp[w]; if (w < warp) wbase += x; tot += x; }
+        const unsigned long long carry = s_carry;
+        if (i < n) streams[i].out_offset = carry + wbase + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + tot;
+        __syncthreads();
+    }
+}
+
 __global__ void k_set_out_offsets(EncStreamDev *streams, const unsigned long long *offs, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) streams[i].out_offset = offs[i];
@@ -1418,7 +1446,7 @@ extern "C" int frb_encode_emit(const frb_encode_params *p, void *d_workspace, si
                                const uint64_t *h_out_offset, uint8_t *d_out, size_t out_capacity,
                                uint32_t *d_frame_bytes, void *stream) {
     using namespace frb;
-    if (!enc_params_ok(p) || !d_workspace || !h_out_offset || !d_out) return FRB_ERR_INVALID_ARG;
+    if (!enc_params_ok(p) || !d_workspace || !d_out) return FRB_ERR_INVALID_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     // recover the frame count from the stream table written by analyse
     EncWorkspace w0;
@@ -1432,9 +1460,14 @@ extern "C" int frb_encode_emit(const frb_encode_params *p, void *d_workspace, si
     }
     EncWorkspace w;
     if (enc_ws_layout(p, frames, d_workspace, &w) > workspace_bytes) return FRB_ERR_OVERFLOW;
-    FRB_TRY(small_upload(w.out_offs, h_out_offset, 8 * (size_t)p->n_streams, s));
-    k_set_out_offsets<<<(p->n_streams + 255) / 256, 256, 0, s>>>(w.streams, w.out_offs, p->n_streams);
-    FRB_LAUNCH_CHECK("k_set_out_offsets");
+    if (h_out_offset) {
+        FRB_TRY(small_upload(w.out_offs, h_out_offset, 8 * (size_t)p->n_streams, s));
+        k_set_out_offsets<<<(p->n_streams + 255) / 256, 256, 0, s>>>(w.streams, w.out_offs, p->n_streams);
+        FRB_LAUNCH_CHECK("k_set_out_offsets");
+    } else {        // packed: stream s starts where stream s-1 ends, computed on the device
+        k_pack_out_offsets<<<1, 1024, 0, s>>>(w.streams, w.stream_bytes, p->n_streams);
+        FRB_LAUNCH_CHECK("k_pack_out_offsets");
+    }
     prof_begin(2, s);
     {
         // a warp per frame when frames are small (their raw size bounds the coded size), the whole CTA otherwise

@@ -202,24 +202,37 @@ class Engine:
         sizes = np.zeros(n_streams, dtype=np.uint64)
         with torch.cuda.device(self.device):
             s = _stream_ptr()
+            fb = torch.empty(frames, dtype=torch.int32, device=self.device)
+            sb = torch.empty(frames * channels, dtype=torch.int32, device=self.device)
             if fetch is None:
                 nat.check(self.L.frb_encode_analyse(C.byref(p), audio.data_ptr(), hn.ctypes.data, hr.ctypes.data, hb.ctypes.data,
                                                     ws.data_ptr(), ws.numel(), None, sizes.ctypes.data, s), "frb_encode_analyse")
+                offsets = np.zeros(n_streams, dtype=np.uint64)
+                np.cumsum(sizes[:-1], out=offsets[1:])
+                total = int(sizes.sum())
+                payload = self._buf(payload_name, total + 16)
+                nat.check(self.L.frb_encode_emit(C.byref(p), ws.data_ptr(), ws.numel(), offsets.ctypes.data,
+                                                 payload.data_ptr(), payload.numel(), None, s), "frb_encode_emit")
             else:
+                # No host round trip between analysis and frame assembly: the streams are packed back to back by a device-side
+                # scan of their sizes (frb_encode_emit with no host offsets) into a buffer sized for the worst case (VERBATIM
+                # subframes), and the sizes come back in the step's single download afterwards.
                 d_sizes = fetch.d_sizes
                 nat.check(self.L.frb_encode_analyse(C.byref(p), audio.data_ptr(), hn.ctypes.data, hr.ctypes.data, hb.ctypes.data,
                                                     ws.data_ptr(), ws.numel(), d_sizes.data_ptr(), None, s), "frb_encode_analyse")
-                sizes = np.ascontiguousarray(fetch(), dtype=np.uint64)
-            offsets = np.zeros(n_streams, dtype=np.uint64)
-            np.cumsum(sizes[:-1], out=offsets[1:])
-            total = int(sizes.sum())
-            payload = self._buf(payload_name, total + 16)
-            nat.check(self.L.frb_encode_emit(C.byref(p), ws.data_ptr(), ws.numel(), offsets.ctypes.data,
-                                             payload.data_ptr(), payload.numel(), None, s), "frb_encode_emit")
+                bound = int(n_samples.sum()) * channels * (bps // 8) + frames * (24 + 8 * channels) + 64
+                if channels == 2:
+                    bound += frames * blocksize // 4          # a side subframe carries one more bit per sample
+                payload = self._buf(payload_name, bound + 16)
+                nat.check(self.L.frb_encode_emit(C.byref(p), ws.data_ptr(), ws.numel(), None,
+                                                 payload.data_ptr(), payload.numel(), None, s), "frb_encode_emit")
             # seek index (frame sizes + subframe bit offsets): what lets a decoder skip the sync scan and the subframe walk
-            fb = torch.empty(frames, dtype=torch.int32, device=self.device)
-            sb = torch.empty(frames * channels, dtype=torch.int32, device=self.device)
             nat.check(self.L.frb_encode_index(C.byref(p), ws.data_ptr(), ws.numel(), fb.data_ptr(), sb.data_ptr(), s), "frb_encode_index")
+            if fetch is not None:
+                sizes = np.ascontiguousarray(fetch(), dtype=np.uint64)
+                offsets = np.zeros(n_streams, dtype=np.uint64)
+                np.cumsum(sizes[:-1], out=offsets[1:])
+                total = int(sizes.sum())
         return payload[:total], offsets.astype(np.int64), sizes.astype(np.int64), fb, sb
 
     def encode_tiles(self, raster: torch.Tensor, tiles: np.ndarray, level: int = 5, blocksize: int = 4096,

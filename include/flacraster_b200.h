@@ -170,7 +170,10 @@ int frb_encode_analyse(const frb_encode_params *p, const void *d_audio /* int32,
 /* Pass 2: assemble frames (header, CRC-8, bit-concatenated subframes,
  * padding, CRC-16) into d_out.  Stream s's frames are written contiguously
  * starting at d_out + h_out_offset[s] (host array, bytes; the caller leaves
- * room for metadata blocks in front of each stream).  d_frame_bytes
+ * room for metadata blocks in front of each stream).  h_out_offset == NULL:
+ * the streams are packed back to back in stream order (exclusive scan of the
+ * sizes frb_encode_analyse computed, done on the device: no host round trip
+ * between the two passes; out_capacity must cover the sum).  d_frame_bytes
  * (optional, total_frames uint32) receives every frame's size in stream order. */
 int frb_encode_emit(const frb_encode_params *p, void *d_workspace, size_t workspace_bytes,
                     const uint64_t *h_out_offset, uint8_t *d_out, size_t out_capacity,
