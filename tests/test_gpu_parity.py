@@ -1070,6 +1070,40 @@ def test_streamer_fast_path_equals_python_parse_path(nat, tmp_path, monkeypatch)
         assert all(np.array_equal(a, b) for (a, _), (b, _) in zip(fast, slow)) and len(again) == len(fast)
 
 
+def test_grouped_bbox_decode_equals_one_batch(nat, tmp_path, monkeypatch):
+    """Big bbox queries are cut into groups that are pipelined over two PCIe directions (SpatialFLACStreamer._decode_grouped: a
+    background thread reads and uploads group g+1 on its own stream while group g is decoded and downloaded).  Forced here on a
+    small container (tiny group size): same tiles, same order, same metadata as the one-batch path, also on a second call
+    (buffer reuse) and for ragged multi-band tiles."""
+    from flac_raster_b200 import SpatialFLACEncoder, SpatialFLACStreamer
+    from flac_raster_b200.tiffio import write_geotiff
+    rng = np.random.default_rng(23)
+    yy, xx = np.mgrid[0:700, 0:900]
+    for name, bands, dt in (("one", 1, np.int16), ("three", 3, np.uint16)):
+        src = np.stack([(3000 + 900 * np.sin(xx / 23.0 + b) * np.cos(yy / 17.0) + rng.integers(-20, 20, xx.shape)).astype(dt) for b in range(bands)])
+        write_geotiff(tmp_path / f"{name}.tif", src, (10.0, 0.0, 3e5, 0.0, -10.0, 4e6), "EPSG:32633", None)
+        out = tmp_path / f"{name}.flac"
+        SpatialFLACEncoder(tile_size=64).encode(tmp_path / f"{name}.tif", out, streaming=True)
+        s = SpatialFLACStreamer(out)
+        assert len(s.spatial_index.frames) == 11 * 15
+        monkeypatch.setenv("FRB_NO_GROUPED_DECODE", "1")
+        whole = s.get_tiles_by_bbox(-1e12, -1e12, 1e12, 1e12)
+        monkeypatch.delenv("FRB_NO_GROUPED_DECODE")
+        monkeypatch.setattr(SpatialFLACStreamer, "GROUP_BYTES", 64 << 10)
+        calls = []
+        orig = SpatialFLACStreamer._decode_grouped
+        monkeypatch.setattr(SpatialFLACStreamer, "_decode_grouped", lambda self, fr: (calls.append(len(fr)), orig(self, fr))[1])
+        for _ in range(2):
+            grouped = s.get_tiles_by_bbox(-1e12, -1e12, 1e12, 1e12)
+            assert len(grouped) == len(whole) == 165
+            for (a, ma), (b, mb) in zip(grouped, whole):
+                assert a.dtype == b.dtype and np.array_equal(a, b) and ma == mb
+                w = ma["window"]
+                assert np.array_equal(a, src[:, w["row_off"]:w["row_off"] + w["height"], w["col_off"]:w["col_off"] + w["width"]])
+        assert calls == [165, 165]
+        monkeypatch.undo()
+
+
 def test_tiles_over_http_ranges(nat, tmp_path, range_http_server):
     """a container behind a URL -- the tile byte ranges are fetched with concurrent Range requests straight into
     the pinned staging buffer and handed to the GPU piece by piece; results equal the local-file path, also when the server
