@@ -45,6 +45,7 @@ class EncodeParams(C.Structure):
 
 
 ENC_AUDIO_I16 = 1          # frb_encode_params.reserved flag (FRB_ENC_AUDIO_I16): d_audio holds int16 elements
+ENC_RANGE_30 = 2           # FRB_ENC_RANGE_30: every sample of a 32-bps stream is below 2^30 in magnitude (mid/side is then allowed)
 
 
 class DecodeParams(C.Structure):

@@ -729,10 +729,12 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
         uint32_t typecode = type == 0 ? 0u : type == 1 ? 1u : type == 2 ? (8u | (uint32_t)order) : (32u | (uint32_t)(order - 1));
         bw.put((typecode << 1) | (wasted ? 1u : 0u), 8);
         if (wasted) { bw.zeros(wasted - 1); bw.put(1, 1); }
-        if (type == 0) bw.put((uint32_t)xfirst_shifted & mask_bps, bps);
+        // (bps == 33: the side subframe of a two-channel 32-bps stream; its int32 samples are sign-extended by one bit)
+        auto put_sample = [&](int32_t x) { if (bps > 32) { bw.put(x < 0 ? 1u : 0u, bps - 32); bw.put((uint32_t)x, 32); } else bw.put((uint32_t)x & mask_bps, bps); };
+        if (type == 0) put_sample((int32_t)xfirst_shifted);
         else if (type >= 2) {
 #pragma unroll
-            for (int j = 0; j < kMaxOrd; j++) if (j < order) bw.put((uint32_t)warm[j] & mask_bps, bps);
+            for (int j = 0; j < kMaxOrd; j++) if (j < order) put_sample((int32_t)warm[j]);
             if (type == 3) {
                 const uint32_t prec = (uint32_t)S.best.precision;
                 bw.put(prec - 1, 4);
@@ -748,7 +750,10 @@ k_encode_subframes(const EncStreamDev *__restrict__ streams, uint32_t n_streams,
     if (type == 1) {
         bw.init(bitbuf, hdr_bits + i0 * bps);
 #pragma unroll
-        for (int s = 0; s < kSPT; s++) { const uint32_t i = i0 + s; if (i < n) bw.put((uint32_t)xv_verb[s] & mask_bps, bps); }
+        for (int s = 0; s < kSPT; s++) {
+            const uint32_t i = i0 + s;
+            if (i < n) { if (bps > 32) { bw.put(xv_verb[s] < 0 ? 1u : 0u, bps - 32); bw.put((uint32_t)xv_verb[s], 32); } else bw.put((uint32_t)xv_verb[s] & mask_bps, bps); }
+        }
         bw.finish();
     } else if (type >= 2) {
         bw.init(bitbuf, hdr_bits + my_off);
@@ -802,7 +807,7 @@ __host__ __device__ __forceinline__ uint32_t ms_channel_code(uint32_t sel) { ret
 
 __global__ void __launch_bounds__(256)
 k_ms_expand(const EncStreamDev *__restrict__ streams, const EncStreamDev *__restrict__ vstreams,
-            const EncSrc audio, int32_t *__restrict__ vaudio, uint32_t parts) {
+            const EncSrc audio, int32_t *__restrict__ vaudio, uint32_t parts, uint32_t *__restrict__ err_flag) {
     // flattened grid, `parts` CTAs per stream (gridDim.y stops at 65535 streams)
     const uint32_t si = blockIdx.x / parts, part = blockIdx.x - si * parts;
     const EncStreamDev st = streams[si], vs = vstreams[si];
@@ -811,10 +816,13 @@ k_ms_expand(const EncStreamDev *__restrict__ streams, const EncStreamDev *__rest
     l.src = audio_at(audio, st.audio_base); r.src = audio_at(audio, st.audio_base + (int64_t)st.n_samples);
     int32_t *o = vaudio + vs.audio_base;
     const uint64_t n = st.n_samples;
+    bool bad = false;
     for (uint64_t i = (uint64_t)part * blockDim.x + threadIdx.x; i < n; i += (uint64_t)parts * blockDim.x) {
         const int32_t a = sample_at(l, (uint32_t)i), b = sample_at(r, (uint32_t)i);
-        o[i] = a; o[n + i] = b; o[2 * n + i] = (a + b) >> 1; o[3 * n + i] = a - b;
+        o[i] = a; o[n + i] = b; o[2 * n + i] = (int32_t)(((long long)a + b) >> 1); o[3 * n + i] = a - b;
+        bad |= ((long long)a - b) != (long long)(a - b);
     }
+    if (bad) atomicOr(err_flag + 1, 1u);      // a side sample does not fit int32: the caller's range promise was wrong
 }
 
 __global__ void __launch_bounds__(256)
@@ -1250,8 +1258,12 @@ static inline void make_tukey(float *w, int L, float p) {
 }
 
 // libFLAC's stereo decorrelation applies to exactly two channels at the presets with do_mid_side; the GPU path covers
-// 16-bit streams (a 32-bit stream would need a 33-bit side channel: those stay independent)
-static inline bool enc_mid_side(const frb_encode_params *p) { return p->channels == 2 && p->bps == 16 && level_cfg(p->level).mid_side; }
+// 16-bit streams (17-bit side channel)
+// ... and 32-bps streams whose caller vouches that every sample is below 2^30 in magnitude (FRB_ENC_RANGE_30: the tile path's
+// 24-bit audio of float32 / 32-bit rasters), so that the 33-bit side channel L - R is held exactly by the int32 planar audio.
+static inline bool enc_mid_side(const frb_encode_params *p) {
+    return p->channels == 2 && level_cfg(p->level).mid_side && (p->bps == 16 || (p->bps == 32 && (p->reserved & 2u)));
+}
 
 // frb_encode_emit needs the frame count frb_encode_analyse computed; it is remembered per host thread for the usual
 // analyse -> emit sequence on one workspace (otherwise emit reads it back from the stream table: one more round trip)
@@ -1332,7 +1344,7 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const void *d_audi
         for (uint32_t i = 0; i < p->n_streams; i++) max_n = std::max<uint64_t>(max_n, hs[i].n_samples);
         uint32_t gx = (uint32_t)std::min<uint64_t>((max_n + 256 * 8 - 1) / (256 * 8), std::max<uint32_t>(1u, (uint32_t)kNumSMs * 16 / p->n_streams));
         if (gx < 1) gx = 1;
-        k_ms_expand<<<gx * p->n_streams, 256, 0, s>>>(w.streams, w.vstreams, in_audio, w.vaudio, gx);
+        k_ms_expand<<<gx * p->n_streams, 256, 0, s>>>(w.streams, w.vstreams, in_audio, w.vaudio, gx, w.err_flag);
         FRB_LAUNCH_CHECK("k_ms_expand");
     }
     const uint32_t slot_words = slot_words_for(p->blocksize, enc_slot_bps(p));
@@ -1491,9 +1503,10 @@ extern "C" int frb_encode_emit(const frb_encode_params *p, void *d_workspace, si
     FRB_LAUNCH_CHECK("k_emit_frames");
     if (d_frame_bytes)
         FRB_CUDA(cudaMemcpyAsync(d_frame_bytes, w.frame_bytes, 4 * (size_t)frames, cudaMemcpyDeviceToDevice, s));
-    uint32_t h_err = 0;
-    FRB_TRY(small_download(&h_err, w.err_flag, 4, s));
-    if (h_err) return FRB_ERR_OVERFLOW;
+    uint32_t h_err[2] = {0, 0};
+    FRB_TRY(small_download(h_err, w.err_flag, 8, s));
+    if (h_err[1]) return FRB_ERR_INVALID_ARG;     // FRB_ENC_RANGE_30 was set but a side sample did not fit int32
+    if (h_err[0]) return FRB_ERR_OVERFLOW;
     return FRB_OK;
 }
 extern "C" int frb_encode_index(const frb_encode_params *p, void *d_workspace, size_t workspace_bytes,

@@ -725,7 +725,7 @@ k_enc_model(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bp
 // ------------------------------------------------------------------------------------------------ code
 template <bool WIDE>
 struct CodeShared {
-    uint32_t bitbuf[WIDE ? 4100 : 2052];
+    uint32_t bitbuf[WIDE ? 4232 : 2052];       // VERBATIM upper bound: 8 + 32 + 4096 x 33 bits (the 33-bit side subframe of a 32-bps stream)
     SearchShared search;
     uint8_t best_params[64];
     uint32_t scan[kEncThreads / 32];
@@ -738,6 +738,13 @@ __device__ __forceinline__ void put_bits_atomic(uint32_t *buf, uint32_t pos, uin
     const uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x;
     if (hi) atomicOr(&buf[pos >> 5], hi);
     if (lo) atomicOr(&buf[(pos >> 5) + 1], lo);
+}
+
+// A sample of a subframe with `bps` bits per sample, bps up to 33 (the side subframe of a two-channel 32-bps stream): the
+// samples are int32 (the caller guarantees that the side channel fits), so a 33rd bit is the sign.
+__device__ __forceinline__ void put_sample_atomic(uint32_t *buf, uint32_t pos, int32_t x, uint32_t bps) {
+    if (bps > 32) { put_bits_atomic(buf, pos, x < 0 ? 1u : 0u, bps - 32); put_bits_atomic(buf, pos + bps - 32, (uint32_t)x, 32); }
+    else if (bps) put_bits_atomic(buf, pos, (uint32_t)x & (bps == 32 ? 0xFFFFFFFFu : ((1u << bps) - 1u)), bps);
 }
 
 // Per-thread bit accumulator over the zeroed shared word buffer (MSB first).  `hi` holds the pending bits of
@@ -1052,11 +1059,11 @@ k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps
         const uint32_t typecode = type == 0 ? 0u : type == 1 ? 1u : type == 2 ? (8u | (uint32_t)order) : (32u | (uint32_t)(order - 1));
         put_bits_atomic(S.bitbuf, 0, (typecode << 1) | (wasted ? 1u : 0u), 8);
         if (wasted) put_bits_atomic(S.bitbuf, 8 + wasted - 1, 1, 1);
-        if (type == 0 && bps) put_bits_atomic(S.bitbuf, pos0, (uint32_t)(sample_at(L, 0) >> wasted) & mask_bps, bps);
+        if (type == 0 && bps) put_sample_atomic(S.bitbuf, pos0, sample_at(L, 0) >> wasted, bps);
     }
     if (type >= 2) {
         if (tid >= 32 && tid < 32 + order)                   // warm-up sample j = tid - 32
-            put_bits_atomic(S.bitbuf, pos0 + (uint32_t)(tid - 32) * bps, (uint32_t)(sample_at(L, (uint32_t)(tid - 32)) >> wasted) & mask_bps, bps);
+            put_sample_atomic(S.bitbuf, pos0 + (uint32_t)(tid - 32) * bps, sample_at(L, (uint32_t)(tid - 32)) >> wasted, bps);
         const uint32_t pos1 = pos0 + (uint32_t)order * bps;
         if (type == 3) {
             const uint32_t prec = (uint32_t)best_prec;
@@ -1078,8 +1085,13 @@ k_enc_code(const FrameDesc *__restrict__ frames, uint32_t channels, uint32_t bps
                 for (int j = 12; j < 28; j++) xr[j] >>= wasted;
             }
             const int32_t (&xs)[28] = pick_ref<RELOAD>(xr, xs0);
+            if (WIDE && bps > 32) {
 #pragma unroll
-            for (int s = 0; s < kSPT; s++) bw.put((uint32_t)xs[12 + s] & mask_bps, bps);
+                for (int s = 0; s < kSPT; s++) { bw.put(xs[12 + s] < 0 ? 1u : 0u, bps - 32); bw.put((uint32_t)xs[12 + s], 32); }
+            } else {
+#pragma unroll
+                for (int s = 0; s < kSPT; s++) bw.put((uint32_t)xs[12 + s] & mask_bps, bps);
+            }
         }
         bw.finish();
     } else if (type >= 2) {

@@ -141,7 +141,7 @@ k_minmax_tiles(const T *__restrict__ raster, uint32_t bands, uint32_t H, uint32_
         if (rs.tail0 + lane < t.w) take(src[rs.tail0 + lane]);
         const T *body = src + rs.head;
         uint32_t g = lane;
-        if (PACK16) {
+        if constexpr (PACK16) {
             if (g < rs.ngroups) pany = true;
             for (; g + 96 < rs.ngroups; g += 128) {
                 const uint4 v0 = ld_stream16(body + (size_t)g * G), v1 = ld_stream16(body + (size_t)(g + 32) * G),
@@ -149,22 +149,22 @@ k_minmax_tiles(const T *__restrict__ raster, uint32_t bands, uint32_t H, uint32_
                 take_vec(v0); take_vec(v1); take_vec(v2); take_vec(v3);
             }
             for (; g < rs.ngroups; g += 32) take_vec(ld_stream16(body + (size_t)g * G));
-            continue;
-        }
-        for (; g + 96 < rs.ngroups; g += 128) {
-            T e0[G], e1[G], e2[G], e3[G];
-            load_group(body + (size_t)g * G, e0);
-            load_group(body + (size_t)(g + 32) * G, e1);
-            load_group(body + (size_t)(g + 64) * G, e2);
-            load_group(body + (size_t)(g + 96) * G, e3);
+        } else {
+            for (; g + 96 < rs.ngroups; g += 128) {
+                T e0[G], e1[G], e2[G], e3[G];
+                load_group(body + (size_t)g * G, e0);
+                load_group(body + (size_t)(g + 32) * G, e1);
+                load_group(body + (size_t)(g + 64) * G, e2);
+                load_group(body + (size_t)(g + 96) * G, e3);
 #pragma unroll
-            for (int j = 0; j < G; j++) { take(e0[j]); take(e1[j]); take(e2[j]); take(e3[j]); }
-        }
-        for (; g < rs.ngroups; g += 32) {
-            T e0[G];
-            load_group(body + (size_t)g * G, e0);
+                for (int j = 0; j < G; j++) { take(e0[j]); take(e1[j]); take(e2[j]); take(e3[j]); }
+            }
+            for (; g < rs.ngroups; g += 32) {
+                T e0[G];
+                load_group(body + (size_t)g * G, e0);
 #pragma unroll
-            for (int j = 0; j < G; j++) take(e0[j]);
+                for (int j = 0; j < G; j++) take(e0[j]);
+            }
         }
     }
     if (PACK16 && pany) { take((T)(pmn & 0xFFFFu)); take((T)(pmn >> 16)); take((T)(pmx & 0xFFFFu)); take((T)(pmx >> 16)); }

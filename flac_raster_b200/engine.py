@@ -180,7 +180,7 @@ class Engine:
 
     def encode_audio(self, audio: torch.Tensor, n_samples: np.ndarray, audio_base: np.ndarray, sample_rates: np.ndarray,
                      channels: int, bps: int, level: int = 5, blocksize: int = 4096, payload_name: str = "payload",
-                     fetch=None):
+                     fetch=None, range30: bool = False):
         """planar audio on the device (int32, or int16 for 16-bps streams: the element type is taken from the tensor) ->
         (payload uint8 tensor, offsets, sizes, frame sizes, subframe offsets).
         One host synchronisation: the per-stream sizes, which fix where every stream's frames go.  `fetch(d_sizes)`
@@ -191,7 +191,10 @@ class Engine:
         a16 = audio.dtype == torch.int16
         if a16 and bps != 16:
             raise ValueError("int16 audio is for 16-bps streams")
-        p = nat.EncodeParams(n_streams, channels, bps, blocksize, level, nat.ENC_AUDIO_I16 if a16 else 0)
+        # range30: the caller vouches that a 32-bps stream holds samples below 2^30 in magnitude (24-bit audio of the tile path), which
+        # lets two-channel streams use libFLAC's mid/side search there too (the 33-bit side channel then fits the int32 audio)
+        p = nat.EncodeParams(n_streams, channels, bps, blocksize, level,
+                             (nat.ENC_AUDIO_I16 if a16 else 0) | (nat.ENC_RANGE_30 if (range30 and bps == 32) else 0))
         frames = int(((n_samples + blocksize - 1) // blocksize).sum())
         ws_bytes = C.c_size_t(0)
         nat.check(self.L.frb_encode_workspace_size(C.byref(p), frames, C.byref(ws_bytes)), "frb_encode_workspace_size")
@@ -268,7 +271,8 @@ class Engine:
             return host[:8 * n].view(np.int64)
 
         fetch.d_sizes = d_sizes
-        payload, offsets, sizes, fb, sb = self.encode_audio(audio, npx, base, rates, bands, bps, level, blocksize, payload_name, fetch=fetch)
+        payload, offsets, sizes, fb, sb = self.encode_audio(audio, npx, base, rates, bands, bps, level, blocksize, payload_name, fetch=fetch,
+                                                            range30=(bits == 24))
         enc = EncodedTiles(payload, offsets, sizes, got["minmax"], npx, rates, bands, bps, bits, blocksize, fb, sb)
         enc.sizes_all = got.get("sizes_all")
         return enc

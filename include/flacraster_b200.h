@@ -146,10 +146,15 @@ typedef struct frb_encode_params {
     uint32_t bps;               /* 16 or 32 (what pyflac derives, docs/sonos-pyflac.txt:1988-1991) */
     uint32_t blocksize;         /* 16..4096 */
     uint32_t level;             /* 0..8 */
-    uint32_t reserved;          /* flags: FRB_ENC_AUDIO_I16 */
+    uint32_t reserved;          /* flags: FRB_ENC_AUDIO_I16, FRB_ENC_RANGE_30 */
 } frb_encode_params;
 /* d_audio of frb_encode_analyse holds int16 elements (bps must be 16; written by frb_normalize_tiles_i16) */
 #define FRB_ENC_AUDIO_I16 1u
+/* every sample of a 32-bps stream is below 2^30 in magnitude (24-bit audio in a 32-bps stream, what the reference makes of
+ * float32 / 32-bit rasters): two-channel streams then get libFLAC's mid/side search with its 33-bit side subframes, as 16-bps
+ * streams always do; without the flag they are coded as independent channels.  A sample that breaks the promise makes
+ * frb_encode_emit return FRB_ERR_INVALID_ARG. */
+#define FRB_ENC_RANGE_30 2u
 
 /* Bytes of device workspace needed by frb_encode_analyse/emit for
  * `total_frames` frames (sum over streams of ceil(n/blocksize)). */

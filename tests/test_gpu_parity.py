@@ -620,6 +620,66 @@ def test_two_band_raster_mid_side_tiles(nat, oracle, torch_cuda):
     assert torch.equal(out.view(torch.int16), raster.view(torch.int16))
 
 
+@pytest.mark.parametrize("dt", ["float32", "int32"])
+def test_two_band_32bit_raster_mid_side_with_33bit_side(nat, oracle, torch_cuda, dt):
+    """A 2-band float32 / int32 raster: the reference hands libFLAC a two-channel 32-bps stream, and libFLAC's presets run the
+    mid/side search there too, with a 33-bit side subframe (docs/sonos-pyflac.txt:6926-6934).  The tile path's audio is 24-bit
+    (scale 8388607), so L - R fits the int32 planar audio and the GPU encoder runs the same search (FRB_ENC_RANGE_30): frames
+    equal the oracle's at levels 0-8 (tail frames through the one-kernel encoder included), the decorrelated forms are
+    actually chosen, the frames are smaller than independent coding and decode back on the GPU (33-bit warm-up samples,
+    side reconstruction)."""
+    torch = torch_cuda
+    from flac_raster_b200 import flacfmt
+    from flac_raster_b200.engine import Engine, tile_grid
+    from oracle import normalization_oracle as no
+    rng = np.random.default_rng(31)
+    H, W = 200, 330
+    yy, xx = np.mgrid[0:H, 0:W]
+    base = 1200.0 + 700.0 * np.sin(xx / 37.0) * np.cos(yy / 23.0) + rng.normal(0, 0.4, size=(H, W))
+    other = base * 0.98 + 11.0 + rng.normal(0, 0.05, size=(H, W))
+    x = np.stack([base, other])
+    x = x.astype(np.float32) if dt == "float32" else np.round(x * 1000).astype(np.int32)
+    raster = torch.from_numpy(x).cuda()
+    eng = Engine()
+    tiles = tile_grid(H, W, 128)
+    for level in (0, 1, 5, 8):
+        enc = eng.encode_tiles(raster, tiles, level)
+        assert enc.bps == 32 and enc.bits_per_sample == 24
+        payload = enc.payload.cpu().numpy()
+        assigns, indep = set(), 0
+        for i, t in enumerate(tiles):
+            r, c, h, w = (int(t[k]) for k in ("row_off", "col_off", "h", "w"))
+            want, prm = no.normalize_to_audio(x[:, r:r + h, c:c + w].transpose(1, 2, 0).reshape(-1, 2), 24)
+            oenc, ofs, descs = oracle.encode(want.astype(np.int32), 32, int(enc.sample_rates[i]), level, want_descs=True)
+            assigns.update(d["ch_assign"] for d in descs)
+            frames = payload[enc.offsets[i]:enc.offsets[i] + enc.sizes[i]].tobytes()
+            assert frames == oenc[len(oenc) - int(ofs.sum()):], (level, i)
+            plain, pfs = oracle.encode(want.astype(np.int32), 32, int(enc.sample_rates[i]), level, mid_side=False)
+            indep += int(pfs.sum())
+        if level:                                              # level 0 has no stereo search
+            assert assigns & {8, 9, 10}, (level, assigns)
+            assert int(enc.sizes.sum()) < 0.97 * indep, (level, int(enc.sizes.sum()), indep)
+        dev_payload = torch.cat([enc.payload, torch.zeros(64, dtype=torch.uint8, device=raster.device)])
+        audio, abase, st = eng.decode_streams(dev_payload, enc.offsets, enc.sizes, enc.n_samples, enc.sample_rates, 2, 32, 4096)
+        assert list(st[:3]) == [0, 0, 0], st
+        out = torch.zeros_like(raster)
+        eng.denormalize_tiles(audio, abase, tiles, enc.minmax, 8388607.0, out)
+        want_px = np.zeros_like(x)
+        for i, t in enumerate(tiles):
+            r, c, h, w = (int(t[k]) for k in ("row_off", "col_off", "h", "w"))
+            a, prm = no.normalize_to_audio(x[:, r:r + h, c:c + w].transpose(1, 2, 0).reshape(-1, 2), 24)
+            back = no.denormalize_from_audio(a, prm["data_min"], prm["data_max"], dt, prm["scale_factor"])
+            want_px[:, r:r + h, c:c + w] = back.T.reshape(2, h, w)
+        assert np.array_equal(out.cpu().numpy(), want_px), level
+    # a stream that breaks the range promise is refused, not mis-coded
+    big = torch.tensor([[2 ** 30 + 5] * 5000, [-(2 ** 30) - 9] * 5000], dtype=torch.int32).cuda().reshape(-1)
+    n = np.array([5000], dtype=np.int64)
+    with pytest.raises(nat.NativeError) as ei:
+        eng.encode_audio(big, n, np.array([0], dtype=np.int64), np.array([44100], dtype=np.uint32), 2, 32, 5, 4096, range30=True)
+    assert ei.value.status == nat.ERR_INVALID_ARG
+    eng.encode_audio(big, n, np.array([0], dtype=np.int64), np.array([44100], dtype=np.uint32), 2, 32, 5, 4096)    # independent: fine
+
+
 def test_host_pipeline_equals_device_path(nat, torch_cuda):
     """encode_tiles_host (tile rows pipelined over copy/compute/copy streams, host buffers) produces exactly the
     bytes, offsets and min/max of the one-shot device path, including ragged edge tiles."""
