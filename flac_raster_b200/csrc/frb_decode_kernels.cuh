@@ -201,9 +201,17 @@ struct BitReader {
         consume(nb);
         return v;
     }
-    __device__ __forceinline__ int32_t get_signed(uint32_t nb) {    // nb in 0..33
+    // nb in 0..33.  A 33-bit sample (side subframe of a two-channel 32-bps stream) is returned as int32: *ovf is set when its
+    // 33rd bit is not the sign of the other 32, i.e. the value does not fit (full-range 32-bit stereo audio; the reference's
+    // 24-bit audio always fits) -- the caller reports the subframe as undecodable instead of handing out a wrapped sample.
+    __device__ __forceinline__ int32_t get_signed(uint32_t nb, bool *ovf = nullptr) {
         if (nb == 0) return 0;
-        if (nb > 32) { consume(nb - 32); nb = 32; }
+        if (nb > 32) {
+            const uint32_t top = get(nb - 32);
+            const uint32_t v = get(32);
+            if (ovf && top != (v >> 31)) *ovf = true;
+            return (int32_t)v;
+        }
         const uint32_t v = get(nb);
         const uint32_t sh = 32 - nb;
         return (int32_t)(v << sh) >> sh;
@@ -477,6 +485,28 @@ __device__ __forceinline__ int32_t lpc_predict(const int32_t (&cf)[MAXORD], cons
 #endif
 }
 
+// v << wasted (wasted-bits restore) with a check that nothing is shifted out: only a 33-bit side subframe of full-range
+// 32-bit audio can do that (see BitReader::get_signed)
+__device__ __forceinline__ int32_t shl_checked(int32_t v, uint32_t wasted, bool &err) {
+    const int32_t r = (int32_t)((uint32_t)v << wasted);
+    if ((r >> wasted) != v) err = true;
+    return r;
+}
+
+// the prediction in 64 bits (the 64-bit instantiations check that prediction + residual still fits int32)
+template <int MAXORD>
+__device__ __forceinline__ long long lpc_predict64(const int32_t (&cf)[MAXORD], const int32_t *Hj, int shift) {
+    long long acc = 0;
+#if FRB_LPC_NEWEST_LAST
+#pragma unroll
+    for (int q = MAXORD - 1; q >= 0; q--) acc += (long long)cf[q] * (long long)Hj[-q];
+#else
+#pragma unroll
+    for (int q = 0; q < MAXORD; q++) acc += (long long)cf[q] * (long long)Hj[-q];
+#endif
+    return acc >> shift;
+}
+
 // Optional fused denormalise: instead of the planar int32 audio buffer, a decode thread can write its samples straight
 // into the window of the (bands,H,W) raster that its tile covers (denormalize_from_audio, normalization.py:222-249,
 // same fp64 operation order as k_denormalize_tiles).  This removes the audio round trip through HBM (4 B written +
@@ -696,11 +726,12 @@ __device__ __forceinline__ void decode_prologue(SubCtx &S, bool active, PredStat
     P.escape = false; P.wide = false;
     if (!active) return;
     for (uint32_t w = 0; w < order; w++) {
-        const int32_t v = br.get_signed(S.sbps);
+        const int32_t v = br.get_signed(S.sbps, &S.err);
 #pragma unroll
         for (int q = 0; q < PMAX - 1; q++) P.hist[q] = P.hist[q + 1];
         P.hist[PMAX - 1] = v;
-        if (!RASTER) S.dst[w] = (int32_t)((uint32_t)v << wasted); else sink_put1(G, S.rp, (int32_t)((uint32_t)v << wasted));
+        const int32_t sv = shl_checked(v, wasted, S.err);
+        if (!RASTER) S.dst[w] = sv; else sink_put1(G, S.rp, sv);
     }
     br.top_up();
     if (S.type == 3) {
@@ -712,13 +743,13 @@ __device__ __forceinline__ void decode_prologue(SubCtx &S, bool active, PredStat
         for (int q = 0; q < PMAX; q++) if ((uint32_t)q < order) { P.cf[q] = br.get_signed(prec); if ((q & 7) == 7) br.top_up(); }
         br.top_up();
         // libFLAC's rule: 32-bit arithmetic is exact when bps + precision + ilog2(order) <= 32
-        P.wide = S.sbps + prec + (uint32_t)(31 - __clz(order | 1u)) > 32u;
+        P.wide = S.sbps + prec + (uint32_t)(31 - __clz(order | 1u)) > 32u || S.sbps + wasted > 32u;    // 33-bit subframes: range-checked loop
     } else {
         if (order >= 1) P.cf[0] = order == 1 ? 1 : order == 2 ? 2 : order == 3 ? 3 : 4;
         if (order >= 2) P.cf[1] = order == 2 ? -1 : order == 3 ? -3 : -6;
         if (order >= 3) P.cf[2] = order == 3 ? 1 : 4;
         if (order >= 4) P.cf[3] = -1;
-        P.wide = S.sbps + order > 32u;
+        P.wide = S.sbps + order > 32u || S.sbps + wasted > 32u;
     }
     const uint32_t m = br.get(2);
     const uint32_t po = br.get(4);
@@ -779,10 +810,21 @@ __device__ __forceinline__ void decode_predictive(SubCtx &S, const PredState<PMA
         return maxlen;
     };
     // predictor recursion over a parsed batch into H[MAXORD..]; output of the batch at sample index i
+    // 64-bit instantiations: a reconstructed sample that does not fit int32 (a 33-bit side channel of full-range 32-bit audio;
+    // also what damaged data can produce) marks the subframe as undecodable instead of wrapping silently
+    uint32_t ovf = 0;
     auto reconstruct = [&](const uint32_t (&uu)[kDecBatch]) {
 #pragma unroll
-        for (int j = 0; j < kDecBatch; j++)
-            H[MAXORD + j] = unzigzag(uu[j]) + lpc_predict<MAXORD, WIDE>(cf, &H[MAXORD - 1 + j], shift);
+        for (int j = 0; j < kDecBatch; j++) {
+            if constexpr (WIDE) {
+                const long long v = (long long)unzigzag(uu[j]) + lpc_predict64<MAXORD>(cf, &H[MAXORD - 1 + j], shift);
+                H[MAXORD + j] = (int32_t)v;
+                const long long vs = v << wasted;                 // what is stored: must fit int32 as well
+                ovf |= (uint32_t)((int32_t)(vs >> 32) ^ ((int32_t)vs >> 31));
+            } else {
+                H[MAXORD + j] = unzigzag(uu[j]) + lpc_predict<MAXORD, WIDE>(cf, &H[MAXORD - 1 + j], shift);
+            }
+        }
     };
     auto output_batch = [&]() {
         if (RASTER) {
@@ -803,7 +845,15 @@ __device__ __forceinline__ void decode_predictive(SubCtx &S, const PredState<PMA
     };
     auto single_sample = [&]() {
         const int32_t r = escape ? br.get_signed(raw_bits) : unzigzag(br.rice_u(k));
-        const int32_t v = r + lpc_predict<MAXORD, WIDE>(cf, &H[MAXORD - 1], shift);
+        int32_t v;
+        if constexpr (WIDE) {
+            const long long v64 = (long long)r + lpc_predict64<MAXORD>(cf, &H[MAXORD - 1], shift);
+            v = (int32_t)v64;
+            const long long vs = v64 << wasted;
+            ovf |= (uint32_t)((int32_t)(vs >> 32) ^ ((int32_t)vs >> 31));
+        } else {
+            v = r + lpc_predict<MAXORD, WIDE>(cf, &H[MAXORD - 1], shift);
+        }
 #pragma unroll
         for (int q = 0; q < MAXORD - 1; q++) H[q] = H[q + 1];
         H[MAXORD - 1] = v;
@@ -839,6 +889,7 @@ __device__ __forceinline__ void decode_predictive(SubCtx &S, const PredState<PMA
             k = br.get(plen); escape = (k == esc); raw_bits = escape ? br.get(5) : 0; part_left = psize;
         }
     }
+    if (WIDE && ovf) S.err = true;
 }
 
 #ifndef FRB_DEC_MINB
@@ -963,13 +1014,13 @@ k_decode_subframes(const uint8_t *__restrict__ bytes, const DecStreamDev *__rest
     const bool run = alive && !S.err;
     if (run) {
         if (S.type == 0) {
-            const int32_t v = (int32_t)((uint32_t)S.br.get_signed(S.sbps) << S.wasted);
+            const int32_t v = shl_checked(S.br.get_signed(S.sbps, &S.err), S.wasted, S.err);
             if (!RASTER) { for (uint32_t i = 0; i < S.n; i++) S.dst[i] = v; }
             else { for (uint32_t i = 0; i < S.n; i++) sink_put1(sink, S.rp, v); }
         } else if (S.type == 1) {
             for (uint32_t i = 0; i < S.n; i++) {
                 if ((i & 3u) == 0) S.br.top_up();
-                const int32_t v = (int32_t)((uint32_t)S.br.get_signed(S.sbps) << S.wasted);
+                const int32_t v = shl_checked(S.br.get_signed(S.sbps, &S.err), S.wasted, S.err);
                 if (!RASTER) S.dst[i] = v; else sink_put1(sink, S.rp, v);
             }
         } else if (!BIGORDER && S.order > 12) {

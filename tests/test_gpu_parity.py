@@ -671,6 +671,18 @@ def test_two_band_32bit_raster_mid_side_with_33bit_side(nat, oracle, torch_cuda,
             back = no.denormalize_from_audio(a, prm["data_min"], prm["data_max"], dt, prm["scale_factor"])
             want_px[:, r:r + h, c:c + w] = back.T.reshape(2, h, w)
         assert np.array_equal(out.cpu().numpy(), want_px), level
+    # the other direction: a foreign two-channel 32-bps stream whose side channel really needs 33 bits (full-range audio, never
+    # made by the reference) cannot be held by the int32 sample path: the decoder must say so, not hand out wrapped samples
+    t = np.arange(12000)
+    wob = (900 * np.sin(t / 50.0)).astype(np.int64) + rng.integers(-40, 40, size=t.size)
+    wide = np.stack([(1 << 30) + 1000 + wob, -(1 << 30) - 1000 + wob], axis=1).astype(np.int32)
+    oenc, ofs, descs = oracle.encode(wide, 32, 44100, 5, want_descs=True)
+    assert {d["ch_assign"] for d in descs} & {8, 9, 10}
+    ref, _ = oracle.decode(oenc)
+    assert np.array_equal(ref, wide)
+    with pytest.raises(nat.NativeError) as ei:
+        nat.host_decode(oenc[len(oenc) - int(ofs.sum()):], 2, 32, 4096, 44100, wide.shape[0])
+    assert ei.value.status == nat.ERR_BAD_STREAM
     # a stream that breaks the range promise is refused, not mis-coded
     big = torch.tensor([[2 ** 30 + 5] * 5000, [-(2 ** 30) - 9] * 5000], dtype=torch.int32).cuda().reshape(-1)
     n = np.array([5000], dtype=np.int64)
