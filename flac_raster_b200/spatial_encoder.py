@@ -621,7 +621,8 @@ class SpatialFLACStreamer:
 
                     res = decode_staged_tiles(stage, nbytes, starts, sizes, data=data, while_copying=build_metas)
                     if res is None:
-                        fut.result() if g + 1 < len(groups) else None
+                        if g + 1 < len(groups):
+                            fut.result()                    # let the read in flight finish before its buffers are reused
                         return None
                     out.extend(zip(res[0], metas))
         return out
