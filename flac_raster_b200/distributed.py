@@ -95,8 +95,8 @@ def allgather_tile_sizes(local_sizes: np.ndarray, n_tiles: int, rank: int, world
 
 class SizeExchange:
     """The path's one collective as a stream-ordered step of Engine.encode_tiles: all-gather of the per-tile frame sizes
-    (int64, device to device over NCCL/NVLink) between the analysis kernels and the size download, so that the other
-    ranks' sizes arrive in the transfer the step needs anyway.  Ranks hold contiguous blocks of shard_range(n_tiles)."""
+    (int64, device to device over NCCL/NVLink) started behind the analysis kernels, running next to the frame assembly and
+    joined in front of the step's single download, so that the other ranks' sizes arrive in the transfer the step needs anyway.  Ranks hold contiguous blocks of shard_range(n_tiles)."""
 
     def __init__(self, n_tiles: int, rank: int, world: int, device):
         self.n_tiles, self.rank, self.world, self.device = n_tiles, rank, world, device
@@ -105,9 +105,21 @@ class SizeExchange:
         self.recv_count = self.per * world
         self._send = torch.zeros(self.per, dtype=torch.int64, device=device)
 
-    def enqueue(self, d_sizes: torch.Tensor, d_recv: torch.Tensor):
+    def start(self, d_sizes: torch.Tensor, d_recv: torch.Tensor):
+        """Enqueue the all-gather behind what the current stream holds (the analysis kernels that produce d_sizes) WITHOUT making
+        the stream wait for it: the collective runs on the process group's own stream next to the frame assembly."""
         self._send[:d_sizes.numel()].copy_(d_sizes, non_blocking=True)
-        dist.all_gather_into_tensor(d_recv, self._send)
+        self._work = dist.all_gather_into_tensor(d_recv, self._send, async_op=True)
+
+    def wait(self):
+        """Make the current stream wait for the collective started by start() (no host synchronisation)."""
+        w, self._work = getattr(self, "_work", None), None
+        if w is not None:
+            w.wait()
+
+    def enqueue(self, d_sizes: torch.Tensor, d_recv: torch.Tensor):
+        self.start(d_sizes, d_recv)
+        self.wait()
 
     def unpack(self, recv_host: np.ndarray) -> np.ndarray:
         recv = np.asarray(recv_host, dtype=np.int64).reshape(self.world, self.per)

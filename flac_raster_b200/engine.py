@@ -223,6 +223,8 @@ class Engine:
                 d_sizes = fetch.d_sizes
                 nat.check(self.L.frb_encode_analyse(C.byref(p), audio.data_ptr(), hn.ctypes.data, hr.ctypes.data, hb.ctypes.data,
                                                     ws.data_ptr(), ws.numel(), d_sizes.data_ptr(), None, s), "frb_encode_analyse")
+                if hasattr(fetch, "start"):
+                    fetch.start()                         # e.g. the multi-GPU size exchange: overlaps the frame assembly
                 bound = int(n_samples.sum()) * channels * (bps // 8) + frames * (24 + 8 * channels) + 64
                 if channels == 2:
                     bound += frames * blocksize // 4          # a side subframe carries one more bit per sample
@@ -261,9 +263,13 @@ class Engine:
         rates = sample_rates_for_pixel_counts(npx)                # one vector expression (4096 tiles: 5 ms of Python before)
         got = {}
 
+        def start():          # called by encode_audio between analysis and frame assembly
+            if size_exchange is not None:
+                size_exchange.start(d_sizes, combo[3 * n:].view(torch.int64))
+
         def fetch():
             if size_exchange is not None:
-                size_exchange.enqueue(d_sizes, combo[3 * n:].view(torch.int64))
+                size_exchange.wait()
             host = self._download(combo.view(torch.uint8), np.uint8, combo.numel() * 8)
             got["minmax"] = host[8 * n:24 * n].view(np.float64).reshape(-1, 2).copy()
             if size_exchange is not None:
@@ -271,6 +277,7 @@ class Engine:
             return host[:8 * n].view(np.int64)
 
         fetch.d_sizes = d_sizes
+        fetch.start = start
         payload, offsets, sizes, fb, sb = self.encode_audio(audio, npx, base, rates, bands, bps, level, blocksize, payload_name, fetch=fetch,
                                                             range30=(bits == 24))
         enc = EncodedTiles(payload, offsets, sizes, got["minmax"], npx, rates, bands, bps, bits, blocksize, fb, sb)
