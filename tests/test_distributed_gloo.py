@@ -32,6 +32,16 @@ def _worker(rank, world, port, path, n_tiles):
     local_file_sizes = psizes + 10
     sizes = allgather_tile_sizes(local_file_sizes, n_tiles, rank, world)
     assert list(sizes) == [17 + t for t in range(n_tiles)]
+    # the same exchange as the encode step runs it: started asynchronously behind the analysis, joined before the download
+    import torch
+    from flac_raster_b200.distributed import SizeExchange
+    x = SizeExchange(n_tiles, rank, world, "cpu")
+    recv = torch.zeros(x.recv_count, dtype=torch.int64)
+    x.start(torch.from_numpy(local_file_sizes.copy()), recv)
+    x.wait()
+    assert list(x.unpack(recv.numpy())) == [17 + t for t in range(n_tiles)]
+    x.enqueue(torch.from_numpy(local_file_sizes.copy()), recv)          # the blocking form
+    assert list(x.unpack(recv.numpy())) == [17 + t for t in range(n_tiles)]
     tiles = np.zeros(n_tiles, dtype=nat.TILE_DTYPE)
     tiles["h"] = 1
     tiles["w"] = 1
