@@ -29,6 +29,11 @@ __device__ __forceinline__ int32_t unzigzag(uint32_t u) {
     asm("bfe.s32 %0, %1, 0, 1;" : "=r"(sgn) : "r"(u));
     return (int32_t)(u >> 1) ^ sgn;
 }
+// (defined here, in front of its first use: round 2's first build had the default further down, so `#if FRB_BFIND_I2F` saw an
+// undefined macro and the library kept using bfind)
+#ifndef FRB_BFIND_I2F
+#define FRB_BFIND_I2F 1
+#endif
 // position of the most significant set bit (0xFFFFFFFF for 0): clz(w) = 31 - bfind(w), so the length of a Rice code with
 // parameter k is (k + 32) - bfind(window) in one subtraction, and 33 + k (> 32, "too long") for an all-zero window
 // Measured on B200 (tools/microbench/lat.cu, dependent chains): bfind/clz/popc ~20 cycles, an integer -> float conversion
@@ -99,9 +104,6 @@ __device__ __forceinline__ FrameLoc locate_frame(const DecStreamDev *__restrict_
 //     predicated copies, and one wait_group per batch covers every word the batch can touch.
 #ifndef FRB_SKIM_BATCH
 #define FRB_SKIM_BATCH 8
-#endif
-#ifndef FRB_BFIND_I2F
-#define FRB_BFIND_I2F 1
 #endif
 #ifndef FRB_LPC_NEWEST_LAST
 #define FRB_LPC_NEWEST_LAST 1
