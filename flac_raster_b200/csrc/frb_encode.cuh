@@ -1020,7 +1020,8 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
               uint32_t blocksize, uint32_t total_frames, const uint32_t *__restrict__ sub_bits,
               const uint32_t *__restrict__ slots, uint32_t slot_words, const uint32_t *__restrict__ frame_bytes,
               const unsigned long long *__restrict__ frame_off, uint8_t *__restrict__ out, uint64_t out_capacity,
-              uint32_t *__restrict__ err_flag, uint32_t vch, const uint8_t *__restrict__ frame_sel) {
+              uint32_t *__restrict__ err_flag, uint32_t vch, const uint8_t *__restrict__ frame_sel,
+              const FrameDesc *__restrict__ frame_table) {
     __shared__ __align__(16) EmitShared SS;
     constexpr int kGroups = kEmitThreads / TPF;
     const int tid = threadIdx.x % TPF, grp = threadIdx.x / TPF;
@@ -1031,11 +1032,9 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
     // persistent CTAs: the CRC tables (8 KB) are staged once, then every group walks frames with stride gridDim.x * kGroups
     for (uint32_t f = blockIdx.x * kGroups + grp; f < total_frames; f += gridDim.x * kGroups) {
     group_sync();                                         // previous frame's shared state consumed
-    uint32_t lo = 0, hi = n_streams - 1;
-    while (lo < hi) {
-        uint32_t mid = (lo + hi + 1) >> 1;
-        if (streams[mid].frame_base <= f) lo = mid; else hi = mid - 1;
-    }
+    // the frame's stream from the descriptor table of the analysis (one load instead of a binary search of log2(n_streams)
+    // dependent loads per frame: with 4096 streams of 64 small frames, C5, that search was a fifth of a frame's time)
+    const uint32_t lo = frame_table[f].stream;
     const EncStreamDev st = streams[lo];
     const uint32_t k = f - st.frame_base;
     const uint32_t n = (k + 1 < st.n_frames) ? blocksize : (uint32_t)(st.n_samples - (uint64_t)k * blocksize);
@@ -1385,6 +1384,10 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const void *d_audi
             }
         }
     }
+    // per-frame descriptors (stream index, sample position): the analysis kernels and the frame assembly look frames up
+    // here instead of searching the stream table per CTA
+    k_frame_table<<<(uint32_t)((frames + 255) / 256), 256, 0, s>>>(an_streams, p->n_streams, p->blocksize, (uint32_t)frames, w.frame_table);
+    FRB_LAUNCH_CHECK("k_frame_table");
     prof_begin(6, s);
     if (fast && slow.size() < total_tasks) {
         const uint32_t windows = (uint32_t)cfg.windows, max_lpc = (uint32_t)cfg.max_lpc_order;
@@ -1392,8 +1395,6 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const void *d_audi
         const bool wide = p->bps > 16;
         // one CTA per subframe; with mid/side the 17-bit side channel (virtual channel 3) runs in the 64-bit kernels
         const dim3 grid((uint32_t)frames, ms ? 3u : p->channels), grid_side((uint32_t)frames, 1);
-        k_frame_table<<<(uint32_t)((frames + 255) / 256), 256, 0, s>>>(an_streams, p->n_streams, p->blocksize, (uint32_t)frames, w.frame_table);
-        FRB_LAUNCH_CHECK("k_frame_table");
         prof_begin(4, s);
 #define FRB_STATS(W, NL, G, C0, EX) k_enc_stats<W, NL><<<G, kEncThreads, 0, s>>>(w.frame_table, an_ch, p->bps, windows, (uint32_t)cfg.max_po, an_audio, \
             w.window, w.stats, w.autoc, w.fx_fin, C0, EX)
@@ -1493,11 +1494,11 @@ extern "C" int frb_encode_emit(const frb_encode_params *p, void *d_workspace, si
         if (warp_per_frame)
             k_emit_frames<32><<<(uint32_t)std::min<uint64_t>((frames + 3) / 4, (uint64_t)kNumSMs * 16), kEmitThreads, 0, s>>>(
                 w.streams, p->n_streams, p->channels, p->bps, p->blocksize, (uint32_t)frames, w.sub_bits, w.slots, sw,
-                w.frame_bytes, w.frame_off, d_out, (uint64_t)out_capacity, w.err_flag, vch, sel);
+                w.frame_bytes, w.frame_off, d_out, (uint64_t)out_capacity, w.err_flag, vch, sel, w.frame_table);
         else
             k_emit_frames<kEmitThreads><<<(uint32_t)std::min<uint64_t>(frames, (uint64_t)kNumSMs * 16), kEmitThreads, 0, s>>>(
                 w.streams, p->n_streams, p->channels, p->bps, p->blocksize, (uint32_t)frames, w.sub_bits, w.slots, sw,
-                w.frame_bytes, w.frame_off, d_out, (uint64_t)out_capacity, w.err_flag, vch, sel);
+                w.frame_bytes, w.frame_off, d_out, (uint64_t)out_capacity, w.err_flag, vch, sel, w.frame_table);
     }
     prof_end(2, s);
     FRB_LAUNCH_CHECK("k_emit_frames");
