@@ -387,7 +387,9 @@ def decode_staged_tiles(stage, nbytes: int, starts: np.ndarray, sizes: np.ndarra
         while_copying(hdr)
     torch.cuda.current_stream().synchronize()
     host_out = host.numpy().view(dtype).reshape(channels, row, maxw)
-    if channels == 1 and (widths == maxw).all():
+    if n == 1:
+        arrays = [host_out]                      # one tile (get_tile_by_id): the result block IS the tile, whatever its band count
+    elif channels == 1 and (widths == maxw).all():
         arrays = [host_out[:, int(r0):int(r0 + h_)] for r0, h_ in zip(rows0, heights)]     # C-contiguous views, one owner
     else:
         arrays = _copy_tiles_out(host_out, rows0, heights, widths)
