@@ -1371,7 +1371,7 @@ extern "C" int frb_encode_analyse(const frb_encode_params *p, const void *d_audi
             const EncStreamDev &d = ahs[i];
             const bool tail = (d.n_samples % p->blocksize) != 0;
             for (uint32_t c = 0; c < an_ch; c++) {
-                const bool aligned = ((base_addr + ((uint64_t)d.audio_base + (uint64_t)c * d.n_samples) * an_esz) & 15u) == 0;
+                const bool aligned = ((base_addr + ((uint64_t)d.audio_base + (uint64_t)c * d.n_samples) * an_esz) & (an_esz == 2 ? 7u : 15u)) == 0;
                 for (uint32_t k = aligned ? (tail ? d.n_frames - 1 : d.n_frames) : 0; k < d.n_frames; k++)
                     slow.push_back((d.frame_base + k) * an_ch + c);
             }

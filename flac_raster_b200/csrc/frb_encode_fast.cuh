@@ -75,8 +75,10 @@ __device__ __forceinline__ TaskLoc locate_task(const FrameDesc *__restrict__ fra
 }
 // The fast path handles full 4096-sample blocks whose first sample is 16-byte aligned (the host lists every
 // other subframe for the one-kernel encoder with the same predicate, see frb_encode_analyse).
+// (int16 audio: 8-byte alignment is enough -- a channel that starts at a sample index of 4 mod 8 is read with 8-byte loads; with
+// 16 bytes required, tiles of h*w = 4 mod 8 pixels would have sent every other band to the one-kernel encoder)
 __device__ __forceinline__ bool fast_eligible(const TaskLoc &L) {
-    return L.n == (uint32_t)kMaxBlock && (reinterpret_cast<uintptr_t>(L.src) & 15u) == 0;
+    return L.n == (uint32_t)kMaxBlock && (reinterpret_cast<uintptr_t>(L.src) & (L.a16 ? 7u : 15u)) == 0;
 }
 
 // compile-time choice between two arrays of the same type (a reference, so that the unused one stays dead)
@@ -93,9 +95,15 @@ __device__ __forceinline__ void load_samples28(const TaskLoc &L, int tid, int32_
     if (L.a16) {
         // int16 audio: the thread's 16 samples are 32 bytes (two 16-byte loads), the halo 24 bytes (three 8-byte loads)
         const uint4 *p = reinterpret_cast<const uint4 *>(reinterpret_cast<const int16_t *>(L.src) + tid * kSPT);
+        const bool al16 = (reinterpret_cast<uintptr_t>(p) & 15u) == 0;          // uniform over the CTA (tid * 32 bytes)
 #pragma unroll
         for (int q = 0; q < 2; q++) {
-            const uint4 v = __ldg(p + q);
+            uint4 v;
+            if (al16) v = __ldg(p + q);
+            else {
+                const uint2 a = __ldg(reinterpret_cast<const uint2 *>(p) + 2 * q), b = __ldg(reinterpret_cast<const uint2 *>(p) + 2 * q + 1);
+                v = make_uint4(a.x, a.y, b.x, b.y);
+            }
             xs[12 + 8 * q] = s16_lo(v.x); xs[13 + 8 * q] = s16_hi(v.x); xs[14 + 8 * q] = s16_lo(v.y); xs[15 + 8 * q] = s16_hi(v.y);
             xs[16 + 8 * q] = s16_lo(v.z); xs[17 + 8 * q] = s16_hi(v.z); xs[18 + 8 * q] = s16_lo(v.w); xs[19 + 8 * q] = s16_hi(v.w);
         }

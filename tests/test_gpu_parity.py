@@ -748,8 +748,11 @@ def test_int16_audio_equals_int32_audio(nat, oracle, torch_cuda, dt):
     yy, xx = np.mgrid[0:H, 0:W]
     x = np.stack([np.clip(info.min // 2 + (info.max - info.min) // 3 * (1 + np.sin(xx / 19.0 + b) * np.cos(yy / 13.0)) / 2
                           + rng.integers(-3, 4, xx.shape), info.min, info.max).astype(dt) for b in range(bands)])
-    tiles = np.zeros(5, dtype=natmod.TILE_DTYPE)
+    tiles = np.zeros(7, dtype=natmod.TILE_DTYPE)
     tiles[0] = (0, 0, 128, 128); tiles[1] = (1, 3, 67, 211); tiles[2] = (7, 13, 33, 37); tiles[3] = (44, 1, 256, 512); tiles[4] = (2, 5, 5, 1)
+    # 250 x 250 = 4 mod 8 pixels: every other band starts 8-byte (not 16-byte) aligned in the int16 audio -- still the fast kernels;
+    # twice, so that the second one starts at a different alignment of the running base
+    tiles[5] = (10, 10, 250, 250); tiles[6] = (30, 200, 250, 250)
     eng = Engine()
     dev = torch.from_numpy(x.view(np.uint8).reshape(-1)).cuda().view(getattr(torch, dt)).reshape(bands, H, W)
     a32, base, npx, d_mm, bits = eng.normalize_tiles(dev, tiles)
