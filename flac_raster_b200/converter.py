@@ -380,12 +380,21 @@ def decode_staged_tiles(stage, nbytes: int, starts: np.ndarray, sizes: np.ndarra
     status = eng.decode_tiles(data, offs, lens, tiles, hdr["sample_rate"].astype(np.uint32), minmax, scale, out, bps, blocksize, index=index)
     _raise_for_status(status)
     nb = out.numel() * dtype.itemsize
+    # Multi-band tiles of one size: the decode wrote band-major planes (band, tile rows stacked, width); one device-side
+    # re-layout to (tile, band, h, w) lets every tile be handed out as a view of the result block instead of a strided
+    # host copy per tile (1.9 GB of host copies for a bbox query over an 8-band C3-sized scene).
+    tile_major = n > 1 and channels > 1 and bool((widths == maxw).all()) and bool((heights == heights[0]).all())
+    if tile_major:
+        out = out.view(channels, n, int(heights[0]), maxw).permute(1, 0, 2, 3).contiguous()
     # result buffer: a fresh pinned block per call (cached by torch's host allocator), owned by the arrays handed out
     host = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
     host.copy_(out.reshape(-1).view(torch.uint8), non_blocking=True)
     if while_copying is not None:
         while_copying(hdr)
     torch.cuda.current_stream().synchronize()
+    if tile_major:
+        tm = host.numpy().view(dtype).reshape(n, channels, int(heights[0]), maxw)
+        return [tm[i] for i in range(n)], hdr
     host_out = host.numpy().view(dtype).reshape(channels, row, maxw)
     if n == 1:
         arrays = [host_out]                      # one tile (get_tile_by_id): the result block IS the tile, whatever its band count

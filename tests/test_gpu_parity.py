@@ -1125,7 +1125,10 @@ def test_streamer_fast_path_equals_python_parse_path(nat, tmp_path, monkeypatch)
     write_geotiff(tmp_path / "rgb.tif", rgb, (30.0, 0.0, 4e5, 0.0, -30.0, 5e6), "EPSG:32633", 65535.0)
     dem = (2000 * np.sin(xx[:256, :384] / 31.0)).astype(np.int16)[None]
     write_geotiff(tmp_path / "dem.tif", dem, None, None, None)
-    for name, ts, src in (("rgb", 128, rgb), ("dem", 128, dem)):
+    # three bands, tiles all of one size: handed out as views of a (tile, band, h, w) result block
+    uni = np.stack([(500 + 300 * np.cos(xx[:256, :384] / 11.0 + b) + rng.integers(-4, 4, (256, 384))).astype(np.int16) for b in range(3)])
+    write_geotiff(tmp_path / "uni.tif", uni, (30.0, 0.0, 4e5, 0.0, -30.0, 5e6), "EPSG:32633", None)
+    for name, ts, src in (("rgb", 128, rgb), ("dem", 128, dem), ("uni", 128, uni)):
         out = tmp_path / f"{name}.flac"
         SpatialFLACEncoder(tile_size=ts).encode(tmp_path / f"{name}.tif", out, streaming=True)
         s = SpatialFLACStreamer(out)

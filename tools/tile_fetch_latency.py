@@ -30,3 +30,10 @@ ts = []
 for _ in range(15):
     t0 = time.perf_counter(); sb.get_tile_by_id(1); ts.append(time.perf_counter() - t0)
 print("C3-size tile get_tile_by_id ms: median %.3f min %.3f" % (1e3 * np.median(ts), 1e3 * min(ts)))
+# both tiles of that container through get_tiles_by_bbox (multi-band tiles of one size: views of a (tile, band, h, w) block)
+for _ in range(3): sb.get_tiles_by_bbox(-1e12, -1e12, 1e12, 1e12)
+ts = []
+for _ in range(10):
+    t0 = time.perf_counter(); res = sb.get_tiles_by_bbox(-1e12, -1e12, 1e12, 1e12); ts.append(time.perf_counter() - t0)
+print("2 x C3-size tiles get_tiles_by_bbox ms: median %.3f min %.3f (%d tiles, %.1f MB of pixels)" % (1e3 * np.median(ts), 1e3 * min(ts), len(res), sum(a.nbytes for a, _ in res) / 1e6))
+assert all(np.array_equal(a, big[:, m["window"]["row_off"]:m["window"]["row_off"] + 1024, m["window"]["col_off"]:m["window"]["col_off"] + 1024]) for a, m in res)
