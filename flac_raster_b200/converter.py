@@ -346,8 +346,22 @@ def decode_staged_tiles(stage, nbytes: int, starts: np.ndarray, sizes: np.ndarra
     if not (hdr["count"] == channels).all():
         raise ValueError("band count in tags does not match the FLAC channel count")
     dtype = np.dtype(_DTYPE_NAMES[int(h0["dtype"])])
+    hdr_in = hdr                                   # records in the caller's tile order (what is returned)
     widths = hdr["width"].astype(np.int64)
     heights = hdr["height"].astype(np.int64)
+    # Multi-band tiles: the decode writes band-major planes (band, tile rows stacked, width), so a tile is strided across its
+    # bands.  Tiles of the full size (all of them, or the interior of a scene whose edge tiles are ragged) are decoded FIRST:
+    # their part of the planes is re-laid out to (tile, band, h, w) on the device and handed out as views of the result block;
+    # only the ragged rest takes a strided host copy per tile (1.9 GB of host copies for a bbox query over an 8-band C3 scene).
+    full = (widths == widths.max()) & (heights == heights.max())
+    n_full = int(full.sum()) if (n > 1 and channels > 1) else 0
+    order = None
+    if 2 <= n_full < n:
+        order = np.argsort(~full, kind="stable")
+        hdr, offs64, size64 = hdr[order], np.ascontiguousarray(offs64[order]), np.ascontiguousarray(size64[order])
+        widths, heights = widths[order], heights[order]
+    elif n_full < 2:
+        n_full = 0
     nsamp = widths * heights
     tiles = np.zeros(n, dtype=nat.TILE_DTYPE)
     rows0 = np.zeros(n, dtype=np.int64)
@@ -380,21 +394,34 @@ def decode_staged_tiles(stage, nbytes: int, starts: np.ndarray, sizes: np.ndarra
     status = eng.decode_tiles(data, offs, lens, tiles, hdr["sample_rate"].astype(np.uint32), minmax, scale, out, bps, blocksize, index=index)
     _raise_for_status(status)
     nb = out.numel() * dtype.itemsize
-    # Multi-band tiles of one size: the decode wrote band-major planes (band, tile rows stacked, width); one device-side
-    # re-layout to (tile, band, h, w) lets every tile be handed out as a view of the result block instead of a strided
-    # host copy per tile (1.9 GB of host copies for a bbox query over an 8-band C3-sized scene).
-    tile_major = n > 1 and channels > 1 and bool((widths == maxw).all()) and bool((heights == heights[0]).all())
-    if tile_major:
-        out = out.view(channels, n, int(heights[0]), maxw).permute(1, 0, 2, 3).contiguous()
     # result buffer: a fresh pinned block per call (cached by torch's host allocator), owned by the arrays handed out
     host = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+    if n_full:
+        hf = int(heights[0])
+        nb_full = channels * n_full * hf * maxw * dtype.itemsize
+        tm_dev = out[:, :n_full * hf].reshape(channels, n_full, hf, maxw).permute(1, 0, 2, 3).contiguous()
+        host[:nb_full].copy_(tm_dev.reshape(-1).view(torch.uint8), non_blocking=True)
+        if n_full < n:
+            rest_dev = out[:, n_full * hf:].contiguous()
+            host[nb_full:].copy_(rest_dev.reshape(-1).view(torch.uint8), non_blocking=True)
+        if while_copying is not None:
+            while_copying(hdr_in)
+        torch.cuda.current_stream().synchronize()
+        tm = host[:nb_full].numpy().view(dtype).reshape(n_full, channels, hf, maxw)
+        arrays = [tm[i] for i in range(n_full)]
+        if n_full < n:
+            rest = host[nb_full:].numpy().view(dtype).reshape(channels, row - n_full * hf, maxw)
+            arrays += _copy_tiles_out(rest, rows0[n_full:] - n_full * hf, heights[n_full:], widths[n_full:])
+        if order is not None:
+            back = [None] * n
+            for i, o in enumerate(order):
+                back[int(o)] = arrays[i]
+            arrays = back
+        return arrays, hdr_in
     host.copy_(out.reshape(-1).view(torch.uint8), non_blocking=True)
     if while_copying is not None:
-        while_copying(hdr)
+        while_copying(hdr_in)
     torch.cuda.current_stream().synchronize()
-    if tile_major:
-        tm = host.numpy().view(dtype).reshape(n, channels, int(heights[0]), maxw)
-        return [tm[i] for i in range(n)], hdr
     host_out = host.numpy().view(dtype).reshape(channels, row, maxw)
     if n == 1:
         arrays = [host_out]                      # one tile (get_tile_by_id): the result block IS the tile, whatever its band count
@@ -402,7 +429,7 @@ def decode_staged_tiles(stage, nbytes: int, starts: np.ndarray, sizes: np.ndarra
         arrays = [host_out[:, int(r0):int(r0 + h_)] for r0, h_ in zip(rows0, heights)]     # C-contiguous views, one owner
     else:
         arrays = _copy_tiles_out(host_out, rows0, heights, widths)
-    return arrays, hdr
+    return arrays, hdr_in
 
 
 def _raise_for_status(status):
