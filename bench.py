@@ -797,6 +797,24 @@ def container_check(args, eng, rank, world, dev, host_raster, r0, full_shape, ts
             ok = ok and tile.shape == src_np.shape and bool(np.array_equal(tile, src_np))
         res = {"ok": bool(ok), "bytes": size, "tiles_verified": picks, "write_wall_s": wall,
                "path": "distributed.encode_streaming_sharded -> write_sharded_container -> SpatialFLACStreamer.get_tile_by_id"}
+        if world == 1 and ok:
+            # the whole scene back through the public call (file in page cache -> pinned staging -> H2D -> fused decode -> D2H ->
+            # one array per tile): the read direction of the same container, wall clock of the second call
+            bb = (-1e12, -1e12, 1e12, 1e12)
+            got = s.get_tiles_by_bbox(*bb)
+            del got
+            t1 = time.perf_counter()
+            got = s.get_tiles_by_bbox(*bb)
+            dt = time.perf_counter() - t1
+            n_px = sum(int(a.size) for a, _ in got)
+            a_last, m_last = got[-1]
+            t = tiles_all[-1]
+            src = make_rows(args.workload, dev, int(t["row_off"]), int(t["row_off"] + t["h"]), args.scale_div)[:, :, int(t["col_off"]):int(t["col_off"] + t["w"])]
+            src_np = src.view(torch.int16).cpu().numpy().view(a_last.dtype) if src.dtype == torch.uint16 else src.cpu().numpy()
+            res["bbox_all"] = {"ok": bool(len(got) == len(tiles_all) and np.array_equal(a_last, src_np)), "ms_per_call": 1e3 * dt,
+                               "value": n_px / dt / 1e9, "unit": UNIT, "tiles": len(got)}
+            res["ok"] = bool(res["ok"] and res["bbox_all"]["ok"])
+            del got
     if world > 1:
         dist.barrier()
     if rank == 0:
