@@ -353,15 +353,10 @@ def decode_staged_tiles(stage, nbytes: int, starts: np.ndarray, sizes: np.ndarra
     # bands.  Tiles of the full size (all of them, or the interior of a scene whose edge tiles are ragged) are decoded FIRST:
     # their part of the planes is re-laid out to (tile, band, h, w) on the device and handed out as views of the result block;
     # only the ragged rest takes a strided host copy per tile (1.9 GB of host copies for a bbox query over an 8-band C3 scene).
-    full = (widths == widths.max()) & (heights == heights.max())
-    n_full = int(full.sum()) if (n > 1 and channels > 1) else 0
-    order = None
-    if 2 <= n_full < n:
-        order = np.argsort(~full, kind="stable")
+    order, n_full = full_tiles_first(widths, heights, channels)
+    if order is not None:
         hdr, offs64, size64 = hdr[order], np.ascontiguousarray(offs64[order]), np.ascontiguousarray(size64[order])
         widths, heights = widths[order], heights[order]
-    elif n_full < 2:
-        n_full = 0
     nsamp = widths * heights
     tiles = np.zeros(n, dtype=nat.TILE_DTYPE)
     rows0 = np.zeros(n, dtype=np.int64)
@@ -430,6 +425,24 @@ def decode_staged_tiles(stage, nbytes: int, starts: np.ndarray, sizes: np.ndarra
     else:
         arrays = _copy_tiles_out(host_out, rows0, heights, widths)
     return arrays, hdr_in
+
+
+def full_tiles_first(widths, heights, channels: int):
+    """Decode order of a batch of multi-band tiles: (order, n_full).  The n_full tiles of the full size (largest width AND
+    largest height of the batch) come first, in their original relative order, then the ragged ones; order is None when nothing
+    moves (every tile is full size, or they already lead).  n_full is 0 for single-band batches, single tiles and batches with
+    fewer than two full-size tiles: those keep the band-major result layout."""
+    widths, heights = np.asarray(widths), np.asarray(heights)
+    n = len(widths)
+    if n < 2 or channels < 2:
+        return None, 0
+    full = (widths == widths.max()) & (heights == heights.max())
+    n_full = int(full.sum())
+    if n_full < 2:
+        return None, 0
+    if n_full == n or bool(full[:n_full].all()):
+        return None, n_full
+    return np.argsort(~full, kind="stable"), n_full
 
 
 def _raise_for_status(status):

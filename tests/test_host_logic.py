@@ -376,3 +376,22 @@ def test_oversized_tile_is_rejected():
     engine._check_tile_sizes(np.array([1 << 20, (1 << 32) - 1], dtype=np.int64))
     with pytest.raises(ValueError, match="pixels"):
         engine._check_tile_sizes(np.array([70000 * 70000], dtype=np.int64))
+
+
+def test_full_tiles_first_ordering():
+    """Host side of the tile-major result layout (converter.decode_staged_tiles): full-size tiles of a multi-band batch are decoded
+    first so that their planes can be re-laid out on the device; the ragged rest keeps its relative order behind them."""
+    from flac_raster_b200.converter import full_tiles_first
+    # 3 x 4 grid of a 333 x 420 raster at tile 128: interior 128 x 128, last column 36 wide, last row 77 high
+    w = np.array([128, 128, 128, 36] * 3)
+    h = np.array([128] * 8 + [77] * 4)
+    order, nf = full_tiles_first(w, h, 3)
+    assert nf == 6 and list(order[:6]) == [0, 1, 2, 4, 5, 6] and list(order[6:]) == [3, 7, 8, 9, 10, 11]
+    assert sorted(order) == list(range(12))
+    assert full_tiles_first(w, h, 1) == (None, 0)                      # single band: views of the band-major block already
+    assert full_tiles_first(w[:1], h[:1], 3) == (None, 0)              # one tile: the block is the tile
+    assert full_tiles_first(np.array([64, 64, 64]), np.array([64, 64, 64]), 8) == (None, 3)          # all full: nothing moves
+    assert full_tiles_first(np.array([64, 64, 10]), np.array([64, 64, 64]), 8) == (None, 2)          # full ones already lead
+    assert full_tiles_first(np.array([64, 10, 20]), np.array([64, 64, 64]), 8) == (None, 0)          # a single full tile: not worth it
+    o, nf = full_tiles_first(np.array([10, 64, 64]), np.array([64, 64, 64]), 2)
+    assert nf == 2 and list(o) == [1, 2, 0]
