@@ -17,8 +17,10 @@ distributed.shard_range gives it (15-16 of the 121 tiles at N = 8), the per-tile
 all-gathered over NCCL (the one collective; its scan gives the container's byte offsets) and
 `value` = the scene's samples / the slowest rank's time.  After the timed regions the ranks write
 ONE container with distributed.write_sharded_container and rank 0 re-reads its index and decodes
-tiles of three different ranks through the public SpatialFLACStreamer as a check.  The old weak
-number (every rank codes a whole scene) is kept under "weak".
+tiles of three different ranks through the public SpatialFLACStreamer as a check (at N = 1 it also
+reads the whole scene back with get_tiles_by_bbox: "container_check.bbox_all").  The old weak
+number (every rank codes a whole scene) is kept under "weak".  "cpu_baseline.ffmpeg" holds the
+second labelled CPU row: FFmpeg libavcodec's FLAC encoder and decoder on one core.
 
 `e2e` is the same step through the public engine API with HOST (pinned) buffers: H2D of the
 raster and D2H of the frames inside the timed region.  "c5_bbox" is BASELINE.json configs[4]
