@@ -395,3 +395,44 @@ def test_full_tiles_first_ordering():
     assert full_tiles_first(np.array([64, 10, 20]), np.array([64, 64, 64]), 8) == (None, 0)          # a single full tile: not worth it
     o, nf = full_tiles_first(np.array([10, 64, 64]), np.array([64, 64, 64]), 2)
     assert nf == 2 and list(o) == [1, 2, 0]
+
+
+def test_ctypes_bindings_match_the_header_arity():
+    """Every entry point whose ctypes argtypes are declared in _native.py takes exactly as many parameters as its prototype in
+    include/flacraster_b200.h (a binding that drifts from the header would pass garbage on the stack without any error)."""
+    from flac_raster_b200 import _native as nat
+    hdr = (ROOT / "include" / "flacraster_b200.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(frb_[a-z0-9_]+)\s*\(", hdr):
+        name = m.group(1)
+        if name.endswith("_cb") or hdr[max(0, m.start() - 2):m.start()].endswith("(*"):
+            continue
+        depth, i, args, cur = 1, m.end(), [], ""
+        while depth and i < len(hdr):
+            ch = hdr[i]
+            if ch == "(":
+                depth += 1
+            elif ch == ")":
+                depth -= 1
+                if depth == 0:
+                    break
+            if ch == "," and depth == 1:
+                args.append(cur); cur = ""
+            else:
+                cur += ch
+            i += 1
+        args.append(cur)
+        args = [a.strip() for a in args if a.strip() and a.strip() != "void"]
+        if hdr[i + 1:i + 3].lstrip().startswith(";"):
+            protos[name] = len(args)
+    L = nat.lib()
+    checked = 0
+    for name, n_params in protos.items():
+        fn = getattr(L, name, None)
+        at = getattr(fn, "argtypes", None)
+        if at is None:
+            continue
+        assert len(at) == n_params, (name, len(at), n_params)
+        checked += 1
+    assert checked >= 25, checked
