@@ -1101,20 +1101,23 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
     // byte by byte by ONE lane (~50 instructions per byte, up to 30 bytes per frame) while the other 31 waited -- for 6 KB
     // frames (C5) about a third of the kernel.  Here the warp produces them together, one byte per lane, and assembles the
     // chunk's four words with warp-wide ORs; every lane gets the words, lane 0 (head) / lane 31 (tail) feed them to the CRC.
+    // (CTA-per-frame groups do the same inside the warp that owns the chunk -- warp 0 for the head, the last warp for the tail:
+    // there the single lane was the straggler every other thread waited for at the frame's closing barrier.)
+    const int lane = tid & 31;
     auto coop_partial = [&](int32_t b_first /* frame byte of the chunk's byte 0 */, uint32_t nbytes, uint8_t *gdst, uint32_t (&w)[4]) {
-        const bool valid = (uint32_t)tid < nbytes && b_first + tid >= 0;
+        const bool valid = (uint32_t)lane < nbytes && b_first + lane >= 0;      // called by all 32 lanes of ONE warp
         uint32_t contrib = 0;
         if (valid) {
-            const uint32_t byte = emit_gather32(8u * (uint32_t)(b_first + tid), S, channels, hdr_bits, end_bits, slots_f, slot_words) >> 24;
-            gdst[tid] = (uint8_t)byte;
-            contrib = byte << (24 - 8 * (tid & 3));
+            const uint32_t byte = emit_gather32(8u * (uint32_t)(b_first + lane), S, channels, hdr_bits, end_bits, slots_f, slot_words) >> 24;
+            gdst[lane] = (uint8_t)byte;
+            contrib = byte << (24 - 8 * (lane & 3));
         }
 #pragma unroll
-        for (int q = 0; q < 4; q++) w[q] = __reduce_or_sync(0xFFFFFFFFu, (tid >> 2) == q ? contrib : 0u);
+        for (int q = 0; q < 4; q++) w[q] = __reduce_or_sync(0xFFFFFFFFu, (lane >> 2) == q ? contrib : 0u);
     };
     uint32_t w_head[4] = {0, 0, 0, 0};
-    const bool head_pre = TPF == 32 && a > 0 && nfull >= 1;      // uniform over the warp
-    if (head_pre) coop_partial(-(int32_t)a, 16, g0, w_head);
+    const bool head_pre = a > 0 && nfull >= 1;                   // uniform over the group
+    if (head_pre && (tid >> 5) == 0) coop_partial(-(int32_t)a, 16, g0, w_head);
     // produce chunk c: returns its four big-endian words (head-masked), stores its bytes
     auto do_chunk = [&](uint32_t c, uint32_t (&w)[4], uint32_t nbytes /* valid bytes from the chunk start, 16 = full */) {
         const int32_t b0 = (int32_t)(16 * c) - (int32_t)a;    // frame byte of the chunk's first byte (negative in the head chunk)
@@ -1182,28 +1185,17 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
         do_chunk(rows * TPF + tid, w, 16);
         v ^= gf16_mul(crc16_words4(0, w, T.s4), T.xp[16 * (rem - 1 - tid) + tl]);
     }
-    if (TPF == 32) {
-        if (tl) {                                            // uniform over the warp
-            uint32_t w[4];
-            coop_partial((int32_t)(16 * nfull) - (int32_t)a, tl, g0 + 16 * (size_t)nfull, w);
-            if (tid == TPF - 1) {
-                uint32_t c = 0;
-                for (uint32_t q = 0; q < tl; q++) {
-                    const uint32_t byte = (w[q >> 2] >> (24 - 8 * (q & 3))) & 0xFF;
-                    c = ((c << 8) & 0xFFFFu) ^ T.s4[((c >> 8) ^ byte) & 0xFF];
-                }
-                v ^= c;
-            }
-        }
-    } else if (tid == TPF - 1 && tl) {
+    if (tl && (tid >> 5) == ((TPF - 1) >> 5)) {              // the group's last warp, all 32 lanes; tl is uniform over the group
         uint32_t w[4];
-        do_chunk(nfull, w, tl);
-        uint32_t c = 0;
-        for (uint32_t q = 0; q < tl; q++) {
-            const uint32_t byte = (w[q >> 2] >> (24 - 8 * (q & 3))) & 0xFF;
-            c = ((c << 8) & 0xFFFFu) ^ T.s4[((c >> 8) ^ byte) & 0xFF];
+        coop_partial((int32_t)(16 * nfull) - (int32_t)a, tl, g0 + 16 * (size_t)nfull, w);
+        if (tid == TPF - 1) {
+            uint32_t c = 0;
+            for (uint32_t q = 0; q < tl; q++) {
+                const uint32_t byte = (w[q >> 2] >> (24 - 8 * (q & 3))) & 0xFF;
+                c = ((c << 8) & 0xFFFFu) ^ T.s4[((c >> 8) ^ byte) & 0xFF];
+            }
+            v ^= c;
         }
-        v ^= c;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(0xFFFFFFFFu, v, o);
