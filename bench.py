@@ -13,7 +13,7 @@ CRC-16 -> denormalise) is timed the same way and reported under "decode".
 
 N > 1 is STRONG scaling of that ONE scene (north_star: "work is sharded across the GPUs of one box
 by tile"): one process per GPU, rank r holds and codes the contiguous row-major block of tiles
-distributed.shard_range gives it (15-16 of the 121 tiles at N = 8), the per-tile sizes are
+distributed.tile_shards gives it (balanced by pixel count: 15-17 of the 121 tiles at N = 8), the per-tile sizes are
 all-gathered over NCCL (the one collective; its scan gives the container's byte offsets) and
 `value` = the scene's samples / the slowest rank's time.  After the timed regions the ranks write
 ONE container with distributed.write_sharded_container and rank 0 re-reads its index and decodes
@@ -402,7 +402,7 @@ def run_ours(args, rank, world, local):
 
     from flac_raster_b200 import _native as nat
     from flac_raster_b200.distributed import (SizeExchange, allgather_tile_sizes, bind_to_gpu_numa_node, exclusive_scan, init_from_env,
-                                              shard_plan, shard_range)
+                                              shard_plan, tile_shards)
     from flac_raster_b200.engine import Engine, tile_grid
 
     desc, level, tile_size, bands = WORKLOADS[args.workload]
@@ -444,7 +444,8 @@ def run_ours(args, rank, world, local):
 
     # the one collective of the path: every tile's frame bytes -> global byte offsets of the container (cli.py:615-621); it is
     # enqueued on the stream inside the step and its result comes back with the step's own size download
-    xchg = SizeExchange(len(tiles_all), rank, world, dev) if world > 1 and shardable else None
+    shards = tile_shards(tiles_all, world)
+    xchg = SizeExchange(len(tiles_all), rank, world, dev, ranges=shards) if world > 1 and shardable else None
 
     def encode_step():
         enc = eng.encode_tiles(raster, tiles, level, size_exchange=xchg)
@@ -554,7 +555,7 @@ def run_ours(args, rank, world, local):
         # size all-gather that fixes the container offsets
         e = eng.encode_tiles_host(host_raster, tiles, level, host_out=host_out)
         if world > 1 and shardable:
-            allgather_tile_sizes(e.sizes, len(tiles_all), rank, world, device=dev)
+            allgather_tile_sizes(e.sizes, len(tiles_all), rank, world, device=dev, ranges=shards)
         return int(e.payload.numel())
 
     for _ in range(min(args.warmup, 2)):
@@ -772,7 +773,7 @@ def container_check(args, eng, rank, world, dev, host_raster, r0, full_shape, ts
     with the public SpatialFLACStreamer, decodes the first tile of three different ranks and compares them with the source."""
     import torch
     import torch.distributed as dist
-    from flac_raster_b200.distributed import encode_streaming_sharded, shard_range
+    from flac_raster_b200.distributed import encode_streaming_sharded, tile_shards
     from flac_raster_b200.spatial_encoder import SpatialFLACStreamer
 
     d = _scratch_dir(rank, world, dev)
@@ -788,7 +789,7 @@ def container_check(args, eng, rank, world, dev, host_raster, r0, full_shape, ts
         size = os.path.getsize(path)
         s = SpatialFLACStreamer(path)
         want_size = s.header_size + sum(f["byte_size"] for f in index["frames"])
-        picks = sorted({shard_range(len(tiles_all), r, world)[0] for r in (0, world // 2, world - 1)} | {len(tiles_all) - 1})
+        picks = sorted({tile_shards(tiles_all, world)[r][0] for r in (0, world // 2, world - 1)} | {len(tiles_all) - 1})
         ok = size == want_size and len(s.spatial_index.frames) == len(tiles_all)
         for tid in picks:
             tile, meta = s.get_tile_by_id(tid)
@@ -830,7 +831,7 @@ def c5_bbox_sweep(eng, rank, world, dev, barrier, reps: int = 3):
     import torch
     import torch.distributed as dist
     from flac_raster_b200 import synth
-    from flac_raster_b200.distributed import encode_streaming_sharded, shard_plan, shard_range
+    from flac_raster_b200.distributed import encode_streaming_sharded, shard_plan
     from flac_raster_b200.spatial_encoder import SpatialFLACStreamer
 
     n_tiles, T = 4096, 512

@@ -690,7 +690,7 @@ class SpatialFLACStreamer:
     def get_tiles_by_bbox(self, xmin, ymin, xmax, ymax, shard=None):
         """README.md:202 -> list of (tile_data, metadata) for ALL intersecting tiles (one batched decode).
 
-        Multi-GPU (one process per GPU): the intersecting tiles are split over the ranks in contiguous blocks and each
+        Multi-GPU (one process per GPU): the intersecting tiles are split over the ranks in contiguous blocks (balanced by pixel count) and each
         rank fetches and decodes only its own block -- no collective; the call returns this rank's tiles.
         `shard`: (rank, world) to split explicitly, None = the initialised torch.distributed group (or no split),
         False = never split."""
@@ -699,8 +699,8 @@ class SpatialFLACStreamer:
             from .distributed import current_rank_world
             shard = current_rank_world()
         if shard and shard[1] > 1:
-            from .distributed import shard_range
-            a, b = shard_range(len(frames), int(shard[0]), int(shard[1]))
+            from .distributed import shard_ranges_weighted
+            a, b = shard_ranges_weighted([f.window.width * f.window.height for f in frames], int(shard[1]))[int(shard[0])]
             frames = frames[a:b]
         if not frames:
             return []

@@ -19,10 +19,13 @@ def _free_port():
 def _worker(rank, world, port, path, n_tiles):
     import torch.distributed as dist
     from flac_raster_b200 import _native as nat
-    from flac_raster_b200.distributed import (allgather_tile_sizes, build_index, shard_range, write_sharded_container)
+    from flac_raster_b200.distributed import (allgather_tile_sizes, build_index, shard_ranges_weighted, write_sharded_container)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    a, b = shard_range(n_tiles, rank, world)
+    # unequal tiles: the pixel-count split gives the ranks different tile COUNTS (7 + 4 here), as the ragged edge of a scene does
+    ranges = shard_ranges_weighted([1, 1, 1, 1, 1, 1, 3, 3, 3, 3, 1], world)
+    assert ranges == [(0, 7), (7, 11)]
+    a, b = ranges[rank]
     # fake per-tile files: header of 10 bytes + payload of (7 + tile id) bytes filled with the tile id
     headers = [bytes([0xA0 + (t % 16)]) * 10 for t in range(a, b)]
     psizes = np.array([7 + t for t in range(a, b)], dtype=np.int64)
@@ -30,12 +33,12 @@ def _worker(rank, world, port, path, n_tiles):
     np.cumsum(psizes[:-1], out=poffs[1:])
     payload = np.concatenate([np.full(7 + t, t, dtype=np.uint8) for t in range(a, b)])
     local_file_sizes = psizes + 10
-    sizes = allgather_tile_sizes(local_file_sizes, n_tiles, rank, world)
+    sizes = allgather_tile_sizes(local_file_sizes, n_tiles, rank, world, ranges=ranges)
     assert list(sizes) == [17 + t for t in range(n_tiles)]
     # the same exchange as the encode step runs it: started asynchronously behind the analysis, joined before the download
     import torch
     from flac_raster_b200.distributed import SizeExchange
-    x = SizeExchange(n_tiles, rank, world, "cpu")
+    x = SizeExchange(n_tiles, rank, world, "cpu", ranges=ranges)
     recv = torch.zeros(x.recv_count, dtype=torch.int64)
     x.start(torch.from_numpy(local_file_sizes.copy()), recv)
     x.wait()

@@ -164,6 +164,33 @@ def test_shard_range_partitions():
     assert list(exclusive_scan(np.array([5, 7, 9]))) == [0, 5, 12]
 
 
+def test_weighted_shards_balance_pixel_counts():
+    """distributed.shard_ranges_weighted / tile_shards: contiguous blocks, every item once, the heaviest rank as light as a
+    contiguous split allows (checked against a brute-force search on small cases), equal weights = equal counts."""
+    import itertools
+    from flac_raster_b200.distributed import shard_range, shard_ranges_weighted, tile_shards
+    from flac_raster_b200.engine import tile_grid
+    rng = np.random.default_rng(5)
+    for n, world in ((1, 1), (1, 4), (3, 8), (7, 3), (9, 4), (10, 2), (12, 5)):
+        w = rng.integers(1, 50, n).tolist()
+        spans = shard_ranges_weighted(w, world)
+        assert len(spans) == world and spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:])) and all(b >= a for a, b in spans)
+        assert sum(1 for a, b in spans if b > a) == min(n, world)                 # no idle rank while items are left
+        k = min(n, world)
+        best = min(max(sum(w[a:b]) for a, b in zip((0,) + cuts, cuts + (n,))) for cuts in itertools.combinations(range(1, n), k - 1))
+        assert max(sum(w[a:b]) for a, b in spans) == best
+    for n, world in ((4096, 8), (121, 8), (16, 4)):
+        assert max(b - a for a, b in shard_ranges_weighted([262144] * n, world)) == -(-n // world)
+    # C3: 121 tiles with a 740-pixel last column and row; N = 8: 2.4 % above the mean instead of 9.4 % by tile count
+    tiles = tile_grid(10980, 10980, 1024)
+    px = tiles["h"].astype(np.int64) * tiles["w"]
+    for world, bound in ((2, 1.003), (4, 1.015), (8, 1.025)):
+        spans = tile_shards(tiles, world)
+        assert max(px[a:b].sum() for a, b in spans) <= bound * px.sum() / world
+        assert max(px[a:b].sum() for a, b in (shard_range(121, r, world) for r in range(world))) > max(px[a:b].sum() for a, b in spans)
+
+
 def test_pyflac_shim_signatures():
     """Constructor/method surface of pyflac 3.0.0 that the reference uses."""
     import inspect
@@ -265,6 +292,8 @@ def test_shard_plan_covers_every_tile_once():
                 assert (r0, r1) == (0, 0)
         assert seen == list(range(121))
     assert [shard_range(121, r, 8) for r in (0, 7)] == [(0, 16), (106, 121)]
+    from flac_raster_b200.distributed import tile_shards
+    assert [shard_plan(10980, 10980, 1024, r, 8)[1] for r in range(8)] == tile_shards(shard_plan(10980, 10980, 1024, 0, 8)[0], 8)
 
 
 def test_c_tile_header_parser_equals_python_parser():
