@@ -87,7 +87,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 _lib = None
 
 _EXPORTS = [
-    "frb_version", "frb_error_string", "frb_last_cuda_error", "frb_device_count", "frb_launch_count",
+    "frb_version", "frb_error_string", "frb_last_cuda_error", "frb_device_count", "frb_launch_count", "frb_selftest_crc16",
     "frb_profile_enable", "frb_profile_last_ms", "frb_small_upload", "frb_small_download",
     "frb_minmax_tiles", "frb_normalize_tiles", "frb_normalize_tiles_i16", "frb_denormalize_tiles", "frb_sample_map_workspace_size",
     "frb_minmax_flat", "frb_normalize_flat", "frb_denormalize_flat", "frb_selftest_division",
@@ -176,6 +176,7 @@ def lib():
     L.frb_last_cuda_error.restype = C.c_char_p
     L.frb_device_count.argtypes = [C.POINTER(i32)]
     L.frb_launch_count.restype = u64
+    L.frb_selftest_crc16.argtypes = [vp, u64, u64, i32, C.POINTER(u32)]
     L.frb_profile_enable.argtypes = [i32]
     L.frb_profile_last_ms.argtypes = [i32, C.POINTER(C.c_float)]
     L.frb_minmax_tiles.argtypes = [vp, i32, u32, u32, u32, vp, u32, vp, vp]

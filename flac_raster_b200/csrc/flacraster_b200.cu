@@ -17,6 +17,26 @@ static int ensure_tables_impl();
 #include "frb_hostparse.cuh"
 
 namespace frb {
+// The CRC-16 tables, built once on the host (no CUDA call: the host self-test uses them too).
+static const CrcTables &host_crc_tables() {
+    static CrcTables T;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        uint16_t t16[256];
+        for (int i = 0; i < 256; i++) {
+            uint16_t d = (uint16_t)(i << 8);
+            for (int b = 0; b < 8; b++) d = (d & 0x8000) ? (uint16_t)((d << 1) ^ 0x8005) : (uint16_t)(d << 1);
+            t16[i] = d;
+        }
+        for (int b = 0; b < 256; b++) {
+            uint32_t c = t16[b];                                  // byte b followed by 0 zero bytes
+            T.s4[b] = (uint16_t)c;
+            for (int k = 1; k < 4; k++) { c = ((c << 8) & 0xFFFFu) ^ t16[c >> 8]; T.s4[k * 256 + b] = (uint16_t)c; }
+        }
+        for (int i = 0; i < 2048; i++) T.xp[i] = (uint16_t)gf16_xpow8((uint64_t)i);
+    });
+    return T;
+}
 // CRC tables are uploaded once per device.
 static int ensure_tables_impl() {
     static std::mutex mu;
@@ -36,26 +56,8 @@ static int ensure_tables_impl() {
     }
     FRB_CUDA(cudaMemcpyToSymbol(c_crc8, t8, sizeof t8));
     FRB_CUDA(cudaMemcpyToSymbol(c_crc16, t16, sizeof t16));
-    {
-        static CrcTables T;
-        for (int b = 0; b < 256; b++) {
-            uint32_t c = t16[b];                                  // byte b followed by 0 zero bytes
-            T.s4[b] = (uint16_t)c;
-            for (int k = 1; k < 4; k++) { c = ((c << 8) & 0xFFFFu) ^ t16[c >> 8]; T.s4[k * 256 + b] = (uint16_t)c; }
-        }
-        const uint32_t K = gf16_xpow8(496);
-        for (int b = 0; b < 256; b++) {
-            T.k496[b] = (uint16_t)gf16_mul((uint32_t)b << 8, K);
-            T.k496[256 + b] = (uint16_t)gf16_mul((uint32_t)b, K);
-        }
-        const uint32_t K2 = gf16_xpow8(2032);
-        for (int b = 0; b < 256; b++) {
-            T.k2032[b] = (uint16_t)gf16_mul((uint32_t)b << 8, K2);
-            T.k2032[256 + b] = (uint16_t)gf16_mul((uint32_t)b, K2);
-        }
-        for (int i = 0; i < 2048; i++) T.xp[i] = (uint16_t)gf16_xpow8((uint64_t)i);
-        FRB_CUDA(cudaMemcpyToSymbol(d_crct, &T, sizeof T));
-    }
+    const CrcTables &T = host_crc_tables();
+    FRB_CUDA(cudaMemcpyToSymbol(d_crct, &T, sizeof T));
     if (dev >= 0 && dev < 64) done[dev] = true;
     return FRB_OK;
 }
@@ -80,6 +82,18 @@ extern "C" int frb_device_count(int *count) {
     if (!count) return FRB_ERR_INVALID_ARG;
     cudaError_t e = cudaGetDeviceCount(count);
     if (e != cudaSuccess) { *count = 0; cudaGetLastError(); return FRB_ERR_NO_DEVICE; }
+    return FRB_OK;
+}
+// Host self-test of the table-free CRC-16 (frb_crc16.cuh): runs the per-lane code of warp_crc16 for lanes 0..31 on the host, for
+// bytes [a, e) of `bytes` (readable up to the next 16-byte boundary after e, base 16-byte aligned).  No GPU needed.
+extern "C" int frb_selftest_crc16(const uint8_t *bytes, uint64_t a, uint64_t e, int group, uint32_t *crc) {
+    if (!bytes || !crc || e < a || (reinterpret_cast<uintptr_t>(bytes) & 15u) || e - a >= (1ull << 32) || (group != 32 && group != 128))
+        return FRB_ERR_INVALID_ARG;
+    const frb::CrcTables &T = frb::host_crc_tables();
+    uint32_t v = 0;
+    for (int lane = 0; lane < group; lane++)
+        v ^= group == 32 ? frb::lane_crc16<30>(bytes, a, e, T.s4, T.xp, lane) : frb::lane_crc16<120>(bytes, a, e, T.s4, T.xp, lane);
+    *crc = v;
     return FRB_OK;
 }
 extern "C" uint64_t frb_launch_count(void) { return frb::g_launches.load(); }

@@ -140,7 +140,13 @@ inline void prof_end(int which, cudaStream_t s) {
 }
 
 // ---- big-endian / bit helpers -------------------------------------------
-__device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+__host__ __device__ __forceinline__ uint32_t bswap32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return __byte_perm(v, 0, 0x0123);
+#else
+    return (v >> 24) | ((v >> 8) & 0xFF00u) | ((v << 8) & 0xFF0000u) | (v << 24);
+#endif
+}
 
 // CRC tables live in constant memory (CRC-8 poly 0x07, CRC-16 poly 0x8005; RFC 9639 9.1.8 / 9.3)
 __constant__ uint8_t  c_crc8[256];

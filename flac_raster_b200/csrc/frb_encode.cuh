@@ -1089,9 +1089,11 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
     uint8_t *g0 = dst - a;
     const uint32_t span = a + payload;
     const uint32_t nfull = span >> 4, tl = span & 15;
-    const uint32_t rows = nfull / TPF, rem = nfull % TPF;
+    // rows of ROW 16-byte chunks, one chunk per thread and row: 30 of a warp's 32 lanes / 120 of a CTA's 128 threads, because x^(128 * ROW)
+    // is then a two-term multiplier and the CRC-16 needs no table in the loop (CrcFold, frb_crc16.cuh)
+    constexpr int ROW = TPF == 32 ? 30 : 120;
+    const uint32_t rows = nfull / (uint32_t)ROW, rem = nfull - rows * (uint32_t)ROW;
     const CrcTables &T = SS.T;
-    const uint16_t *kskip = TPF == kEmitThreads ? T.k2032 : T.k496;      // x^(8 * 16 * (TPF - 1)): skip the other threads' chunks
 
     // A thread visits its chunks in increasing order, so the subframe that holds a chunk only moves forward: the
     // segment search resumes where the previous chunk left it (it restarted from 0 for every chunk: 19 % of the kernel's
@@ -1172,18 +1174,22 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
         }
     };
 
-    uint32_t acc = 0;
-    for (uint32_t m = 0; m < rows; m++) {
-        uint32_t w[4];
-        do_chunk(m * TPF + tid, w, 16);
-        acc = (uint32_t)kskip[acc >> 8] ^ kskip[256 + (acc & 0xFF)];
-        acc = crc16_words4(acc, w, T.s4);
-    }
-    uint32_t v = gf16_mul(gf16_mul(acc, T.xp[16 * (TPF - 1 - tid)]), T.xp[16 * rem + tl]);
-    if ((uint32_t)tid < rem) {
-        uint32_t w[4];
-        do_chunk(rows * TPF + tid, w, 16);
-        v ^= gf16_mul(crc16_words4(0, w, T.s4), T.xp[16 * (rem - 1 - tid) + tl]);
+    uint32_t v = 0;
+    if (tid < ROW) {
+        CrcFold F;
+        crcfold_init(F);
+        for (uint32_t m = 0; m < rows; m++) {
+            uint32_t w[4];
+            do_chunk(m * ROW + tid, w, 16);
+            crcfold_step<ROW>(F, w);
+        }
+        // x^16 (message -> CRC register), the chunks of the last full row after this thread's, then everything after the full rows
+        if (rows) v = gf16_mul(gf16_mul(crcfold_finish(F), T.xp[16 * (ROW - 1 - tid) + 2]), T.xp[16 * rem + tl]);
+        if ((uint32_t)tid < rem) {
+            uint32_t w[4];
+            do_chunk(rows * ROW + tid, w, 16);
+            v ^= gf16_mul(crc16_words4(0, w, T.s4), T.xp[16 * (rem - 1 - tid) + tl]);
+        }
     }
     if (tl && (tid >> 5) == ((TPF - 1) >> 5)) {              // the group's last warp, all 32 lanes; tl is uniform over the group
         uint32_t w[4];
@@ -1511,11 +1517,11 @@ extern "C" int frb_encode_emit(const frb_encode_params *p, void *d_workspace, si
     }
     prof_begin(2, s);
     {
-        // a warp per frame when frames are small (their raw size bounds the coded size), the whole CTA otherwise
+        // a warp per frame; the whole CTA per frame only on request (FRB_EMIT_TPF=128, A/B runs): with the table-free CRC the warp form
+        // is the faster one for large frames as well (C3's 48 KB frames: 0.83 against 1.02 ms; C5's 6 KB frames: 1.11 against 1.97 ms)
         static int tpf_cfg = -1;
         if (tpf_cfg < 0) { const char *e = getenv("FRB_EMIT_TPF"); tpf_cfg = e ? atoi(e) : 0; }
-        const uint64_t raw_frame_bytes = (uint64_t)p->channels * p->blocksize * p->bps / 8;
-        const bool warp_per_frame = tpf_cfg == 32 || (tpf_cfg != 128 && raw_frame_bytes <= 16384);
+        const bool warp_per_frame = tpf_cfg != 128;
         const uint32_t vch = enc_mid_side(p) ? 4u : p->channels;
         const uint8_t *sel = enc_mid_side(p) ? w.frame_sel : nullptr;
         const uint32_t sw = slot_words_for(p->blocksize, enc_slot_bps(p));

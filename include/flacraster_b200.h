@@ -62,6 +62,11 @@ const char *frb_last_cuda_error(void);      /* text of the last CUDA failure on 
 int frb_device_count(int *count);
 /* number of kernel launches issued by this library since load (bench gpu_launches) */
 uint64_t frb_launch_count(void);
+/* Host self-test (no GPU): CRC-16 (poly 0x8005, init 0; RFC 9639 9.3, the frame footer libFLAC writes and checks) of bytes
+ * [a, e) of `bytes`, computed by the SAME per-lane code the kernels run (table-free fold form, frb_crc16.cuh), the lanes of a
+ * thread group one after the other.  group: 32 (a warp per frame, rows of 30 chunks) or 128 (rows of 120 chunks).  `bytes`
+ * 16-byte aligned and readable up to the 16-byte boundary after e. */
+int frb_selftest_crc16(const uint8_t *bytes, uint64_t a, uint64_t e, int group, uint32_t *crc);
 
 /* Optional per-kernel timing: when enabled the library brackets its dominant kernels with
  * cudaEvents on the caller's stream.  which: 0 k_enc_code (Rice search + packing, the dominant

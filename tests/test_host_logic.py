@@ -465,3 +465,62 @@ def test_ctypes_bindings_match_the_header_arity():
         assert len(at) == n_params, (name, len(at), n_params)
         checked += 1
     assert checked >= 25, checked
+
+
+def test_table_free_crc16_equals_bitwise_crc(oracle):
+    """frb_selftest_crc16 runs the kernels' per-lane CRC-16 code (rows of 30 chunks folded with x^3840 = x^256 + 1 modulo the
+    degree-15 factor of the polynomial, parity for the factor x + 1, CRT at the end; frb_crc16.cuh) on the host.  Checked against
+    a bit-by-bit CRC-16/0x8005 and against the footer libFLAC wrote into the reference golden's frames, for every alignment of
+    the start, lengths around the row size (480 bytes) and its multiples, and long ranges."""
+    import ctypes as C
+    from flac_raster_b200 import _native as nat
+    L = nat.lib()
+
+    def crc_ref(bs):
+        c = 0
+        for b in bs:
+            c ^= b << 8
+            for _ in range(8):
+                c = ((c << 1) ^ 0x8005) & 0xFFFF if c & 0x8000 else (c << 1) & 0xFFFF
+        return c
+
+    rng = np.random.default_rng(11)
+    raw = np.zeros(70000 + 64, dtype=np.uint8)
+    base = (-raw.ctypes.data) % 16
+    buf = raw[base:base + 70000 + 32]
+    buf[:] = rng.integers(0, 256, buf.size, dtype=np.uint8)
+
+    def crc_lib(a, e):
+        out32, out128 = C.c_uint32(0), C.c_uint32(0)
+        assert L.frb_selftest_crc16(buf.ctypes.data, a, e, 32, C.byref(out32)) == 0
+        assert L.frb_selftest_crc16(buf.ctypes.data, a, e, 128, C.byref(out128)) == 0
+        assert out32.value == out128.value, (a, e, out32.value, out128.value)
+        return out32.value
+
+    lengths = sorted(set(list(range(0, 40)) + [463, 464, 465, 479, 480, 481, 495, 496, 497, 511, 512, 513, 959, 960, 961, 976,
+                                                  1440, 1919, 1920, 1921, 1936, 3839, 3840, 3841, 5760, 14400, 14401, 48211, 65535]))
+    for a in list(range(0, 17)) + [31, 100, 1000]:
+        for n in lengths:
+            assert crc_lib(a, a + n) == crc_ref(buf[a:a + n].tobytes()), (a, n)
+    # all-zero and all-ones payloads (parity / CRT corner cases)
+    for fill in (0x00, 0xFF, 0x80, 0x01):
+        buf[:20000] = fill
+        for a, n in ((0, 480), (3, 481), (0, 14400), (5, 19000)):
+            assert crc_lib(a, a + n) == crc_ref(buf[a:a + n].tobytes()), (fill, a, n)
+    # libFLAC's own frames: the footers of the reference golden (frames found by walking 0xFFF8 candidates with the oracle's CRC)
+    from flac_raster_b200 import flacfmt
+    flac_oracle = oracle
+    blob = (GOLDEN / "sample_rgb.flac").read_bytes()
+    p0 = flacfmt.parse_header(blob).first_frame_offset
+    fr = np.frombuffer(blob, dtype=np.uint8)
+    frames = 0
+    while p0 < len(blob):
+        ends = [m.start() for m in re.finditer(b"\xff\xf8", blob[p0 + 2:])]
+        ends = [p0 + 2 + q for q in ends] + [len(blob)]
+        p1 = next(q for q in ends if flac_oracle.crc16(blob[p0:q - 2]) == ((blob[q - 2] << 8) | blob[q - 1]))
+        for a in (0, 7):
+            buf[a:a + p1 - p0] = fr[p0:p1]
+            assert crc_lib(a, a + p1 - p0 - 2) == ((blob[p1 - 2] << 8) | blob[p1 - 1])
+        frames += 1
+        p0 = p1
+    assert frames == 16
