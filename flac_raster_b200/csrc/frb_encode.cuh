@@ -973,6 +973,13 @@ constexpr int kEmitThreads = 128;
 #ifndef FRB_EMIT_VLOAD
 #define FRB_EMIT_VLOAD 1
 #endif
+// rows ahead whose slot words a thread asks for while it works on the current chunk (0 = off); see do_chunk
+#ifndef FRB_EMIT_PF_L1
+#define FRB_EMIT_PF_L1 1
+#endif
+#ifndef FRB_EMIT_PF_L2
+#define FRB_EMIT_PF_L2 0
+#endif
 
 struct EmitGroup {                           // state of the frame a thread group (a CTA or a warp) is assembling
     uint32_t hdr[6];
@@ -1144,6 +1151,18 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
                 const uint32_t k = (uint32_t)((reinterpret_cast<uintptr_t>(sl) >> 2) & 3u);
                 const uint4 *al = reinterpret_cast<const uint4 *>(sl - k);
                 const uint4 a4 = __ldg(al), b4 = __ldg(al + 1);
+                // The loop is one dependent chain per chunk (segment lookup -> two loads from DRAM -> funnel shifts -> store -> CRC
+                // fold) and a thread has one chunk in flight: ask for the words of the chunk it will need N rows on while this one is
+                // on its way.  Same subframe only, so the address is inside this frame's slot.  Same-box A/B (tools/enc_kernels_ab.py): C3
+                // 0.836 -> 0.703 ms, C5 1.111 -> 0.991 ms with one row ahead into L1; two rows ahead or L2 prefetches measure the same or worse.
+#if FRB_EMIT_PF_L1
+                if (P + 128u * ROW * FRB_EMIT_PF_L1 + 128 <= S.seg_start[ch + 1])
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(al + ROW * FRB_EMIT_PF_L1 + 1));
+#endif
+#if FRB_EMIT_PF_L2
+                if (P + 128u * ROW * FRB_EMIT_PF_L2 + 128 <= S.seg_start[ch + 1])
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(al + ROW * FRB_EMIT_PF_L2 + 1));
+#endif
                 uint32_t v0, v1, v2, v3, v4;
                 switch (k) {
                     case 0: v0 = a4.x; v1 = a4.y; v2 = a4.z; v3 = a4.w; v4 = b4.x; break;
