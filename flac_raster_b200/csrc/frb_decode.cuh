@@ -331,22 +331,21 @@ static int decode_batch_impl(const frb_decode_params *p, const frb_decode_stream
                                                                             w.frame_cand + total_frames + 1, w.frame_pos);
         FRB_LAUNCH_CHECK("k_sync_resolve");
     }
-    // CRC-16 only needs the frame positions: it runs on a side stream next to the skim pass (a latency-bound kernel
-    // that leaves most issue slots idle) and joins the caller's stream at the end.
+    // CRC-16 only needs the frame positions: it runs on a side stream and joins the caller's stream at the end.  It is launched
+    // AFTER the decode kernel: CTAs of the earlier launch are placed first, so the CRC's CTAs fill the SMs only as the decode grid
+    // drains -- a thread per subframe leaves a tail of ~0.4 ms in which most decode threads are done and the last ones run at the
+    // speed of their dependent chains.  Launched first (as it was), the CRC's persistent CTAs took most of every SM's registers
+    // and the decode CTAs queued behind them.  FRB_CRC_FIRST=1 restores the old order (A/B runs).
     static cudaStream_t side_of[64] = {nullptr};
     static cudaEvent_t fork_of[64] = {nullptr}, join_of[64] = {nullptr};
+    static int crc_first = -1;
+    if (crc_first < 0) { const char *e = getenv("FRB_CRC_FIRST"); crc_first = e ? atoi(e) : 0; }
     int dev = 0;
     FRB_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return FRB_ERR_UNSUPPORTED;
     cudaStream_t &side = side_of[dev];
     cudaEvent_t &ev_fork = fork_of[dev], &ev_join = join_of[dev];
-    if (p->verify_crc16 & 1u) {
-        if (!side) {
-            FRB_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
-            FRB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-            FRB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-        }
-        FRB_CUDA(cudaEventRecord(ev_fork, s));
+    auto launch_crc = [&]() -> int {
         FRB_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
         const uint64_t threads = total_frames * 32;
         uint32_t crc_grid = (uint32_t)((threads + 255) / 256);
@@ -355,6 +354,16 @@ static int decode_batch_impl(const frb_decode_params *p, const frb_decode_stream
                                                   (uint32_t)total_frames, w.frame_pos, d_status);
         FRB_LAUNCH_CHECK("k_crc16_frames");
         FRB_CUDA(cudaEventRecord(ev_join, side));
+        return FRB_OK;
+    };
+    if (p->verify_crc16 & 1u) {
+        if (!side) {
+            FRB_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+            FRB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+            FRB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        }
+        FRB_CUDA(cudaEventRecord(ev_fork, s));               // frame positions are ready here
+        if (crc_first) FRB_TRY(launch_crc());
     }
     {
         uint32_t *sub_bitoff = nullptr;
@@ -399,6 +408,7 @@ static int decode_batch_impl(const frb_decode_params *p, const frb_decode_stream
         prof_end(1, s);
         FRB_LAUNCH_CHECK("k_decode_subframes");
     }
+    if ((p->verify_crc16 & 1u) && !crc_first) FRB_TRY(launch_crc());
     if (p->verify_crc16 & 1u) FRB_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
     if (p->channels == 2 && sink.dtype < 0) {
         k_stereo_fix<<<(uint32_t)total_frames, 128, 0, s>>>(w.streams, p->n_streams, p->blocksize, (uint32_t)total_frames,
