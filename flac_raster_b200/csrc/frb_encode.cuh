@@ -1105,7 +1105,8 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
     // A thread visits its chunks in increasing order, so the subframe that holds a chunk only moves forward: the
     // segment search resumes where the previous chunk left it (it restarted from 0 for every chunk: 19 % of the kernel's
     // instructions, profiles/r01_ncu_emit_v7.txt).  seg_start[] entries and the chunk's register state: per frame.
-    uint32_t ch = 0;
+    uint32_t ch = 0, seg_lo = S.seg_start[0], seg_hi = S.seg_start[1];
+    const uint32_t *seg_sl = slots_f + (size_t)S.slot_of[0] * slot_words;
     // Warp-per-frame groups: a frame's partial head and tail chunks (its start and end are not 16-byte aligned) were produced
     // byte by byte by ONE lane (~50 instructions per byte, up to 30 bytes per frame) while the other 31 waited -- for 6 KB
     // frames (C5) about a third of the kernel.  Here the warp produces them together, one byte per lane, and assembles the
@@ -1137,11 +1138,18 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
         }
         if (b0 >= 0 && nbytes == 16) {
             const uint32_t P = 8u * (uint32_t)b0;
-            // common case: all 128 bits lie inside one subframe -> one segment lookup, five slot words, four funnel shifts
-            while (ch + 1 < channels && S.seg_start[ch + 1] <= P) ch++;
-            if (P >= hdr_bits && P + 128 <= S.seg_start[ch + 1]) {
-                const uint32_t o = P - S.seg_start[ch];
-                const uint32_t *sl = slots_f + (size_t)S.slot_of[ch] * slot_words + (o >> 5);
+            // common case: all 128 bits lie inside one subframe -> five slot words, four funnel shifts.  The subframe's bounds and
+            // slot address sit in registers and are looked up again only when a chunk leaves it (a subframe is a dozen rows long):
+            // the three shared-memory loads and the 64-bit multiply per chunk were at the head of the chunk's dependent chain.
+            if (P >= seg_hi) {
+                while (ch + 1 < channels && S.seg_start[ch + 1] <= P) ch++;
+                seg_lo = S.seg_start[ch];
+                seg_hi = S.seg_start[ch + 1];
+                seg_sl = slots_f + (size_t)S.slot_of[ch] * slot_words;
+            }
+            if (P >= hdr_bits && P + 128 <= seg_hi) {
+                const uint32_t o = P - seg_lo;
+                const uint32_t *sl = seg_sl + (o >> 5);
                 const uint32_t sh = o & 31;
 #if FRB_EMIT_VLOAD
                 // the five words as TWO aligned 16-byte loads (slots are 16-byte aligned and over-allocated by a vector): five
@@ -1156,11 +1164,11 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
                 // on its way.  Same subframe only, so the address is inside this frame's slot.  Same-box A/B (tools/enc_kernels_ab.py): C3
                 // 0.836 -> 0.703 ms, C5 1.111 -> 0.991 ms with one row ahead into L1; two rows ahead or L2 prefetches measure the same or worse.
 #if FRB_EMIT_PF_L1
-                if (P + 128u * ROW * FRB_EMIT_PF_L1 + 128 <= S.seg_start[ch + 1])
+                if (P + 128u * ROW * FRB_EMIT_PF_L1 + 128 <= seg_hi)
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(al + ROW * FRB_EMIT_PF_L1 + 1));
 #endif
 #if FRB_EMIT_PF_L2
-                if (P + 128u * ROW * FRB_EMIT_PF_L2 + 128 <= S.seg_start[ch + 1])
+                if (P + 128u * ROW * FRB_EMIT_PF_L2 + 128 <= seg_hi)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(al + ROW * FRB_EMIT_PF_L2 + 1));
 #endif
                 uint32_t v0, v1, v2, v3, v4;
@@ -1175,6 +1183,24 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
 #endif
                 w[0] = __funnelshift_l(v1, v0, sh); w[1] = __funnelshift_l(v2, v1, sh);
                 w[2] = __funnelshift_l(v3, v2, sh); w[3] = __funnelshift_l(v4, v3, sh);
+            } else if (P >= seg_lo && P < seg_hi && ch + 1 < channels && P + 128 <= S.seg_start[ch + 2]) {
+                // the chunk runs from subframe ch into subframe ch + 1 (seven such chunks per 8-channel frame, one lane of a row of 30):
+                // every word is A's bits, B's bits or t bits of A followed by B's first 32 - t -- both fetched for every word, so the 16
+                // loads are independent.  Through the general path (a loop of dependent segment searches and loads per word) this one
+                // lane held its row up for several memory latencies.
+                const uint32_t *slB = slots_f + (size_t)S.slot_of[ch + 1] * slot_words;
+                auto fetch32 = [](const uint32_t *sl, uint32_t o) {
+                    const uint32_t wi = o >> 5;
+                    return __funnelshift_l(__ldg(sl + wi + 1), __ldg(sl + wi), o & 31);
+                };
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t Pq = P + 32u * q;
+                    const bool inA = Pq < seg_hi;
+                    const uint32_t a = fetch32(seg_sl, inA ? Pq - seg_lo : 0u), b = fetch32(slB, inA ? 0u : Pq - seg_hi);
+                    const uint32_t t = seg_hi - Pq;                 // bits of A in this word (meaningful when inA)
+                    w[q] = !inA ? b : t >= 32 ? a : ((a & ~(0xFFFFFFFFu >> t)) | (b >> t));
+                }
             } else {
 #pragma unroll
                 for (int q = 0; q < 4; q++) w[q] = emit_gather32(P + 32u * q, S, channels, hdr_bits, end_bits, slots_f, slot_words);
