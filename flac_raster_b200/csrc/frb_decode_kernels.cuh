@@ -10,8 +10,9 @@
 //                       to the warp's order class 4/8/12, 64-bit MACs only when libFLAC's rule demands them); output is
 //                       either the planar int32 audio (128-bit stores) or, fused, the denormalised pixels written
 //                       straight into the tile's window of the raster
-//   k_crc16_frames      one warp per frame, 16-byte chunks per lane, slice-by-4 tables in shared
-//                       memory, Horner combination with x^(8*512) and a final x^(8*n) weight (side stream)
+//   k_crc16_frames      one warp per frame, rows of 30 16-byte chunks, one chunk per lane and row, folded without tables
+//                       (CrcFold, frb_crc16.cuh), lane weights and tail powers once per frame (side stream, launched
+//                       behind the decode kernel)
 
 // ---- cp.async / shared-memory helpers ------------------------------------------------------------------
 constexpr int kDecThreads = 128;

@@ -963,11 +963,11 @@ __global__ void k_set_out_offsets(EncStreamDev *streams, const unsigned long lon
 }
 
 // ---- frame assembly ------------------------------------------------------------------------------
-// One 128-thread CTA per frame.  The frame's bytes are produced in 16-byte chunks aligned to the
-// GLOBAL address (coalesced 128-bit stores; the first/last chunk of a frame is partial and written
-// bytewise), each chunk gathered from the header words / subframe slots with funnel shifts.  CRC-16:
-// per-thread Horner over its chunks (stride 128 chunks = 2048 bytes) with slice-by-4 tables, then
-// weights x^(128*(127-t)) and small tail powers, XOR-reduced over the CTA (see frb_crc16.cuh).
+// One warp per frame (a 128-thread CTA per frame on request).  The frame's bytes are produced in 16-byte chunks aligned to the
+// GLOBAL address (coalesced 128-bit stores; the first/last chunk of a frame is partial and produced by the whole warp, a byte
+// per lane), each chunk gathered from the header words / subframe slots with funnel shifts.  CRC-16: a lane folds its chunks
+// (rows of 30, or 120 for the CTA form) without tables (CrcFold, frb_crc16.cuh), then weights x^(128*(ROW-1-t)) and small tail
+// powers, XOR-reduced over the group.
 // v1 stored single bytes and ran a byte-serial CRC per thread: 13.8 ms on C3 (profiles/r01_launches_c3_v1.csv).
 constexpr int kEmitThreads = 128;
 #ifndef FRB_EMIT_VLOAD
@@ -1036,7 +1036,7 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
     auto group_sync = [&]() { if (TPF == kEmitThreads) __syncthreads(); else __syncwarp(); };
     crc_tables_to_smem(&SS.T);
     __syncthreads();                                      // tables staged
-    // persistent CTAs: the CRC tables (8 KB) are staged once, then every group walks frames with stride gridDim.x * kGroups
+    // persistent CTAs: the CRC tables (6 KB: slice-by-4 for ragged rows and tails, powers of x) are staged once, then every group walks frames with stride gridDim.x * kGroups
     for (uint32_t f = blockIdx.x * kGroups + grp; f < total_frames; f += gridDim.x * kGroups) {
     group_sync();                                         // previous frame's shared state consumed
     // the frame's stream from the descriptor table of the analysis (one load instead of a binary search of log2(n_streams)
@@ -1153,8 +1153,7 @@ k_emit_frames(const EncStreamDev *__restrict__ streams, uint32_t n_streams, uint
                 const uint32_t sh = o & 31;
 #if FRB_EMIT_VLOAD
                 // the five words as TWO aligned 16-byte loads (slots are 16-byte aligned and over-allocated by a vector): five
-                // 4-byte loads at a 16-byte lane stride cost 20 L1 wavefronts per warp against 8, and the kernel is bound by
-                // its L1 / shared-memory data path (CRC table lookups with 92 M bank conflicts).  The word offset inside the
+                // 4-byte loads at a 16-byte lane stride cost 20 L1 wavefronts per warp against 8.  The word offset inside the
                 // vector is the same for every lane of a warp inside one subframe, so the switch does not diverge.
                 const uint32_t k = (uint32_t)((reinterpret_cast<uintptr_t>(sl) >> 2) & 3u);
                 const uint4 *al = reinterpret_cast<const uint4 *>(sl - k);
