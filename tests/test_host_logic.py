@@ -524,3 +524,23 @@ def test_table_free_crc16_equals_bitwise_crc(oracle):
         frames += 1
         p0 = p1
     assert frames == 16
+
+
+def test_size_exchange_unpack_with_pixel_count_shards():
+    """The gathered size block of the sharded encode step (distributed.SizeExchange: `per` entries per rank, ranks hold
+    tile_shards blocks of different lengths) unpacks to the sizes in tile order for the C3 grid at N = 2, 4, 8."""
+    from flac_raster_b200.distributed import SizeExchange, exclusive_scan, tile_shards
+    from flac_raster_b200.engine import tile_grid
+    tiles = tile_grid(10980, 10980, 1024)
+    sizes = np.arange(1000, 1000 + len(tiles), dtype=np.int64) * 7
+    for world in (2, 4, 8):
+        shards = tile_shards(tiles, world)
+        x = SizeExchange(len(tiles), 0, world, "cpu", ranges=shards)
+        assert x.per == max(b - a for a, b in shards) and x.recv_count == x.per * world
+        recv = np.zeros((world, x.per), dtype=np.int64)
+        for r, (a, b) in enumerate(shards):
+            recv[r, :b - a] = sizes[a:b]
+        got = x.unpack(recv.reshape(-1))
+        assert np.array_equal(got, sizes)
+        off = exclusive_scan(got)
+        assert off[0] == 0 and off[-1] + got[-1] == sizes.sum()
